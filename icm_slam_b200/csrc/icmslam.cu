@@ -1,0 +1,766 @@
+// icmslam.cu -- C ABI (include/icmslam.h) and host orchestration of libicmslam.so.
+// One translation unit: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ...
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "assoc.cuh"
+#include "extract.cuh"
+#include "pose.cuh"
+#include "mapfilter.cuh"
+#include "fused.cuh"
+
+#define MAX_CELLS (1 << 22)
+
+struct icmslam_handle {
+    icmslam_config cfg;
+    DevCfg dcfg;
+    cudaStream_t stream = nullptr;
+    char err[512];
+    // dataset
+    int B = 0, T = 0, precondition = 0;
+    double *d_scans = nullptr, *d_odo = nullptr, *d_u = nullptr, *d_cos = nullptr, *d_sin = nullptr, *d_ang = nullptr;
+    // extraction
+    bool extracted = false;
+    int64_t n = 0;
+    int n_empty = 0, max_per_scan = 0;
+    bool first_empty = false, last_empty = false;
+    int *d_off = nullptr, *d_beam = nullptr, *d_scan_of = nullptr;
+    double *d_d = nullptr, *d_bx = nullptr, *d_by = nullptr;
+    // per observation workspace
+    int *d_c = nullptr, *d_keys_out = nullptr, *d_iota = nullptr, *d_sorted = nullptr;
+    double *d_seen_x = nullptr, *d_seen_y = nullptr;
+    // per scan workspace
+    int *d_nfar = nullptr, *d_flag = nullptr, *d_prefix = nullptr;
+    // per label workspace (capacity Lcap)
+    int Lcap = 0;
+    double *d_sum_x = nullptr, *d_sum_y = nullptr, *d_raw = nullptr /*2 x Lcap*/, *d_counts = nullptr;
+    int *d_cnt = nullptr, *d_seg = nullptr;
+    int *d_kflag = nullptr, *d_kpos = nullptr, *d_parent = nullptr, *d_nn = nullptr, *d_indflag = nullptr, *d_indpos = nullptr,
+        *d_ind = nullptr, *d_lab = nullptr, *d_used = nullptr, *d_rank = nullptr;
+    double *d_kx = nullptr, *d_ky = nullptr, *d_kc = nullptr, *d_ox = nullptr, *d_oy = nullptr, *d_oc = nullptr, *d_acc = nullptr;
+    double *d_map_in = nullptr /*2 x Lcap*/, *d_map_out = nullptr /*2 x Lcap*/, *d_x = nullptr /*3 x T*/;
+    double *d_tmp_a = nullptr, *d_tmp_b = nullptr; /* 2 x Lcap scratch for filter_map / calc_cambio inputs */
+    // grid
+    int *d_cell_start = nullptr, *d_cell_fill = nullptr, *d_cell_id = nullptr, *d_gidx = nullptr;
+    double *d_glx = nullptr, *d_gly = nullptr;
+    // state
+    DevState* d_st = nullptr;
+    DevState* h_st = nullptr;   // pinned mirror
+    int lact_host = 0;          // mirror of landmarks_actuales (valid when !lact_dirty)
+    bool lact_dirty = false;
+    void* d_cub = nullptr;
+    size_t cub_bytes = 0;
+    FusedWorkspace fw;
+};
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            snprintf(h->err, sizeof h->err, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return ICMSLAM_ERR_CUDA;                                                                     \
+        }                                                                                                \
+    } while (0)
+
+template <typename Tp>
+static cudaError_t dalloc(Tp** p, size_t count)
+{
+    return cudaMalloc((void**)p, (count ? count : 1) * sizeof(Tp));
+}
+#define DFREE(p) do { if (p) { cudaFree(p); p = nullptr; } } while (0)
+
+static inline int nblk(int64_t n, int b) { return (int)((n + b - 1) / b); }
+
+extern "C" int icmslam_abi_version(void) { return ICMSLAM_ABI_VERSION; }
+
+extern "C" const char* icmslam_strerror(int s)
+{
+    switch (s) {
+    case ICMSLAM_OK: return "ok";
+    case ICMSLAM_EMPTY_FIRST_SCAN: return "first scan has no observation; inputs returned unchanged (sensors.py:137-139)";
+    case ICMSLAM_ERR_INVALID: return "invalid argument or call order";
+    case ICMSLAM_ERR_LABEL_CAP: return "label capacity L exceeded (reference: IndexError, ICM_SLAM.py:191)";
+    case ICMSLAM_ERR_EMPTY_LAST: return "last scan has no observation (reference: IndexError, sensors.py:148)";
+    case ICMSLAM_ERR_EMPTY_MAP: return "no landmark reaches cota (reference: ValueError, ICM_SLAM.py:241-255)";
+    case ICMSLAM_ERR_ALLOC: return "allocation failed";
+    case ICMSLAM_ERR_CUDA: return "CUDA error";
+    case ICMSLAM_ERR_UNSUPPORTED: return "unsupported";
+    default: return "unknown status";
+    }
+}
+
+extern "C" const char* icmslam_last_error(const icmslam_handle* h) { return h ? h->err : "null handle"; }
+
+static void free_dataset(icmslam_handle* h)
+{
+    DFREE(h->d_scans); DFREE(h->d_odo); DFREE(h->d_u); DFREE(h->d_cos); DFREE(h->d_sin); DFREE(h->d_ang);
+    DFREE(h->d_off); DFREE(h->d_beam); DFREE(h->d_scan_of); DFREE(h->d_d); DFREE(h->d_bx); DFREE(h->d_by);
+    DFREE(h->d_c); DFREE(h->d_keys_out); DFREE(h->d_iota); DFREE(h->d_sorted); DFREE(h->d_seen_x); DFREE(h->d_seen_y);
+    DFREE(h->d_nfar); DFREE(h->d_flag); DFREE(h->d_prefix); DFREE(h->d_x);
+    fused_free(h->fw);
+    h->extracted = false;
+    h->n = 0;
+}
+
+extern "C" int icmslam_destroy(icmslam_handle* h)
+{
+    if (!h) return ICMSLAM_OK;
+    cudaSetDevice(h->cfg.device);
+    free_dataset(h);
+    DFREE(h->d_sum_x); DFREE(h->d_sum_y); DFREE(h->d_raw); DFREE(h->d_counts); DFREE(h->d_cnt); DFREE(h->d_seg);
+    DFREE(h->d_kflag); DFREE(h->d_kpos); DFREE(h->d_parent); DFREE(h->d_nn); DFREE(h->d_indflag); DFREE(h->d_indpos);
+    DFREE(h->d_ind); DFREE(h->d_lab); DFREE(h->d_used); DFREE(h->d_rank);
+    DFREE(h->d_kx); DFREE(h->d_ky); DFREE(h->d_kc); DFREE(h->d_ox); DFREE(h->d_oy); DFREE(h->d_oc); DFREE(h->d_acc);
+    DFREE(h->d_map_in); DFREE(h->d_map_out); DFREE(h->d_tmp_a); DFREE(h->d_tmp_b);
+    DFREE(h->d_cell_start); DFREE(h->d_cell_fill); DFREE(h->d_cell_id); DFREE(h->d_gidx); DFREE(h->d_glx); DFREE(h->d_gly);
+    DFREE(h->d_st); DFREE(h->d_cub);
+    if (h->h_st) cudaFreeHost(h->h_st);
+    delete h;
+    return ICMSLAM_OK;
+}
+
+static int ensure_cub(icmslam_handle* h, size_t bytes)
+{
+    if (bytes <= h->cub_bytes) return ICMSLAM_OK;
+    DFREE(h->d_cub);
+    h->cub_bytes = 0;
+    CK(cudaMalloc(&h->d_cub, bytes));
+    h->cub_bytes = bytes;
+    return ICMSLAM_OK;
+}
+
+static int exclusive_sum(icmslam_handle* h, const int* in, int* out, int n)
+{
+    size_t bytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, h->stream));
+    int rc = ensure_cub(h, bytes);
+    if (rc) return rc;
+    CK(cub::DeviceScan::ExclusiveSum(h->d_cub, bytes, in, out, n, h->stream));
+    return ICMSLAM_OK;
+}
+
+extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
+{
+    if (!cfg || !out || cfg->L <= 0) return ICMSLAM_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device || cfg->device < 0) return ICMSLAM_ERR_CUDA;
+    icmslam_handle* h = new (std::nothrow) icmslam_handle();
+    if (!h) return ICMSLAM_ERR_ALLOC;
+    h->err[0] = 0;
+    h->cfg = *cfg;
+    h->dcfg.dt = cfg->deltat; h->dcfg.q1 = cfg->q1; h->dcfg.q2 = cfg->q2;
+    h->dcfg.r1 = cfg->r1; h->dcfg.r2 = cfg->r2; h->dcfg.r3 = cfg->r3;
+    h->dcfg.kod = cfg->cte_odom; h->dcfg.cota = cfg->cota; h->dcfg.dist_thr = cfg->dist_thr;
+    h->dcfg.rmax = cfg->rango_laser_max; h->dcfg.radio = cfg->radio; h->dcfg.L = cfg->L;
+    h->Lcap = cfg->L;
+    const size_t L = (size_t)h->Lcap;
+    cudaError_t e = cudaSetDevice(cfg->device);
+    if (e == cudaSuccess) e = dalloc(&h->d_sum_x, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_sum_y, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_raw, 2 * L);
+    if (e == cudaSuccess) e = dalloc(&h->d_counts, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_cnt, L + 1);
+    if (e == cudaSuccess) e = dalloc(&h->d_seg, L + 1);
+    if (e == cudaSuccess) e = dalloc(&h->d_kflag, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_kpos, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_parent, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_nn, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_indflag, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_indpos, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_ind, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_lab, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_used, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_rank, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_kx, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_ky, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_kc, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_ox, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_oy, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_oc, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_acc, 8);
+    if (e == cudaSuccess) e = dalloc(&h->d_map_in, 2 * L);
+    if (e == cudaSuccess) e = dalloc(&h->d_map_out, 2 * L);
+    if (e == cudaSuccess) e = dalloc(&h->d_tmp_a, 2 * L);
+    if (e == cudaSuccess) e = dalloc(&h->d_tmp_b, 2 * L);
+    if (e == cudaSuccess) e = dalloc(&h->d_cell_start, (size_t)MAX_CELLS + 2);
+    if (e == cudaSuccess) e = dalloc(&h->d_cell_fill, (size_t)MAX_CELLS + 2);
+    if (e == cudaSuccess) e = dalloc(&h->d_cell_id, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_gidx, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_glx, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_gly, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_st, 1);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_st, sizeof(DevState));
+    if (e == cudaSuccess) e = cudaMemset(h->d_st, 0, sizeof(DevState));
+    if (e == cudaSuccess) e = cudaMemset(h->d_counts, 0, L * sizeof(double));
+    if (e != cudaSuccess) {
+        icmslam_destroy(h);
+        return e == cudaErrorMemoryAllocation ? ICMSLAM_ERR_ALLOC : ICMSLAM_ERR_CUDA;
+    }
+    *out = h;
+    return ICMSLAM_OK;
+}
+
+extern "C" int icmslam_set_stream(icmslam_handle* h, void* s)
+{
+    if (!h) return ICMSLAM_ERR_INVALID;
+    h->stream = (cudaStream_t)s;
+    return ICMSLAM_OK;
+}
+
+extern "C" int icmslam_synchronize(icmslam_handle* h)
+{
+    if (!h) return ICMSLAM_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    return ICMSLAM_OK;
+}
+
+extern "C" int icmslam_load(icmslam_handle* h, const double* scans, int32_t B, int32_t T, int64_t ld_scans,
+                            const double* odo, int64_t ld_odo, const double* u, int64_t ld_u, const double* cos_tab,
+                            const double* sin_tab, int32_t precondition, int32_t memspace)
+{
+    if (!h || !scans || !odo || !u || B <= 0 || B > 1024 || T <= 0 || ld_scans < T || ld_odo < T || ld_u < T)
+        return ICMSLAM_ERR_INVALID;
+    (void)memspace;   // cudaMemcpyDefault resolves host / device pointers (UVA)
+    CK(cudaSetDevice(h->cfg.device));
+    free_dataset(h);
+    h->B = B; h->T = T; h->precondition = precondition;
+    CK(dalloc(&h->d_scans, (size_t)B * T));
+    CK(dalloc(&h->d_odo, (size_t)3 * T));
+    CK(dalloc(&h->d_u, (size_t)2 * T));
+    CK(dalloc(&h->d_cos, (size_t)B));
+    CK(dalloc(&h->d_sin, (size_t)B));
+    CK(dalloc(&h->d_ang, (size_t)B));
+    CK(dalloc(&h->d_x, (size_t)3 * T));
+    CK(dalloc(&h->d_nfar, (size_t)T + 1));
+    CK(dalloc(&h->d_flag, (size_t)T + 1));
+    CK(dalloc(&h->d_prefix, (size_t)T + 1));
+    const size_t w = (size_t)T * sizeof(double);
+    CK(cudaMemcpy2DAsync(h->d_scans, w, scans, (size_t)ld_scans * sizeof(double), w, B, cudaMemcpyDefault, h->stream));
+    CK(cudaMemcpy2DAsync(h->d_odo, w, odo, (size_t)ld_odo * sizeof(double), w, 3, cudaMemcpyDefault, h->stream));
+    CK(cudaMemcpy2DAsync(h->d_u, w, u, (size_t)ld_u * sizeof(double), w, 2, cudaMemcpyDefault, h->stream));
+    std::vector<double> ang(B), cb(B), sb(B);
+    for (int i = 0; i < B; ++i) {
+        ang[i] = ((double)i * ICM_PI) / 180.0;                 // nind*np.pi/180.0 (ICM_SLAM.py:44,51)
+        cb[i] = cos_tab ? cos_tab[i] : cos(ang[i]);
+        sb[i] = sin_tab ? sin_tab[i] : sin(ang[i]);
+    }
+    CK(cudaMemcpyAsync(h->d_ang, ang.data(), B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_cos, cb.data(), B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_sin, sb.data(), B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // the host staging vectors and caller buffers may go away
+    return ICMSLAM_OK;
+}
+
+extern "C" int icmslam_extract(icmslam_handle* h)
+{
+    if (!h || !h->d_scans) return ICMSLAM_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    const int B = h->B, T = h->T;
+    const int nwords = (B + 31) / 32;
+    uint32_t* d_masks = nullptr;
+    int* d_counts = nullptr;
+    CK(dalloc(&d_masks, (size_t)T * nwords));
+    CK(dalloc(&d_counts, (size_t)T + 1));
+    DFREE(h->d_off);
+    CK(dalloc(&h->d_off, (size_t)T + 1));
+    CK(cudaMemsetAsync(d_counts, 0, ((size_t)T + 1) * sizeof(int), h->stream));
+    const size_t smem = extract_smem_bytes(B);
+    CK(cudaFuncSetAttribute(k_extract<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_extract<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int blocks = nblk(T, EX_TILE);
+    k_extract<1><<<blocks, EX_THREADS, smem, h->stream>>>(h->d_scans, B, T, T, h->d_cos, h->d_sin, h->dcfg, h->precondition,
+                                                          nwords, d_masks, d_counts, nullptr, nullptr, nullptr, nullptr,
+                                                          nullptr, nullptr);
+    CK(cudaGetLastError());
+    int rc = exclusive_sum(h, d_counts, h->d_off, T + 1);
+    if (rc) return rc;
+    std::vector<int> off((size_t)T + 1);
+    CK(cudaMemcpyAsync(off.data(), h->d_off, ((size_t)T + 1) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->n = off[T];
+    h->n_empty = 0; h->max_per_scan = 0;
+    for (int t = 0; t < T; ++t) {
+        int k = off[t + 1] - off[t];
+        if (k == 0) ++h->n_empty;
+        if (k > h->max_per_scan) h->max_per_scan = k;
+    }
+    h->first_empty = off[1] == off[0];
+    h->last_empty = off[T] == off[T - 1];
+    const size_t n = (size_t)h->n;
+    DFREE(h->d_beam); DFREE(h->d_scan_of); DFREE(h->d_d); DFREE(h->d_bx); DFREE(h->d_by);
+    DFREE(h->d_c); DFREE(h->d_keys_out); DFREE(h->d_iota); DFREE(h->d_sorted); DFREE(h->d_seen_x); DFREE(h->d_seen_y);
+    CK(dalloc(&h->d_beam, n)); CK(dalloc(&h->d_scan_of, n)); CK(dalloc(&h->d_d, n)); CK(dalloc(&h->d_bx, n)); CK(dalloc(&h->d_by, n));
+    CK(dalloc(&h->d_c, n));
+    k_extract<2><<<blocks, EX_THREADS, smem, h->stream>>>(h->d_scans, B, T, T, h->d_cos, h->d_sin, h->dcfg, h->precondition,
+                                                          nwords, d_masks, nullptr, h->d_off, h->d_beam, h->d_d, h->d_bx,
+                                                          h->d_by, h->d_scan_of);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_masks);
+    cudaFree(d_counts);
+    h->extracted = true;
+    fused_free(h->fw);
+    return ICMSLAM_OK;
+}
+
+extern "C" int icmslam_extraction_size(const icmslam_handle* h, int64_t* n_obs, int32_t* n_empty, int32_t* max_per_scan)
+{
+    if (!h || !h->extracted) return ICMSLAM_ERR_INVALID;
+    if (n_obs) *n_obs = h->n;
+    if (n_empty) *n_empty = h->n_empty;
+    if (max_per_scan) *max_per_scan = h->max_per_scan;
+    return ICMSLAM_OK;
+}
+
+extern "C" int icmslam_get_extraction(icmslam_handle* h, int32_t* off, int32_t* beam, double* d, double* bx, double* by,
+                                      int32_t memspace)
+{
+    if (!h || !h->extracted) return ICMSLAM_ERR_INVALID;
+    (void)memspace;
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t n = (size_t)h->n;
+    if (off) CK(cudaMemcpyAsync(off, h->d_off, ((size_t)h->T + 1) * sizeof(int), cudaMemcpyDefault, h->stream));
+    if (beam) CK(cudaMemcpyAsync(beam, h->d_beam, n * sizeof(int), cudaMemcpyDefault, h->stream));
+    if (d) CK(cudaMemcpyAsync(d, h->d_d, n * sizeof(double), cudaMemcpyDefault, h->stream));
+    if (bx) CK(cudaMemcpyAsync(bx, h->d_bx, n * sizeof(double), cudaMemcpyDefault, h->stream));
+    if (by) CK(cudaMemcpyAsync(by, h->d_by, n * sizeof(double), cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return ICMSLAM_OK;
+}
+
+// ---- Mapa state ------------------------------------------------------------------------------
+__global__ void k_set_lact(DevState* st, int v) { st->lact = v; }
+
+static int sync_state(icmslam_handle* h)
+{
+    CK(cudaMemcpyAsync(h->h_st, h->d_st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->lact_host = h->h_st->lact;
+    h->lact_dirty = false;
+    return ICMSLAM_OK;
+}
+
+extern "C" int icmslam_set_landmarks_actuales(icmslam_handle* h, int32_t lact)
+{
+    if (!h || lact < 0 || lact > h->Lcap) return ICMSLAM_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    k_set_lact<<<1, 1, 0, h->stream>>>(h->d_st, lact);
+    CK(cudaGetLastError());
+    h->lact_host = lact;
+    h->lact_dirty = false;
+    return ICMSLAM_OK;
+}
+
+extern "C" int icmslam_get_landmarks_actuales(const icmslam_handle* hc, int32_t* lact)
+{
+    icmslam_handle* h = const_cast<icmslam_handle*>(hc);
+    if (!h || !lact) return ICMSLAM_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->lact_dirty) { int rc = sync_state(h); if (rc) return rc; }
+    *lact = h->lact_host;
+    return ICMSLAM_OK;
+}
+
+extern "C" int icmslam_get_counts(icmslam_handle* h, double* out, int32_t n, int32_t memspace)
+{
+    if (!h || !out || n < 0 || n > h->Lcap) return ICMSLAM_ERR_INVALID;
+    (void)memspace;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpyAsync(out, h->d_counts, (size_t)n * sizeof(double), cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return ICMSLAM_OK;
+}
+
+// ---- grid over a point set whose size lives on the device --------------------------------------
+static int build_grid(icmslam_handle* h, const double* px, const double* py, const int* n_ptr, int n_cap, bool filter_grid)
+{
+    DevState* st = h->d_st;
+    double *gx0 = filter_grid ? &st->fx0 : &st->gx0, *gy0 = filter_grid ? &st->fy0 : &st->gy0;
+    double* ginv = filter_grid ? &st->finv_h : &st->ginv_h;
+    int *gnx = filter_grid ? &st->fnx : &st->gnx, *gny = filter_grid ? &st->fny : &st->gny;
+    CK(cudaMemsetAsync(h->d_cell_fill, 0, ((size_t)MAX_CELLS + 2) * sizeof(int), h->stream));
+    k_grid_setup<<<1, 1024, 0, h->stream>>>(px, py, n_ptr, h->dcfg.dist_thr, MAX_CELLS, gx0, gy0, ginv, gnx, gny,
+                                            filter_grid ? &st->f_extent : nullptr);
+    CK(cudaGetLastError());
+    // counts go to cell_fill, scanned into cell_start, then cell_fill is reused as the fill cursor
+    k_cell_count<<<nblk(n_cap, 256), 256, 0, h->stream>>>(px, py, n_ptr, gx0, gy0, ginv, gnx, gny, h->d_cell_fill, h->d_cell_id);
+    CK(cudaGetLastError());
+    int rc = exclusive_sum(h, h->d_cell_fill, h->d_cell_start, MAX_CELLS + 1);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(h->d_cell_fill, 0, ((size_t)MAX_CELLS + 2) * sizeof(int), h->stream));
+    k_cell_fill<<<nblk(n_cap, 256), 256, 0, h->stream>>>(px, py, n_ptr, h->d_cell_id, h->d_cell_start, h->d_cell_fill, h->d_glx,
+                                                         h->d_gly, h->d_gidx);
+    CK(cudaGetLastError());
+    return ICMSLAM_OK;
+}
+
+// ---- Mapa.filtrar on device-resident raw map (d_raw, counts from cnt_i or cnt_d) -----------------
+// Expects d_kflag already set.  Writes map_out (device pointer) and the Mapa state.
+static int run_filter(icmslam_handle* h, const double* raw_x, const double* raw_y, const int* cnt_i, const double* cnt_d,
+                      double* map_out, int cap_out, int64_t ld_out, double* counts_out, int update_state)
+{
+    const int L = h->Lcap;
+    DevState* st = h->d_st;
+    int rc = exclusive_sum(h, h->d_kflag, h->d_kpos, L);
+    if (rc) return rc;
+    k_compact_kept<<<nblk(L, 256), 256, 0, h->stream>>>(st, h->d_kflag, h->d_kpos, raw_x, raw_y, cnt_i, cnt_d, h->d_kx, h->d_ky,
+                                                        h->d_kc, h->d_parent, L);
+    CK(cudaGetLastError());
+    rc = build_grid(h, h->d_kx, h->d_ky, &st->kept, L, true);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(h->d_acc, 0, 8 * sizeof(double), h->stream));
+    k_filter_diameter<<<nblk(FILTER_SMALL_K, 128), 128, 0, h->stream>>>(st, h->d_kx, h->d_ky, h->dcfg.dist_thr, h->d_acc);
+    CK(cudaGetLastError());
+    k_filter_nn<<<nblk(L, 128), 128, 0, h->stream>>>(st, h->d_kx, h->d_ky, h->dcfg.dist_thr, h->d_acc, h->d_cell_start, h->d_glx,
+                                                     h->d_gly, h->d_gidx, h->d_nn, h->d_indflag, L);
+    CK(cudaGetLastError());
+    rc = exclusive_sum(h, h->d_indflag, h->d_indpos, L);
+    if (rc) return rc;
+    k_ind_compact<<<nblk(L, 256), 256, 0, h->stream>>>(st, h->d_indflag, h->d_indpos, h->d_ind, L);
+    CK(cudaGetLastError());
+    k_relabel<<<1, 32, 0, h->stream>>>(st, h->d_ind, h->d_nn, h->d_parent);
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(h->d_used, 0, (size_t)L * sizeof(int), h->stream));
+    CK(cudaMemsetAsync(h->d_ox, 0, (size_t)L * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->d_oy, 0, (size_t)L * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->d_oc, 0, (size_t)L * sizeof(double), h->stream));
+    k_roots<<<nblk(L, 256), 256, 0, h->stream>>>(st, h->d_parent, h->d_lab, h->d_used);
+    CK(cudaGetLastError());
+    rc = exclusive_sum(h, h->d_used, h->d_rank, L);
+    if (rc) return rc;
+    k_merge_accumulate<<<nblk(L, 256), 256, 0, h->stream>>>(st, h->d_lab, h->d_rank, h->d_kx, h->d_ky, h->d_kc, h->d_ox, h->d_oy,
+                                                            h->d_oc);
+    CK(cudaGetLastError());
+    k_filter_finalize<<<nblk(L, 256), 256, 0, h->stream>>>(st, h->d_used, h->d_rank, h->d_ox, h->d_oy, h->d_oc, map_out, cap_out,
+                                                           ld_out, update_state ? h->d_counts : nullptr, counts_out, L,
+                                                           update_state);
+    CK(cudaGetLastError());
+    return ICMSLAM_OK;
+}
+
+__global__ void k_sweep_begin(DevState* st, int L_in)
+{
+    st->lact0 = st->lact;
+    st->lsearch = min(st->lact, L_in);
+    st->raw_l = st->lact;
+    st->status = ST_OK;
+    st->n_far_scans = 0;
+    st->newton_iters = 0ull;
+    st->solved = 0ull;
+}
+
+static int status_from_state(const DevState* s)
+{
+    if (s->status & ST_LABEL_CAP) return ICMSLAM_ERR_LABEL_CAP;
+    if (s->status & 4) return ICMSLAM_ERR_EMPTY_MAP;
+    return ICMSLAM_OK;
+}
+
+extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_in, int64_t ld_map_in, double* x, int64_t ld_x,
+                             const double* x0, double* map_out, int32_t cap_out, int64_t ld_map_out, int32_t* L_out,
+                             const icmslam_sweep_opts* opts, int32_t memspace)
+{
+    if (!h || !h->extracted || !x || !x0 || L_in < 0 || L_in > h->Lcap || ld_x < h->T || (L_in > 0 && (!map_in || ld_map_in < L_in)))
+        return ICMSLAM_ERR_INVALID;
+    if (map_out && (cap_out <= 0 || ld_map_out < cap_out)) return ICMSLAM_ERR_INVALID;
+    icmslam_sweep_opts o;
+    o.schedule = ICMSLAM_SCHED_REDBLACK; o.solver = ICMSLAM_SOLVER_NEWTON; o.map_view = ICMSLAM_VIEW_PREV;
+    o.newton_maxit = 0; o.newton_tol = 0.0; o.fused = 1; o.reserved = 0;
+    if (opts) o = *opts;
+    if (o.newton_maxit <= 0) o.newton_maxit = 20;
+    if (!(o.newton_tol > 0.0)) o.newton_tol = 1e-10;
+    CK(cudaSetDevice(h->cfg.device));
+    const int T = h->T, L = h->Lcap;
+    const int64_t n = h->n;
+    cudaStream_t s = h->stream;
+    DevState* st = h->d_st;
+    // Mapa.clear_obs (sensors.py:133) happens before the early return of :137-139
+    CK(cudaMemsetAsync(h->d_counts, 0, (size_t)L * sizeof(double), s));
+    if (h->first_empty) {   // sensors.py:137-139: inputs returned unchanged
+        if (map_out && L_in > 0) {
+            int w = L_in < cap_out ? L_in : cap_out;
+            CK(cudaMemcpy2DAsync(map_out, (size_t)ld_map_out * 8, map_in, (size_t)ld_map_in * 8, (size_t)w * 8, 2, cudaMemcpyDefault, s));
+            CK(cudaStreamSynchronize(s));
+        }
+        if (L_out) *L_out = L_in;
+        return ICMSLAM_EMPTY_FIRST_SCAN;
+    }
+    if (h->last_empty && T > 1) return ICMSLAM_ERR_EMPTY_LAST;
+    // inputs
+    double* dx = x;
+    int64_t ldx = ld_x;
+    if (memspace == ICMSLAM_HOST) {
+        CK(cudaMemcpy2DAsync(h->d_x, (size_t)T * 8, x, (size_t)ld_x * 8, (size_t)T * 8, 3, cudaMemcpyHostToDevice, s));
+        dx = h->d_x;
+        ldx = T;
+    }
+    if (L_in > 0)
+        CK(cudaMemcpy2DAsync(h->d_map_in, (size_t)L * 8, map_in, (size_t)ld_map_in * 8, (size_t)L_in * 8, 2, cudaMemcpyDefault, s));
+    const double* min_x = h->d_map_in;
+    const double* min_y = h->d_map_in + L;
+    double* raw_x = h->d_raw;
+    double* raw_y = h->d_raw + L;
+    double* dmap_out = (memspace == ICMSLAM_HOST || !map_out) ? h->d_map_out : map_out;
+    const int out_cap = (memspace == ICMSLAM_HOST || !map_out) ? L : cap_out;
+    const int64_t out_ld = (memspace == ICMSLAM_HOST || !map_out) ? L : ld_map_out;
+
+    k_sweep_begin<<<1, 1, 0, s>>>(st, L_in);
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(h->d_sum_x, 0, (size_t)L * 8, s));
+    CK(cudaMemsetAsync(h->d_sum_y, 0, (size_t)L * 8, s));
+    CK(cudaMemsetAsync(h->d_cnt, 0, ((size_t)L + 1) * sizeof(int), s));
+    int rc = build_grid(h, min_x, min_y, &st->lsearch, L_in > 0 ? L_in : 1, false);
+    if (rc) return rc;
+
+    const bool collect = (o.reserved & 1) != 0;
+    unsigned long long* iters = collect ? &st->newton_iters : nullptr;
+    const bool use_fused = h->fw.available && o.fused && o.schedule == ICMSLAM_SCHED_REDBLACK && o.solver == ICMSLAM_SOLVER_NEWTON &&
+                           o.map_view == ICMSLAM_VIEW_PREV;
+    PoseArrays A;
+    A.x = dx; A.ldx = ldx; A.odo = h->d_odo; A.ldo = T; A.u = h->d_u; A.ldu = T;
+    A.x0[0] = x0[0]; A.x0[1] = x0[1]; A.x0[2] = x0[2];
+    A.off = h->d_off; A.T = T;
+    if (use_fused) {
+        rc = fused_sweep(h->fw, s, h->dcfg, A, h->d_bx, h->d_by, n, st, h->d_cell_start, h->d_glx, h->d_gly, h->d_gidx, h->d_c,
+                         h->d_nfar, h->d_sum_x, h->d_sum_y, h->d_cnt, o.newton_tol, o.newton_maxit, iters, h->err, sizeof h->err);
+        if (rc) return rc;
+    } else {
+        k_assoc<<<148 * 8, 256, 0, s>>>(T, h->d_off, h->d_bx, h->d_by, dx, ldx, x0[0], x0[1], x0[2], st, h->d_cell_start, h->d_glx,
+                                        h->d_gly, h->d_gidx, h->dcfg.dist_thr, h->d_c, h->d_nfar, h->d_sum_x, h->d_sum_y, h->d_cnt);
+        CK(cudaGetLastError());
+    }
+    // new labels: one per scan that has a far observation, numbered in time order
+    k_flag_positive<<<nblk(T, 256), 256, 0, s>>>(h->d_nfar, T, h->d_flag);
+    CK(cudaGetLastError());
+    rc = exclusive_sum(h, h->d_flag, h->d_prefix, T);
+    if (rc) return rc;
+    // (the fused kernel has already updated the poses; labels / statistics use its saved input poses)
+    const double* xin = use_fused ? h->fw.d_xin : dx;
+    const int64_t ldxin = use_fused ? T : ldx;
+    k_new_labels<<<148 * 4, 256, 0, s>>>(T, h->d_off, h->d_bx, h->d_by, xin, ldxin, x0[0], x0[1], x0[2], st, h->d_nfar, h->d_prefix,
+                                         L, h->d_c, h->d_sum_x, h->d_sum_y, h->d_cnt);
+    CK(cudaGetLastError());
+    const bool running = o.map_view == ICMSLAM_VIEW_RUNNING;
+    if (running) {
+        if (!h->d_sorted) {
+            CK(dalloc(&h->d_keys_out, (size_t)n)); CK(dalloc(&h->d_iota, (size_t)n)); CK(dalloc(&h->d_sorted, (size_t)n));
+            CK(dalloc(&h->d_seen_x, (size_t)n)); CK(dalloc(&h->d_seen_y, (size_t)n));
+            k_iota<<<nblk(n, 256), 256, 0, s>>>((int)n, h->d_iota);
+            CK(cudaGetLastError());
+        }
+        rc = exclusive_sum(h, h->d_cnt, h->d_seg, L);
+        if (rc) return rc;
+        int end_bit = 1;
+        while ((1ll << end_bit) < (long long)L + 1 && end_bit < 32) ++end_bit;
+        size_t bytes = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned*)h->d_c, (unsigned*)h->d_keys_out, h->d_iota, h->d_sorted,
+                                           (int)n, 0, end_bit, s));
+        rc = ensure_cub(h, bytes);
+        if (rc) return rc;
+        CK(cub::DeviceRadixSort::SortPairs(h->d_cub, bytes, (const unsigned*)h->d_c, (unsigned*)h->d_keys_out, h->d_iota, h->d_sorted,
+                                           (int)n, 0, end_bit, s));
+        k_running_mean<<<nblk(L, 128), 128, 0, s>>>(st, h->d_seg, h->d_cnt, h->d_sorted, h->d_scan_of, h->d_bx, h->d_by, dx, ldx,
+                                                    x0[0], x0[1], x0[2], h->d_seen_x, h->d_seen_y, raw_x, raw_y, L);
+        CK(cudaGetLastError());
+    }
+    k_means_flags<<<nblk(L, 256), 256, 0, s>>>(st, h->d_sum_x, h->d_sum_y, h->d_cnt, h->dcfg.cota, running ? 1 : 0, raw_x, raw_y,
+                                               h->d_kflag, L);
+    CK(cudaGetLastError());
+    if (!use_fused) {
+        ObsArrays O;
+        O.bx = h->d_bx; O.by = h->d_by; O.d = h->d_d; O.beam = h->d_beam; O.ang = h->d_ang;
+        SeenSrc S;
+        S.view = o.map_view; S.c = h->d_c; S.seen_x = h->d_seen_x; S.seen_y = h->d_seen_y;
+        S.raw_x = raw_x; S.raw_y = raw_y; S.min_x = min_x; S.min_y = min_y;
+        S.lsearch_ptr = &st->lsearch;
+        if (o.schedule == ICMSLAM_SCHED_REDBLACK) {
+            int half = (T + 1) / 2;
+            k_pose_colour<<<nblk(half, 128), 128, 0, s>>>(1, h->dcfg, A, O, S, o.solver, o.newton_tol, o.newton_maxit, iters);
+            CK(cudaGetLastError());
+            k_pose_colour<<<nblk(half, 128), 128, 0, s>>>(0, h->dcfg, A, O, S, o.solver, o.newton_tol, o.newton_maxit, iters);
+            CK(cudaGetLastError());
+        } else {
+            k_pose_sequential<<<1, 32, 0, s>>>(h->dcfg, A, O, S, o.solver, o.newton_tol, o.newton_maxit, iters);
+            CK(cudaGetLastError());
+        }
+    }
+    // Mapa.filtrar (sensors.py:165-166)
+    rc = run_filter(h, raw_x, raw_y, h->d_cnt, nullptr, dmap_out, out_cap, out_ld, nullptr, 1);
+    if (rc) return rc;
+    h->lact_dirty = true;
+    if (memspace == ICMSLAM_HOST) {
+        CK(cudaMemcpy2DAsync(x, (size_t)ld_x * 8, dx, (size_t)T * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToHost, s));
+        rc = sync_state(h);
+        if (rc) return rc;
+        int status = status_from_state(h->h_st);
+        if (status) return status;
+        const int newL = h->h_st->new_l;
+        if (map_out) {
+            int w = newL < cap_out ? newL : cap_out;
+            if (w > 0) {
+                CK(cudaMemcpy2DAsync(map_out, (size_t)ld_map_out * 8, h->d_map_out, (size_t)L * 8, (size_t)w * 8, 2, cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+            }
+        }
+        if (L_out) *L_out = newL;
+        return ICMSLAM_OK;
+    }
+    if (L_out) {   // device buffers, but the caller wants the new width now: one 4-byte round trip
+        rc = sync_state(h);
+        if (rc) return rc;
+        int status = status_from_state(h->h_st);
+        if (status) return status;
+        *L_out = h->h_st->new_l;
+    }
+    return ICMSLAM_OK;
+}
+
+extern "C" int icmslam_get_associations(icmslam_handle* h, int32_t* c, int32_t memspace)
+{
+    if (!h || !h->extracted || !c) return ICMSLAM_ERR_INVALID;
+    (void)memspace;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpyAsync(c, h->d_c, (size_t)h->n * sizeof(int), cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return ICMSLAM_OK;
+}
+
+__global__ void k_counts_to_double(const int* __restrict__ cnt, int n, double* __restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)cnt[i];
+}
+
+extern "C" int icmslam_get_raw_map(icmslam_handle* h, double* raw_map, int32_t cap, int64_t ld, double* raw_counts, int32_t* raw_L,
+                                   int32_t memspace)
+{
+    if (!h) return ICMSLAM_ERR_INVALID;
+    (void)memspace;
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = sync_state(h);
+    if (rc) return rc;
+    const int rl = h->h_st->raw_l;
+    if (raw_L) *raw_L = rl;
+    const int w = rl < cap ? rl : cap;
+    if (raw_map && w > 0)
+        CK(cudaMemcpy2DAsync(raw_map, (size_t)ld * 8, h->d_raw, (size_t)h->Lcap * 8, (size_t)w * 8, 2, cudaMemcpyDefault, h->stream));
+    if (raw_counts && w > 0) {
+        k_counts_to_double<<<nblk(w, 256), 256, 0, h->stream>>>(h->d_cnt, w, h->d_tmp_a);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(raw_counts, h->d_tmp_a, (size_t)w * 8, cudaMemcpyDefault, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return ICMSLAM_OK;
+}
+
+extern "C" int icmslam_get_sweep_stats(icmslam_handle* h, int64_t* stats, int32_t n)
+{
+    if (!h || !stats || n < 0) return ICMSLAM_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = sync_state(h);
+    if (rc) return rc;
+    const DevState* s = h->h_st;
+    int64_t v[8] = {(int64_t)s->newton_iters, s->n_far_scans, s->raw_l, s->kept, s->new_l, s->n_ind, s->lsearch, s->status};
+    for (int i = 0; i < n && i < 8; ++i) stats[i] = v[i];
+    return ICMSLAM_OK;
+}
+
+__global__ void k_set_raw_l(DevState* st, int v) { st->raw_l = v; st->status = 0; }
+
+extern "C" int icmslam_filter_map(icmslam_handle* h, const double* map_in, int64_t ld_in, const double* counts_in, int32_t L_in,
+                                  double* map_out, int32_t cap_out, int64_t ld_out, double* counts_out, int32_t* L_out,
+                                  int32_t memspace)
+{
+    if (!h || !map_in || !counts_in || L_in <= 0 || L_in > h->Lcap || ld_in < L_in || !L_out) return ICMSLAM_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    const int L = h->Lcap;
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpy2DAsync(h->d_tmp_a, (size_t)L * 8, map_in, (size_t)ld_in * 8, (size_t)L_in * 8, 2, cudaMemcpyDefault, s));
+    CK(cudaMemcpyAsync(h->d_tmp_b, counts_in, (size_t)L_in * 8, cudaMemcpyDefault, s));
+    k_set_raw_l<<<1, 1, 0, s>>>(h->d_st, L_in);
+    CK(cudaGetLastError());
+    k_flags_from_counts<<<nblk(L, 256), 256, 0, s>>>(h->d_tmp_b, L_in, h->dcfg.cota, h->d_kflag, L);
+    CK(cudaGetLastError());
+    int rc = run_filter(h, h->d_tmp_a, h->d_tmp_a + L, nullptr, h->d_tmp_b, h->d_map_out, L, L, h->d_tmp_b + L, 1);
+    if (rc) return rc;
+    rc = sync_state(h);
+    if (rc) return rc;
+    int status = status_from_state(h->h_st);
+    if (status) return status;
+    const int newL = h->h_st->new_l;
+    *L_out = newL;
+    (void)memspace;
+    int w = newL < cap_out ? newL : cap_out;
+    if (map_out && w > 0)
+        CK(cudaMemcpy2DAsync(map_out, (size_t)ld_out * 8, h->d_map_out, (size_t)L * 8, (size_t)w * 8, 2, cudaMemcpyDefault, s));
+    if (counts_out && w > 0) CK(cudaMemcpyAsync(counts_out, h->d_counts, (size_t)w * 8, cudaMemcpyDefault, s));
+    CK(cudaStreamSynchronize(s));
+    return ICMSLAM_OK;
+}
+
+__global__ void k_set_lsearch(DevState* st, int v) { st->lsearch = v; }
+
+extern "C" int icmslam_calc_cambio(icmslam_handle* h, const double* map_new, int32_t L_new, int64_t ld_new, const double* map_old,
+                                   int32_t L_old, int64_t ld_old, double* out3, int32_t memspace)
+{
+    if (!h || !map_new || !map_old || !out3 || L_new <= 0 || L_old <= 0 || L_new > h->Lcap || L_old > h->Lcap)
+        return ICMSLAM_ERR_INVALID;
+    (void)memspace;
+    CK(cudaSetDevice(h->cfg.device));
+    const int L = h->Lcap;
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpy2DAsync(h->d_tmp_a, (size_t)L * 8, map_new, (size_t)ld_new * 8, (size_t)L_new * 8, 2, cudaMemcpyDefault, s));
+    CK(cudaMemcpy2DAsync(h->d_tmp_b, (size_t)L * 8, map_old, (size_t)ld_old * 8, (size_t)L_old * 8, 2, cudaMemcpyDefault, s));
+    k_set_lsearch<<<1, 1, 0, s>>>(h->d_st, L_old);
+    CK(cudaGetLastError());
+    int rc = build_grid(h, h->d_tmp_b, h->d_tmp_b + L, &h->d_st->lsearch, L_old, false);
+    if (rc) return rc;
+    double init[3] = {INFINITY, 0.0, 0.0};
+    CK(cudaMemcpyAsync(h->d_acc, init, sizeof init, cudaMemcpyHostToDevice, s));
+    k_cambio<<<nblk(L_new, 128), 128, 0, s>>>(h->d_st, h->d_tmp_a, h->d_tmp_a + L, L_new, h->d_tmp_b, h->d_tmp_b + L, L_old,
+                                              h->d_cell_start, h->d_glx, h->d_gly, h->d_gidx, h->d_acc);
+    CK(cudaGetLastError());
+    double res[3];
+    CK(cudaMemcpyAsync(res, h->d_acc, sizeof res, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    out3[0] = res[0]; out3[1] = res[1]; out3[2] = res[2] / (double)L_new;
+    return ICMSLAM_OK;
+}
+
+extern "C" int icmslam_filtrar_obs(icmslam_handle* h, const double* obs, int32_t B, int32_t T, int64_t ld, double max_dist,
+                                   int32_t cant_max, double* out, int64_t ld_out, int32_t memspace)
+{
+    if (!h || !obs || !out || B <= 0 || B > 1024 || T <= 0 || ld < T || ld_out < T) return ICMSLAM_ERR_INVALID;
+    (void)memspace;
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = h->stream;
+    double *d_in = nullptr, *d_out = nullptr;
+    int *d_a = nullptr, *d_keep = nullptr, *d_err = nullptr;
+    CK(dalloc(&d_in, (size_t)B * T)); CK(dalloc(&d_out, (size_t)B * T));
+    CK(dalloc(&d_a, (size_t)T)); CK(dalloc(&d_keep, (size_t)T)); CK(dalloc(&d_err, 1));
+    CK(cudaMemcpy2DAsync(d_in, (size_t)T * 8, obs, (size_t)ld * 8, (size_t)T * 8, B, cudaMemcpyDefault, s));
+    CK(cudaMemsetAsync(d_err, 0, sizeof(int), s));
+    k_fo_count<<<nblk(T, 128), 128, 0, s>>>(d_in, B, T, T, max_dist, d_a);
+    CK(cudaGetLastError());
+    k_fo_interp<<<nblk(T, 128), 128, 0, s>>>(d_a, T, cant_max, d_keep, d_err);
+    CK(cudaGetLastError());
+    const size_t smem = (size_t)2 * B * (EX_TILE + 1) * sizeof(double);
+    CK(cudaFuncSetAttribute(k_fo_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fo_select<<<nblk(T, EX_TILE), 256, smem, s>>>(d_in, B, T, T, max_dist, d_keep, d_out, T);
+    CK(cudaGetLastError());
+    int err = 0;
+    CK(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpy2DAsync(out, (size_t)ld_out * 8, d_out, (size_t)T * 8, (size_t)T * 8, B, cudaMemcpyDefault, s));
+    CK(cudaStreamSynchronize(s));
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_a); cudaFree(d_keep); cudaFree(d_err);
+    return err ? ICMSLAM_ERR_INVALID : ICMSLAM_OK;
+}

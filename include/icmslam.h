@@ -1,0 +1,160 @@
+/*
+ * icmslam.h -- C ABI of libicmslam.so, the B200 (sm_100a) implementation of the ICM-SLAM
+ * offline sweep path of Seba-san/icm-slam.
+ *
+ * The reference has no FFI: its hot path sits behind a Python class surface
+ * (scripts/sensors.py:15-282 `ICM_ROS`, scripts/ICM_SLAM.py:104-265 `Mapa`,
+ * scripts/ICM_SLAM.py:22-58 `filtrar_z`).  Each entry point below names the reference
+ * interface it replaces; the ctypes binding a maintainer adds to the reference is shown in
+ * INTEGRATION.md and implemented in icm_slam_b200/_lib.py.
+ *
+ * Conventions
+ *  - plain C types only; all arrays are IEEE fp64 / int32 in numpy C order: a "3 x T" array is
+ *    three rows, row r starts at base + r*ld (ld in ELEMENTS, ld >= T).
+ *  - `memspace` says where caller buffers live: ICMSLAM_HOST (the library copies) or
+ *    ICMSLAM_DEVICE (CUDA device pointers on the handle's device, used in place / copied D2D).
+ *  - every call returns an int status (0 = ok, <0 = error below); nothing throws or exits.
+ *    The reference's failure modes are mapped to status codes (see each code).
+ *  - one handle per GPU, not thread-safe (the reference solver is not re-entrant either,
+ *    sensors.py:214-220).  Work is enqueued on the handle's CUDA stream; calls that return
+ *    data to HOST buffers synchronise that stream before returning.
+ *  - there is NO CPU fallback: without a CUDA device icmslam_create fails with
+ *    ICMSLAM_ERR_CUDA.
+ */
+#ifndef ICMSLAM_H_
+#define ICMSLAM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICMSLAM_ABI_VERSION 1
+
+enum { ICMSLAM_HOST = 0, ICMSLAM_DEVICE = 1 };
+
+/* status codes */
+enum {
+    ICMSLAM_OK = 0,
+    ICMSLAM_EMPTY_FIRST_SCAN = 1,   /* not an error: scan 0 has no observation, the reference returns
+                                       its inputs unchanged (sensors.py:137-139); outputs = inputs */
+    ICMSLAM_ERR_INVALID = -1,       /* bad argument / call order */
+    ICMSLAM_ERR_LABEL_CAP = -2,     /* a new label would exceed config.L: the reference raises
+                                       IndexError at ICM_SLAM.py:191 */
+    ICMSLAM_ERR_EMPTY_LAST = -3,    /* last scan has no observation: IndexError at sensors.py:148 */
+    ICMSLAM_ERR_EMPTY_MAP = -4,     /* no landmark reaches `cota`: ValueError at ICM_SLAM.py:241-255 */
+    ICMSLAM_ERR_ALLOC = -5,         /* device or host allocation failed */
+    ICMSLAM_ERR_CUDA = -6,          /* CUDA runtime error; text via icmslam_last_error */
+    ICMSLAM_ERR_UNSUPPORTED = -7
+};
+
+/* sweep mode switches.  (SEQUENTIAL, NM, RUNNING) is the reference's own semantics
+ * (sensors.py:145-162, :221, ICM_SLAM.py:191-194); the others are the restated, parallel
+ * variants described in DESIGN.md. */
+enum { ICMSLAM_SCHED_SEQUENTIAL = 0, ICMSLAM_SCHED_REDBLACK = 1 };
+enum { ICMSLAM_SOLVER_NM = 0, ICMSLAM_SOLVER_NEWTON = 1 };
+enum { ICMSLAM_VIEW_RUNNING = 0, ICMSLAM_VIEW_FULL = 1, ICMSLAM_VIEW_PREV = 2 };
+
+/* The live keys of ConfigICM (ICM_SLAM.py:72-99, config_default.yaml / config_ros.yaml). */
+typedef struct icmslam_config {
+    double deltat;          /* D['deltat'] */
+    double q1, q2;          /* D['Q']  (diagonal observation weights) */
+    double r1, r2, r3;      /* D['R']  (diagonal motion weights) */
+    double cte_odom;        /* D['cte_odom'] */
+    double cota;            /* D['cota'] */
+    double dist_thr;        /* D['dist_thr'] */
+    double rango_laser_max; /* D['rango_laser_max'] */
+    double radio;           /* D['radio'] */
+    int32_t L;              /* D['L']: label capacity */
+    int32_t device;         /* CUDA device ordinal */
+} icmslam_config;
+
+typedef struct icmslam_sweep_opts {
+    int32_t schedule;       /* ICMSLAM_SCHED_* */
+    int32_t solver;         /* ICMSLAM_SOLVER_* */
+    int32_t map_view;       /* ICMSLAM_VIEW_* */
+    int32_t newton_maxit;   /* <=0: default 20 */
+    double newton_tol;      /* Newton stops when |dtheta| <= tol; <=0: default 1e-10 */
+    int32_t fused;          /* 1: allow the single-kernel path when (REDBLACK, NEWTON, PREV) */
+    int32_t reserved;
+} icmslam_sweep_opts;
+
+typedef struct icmslam_handle icmslam_handle;
+
+/* -- lifecycle.  Replaces ICM_ROS.__init__ / Mapa.__init__ (sensors.py:16-49, ICM_SLAM.py:109-117). */
+int icmslam_create(const icmslam_config* cfg, icmslam_handle** out);
+int icmslam_destroy(icmslam_handle* h);
+int icmslam_abi_version(void);
+const char* icmslam_strerror(int status);
+const char* icmslam_last_error(const icmslam_handle* h);
+/* cudaStream_t to enqueue on (NULL = the legacy default stream). */
+int icmslam_set_stream(icmslam_handle* h, void* cuda_stream);
+int icmslam_synchronize(icmslam_handle* h);
+
+/* -- data.  Replaces the ICM_ROS attributes `mediciones` (B x T), `odometria` (3 x T), `u` (2 x T)
+ * (sensors.py:26-28, filled by ROS.principal_callback ICM_SLAM.py:332-339) and the legacy
+ * ICM_method.load_data (ICM_SLAM_old.py:249-264).  `scans` are ranges ALREADY pre-conditioned
+ * unless precondition != 0, in which case z = min(z + radio, rango_laser_max), NaN -> max is
+ * applied on the device (sensors_definitions.py:21-22, IJAC2018_python.txt:43).
+ * cos_tab / sin_tab (length B, host pointers, may be NULL) are cos/sin of the beam angles
+ * (i*pi)/180 exactly as the caller's numpy computes them (ICM_SLAM.py:44,51-53); NULL -> libm. */
+int icmslam_load(icmslam_handle* h, const double* scans, int32_t B, int32_t T, int64_t ld_scans,
+                 const double* odometry, int64_t ld_odo, const double* controls, int64_t ld_u,
+                 const double* cos_tab, const double* sin_tab, int32_t precondition, int32_t memspace);
+
+/* -- filtrar_z for every scan (ICM_SLAM.py:22-58), once per dataset (the reference recomputes it
+ * every sweep, sensors.py:134,146, although it does not depend on the poses).  Builds the CSR of
+ * kept beams on the device. */
+int icmslam_extract(icmslam_handle* h);
+int icmslam_extraction_size(const icmslam_handle* h, int64_t* n_obs, int32_t* n_empty_scans,
+                            int32_t* max_per_scan);
+/* any pointer may be NULL.  off: T+1, the others: n_obs. */
+int icmslam_get_extraction(icmslam_handle* h, int32_t* off, int32_t* beam, double* d, double* bx,
+                           double* by, int32_t memspace);
+
+/* -- Mapa state (ICM_SLAM.py:115, :119-126): landmarks_actuales and cant_obs_i. */
+int icmslam_set_landmarks_actuales(icmslam_handle* h, int32_t lact);
+int icmslam_get_landmarks_actuales(const icmslam_handle* h, int32_t* lact);
+int icmslam_get_counts(icmslam_handle* h, double* cant_obs_i, int32_t n, int32_t memspace);
+
+/* -- one ICM sweep = ICM_ROS.iterations_process_offline(mapa_viejo, x) (sensors.py:125-168).
+ * map_in: 2 x L_in (ld_map_in).  x: 3 x T (ld_x), updated IN PLACE like the reference.
+ * x0: the pinned first pose `self.x0` (sensors.py:131), 3 doubles, always a HOST pointer.
+ * map_out: 2 x cap_out (ld_map_out) receives `mapa_refinado`; *L_out its width (host int).
+ * Association uses the first min(landmarks_actuales, L_in) columns of map_in; new labels start
+ * at landmarks_actuales (ICM_SLAM.py:169-182).  On return landmarks_actuales = *L_out. */
+int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_in, int64_t ld_map_in, double* x,
+                  int64_t ld_x, const double* x0, double* map_out, int32_t cap_out, int64_t ld_map_out,
+                  int32_t* L_out, const icmslam_sweep_opts* opts, int32_t memspace);
+
+/* -- results of the last sweep (all optional; mirror what Mapa / actualizar expose).
+ * c: association label of every kept observation, CSR order (`c` of ICM_SLAM.py:201).
+ * raw map / counts / Lact: the map before Mapa.filtrar (`y`, cant_obs_i, landmarks_actuales at
+ * sensors.py:165). */
+int icmslam_get_associations(icmslam_handle* h, int32_t* c, int32_t memspace);
+int icmslam_get_raw_map(icmslam_handle* h, double* raw_map, int32_t cap, int64_t ld, double* raw_counts,
+                        int32_t* raw_L, int32_t memspace);
+/* device-side statistics of the last sweep: number of Newton iterations summed over poses etc. */
+int icmslam_get_sweep_stats(icmslam_handle* h, int64_t* stats, int32_t n);
+
+/* -- Mapa.filtrar on caller data (ICM_SLAM.py:204-265): prune counts < cota, merge neighbours
+ * closer than dist_thr, count-weighted means.  In: 2 x L_in map + counts; out: 2 x cap map, counts. */
+int icmslam_filter_map(icmslam_handle* h, const double* map_in, int64_t ld_in, const double* counts_in,
+                       int32_t L_in, double* map_out, int32_t cap_out, int64_t ld_out, double* counts_out,
+                       int32_t* L_out, int32_t memspace);
+
+/* -- calc_cambio (ICM_SLAM.py:490-495): min / max / mean over the new landmarks of the distance to
+ * the nearest old landmark.  out3 is a HOST pointer. */
+int icmslam_calc_cambio(icmslam_handle* h, const double* map_new, int32_t L_new, int64_t ld_new,
+                        const double* map_old, int32_t L_old, int64_t ld_old, double* out3, int32_t memspace);
+
+/* -- filtrar_obs.m (scripts/filtrar_obs.m:6-50), the offline scan gate: keep the k(t) nearest
+ * returns per scan.  obs / out: B x T. */
+int icmslam_filtrar_obs(icmslam_handle* h, const double* obs, int32_t B, int32_t T, int64_t ld, double max_dist,
+                        int32_t cant_max, double* out, int64_t ld_out, int32_t memspace);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICMSLAM_H_ */

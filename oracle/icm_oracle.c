@@ -521,8 +521,10 @@ ORC_API void orc_tras_rot(const double pose[3], int n, const double* bx, const d
 {
     double ct = cos(pose[2] - ORC_PI / 2.0), st = sin(pose[2] - ORC_PI / 2.0);
     for (int i = 0; i < n; ++i) {
-        wx[i] = (bx[i] * ct + by[i] * (-st)) + pose[0];
-        wy[i] = (bx[i] * st + by[i] * ct) + pose[1];
+        /* numpy's matmul accumulates acc = a0*b0; acc = fma(a1, b1, acc) on this host (verified
+         * bit-for-bit against tests/golden/units.npz tr_out); the CUDA path uses __fma_rn. */
+        wx[i] = fma(by[i], -st, bx[i] * ct) + pose[0];
+        wy[i] = fma(by[i], ct, bx[i] * st) + pose[1];
     }
 }
 

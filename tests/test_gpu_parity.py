@@ -1,0 +1,282 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI,
+against (a) the fixtures minted from the unmodified reference and (b) the pinned CPU oracle on
+the same seeded inputs.
+
+Bars (BASELINE.json north_star): association labels, label counts, landmark counts bit-exact;
+poses / landmarks within 1e-6 m and 1e-8 rad in matching solver modes.
+"""
+import numpy as np
+import pytest
+
+from helpers import CONFIG_ROS, c1_inputs, c2_inputs, golden
+
+pytestmark = pytest.mark.gpu
+
+TOL_XY = 1e-6
+TOL_TH = 1e-8
+
+
+def _cfg(**kw):
+    from icm_slam_b200.config import ConfigICM
+    d = dict(CONFIG_ROS)
+    d.update(kw)
+    return ConfigICM.from_values(**d)
+
+
+def _engine(cfg, z, odo, u):
+    from icm_slam_b200.engine import Engine
+    e = Engine(cfg)
+    e.load(z, odo, u, precondition=True)
+    e.extract()
+    return e
+
+
+def _oracle(cfgd, z, odo, u):
+    from oracle import oracle as orc
+    ocfg = orc.make_cfg(**cfgd)
+    ext = orc.extract_all(orc.precondition(z, ocfg.radio, ocfg.rango_laser_max), ocfg)
+    return orc, ocfg, ext
+
+
+# ---------------------------------------------------------------------------------------------
+def test_library_loads_and_reports_abi():
+    from icm_slam_b200 import _lib
+    assert _lib.lib().icmslam_abi_version() == 1
+
+
+def test_extraction_matches_oracle_bit_exact_c1_c2():
+    for z, odo, u in (c1_inputs(), c2_inputs()):
+        e = _engine(_cfg(), z, odo, u)
+        orc, ocfg, ext = _oracle(CONFIG_ROS, z, odo, u)
+        g = e.get_extraction()
+        assert np.array_equal(g["off"], ext["off"])
+        assert np.array_equal(g["beam"], ext["beam"])
+        assert np.array_equal(g["d"], ext["d"]) and np.array_equal(g["bx"], ext["bx"]) and np.array_equal(g["by"], ext["by"])
+        e.close()
+    assert ext["n"] > 17892  # c2 is the raw, denser log
+
+
+def test_extraction_units_vs_reference_fixture():
+    u = golden("units.npz")
+    T = u["fz_scans"].shape[1]
+    e = _engine(_cfg(), u["fz_scans"], np.zeros((3, T)), np.zeros((2, T)))   # fixture scans are already pre-conditioned
+    e2 = None
+    from icm_slam_b200.engine import Engine
+    e2 = Engine(_cfg())
+    e2.load(u["fz_scans"], np.zeros((3, T)), np.zeros((2, T)), precondition=False)
+    e2.extract()
+    g = e2.get_extraction()
+    assert np.array_equal(g["off"], u["fz_off"])
+    rows = u["fz_rows"]
+    assert np.array_equal(g["d"], rows[:, 0]) and np.array_equal(g["bx"], rows[:, 2]) and np.array_equal(g["by"], rows[:, 3])
+    assert np.array_equal(g["beam"] * np.pi / 180.0, rows[:, 1])
+    e.close()
+    e2.close()
+
+
+def test_filtrar_obs_reproduces_dataset_pair():
+    raw, odo, u = c2_inputs()
+    want, _, _ = c1_inputs()
+    from icm_slam_b200.engine import Engine
+    e = Engine(_cfg())
+    got = e.filtrar_obs(raw, 10.0, 15)
+    assert np.array_equal(got, want)
+    e.close()
+
+
+def _teacher_forced_reference(gold, z, odo, u, cfgd, map0_key, x0_key, view):
+    """Per sweep: feed the reference's own input poses/map; association labels, label counts, raw
+    landmark count and filtered landmark count must equal the reference bit for bit (they do not
+    depend on the pose update)."""
+    cfg = _cfg(**cfgd)
+    e = _engine(cfg, z, odo, u)
+    mapa = gold[map0_key].copy()
+    e.landmarks_actuales = mapa.shape[1]
+    for k in range(1, int(gold["nsweeps"]) + 1):
+        p = "s%d_" % k
+        x = np.ascontiguousarray(gold[p + "x_in"].copy())
+        st, Lout, mout = e.sweep(mapa, x, odo[:, 0], schedule="redblack", solver="newton", view=view, fused=False)
+        assert st == 0
+        assert np.array_equal(e.associations(), gold[p + "labels"]), "labels differ in sweep %d" % k
+        raw, cnt, rl = e.raw_map()
+        assert rl == int(gold[p + "raw_L"])
+        assert np.array_equal(cnt, gold[p + "raw_counts"])
+        assert np.max(np.abs(raw - gold[p + "raw_map"])) <= 1e-9
+        assert Lout == gold[p + "map_out"].shape[1]
+        assert np.max(np.abs(mout - gold[p + "map_out"])) <= 1e-9
+        assert np.array_equal(e.counts(Lout), gold[p + "counts_out"])
+        cam = e.calc_cambio(mout, mapa)
+        assert np.allclose(cam, gold[p + "cambio"], rtol=0, atol=1e-9)
+        mapa = gold[p + "map_out"].copy()
+        assert e.landmarks_actuales == mapa.shape[1]
+    e.close()
+
+
+@pytest.mark.parametrize("view", ["prev", "full", "running"])
+def test_associations_and_map_vs_reference_c1(view):
+    g = golden("c1_ref.npz")
+    z, odo, u = c1_inputs()
+    _teacher_forced_reference(g, z, odo, u, {}, "p0_map", "p0_x", view)
+
+
+def test_associations_and_map_vs_reference_c2():
+    g = golden("c2_ref.npz")
+    z, odo, u = c2_inputs()
+    _teacher_forced_reference(g, z, odo, u, {}, "p0_map", "p0_x", "prev")
+
+
+@pytest.mark.parametrize("name", ["synth_a.npz", "synth_b.npz"])
+def test_associations_and_map_vs_reference_synthetic(name):
+    g = golden(name)
+    _teacher_forced_reference(g, g["observations"].astype(np.float64), g["odometry"], g["velocities"],
+                              dict(L=int(g["cfg_L"]), cota=float(g["cfg_cota"])), "map_init", "x_init", "running")
+
+
+def _reference_mode_gpu(gold, z, odo, u, cfgd, map0):
+    """(sequential, NM, running) on the GPU == the unmodified reference: poses to 1e-6 m / 1e-8 rad."""
+    cfg = _cfg(**cfgd)
+    e = _engine(cfg, z, odo, u)
+    mapa = map0.copy()
+    e.landmarks_actuales = mapa.shape[1]
+    for k in range(1, int(gold["nsweeps"]) + 1):
+        p = "s%d_" % k
+        x = np.ascontiguousarray(gold[p + "x_in"].copy())
+        st, Lout, mout = e.sweep(mapa, x, odo[:, 0], schedule="sequential", solver="nm", view="running", stats=True)
+        assert np.array_equal(e.associations(), gold[p + "labels"])
+        d = np.abs(x - gold[p + "x_out"])
+        assert d[:2].max() <= TOL_XY and d[2].max() <= TOL_TH, d.max(axis=1)
+        assert np.max(np.abs(mout - gold[p + "map_out"])) <= TOL_XY
+        assert e.sweep_stats()["newton_iters"] == int(gold[p + "nev"])   # same number of energy evaluations
+        mapa = gold[p + "map_out"].copy()
+    e.close()
+
+
+def test_reference_mode_poses_c1():
+    g = golden("c1_ref.npz")
+    z, odo, u = c1_inputs()
+    _reference_mode_gpu(g, z, odo, u, {}, g["p0_map"])
+
+
+@pytest.mark.parametrize("name", ["synth_a.npz", "synth_b.npz"])
+def test_reference_mode_poses_synthetic(name):
+    g = golden(name)
+    _reference_mode_gpu(g, g["observations"].astype(np.float64), g["odometry"], g["velocities"],
+                        dict(L=int(g["cfg_L"]), cota=float(g["cfg_cota"])), g["map_init"])
+
+
+MODES = [("redblack", "newton", "prev"), ("redblack", "newton", "full"), ("redblack", "newton", "running"),
+         ("sequential", "newton", "running"), ("redblack", "nm", "running"), ("sequential", "newton", "prev")]
+
+
+@pytest.mark.parametrize("schedule,solver,view", MODES)
+def test_modes_vs_oracle_c1(schedule, solver, view):
+    """3 chained sweeps on data_IJAC2018.mat in each restated mode: GPU == oracle in the same mode."""
+    g = golden("c1_ref.npz")
+    z, odo, u = c1_inputs()
+    orc, ocfg, ext = _oracle(CONFIG_ROS, z, odo, u)
+    e = _engine(_cfg(), z, odo, u)
+    mo = orc.Mapa(ocfg)
+    map_o = g["p0_map"].copy()
+    map_g = g["p0_map"].copy()
+    mo.landmarks_actuales = map_o.shape[1]
+    e.landmarks_actuales = map_g.shape[1]
+    xo = np.ascontiguousarray(g["p0_x"].copy())
+    xg = xo.copy()
+    for k in range(3):
+        r = orc.sweep(ocfg, mo, ext, odo, u, odo[:, 0], map_o, xo, schedule, solver, view)
+        st, Lout, mout = e.sweep(map_g, xg, odo[:, 0], schedule=schedule, solver=solver, view=view, fused=False,
+                                 newton_tol=1e-12, newton_maxit=50)
+        assert np.array_equal(e.associations(), r["c"])
+        assert Lout == r["map"].shape[1]
+        d = np.abs(xg - xo)
+        assert d[:2].max() <= TOL_XY and d[2].max() <= TOL_TH, (k, d.max(axis=1))
+        assert np.max(np.abs(mout - r["map"])) <= TOL_XY
+        map_o = r["map"]
+        map_g = np.ascontiguousarray(mout.copy())
+    e.close()
+
+
+def _synthetic_case(L_true, T, seed):
+    from icm_slam_b200.synthetic import make_synthetic
+    d = make_synthetic(L_true, T=T, seed=seed)
+    cfgd = dict(CONFIG_ROS, L=2 * L_true + 64, cota=20.0)
+    return d, cfgd
+
+
+@pytest.mark.parametrize("view", ["prev", "full", "running"])
+def test_synthetic_medium_vs_oracle(view):
+    """T=6000 / 625 landmarks: grid association vs the oracle's brute force, 2 sweeps."""
+    d, cfgd = _synthetic_case(625, 6000, 20181 + 7)
+    z, odo, u = d["observations"], d["odometry"], d["velocities"]
+    orc, ocfg, ext = _oracle(cfgd, z, odo, u)
+    e = _engine(_cfg(**cfgd), z, odo, u)
+    assert e.n == ext["n"]
+    mo = orc.Mapa(ocfg)
+    map_o = d["map_init"].copy()
+    map_g = d["map_init"].copy()
+    mo.landmarks_actuales = map_o.shape[1]
+    e.landmarks_actuales = map_g.shape[1]
+    xo = np.ascontiguousarray(d["x_init"].copy())
+    xg = xo.copy()
+    for k in range(2):
+        r = orc.sweep(ocfg, mo, ext, odo, u, odo[:, 0], map_o, xo, "redblack", "newton", view)
+        st, Lout, mout = e.sweep(map_g, xg, odo[:, 0], schedule="redblack", solver="newton", view=view, fused=False,
+                                 newton_tol=1e-12, newton_maxit=50)
+        assert np.array_equal(e.associations(), r["c"])
+        assert Lout == r["map"].shape[1]
+        dd = np.abs(xg - xo)
+        assert dd[:2].max() <= TOL_XY and dd[2].max() <= TOL_TH, (k, dd.max(axis=1))
+        assert np.max(np.abs(mout - r["map"])) <= TOL_XY
+        map_o = r["map"]
+        map_g = np.ascontiguousarray(mout.copy())
+    e.close()
+
+
+def test_filter_map_units_vs_reference_fixture():
+    u = golden("units.npz")
+    from icm_slam_b200.engine import Engine
+    e = Engine(_cfg(L=40, cota=10.0))
+    for q in range(int(u["fl_n"])):
+        if not int(u[f"fl{q}_ok"]):
+            continue
+        out, cnt, Lout = e.filter_map(u[f"fl{q}_in"], u[f"fl{q}_cnt"])
+        assert Lout == int(u[f"fl{q}_Lact"]), q
+        assert np.array_equal(cnt, u[f"fl{q}_cant"]), q
+        assert np.max(np.abs(out - u[f"fl{q}_out"])) <= 1e-12, q
+    e.close()
+
+
+def test_error_codes_mirror_reference_failures():
+    g = golden("synth_a.npz")
+    z = g["observations"].astype(np.float64).copy()
+    odo, u = g["odometry"], g["velocities"]
+    cfgd = dict(L=int(g["cfg_L"]), cota=float(g["cfg_cota"]))
+    # empty last scan -> IndexError (sensors.py:148)
+    z2 = z.copy()
+    z2[:, -1] = 10.0
+    e = _engine(_cfg(**cfgd), z2, odo, u)
+    e.landmarks_actuales = g["map_init"].shape[1]
+    with pytest.raises(IndexError):
+        e.sweep(g["map_init"].copy(), np.ascontiguousarray(g["x_init"].copy()), odo[:, 0], fused=False)
+    e.close()
+    # empty first scan -> inputs returned unchanged (sensors.py:137-139)
+    z3 = z.copy()
+    z3[:, 0] = 10.0
+    e = _engine(_cfg(**cfgd), z3, odo, u)
+    e.landmarks_actuales = g["map_init"].shape[1]
+    x = np.ascontiguousarray(g["x_init"].copy())
+    st, Lout, mout = e.sweep(g["map_init"].copy(), x, odo[:, 0], fused=False)
+    assert st == 1 and np.array_equal(x, g["x_init"]) and np.array_equal(mout, g["map_init"])
+    e.close()
+    # label capacity -> IndexError (ICM_SLAM.py:191)
+    e = _engine(_cfg(L=g["map_init"].shape[1], cota=1.0), z, odo, u)
+    e.landmarks_actuales = g["map_init"].shape[1]
+    with pytest.raises(IndexError):
+        e.sweep(g["map_init"].copy()[:, :5] + 100.0, np.ascontiguousarray(g["x_init"].copy()), odo[:, 0], fused=False)
+    e.close()
+    # nothing reaches cota -> ValueError (ICM_SLAM.py:255)
+    e = _engine(_cfg(L=int(g["cfg_L"]), cota=1e9), z, odo, u)
+    e.landmarks_actuales = g["map_init"].shape[1]
+    with pytest.raises(ValueError):
+        e.sweep(g["map_init"].copy(), np.ascontiguousarray(g["x_init"].copy()), odo[:, 0], fused=False)
+    e.close()

@@ -64,8 +64,8 @@ def test_tras_rot_units():
     u = units()
     for p, zi, zo in zip(u["tr_poses"], u["tr_in"], u["tr_out"]):
         wx, wy = orc.tras_rot(p, zi[:, 2], zi[:, 3])
-        # numpy's matmul may fuse the two products (BLAS FMA); allow the last bit
-        assert np.max(np.abs(wx - zo[:, 2])) <= 2e-14 and np.max(np.abs(wy - zo[:, 3])) <= 2e-14
+        # bit-exact: numpy's matmul fuses the second product (acc = fma(a1, b1, a0*b0))
+        assert np.array_equal(wx, zo[:, 2]) and np.array_equal(wy, zo[:, 3])
 
 
 # ------------------------------------------------------------------ a5: Mapa.actualizar
