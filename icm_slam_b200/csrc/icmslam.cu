@@ -58,6 +58,9 @@ struct icmslam_handle {
     void* d_cub = nullptr;
     size_t cub_bytes = 0;
     FusedWorkspace fw;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool timed_fused = false;
+    int64_t n_launch = 0;   // kernels of this library launched so far (cub's not counted)
 };
 
 #define CK(call)                                                                                         \
@@ -122,6 +125,7 @@ extern "C" int icmslam_destroy(icmslam_handle* h)
     DFREE(h->d_cell_start); DFREE(h->d_cell_fill); DFREE(h->d_cell_id); DFREE(h->d_gidx); DFREE(h->d_glx); DFREE(h->d_gly);
     DFREE(h->d_st); DFREE(h->d_cub);
     if (h->h_st) cudaFreeHost(h->h_st);
+    for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
     return ICMSLAM_OK;
 }
@@ -198,6 +202,7 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     if (e == cudaSuccess) e = dalloc(&h->d_gly, L);
     if (e == cudaSuccess) e = dalloc(&h->d_st, 1);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_st, sizeof(DevState));
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
     if (e == cudaSuccess) e = cudaMemset(h->d_st, 0, sizeof(DevState));
     if (e == cudaSuccess) e = cudaMemset(h->d_counts, 0, L * sizeof(double));
     if (e != cudaSuccess) {
@@ -465,60 +470,38 @@ static int status_from_state(const DevState* s)
     return ICMSLAM_OK;
 }
 
-extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_in, int64_t ld_map_in, double* x, int64_t ld_x,
-                             const double* x0, double* map_out, int32_t cap_out, int64_t ld_map_out, int32_t* L_out,
-                             const icmslam_sweep_opts* opts, int32_t memspace)
+static void default_opts(icmslam_sweep_opts& o, const icmslam_sweep_opts* opts)
 {
-    if (!h || !h->extracted || !x || !x0 || L_in < 0 || L_in > h->Lcap || ld_x < h->T || (L_in > 0 && (!map_in || ld_map_in < L_in)))
-        return ICMSLAM_ERR_INVALID;
-    if (map_out && (cap_out <= 0 || ld_map_out < cap_out)) return ICMSLAM_ERR_INVALID;
-    icmslam_sweep_opts o;
     o.schedule = ICMSLAM_SCHED_REDBLACK; o.solver = ICMSLAM_SOLVER_NEWTON; o.map_view = ICMSLAM_VIEW_PREV;
     o.newton_maxit = 0; o.newton_tol = 0.0; o.fused = 1; o.reserved = 0;
     if (opts) o = *opts;
     if (o.newton_maxit <= 0) o.newton_maxit = 20;
     if (!(o.newton_tol > 0.0)) o.newton_tol = 1e-10;
-    CK(cudaSetDevice(h->cfg.device));
+}
+
+// One sweep on device-resident data.  The previous map is in h->d_map_in (2 x Lcap); L_in is its
+// width known on the host, or -1 when only the device knows it (= landmarks_actuales, chained
+// sweeps).  Poses dx (3 x T, ldx) are updated in place; the filtered map goes to dmap_out.
+static int sweep_core(icmslam_handle* h, double* dx, int64_t ldx, const double* x0, const icmslam_sweep_opts& o, int L_in,
+                      double* dmap_out, int out_cap, int64_t out_ld)
+{
     const int T = h->T, L = h->Lcap;
     const int64_t n = h->n;
     cudaStream_t s = h->stream;
     DevState* st = h->d_st;
-    // Mapa.clear_obs (sensors.py:133) happens before the early return of :137-139
-    CK(cudaMemsetAsync(h->d_counts, 0, (size_t)L * sizeof(double), s));
-    if (h->first_empty) {   // sensors.py:137-139: inputs returned unchanged
-        if (map_out && L_in > 0) {
-            int w = L_in < cap_out ? L_in : cap_out;
-            CK(cudaMemcpy2DAsync(map_out, (size_t)ld_map_out * 8, map_in, (size_t)ld_map_in * 8, (size_t)w * 8, 2, cudaMemcpyDefault, s));
-            CK(cudaStreamSynchronize(s));
-        }
-        if (L_out) *L_out = L_in;
-        return ICMSLAM_EMPTY_FIRST_SCAN;
-    }
-    if (h->last_empty && T > 1) return ICMSLAM_ERR_EMPTY_LAST;
-    // inputs
-    double* dx = x;
-    int64_t ldx = ld_x;
-    if (memspace == ICMSLAM_HOST) {
-        CK(cudaMemcpy2DAsync(h->d_x, (size_t)T * 8, x, (size_t)ld_x * 8, (size_t)T * 8, 3, cudaMemcpyHostToDevice, s));
-        dx = h->d_x;
-        ldx = T;
-    }
-    if (L_in > 0)
-        CK(cudaMemcpy2DAsync(h->d_map_in, (size_t)L * 8, map_in, (size_t)ld_map_in * 8, (size_t)L_in * 8, 2, cudaMemcpyDefault, s));
     const double* min_x = h->d_map_in;
     const double* min_y = h->d_map_in + L;
     double* raw_x = h->d_raw;
     double* raw_y = h->d_raw + L;
-    double* dmap_out = (memspace == ICMSLAM_HOST || !map_out) ? h->d_map_out : map_out;
-    const int out_cap = (memspace == ICMSLAM_HOST || !map_out) ? L : cap_out;
-    const int64_t out_ld = (memspace == ICMSLAM_HOST || !map_out) ? L : ld_map_out;
+    const bool timing = (o.reserved & 2) != 0;
 
-    k_sweep_begin<<<1, 1, 0, s>>>(st, L_in);
+    k_sweep_begin<<<1, 1, 0, s>>>(st, L_in < 0 ? L : L_in);
     CK(cudaGetLastError());
+    h->n_launch += 1;
     CK(cudaMemsetAsync(h->d_sum_x, 0, (size_t)L * 8, s));
     CK(cudaMemsetAsync(h->d_sum_y, 0, (size_t)L * 8, s));
     CK(cudaMemsetAsync(h->d_cnt, 0, ((size_t)L + 1) * sizeof(int), s));
-    int rc = build_grid(h, min_x, min_y, &st->lsearch, L_in > 0 ? L_in : 1, false);
+    int rc = build_grid(h, min_x, min_y, &st->lsearch, L_in < 0 ? L : (L_in > 0 ? L_in : 1), false);
     if (rc) return rc;
 
     const bool collect = (o.reserved & 1) != 0;
@@ -529,15 +512,19 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
     A.x = dx; A.ldx = ldx; A.odo = h->d_odo; A.ldo = T; A.u = h->d_u; A.ldu = T;
     A.x0[0] = x0[0]; A.x0[1] = x0[1]; A.x0[2] = x0[2];
     A.off = h->d_off; A.T = T;
+    if (timing) CK(cudaEventRecord(h->ev[0], s));
     if (use_fused) {
         rc = fused_sweep(h->fw, s, h->dcfg, A, h->d_bx, h->d_by, n, st, h->d_cell_start, h->d_glx, h->d_gly, h->d_gidx, h->d_c,
                          h->d_nfar, h->d_sum_x, h->d_sum_y, h->d_cnt, o.newton_tol, o.newton_maxit, iters, h->err, sizeof h->err);
         if (rc) return rc;
+        h->n_launch += 1;
     } else {
         k_assoc<<<148 * 8, 256, 0, s>>>(T, h->d_off, h->d_bx, h->d_by, dx, ldx, x0[0], x0[1], x0[2], st, h->d_cell_start, h->d_glx,
                                         h->d_gly, h->d_gidx, h->dcfg.dist_thr, h->d_c, h->d_nfar, h->d_sum_x, h->d_sum_y, h->d_cnt);
         CK(cudaGetLastError());
+        h->n_launch += 1;
     }
+    if (timing) CK(cudaEventRecord(h->ev[1], s));
     // new labels: one per scan that has a far observation, numbered in time order
     k_flag_positive<<<nblk(T, 256), 256, 0, s>>>(h->d_nfar, T, h->d_flag);
     CK(cudaGetLastError());
@@ -549,6 +536,7 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
     k_new_labels<<<148 * 4, 256, 0, s>>>(T, h->d_off, h->d_bx, h->d_by, xin, ldxin, x0[0], x0[1], x0[2], st, h->d_nfar, h->d_prefix,
                                          L, h->d_c, h->d_sum_x, h->d_sum_y, h->d_cnt);
     CK(cudaGetLastError());
+    h->n_launch += 2;
     const bool running = o.map_view == ICMSLAM_VIEW_RUNNING;
     if (running) {
         if (!h->d_sorted) {
@@ -571,10 +559,12 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
         k_running_mean<<<nblk(L, 128), 128, 0, s>>>(st, h->d_seg, h->d_cnt, h->d_sorted, h->d_scan_of, h->d_bx, h->d_by, dx, ldx,
                                                     x0[0], x0[1], x0[2], h->d_seen_x, h->d_seen_y, raw_x, raw_y, L);
         CK(cudaGetLastError());
+        h->n_launch += 1;
     }
     k_means_flags<<<nblk(L, 256), 256, 0, s>>>(st, h->d_sum_x, h->d_sum_y, h->d_cnt, h->dcfg.cota, running ? 1 : 0, raw_x, raw_y,
                                                h->d_kflag, L);
     CK(cudaGetLastError());
+    h->n_launch += 1;
     if (!use_fused) {
         ObsArrays O;
         O.bx = h->d_bx; O.by = h->d_by; O.d = h->d_d; O.beam = h->d_beam; O.ang = h->d_ang;
@@ -582,21 +572,66 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
         S.view = o.map_view; S.c = h->d_c; S.seen_x = h->d_seen_x; S.seen_y = h->d_seen_y;
         S.raw_x = raw_x; S.raw_y = raw_y; S.min_x = min_x; S.min_y = min_y;
         S.lsearch_ptr = &st->lsearch;
+        if (timing) CK(cudaEventRecord(h->ev[2], s));
         if (o.schedule == ICMSLAM_SCHED_REDBLACK) {
             int half = (T + 1) / 2;
             k_pose_colour<<<nblk(half, 128), 128, 0, s>>>(1, h->dcfg, A, O, S, o.solver, o.newton_tol, o.newton_maxit, iters);
             CK(cudaGetLastError());
             k_pose_colour<<<nblk(half, 128), 128, 0, s>>>(0, h->dcfg, A, O, S, o.solver, o.newton_tol, o.newton_maxit, iters);
             CK(cudaGetLastError());
+            h->n_launch += 2;
         } else {
             k_pose_sequential<<<1, 32, 0, s>>>(h->dcfg, A, O, S, o.solver, o.newton_tol, o.newton_maxit, iters);
             CK(cudaGetLastError());
+            h->n_launch += 1;
         }
+        if (timing) CK(cudaEventRecord(h->ev[3], s));
     }
+    h->timed_fused = use_fused;
     // Mapa.filtrar (sensors.py:165-166)
     rc = run_filter(h, raw_x, raw_y, h->d_cnt, nullptr, dmap_out, out_cap, out_ld, nullptr, 1);
     if (rc) return rc;
+    h->n_launch += 14;   // grid build (3+3) + filter kernels (8)
     h->lact_dirty = true;
+    return ICMSLAM_OK;
+}
+
+extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_in, int64_t ld_map_in, double* x, int64_t ld_x,
+                             const double* x0, double* map_out, int32_t cap_out, int64_t ld_map_out, int32_t* L_out,
+                             const icmslam_sweep_opts* opts, int32_t memspace)
+{
+    if (!h || !h->extracted || !x || !x0 || L_in < 0 || L_in > h->Lcap || ld_x < h->T || (L_in > 0 && (!map_in || ld_map_in < L_in)))
+        return ICMSLAM_ERR_INVALID;
+    if (map_out && (cap_out <= 0 || ld_map_out < cap_out)) return ICMSLAM_ERR_INVALID;
+    icmslam_sweep_opts o;
+    default_opts(o, opts);
+    CK(cudaSetDevice(h->cfg.device));
+    const int T = h->T, L = h->Lcap;
+    cudaStream_t s = h->stream;
+    // Mapa.clear_obs (sensors.py:133) happens before the early return of :137-139
+    CK(cudaMemsetAsync(h->d_counts, 0, (size_t)L * sizeof(double), s));
+    if (h->first_empty) {   // sensors.py:137-139: inputs returned unchanged
+        if (map_out && L_in > 0) {
+            int w = L_in < cap_out ? L_in : cap_out;
+            CK(cudaMemcpy2DAsync(map_out, (size_t)ld_map_out * 8, map_in, (size_t)ld_map_in * 8, (size_t)w * 8, 2, cudaMemcpyDefault, s));
+            CK(cudaStreamSynchronize(s));
+        }
+        if (L_out) *L_out = L_in;
+        return ICMSLAM_EMPTY_FIRST_SCAN;
+    }
+    if (h->last_empty && T > 1) return ICMSLAM_ERR_EMPTY_LAST;
+    double* dx = x;
+    int64_t ldx = ld_x;
+    if (memspace == ICMSLAM_HOST) {
+        CK(cudaMemcpy2DAsync(h->d_x, (size_t)T * 8, x, (size_t)ld_x * 8, (size_t)T * 8, 3, cudaMemcpyHostToDevice, s));
+        dx = h->d_x;
+        ldx = T;
+    }
+    if (L_in > 0)
+        CK(cudaMemcpy2DAsync(h->d_map_in, (size_t)L * 8, map_in, (size_t)ld_map_in * 8, (size_t)L_in * 8, 2, cudaMemcpyDefault, s));
+    const bool own_out = (memspace == ICMSLAM_HOST || !map_out);
+    int rc = sweep_core(h, dx, ldx, x0, o, L_in, own_out ? h->d_map_out : map_out, own_out ? L : cap_out, own_out ? (int64_t)L : ld_map_out);
+    if (rc) return rc;
     if (memspace == ICMSLAM_HOST) {
         CK(cudaMemcpy2DAsync(x, (size_t)ld_x * 8, dx, (size_t)T * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToHost, s));
         rc = sync_state(h);
@@ -621,6 +656,90 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
         if (status) return status;
         *L_out = h->h_st->new_l;
     }
+    return ICMSLAM_OK;
+}
+
+// ---- the driver loop (sensors.py:302-315): N sweeps with everything resident on the device -------
+extern "C" int icmslam_set_map(icmslam_handle* h, const double* map, int32_t L_map, int64_t ld, int32_t memspace)
+{
+    if (!h || L_map < 0 || L_map > h->Lcap || (L_map > 0 && (!map || ld < L_map))) return ICMSLAM_ERR_INVALID;
+    (void)memspace;
+    CK(cudaSetDevice(h->cfg.device));
+    if (L_map > 0)
+        CK(cudaMemcpy2DAsync(h->d_map_in, (size_t)h->Lcap * 8, map, (size_t)ld * 8, (size_t)L_map * 8, 2, cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return icmslam_set_landmarks_actuales(h, L_map);
+}
+
+extern "C" int icmslam_get_map(icmslam_handle* h, double* map, int32_t cap, int64_t ld, int32_t* L_map, int32_t memspace)
+{
+    if (!h || !L_map) return ICMSLAM_ERR_INVALID;
+    (void)memspace;
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = sync_state(h);
+    if (rc) return rc;
+    int status = status_from_state(h->h_st);
+    if (status) return status;
+    *L_map = h->lact_host;
+    int w = h->lact_host < cap ? h->lact_host : cap;
+    if (map && w > 0) {
+        CK(cudaMemcpy2DAsync(map, (size_t)ld * 8, h->d_map_in, (size_t)h->Lcap * 8, (size_t)w * 8, 2, cudaMemcpyDefault, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return ICMSLAM_OK;
+}
+
+extern "C" int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const double* x0, int32_t n_sweeps,
+                               const icmslam_sweep_opts* opts, int32_t memspace)
+{
+    if (!h || !h->extracted || !x || !x0 || ld_x < h->T || n_sweeps < 0) return ICMSLAM_ERR_INVALID;
+    icmslam_sweep_opts o;
+    default_opts(o, opts);
+    CK(cudaSetDevice(h->cfg.device));
+    const int T = h->T, L = h->Lcap;
+    cudaStream_t s = h->stream;
+    if (h->first_empty) return ICMSLAM_EMPTY_FIRST_SCAN;
+    if (h->last_empty && T > 1) return ICMSLAM_ERR_EMPTY_LAST;
+    double* dx = x;
+    int64_t ldx = ld_x;
+    if (memspace == ICMSLAM_HOST) {
+        CK(cudaMemcpy2DAsync(h->d_x, (size_t)T * 8, x, (size_t)ld_x * 8, (size_t)T * 8, 3, cudaMemcpyHostToDevice, s));
+        dx = h->d_x;
+        ldx = T;
+    }
+    for (int k = 0; k < n_sweeps; ++k) {
+        CK(cudaMemsetAsync(h->d_counts, 0, (size_t)L * sizeof(double), s));
+        int rc = sweep_core(h, dx, ldx, x0, o, -1, h->d_map_out, L, L);
+        if (rc) return rc;
+        double* t = h->d_map_in; h->d_map_in = h->d_map_out; h->d_map_out = t;   // mapa_viejo = mapa_refinado (sensors.py:315)
+    }
+    if (memspace == ICMSLAM_HOST) {
+        CK(cudaMemcpy2DAsync(x, (size_t)ld_x * 8, dx, (size_t)T * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToHost, s));
+        int rc = sync_state(h);
+        if (rc) return rc;
+        return status_from_state(h->h_st);
+    }
+    return ICMSLAM_OK;
+}
+
+// elapsed milliseconds of the dominant kernels of the LAST sweep run with opts.reserved & 2:
+// out[0] = association (or the fused sweep kernel), out[1] = pose kernels (0 when fused).
+extern "C" int icmslam_get_kernel_ms(icmslam_handle* h, double* out2)
+{
+    if (!h || !out2) return ICMSLAM_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    float a = 0.f, b = 0.f;
+    CK(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
+    if (!h->timed_fused) CK(cudaEventElapsedTime(&b, h->ev[2], h->ev[3]));
+    out2[0] = a; out2[1] = b;
+    return ICMSLAM_OK;
+}
+
+extern "C" int icmslam_get_launch_count(icmslam_handle* h, int64_t* n)
+{
+    if (!h || !n) return ICMSLAM_ERR_INVALID;
+    *n = h->n_launch;
     return ICMSLAM_OK;
 }
 

@@ -168,6 +168,41 @@ class Engine:
             return st, int(Lout.value), (map_out[:, : int(Lout.value)] if want_L else map_out)
         return st, int(Lout.value)
 
+    # -- the driver loop with the map resident on the device (sensors.py:302-315) ------------------
+    def set_map(self, mapa):
+        """mapa_viejo (2 x L_map) -> device; landmarks_actuales = L_map."""
+        if not _is_torch(mapa):
+            mapa = np.ascontiguousarray(mapa, dtype=np.float64)
+        Lm = int(mapa.shape[1])
+        pm, ms = _ptr(mapa)
+        check(self.lib.icmslam_set_map(self._h, pm, Lm, _rows(mapa, 2) if Lm else 1, ms), self._h)
+
+    def get_map(self):
+        out = np.zeros((2, self.L))
+        Lm = C.c_int32()
+        check(self.lib.icmslam_get_map(self._h, _ptr(out)[0], self.L, self.L, C.byref(Lm), HOST), self._h)
+        return out[:, : Lm.value].copy()
+
+    def iterate(self, x, x0, n_sweeps=1, schedule="redblack", solver="newton", view="prev", newton_tol=0.0, newton_maxit=0,
+                fused=True, timing=False, stats=False):
+        """n_sweeps x iterations_process_offline on the device-resident map; x (3 x T, numpy or torch CUDA) in place."""
+        opts = SweepOpts(_lib.SCHED[schedule], _lib.SOLVER[solver], _lib.VIEW[view], int(newton_maxit), float(newton_tol),
+                         int(bool(fused)), (1 if stats else 0) | (2 if timing else 0))
+        px, ms = _ptr(x)
+        x0 = np.ascontiguousarray(np.asarray(x0, dtype=np.float64).reshape(3))
+        st = self.lib.icmslam_iterate(self._h, px, _rows(x, 3), C.c_void_p(x0.ctypes.data), int(n_sweeps), C.byref(opts), ms)
+        return check(st, self._h)
+
+    def kernel_ms(self):
+        out = np.zeros(2)
+        check(self.lib.icmslam_get_kernel_ms(self._h, _ptr(out)[0]), self._h)
+        return float(out[0]), float(out[1])
+
+    def launch_count(self) -> int:
+        v = C.c_int64()
+        check(self.lib.icmslam_get_launch_count(self._h, C.byref(v)), self._h)
+        return int(v.value)
+
     def associations(self):
         c = np.empty(self.n, np.int32)
         if self.n:

@@ -1,0 +1,265 @@
+"""The reference's operator surface for the offline batch path, backed by libicmslam.so.
+
+Names, argument meaning and error behaviour follow the reference so that its drivers
+(sensors.py:284-320, example.py:37-54, external_options.py:37-92) run unchanged on top of this
+module:
+
+* `ICM_SLAM(config, x0='')`  -- the solver.  The reference has no class of this name (ICM_SLAM is
+  its tools *module*); the solver class is `ICM_ROS` (sensors.py:15) and, for the legacy offline
+  API, `ICM_method` (ICM_SLAM_old.py:59).  Both names are aliases of this class:
+  `iterations_process_offline(mapa_viejo, x)` (sensors.py:125-168) and
+  `load_data / itererar` (ICM_SLAM_old.py:249, :336).
+* `Mapa(config)` -- `landmarks_actuales`, `cant_obs_i`, `clear_obs()`, `filtrar(mapa)`
+  (ICM_SLAM.py:104-265).
+* `filtrar_z(z, config)`, `tras_rot_z`, `calc_cambio`, `entrepi`, `Rota` (ICM_SLAM.py:22-58, :455-495).
+
+Everything numeric runs in the CUDA library through the C ABI (include/icmslam.h); there is no
+CPU fallback -- without the built library or without a GPU these calls raise.
+"""
+from __future__ import annotations
+
+from copy import copy
+
+import numpy as np
+
+from .config import ConfigICM
+from .engine import Engine
+
+__all__ = ["ICM_SLAM", "ICM_ROS", "ICM_method", "Mapa", "ConfigICM", "filtrar_z", "tras_rot_z", "calc_cambio", "entrepi",
+           "Rota", "precondicionar", "load_mat"]
+
+
+# ---- geometry helpers (host-side conveniences of ICM_SLAM.py:455-488; a handful of flops) --------
+def entrepi(angulo):
+    """ICM_SLAM.py:455-463."""
+    angulo = np.mod(angulo, 2 * np.pi)
+    if angulo > np.pi:
+        angulo = angulo - 2 * np.pi
+    return angulo
+
+
+def Rota(theta):
+    """ICM_SLAM.py:482-488."""
+    c, s = np.cos(theta), np.sin(theta)
+    return np.array([[c, s], [-s, c]])
+
+
+def tras_rot_z(x, z):
+    """ICM_SLAM.py:465-480: body -> world, columns 2:4 of z updated IN PLACE like the reference."""
+    x = np.asarray(x, dtype=np.float64).reshape(3)
+    th = x[2] - np.pi / 2.0
+    c, s = np.cos(th), np.sin(th)
+    R = np.array([[c, s], [-s, c]])
+    z[:, 2:4] = np.matmul(z[:, 2:4], R) + x[0:2]
+    return z
+
+
+def precondicionar(z, config):
+    """sensors_definitions.py:21-22 / IJAC2018_python.txt:43: NaN -> max, z = min(z + radio, max)."""
+    z = np.array(z, dtype=np.float64)
+    z[np.isnan(z)] = config.rango_laser_max
+    return np.minimum(z + config.radio, config.rango_laser_max)
+
+
+def load_mat(path):
+    """Both `.mat` layouts the reference ships: data_IJAC2018.mat
+    (`observations`, `odometry`, `velocities`; createbag.py:124-127) and datos_palomar1.mat
+    (struct `datos` with `observaciones`, `odometria`, `control`).  Returns (z, odometria, u)."""
+    import scipy.io as sio
+    d = sio.loadmat(path)
+    if "datos" in d:
+        s = d["datos"][0, 0]
+        return (np.array(s["observaciones"], dtype=np.float64), np.array(s["odometria"], dtype=np.float64),
+                np.array(s["control"], dtype=np.float64))
+    return (np.array(d["observations"], dtype=np.float64), np.array(d["odometry"], dtype=np.float64),
+            np.array(d["velocities"], dtype=np.float64))
+
+
+_scratch = {}
+
+
+def _scratch_engine(config, L=None):
+    key = (int(getattr(config, "device", 0)), float(config.dist_thr), float(config.rango_laser_max), float(config.cota),
+           int(L if L is not None else config.L))
+    e = _scratch.get(key)
+    if e is None:
+        e = Engine(config, device=key[0], L=key[4])
+        _scratch[key] = e
+    return e
+
+
+def filtrar_z(z, config):
+    """ICM_SLAM.py:22-58 for one scan (a length-B column, already pre-conditioned).  Returns the
+    (n, 4) array [d, angle, d cos, d sin]; an empty scan gives shape (0,) or (0, 4) exactly as the
+    reference does (np.array([]) when fewer than two beams pass the range gate)."""
+    z = np.asarray(z, dtype=np.float64).reshape(-1, 1)
+    e = _scratch_engine(config)
+    e.load(z, np.zeros((3, 1)), np.zeros((2, 1)), precondition=False)
+    e.extract()
+    g = e.get_extraction()
+    if e.n == 0:
+        nvalid = int((_median3(z[:, 0]) < config.rango_laser_max).sum())
+        return np.array([]) if nvalid <= 1 else np.zeros((0, 4))
+    return np.stack([g["d"], g["beam"] * np.pi / 180.0, g["bx"], g["by"]], axis=1)
+
+
+def _median3(z):
+    p = np.concatenate([[0.0], z, [0.0]])
+    return np.median(np.stack([p[:-2], p[1:-1], p[2:]]), axis=0)
+
+
+def calc_cambio(y, mapa_viejo, config=None):
+    """ICM_SLAM.py:490-495 -> [min, max, mean]."""
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    old = np.ascontiguousarray(mapa_viejo, dtype=np.float64)
+    cfg = config if config is not None else ConfigICM.from_values(L=max(int(y.shape[1]), int(old.shape[1]), 1))
+    e = _scratch_engine(cfg, L=max(int(y.shape[1]), int(old.shape[1]), int(cfg.L)))
+    mn, mx, me = e.calc_cambio(y, old)
+    return [mn, mx, me]
+
+
+class Mapa:
+    """ICM_SLAM.py:104-265.  Holds `landmarks_actuales` and `cant_obs_i`; when attached to a solver
+    the state lives in the solver's device handle and these attributes are views of it."""
+
+    def __init__(self, config):
+        self.L = config.L
+        self.cota = config.cota
+        self.dist_thr = config.dist_thr
+        self._config = config
+        self._engine = None
+        self._lact = 0
+        self.clear_obs()
+
+    def _attach(self, engine):
+        self._engine = engine
+        engine.landmarks_actuales = self._lact
+
+    @property
+    def landmarks_actuales(self):
+        return self._engine.landmarks_actuales if self._engine is not None else self._lact
+
+    @landmarks_actuales.setter
+    def landmarks_actuales(self, v):
+        self._lact = int(v)
+        if self._engine is not None:
+            self._engine.landmarks_actuales = int(v)
+
+    @property
+    def cant_obs_i(self):
+        if self._engine is not None:
+            return self._engine.counts()
+        return self._cant
+
+    def clear_obs(self):
+        self._cant = np.zeros(self.L)
+
+    def filtrar(self, mapa, cant_obs_i=None):
+        """ICM_SLAM.py:204-265 on a 2 x L map; counts default to the attached solver's last sweep.
+        Returns the 2 x L buffer (caller slices [:, :landmarks_actuales]) like the reference."""
+        e = self._engine if self._engine is not None else _scratch_engine(self._config)
+        mapa = np.ascontiguousarray(mapa, dtype=np.float64)
+        cnt = np.ascontiguousarray(self.cant_obs_i if cant_obs_i is None else cant_obs_i, dtype=np.float64)
+        n = min(mapa.shape[1], cnt.shape[0], self.landmarks_actuales if cant_obs_i is None else cnt.shape[0])
+        out, cout, Lout = e.filter_map(mapa[:, :n], cnt[:n])
+        self._lact = Lout
+        self._cant = cout
+        return out
+
+
+class ICM_SLAM:
+    """Offline ICM-SLAM solver on one B200.  See the module docstring for the name mapping."""
+
+    def __init__(self, config, x0=""):
+        if isinstance(x0, str) and x0 == "":
+            self.x0 = np.zeros((3, 1))          # sensors.py:19-22
+        else:
+            self.x0 = np.asarray(x0, dtype=np.float64).reshape(3, 1)
+        self.config = config
+        self.odometria = np.array([])
+        self.mediciones = np.array([])
+        self.u = np.array([])
+        self.iterations_flag = False
+        self.debug = False
+        self.mapa_obj = None
+        self.mapa_viejo = None
+        self.positions = None
+        self._engine = Engine(config, device=int(getattr(config, "device", 0)))
+        self._loaded = None
+
+    # ---- data ---------------------------------------------------------------------------------
+    def load_data(self, mapa_obj, mediciones, u, odometria, x0=""):
+        """ICM_SLAM_old.py:249-264.  `mediciones` are pre-conditioned ranges (B x T), `u` 2 x T,
+        `odometria` 3 x T -- the arrays ROS.principal_callback accumulates (ICM_SLAM.py:332-339)."""
+        self.mediciones = mediciones
+        self.u = u
+        self.mapa_obj = copy(mapa_obj)
+        self.odometria = odometria
+        if not (isinstance(x0, str) and x0 == ""):
+            self.x0 = np.asarray(x0, dtype=np.float64).reshape(3, 1)
+        elif odometria is not None and np.size(odometria):
+            pass   # the legacy API keeps zeros; ICM_ROS sets x0 = odometria[:,0] in inicializar_online (sensors.py:61)
+        self._sync_data()
+
+    def _sync_data(self):
+        key = (id(self.mediciones), id(self.u), id(self.odometria), np.shape(self.mediciones))
+        if self._loaded == key:
+            return
+        self._engine.load(self.mediciones, self.odometria, self.u, precondition=False)
+        self._engine.extract()
+        self._loaded = key
+        if self.mapa_obj is None:
+            self.mapa_obj = Mapa(self.config)
+        self.mapa_obj._attach(self._engine)
+
+    # ---- the sweep ------------------------------------------------------------------------------
+    def iterations_process_offline(self, mapa_viejo, x):
+        """sensors.py:125-168: one ICM sweep.  `x` (3 x T) is updated IN PLACE and returned;
+        `mapa_viejo` (2 x L) is not modified; returns (mapa_refinado (2 x L'), x).  The sweep variant
+        is config.schedule / solver / map_view; ('sequential', 'nm', 'running') is the
+        reference's own semantics."""
+        self._sync_data()
+        cfg = self.config
+        mapa_viejo = np.ascontiguousarray(mapa_viejo, dtype=np.float64)
+        xin = x
+        xc = x if (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.c_contiguous) else np.ascontiguousarray(x, dtype=np.float64)
+        st, Lout, mapa = self._engine.sweep(mapa_viejo, xc, np.asarray(self.x0).reshape(3), schedule=getattr(cfg, "schedule", "redblack"),
+                                            solver=getattr(cfg, "solver", "newton"), view=getattr(cfg, "map_view", "prev"))
+        if xc is not xin:
+            xin[...] = xc
+        if st == 1:   # empty first scan: inputs returned unchanged (sensors.py:137-139)
+            return mapa_viejo, xin
+        return np.array(mapa), xin
+
+    itererar = iterations_process_offline          # ICM_SLAM_old.py:336
+
+    def iterar(self, x, N=None):
+        """The driver loop (sensors.py:302-315) with the map resident on the device: N sweeps starting
+        from self.mapa_viejo; returns (mapa_refinado, x)."""
+        self._sync_data()
+        cfg = self.config
+        self._engine.set_map(self.mapa_viejo)
+        self._engine.iterate(x, np.asarray(self.x0).reshape(3), int(cfg.N if N is None else N),
+                             schedule=getattr(cfg, "schedule", "redblack"), solver=getattr(cfg, "solver", "newton"),
+                             view=getattr(cfg, "map_view", "prev"))
+        self.mapa_viejo = self._engine.get_map()
+        return self.mapa_viejo, x
+
+    def inicializar(self, x):
+        """Pass 0 (sensors.py:51-123 / ICM_SLAM_old.py:266-333) is causal and strictly sequential; it is a
+        'next' row of the scope table and not implemented natively yet."""
+        raise NotImplementedError("pass 0 (inicializar / inicializar_online) is not part of the accelerated path yet; "
+                                  "start from odometry and an initial map (see DESIGN.md, scope row f1)")
+
+    inicializar_online = inicializar
+
+    @property
+    def engine(self):
+        return self._engine
+
+    def associations(self):
+        return self._engine.associations()
+
+
+ICM_ROS = ICM_SLAM
+ICM_method = ICM_SLAM

@@ -128,6 +128,23 @@ int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_in, int64_t
                   int64_t ld_x, const double* x0, double* map_out, int32_t cap_out, int64_t ld_map_out,
                   int32_t* L_out, const icmslam_sweep_opts* opts, int32_t memspace);
 
+/* -- the driver loop `for i in range(config.N): mapa_refinado, x = iterations_process_offline(
+ * mapa_viejo, x); mapa_viejo = mapa_refinado` (sensors.py:302-315, example.py:49-53) with the map
+ * kept on the device between sweeps.  icmslam_set_map uploads `mapa_viejo` (2 x L_map) and sets
+ * landmarks_actuales = L_map (sensors.py:102-103); icmslam_iterate runs n_sweeps sweeps, updating
+ * x (3 x T) in place; icmslam_get_map returns the current `mapa_viejo` and its width. */
+int icmslam_set_map(icmslam_handle* h, const double* map, int32_t L_map, int64_t ld, int32_t memspace);
+int icmslam_get_map(icmslam_handle* h, double* map, int32_t cap, int64_t ld, int32_t* L_map, int32_t memspace);
+int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const double* x0, int32_t n_sweeps,
+                    const icmslam_sweep_opts* opts, int32_t memspace);
+
+/* -- instrumentation (no reference counterpart).  Kernel time of the last sweep run with
+ * opts.reserved & 2, from CUDA events on the handle's stream: out2[0] = association (or the fused
+ * sweep kernel), out2[1] = pose kernels (0 when fused), milliseconds.  Launch count = kernels of
+ * this library enqueued since icmslam_create. */
+int icmslam_get_kernel_ms(icmslam_handle* h, double* out2);
+int icmslam_get_launch_count(icmslam_handle* h, int64_t* n);
+
 /* -- results of the last sweep (all optional; mirror what Mapa / actualizar expose).
  * c: association label of every kept observation, CSR order (`c` of ICM_SLAM.py:201).
  * raw map / counts / Lact: the map before Mapa.filtrar (`y`, cant_obs_i, landmarks_actuales at
