@@ -207,8 +207,9 @@ def run_gpu(args, rank, world, local_rank):
     eng.load(d["observations"], d["odometry"], d["velocities"], precondition=True)
     n = eng.extract()
     prep_s = time.time() - t0
-    x_dev = torch.from_numpy(d["x_init"].copy()).to(dev)
+    eng.set_poses(d["x_init"])                 # ICM.positions resident on the device
     eng.set_map(d["map_init"])
+    x_dev = None
     mode = dict(schedule="redblack", solver="newton", view="prev")
     for _ in range(args.warmup):
         eng.iterate(x_dev, x0, 1, **mode)

@@ -1,22 +1,479 @@
-// fused.cuh -- single-kernel (REDBLACK, NEWTON, PREV) sweep.  (stub: generic path only for now)
+// fused.cuh -- the single-pass (REDBLACK, NEWTON, PREV) sweep kernel.
+//
+// One launch does, for every pose t of the trajectory (sensors.py:145-162 restated per SURVEY.md
+// App. A): projection of the scan's kept beams with the sweep's INPUT pose (tras_rot_z,
+// ICM_SLAM.py:465-480), nearest-landmark association against the previous map with the dist_thr
+// gate (Mapa.actualizar Branch B, ICM_SLAM.py:169-182), per-landmark statistics for the landmark
+// update (:191-194), and the pose's conditional minimiser of fun_xn / fun_x (sensors.py:224-282)
+// in red-black order.  Every observation is read from HBM exactly once.
+//
+// Work decomposition (block = 128 threads = 2 "odd" warps + 2 "even" warps, 126 owned poses):
+//   * thread per pose.  The block's contiguous slice of the observation arrays (bx, by) is staged
+//     in shared memory with one TMA bulk copy per array (cp.async.bulk + mbarrier), so the
+//     per-thread walks over a scan's beams hit shared memory, not strided global memory;
+//   * phase A (all threads): project, associate (fastgrid.cuh), accumulate the 12 moment sums the
+//     Newton solve needs and the landmark statistics.  Statistics are summed as int64 fixed point
+//     of (observation - previous landmark) in a block-level shared-memory hash table and flushed
+//     with one global integer atomic per (block, landmark): integer addition is associative, so
+//     the landmark update is bit-reproducible for any block order or GPU count;
+//   * phase B1: the odd warps solve their poses from the OLD even neighbours; phase B2 (after one
+//     __syncthreads) the even warps solve theirs from the NEW odd neighbours held in shared memory.
+//     The odd pose just left of the tile is recomputed locally (halo), so no block waits on another;
+//   * new poses are staged in shared memory and written coalesced; labels go straight to global.
+// Poses are double-buffered (xin -> xout): neighbouring tiles read each other's input poses.
 #pragma once
 #include "common.cuh"
 #include "assoc.cuh"
-#include "pose.cuh"
+#include "fastgrid.cuh"
 
-struct FusedWorkspace {
-    double* d_xin = nullptr;   // 3 x T copy of the sweep's input poses
-    bool available = false;
+#define FS_THREADS 128
+#define FS_HALF 64
+#define FS_OWN 126            // poses owned by a block: tb .. tb+125 (tb even)
+#define FS_XT 132             // pose-tile entries: poses tb-2 .. tb+126 (129 used)
+#define FS_HASH 256           // landmark slots of the block-level statistics table
+#define FS_PROBES 8
+
+struct FusedParams {
+    int T;
+    const int* off;                       // CSR offsets of the kept observations (T + 1)
+    const double* bx; const double* by;   // body-frame observations (n, padded allocation)
+    const double* xin; int64_t ldin;      // 3 x T input poses
+    double* xout; int64_t ldout;          // 3 x T output poses
+    double x0[3];                         // self.x0 (sensors.py:131)
+    const double* inc; int64_t ldinc;     // 3 x T odometry increments (see k_odo_increments)
+    const double* u; int64_t ldu;         // 2 x T controls
+    DevCfg cfg;
+    double thr2_hi;                       // largest s with sqrt_rn(s) <= dist_thr
+    double fix_scale;                     // fixed-point scale of the statistics (power of two)
+    double tol; int maxit;
+    const DevState* st;
+    const FGeom* geom;
+    const int* cell_start; const double2* gpts; const int* gidx;
+    int* c;                               // labels per observation (out)
+    long long* fsum_x; long long* fsum_y; int* cnt;   // per previous-map landmark statistics
+    int* nfar; double* far_sx; double* far_sy;        // per scan: far observations (new label)
+    int obs_cap;                          // shared-memory capacity in observations
+    unsigned long long* iters;
 };
 
-static void fused_free(FusedWorkspace& fw)
+// odometry increments, sweep-invariant: D_t = Rota(o_t.theta) (o_{t+1}.xy - o_t.xy), dtheta_t
+// (sensors.py:236-238, :250-253).  inc[:, t] for t < T-1; the last column is zero.
+__global__ void k_odo_increments(const double* __restrict__ odo, int64_t ldo, int T, double* __restrict__ inc, int64_t ldi)
 {
-    if (fw.d_xin) { cudaFree(fw.d_xin); fw.d_xin = nullptr; }
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    double dx = 0.0, dy = 0.0, dth = 0.0;
+    if (t + 1 < T) {
+        double s, c;
+        sincos(odo[2 * ldo + t], &s, &c);
+        const double vx = odo[t + 1] - odo[t], vy = odo[ldo + t + 1] - odo[ldo + t];
+        dx = c * vx + s * vy;
+        dy = -s * vx + c * vy;
+        dth = odo[2 * ldo + t + 1] - odo[2 * ldo + t];
+    }
+    inc[t] = dx; inc[ldi + t] = dy; inc[2 * ldi + t] = dth;
 }
 
-static int fused_sweep(FusedWorkspace&, cudaStream_t, const DevCfg&, const PoseArrays&, const double*, const double*, int64_t,
-                       DevState*, const int*, const double*, const double*, const int*, int*, int*, double*, double*, int*,
-                       double, int, unsigned long long*, char*, size_t)
+__device__ __forceinline__ double entrepi_fast(double a)
 {
-    return ICMSLAM_ERR_UNSUPPORTED;
+    return (fabs(a) <= ICM_PI) ? a : entrepi(a);
+}
+
+// sin/cos of a small increment (|d| <= 0.125): Taylor to d^11 / d^10, error < 1e-18
+__device__ __forceinline__ void sincos_small(double d, double& s, double& c)
+{
+    const double z = d * d;
+    s = d * fma(z, fma(z, fma(z, fma(z, fma(z, -2.5052108385441719e-08, 2.7557319223985893e-06), -1.9841269841269841e-04),
+                              8.3333333333333332e-03), -1.6666666666666666e-01), 1.0);
+    c = fma(z, fma(z, fma(z, fma(z, fma(z, -2.7557319223985888e-07, 2.4801587301587302e-05), -1.3888888888888889e-03),
+                          4.1666666666666664e-02), -0.5), 1.0);
+}
+
+struct Mom {   // moment sums of one pose's observations (landmark coordinates relative to the origin)
+    double n, Bx, By, Bxx, Byy, Bxy, Yx, Yy, Mxx, Mxy, Myx, Myy;
+};
+
+struct PoseIn {
+    double ax, ay, ath, sa, ca;     // x_{t-1} and sin/cos of its heading
+    double bx, by, bth;             // x_{t+1}
+    double uav, uaw, ucv, ucw;      // u_{t-1}, u_t
+    double D0x, D0y, dth0;          // odometry increment t-1 -> t
+    double D1x, D1y, dth1;          // odometry increment t -> t+1
+    int has_next;
+};
+
+// Exact conditional minimiser (same reduced 1-D Newton as newton_moments in pose.cuh, with the
+// odometry rotations and the neighbour's sin/cos supplied, the start heading's sin/cos supplied,
+// and the heading's sin/cos carried through the iterations by small-angle rotation).
+__device__ __forceinline__ int newton_lean(const DevCfg& cfg, const PoseIn& P, const Mom& M, double ox, double oy, double th,
+                                           double s, double c, double tol, int maxit, double out[3], double& s_out, double& c_out)
+{
+    const double dt = cfg.dt, k = cfg.kod;
+    const double gax = (P.ax - ox) + dt * (P.ca * P.uav), gay = (P.ay - oy) + dt * (P.sa * P.uav), th_ga = P.ath + dt * P.uaw;
+    const double e0x = (P.ax - ox) + (P.ca * P.D0x - P.sa * P.D0y);
+    const double e0y = (P.ay - oy) + (P.sa * P.D0x + P.ca * P.D0y);
+    const double hn = P.has_next ? 1.0 : 0.0;
+    const double bxp = hn * (P.bx - ox), byp = hn * (P.by - oy);
+    const double D1x = hn * P.D1x, D1y = hn * P.D1y;
+    const double dv = hn * dt * P.ucv;
+    const double Sx = cfg.r1 + k + M.n * cfg.q1 + hn * (cfg.r1 + k), Sy = cfg.r2 + k + M.n * cfg.q2 + hn * (cfg.r2 + k);
+    const double iSx = 1.0 / Sx, iSy = 1.0 / Sy;
+    const double KAx = cfg.r1 * gax + k * e0x + cfg.q1 * M.Yx + (cfg.r1 + k) * bxp;
+    const double KAy = cfg.r2 * gay + k * e0y + cfg.q2 * M.Yy + (cfg.r2 + k) * byp;
+    const double ang2 = (2.0 * cfg.r3 + 2.0 * k) * (1.0 + hn);
+    const double Pxc = (cfg.r1 * dv + k * D1x) + cfg.q1 * M.By;
+    const double Pxs = cfg.q1 * M.Bx - k * D1y;
+    const double Pys = (cfg.r2 * dv + k * D1x) + cfg.q2 * M.By;
+    const double Pyc = k * D1y - cfg.q2 * M.Bx;
+    const double c3 = P.dth0 + P.ath;
+    const double c4 = P.dth1 - P.bth;
+    const double wb = dt * P.ucw - P.bth;
+    const double dByx = M.Byy - M.Bxx;
+    int it = 0;
+    for (;;) {
+        const double ss = s * s, cc = c * c, sc = s * c;
+        const double Ax = KAx - c * Pxc - s * Pxs, Ax1 = s * Pxc - c * Pxs, Ax2 = KAx - Ax;
+        const double Ay = KAy - s * Pys - c * Pyc, Ay1 = -c * Pys + s * Pyc, Ay2 = KAy - Ay;
+        // motion / odometry terms towards t+1 (all zero when !has_next: dv = D1 = bxp = 0 and hn scales them)
+        const double r1x = c * D1x - s * D1y, r1y = s * D1x + c * D1y;     // Rota(th)^T D1
+        const double f2 = bxp - dv * c, f21 = dv * s;
+        const double f4 = bxp - r1x;
+        const double h2 = byp - dv * s, h21 = -dv * c;
+        const double h4 = byp - r1y;
+        double Cx1 = hn * (cfg.r1 * f2 * f21 + k * f4 * r1y);
+        double Cx2 = hn * (cfg.r1 * (f21 * f21 + f2 * (dv * c)) + k * (r1y * r1y + f4 * r1x));
+        double Cy1 = hn * (cfg.r2 * h2 * h21 - k * h4 * r1x);
+        double Cy2 = hn * (cfg.r2 * (h21 * h21 + h2 * (dv * s)) + k * (r1x * r1x + h4 * r1y));
+        // observation sums with w = Rot(th - pi/2) b = (bx s + by c, -bx c + by s)
+        const double Swxwy = sc * dByx + (ss - cc) * M.Bxy;
+        const double Swxx = ss * M.Bxx + 2.0 * sc * M.Bxy + cc * M.Byy;
+        const double Swyy = cc * M.Bxx - 2.0 * sc * M.Bxy + ss * M.Byy;
+        const double Yxwy = -c * M.Mxx + s * M.Mxy, Yxwx = s * M.Mxx + c * M.Mxy;
+        const double Yywx = s * M.Myx + c * M.Myy, Yywy = -c * M.Myx + s * M.Myy;
+        Cx1 += cfg.q1 * (Yxwy - Swxwy);
+        Cx2 += cfg.q1 * (Swyy + Yxwx - Swxx);
+        Cy1 += cfg.q2 * (-Yywx + Swxwy);
+        Cy2 += cfg.q2 * (Swxx + Yywy - Swyy);
+        double ang1 = 2.0 * cfg.r3 * entrepi_fast(th - th_ga) - 2.0 * k * entrepi_fast(c3 - th);
+        if (P.has_next) ang1 += 2.0 * cfg.r3 * entrepi_fast(th + wb) + 2.0 * k * entrepi_fast(c4 + th);
+        const double p1 = 2.0 * (Cx1 - Ax * Ax1 * iSx + Cy1 - Ay * Ay1 * iSy) + ang1;
+        double p2 = 2.0 * (Cx2 - (Ax1 * Ax1 + Ax * Ax2) * iSx + Cy2 - (Ay1 * Ay1 + Ay * Ay2) * iSy) + ang2;
+        if (!(p2 > 0.0)) p2 = ang2;
+        const double dth = -p1 / p2;
+        th += dth;
+        ++it;
+        if (fabs(dth) <= 0.125) {
+            double sd, cd;
+            sincos_small(dth, sd, cd);
+            const double s2 = s * cd + c * sd;
+            c = c * cd - s * sd;
+            s = s2;
+        } else {
+            sincos(th, &s, &c);
+        }
+        const bool done = fabs(dth) <= tol || it >= maxit;
+        if (__all_sync(__activemask(), done)) break;
+    }
+    out[0] = (KAx - c * Pxc - s * Pxs) * iSx + ox;
+    out[1] = (KAy - s * Pys - c * Pyc) * iSy + oy;
+    out[2] = th;
+    s_out = s; c_out = c;
+    return it;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct __align__(16) FusedSmemFixed {
+    double xs[3][FS_XT];        // input poses tb-2 .. tb+126
+    double sn[FS_XT], cs[FS_XT];   // sin/cos of the input headings (later: of the new odd headings)
+    double xn[3][FS_XT];        // new poses (same indexing)
+    double inc[3][FS_XT];       // odometry increments t = tb-2 ..
+    double u[2][FS_XT];
+    int off[FS_XT];             // off[tb-1 .. tb+127] clamped, at index li = t - (tb-2)
+    int hkey[FS_HASH];
+    int hcnt[FS_HASH];
+    long long hsx[FS_HASH], hsy[FS_HASH];
+    unsigned long long mbar;
+    int nfar_scans;
+};
+
+__device__ __forceinline__ void stat_add(FusedSmemFixed& S, const FusedParams& p, int arg, double rdx, double rdy, int rn)
+{
+    const long long vx = __double2ll_rn(rdx * p.fix_scale), vy = __double2ll_rn(rdy * p.fix_scale);
+    unsigned h = ((unsigned)arg * 2654435761u) >> 24;      // FS_HASH = 256
+    for (int q = 0; q < FS_PROBES; ++q) {
+        int key = ((volatile int*)S.hkey)[h];
+        if (key != arg && key == -1) {
+            int prev = atomicCAS(&S.hkey[h], -1, arg);
+            key = (prev == -1) ? arg : prev;
+        }
+        if (key == arg) {
+            atomicAdd((unsigned long long*)&S.hsx[h], (unsigned long long)vx);
+            atomicAdd((unsigned long long*)&S.hsy[h], (unsigned long long)vy);
+            atomicAdd(&S.hcnt[h], rn);
+            return;
+        }
+        h = (h + 1) & (FS_HASH - 1);
+    }
+    atomicAdd((unsigned long long*)(p.fsum_x + arg), (unsigned long long)vx);   // table crowded: go to global directly
+    atomicAdd((unsigned long long*)(p.fsum_y + arg), (unsigned long long)vy);
+    atomicAdd(p.cnt + arg, rn);
+}
+
+template <bool STAGED>
+__device__ __forceinline__ void fused_phase_a(const FusedParams& p, FusedSmemFixed& S, const FGrid& G, const double* sbx, const double* sby,
+                                              int obase, int o, int e, double px, double py, double st, double ct, bool owned,
+                                              Mom& M, int& nfar, double& fsx, double& fsy, double& FBx, double& FBy)
+{
+    int run_arg = -1, run_n = 0;
+    double run_dx = 0.0, run_dy = 0.0;
+    for (int i = o; i < e; ++i) {
+        double bx, by;
+        if (STAGED) { bx = sbx[i - obase]; by = sby[i - obase]; }
+        else { bx = __ldg(p.bx + i); by = __ldg(p.by + i); }
+        // tras_rot_z: numpy's matmul order, acc = a0*b0; acc = fma(a1, b1, acc); + translation
+        const double wx = add_rn(__fma_rn(by, -st, mul_rn(bx, ct)), px);
+        const double wy = add_rn(__fma_rn(by, ct, mul_rn(bx, st)), py);
+        double best, lx, ly;
+        const int bk = fgrid_nearest(G, wx, wy, best, lx, ly);
+        M.n += 1.0;
+        M.Bx += bx; M.By += by;
+        M.Bxx = fma(bx, bx, M.Bxx); M.Byy = fma(by, by, M.Byy); M.Bxy = fma(bx, by, M.Bxy);
+        int lab;
+        if (bk < 0 || best > p.thr2_hi) {        // amin > dist_thr (ICM_SLAM.py:172)
+            lab = -1;
+            ++nfar;
+            fsx += wx; fsy += wy;               // np.sum(obs[c==i], axis=0): row order
+            FBx += bx; FBy += by;
+        } else {
+            lab = __ldg(G.idx + bk);
+            const double yx = lx - px, yy = ly - py;
+            M.Yx += yx; M.Yy += yy;
+            M.Mxx = fma(yx, bx, M.Mxx); M.Mxy = fma(yx, by, M.Mxy);
+            M.Myx = fma(yy, bx, M.Myx); M.Myy = fma(yy, by, M.Myy);
+            if (owned) {
+                if (lab != run_arg) {
+                    if (run_n) stat_add(S, p, run_arg, run_dx, run_dy, run_n);
+                    run_arg = lab; run_n = 0; run_dx = 0.0; run_dy = 0.0;
+                }
+                run_dx += wx - lx; run_dy += wy - ly; ++run_n;
+            }
+        }
+        if (owned) p.c[i] = lab;
+    }
+    if (run_n) stat_add(S, p, run_arg, run_dx, run_dy, run_n);
+}
+
+template <bool STAGED>
+__global__ void __launch_bounds__(FS_THREADS, 4)
+k_sweep_fused(const FusedParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FusedSmemFixed& S = *reinterpret_cast<FusedSmemFixed*>(smem_raw);
+    double* sbx = reinterpret_cast<double*>(smem_raw + sizeof(FusedSmemFixed));
+    double* sby = sbx + p.obs_cap + 2;
+
+    const int tid = threadIdx.x;
+    const int tb = blockIdx.x * FS_OWN;
+    const int T = p.T;
+    // ---- tile loads ---------------------------------------------------------------------------
+    for (int li = tid; li < FS_XT; li += FS_THREADS) {
+        const int t = tb - 2 + li;
+        const bool ok = t >= 0 && t < T;
+        for (int r = 0; r < 3; ++r) {
+            S.xs[r][li] = ok ? p.xin[r * p.ldin + t] : 0.0;
+            S.inc[r][li] = ok ? p.inc[r * p.ldinc + t] : 0.0;
+        }
+        S.u[0][li] = ok ? p.u[t] : 0.0;
+        S.u[1][li] = ok ? p.u[p.ldu + t] : 0.0;
+        S.off[li] = p.off[min(max(t, 0), T)];
+    }
+    for (int h = tid; h < FS_HASH; h += FS_THREADS) { S.hkey[h] = -1; S.hcnt[h] = 0; S.hsx[h] = 0; S.hsy[h] = 0; }
+    if (tid == 0) S.nfar_scans = 0;
+    const int t_first = max(tb - 1, 0), t_last = min(tb + FS_OWN - 1, T - 1);     // scans processed by this block
+    const int obase_raw = p.off[t_first], oend = p.off[t_last + 1];
+    const int obase = obase_raw & ~1;                                            // 16-byte aligned source
+    const bool staged = STAGED && (oend - obase) <= p.obs_cap;
+    if (STAGED) {
+        if (tid == 0) {
+            const uint32_t mb = smem_u32(&S.mbar);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    __syncthreads();
+    if (STAGED && staged && tid == 0) {
+        const uint32_t mb = smem_u32(&S.mbar);
+        const uint32_t bytes = (uint32_t)(((oend - obase + 1) & ~1) * 8);
+        if (bytes > 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(2u * bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(sbx)), "l"(p.bx + obase), "r"(bytes), "r"(mb) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(sby)), "l"(p.by + obase), "r"(bytes), "r"(mb) : "memory");
+        } else {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb) : "memory");
+        }
+    }
+    // ---- thread -> pose --------------------------------------------------------------------------
+    const int grp = tid >> 6, j = tid & (FS_HALF - 1);          // grp 0: odd poses, grp 1: even poses
+    const int t = grp == 0 ? tb - 1 + 2 * j : tb + 2 * j;
+    const int li = t - (tb - 2);
+    const bool spare = grp == 1 && j == FS_HALF - 1;            // even lane 63 (pose tb+126 belongs to the next tile)
+    const bool valid = !spare && t >= 0 && t < T;
+    const bool owned = valid && !(grp == 0 && j == 0);          // the halo pose tb-1 is recomputed, not owned
+    double px = 0.0, py = 0.0, th = 0.0, st = 0.0, ct = 1.0;
+    if (valid) {
+        if (t == 0) { px = p.x0[0]; py = p.x0[1]; th = p.x0[2]; }
+        else { px = S.xs[0][li]; py = S.xs[1][li]; th = S.xs[2][li]; }
+        sincos(sub_rn(th, ICM_HALFPI), &st, &ct);               // make_rot: cos/sin of (theta - pi/2)
+        double sh, ch;                                           // sin/cos of the heading itself, for the neighbours
+        if (t == 0) sincos(S.xs[2][li], &sh, &ch);               // x[:,0] may differ from x0
+        else { sh = ct; ch = -st; }
+        S.sn[li] = sh; S.cs[li] = ch;
+    } else if (spare && tb - 2 >= 0) {                          // heading of the pose left of the halo
+        double sh, ch;
+        sincos(S.xs[2][0], &sh, &ch);
+        S.sn[0] = sh; S.cs[0] = ch;
+    }
+    // ---- phase A ---------------------------------------------------------------------------------
+    FGrid G;
+    G.g = *p.geom;
+    G.cell_start = p.cell_start; G.pts = p.gpts; G.idx = p.gidx;
+    const bool have_map = p.st->lsearch > 0;
+    Mom M;
+    M.n = M.Bx = M.By = M.Bxx = M.Byy = M.Bxy = M.Yx = M.Yy = M.Mxx = M.Mxy = M.Myx = M.Myy = 0.0;
+    int nfar = 0;
+    double fsx = 0.0, fsy = 0.0, FBx = 0.0, FBy = 0.0;
+    int o = 0, e = 0;
+    if (valid) { o = S.off[li]; e = S.off[li + 1]; }
+    if (!have_map) { G.g.nx = 1; G.g.ny = 1; G.cell_start = p.cell_start; }   // (cell_start is all zero then: no candidates)
+    if (STAGED && staged) {
+        const uint32_t mb = smem_u32(&S.mbar);
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}"
+                         : "=r"(done) : "r"(mb), "r"(0u) : "memory");
+        }
+        fused_phase_a<true>(p, S, G, sbx, sby, obase, o, e, px, py, st, ct, owned, M, nfar, fsx, fsy, FBx, FBy);
+    } else {
+        fused_phase_a<false>(p, S, G, sbx, sby, obase, o, e, px, py, st, ct, owned, M, nfar, fsx, fsy, FBx, FBy);
+    }
+    if (owned) {
+        p.nfar[t] = nfar;
+        if (nfar > 0) { p.far_sx[t] = fsx; p.far_sy[t] = fsy; atomicAdd(&S.nfar_scans, 1); }
+    }
+    if (nfar > 0) {   // far observations see the mean of the scan's new label (PREV view, raw = sum / k)
+        const double yx = fsx / (double)nfar - px, yy = fsy / (double)nfar - py;
+        M.Yx += (double)nfar * yx; M.Yy += (double)nfar * yy;
+        M.Mxx = fma(yx, FBx, M.Mxx); M.Mxy = fma(yx, FBy, M.Mxy);
+        M.Myx = fma(yy, FBx, M.Myx); M.Myy = fma(yy, FBy, M.Myy);
+    }
+    __syncthreads();     // sn/cs of all input headings visible
+    // ---- phase B: red (odd) then black (even) -----------------------------------------------------
+    unsigned long long my_iters = 0;
+    for (int phase = 0; phase < 2; ++phase) {
+        if (phase == grp && valid) {
+            double res[3], s_new = 0.0, c_new = 1.0;
+            if (t == 0) {
+                res[0] = S.xs[0][li]; res[1] = S.xs[1][li]; res[2] = S.xs[2][li];
+            } else {
+                // neighbours: old poses for the odd phase, new (odd) poses for the even phase
+                double (*X)[FS_XT] = phase == 0 ? S.xs : S.xn;
+                const bool has_next = t + 1 < T;
+                if (e == o) {     // sensors.py:147-151
+                    for (int r = 0; r < 3; ++r) {
+                        const double prev = (t == 1) ? p.x0[r] : X[r][li - 1];
+                        res[r] = (prev + X[r][li + 1]) / 2.0;
+                    }
+                    sincos(res[2], &s_new, &c_new);
+                } else {
+                    PoseIn P;
+                    P.ax = X[0][li - 1]; P.ay = X[1][li - 1]; P.ath = X[2][li - 1];
+                    P.sa = S.sn[li - 1]; P.ca = S.cs[li - 1];
+                    P.bx = has_next ? X[0][li + 1] : 0.0; P.by = has_next ? X[1][li + 1] : 0.0; P.bth = has_next ? X[2][li + 1] : 0.0;
+                    P.uav = S.u[0][li - 1]; P.uaw = S.u[1][li - 1];
+                    P.ucv = S.u[0][li]; P.ucw = S.u[1][li];
+                    P.D0x = S.inc[0][li - 1]; P.D0y = S.inc[1][li - 1]; P.dth0 = S.inc[2][li - 1];
+                    P.D1x = S.inc[0][li]; P.D1y = S.inc[1][li]; P.dth1 = S.inc[2][li];
+                    P.has_next = has_next ? 1 : 0;
+                    // start at the pose's own input heading: its sin/cos are already known (ct, -st)
+                    const int it = newton_lean(p.cfg, P, M, px, py, th, ct, -st, p.tol, p.maxit, res, s_new, c_new);
+                    my_iters += (unsigned long long)it;
+                }
+            }
+            S.xn[0][li] = res[0]; S.xn[1][li] = res[1]; S.xn[2][li] = res[2];
+            if (phase == 0) { S.sn[li] = s_new; S.cs[li] = c_new; }   // (old odd headings are no longer needed)
+        }
+        __syncthreads();
+    }
+    if (p.iters) {
+        my_iters = (unsigned long long)warp_sum_i((int)my_iters);
+        if ((tid & 31) == 0 && my_iters) atomicAdd(p.iters, my_iters);
+    }
+    // ---- outputs ----------------------------------------------------------------------------------
+    const int n_own = min(FS_OWN, T - tb);
+    for (int q = tid; q < 3 * n_own; q += FS_THREADS) {
+        const int r = q / n_own, k = q - r * n_own;
+        p.xout[r * p.ldout + tb + k] = S.xn[r][k + 2];
+    }
+    for (int h = tid; h < FS_HASH; h += FS_THREADS) {
+        const int key = S.hkey[h];
+        if (key >= 0 && S.hcnt[h] > 0) {
+            atomicAdd((unsigned long long*)(p.fsum_x + key), (unsigned long long)S.hsx[h]);
+            atomicAdd((unsigned long long*)(p.fsum_y + key), (unsigned long long)S.hsy[h]);
+            atomicAdd(p.cnt + key, S.hcnt[h]);
+        }
+    }
+}
+
+static size_t fused_smem_bytes(int obs_cap) { return sizeof(FusedSmemFixed) + (size_t)2 * (obs_cap + 2) * 8 + 16; }
+
+// ---- after the fused kernel: new labels ------------------------------------------------------------
+// label(t) = lact0 + (number of earlier scans with a far observation) (ICM_SLAM.py:174-182, one new
+// label per scan).  Thread per scan; only scans with far observations do any work.
+__global__ void __launch_bounds__(256)
+k_fused_labels(int T, const int* __restrict__ off, DevState* st, const int* __restrict__ nfar, const int* __restrict__ far_prefix,
+               const double* __restrict__ far_sx, const double* __restrict__ far_sy, int Lcap, int* __restrict__ c,
+               double* __restrict__ raw_x, double* __restrict__ raw_y, int* __restrict__ cnt)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int lact0 = st->lact0;
+    const int k = nfar[t];
+    if (t == T - 1) {
+        const int total = far_prefix[t] + (k > 0 ? 1 : 0);
+        st->n_far_scans = total;
+        st->raw_l = lact0 + total;
+        if (lact0 + total > Lcap) st->status = ST_LABEL_CAP;   // IndexError at ICM_SLAM.py:191
+    }
+    if (k == 0) return;
+    const int label = lact0 + far_prefix[t];
+    if (label >= Lcap) return;
+    raw_x[label] = far_sx[t] / (double)k;
+    raw_y[label] = far_sy[t] / (double)k;
+    cnt[label] = k;
+    for (int i = off[t]; i < off[t + 1]; ++i)
+        if (c[i] < 0) c[i] = label;
+}
+
+// raw map of the previous-map landmarks from the fixed-point statistics + keep flags for all labels;
+// clears the statistics for the next sweep.
+__global__ void __launch_bounds__(256)
+k_fused_means(const DevState* st, long long* __restrict__ fsum_x, long long* __restrict__ fsum_y, const int* __restrict__ cnt,
+              const double* __restrict__ map_x, const double* __restrict__ map_y, double inv_scale, double cota,
+              double* __restrict__ raw_x, double* __restrict__ raw_y, int* __restrict__ flag, int Lcap)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= Lcap) return;
+    const int raw_l = st->raw_l, ls = st->lsearch;
+    const int k = l < raw_l ? cnt[l] : 0;
+    if (l < ls) {
+        raw_x[l] = k > 0 ? map_x[l] + ((double)fsum_x[l] * inv_scale) / (double)k : 0.0;
+        raw_y[l] = k > 0 ? map_y[l] + ((double)fsum_y[l] * inv_scale) / (double)k : 0.0;
+    } else if (!(l < raw_l && k > 0)) {
+        raw_x[l] = 0.0; raw_y[l] = 0.0;
+    }
+    fsum_x[l] = 0; fsum_y[l] = 0;
+    flag[l] = (l < raw_l && !((double)k < cota)) ? 1 : 0;      // ICM_SLAM.py:232-236
 }

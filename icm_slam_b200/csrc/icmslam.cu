@@ -14,6 +14,7 @@
 #include "extract.cuh"
 #include "pose.cuh"
 #include "mapfilter.cuh"
+#include "fastgrid.cuh"
 #include "fused.cuh"
 
 #define MAX_CELLS (1 << 22)
@@ -57,10 +58,23 @@ struct icmslam_handle {
     bool lact_dirty = false;
     void* d_cub = nullptr;
     size_t cub_bytes = 0;
-    FusedWorkspace fw;
+    // fused (REDBLACK, NEWTON, PREV) path
+    bool fused_ok = false;
+    double *d_inc = nullptr /*3 x T odometry increments*/, *d_x2 = nullptr /*3 x T, pose double buffer*/;
+    double *d_far_sx = nullptr, *d_far_sy = nullptr;
+    long long *d_fsum_x = nullptr, *d_fsum_y = nullptr;
+    int fg_cells = 0;            // cell budget of the fast grid (host constant)
+    int *d_fg_cnt = nullptr, *d_fg_start = nullptr, *d_fg_idx = nullptr, *d_fg_cell = nullptr;
+    double2* d_fg_pts = nullptr;
+    FGeom* d_fg_geom = nullptr;
+    unsigned long long* d_bb = nullptr;
+    int obs_cap = 0, max_tile_obs = 0;
+    size_t fused_smem = 0;
+    double thr2_hi = 0.0, fix_scale = 1.0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool timed_fused = false;
     int64_t n_launch = 0;   // kernels of this library launched so far (cub's not counted)
+    int x_cur = 0;          // which pose buffer (d_x / d_x2) holds the resident poses
 };
 
 #define CK(call)                                                                                         \
@@ -107,7 +121,8 @@ static void free_dataset(icmslam_handle* h)
     DFREE(h->d_off); DFREE(h->d_beam); DFREE(h->d_scan_of); DFREE(h->d_d); DFREE(h->d_bx); DFREE(h->d_by);
     DFREE(h->d_c); DFREE(h->d_keys_out); DFREE(h->d_iota); DFREE(h->d_sorted); DFREE(h->d_seen_x); DFREE(h->d_seen_y);
     DFREE(h->d_nfar); DFREE(h->d_flag); DFREE(h->d_prefix); DFREE(h->d_x);
-    fused_free(h->fw);
+    DFREE(h->d_inc); DFREE(h->d_x2); DFREE(h->d_far_sx); DFREE(h->d_far_sy);
+    h->fused_ok = false;
     h->extracted = false;
     h->n = 0;
 }
@@ -124,6 +139,8 @@ extern "C" int icmslam_destroy(icmslam_handle* h)
     DFREE(h->d_map_in); DFREE(h->d_map_out); DFREE(h->d_tmp_a); DFREE(h->d_tmp_b);
     DFREE(h->d_cell_start); DFREE(h->d_cell_fill); DFREE(h->d_cell_id); DFREE(h->d_gidx); DFREE(h->d_glx); DFREE(h->d_gly);
     DFREE(h->d_st); DFREE(h->d_cub);
+    DFREE(h->d_fsum_x); DFREE(h->d_fsum_y); DFREE(h->d_fg_cnt); DFREE(h->d_fg_start); DFREE(h->d_fg_idx); DFREE(h->d_fg_cell);
+    DFREE(h->d_fg_pts); DFREE(h->d_fg_geom); DFREE(h->d_bb);
     if (h->h_st) cudaFreeHost(h->h_st);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
@@ -200,6 +217,28 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     if (e == cudaSuccess) e = dalloc(&h->d_gidx, L);
     if (e == cudaSuccess) e = dalloc(&h->d_glx, L);
     if (e == cudaSuccess) e = dalloc(&h->d_gly, L);
+    h->fg_cells = (int)(4 * L > 4096 ? 4 * L : 4096);
+    if (e == cudaSuccess) e = dalloc(&h->d_fsum_x, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_fsum_y, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_fg_cnt, (size_t)h->fg_cells + 2);
+    if (e == cudaSuccess) e = dalloc(&h->d_fg_start, (size_t)h->fg_cells + 2);
+    if (e == cudaSuccess) e = dalloc(&h->d_fg_idx, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_fg_cell, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_fg_pts, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_fg_geom, 1);
+    if (e == cudaSuccess) e = dalloc(&h->d_bb, 4);
+    if (e == cudaSuccess) e = cudaMemset(h->d_fsum_x, 0, L * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMemset(h->d_fsum_y, 0, L * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMemset(h->d_fg_cnt, 0, ((size_t)h->fg_cells + 2) * sizeof(int));
+    {   // gate and fixed-point scale of the fused path
+        const double thr = cfg->dist_thr;
+        double s2 = thr * thr;
+        while (sqrt(nextafter(s2, INFINITY)) <= thr) s2 = nextafter(s2, INFINITY);
+        while (s2 > 0.0 && sqrt(s2) > thr) s2 = nextafter(s2, -INFINITY);
+        h->thr2_hi = s2;
+        int ex = thr > 1.0 ? ilogb(thr) + 1 : 0;
+        h->fix_scale = ldexp(1.0, 40 - ex);
+    }
     if (e == cudaSuccess) e = dalloc(&h->d_st, 1);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_st, sizeof(DevState));
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
@@ -248,6 +287,10 @@ extern "C" int icmslam_load(icmslam_handle* h, const double* scans, int32_t B, i
     CK(dalloc(&h->d_nfar, (size_t)T + 1));
     CK(dalloc(&h->d_flag, (size_t)T + 1));
     CK(dalloc(&h->d_prefix, (size_t)T + 1));
+    CK(dalloc(&h->d_inc, (size_t)3 * T));
+    CK(dalloc(&h->d_x2, (size_t)3 * T));
+    CK(dalloc(&h->d_far_sx, (size_t)T));
+    CK(dalloc(&h->d_far_sy, (size_t)T));
     const size_t w = (size_t)T * sizeof(double);
     CK(cudaMemcpy2DAsync(h->d_scans, w, scans, (size_t)ld_scans * sizeof(double), w, B, cudaMemcpyDefault, h->stream));
     CK(cudaMemcpy2DAsync(h->d_odo, w, odo, (size_t)ld_odo * sizeof(double), w, 3, cudaMemcpyDefault, h->stream));
@@ -258,6 +301,8 @@ extern "C" int icmslam_load(icmslam_handle* h, const double* scans, int32_t B, i
         cb[i] = cos_tab ? cos_tab[i] : cos(ang[i]);
         sb[i] = sin_tab ? sin_tab[i] : sin(ang[i]);
     }
+    k_odo_increments<<<nblk(T, 256), 256, 0, h->stream>>>(h->d_odo, T, T, h->d_inc, T);
+    CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->d_ang, ang.data(), B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_cos, cb.data(), B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_sin, sb.data(), B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -303,7 +348,9 @@ extern "C" int icmslam_extract(icmslam_handle* h)
     const size_t n = (size_t)h->n;
     DFREE(h->d_beam); DFREE(h->d_scan_of); DFREE(h->d_d); DFREE(h->d_bx); DFREE(h->d_by);
     DFREE(h->d_c); DFREE(h->d_keys_out); DFREE(h->d_iota); DFREE(h->d_sorted); DFREE(h->d_seen_x); DFREE(h->d_seen_y);
-    CK(dalloc(&h->d_beam, n)); CK(dalloc(&h->d_scan_of, n)); CK(dalloc(&h->d_d, n)); CK(dalloc(&h->d_bx, n)); CK(dalloc(&h->d_by, n));
+    CK(dalloc(&h->d_beam, n)); CK(dalloc(&h->d_scan_of, n)); CK(dalloc(&h->d_d, n)); CK(dalloc(&h->d_bx, n + 2)); CK(dalloc(&h->d_by, n + 2));
+    CK(cudaMemsetAsync(h->d_bx, 0, (n + 2) * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->d_by, 0, (n + 2) * sizeof(double), h->stream));
     CK(dalloc(&h->d_c, n));
     k_extract<2><<<blocks, EX_THREADS, smem, h->stream>>>(h->d_scans, B, T, T, h->d_cos, h->d_sin, h->dcfg, h->precondition,
                                                           nwords, d_masks, nullptr, h->d_off, h->d_beam, h->d_d, h->d_bx,
@@ -313,7 +360,27 @@ extern "C" int icmslam_extract(icmslam_handle* h)
     cudaFree(d_masks);
     cudaFree(d_counts);
     h->extracted = true;
-    fused_free(h->fw);
+    {   // shared-memory budget of the fused kernel: observations of one tile (FS_OWN poses + the halo scan)
+        int mx = 0;
+        for (int tb = 0; tb < T; tb += FS_OWN) {
+            int t0 = tb > 0 ? tb - 1 : 0, t1 = tb + FS_OWN < T ? tb + FS_OWN : T;
+            int m = off[t1] - (off[t0] & ~1);
+            if (m > mx) mx = m;
+        }
+        h->max_tile_obs = mx;
+        const size_t per_block = (size_t)(232448 - 3 * 1024) / 3;            // aim at >= 3 blocks per SM
+        int cap3 = (int)((per_block - sizeof(FusedSmemFixed) - 16) / 16) - 2;
+        const char* env = getenv("ICMSLAM_OBS_CAP");
+        if (env && atoi(env) > 0) cap3 = atoi(env);
+        const int cap_max = (int)((232448 - sizeof(FusedSmemFixed) - 16) / 16) - 2;
+        if (cap3 > cap_max) cap3 = cap_max;
+        h->obs_cap = mx < cap3 ? mx : cap3;
+        if (h->obs_cap < 2) h->obs_cap = 2;
+        h->obs_cap = (h->obs_cap + 1) & ~1;
+        h->fused_smem = fused_smem_bytes(h->obs_cap);
+        CK(cudaFuncSetAttribute(k_sweep_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
+        h->fused_ok = true;
+    }
     return ICMSLAM_OK;
 }
 
@@ -479,11 +546,36 @@ static void default_opts(icmslam_sweep_opts& o, const icmslam_sweep_opts* opts)
     if (!(o.newton_tol > 0.0)) o.newton_tol = 1e-10;
 }
 
+// fast grid (fastgrid.cuh) over the first *n_ptr points of (px, py).  cell_cnt is all zero on entry and
+// on exit (the fill pass counts it back down), so no per-build memset is needed.
+static int build_fgrid(icmslam_handle* h, const double* px, const double* py, const int* n_ptr, int n_cap)
+{
+    cudaStream_t s = h->stream;
+    k_fgrid_bbox_reset<<<1, 1, 0, s>>>(h->d_bb);
+    CK(cudaGetLastError());
+    int nb = nblk(n_cap, 256);
+    if (nb > 148 * 2) nb = 148 * 2;
+    k_fgrid_bbox<<<nb, 256, 0, s>>>(px, py, n_ptr, h->d_bb);
+    CK(cudaGetLastError());
+    k_fgrid_geom<<<1, 1, 0, s>>>(h->d_bb, n_ptr, h->dcfg.dist_thr, h->fg_cells, h->d_fg_geom);
+    CK(cudaGetLastError());
+    k_fgrid_count<<<nblk(n_cap, 256), 256, 0, s>>>(px, py, n_ptr, h->d_fg_geom, h->d_fg_cnt, h->d_fg_cell);
+    CK(cudaGetLastError());
+    int rc = exclusive_sum(h, h->d_fg_cnt, h->d_fg_start, h->fg_cells + 1);
+    if (rc) return rc;
+    k_fgrid_fill<<<nblk(n_cap, 256), 256, 0, s>>>(px, py, n_ptr, h->d_fg_cell, h->d_fg_start, h->d_fg_cnt, h->d_fg_pts, h->d_fg_idx);
+    CK(cudaGetLastError());
+    h->n_launch += 5;
+    return ICMSLAM_OK;
+}
+
 // One sweep on device-resident data.  The previous map is in h->d_map_in (2 x Lcap); L_in is its
 // width known on the host, or -1 when only the device knows it (= landmarks_actuales, chained
-// sweeps).  Poses dx (3 x T, ldx) are updated in place; the filtered map goes to dmap_out.
-static int sweep_core(icmslam_handle* h, double* dx, int64_t ldx, const double* x0, const icmslam_sweep_opts& o, int L_in,
-                      double* dmap_out, int out_cap, int64_t out_ld)
+// sweeps).  Poses are read from xin (3 x T, ldin) and the updated poses written to xout (3 x T,
+// ldout); xin == xout is allowed (the fused path then goes through the internal double buffer).
+// The filtered map goes to dmap_out.
+static int sweep_core(icmslam_handle* h, const double* xin, int64_t ldin, double* xout, int64_t ldout, const double* x0,
+                      const icmslam_sweep_opts& o, int L_in, double* dmap_out, int out_cap, int64_t out_ld)
 {
     const int T = h->T, L = h->Lcap;
     const int64_t n = h->n;
@@ -494,78 +586,107 @@ static int sweep_core(icmslam_handle* h, double* dx, int64_t ldx, const double* 
     double* raw_x = h->d_raw;
     double* raw_y = h->d_raw + L;
     const bool timing = (o.reserved & 2) != 0;
+    const bool collect = (o.reserved & 1) != 0;
+    unsigned long long* iters = collect ? &st->newton_iters : nullptr;
+    const bool use_fused = h->fused_ok && o.fused && o.schedule == ICMSLAM_SCHED_REDBLACK && o.solver == ICMSLAM_SOLVER_NEWTON &&
+                           o.map_view == ICMSLAM_VIEW_PREV;
+    const int n_search_cap = L_in < 0 ? L : (L_in > 0 ? L_in : 1);
 
     k_sweep_begin<<<1, 1, 0, s>>>(st, L_in < 0 ? L : L_in);
     CK(cudaGetLastError());
     h->n_launch += 1;
-    CK(cudaMemsetAsync(h->d_sum_x, 0, (size_t)L * 8, s));
-    CK(cudaMemsetAsync(h->d_sum_y, 0, (size_t)L * 8, s));
     CK(cudaMemsetAsync(h->d_cnt, 0, ((size_t)L + 1) * sizeof(int), s));
-    int rc = build_grid(h, min_x, min_y, &st->lsearch, L_in < 0 ? L : (L_in > 0 ? L_in : 1), false);
-    if (rc) return rc;
-
-    const bool collect = (o.reserved & 1) != 0;
-    unsigned long long* iters = collect ? &st->newton_iters : nullptr;
-    const bool use_fused = h->fw.available && o.fused && o.schedule == ICMSLAM_SCHED_REDBLACK && o.solver == ICMSLAM_SOLVER_NEWTON &&
-                           o.map_view == ICMSLAM_VIEW_PREV;
-    PoseArrays A;
-    A.x = dx; A.ldx = ldx; A.odo = h->d_odo; A.ldo = T; A.u = h->d_u; A.ldu = T;
-    A.x0[0] = x0[0]; A.x0[1] = x0[1]; A.x0[2] = x0[2];
-    A.off = h->d_off; A.T = T;
-    if (timing) CK(cudaEventRecord(h->ev[0], s));
+    int rc;
     if (use_fused) {
-        rc = fused_sweep(h->fw, s, h->dcfg, A, h->d_bx, h->d_by, n, st, h->d_cell_start, h->d_glx, h->d_gly, h->d_gidx, h->d_c,
-                         h->d_nfar, h->d_sum_x, h->d_sum_y, h->d_cnt, o.newton_tol, o.newton_maxit, iters, h->err, sizeof h->err);
+        rc = build_fgrid(h, min_x, min_y, &st->lsearch, n_search_cap);
         if (rc) return rc;
+        double* kout = xout;
+        int64_t kld = ldout;
+        if (xin == xout) { kout = (xin == h->d_x2) ? h->d_x : h->d_x2; kld = T; }
+        FusedParams P;
+        P.T = T; P.off = h->d_off; P.bx = h->d_bx; P.by = h->d_by;
+        P.xin = xin; P.ldin = ldin; P.xout = kout; P.ldout = kld;
+        P.x0[0] = x0[0]; P.x0[1] = x0[1]; P.x0[2] = x0[2];
+        P.inc = h->d_inc; P.ldinc = T; P.u = h->d_u; P.ldu = T;
+        P.cfg = h->dcfg; P.thr2_hi = h->thr2_hi; P.fix_scale = h->fix_scale; P.tol = o.newton_tol; P.maxit = o.newton_maxit;
+        P.st = st; P.geom = h->d_fg_geom; P.cell_start = h->d_fg_start; P.gpts = h->d_fg_pts; P.gidx = h->d_fg_idx;
+        P.c = h->d_c; P.fsum_x = h->d_fsum_x; P.fsum_y = h->d_fsum_y; P.cnt = h->d_cnt;
+        P.nfar = h->d_nfar; P.far_sx = h->d_far_sx; P.far_sy = h->d_far_sy;
+        P.obs_cap = h->obs_cap; P.iters = iters;
+        if (timing) CK(cudaEventRecord(h->ev[0], s));
+        k_sweep_fused<true><<<nblk(T, FS_OWN), FS_THREADS, h->fused_smem, s>>>(P);
+        CK(cudaGetLastError());
+        if (timing) CK(cudaEventRecord(h->ev[1], s));
         h->n_launch += 1;
+        if (kout != xout) CK(cudaMemcpy2DAsync(xout, (size_t)ldout * 8, kout, (size_t)kld * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToDevice, s));
+        // new labels: one per scan that has a far observation, numbered in time order
+        k_flag_positive<<<nblk(T, 256), 256, 0, s>>>(h->d_nfar, T, h->d_flag);
+        CK(cudaGetLastError());
+        rc = exclusive_sum(h, h->d_flag, h->d_prefix, T);
+        if (rc) return rc;
+        k_fused_labels<<<nblk(T, 256), 256, 0, s>>>(T, h->d_off, st, h->d_nfar, h->d_prefix, h->d_far_sx, h->d_far_sy, L, h->d_c, raw_x,
+                                                    raw_y, h->d_cnt);
+        CK(cudaGetLastError());
+        k_fused_means<<<nblk(L, 256), 256, 0, s>>>(st, h->d_fsum_x, h->d_fsum_y, h->d_cnt, min_x, min_y, 1.0 / h->fix_scale, h->dcfg.cota,
+                                                   raw_x, raw_y, h->d_kflag, L);
+        CK(cudaGetLastError());
+        h->n_launch += 3;
     } else {
+        if (xin != xout) CK(cudaMemcpy2DAsync(xout, (size_t)ldout * 8, xin, (size_t)ldin * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToDevice, s));
+        double* dx = xout;
+        const int64_t ldx = ldout;
+        CK(cudaMemsetAsync(h->d_sum_x, 0, (size_t)L * 8, s));
+        CK(cudaMemsetAsync(h->d_sum_y, 0, (size_t)L * 8, s));
+        rc = build_grid(h, min_x, min_y, &st->lsearch, n_search_cap, false);
+        if (rc) return rc;
+        h->n_launch += 3;
+        PoseArrays A;
+        A.x = dx; A.ldx = ldx; A.odo = h->d_odo; A.ldo = T; A.u = h->d_u; A.ldu = T;
+        A.x0[0] = x0[0]; A.x0[1] = x0[1]; A.x0[2] = x0[2];
+        A.off = h->d_off; A.T = T;
+        if (timing) CK(cudaEventRecord(h->ev[0], s));
         k_assoc<<<148 * 8, 256, 0, s>>>(T, h->d_off, h->d_bx, h->d_by, dx, ldx, x0[0], x0[1], x0[2], st, h->d_cell_start, h->d_glx,
                                         h->d_gly, h->d_gidx, h->dcfg.dist_thr, h->d_c, h->d_nfar, h->d_sum_x, h->d_sum_y, h->d_cnt);
         CK(cudaGetLastError());
         h->n_launch += 1;
-    }
-    if (timing) CK(cudaEventRecord(h->ev[1], s));
-    // new labels: one per scan that has a far observation, numbered in time order
-    k_flag_positive<<<nblk(T, 256), 256, 0, s>>>(h->d_nfar, T, h->d_flag);
-    CK(cudaGetLastError());
-    rc = exclusive_sum(h, h->d_flag, h->d_prefix, T);
-    if (rc) return rc;
-    // (the fused kernel has already updated the poses; labels / statistics use its saved input poses)
-    const double* xin = use_fused ? h->fw.d_xin : dx;
-    const int64_t ldxin = use_fused ? T : ldx;
-    k_new_labels<<<148 * 4, 256, 0, s>>>(T, h->d_off, h->d_bx, h->d_by, xin, ldxin, x0[0], x0[1], x0[2], st, h->d_nfar, h->d_prefix,
-                                         L, h->d_c, h->d_sum_x, h->d_sum_y, h->d_cnt);
-    CK(cudaGetLastError());
-    h->n_launch += 2;
-    const bool running = o.map_view == ICMSLAM_VIEW_RUNNING;
-    if (running) {
-        if (!h->d_sorted) {
-            CK(dalloc(&h->d_keys_out, (size_t)n)); CK(dalloc(&h->d_iota, (size_t)n)); CK(dalloc(&h->d_sorted, (size_t)n));
-            CK(dalloc(&h->d_seen_x, (size_t)n)); CK(dalloc(&h->d_seen_y, (size_t)n));
-            k_iota<<<nblk(n, 256), 256, 0, s>>>((int)n, h->d_iota);
+        if (timing) CK(cudaEventRecord(h->ev[1], s));
+        // new labels: one per scan that has a far observation, numbered in time order
+        k_flag_positive<<<nblk(T, 256), 256, 0, s>>>(h->d_nfar, T, h->d_flag);
+        CK(cudaGetLastError());
+        rc = exclusive_sum(h, h->d_flag, h->d_prefix, T);
+        if (rc) return rc;
+        k_new_labels<<<148 * 4, 256, 0, s>>>(T, h->d_off, h->d_bx, h->d_by, dx, ldx, x0[0], x0[1], x0[2], st, h->d_nfar, h->d_prefix,
+                                             L, h->d_c, h->d_sum_x, h->d_sum_y, h->d_cnt);
+        CK(cudaGetLastError());
+        h->n_launch += 2;
+        const bool running = o.map_view == ICMSLAM_VIEW_RUNNING;
+        if (running) {
+            if (!h->d_sorted) {
+                CK(dalloc(&h->d_keys_out, (size_t)n)); CK(dalloc(&h->d_iota, (size_t)n)); CK(dalloc(&h->d_sorted, (size_t)n));
+                CK(dalloc(&h->d_seen_x, (size_t)n)); CK(dalloc(&h->d_seen_y, (size_t)n));
+                k_iota<<<nblk(n, 256), 256, 0, s>>>((int)n, h->d_iota);
+                CK(cudaGetLastError());
+            }
+            rc = exclusive_sum(h, h->d_cnt, h->d_seg, L);
+            if (rc) return rc;
+            int end_bit = 1;
+            while ((1ll << end_bit) < (long long)L + 1 && end_bit < 32) ++end_bit;
+            size_t bytes = 0;
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned*)h->d_c, (unsigned*)h->d_keys_out, h->d_iota, h->d_sorted,
+                                               (int)n, 0, end_bit, s));
+            rc = ensure_cub(h, bytes);
+            if (rc) return rc;
+            CK(cub::DeviceRadixSort::SortPairs(h->d_cub, bytes, (const unsigned*)h->d_c, (unsigned*)h->d_keys_out, h->d_iota, h->d_sorted,
+                                               (int)n, 0, end_bit, s));
+            k_running_mean<<<nblk(L, 128), 128, 0, s>>>(st, h->d_seg, h->d_cnt, h->d_sorted, h->d_scan_of, h->d_bx, h->d_by, dx, ldx,
+                                                        x0[0], x0[1], x0[2], h->d_seen_x, h->d_seen_y, raw_x, raw_y, L);
             CK(cudaGetLastError());
+            h->n_launch += 1;
         }
-        rc = exclusive_sum(h, h->d_cnt, h->d_seg, L);
-        if (rc) return rc;
-        int end_bit = 1;
-        while ((1ll << end_bit) < (long long)L + 1 && end_bit < 32) ++end_bit;
-        size_t bytes = 0;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned*)h->d_c, (unsigned*)h->d_keys_out, h->d_iota, h->d_sorted,
-                                           (int)n, 0, end_bit, s));
-        rc = ensure_cub(h, bytes);
-        if (rc) return rc;
-        CK(cub::DeviceRadixSort::SortPairs(h->d_cub, bytes, (const unsigned*)h->d_c, (unsigned*)h->d_keys_out, h->d_iota, h->d_sorted,
-                                           (int)n, 0, end_bit, s));
-        k_running_mean<<<nblk(L, 128), 128, 0, s>>>(st, h->d_seg, h->d_cnt, h->d_sorted, h->d_scan_of, h->d_bx, h->d_by, dx, ldx,
-                                                    x0[0], x0[1], x0[2], h->d_seen_x, h->d_seen_y, raw_x, raw_y, L);
+        k_means_flags<<<nblk(L, 256), 256, 0, s>>>(st, h->d_sum_x, h->d_sum_y, h->d_cnt, h->dcfg.cota, running ? 1 : 0, raw_x, raw_y,
+                                                   h->d_kflag, L);
         CK(cudaGetLastError());
         h->n_launch += 1;
-    }
-    k_means_flags<<<nblk(L, 256), 256, 0, s>>>(st, h->d_sum_x, h->d_sum_y, h->d_cnt, h->dcfg.cota, running ? 1 : 0, raw_x, raw_y,
-                                               h->d_kflag, L);
-    CK(cudaGetLastError());
-    h->n_launch += 1;
-    if (!use_fused) {
         ObsArrays O;
         O.bx = h->d_bx; O.by = h->d_by; O.d = h->d_d; O.beam = h->d_beam; O.ang = h->d_ang;
         SeenSrc S;
@@ -591,7 +712,7 @@ static int sweep_core(icmslam_handle* h, double* dx, int64_t ldx, const double* 
     // Mapa.filtrar (sensors.py:165-166)
     rc = run_filter(h, raw_x, raw_y, h->d_cnt, nullptr, dmap_out, out_cap, out_ld, nullptr, 1);
     if (rc) return rc;
-    h->n_launch += 14;   // grid build (3+3) + filter kernels (8)
+    h->n_launch += 11;   // filter grid build (3) + filter kernels (8)
     h->lact_dirty = true;
     return ICMSLAM_OK;
 }
@@ -620,20 +741,22 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
         return ICMSLAM_EMPTY_FIRST_SCAN;
     }
     if (h->last_empty && T > 1) return ICMSLAM_ERR_EMPTY_LAST;
-    double* dx = x;
-    int64_t ldx = ld_x;
+    const double* xin = x;
+    double* xout = x;
+    int64_t ldin = ld_x, ldout = ld_x;
     if (memspace == ICMSLAM_HOST) {
         CK(cudaMemcpy2DAsync(h->d_x, (size_t)T * 8, x, (size_t)ld_x * 8, (size_t)T * 8, 3, cudaMemcpyHostToDevice, s));
-        dx = h->d_x;
-        ldx = T;
+        xin = h->d_x; ldin = T;
+        xout = h->d_x2; ldout = T;
     }
     if (L_in > 0)
         CK(cudaMemcpy2DAsync(h->d_map_in, (size_t)L * 8, map_in, (size_t)ld_map_in * 8, (size_t)L_in * 8, 2, cudaMemcpyDefault, s));
     const bool own_out = (memspace == ICMSLAM_HOST || !map_out);
-    int rc = sweep_core(h, dx, ldx, x0, o, L_in, own_out ? h->d_map_out : map_out, own_out ? L : cap_out, own_out ? (int64_t)L : ld_map_out);
+    int rc = sweep_core(h, xin, ldin, xout, ldout, x0, o, L_in, own_out ? h->d_map_out : map_out, own_out ? L : cap_out,
+                        own_out ? (int64_t)L : ld_map_out);
     if (rc) return rc;
     if (memspace == ICMSLAM_HOST) {
-        CK(cudaMemcpy2DAsync(x, (size_t)ld_x * 8, dx, (size_t)T * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpy2DAsync(x, (size_t)ld_x * 8, xout, (size_t)T * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToHost, s));
         rc = sync_state(h);
         if (rc) return rc;
         int status = status_from_state(h->h_st);
@@ -689,10 +812,37 @@ extern "C" int icmslam_get_map(icmslam_handle* h, double* map, int32_t cap, int6
     return ICMSLAM_OK;
 }
 
+// Poses resident on the device between calls (ICM.positions, sensors.py:104): icmslam_set_poses uploads
+// x (3 x T); icmslam_iterate with x == NULL then sweeps the resident poses with no copies at all;
+// icmslam_get_poses reads them back.
+extern "C" int icmslam_set_poses(icmslam_handle* h, const double* x, int64_t ld_x, int32_t memspace)
+{
+    if (!h || !h->d_x || !x || ld_x < h->T) return ICMSLAM_ERR_INVALID;
+    (void)memspace;
+    CK(cudaSetDevice(h->cfg.device));
+    const int T = h->T;
+    CK(cudaMemcpy2DAsync(h->d_x, (size_t)T * 8, x, (size_t)ld_x * 8, (size_t)T * 8, 3, cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->x_cur = 0;
+    return ICMSLAM_OK;
+}
+
+extern "C" int icmslam_get_poses(icmslam_handle* h, double* x, int64_t ld_x, int32_t memspace)
+{
+    if (!h || !h->d_x || !x || ld_x < h->T) return ICMSLAM_ERR_INVALID;
+    (void)memspace;
+    CK(cudaSetDevice(h->cfg.device));
+    const int T = h->T;
+    const double* src = h->x_cur ? h->d_x2 : h->d_x;
+    CK(cudaMemcpy2DAsync(x, (size_t)ld_x * 8, src, (size_t)T * 8, (size_t)T * 8, 3, cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return ICMSLAM_OK;
+}
+
 extern "C" int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const double* x0, int32_t n_sweeps,
                                const icmslam_sweep_opts* opts, int32_t memspace)
 {
-    if (!h || !h->extracted || !x || !x0 || ld_x < h->T || n_sweeps < 0) return ICMSLAM_ERR_INVALID;
+    if (!h || !h->extracted || !x0 || (x && ld_x < h->T) || n_sweeps < 0) return ICMSLAM_ERR_INVALID;
     icmslam_sweep_opts o;
     default_opts(o, opts);
     CK(cudaSetDevice(h->cfg.device));
@@ -700,24 +850,27 @@ extern "C" int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const
     cudaStream_t s = h->stream;
     if (h->first_empty) return ICMSLAM_EMPTY_FIRST_SCAN;
     if (h->last_empty && T > 1) return ICMSLAM_ERR_EMPTY_LAST;
-    double* dx = x;
-    int64_t ldx = ld_x;
-    if (memspace == ICMSLAM_HOST) {
-        CK(cudaMemcpy2DAsync(h->d_x, (size_t)T * 8, x, (size_t)ld_x * 8, (size_t)T * 8, 3, cudaMemcpyHostToDevice, s));
-        dx = h->d_x;
-        ldx = T;
+    if (x) {
+        CK(cudaMemcpy2DAsync(h->d_x, (size_t)T * 8, x, (size_t)ld_x * 8, (size_t)T * 8, 3, cudaMemcpyDefault, s));
+        h->x_cur = 0;
     }
     for (int k = 0; k < n_sweeps; ++k) {
         CK(cudaMemsetAsync(h->d_counts, 0, (size_t)L * sizeof(double), s));
-        int rc = sweep_core(h, dx, ldx, x0, o, -1, h->d_map_out, L, L);
+        double* src = h->x_cur ? h->d_x2 : h->d_x;
+        double* dst = h->x_cur ? h->d_x : h->d_x2;
+        int rc = sweep_core(h, src, T, dst, T, x0, o, -1, h->d_map_out, L, L);
         if (rc) return rc;
+        h->x_cur ^= 1;
         double* t = h->d_map_in; h->d_map_in = h->d_map_out; h->d_map_out = t;   // mapa_viejo = mapa_refinado (sensors.py:315)
     }
-    if (memspace == ICMSLAM_HOST) {
-        CK(cudaMemcpy2DAsync(x, (size_t)ld_x * 8, dx, (size_t)T * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToHost, s));
-        int rc = sync_state(h);
-        if (rc) return rc;
-        return status_from_state(h->h_st);
+    if (x) {
+        const double* src = h->x_cur ? h->d_x2 : h->d_x;
+        CK(cudaMemcpy2DAsync(x, (size_t)ld_x * 8, src, (size_t)T * 8, (size_t)T * 8, 3, cudaMemcpyDefault, s));
+        if (memspace == ICMSLAM_HOST) {
+            int rc = sync_state(h);
+            if (rc) return rc;
+            return status_from_state(h->h_st);
+        }
     }
     return ICMSLAM_OK;
 }

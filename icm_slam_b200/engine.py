@@ -185,13 +185,27 @@ class Engine:
 
     def iterate(self, x, x0, n_sweeps=1, schedule="redblack", solver="newton", view="prev", newton_tol=0.0, newton_maxit=0,
                 fused=True, timing=False, stats=False):
-        """n_sweeps x iterations_process_offline on the device-resident map; x (3 x T, numpy or torch CUDA) in place."""
+        """n_sweeps x iterations_process_offline on the device-resident map; x (3 x T, numpy or torch CUDA) in place,
+        or x=None to sweep the poses uploaded with set_poses."""
         opts = SweepOpts(_lib.SCHED[schedule], _lib.SOLVER[solver], _lib.VIEW[view], int(newton_maxit), float(newton_tol),
                          int(bool(fused)), (1 if stats else 0) | (2 if timing else 0))
         px, ms = _ptr(x)
         x0 = np.ascontiguousarray(np.asarray(x0, dtype=np.float64).reshape(3))
-        st = self.lib.icmslam_iterate(self._h, px, _rows(x, 3), C.c_void_p(x0.ctypes.data), int(n_sweeps), C.byref(opts), ms)
+        st = self.lib.icmslam_iterate(self._h, px, _rows(x, 3) if x is not None else 0, C.c_void_p(x0.ctypes.data), int(n_sweeps),
+                                      C.byref(opts), ms)
         return check(st, self._h)
+
+    def set_poses(self, x):
+        """ICM.positions (3 x T) -> device; iterate(None, ...) then sweeps them in place on the device."""
+        if not _is_torch(x):
+            x = np.ascontiguousarray(x, dtype=np.float64)
+        px, ms = _ptr(x)
+        check(self.lib.icmslam_set_poses(self._h, px, _rows(x, 3), ms), self._h)
+
+    def get_poses(self):
+        out = np.empty((3, self.T))
+        check(self.lib.icmslam_get_poses(self._h, _ptr(out)[0], self.T, HOST), self._h)
+        return out
 
     def kernel_ms(self):
         out = np.zeros(2)

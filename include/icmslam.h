@@ -137,6 +137,11 @@ int icmslam_set_map(icmslam_handle* h, const double* map, int32_t L_map, int64_t
 int icmslam_get_map(icmslam_handle* h, double* map, int32_t cap, int64_t ld, int32_t* L_map, int32_t memspace);
 int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const double* x0, int32_t n_sweeps,
                     const icmslam_sweep_opts* opts, int32_t memspace);
+/* `ICM.positions` resident on the device (sensors.py:104): icmslam_set_poses uploads x (3 x T);
+ * icmslam_iterate with x == NULL then sweeps the resident poses without any copy;
+ * icmslam_get_poses reads the current poses back. */
+int icmslam_set_poses(icmslam_handle* h, const double* x, int64_t ld_x, int32_t memspace);
+int icmslam_get_poses(icmslam_handle* h, double* x, int64_t ld_x, int32_t memspace);
 
 /* -- instrumentation (no reference counterpart).  Kernel time of the last sweep run with
  * opts.reserved & 2, from CUDA events on the handle's stream: out2[0] = association (or the fused

@@ -196,10 +196,10 @@ def test_modes_vs_oracle_c1(schedule, solver, view):
     e.close()
 
 
-def _synthetic_case(L_true, T, seed):
+def _synthetic_case(L_true, T, seed, cota=20.0):
     from icm_slam_b200.synthetic import make_synthetic
     d = make_synthetic(L_true, T=T, seed=seed)
-    cfgd = dict(CONFIG_ROS, L=2 * L_true + 64, cota=20.0)
+    cfgd = dict(CONFIG_ROS, L=2 * L_true + 64, cota=cota)
     return d, cfgd
 
 
@@ -280,3 +280,89 @@ def test_error_codes_mirror_reference_failures():
     with pytest.raises(ValueError):
         e.sweep(g["map_init"].copy(), np.ascontiguousarray(g["x_init"].copy()), odo[:, 0], fused=False)
     e.close()
+
+
+# ---- the fused single-kernel path (redblack, newton, prev) -----------------------------------------
+def test_fused_teacher_forced_vs_reference_c1_c2():
+    """The fused kernel's association / label / count outputs against the reference's own, sweep by sweep."""
+    for gname, inputs in (("c1_ref.npz", c1_inputs), ("c2_ref.npz", c2_inputs)):
+        gold = golden(gname)
+        z, odo, u = inputs()
+        e = _engine(_cfg(), z, odo, u)
+        mapa = gold["p0_map"].copy()
+        e.landmarks_actuales = mapa.shape[1]
+        for k in range(1, int(gold["nsweeps"]) + 1):
+            p = "s%d_" % k
+            x = np.ascontiguousarray(gold[p + "x_in"].copy())
+            st, Lout, mout = e.sweep(mapa, x, odo[:, 0], fused=True)
+            assert st == 0
+            assert np.array_equal(e.associations(), gold[p + "labels"]), "labels differ in sweep %d" % k
+            raw, cnt, rl = e.raw_map()
+            assert rl == int(gold[p + "raw_L"])
+            assert np.array_equal(cnt, gold[p + "raw_counts"])
+            assert np.max(np.abs(raw - gold[p + "raw_map"])) <= 1e-9
+            assert Lout == gold[p + "map_out"].shape[1]
+            assert np.max(np.abs(mout - gold[p + "map_out"])) <= 1e-9
+            assert np.array_equal(e.counts(Lout), gold[p + "counts_out"])
+            mapa = gold[p + "map_out"].copy()
+        e.close()
+
+
+def _fused_vs_oracle(z, odo, u, cfgd, map0, x_init, nsweeps, chained):
+    orc, ocfg, ext = _oracle(cfgd, z, odo, u)
+    e = _engine(_cfg(**cfgd), z, odo, u)
+    mo = orc.Mapa(ocfg)
+    map_o = map0.copy()
+    mo.landmarks_actuales = map_o.shape[1]
+    xo = np.ascontiguousarray(x_init.copy())
+    xg = xo.copy()
+    if chained:
+        e.set_map(map0)
+        e.set_poses(xg)
+    else:
+        map_g = map0.copy()
+        e.landmarks_actuales = map_g.shape[1]
+    for k in range(nsweeps):
+        r = orc.sweep(ocfg, mo, ext, odo, u, odo[:, 0], map_o, xo, "redblack", "newton", "prev")
+        if chained:
+            e.iterate(None, odo[:, 0], 1, fused=True)
+            xg = e.get_poses()
+            mout = e.get_map()
+            Lout = mout.shape[1]
+        else:
+            st, Lout, mout = e.sweep(map_g, xg, odo[:, 0], fused=True)
+            map_g = np.ascontiguousarray(mout.copy())
+        assert np.array_equal(e.associations(), r["c"]), k
+        assert Lout == r["map"].shape[1]
+        d = np.abs(xg - xo)
+        assert d[:2].max() <= TOL_XY and d[2].max() <= TOL_TH, (k, d.max(axis=1))
+        assert np.max(np.abs(mout - r["map"])) <= TOL_XY
+        map_o = r["map"]
+    e.close()
+
+
+@pytest.mark.parametrize("chained", [False, True])
+def test_fused_vs_oracle_c1(chained):
+    g = golden("c1_ref.npz")
+    z, odo, u = c1_inputs()
+    _fused_vs_oracle(z, odo, u, dict(CONFIG_ROS), g["p0_map"], g["p0_x"], 3, chained)
+
+
+def test_fused_vs_oracle_c2_dense_scans():
+    """datos_palomar1 raw scans: up to 119 kept beams per scan (tiles beyond the shared-memory budget)."""
+    g = golden("c2_ref.npz")
+    z, odo, u = c2_inputs()
+    _fused_vs_oracle(z, odo, u, dict(CONFIG_ROS), g["p0_map"], g["p0_x"], 2, False)
+
+
+@pytest.mark.parametrize("T,chained", [(6000, True), (2047, False), (127, False), (3, False)])
+def test_fused_vs_oracle_synthetic(T, chained):
+    d, cfgd = _synthetic_case(625, T, 20181 + 7, cota=20.0 if T > 1000 else 1.0)
+    _fused_vs_oracle(d["observations"], d["odometry"], d["velocities"], cfgd, d["map_init"], d["x_init"], 2, chained)
+
+
+def test_fused_small_smem_budget_fallback(monkeypatch):
+    """Tiles whose observations exceed the shared-memory budget read global memory directly: same results."""
+    monkeypatch.setenv("ICMSLAM_OBS_CAP", "64")
+    d, cfgd = _synthetic_case(625, 1500, 20181 + 9)
+    _fused_vs_oracle(d["observations"], d["odometry"], d["velocities"], cfgd, d["map_init"], d["x_init"], 2, False)
