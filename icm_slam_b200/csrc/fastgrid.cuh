@@ -3,8 +3,9 @@
 // Same contract as the grid in common.cuh (every landmark within dist_thr of a query point is
 // visited, ties resolved exactly as cdist + np.argmin do, ICM_SLAM.py:169-172) with a layout made
 // for the hot loop:
-//   * cell edge h >= 2*thr1 (thr1 = dist_thr*(1+2^-20)), so the disc of radius dist_thr around a
-//     query overlaps at most 2 x 2 cells: two cell_start loads per row instead of the 3 x 3 block;
+//   * replicated binning: cell edge h >= 2*thr1 (thr1 = dist_thr*(1+2^-20)) and every landmark is
+//     registered in each of the (at most 2 x 2) cells its thr1-disc overlaps, so a query reads ONE
+//     cell -- the one containing the query point -- instead of a 3 x 3 block;
 //   * a FIXED cell budget (NC cells, host constant) so the counting sort's scan has a host-known
 //     length and no host round trip: the geometry kernel grows h until nx*ny <= NC;
 //   * landmarks stored cell-sorted as double2 (one 16-byte load per candidate); the original index
@@ -87,6 +88,16 @@ __global__ void k_fgrid_geom(const unsigned long long* bb, const int* n_ptr, dou
     *out = g;
 }
 
+// ---- replicated binning -------------------------------------------------------------------------
+// Every landmark is registered in each cell its thr1-disc overlaps (at most 2 x 2 cells since
+// h >= 2*thr1), so a query inspects exactly ONE cell: the one containing the query point.
+__device__ __forceinline__ void fgrid_cell_range(const FGeom& g, double x, double y, int& cx0, int& cx1, int& cy0, int& cy1)
+{
+    const double fx = (x - g.x0) * g.inv_h, fy = (y - g.y0) * g.inv_h;
+    cx0 = min(max(__double2int_rd(fx - g.delta), 0), g.nx - 1); cx1 = min(max(__double2int_rd(fx + g.delta), 0), g.nx - 1);
+    cy0 = min(max(__double2int_rd(fy - g.delta), 0), g.ny - 1); cy1 = min(max(__double2int_rd(fy + g.delta), 0), g.ny - 1);
+}
+
 __device__ __forceinline__ int fgrid_cell(const FGeom& g, double x, double y)
 {
     int cx = __double2int_rd((x - g.x0) * g.inv_h), cy = __double2int_rd((y - g.y0) * g.inv_h);
@@ -97,59 +108,65 @@ __device__ __forceinline__ int fgrid_cell(const FGeom& g, double x, double y)
 
 __global__ void __launch_bounds__(256)
 k_fgrid_count(const double* __restrict__ px, const double* __restrict__ py, const int* __restrict__ n_ptr, const FGeom* __restrict__ geom,
-              int* __restrict__ cell_cnt, int* __restrict__ cell_id)
+              int* __restrict__ cell_cnt)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *n_ptr) return;
     const FGeom g = *geom;
-    const int c = fgrid_cell(g, px[i], py[i]);
-    cell_id[i] = c;
-    atomicAdd(cell_cnt + c, 1);
+    int cx0, cx1, cy0, cy1;
+    fgrid_cell_range(g, px[i], py[i], cx0, cx1, cy0, cy1);
+    for (int cy = cy0; cy <= cy1; ++cy)
+        for (int cx = cx0; cx <= cx1; ++cx) atomicAdd(cell_cnt + cy * g.nx + cx, 1);
 }
 
 __global__ void __launch_bounds__(256)
-k_fgrid_fill(const double* __restrict__ px, const double* __restrict__ py, const int* __restrict__ n_ptr, const int* __restrict__ cell_id,
+k_fgrid_fill(const double* __restrict__ px, const double* __restrict__ py, const int* __restrict__ n_ptr, const FGeom* __restrict__ geom,
              const int* __restrict__ cell_start, int* __restrict__ cell_fill, double2* __restrict__ pts, int* __restrict__ idx)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *n_ptr) return;
-    const int c = cell_id[i];
-    const int p = cell_start[c] + atomicSub(cell_fill + c, 1) - 1;   // counts the cell back down to zero
-    pts[p] = make_double2(px[i], py[i]);
-    idx[p] = i;
+    const FGeom g = *geom;
+    const double x = px[i], y = py[i];
+    int cx0, cx1, cy0, cy1;
+    fgrid_cell_range(g, x, y, cx0, cx1, cy0, cy1);
+    for (int cy = cy0; cy <= cy1; ++cy)
+        for (int cx = cx0; cx <= cx1; ++cx) {
+            const int c = cy * g.nx + cx;
+            const int p = cell_start[c] + atomicSub(cell_fill + c, 1) - 1;   // counts the cell back down to zero
+            pts[p] = make_double2(x, y);
+            idx[p] = i;
+        }
 }
 
-// Nearest landmark of (wx, wy).  Returns the winner's position in the cell-sorted arrays (-1 if no
-// candidate), its squared distance `best` (INFINITY if none) and its coordinates.
-__device__ __forceinline__ int fgrid_nearest(const FGrid& G, double wx, double wy, double& best, double& lx, double& ly)
+// Nearest landmark of (wx, wy) among the cell's entries [s, e).  Returns the winner's position in the
+// cell-sorted arrays (-1 if no candidate), its squared distance `best` (INFINITY if none) and its
+// coordinates.
+__device__ __forceinline__ int fgrid_scan(const FGrid& G, double wx, double wy, int s, int e, double& best, double& lx, double& ly)
 {
-    const double fx = (wx - G.g.x0) * G.g.inv_h, fy = (wy - G.g.y0) * G.g.inv_h;
-    int cx0 = __double2int_rd(fx - G.g.delta), cx1 = __double2int_rd(fx + G.g.delta);
-    int cy0 = __double2int_rd(fy - G.g.delta), cy1 = __double2int_rd(fy + G.g.delta);
-    // clamp BOTH ends into the grid: landmarks outside the box were binned into the border cells
-    cx0 = min(max(cx0, 0), G.g.nx - 1); cx1 = min(max(cx1, 0), G.g.nx - 1);
-    cy0 = min(max(cy0, 0), G.g.ny - 1); cy1 = min(max(cy1, 0), G.g.ny - 1);
     best = INFINITY;
     lx = 0.0; ly = 0.0;
     int bk = -1;
-    for (int r = cy0; r <= cy1; ++r) {
-        const int s = __ldg(G.cell_start + r * G.g.nx + cx0), e = __ldg(G.cell_start + r * G.g.nx + cx1 + 1);
-        for (int k = s; k < e; ++k) {
-            const double2 p = __ldg(G.pts + k);
-            const double s2 = dist2_rn(p.x - wx, p.y - wy);
-            bool take;
-            if (bk < 0) take = true;
-            else {
-                const double lo = best * (1.0 - 8.8817841970012523e-16), hi = best * (1.0 + 8.8817841970012523e-16);   // 2^-50
-                if (s2 < lo) take = true;
-                else if (s2 > hi) take = false;
-                else {   // (almost) equidistant: decide on the rooted values like np.argmin over cdist
-                    const double dk = __dsqrt_rn(s2), db = __dsqrt_rn(best);
-                    take = dk < db || (dk == db && __ldg(G.idx + k) < __ldg(G.idx + bk));
-                }
+    for (int k = s; k < e; ++k) {
+        const double2 p = __ldg(G.pts + k);
+        const double s2 = dist2_rn(p.x - wx, p.y - wy);
+        bool take;
+        if (bk < 0) take = true;
+        else {
+            const double lo = best * (1.0 - 8.8817841970012523e-16), hi = best * (1.0 + 8.8817841970012523e-16);   // 2^-50
+            if (s2 < lo) take = true;
+            else if (s2 > hi) take = false;
+            else {   // (almost) equidistant: decide on the rooted values like np.argmin over cdist
+                const double dk = __dsqrt_rn(s2), db = __dsqrt_rn(best);
+                take = dk < db || (dk == db && __ldg(G.idx + k) < __ldg(G.idx + bk));
             }
-            if (take) { best = s2; bk = k; lx = p.x; ly = p.y; }
         }
+        if (take) { best = s2; bk = k; lx = p.x; ly = p.y; }
     }
     return bk;
+}
+
+__device__ __forceinline__ int fgrid_nearest(const FGrid& G, double wx, double wy, double& best, double& lx, double& ly)
+{
+    const int c = fgrid_cell(G.g, wx, wy);
+    return fgrid_scan(G, wx, wy, __ldg(G.cell_start + c), __ldg(G.cell_start + c + 1), best, lx, ly);
 }

@@ -7,19 +7,26 @@
 // update (:191-194), and the pose's conditional minimiser of fun_xn / fun_x (sensors.py:224-282)
 // in red-black order.  Every observation is read from HBM exactly once.
 //
-// Work decomposition (block = 128 threads = 2 "odd" warps + 2 "even" warps, 126 owned poses):
-//   * thread per pose.  The block's contiguous slice of the observation arrays (bx, by) is staged
-//     in shared memory with one TMA bulk copy per array (cp.async.bulk + mbarrier), so the
-//     per-thread walks over a scan's beams hit shared memory, not strided global memory;
-//   * phase A (all threads): project, associate (fastgrid.cuh), accumulate the 12 moment sums the
-//     Newton solve needs and the landmark statistics.  Statistics are summed as int64 fixed point
-//     of (observation - previous landmark) in a block-level shared-memory hash table and flushed
-//     with one global integer atomic per (block, landmark): integer addition is associative, so
-//     the landmark update is bit-reproducible for any block order or GPU count;
-//   * phase B1: the odd warps solve their poses from the OLD even neighbours; phase B2 (after one
-//     __syncthreads) the even warps solve theirs from the NEW odd neighbours held in shared memory.
-//     The odd pose just left of the tile is recomputed locally (halo), so no block waits on another;
-//   * new poses are staged in shared memory and written coalesced; labels go straight to global.
+// Work decomposition (block = 128 threads, 126 owned poses, one launch for the whole sweep):
+//   * the block's contiguous slice of the observation records (bx, by) is staged in shared memory with
+//     ONE TMA bulk copy (cp.async.bulk + mbarrier); tiles whose observations exceed the budget are
+//     processed in chunks of whole scans;
+//   * phase A -- LANES OVER CONSECUTIVE OBSERVATIONS (two per lane in flight): project, associate
+//     (fastgrid.cuh), write the label.  Adjacent lanes hold adjacent beams, i.e. mostly the same trunk,
+//     so the grid look-ups are coherent and every lane is busy;
+//   * phase B -- THREAD PER POSE over the staged data.  Pass 1 walks the scan once, summing the
+//     body-frame moments and collapsing each run of beams that hit the same landmark into an in-place
+//     record (run length, sum of bx, sum of by).  Pass 2 visits one RUN per step with the lanes in
+//     lockstep: everything that depends on the landmark is linear in the run sums, so the landmark
+//     moments and the landmark statistics cost one update per run, not per beam.  Statistics are
+//     added as int64 fixed point of (observation - previous landmark) to a block-level shared-memory
+//     hash table (32-bit halves with carry: native shared atomics) and flushed with one global integer
+//     atomic per (block, landmark): integer addition is associative, so the landmark update is
+//     bit-reproducible for any block order or GPU count.  Then the exact 1-D Newton solve: the two
+//     odd warps solve from the OLD even neighbours; after one __syncthreads the two even warps solve
+//     from the NEW odd neighbours held in shared memory.  The odd pose just left of the tile is
+//     recomputed locally (halo), so no block waits on another;
+//   * new poses are staged in shared memory and written coalesced.
 // Poses are double-buffered (xin -> xout): neighbouring tiles read each other's input poses.
 #pragma once
 #include "common.cuh"
@@ -28,6 +35,7 @@
 
 #define FS_THREADS 128
 #define FS_HALF 64
+#define FS_WARPS 4
 #define FS_OWN 126            // poses owned by a block: tb .. tb+125 (tb even)
 #define FS_XT 132             // pose-tile entries: poses tb-2 .. tb+126 (129 used)
 #define FS_HASH 256           // landmark slots of the block-level statistics table
@@ -36,7 +44,7 @@
 struct FusedParams {
     int T;
     const int* off;                       // CSR offsets of the kept observations (T + 1)
-    const double* bx; const double* by;   // body-frame observations (n, padded allocation)
+    const double2* bxy;                   // body-frame observations (bx, by), CSR order
     const double* xin; int64_t ldin;      // 3 x T input poses
     double* xout; int64_t ldout;          // 3 x T output poses
     double x0[3];                         // self.x0 (sensors.py:131)
@@ -184,32 +192,39 @@ __device__ __forceinline__ int newton_lean(const DevCfg& cfg, const PoseIn& P, c
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 struct __align__(16) FusedSmemFixed {
-    double xs[3][FS_XT];        // input poses tb-2 .. tb+126
-    double sn[FS_XT], cs[FS_XT];   // sin/cos of the input headings (later: of the new odd headings)
-    double xn[3][FS_XT];        // new poses (same indexing)
-    double inc[3][FS_XT];       // odometry increments t = tb-2 ..
+    double xs[3][FS_XT];           // input poses tb-2 .. tb+126, index lt = t - (tb-2)
+    double2 pp[FS_XT];             // projection origin of each scan (self.x0 for scan 0)
+    double2 rsc[FS_XT];            // (sin, cos) of (projection heading - pi/2)
+    double sn[FS_XT], cs[FS_XT];   // sin/cos of the input headings (after phase B1: of the new odd headings)
+    double xn[3][FS_XT];           // new poses (same indexing)
+    double inc[3][FS_XT];          // odometry increments
     double u[2][FS_XT];
-    int off[FS_XT];             // off[tb-1 .. tb+127] clamped, at index li = t - (tb-2)
+    int off[FS_XT];                // off[t] at lt (clamped)
     int hkey[FS_HASH];
     int hcnt[FS_HASH];
-    long long hsx[FS_HASH], hsy[FS_HASH];
+    unsigned hsx[FS_HASH][2], hsy[FS_HASH][2];     // fixed-point sums as (lo, hi) 32-bit halves: native shared atomics
     unsigned long long mbar;
-    int nfar_scans;
 };
 
+// adds one run (label, sum of (obs - landmark), count) to the block-level table
 __device__ __forceinline__ void stat_add(FusedSmemFixed& S, const FusedParams& p, int arg, double rdx, double rdy, int rn)
 {
     const long long vx = __double2ll_rn(rdx * p.fix_scale), vy = __double2ll_rn(rdy * p.fix_scale);
     unsigned h = ((unsigned)arg * 2654435761u) >> 24;      // FS_HASH = 256
+#pragma unroll 1
     for (int q = 0; q < FS_PROBES; ++q) {
         int key = ((volatile int*)S.hkey)[h];
-        if (key != arg && key == -1) {
-            int prev = atomicCAS(&S.hkey[h], -1, arg);
+        if (key == -1) {
+            const int prev = atomicCAS(&S.hkey[h], -1, arg);
             key = (prev == -1) ? arg : prev;
         }
         if (key == arg) {
-            atomicAdd((unsigned long long*)&S.hsx[h], (unsigned long long)vx);
-            atomicAdd((unsigned long long*)&S.hsy[h], (unsigned long long)vy);
+            const unsigned xl = (unsigned)vx, xh = (unsigned)((unsigned long long)vx >> 32);
+            const unsigned yl = (unsigned)vy, yh = (unsigned)((unsigned long long)vy >> 32);
+            const unsigned ox = atomicAdd(&S.hsx[h][0], xl);
+            atomicAdd(&S.hsx[h][1], xh + ((unsigned)(ox + xl) < ox ? 1u : 0u));      // carry out of the low half
+            const unsigned oy = atomicAdd(&S.hsy[h][0], yl);
+            atomicAdd(&S.hsy[h][1], yh + ((unsigned)(oy + yl) < oy ? 1u : 0u));
             atomicAdd(&S.hcnt[h], rn);
             return;
         }
@@ -220,60 +235,25 @@ __device__ __forceinline__ void stat_add(FusedSmemFixed& S, const FusedParams& p
     atomicAdd(p.cnt + arg, rn);
 }
 
-template <bool STAGED>
-__device__ __forceinline__ void fused_phase_a(const FusedParams& p, FusedSmemFixed& S, const FGrid& G, const double* sbx, const double* sby,
-                                              int obase, int o, int e, double px, double py, double st, double ct, bool owned,
-                                              Mom& M, int& nfar, double& fsx, double& fsy, double& FBx, double& FBy)
+__device__ __forceinline__ void mbar_wait(uint32_t mb, uint32_t parity)
 {
-    int run_arg = -1, run_n = 0;
-    double run_dx = 0.0, run_dy = 0.0;
-    for (int i = o; i < e; ++i) {
-        double bx, by;
-        if (STAGED) { bx = sbx[i - obase]; by = sby[i - obase]; }
-        else { bx = __ldg(p.bx + i); by = __ldg(p.by + i); }
-        // tras_rot_z: numpy's matmul order, acc = a0*b0; acc = fma(a1, b1, acc); + translation
-        const double wx = add_rn(__fma_rn(by, -st, mul_rn(bx, ct)), px);
-        const double wy = add_rn(__fma_rn(by, ct, mul_rn(bx, st)), py);
-        double best, lx, ly;
-        const int bk = fgrid_nearest(G, wx, wy, best, lx, ly);
-        M.n += 1.0;
-        M.Bx += bx; M.By += by;
-        M.Bxx = fma(bx, bx, M.Bxx); M.Byy = fma(by, by, M.Byy); M.Bxy = fma(bx, by, M.Bxy);
-        int lab;
-        if (bk < 0 || best > p.thr2_hi) {        // amin > dist_thr (ICM_SLAM.py:172)
-            lab = -1;
-            ++nfar;
-            fsx += wx; fsy += wy;               // np.sum(obs[c==i], axis=0): row order
-            FBx += bx; FBy += by;
-        } else {
-            lab = __ldg(G.idx + bk);
-            const double yx = lx - px, yy = ly - py;
-            M.Yx += yx; M.Yy += yy;
-            M.Mxx = fma(yx, bx, M.Mxx); M.Mxy = fma(yx, by, M.Mxy);
-            M.Myx = fma(yy, bx, M.Myx); M.Myy = fma(yy, by, M.Myy);
-            if (owned) {
-                if (lab != run_arg) {
-                    if (run_n) stat_add(S, p, run_arg, run_dx, run_dy, run_n);
-                    run_arg = lab; run_n = 0; run_dx = 0.0; run_dy = 0.0;
-                }
-                run_dx += wx - lx; run_dy += wy - ly; ++run_n;
-            }
-        }
-        if (owned) p.c[i] = lab;
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}"
+                     : "=r"(done) : "r"(mb), "r"(parity) : "memory");
     }
-    if (run_n) stat_add(S, p, run_arg, run_dx, run_dy, run_n);
 }
 
-template <bool STAGED>
 __global__ void __launch_bounds__(FS_THREADS, 4)
 k_sweep_fused(const FusedParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FusedSmemFixed& S = *reinterpret_cast<FusedSmemFixed*>(smem_raw);
-    double* sbx = reinterpret_cast<double*>(smem_raw + sizeof(FusedSmemFixed));
-    double* sby = sbx + p.obs_cap + 2;
+    double2* sb = reinterpret_cast<double2*>(smem_raw + sizeof(FusedSmemFixed));   // staged observations; later run sums
+    int* sbk = reinterpret_cast<int*>(sb + p.obs_cap);                              // winner's grid position (-1 far)
+    unsigned short* srn = reinterpret_cast<unsigned short*>(sbk + p.obs_cap);       // run length at run heads
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tb = blockIdx.x * FS_OWN;
     const int T = p.T;
     // ---- tile loads ---------------------------------------------------------------------------
@@ -288,89 +268,196 @@ k_sweep_fused(const FusedParams p)
         S.u[1][li] = ok ? p.u[p.ldu + t] : 0.0;
         S.off[li] = p.off[min(max(t, 0), T)];
     }
-    for (int h = tid; h < FS_HASH; h += FS_THREADS) { S.hkey[h] = -1; S.hcnt[h] = 0; S.hsx[h] = 0; S.hsy[h] = 0; }
-    if (tid == 0) S.nfar_scans = 0;
-    const int t_first = max(tb - 1, 0), t_last = min(tb + FS_OWN - 1, T - 1);     // scans processed by this block
-    const int obase_raw = p.off[t_first], oend = p.off[t_last + 1];
-    const int obase = obase_raw & ~1;                                            // 16-byte aligned source
-    const bool staged = STAGED && (oend - obase) <= p.obs_cap;
-    if (STAGED) {
-        if (tid == 0) {
-            const uint32_t mb = smem_u32(&S.mbar);
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
+    for (int h = tid; h < FS_HASH; h += FS_THREADS) { S.hkey[h] = -1; S.hcnt[h] = 0; S.hsx[h][0] = S.hsx[h][1] = 0u; S.hsy[h][0] = S.hsy[h][1] = 0u; }
+    const uint32_t mb = smem_u32(&S.mbar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (STAGED && staged && tid == 0) {
-        const uint32_t mb = smem_u32(&S.mbar);
-        const uint32_t bytes = (uint32_t)(((oend - obase + 1) & ~1) * 8);
-        if (bytes > 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(2u * bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32(sbx)), "l"(p.bx + obase), "r"(bytes), "r"(mb) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32(sby)), "l"(p.by + obase), "r"(bytes), "r"(mb) : "memory");
-        } else {
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb) : "memory");
+    // ---- per-pose projection parameters: thread tid <-> pose tb-2+tid --------------------------------
+    {
+        const int t = tb - 2 + tid;
+        if (t >= 0 && t < T) {
+            double px = S.xs[0][tid], py = S.xs[1][tid], th = S.xs[2][tid];
+            double st, ct, sh, ch;
+            if (t == 0) {                                        // scan 0 is projected with self.x0; x[:,0] is only a neighbour
+                sincos(th, &sh, &ch);
+                px = p.x0[0]; py = p.x0[1]; th = p.x0[2];
+                sincos(sub_rn(th, ICM_HALFPI), &st, &ct);
+            } else {
+                sincos(sub_rn(th, ICM_HALFPI), &st, &ct);        // make_rot: cos/sin of (theta - pi/2)
+                sh = ct; ch = -st;
+            }
+            S.pp[tid] = make_double2(px, py); S.rsc[tid] = make_double2(st, ct); S.sn[tid] = sh; S.cs[tid] = ch;
         }
     }
-    // ---- thread -> pose --------------------------------------------------------------------------
+    // ---- thread -> pose for phase B ---------------------------------------------------------------------
     const int grp = tid >> 6, j = tid & (FS_HALF - 1);          // grp 0: odd poses, grp 1: even poses
     const int t = grp == 0 ? tb - 1 + 2 * j : tb + 2 * j;
     const int li = t - (tb - 2);
     const bool spare = grp == 1 && j == FS_HALF - 1;            // even lane 63 (pose tb+126 belongs to the next tile)
     const bool valid = !spare && t >= 0 && t < T;
     const bool owned = valid && !(grp == 0 && j == 0);          // the halo pose tb-1 is recomputed, not owned
-    double px = 0.0, py = 0.0, th = 0.0, st = 0.0, ct = 1.0;
-    if (valid) {
-        if (t == 0) { px = p.x0[0]; py = p.x0[1]; th = p.x0[2]; }
-        else { px = S.xs[0][li]; py = S.xs[1][li]; th = S.xs[2][li]; }
-        sincos(sub_rn(th, ICM_HALFPI), &st, &ct);               // make_rot: cos/sin of (theta - pi/2)
-        double sh, ch;                                           // sin/cos of the heading itself, for the neighbours
-        if (t == 0) sincos(S.xs[2][li], &sh, &ch);               // x[:,0] may differ from x0
-        else { sh = ct; ch = -st; }
-        S.sn[li] = sh; S.cs[li] = ch;
-    } else if (spare && tb - 2 >= 0) {                          // heading of the pose left of the halo
-        double sh, ch;
-        sincos(S.xs[2][0], &sh, &ch);
-        S.sn[0] = sh; S.cs[0] = ch;
-    }
-    // ---- phase A ---------------------------------------------------------------------------------
-    FGrid G;
-    G.g = *p.geom;
-    G.cell_start = p.cell_start; G.pts = p.gpts; G.idx = p.gidx;
-    const bool have_map = p.st->lsearch > 0;
     Mom M;
     M.n = M.Bx = M.By = M.Bxx = M.Byy = M.Bxy = M.Yx = M.Yy = M.Mxx = M.Mxy = M.Myx = M.Myy = 0.0;
     int nfar = 0;
     double fsx = 0.0, fsy = 0.0, FBx = 0.0, FBy = 0.0;
-    int o = 0, e = 0;
-    if (valid) { o = S.off[li]; e = S.off[li + 1]; }
-    if (!have_map) { G.g.nx = 1; G.g.ny = 1; G.cell_start = p.cell_start; }   // (cell_start is all zero then: no candidates)
-    if (STAGED && staged) {
-        const uint32_t mb = smem_u32(&S.mbar);
-        uint32_t done = 0;
-        while (!done) {
-            asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}"
-                         : "=r"(done) : "r"(mb), "r"(0u) : "memory");
+
+    FGrid G;
+    G.g = *p.geom;
+    G.cell_start = p.cell_start; G.pts = p.gpts; G.idx = p.gidx;
+    const bool have_map = p.st->lsearch > 0;
+    const int t_first = max(tb - 1, 0), t_last = min(tb + FS_OWN - 1, T - 1);     // scans processed by this block
+    const int lt_first = t_first - (tb - 2), lt_last = t_last - (tb - 2);
+    __syncthreads();
+    // ---- chunks of whole scans whose observations fit the shared-memory budget (normally one) -----------
+    uint32_t parity = 0;
+    for (int c_lo = lt_first; c_lo <= lt_last;) {
+        int c_hi = lt_last;
+        if (S.off[lt_last + 1] - S.off[c_lo] > p.obs_cap) {
+            int lo = c_lo, hi = lt_last;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (S.off[mid + 1] - S.off[c_lo] <= p.obs_cap) lo = mid; else hi = mid - 1;
+            }
+            c_hi = lo;
         }
-        fused_phase_a<true>(p, S, G, sbx, sby, obase, o, e, px, py, st, ct, owned, M, nfar, fsx, fsy, FBx, FBy);
-    } else {
-        fused_phase_a<false>(p, S, G, sbx, sby, obase, o, e, px, py, st, ct, owned, M, nfar, fsx, fsy, FBx, FBy);
+        const int co = S.off[c_lo], ce = S.off[c_hi + 1];
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)(ce - co) * 16u;
+            if (bytes > 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(sb)), "l"(p.bxy + co), "r"(bytes), "r"(mb) : "memory");
+            } else {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb) : "memory");
+            }
+        }
+        mbar_wait(mb, parity);
+        parity ^= 1u;
+        // ---- phase A: lanes over consecutive observations: project + associate -------------------------
+        {
+            const int m = ce - co;
+            const int per = (((m + FS_WARPS - 1) / FS_WARPS) + 63) & ~63;
+            const int wa = co + warp * per, wb = min(wa + per, ce);
+            int lt0 = c_lo;
+            {   // scan of the lane's first observation: largest lt in [c_lo, c_hi] with off[lt] <= i
+                const int i = wa + lane;
+                int lo = c_lo, hi = c_hi;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (S.off[mid] <= i) lo = mid; else hi = mid - 1;
+                }
+                lt0 = lo;
+            }
+            for (int base = wa; base < wb; base += 64) {
+                const int i0 = base + lane, i1 = i0 + 32;
+                const bool a0 = i0 < wb, a1 = i1 < wb;
+                const double2 b0 = a0 ? sb[i0 - co] : make_double2(0.0, 0.0);
+                const double2 b1 = a1 ? sb[i1 - co] : make_double2(0.0, 0.0);
+                if (a0) while (lt0 < c_hi && i0 >= S.off[lt0 + 1]) ++lt0;
+                int lt1 = lt0;
+                if (a1) while (lt1 < c_hi && i1 >= S.off[lt1 + 1]) ++lt1;
+                const double2 pp0 = S.pp[lt0], rc0 = S.rsc[lt0], pp1 = S.pp[lt1], rc1 = S.rsc[lt1];
+                // tras_rot_z: numpy's matmul order, acc = a0*b0; acc = fma(a1, b1, acc); + translation
+                const double wx0 = add_rn(__fma_rn(b0.y, -rc0.x, mul_rn(b0.x, rc0.y)), pp0.x);
+                const double wy0 = add_rn(__fma_rn(b0.y, rc0.y, mul_rn(b0.x, rc0.x)), pp0.y);
+                const double wx1 = add_rn(__fma_rn(b1.y, -rc1.x, mul_rn(b1.x, rc1.y)), pp1.x);
+                const double wy1 = add_rn(__fma_rn(b1.y, rc1.y, mul_rn(b1.x, rc1.x)), pp1.y);
+                int s0 = 0, e0 = 0, s1 = 0, e1 = 0;
+                if (have_map) {
+                    const int c0 = fgrid_cell(G.g, wx0, wy0), c1 = fgrid_cell(G.g, wx1, wy1);
+                    if (a0) { s0 = __ldg(G.cell_start + c0); e0 = __ldg(G.cell_start + c0 + 1); }
+                    if (a1) { s1 = __ldg(G.cell_start + c1); e1 = __ldg(G.cell_start + c1 + 1); }
+                }
+                double best0, best1, lx, ly;
+                const int bk0 = fgrid_scan(G, wx0, wy0, s0, e0, best0, lx, ly);
+                const int bk1 = fgrid_scan(G, wx1, wy1, s1, e1, best1, lx, ly);
+                const bool far0 = bk0 < 0 || best0 > p.thr2_hi;   // amin > dist_thr (ICM_SLAM.py:172)
+                const bool far1 = bk1 < 0 || best1 > p.thr2_hi;
+                if (a0) {
+                    sbk[i0 - co] = far0 ? -1 : bk0;
+                    if (lt0 >= 2) p.c[i0] = far0 ? -1 : __ldg(G.idx + bk0);   // the halo scan (lt == 1) is not owned
+                }
+                if (a1) {
+                    sbk[i1 - co] = far1 ? -1 : bk1;
+                    if (lt1 >= 2) p.c[i1] = far1 ? -1 : __ldg(G.idx + bk1);
+                }
+                lt0 = lt1;
+            }
+        }
+        __syncthreads();     // sbk of the whole chunk visible
+        // ---- phase B, pass 1 (thread per pose): runs of equal winners -> in-place run records -------------
+        const bool mine = valid && li >= c_lo && li <= c_hi;
+        int o = 0, e = 0;
+        if (mine) { o = S.off[li] - co; e = S.off[li + 1] - co; }
+        {
+            int run_start = o, cur = o < e ? sbk[o] : -1;
+            double Sbx = 0.0, Sby = 0.0;
+            for (int i = o; i < e; ++i) {
+                const double2 b = sb[i];
+                const int bk = sbk[i];
+                M.n += 1.0;
+                M.Bx += b.x; M.By += b.y;
+                M.Bxx = fma(b.x, b.x, M.Bxx); M.Byy = fma(b.y, b.y, M.Byy); M.Bxy = fma(b.x, b.y, M.Bxy);
+                if (bk != cur) {
+                    sb[run_start] = make_double2(Sbx, Sby);
+                    srn[run_start] = (unsigned short)(i - run_start);
+                    run_start = i; cur = bk; Sbx = 0.0; Sby = 0.0;
+                }
+                Sbx += b.x; Sby += b.y;
+            }
+            if (o < e) {
+                sb[run_start] = make_double2(Sbx, Sby);
+                srn[run_start] = (unsigned short)(e - run_start);
+            }
+        }
+        // ---- phase B, pass 2: one run per step, lanes in lockstep: moments + landmark statistics ---------
+        {
+            const double2 pq = mine ? S.pp[li] : make_double2(0.0, 0.0), rc = mine ? S.rsc[li] : make_double2(0.0, 1.0);
+            const double px = pq.x, py = pq.y, st = rc.x, ct = rc.y;
+            int i = o;
+            while (__any_sync(FULLMASK, i < e)) {
+                if (i < e) {
+                    const int n = srn[i];
+                    const int bk = sbk[i];
+                    const double2 sxy = sb[i];
+                    const double dn = (double)n;
+                    const double rwx = fma(ct, sxy.x, -st * sxy.y), rwy = fma(st, sxy.x, ct * sxy.y);   // sum of rotated beams
+                    if (bk < 0) {          // far run: new label statistics (np.sum(obs[c==i]) up to rounding order)
+                        nfar += n;
+                        fsx += fma(dn, px, rwx); fsy += fma(dn, py, rwy);
+                        FBx += sxy.x; FBy += sxy.y;
+                    } else {
+                        const double2 q = __ldg(p.gpts + bk);
+                        const double yx = q.x - px, yy = q.y - py;
+                        M.Yx = fma(dn, yx, M.Yx); M.Yy = fma(dn, yy, M.Yy);
+                        M.Mxx = fma(yx, sxy.x, M.Mxx); M.Mxy = fma(yx, sxy.y, M.Mxy);
+                        M.Myx = fma(yy, sxy.x, M.Myx); M.Myy = fma(yy, sxy.y, M.Myy);
+                        if (owned) stat_add(S, p, __ldg(G.idx + bk), rwx - dn * yx, rwy - dn * yy, n);   // sum of (obs - landmark)
+                    }
+                    i += n;
+                }
+            }
+        }
+        c_lo = c_hi + 1;
+        if (c_lo <= lt_last) __syncthreads();   // the next chunk overwrites the staging buffers
     }
+    const int o_n = valid ? S.off[li + 1] - S.off[li] : 0;
     if (owned) {
         p.nfar[t] = nfar;
-        if (nfar > 0) { p.far_sx[t] = fsx; p.far_sy[t] = fsy; atomicAdd(&S.nfar_scans, 1); }
+        if (nfar > 0) { p.far_sx[t] = fsx; p.far_sy[t] = fsy; }
     }
+    double px = 0.0, py = 0.0, st = 0.0, ct = 1.0;
+    if (valid) { px = S.pp[li].x; py = S.pp[li].y; st = S.rsc[li].x; ct = S.rsc[li].y; }
     if (nfar > 0) {   // far observations see the mean of the scan's new label (PREV view, raw = sum / k)
         const double yx = fsx / (double)nfar - px, yy = fsy / (double)nfar - py;
         M.Yx += (double)nfar * yx; M.Yy += (double)nfar * yy;
         M.Mxx = fma(yx, FBx, M.Mxx); M.Mxy = fma(yx, FBy, M.Mxy);
         M.Myx = fma(yy, FBx, M.Myx); M.Myy = fma(yy, FBy, M.Myy);
     }
-    __syncthreads();     // sn/cs of all input headings visible
-    // ---- phase B: red (odd) then black (even) -----------------------------------------------------
+    __syncthreads();
     unsigned long long my_iters = 0;
     for (int phase = 0; phase < 2; ++phase) {
         if (phase == grp && valid) {
@@ -381,7 +468,7 @@ k_sweep_fused(const FusedParams p)
                 // neighbours: old poses for the odd phase, new (odd) poses for the even phase
                 double (*X)[FS_XT] = phase == 0 ? S.xs : S.xn;
                 const bool has_next = t + 1 < T;
-                if (e == o) {     // sensors.py:147-151
+                if (o_n == 0) {     // sensors.py:147-151
                     for (int r = 0; r < 3; ++r) {
                         const double prev = (t == 1) ? p.x0[r] : X[r][li - 1];
                         res[r] = (prev + X[r][li + 1]) / 2.0;
@@ -397,8 +484,8 @@ k_sweep_fused(const FusedParams p)
                     P.D0x = S.inc[0][li - 1]; P.D0y = S.inc[1][li - 1]; P.dth0 = S.inc[2][li - 1];
                     P.D1x = S.inc[0][li]; P.D1y = S.inc[1][li]; P.dth1 = S.inc[2][li];
                     P.has_next = has_next ? 1 : 0;
-                    // start at the pose's own input heading: its sin/cos are already known (ct, -st)
-                    const int it = newton_lean(p.cfg, P, M, px, py, th, ct, -st, p.tol, p.maxit, res, s_new, c_new);
+                    // start at the pose's own input heading: its sin/cos are already known
+                    const int it = newton_lean(p.cfg, P, M, S.xs[0][li], S.xs[1][li], S.xs[2][li], ct, -st, p.tol, p.maxit, res, s_new, c_new);
                     my_iters += (unsigned long long)it;
                 }
             }
@@ -409,7 +496,7 @@ k_sweep_fused(const FusedParams p)
     }
     if (p.iters) {
         my_iters = (unsigned long long)warp_sum_i((int)my_iters);
-        if ((tid & 31) == 0 && my_iters) atomicAdd(p.iters, my_iters);
+        if (lane == 0 && my_iters) atomicAdd(p.iters, my_iters);
     }
     // ---- outputs ----------------------------------------------------------------------------------
     const int n_own = min(FS_OWN, T - tb);
@@ -420,14 +507,21 @@ k_sweep_fused(const FusedParams p)
     for (int h = tid; h < FS_HASH; h += FS_THREADS) {
         const int key = S.hkey[h];
         if (key >= 0 && S.hcnt[h] > 0) {
-            atomicAdd((unsigned long long*)(p.fsum_x + key), (unsigned long long)S.hsx[h]);
-            atomicAdd((unsigned long long*)(p.fsum_y + key), (unsigned long long)S.hsy[h]);
+            atomicAdd((unsigned long long*)(p.fsum_x + key), ((unsigned long long)S.hsx[h][1] << 32) | S.hsx[h][0]);
+            atomicAdd((unsigned long long*)(p.fsum_y + key), ((unsigned long long)S.hsy[h][1] << 32) | S.hsy[h][0]);
             atomicAdd(p.cnt + key, S.hcnt[h]);
         }
     }
 }
 
-static size_t fused_smem_bytes(int obs_cap) { return sizeof(FusedSmemFixed) + (size_t)2 * (obs_cap + 2) * 8 + 16; }
+// interleaves the extraction's (bx, by) arrays into the double2 records the fused kernel stages
+__global__ void k_interleave(const double* __restrict__ bx, const double* __restrict__ by, int64_t n, double2* __restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_double2(bx[i], by[i]);
+}
+
+static size_t fused_smem_bytes(int obs_cap) { return sizeof(FusedSmemFixed) + (size_t)obs_cap * 22 + 32; }   // obs_cap is even
 
 // ---- after the fused kernel: new labels ------------------------------------------------------------
 // label(t) = lact0 + (number of earlier scans with a far observation) (ICM_SLAM.py:174-182, one new

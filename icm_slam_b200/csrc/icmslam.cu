@@ -62,9 +62,10 @@ struct icmslam_handle {
     bool fused_ok = false;
     double *d_inc = nullptr /*3 x T odometry increments*/, *d_x2 = nullptr /*3 x T, pose double buffer*/;
     double *d_far_sx = nullptr, *d_far_sy = nullptr;
+    double2* d_bxy = nullptr;    // interleaved (bx, by) records for the TMA staging
     long long *d_fsum_x = nullptr, *d_fsum_y = nullptr;
     int fg_cells = 0;            // cell budget of the fast grid (host constant)
-    int *d_fg_cnt = nullptr, *d_fg_start = nullptr, *d_fg_idx = nullptr, *d_fg_cell = nullptr;
+    int *d_fg_cnt = nullptr, *d_fg_start = nullptr, *d_fg_idx = nullptr;
     double2* d_fg_pts = nullptr;
     FGeom* d_fg_geom = nullptr;
     unsigned long long* d_bb = nullptr;
@@ -121,7 +122,7 @@ static void free_dataset(icmslam_handle* h)
     DFREE(h->d_off); DFREE(h->d_beam); DFREE(h->d_scan_of); DFREE(h->d_d); DFREE(h->d_bx); DFREE(h->d_by);
     DFREE(h->d_c); DFREE(h->d_keys_out); DFREE(h->d_iota); DFREE(h->d_sorted); DFREE(h->d_seen_x); DFREE(h->d_seen_y);
     DFREE(h->d_nfar); DFREE(h->d_flag); DFREE(h->d_prefix); DFREE(h->d_x);
-    DFREE(h->d_inc); DFREE(h->d_x2); DFREE(h->d_far_sx); DFREE(h->d_far_sy);
+    DFREE(h->d_inc); DFREE(h->d_x2); DFREE(h->d_far_sx); DFREE(h->d_far_sy); DFREE(h->d_bxy);
     h->fused_ok = false;
     h->extracted = false;
     h->n = 0;
@@ -139,7 +140,7 @@ extern "C" int icmslam_destroy(icmslam_handle* h)
     DFREE(h->d_map_in); DFREE(h->d_map_out); DFREE(h->d_tmp_a); DFREE(h->d_tmp_b);
     DFREE(h->d_cell_start); DFREE(h->d_cell_fill); DFREE(h->d_cell_id); DFREE(h->d_gidx); DFREE(h->d_glx); DFREE(h->d_gly);
     DFREE(h->d_st); DFREE(h->d_cub);
-    DFREE(h->d_fsum_x); DFREE(h->d_fsum_y); DFREE(h->d_fg_cnt); DFREE(h->d_fg_start); DFREE(h->d_fg_idx); DFREE(h->d_fg_cell);
+    DFREE(h->d_fsum_x); DFREE(h->d_fsum_y); DFREE(h->d_fg_cnt); DFREE(h->d_fg_start); DFREE(h->d_fg_idx);
     DFREE(h->d_fg_pts); DFREE(h->d_fg_geom); DFREE(h->d_bb);
     if (h->h_st) cudaFreeHost(h->h_st);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -222,9 +223,8 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     if (e == cudaSuccess) e = dalloc(&h->d_fsum_y, L);
     if (e == cudaSuccess) e = dalloc(&h->d_fg_cnt, (size_t)h->fg_cells + 2);
     if (e == cudaSuccess) e = dalloc(&h->d_fg_start, (size_t)h->fg_cells + 2);
-    if (e == cudaSuccess) e = dalloc(&h->d_fg_idx, L);
-    if (e == cudaSuccess) e = dalloc(&h->d_fg_cell, L);
-    if (e == cudaSuccess) e = dalloc(&h->d_fg_pts, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_fg_idx, 4 * L);    // replicated binning: <= 4 cells per landmark
+    if (e == cudaSuccess) e = dalloc(&h->d_fg_pts, 4 * L);
     if (e == cudaSuccess) e = dalloc(&h->d_fg_geom, 1);
     if (e == cudaSuccess) e = dalloc(&h->d_bb, 4);
     if (e == cudaSuccess) e = cudaMemset(h->d_fsum_x, 0, L * sizeof(long long));
@@ -346,7 +346,7 @@ extern "C" int icmslam_extract(icmslam_handle* h)
     h->first_empty = off[1] == off[0];
     h->last_empty = off[T] == off[T - 1];
     const size_t n = (size_t)h->n;
-    DFREE(h->d_beam); DFREE(h->d_scan_of); DFREE(h->d_d); DFREE(h->d_bx); DFREE(h->d_by);
+    DFREE(h->d_beam); DFREE(h->d_scan_of); DFREE(h->d_d); DFREE(h->d_bx); DFREE(h->d_by); DFREE(h->d_bxy);
     DFREE(h->d_c); DFREE(h->d_keys_out); DFREE(h->d_iota); DFREE(h->d_sorted); DFREE(h->d_seen_x); DFREE(h->d_seen_y);
     CK(dalloc(&h->d_beam, n)); CK(dalloc(&h->d_scan_of, n)); CK(dalloc(&h->d_d, n)); CK(dalloc(&h->d_bx, n + 2)); CK(dalloc(&h->d_by, n + 2));
     CK(cudaMemsetAsync(h->d_bx, 0, (n + 2) * sizeof(double), h->stream));
@@ -356,6 +356,9 @@ extern "C" int icmslam_extract(icmslam_handle* h)
                                                           nwords, d_masks, nullptr, h->d_off, h->d_beam, h->d_d, h->d_bx,
                                                           h->d_by, h->d_scan_of);
     CK(cudaGetLastError());
+    CK(dalloc(&h->d_bxy, n + 2));
+    k_interleave<<<nblk((int64_t)n, 256), 256, 0, h->stream>>>(h->d_bx, h->d_by, (int64_t)n, h->d_bxy);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
     cudaFree(d_masks);
     cudaFree(d_counts);
@@ -364,21 +367,25 @@ extern "C" int icmslam_extract(icmslam_handle* h)
         int mx = 0;
         for (int tb = 0; tb < T; tb += FS_OWN) {
             int t0 = tb > 0 ? tb - 1 : 0, t1 = tb + FS_OWN < T ? tb + FS_OWN : T;
-            int m = off[t1] - (off[t0] & ~1);
+            int m = off[t1] - off[t0];
             if (m > mx) mx = m;
         }
         h->max_tile_obs = mx;
-        const size_t per_block = (size_t)(232448 - 3 * 1024) / 3;            // aim at >= 3 blocks per SM
-        int cap3 = (int)((per_block - sizeof(FusedSmemFixed) - 16) / 16) - 2;
+        int blocks_per_sm = 2;
+        const char* envb = getenv("ICMSLAM_BLOCKS_PER_SM");
+        if (envb && atoi(envb) > 0) blocks_per_sm = atoi(envb);
+        const size_t per_block = (size_t)(233472 - blocks_per_sm * 1024) / blocks_per_sm;
+        int cap = (int)((per_block - sizeof(FusedSmemFixed) - 32) / 22);
         const char* env = getenv("ICMSLAM_OBS_CAP");
-        if (env && atoi(env) > 0) cap3 = atoi(env);
-        const int cap_max = (int)((232448 - sizeof(FusedSmemFixed) - 16) / 16) - 2;
-        if (cap3 > cap_max) cap3 = cap_max;
-        h->obs_cap = mx < cap3 ? mx : cap3;
-        if (h->obs_cap < 2) h->obs_cap = 2;
-        h->obs_cap = (h->obs_cap + 1) & ~1;
+        if (env && atoi(env) > 0) cap = atoi(env);
+        const int cap_max = (int)((232448 - sizeof(FusedSmemFixed) - 32) / 22);
+        if (cap > cap_max) cap = cap_max;
+        if (cap > mx) cap = mx;                                    // the whole tile fits: one chunk
+        if (cap < h->max_per_scan) cap = h->max_per_scan;          // a chunk holds at least one whole scan
+        if (cap < 2) cap = 2;
+        h->obs_cap = (cap + 1) & ~1;
         h->fused_smem = fused_smem_bytes(h->obs_cap);
-        CK(cudaFuncSetAttribute(k_sweep_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
+        CK(cudaFuncSetAttribute(k_sweep_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
         h->fused_ok = true;
     }
     return ICMSLAM_OK;
@@ -559,11 +566,11 @@ static int build_fgrid(icmslam_handle* h, const double* px, const double* py, co
     CK(cudaGetLastError());
     k_fgrid_geom<<<1, 1, 0, s>>>(h->d_bb, n_ptr, h->dcfg.dist_thr, h->fg_cells, h->d_fg_geom);
     CK(cudaGetLastError());
-    k_fgrid_count<<<nblk(n_cap, 256), 256, 0, s>>>(px, py, n_ptr, h->d_fg_geom, h->d_fg_cnt, h->d_fg_cell);
+    k_fgrid_count<<<nblk(n_cap, 256), 256, 0, s>>>(px, py, n_ptr, h->d_fg_geom, h->d_fg_cnt);
     CK(cudaGetLastError());
     int rc = exclusive_sum(h, h->d_fg_cnt, h->d_fg_start, h->fg_cells + 1);
     if (rc) return rc;
-    k_fgrid_fill<<<nblk(n_cap, 256), 256, 0, s>>>(px, py, n_ptr, h->d_fg_cell, h->d_fg_start, h->d_fg_cnt, h->d_fg_pts, h->d_fg_idx);
+    k_fgrid_fill<<<nblk(n_cap, 256), 256, 0, s>>>(px, py, n_ptr, h->d_fg_geom, h->d_fg_start, h->d_fg_cnt, h->d_fg_pts, h->d_fg_idx);
     CK(cudaGetLastError());
     h->n_launch += 5;
     return ICMSLAM_OK;
@@ -604,7 +611,7 @@ static int sweep_core(icmslam_handle* h, const double* xin, int64_t ldin, double
         int64_t kld = ldout;
         if (xin == xout) { kout = (xin == h->d_x2) ? h->d_x : h->d_x2; kld = T; }
         FusedParams P;
-        P.T = T; P.off = h->d_off; P.bx = h->d_bx; P.by = h->d_by;
+        P.T = T; P.off = h->d_off; P.bxy = h->d_bxy;
         P.xin = xin; P.ldin = ldin; P.xout = kout; P.ldout = kld;
         P.x0[0] = x0[0]; P.x0[1] = x0[1]; P.x0[2] = x0[2];
         P.inc = h->d_inc; P.ldinc = T; P.u = h->d_u; P.ldu = T;
@@ -614,7 +621,7 @@ static int sweep_core(icmslam_handle* h, const double* xin, int64_t ldin, double
         P.nfar = h->d_nfar; P.far_sx = h->d_far_sx; P.far_sy = h->d_far_sy;
         P.obs_cap = h->obs_cap; P.iters = iters;
         if (timing) CK(cudaEventRecord(h->ev[0], s));
-        k_sweep_fused<true><<<nblk(T, FS_OWN), FS_THREADS, h->fused_smem, s>>>(P);
+        k_sweep_fused<<<nblk(T, FS_OWN), FS_THREADS, h->fused_smem, s>>>(P);
         CK(cudaGetLastError());
         if (timing) CK(cudaEventRecord(h->ev[1], s));
         h->n_launch += 1;
