@@ -139,34 +139,29 @@ k_fgrid_fill(const double* __restrict__ px, const double* __restrict__ py, const
 }
 
 // Nearest landmark of (wx, wy) among the cell's entries [s, e).  Returns the winner's position in the
-// cell-sorted arrays (-1 if no candidate), its squared distance `best` (INFINITY if none) and its
-// coordinates.
-__device__ __forceinline__ int fgrid_scan(const FGrid& G, double wx, double wy, int s, int e, double& best, double& lx, double& ly)
+// cell-sorted arrays (-1 if no candidate) and its squared distance `best` (INFINITY if none).
+// Squared distances are compared against a 2^-50 window around the current best; only inside the
+// window (an almost exact tie) are the rooted values formed, as cdist + np.argmin compare them.
+__device__ __forceinline__ int fgrid_scan(const FGrid& G, double wx, double wy, int s, int e, double& best)
 {
     best = INFINITY;
-    lx = 0.0; ly = 0.0;
+    double lo = INFINITY, hi = INFINITY;
     int bk = -1;
     for (int k = s; k < e; ++k) {
         const double2 p = __ldg(G.pts + k);
         const double s2 = dist2_rn(p.x - wx, p.y - wy);
-        bool take;
-        if (bk < 0) take = true;
-        else {
-            const double lo = best * (1.0 - 8.8817841970012523e-16), hi = best * (1.0 + 8.8817841970012523e-16);   // 2^-50
-            if (s2 < lo) take = true;
-            else if (s2 > hi) take = false;
-            else {   // (almost) equidistant: decide on the rooted values like np.argmin over cdist
-                const double dk = __dsqrt_rn(s2), db = __dsqrt_rn(best);
-                take = dk < db || (dk == db && __ldg(G.idx + k) < __ldg(G.idx + bk));
-            }
+        bool take = s2 < lo;
+        if (!take && s2 <= hi && bk >= 0) {   // (almost) equidistant
+            const double dk = __dsqrt_rn(s2), db = __dsqrt_rn(best);
+            take = dk < db || (dk == db && __ldg(G.idx + k) < __ldg(G.idx + bk));
         }
-        if (take) { best = s2; bk = k; lx = p.x; ly = p.y; }
+        if (take) { best = s2; bk = k; lo = s2 * (1.0 - 8.8817841970012523e-16); hi = s2 * (1.0 + 8.8817841970012523e-16); }
     }
     return bk;
 }
 
-__device__ __forceinline__ int fgrid_nearest(const FGrid& G, double wx, double wy, double& best, double& lx, double& ly)
+__device__ __forceinline__ int fgrid_nearest(const FGrid& G, double wx, double wy, double& best)
 {
     const int c = fgrid_cell(G.g, wx, wy);
-    return fgrid_scan(G, wx, wy, __ldg(G.cell_start + c), __ldg(G.cell_start + c + 1), best, lx, ly);
+    return fgrid_scan(G, wx, wy, __ldg(G.cell_start + c), __ldg(G.cell_start + c + 1), best);
 }

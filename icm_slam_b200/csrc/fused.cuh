@@ -33,9 +33,10 @@
 #include "assoc.cuh"
 #include "fastgrid.cuh"
 
-#define FS_THREADS 128
+#define FS_THREADS 256        // 8 warps: all of them associate (phase A) and build moments; warps 0-3 solve the poses
 #define FS_HALF 64
-#define FS_WARPS 4
+#define FS_WARPS 8
+#define FS_SLOTS 128           // pose slots (thread pairs) of a block
 #define FS_OWN 126            // poses owned by a block: tb .. tb+125 (tb even)
 #define FS_XT 132             // pose-tile entries: poses tb-2 .. tb+126 (129 used)
 #define FS_HASH 256           // landmark slots of the block-level statistics table
@@ -203,6 +204,8 @@ struct __align__(16) FusedSmemFixed {
     int hkey[FS_HASH];
     int hcnt[FS_HASH];
     unsigned hsx[FS_HASH][2], hsy[FS_HASH][2];     // fixed-point sums as (lo, hi) 32-bit halves: native shared atomics
+    double mom[12][FS_SLOTS];      // moment sums per pose slot (pair leader -> solver thread)
+    int onum[FS_SLOTS];            // observations of the slot's scan
     unsigned long long mbar;
 };
 
@@ -244,7 +247,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t mb, uint32_t parity)
     }
 }
 
-__global__ void __launch_bounds__(FS_THREADS, 4)
+__global__ void __launch_bounds__(FS_THREADS, 2)
 k_sweep_fused(const FusedParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -252,6 +255,7 @@ k_sweep_fused(const FusedParams p)
     double2* sb = reinterpret_cast<double2*>(smem_raw + sizeof(FusedSmemFixed));   // staged observations; later run sums
     int* sbk = reinterpret_cast<int*>(sb + p.obs_cap);                              // winner's grid position (-1 far)
     unsigned short* srn = reinterpret_cast<unsigned short*>(sbk + p.obs_cap);       // run length at run heads
+    unsigned char* slt = reinterpret_cast<unsigned char*>(srn + p.obs_cap);         // scan (local pose index) of each observation
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tb = blockIdx.x * FS_OWN;
@@ -276,7 +280,7 @@ k_sweep_fused(const FusedParams p)
     }
     __syncthreads();
     // ---- per-pose projection parameters: thread tid <-> pose tb-2+tid --------------------------------
-    {
+    if (tid < FS_SLOTS) {
         const int t = tb - 2 + tid;
         if (t >= 0 && t < T) {
             double px = S.xs[0][tid], py = S.xs[1][tid], th = S.xs[2][tid];
@@ -292,13 +296,13 @@ k_sweep_fused(const FusedParams p)
             S.pp[tid] = make_double2(px, py); S.rsc[tid] = make_double2(st, ct); S.sn[tid] = sh; S.cs[tid] = ch;
         }
     }
-    // ---- thread -> pose for phase B ---------------------------------------------------------------------
-    const int grp = tid >> 6, j = tid & (FS_HALF - 1);          // grp 0: odd poses, grp 1: even poses
-    const int t = grp == 0 ? tb - 1 + 2 * j : tb + 2 * j;
-    const int li = t - (tb - 2);
-    const bool spare = grp == 1 && j == FS_HALF - 1;            // even lane 63 (pose tb+126 belongs to the next tile)
-    const bool valid = !spare && t >= 0 && t < T;
-    const bool owned = valid && !(grp == 0 && j == 0);          // the halo pose tb-1 is recomputed, not owned
+    // ---- pose slots: slot q is worked by the thread pair (2q, 2q+1) in phase B and solved by thread q -----
+    //      slots 0..63: odd poses tb-1+2j (slot 0 = halo), slots 64..127: even poses tb+2j (slot 127 spare)
+    const int q = tid >> 1, half = tid & 1;
+    const int qt = q < FS_HALF ? tb - 1 + 2 * q : tb + 2 * (q - FS_HALF);
+    const int qli = qt - (tb - 2);
+    const bool qvalid = q != FS_SLOTS - 1 && qt >= 0 && qt < T;
+    const bool qowned = qvalid && q != 0;                       // the halo pose tb-1 is recomputed, not owned
     Mom M;
     M.n = M.Bx = M.By = M.Bxx = M.Byy = M.Bxy = M.Yx = M.Yy = M.Mxx = M.Mxy = M.Myx = M.Myy = 0.0;
     int nfar = 0;
@@ -334,31 +338,29 @@ k_sweep_fused(const FusedParams p)
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb) : "memory");
             }
         }
+        // the slot's half of its scan's observations (indices relative to the chunk)
+        const bool mine = qvalid && qli >= c_lo && qli <= c_hi;
+        int o = 0, e = 0;
+        if (mine) {
+            const int so = S.off[qli] - co, se = S.off[qli + 1] - co, h1 = (se - so + 1) >> 1;
+            o = half ? so + h1 : so;
+            e = half ? se : so + h1;
+        }
+        for (int i = o; i < e; ++i) slt[i] = (unsigned char)qli;     // (while the bulk copy is in flight)
         mbar_wait(mb, parity);
         parity ^= 1u;
+        __syncthreads();
         // ---- phase A: lanes over consecutive observations: project + associate -------------------------
         {
             const int m = ce - co;
             const int per = (((m + FS_WARPS - 1) / FS_WARPS) + 63) & ~63;
-            const int wa = co + warp * per, wb = min(wa + per, ce);
-            int lt0 = c_lo;
-            {   // scan of the lane's first observation: largest lt in [c_lo, c_hi] with off[lt] <= i
-                const int i = wa + lane;
-                int lo = c_lo, hi = c_hi;
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (S.off[mid] <= i) lo = mid; else hi = mid - 1;
-                }
-                lt0 = lo;
-            }
+            const int wa = warp * per, wb = min(wa + per, m);
             for (int base = wa; base < wb; base += 64) {
                 const int i0 = base + lane, i1 = i0 + 32;
                 const bool a0 = i0 < wb, a1 = i1 < wb;
-                const double2 b0 = a0 ? sb[i0 - co] : make_double2(0.0, 0.0);
-                const double2 b1 = a1 ? sb[i1 - co] : make_double2(0.0, 0.0);
-                if (a0) while (lt0 < c_hi && i0 >= S.off[lt0 + 1]) ++lt0;
-                int lt1 = lt0;
-                if (a1) while (lt1 < c_hi && i1 >= S.off[lt1 + 1]) ++lt1;
+                const double2 b0 = a0 ? sb[i0] : make_double2(0.0, 0.0);
+                const double2 b1 = a1 ? sb[i1] : make_double2(0.0, 0.0);
+                const int lt0 = a0 ? slt[i0] : c_lo, lt1 = a1 ? slt[i1] : c_lo;
                 const double2 pp0 = S.pp[lt0], rc0 = S.rsc[lt0], pp1 = S.pp[lt1], rc1 = S.rsc[lt1];
                 // tras_rot_z: numpy's matmul order, acc = a0*b0; acc = fma(a1, b1, acc); + translation
                 const double wx0 = add_rn(__fma_rn(b0.y, -rc0.x, mul_rn(b0.x, rc0.y)), pp0.x);
@@ -371,27 +373,23 @@ k_sweep_fused(const FusedParams p)
                     if (a0) { s0 = __ldg(G.cell_start + c0); e0 = __ldg(G.cell_start + c0 + 1); }
                     if (a1) { s1 = __ldg(G.cell_start + c1); e1 = __ldg(G.cell_start + c1 + 1); }
                 }
-                double best0, best1, lx, ly;
-                const int bk0 = fgrid_scan(G, wx0, wy0, s0, e0, best0, lx, ly);
-                const int bk1 = fgrid_scan(G, wx1, wy1, s1, e1, best1, lx, ly);
+                double best0, best1;
+                const int bk0 = fgrid_scan(G, wx0, wy0, s0, e0, best0);
+                const int bk1 = fgrid_scan(G, wx1, wy1, s1, e1, best1);
                 const bool far0 = bk0 < 0 || best0 > p.thr2_hi;   // amin > dist_thr (ICM_SLAM.py:172)
                 const bool far1 = bk1 < 0 || best1 > p.thr2_hi;
                 if (a0) {
-                    sbk[i0 - co] = far0 ? -1 : bk0;
-                    if (lt0 >= 2) p.c[i0] = far0 ? -1 : __ldg(G.idx + bk0);   // the halo scan (lt == 1) is not owned
+                    sbk[i0] = far0 ? -1 : bk0;
+                    if (lt0 >= 2) p.c[co + i0] = far0 ? -1 : __ldg(G.idx + bk0);   // the halo scan (lt == 1) is not owned
                 }
                 if (a1) {
-                    sbk[i1 - co] = far1 ? -1 : bk1;
-                    if (lt1 >= 2) p.c[i1] = far1 ? -1 : __ldg(G.idx + bk1);
+                    sbk[i1] = far1 ? -1 : bk1;
+                    if (lt1 >= 2) p.c[co + i1] = far1 ? -1 : __ldg(G.idx + bk1);
                 }
-                lt0 = lt1;
             }
         }
         __syncthreads();     // sbk of the whole chunk visible
-        // ---- phase B, pass 1 (thread per pose): runs of equal winners -> in-place run records -------------
-        const bool mine = valid && li >= c_lo && li <= c_hi;
-        int o = 0, e = 0;
-        if (mine) { o = S.off[li] - co; e = S.off[li + 1] - co; }
+        // ---- phase B, pass 1 (thread pair per pose): runs of equal winners -> in-place run records --------
         {
             int run_start = o, cur = o < e ? sbk[o] : -1;
             double Sbx = 0.0, Sby = 0.0;
@@ -415,7 +413,7 @@ k_sweep_fused(const FusedParams p)
         }
         // ---- phase B, pass 2: one run per step, lanes in lockstep: moments + landmark statistics ---------
         {
-            const double2 pq = mine ? S.pp[li] : make_double2(0.0, 0.0), rc = mine ? S.rsc[li] : make_double2(0.0, 1.0);
+            const double2 pq = mine ? S.pp[qli] : make_double2(0.0, 0.0), rc = mine ? S.rsc[qli] : make_double2(0.0, 1.0);
             const double px = pq.x, py = pq.y, st = rc.x, ct = rc.y;
             int i = o;
             while (__any_sync(FULLMASK, i < e)) {
@@ -425,17 +423,17 @@ k_sweep_fused(const FusedParams p)
                     const double2 sxy = sb[i];
                     const double dn = (double)n;
                     const double rwx = fma(ct, sxy.x, -st * sxy.y), rwy = fma(st, sxy.x, ct * sxy.y);   // sum of rotated beams
-                    if (bk < 0) {          // far run: new label statistics (np.sum(obs[c==i]) up to rounding order)
+                    if (bk < 0) {          // far run: statistics of the scan's new label
                         nfar += n;
                         fsx += fma(dn, px, rwx); fsy += fma(dn, py, rwy);
                         FBx += sxy.x; FBy += sxy.y;
                     } else {
-                        const double2 q = __ldg(p.gpts + bk);
-                        const double yx = q.x - px, yy = q.y - py;
+                        const double2 lm = __ldg(p.gpts + bk);
+                        const double yx = lm.x - px, yy = lm.y - py;
                         M.Yx = fma(dn, yx, M.Yx); M.Yy = fma(dn, yy, M.Yy);
                         M.Mxx = fma(yx, sxy.x, M.Mxx); M.Mxy = fma(yx, sxy.y, M.Mxy);
                         M.Myx = fma(yy, sxy.x, M.Myx); M.Myy = fma(yy, sxy.y, M.Myy);
-                        if (owned) stat_add(S, p, __ldg(G.idx + bk), rwx - dn * yx, rwy - dn * yy, n);   // sum of (obs - landmark)
+                        if (qowned) stat_add(S, p, __ldg(G.idx + bk), rwx - dn * yx, rwy - dn * yy, n);   // sum of (obs - landmark)
                     }
                     i += n;
                 }
@@ -444,66 +442,88 @@ k_sweep_fused(const FusedParams p)
         c_lo = c_hi + 1;
         if (c_lo <= lt_last) __syncthreads();   // the next chunk overwrites the staging buffers
     }
-    const int o_n = valid ? S.off[li + 1] - S.off[li] : 0;
-    if (owned) {
-        p.nfar[t] = nfar;
-        if (nfar > 0) { p.far_sx[t] = fsx; p.far_sy[t] = fsy; }
-    }
-    double px = 0.0, py = 0.0, st = 0.0, ct = 1.0;
-    if (valid) { px = S.pp[li].x; py = S.pp[li].y; st = S.rsc[li].x; ct = S.rsc[li].y; }
-    if (nfar > 0) {   // far observations see the mean of the scan's new label (PREV view, raw = sum / k)
-        const double yx = fsx / (double)nfar - px, yy = fsy / (double)nfar - py;
-        M.Yx += (double)nfar * yx; M.Yy += (double)nfar * yy;
-        M.Mxx = fma(yx, FBx, M.Mxx); M.Mxy = fma(yx, FBy, M.Mxy);
-        M.Myx = fma(yy, FBx, M.Myx); M.Myy = fma(yy, FBy, M.Myy);
+    // ---- combine the pair's partial sums; the pair leader publishes the slot's moments ---------------------
+    {
+#define FS_PAIR(v) v += __shfl_xor_sync(FULLMASK, v, 1)
+        FS_PAIR(M.n); FS_PAIR(M.Bx); FS_PAIR(M.By); FS_PAIR(M.Bxx); FS_PAIR(M.Byy); FS_PAIR(M.Bxy);
+        FS_PAIR(M.Yx); FS_PAIR(M.Yy); FS_PAIR(M.Mxx); FS_PAIR(M.Mxy); FS_PAIR(M.Myx); FS_PAIR(M.Myy);
+        FS_PAIR(fsx); FS_PAIR(fsy); FS_PAIR(FBx); FS_PAIR(FBy);
+        nfar += __shfl_xor_sync(FULLMASK, nfar, 1);
+#undef FS_PAIR
+        if (half == 0) {
+            if (qowned) {
+                p.nfar[qt] = nfar;
+                if (nfar > 0) { p.far_sx[qt] = fsx; p.far_sy[qt] = fsy; }
+            }
+            if (nfar > 0) {   // far observations see the mean of the scan's new label (PREV view, raw = sum / k)
+                const double px = S.pp[qli].x, py = S.pp[qli].y;
+                const double yx = fsx / (double)nfar - px, yy = fsy / (double)nfar - py;
+                M.Yx += (double)nfar * yx; M.Yy += (double)nfar * yy;
+                M.Mxx = fma(yx, FBx, M.Mxx); M.Mxy = fma(yx, FBy, M.Mxy);
+                M.Myx = fma(yy, FBx, M.Myx); M.Myy = fma(yy, FBy, M.Myy);
+            }
+            S.mom[0][q] = M.n; S.mom[1][q] = M.Bx; S.mom[2][q] = M.By; S.mom[3][q] = M.Bxx; S.mom[4][q] = M.Byy; S.mom[5][q] = M.Bxy;
+            S.mom[6][q] = M.Yx; S.mom[7][q] = M.Yy; S.mom[8][q] = M.Mxx; S.mom[9][q] = M.Mxy; S.mom[10][q] = M.Myx; S.mom[11][q] = M.Myy;
+            S.onum[q] = qvalid ? S.off[qli + 1] - S.off[qli] : 0;
+        }
     }
     __syncthreads();
-    unsigned long long my_iters = 0;
-    for (int phase = 0; phase < 2; ++phase) {
-        if (phase == grp && valid) {
-            double res[3], s_new = 0.0, c_new = 1.0;
-            if (t == 0) {
-                res[0] = S.xs[0][li]; res[1] = S.xs[1][li]; res[2] = S.xs[2][li];
-            } else {
-                // neighbours: old poses for the odd phase, new (odd) poses for the even phase
-                double (*X)[FS_XT] = phase == 0 ? S.xs : S.xn;
-                const bool has_next = t + 1 < T;
-                if (o_n == 0) {     // sensors.py:147-151
-                    for (int r = 0; r < 3; ++r) {
-                        const double prev = (t == 1) ? p.x0[r] : X[r][li - 1];
-                        res[r] = (prev + X[r][li + 1]) / 2.0;
-                    }
-                    sincos(res[2], &s_new, &c_new);
+    // ---- pose solve: thread q <-> slot q; warps 0-1 red (odd poses), then warps 2-3 black (even poses) --------
+    {
+        const int sq = tid;                                         // slot solved by this thread (tid < FS_SLOTS)
+        const int grp = sq >> 6;
+        const int t = sq < FS_HALF ? tb - 1 + 2 * sq : tb + 2 * (sq - FS_HALF);
+        const int li = t - (tb - 2);
+        const bool valid = tid < FS_SLOTS && sq != FS_SLOTS - 1 && t >= 0 && t < T;
+        unsigned long long my_iters = 0;
+        for (int phase = 0; phase < 2; ++phase) {
+            if (valid && phase == grp) {
+                double res[3], s_new = 0.0, c_new = 1.0;
+                if (t == 0) {
+                    res[0] = S.xs[0][li]; res[1] = S.xs[1][li]; res[2] = S.xs[2][li];
                 } else {
-                    PoseIn P;
-                    P.ax = X[0][li - 1]; P.ay = X[1][li - 1]; P.ath = X[2][li - 1];
-                    P.sa = S.sn[li - 1]; P.ca = S.cs[li - 1];
-                    P.bx = has_next ? X[0][li + 1] : 0.0; P.by = has_next ? X[1][li + 1] : 0.0; P.bth = has_next ? X[2][li + 1] : 0.0;
-                    P.uav = S.u[0][li - 1]; P.uaw = S.u[1][li - 1];
-                    P.ucv = S.u[0][li]; P.ucw = S.u[1][li];
-                    P.D0x = S.inc[0][li - 1]; P.D0y = S.inc[1][li - 1]; P.dth0 = S.inc[2][li - 1];
-                    P.D1x = S.inc[0][li]; P.D1y = S.inc[1][li]; P.dth1 = S.inc[2][li];
-                    P.has_next = has_next ? 1 : 0;
-                    // start at the pose's own input heading: its sin/cos are already known
-                    const int it = newton_lean(p.cfg, P, M, S.xs[0][li], S.xs[1][li], S.xs[2][li], ct, -st, p.tol, p.maxit, res, s_new, c_new);
-                    my_iters += (unsigned long long)it;
+                    // neighbours: old poses for the odd phase, new (odd) poses for the even phase
+                    double (*X)[FS_XT] = phase == 0 ? S.xs : S.xn;
+                    const bool has_next = t + 1 < T;
+                    if (S.onum[sq] == 0) {     // sensors.py:147-151
+                        for (int r = 0; r < 3; ++r) {
+                            const double prev = (t == 1) ? p.x0[r] : X[r][li - 1];
+                            res[r] = (prev + X[r][li + 1]) / 2.0;
+                        }
+                        sincos(res[2], &s_new, &c_new);
+                    } else {
+                        Mom Q;
+                        Q.n = S.mom[0][sq]; Q.Bx = S.mom[1][sq]; Q.By = S.mom[2][sq]; Q.Bxx = S.mom[3][sq]; Q.Byy = S.mom[4][sq]; Q.Bxy = S.mom[5][sq];
+                        Q.Yx = S.mom[6][sq]; Q.Yy = S.mom[7][sq]; Q.Mxx = S.mom[8][sq]; Q.Mxy = S.mom[9][sq]; Q.Myx = S.mom[10][sq]; Q.Myy = S.mom[11][sq];
+                        PoseIn P;
+                        P.ax = X[0][li - 1]; P.ay = X[1][li - 1]; P.ath = X[2][li - 1];
+                        P.sa = S.sn[li - 1]; P.ca = S.cs[li - 1];
+                        P.bx = has_next ? X[0][li + 1] : 0.0; P.by = has_next ? X[1][li + 1] : 0.0; P.bth = has_next ? X[2][li + 1] : 0.0;
+                        P.uav = S.u[0][li - 1]; P.uaw = S.u[1][li - 1];
+                        P.ucv = S.u[0][li]; P.ucw = S.u[1][li];
+                        P.D0x = S.inc[0][li - 1]; P.D0y = S.inc[1][li - 1]; P.dth0 = S.inc[2][li - 1];
+                        P.D1x = S.inc[0][li]; P.D1y = S.inc[1][li]; P.dth1 = S.inc[2][li];
+                        P.has_next = has_next ? 1 : 0;
+                        // start at the pose's own input heading: its sin/cos are already known
+                        const double st = S.rsc[li].x, ct = S.rsc[li].y;
+                        const int it = newton_lean(p.cfg, P, Q, S.xs[0][li], S.xs[1][li], S.xs[2][li], ct, -st, p.tol, p.maxit, res, s_new, c_new);
+                        my_iters += (unsigned long long)it;
+                    }
                 }
+                S.xn[0][li] = res[0]; S.xn[1][li] = res[1]; S.xn[2][li] = res[2];
+                if (phase == 0) { S.sn[li] = s_new; S.cs[li] = c_new; }   // (old odd headings are no longer needed)
             }
-            S.xn[0][li] = res[0]; S.xn[1][li] = res[1]; S.xn[2][li] = res[2];
-            if (phase == 0) { S.sn[li] = s_new; S.cs[li] = c_new; }   // (old odd headings are no longer needed)
+            __syncthreads();
         }
-        __syncthreads();
-    }
-    if (p.iters) {
-        my_iters = (unsigned long long)warp_sum_i((int)my_iters);
-        if (lane == 0 && my_iters) atomicAdd(p.iters, my_iters);
+        if (p.iters) {
+            my_iters = (unsigned long long)warp_sum_i((int)my_iters);
+            if (lane == 0 && my_iters) atomicAdd(p.iters, my_iters);
+        }
     }
     // ---- outputs ----------------------------------------------------------------------------------
     const int n_own = min(FS_OWN, T - tb);
-    for (int q = tid; q < 3 * n_own; q += FS_THREADS) {
-        const int r = q / n_own, k = q - r * n_own;
-        p.xout[r * p.ldout + tb + k] = S.xn[r][k + 2];
-    }
+    for (int r = 0; r < 3; ++r)
+        for (int k = tid; k < n_own; k += FS_THREADS) p.xout[r * p.ldout + tb + k] = S.xn[r][k + 2];
     for (int h = tid; h < FS_HASH; h += FS_THREADS) {
         const int key = S.hkey[h];
         if (key >= 0 && S.hcnt[h] > 0) {
@@ -521,7 +541,7 @@ __global__ void k_interleave(const double* __restrict__ bx, const double* __rest
     if (i < n) out[i] = make_double2(bx[i], by[i]);
 }
 
-static size_t fused_smem_bytes(int obs_cap) { return sizeof(FusedSmemFixed) + (size_t)obs_cap * 22 + 32; }   // obs_cap is even
+static size_t fused_smem_bytes(int obs_cap) { return sizeof(FusedSmemFixed) + (size_t)obs_cap * 23 + 32; }   // obs_cap is even
 
 // ---- after the fused kernel: new labels ------------------------------------------------------------
 // label(t) = lact0 + (number of earlier scans with a far observation) (ICM_SLAM.py:174-182, one new

@@ -374,11 +374,11 @@ extern "C" int icmslam_extract(icmslam_handle* h)
         int blocks_per_sm = 2;
         const char* envb = getenv("ICMSLAM_BLOCKS_PER_SM");
         if (envb && atoi(envb) > 0) blocks_per_sm = atoi(envb);
-        const size_t per_block = (size_t)(233472 - blocks_per_sm * 1024) / blocks_per_sm;
-        int cap = (int)((per_block - sizeof(FusedSmemFixed) - 32) / 22);
+        const size_t per_block = (size_t)233472 / blocks_per_sm - 1024 - 512;   // 228 KB per SM, 1 KB reserved per block
+        int cap = (int)((per_block - sizeof(FusedSmemFixed) - 32) / 23);
         const char* env = getenv("ICMSLAM_OBS_CAP");
         if (env && atoi(env) > 0) cap = atoi(env);
-        const int cap_max = (int)((232448 - sizeof(FusedSmemFixed) - 32) / 22);
+        const int cap_max = (int)((232448 - sizeof(FusedSmemFixed) - 32) / 23);
         if (cap > cap_max) cap = cap_max;
         if (cap > mx) cap = mx;                                    // the whole tile fits: one chunk
         if (cap < h->max_per_scan) cap = h->max_per_scan;          // a chunk holds at least one whole scan
