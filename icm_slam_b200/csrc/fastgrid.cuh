@@ -66,10 +66,9 @@ k_fgrid_bbox(const double* __restrict__ px, const double* __restrict__ py, const
     }
 }
 
-__global__ void k_fgrid_geom(const unsigned long long* bb, const int* n_ptr, double dist_thr, int max_cells, FGeom* out)
+// cell edge h = 2*thr1*(1+2^-20) grown by 25 % steps until the grid fits the cell budget
+__device__ __forceinline__ FGeom fgrid_make_geom(double mnx, double mny, double mxx, double mxy, double dist_thr, int max_cells)
 {
-    double mnx = 0.0, mny = 0.0, mxx = 0.0, mxy = 0.0;
-    if (*n_ptr > 0 && bb[0] != ~0ull) { mnx = dkey_inv(bb[0]); mny = dkey_inv(bb[1]); mxx = dkey_inv(bb[2]); mxy = dkey_inv(bb[3]); }
     const double thr1 = dist_thr * (1.0 + 9.5367431640625e-07);   // 1 + 2^-20
     double h = 2.0 * thr1 * (1.0 + 9.5367431640625e-07);
     if (!(h > 0.0)) h = 1.0;
@@ -85,7 +84,14 @@ __global__ void k_fgrid_geom(const unsigned long long* bb, const int* n_ptr, dou
     g.ny = __double2int_rd((mxy - mny) * g.inv_h) + 1;
     if (g.nx < 1) g.nx = 1;
     if (g.ny < 1) g.ny = 1;
-    *out = g;
+    return g;
+}
+
+__global__ void k_fgrid_geom(const unsigned long long* bb, const int* n_ptr, double dist_thr, int max_cells, FGeom* out)
+{
+    double mnx = 0.0, mny = 0.0, mxx = 0.0, mxy = 0.0;
+    if (*n_ptr > 0 && bb[0] != ~0ull) { mnx = dkey_inv(bb[0]); mny = dkey_inv(bb[1]); mxx = dkey_inv(bb[2]); mxy = dkey_inv(bb[3]); }
+    *out = fgrid_make_geom(mnx, mny, mxx, mxy, dist_thr, max_cells);
 }
 
 // ---- replicated binning -------------------------------------------------------------------------

@@ -32,6 +32,7 @@
 #include "common.cuh"
 #include "assoc.cuh"
 #include "fastgrid.cuh"
+#include "tail.cuh"
 
 #define FS_THREADS 256        // 8 warps: all of them associate (phase A) and build moments; warps 0-3 solve the poses
 #define FS_HALF 64
@@ -60,7 +61,7 @@ struct FusedParams {
     const int* cell_start; const double2* gpts; const int* gidx;
     int* c;                               // labels per observation (out)
     long long* fsum_x; long long* fsum_y; int* cnt;   // per previous-map landmark statistics
-    int* nfar; double* far_sx; double* far_sy;        // per scan: far observations (new label)
+    FarRec* far_list; TailState* ts; int* blk_far;    // scans with far observations (each creates one new label)
     int obs_cap;                          // shared-memory capacity in observations
     unsigned long long* iters;
 };
@@ -206,6 +207,7 @@ struct __align__(16) FusedSmemFixed {
     unsigned hsx[FS_HASH][2], hsy[FS_HASH][2];     // fixed-point sums as (lo, hi) 32-bit halves: native shared atomics
     double mom[12][FS_SLOTS];      // moment sums per pose slot (pair leader -> solver thread)
     int onum[FS_SLOTS];            // observations of the slot's scan
+    unsigned farbits[4];           // owned scans (bit t - tb) that have far observations
     unsigned long long mbar;
 };
 
@@ -274,6 +276,7 @@ k_sweep_fused(const FusedParams p)
     }
     for (int h = tid; h < FS_HASH; h += FS_THREADS) { S.hkey[h] = -1; S.hcnt[h] = 0; S.hsx[h][0] = S.hsx[h][1] = 0u; S.hsy[h][0] = S.hsy[h][1] = 0u; }
     const uint32_t mb = smem_u32(&S.mbar);
+    if (tid < 4) S.farbits[tid] = 0u;
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -451,10 +454,7 @@ k_sweep_fused(const FusedParams p)
         nfar += __shfl_xor_sync(FULLMASK, nfar, 1);
 #undef FS_PAIR
         if (half == 0) {
-            if (qowned) {
-                p.nfar[qt] = nfar;
-                if (nfar > 0) { p.far_sx[qt] = fsx; p.far_sy[qt] = fsy; }
-            }
+            if (qowned && nfar > 0) atomicOr(&S.farbits[(qt - tb) >> 5], 1u << ((qt - tb) & 31));
             if (nfar > 0) {   // far observations see the mean of the scan's new label (PREV view, raw = sum / k)
                 const double px = S.pp[qli].x, py = S.pp[qli].y;
                 const double yx = fsx / (double)nfar - px, yy = fsy / (double)nfar - py;
@@ -468,6 +468,17 @@ k_sweep_fused(const FusedParams p)
         }
     }
     __syncthreads();
+    // scans with far observations: one record each, ranked in time order within the tile (the label is
+    // lact0 + scans with far observations before it, ICM_SLAM.py:174-182)
+    if (half == 0 && qowned && nfar > 0) {
+        const int bit = qt - tb, w = bit >> 5;
+        int rank = __popc(S.farbits[w] & ((1u << (bit & 31)) - 1u));
+        for (int k = 0; k < w; ++k) rank += __popc(S.farbits[k]);
+        FarRec r;
+        r.t = qt; r.rank = rank; r.n = nfar; r.pad = 0; r.sx = fsx; r.sy = fsy;
+        p.far_list[atomicAdd(&p.ts->far_count, 1)] = r;
+    }
+    if (tid == 0) p.blk_far[blockIdx.x] = __popc(S.farbits[0]) + __popc(S.farbits[1]) + __popc(S.farbits[2]) + __popc(S.farbits[3]);
     // ---- pose solve: thread q <-> slot q; warps 0-1 red (odd poses), then warps 2-3 black (even poses) --------
     {
         const int sq = tid;                                         // slot solved by this thread (tid < FS_SLOTS)
@@ -542,34 +553,6 @@ __global__ void k_interleave(const double* __restrict__ bx, const double* __rest
 }
 
 static size_t fused_smem_bytes(int obs_cap) { return sizeof(FusedSmemFixed) + (size_t)obs_cap * 23 + 32; }   // obs_cap is even
-
-// ---- after the fused kernel: new labels ------------------------------------------------------------
-// label(t) = lact0 + (number of earlier scans with a far observation) (ICM_SLAM.py:174-182, one new
-// label per scan).  Thread per scan; only scans with far observations do any work.
-__global__ void __launch_bounds__(256)
-k_fused_labels(int T, const int* __restrict__ off, DevState* st, const int* __restrict__ nfar, const int* __restrict__ far_prefix,
-               const double* __restrict__ far_sx, const double* __restrict__ far_sy, int Lcap, int* __restrict__ c,
-               double* __restrict__ raw_x, double* __restrict__ raw_y, int* __restrict__ cnt)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
-    const int lact0 = st->lact0;
-    const int k = nfar[t];
-    if (t == T - 1) {
-        const int total = far_prefix[t] + (k > 0 ? 1 : 0);
-        st->n_far_scans = total;
-        st->raw_l = lact0 + total;
-        if (lact0 + total > Lcap) st->status = ST_LABEL_CAP;   // IndexError at ICM_SLAM.py:191
-    }
-    if (k == 0) return;
-    const int label = lact0 + far_prefix[t];
-    if (label >= Lcap) return;
-    raw_x[label] = far_sx[t] / (double)k;
-    raw_y[label] = far_sy[t] / (double)k;
-    cnt[label] = k;
-    for (int i = off[t]; i < off[t + 1]; ++i)
-        if (c[i] < 0) c[i] = label;
-}
 
 // raw map of the previous-map landmarks from the fixed-point statistics + keep flags for all labels;
 // clears the statistics for the next sweep.

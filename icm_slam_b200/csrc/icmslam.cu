@@ -23,6 +23,7 @@ struct icmslam_handle {
     icmslam_config cfg;
     DevCfg dcfg;
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;   // created with the handle; replaced by icmslam_set_stream
     char err[512];
     // dataset
     int B = 0, T = 0, precondition = 0;
@@ -61,7 +62,15 @@ struct icmslam_handle {
     // fused (REDBLACK, NEWTON, PREV) path
     bool fused_ok = false;
     double *d_inc = nullptr /*3 x T odometry increments*/, *d_x2 = nullptr /*3 x T, pose double buffer*/;
-    double *d_far_sx = nullptr, *d_far_sy = nullptr;
+    FarRec* d_far_list = nullptr;
+    int *d_blk_far = nullptr, *d_blk_prefix = nullptr;
+    int n_tiles = 0;
+    TailState* d_ts = nullptr;
+    double thr2_lt = 0.0;        // largest s with sqrt_rn(s) < dist_thr
+    const double* grid_map = nullptr;   // the map buffer the fast grid currently indexes (nullptr: rebuild)
+    struct GraphSlot { cudaGraphExec_t exec = nullptr; const double* src = nullptr; const double* map_in = nullptr; double x0[3] = {0, 0, 0}; double tol = 0; int maxit = 0; };
+    GraphSlot graphs[4];
+    int use_graph = 1;
     double2* d_bxy = nullptr;    // interleaved (bx, by) records for the TMA staging
     long long *d_fsum_x = nullptr, *d_fsum_y = nullptr;
     int fg_cells = 0;            // cell budget of the fast grid (host constant)
@@ -116,13 +125,20 @@ extern "C" const char* icmslam_strerror(int s)
 
 extern "C" const char* icmslam_last_error(const icmslam_handle* h) { return h ? h->err : "null handle"; }
 
+static void drop_graphs(icmslam_handle* h)
+{
+    for (auto& g : h->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+}
+
 static void free_dataset(icmslam_handle* h)
 {
     DFREE(h->d_scans); DFREE(h->d_odo); DFREE(h->d_u); DFREE(h->d_cos); DFREE(h->d_sin); DFREE(h->d_ang);
     DFREE(h->d_off); DFREE(h->d_beam); DFREE(h->d_scan_of); DFREE(h->d_d); DFREE(h->d_bx); DFREE(h->d_by);
     DFREE(h->d_c); DFREE(h->d_keys_out); DFREE(h->d_iota); DFREE(h->d_sorted); DFREE(h->d_seen_x); DFREE(h->d_seen_y);
     DFREE(h->d_nfar); DFREE(h->d_flag); DFREE(h->d_prefix); DFREE(h->d_x);
-    DFREE(h->d_inc); DFREE(h->d_x2); DFREE(h->d_far_sx); DFREE(h->d_far_sy); DFREE(h->d_bxy);
+    DFREE(h->d_inc); DFREE(h->d_x2); DFREE(h->d_far_list); DFREE(h->d_blk_far); DFREE(h->d_blk_prefix); DFREE(h->d_bxy);
+    drop_graphs(h);
+    h->grid_map = nullptr;
     h->fused_ok = false;
     h->extracted = false;
     h->n = 0;
@@ -141,9 +157,10 @@ extern "C" int icmslam_destroy(icmslam_handle* h)
     DFREE(h->d_cell_start); DFREE(h->d_cell_fill); DFREE(h->d_cell_id); DFREE(h->d_gidx); DFREE(h->d_glx); DFREE(h->d_gly);
     DFREE(h->d_st); DFREE(h->d_cub);
     DFREE(h->d_fsum_x); DFREE(h->d_fsum_y); DFREE(h->d_fg_cnt); DFREE(h->d_fg_start); DFREE(h->d_fg_idx);
-    DFREE(h->d_fg_pts); DFREE(h->d_fg_geom); DFREE(h->d_bb);
+    DFREE(h->d_fg_pts); DFREE(h->d_fg_geom); DFREE(h->d_bb); DFREE(h->d_ts);
     if (h->h_st) cudaFreeHost(h->h_st);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return ICMSLAM_OK;
 }
@@ -227,6 +244,9 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     if (e == cudaSuccess) e = dalloc(&h->d_fg_pts, 4 * L);
     if (e == cudaSuccess) e = dalloc(&h->d_fg_geom, 1);
     if (e == cudaSuccess) e = dalloc(&h->d_bb, 4);
+    if (e == cudaSuccess) e = dalloc(&h->d_ts, 1);
+    if (e == cudaSuccess) e = cudaMemset(h->d_ts, 0, sizeof(TailState));
+    { const char* eg = getenv("ICMSLAM_GRAPH"); if (eg) h->use_graph = atoi(eg); }
     if (e == cudaSuccess) e = cudaMemset(h->d_fsum_x, 0, L * sizeof(long long));
     if (e == cudaSuccess) e = cudaMemset(h->d_fsum_y, 0, L * sizeof(long long));
     if (e == cudaSuccess) e = cudaMemset(h->d_fg_cnt, 0, ((size_t)h->fg_cells + 2) * sizeof(int));
@@ -236,12 +256,18 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
         while (sqrt(nextafter(s2, INFINITY)) <= thr) s2 = nextafter(s2, INFINITY);
         while (s2 > 0.0 && sqrt(s2) > thr) s2 = nextafter(s2, -INFINITY);
         h->thr2_hi = s2;
+        double s3 = thr * thr;
+        while (sqrt(s3) >= thr && s3 > 0.0) s3 = nextafter(s3, -INFINITY);
+        while (sqrt(nextafter(s3, INFINITY)) < thr) s3 = nextafter(s3, INFINITY);
+        h->thr2_lt = s3;
         int ex = thr > 1.0 ? ilogb(thr) + 1 : 0;
         h->fix_scale = ldexp(1.0, 40 - ex);
     }
     if (e == cudaSuccess) e = dalloc(&h->d_st, 1);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_st, sizeof(DevState));
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) h->stream = h->own_stream;
     if (e == cudaSuccess) e = cudaMemset(h->d_st, 0, sizeof(DevState));
     if (e == cudaSuccess) e = cudaMemset(h->d_counts, 0, L * sizeof(double));
     if (e != cudaSuccess) {
@@ -255,7 +281,9 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
 extern "C" int icmslam_set_stream(icmslam_handle* h, void* s)
 {
     if (!h) return ICMSLAM_ERR_INVALID;
-    h->stream = (cudaStream_t)s;
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->stream = s ? (cudaStream_t)s : h->own_stream;   // NULL: back to the handle's own stream
+    drop_graphs(h);
     return ICMSLAM_OK;
 }
 
@@ -289,8 +317,17 @@ extern "C" int icmslam_load(icmslam_handle* h, const double* scans, int32_t B, i
     CK(dalloc(&h->d_prefix, (size_t)T + 1));
     CK(dalloc(&h->d_inc, (size_t)3 * T));
     CK(dalloc(&h->d_x2, (size_t)3 * T));
-    CK(dalloc(&h->d_far_sx, (size_t)T));
-    CK(dalloc(&h->d_far_sy, (size_t)T));
+    h->n_tiles = nblk(T, FS_OWN);
+    CK(dalloc(&h->d_far_list, (size_t)T));
+    CK(dalloc(&h->d_blk_far, (size_t)h->n_tiles));
+    CK(dalloc(&h->d_blk_prefix, (size_t)h->n_tiles));
+    {   // scan workspace for the largest scan of a sweep, so that nothing allocates inside a graph capture
+        size_t need = 0, b = 0;
+        const int lens[3] = {h->Lcap + 1, h->fg_cells + 2, T + 1};
+        for (int k = 0; k < 3; ++k) { CK(cub::DeviceScan::ExclusiveSum(nullptr, b, (const int*)nullptr, (int*)nullptr, lens[k], h->stream)); if (b > need) need = b; }
+        int rcw = ensure_cub(h, need);
+        if (rcw) return rcw;
+    }
     const size_t w = (size_t)T * sizeof(double);
     CK(cudaMemcpy2DAsync(h->d_scans, w, scans, (size_t)ld_scans * sizeof(double), w, B, cudaMemcpyDefault, h->stream));
     CK(cudaMemcpy2DAsync(h->d_odo, w, odo, (size_t)ld_odo * sizeof(double), w, 3, cudaMemcpyDefault, h->stream));
@@ -434,6 +471,7 @@ extern "C" int icmslam_set_landmarks_actuales(icmslam_handle* h, int32_t lact)
     CK(cudaSetDevice(h->cfg.device));
     k_set_lact<<<1, 1, 0, h->stream>>>(h->d_st, lact);
     CK(cudaGetLastError());
+    h->grid_map = nullptr;
     h->lact_host = lact;
     h->lact_dirty = false;
     return ICMSLAM_OK;
@@ -526,8 +564,9 @@ static int run_filter(icmslam_handle* h, const double* raw_x, const double* raw_
     return ICMSLAM_OK;
 }
 
-__global__ void k_sweep_begin(DevState* st, int L_in)
+__global__ void k_sweep_begin(DevState* st, TailState* ts, int L_in)
 {
+    ts->far_count = 0;
     st->lact0 = st->lact;
     st->lsearch = min(st->lact, L_in);
     st->raw_l = st->lact;
@@ -599,14 +638,16 @@ static int sweep_core(icmslam_handle* h, const double* xin, int64_t ldin, double
                            o.map_view == ICMSLAM_VIEW_PREV;
     const int n_search_cap = L_in < 0 ? L : (L_in > 0 ? L_in : 1);
 
-    k_sweep_begin<<<1, 1, 0, s>>>(st, L_in < 0 ? L : L_in);
+    k_sweep_begin<<<1, 1, 0, s>>>(st, h->d_ts, L_in < 0 ? L : L_in);
     CK(cudaGetLastError());
     h->n_launch += 1;
     CK(cudaMemsetAsync(h->d_cnt, 0, ((size_t)L + 1) * sizeof(int), s));
     int rc;
     if (use_fused) {
-        rc = build_fgrid(h, min_x, min_y, &st->lsearch, n_search_cap);
-        if (rc) return rc;
+        if (h->grid_map != h->d_map_in) {      // the grid of the previous sweep's tail does not index this map: build it
+            rc = build_fgrid(h, min_x, min_y, &st->lsearch, n_search_cap);
+            if (rc) return rc;
+        }
         double* kout = xout;
         int64_t kld = ldout;
         if (xin == xout) { kout = (xin == h->d_x2) ? h->d_x : h->d_x2; kld = T; }
@@ -618,26 +659,50 @@ static int sweep_core(icmslam_handle* h, const double* xin, int64_t ldin, double
         P.cfg = h->dcfg; P.thr2_hi = h->thr2_hi; P.fix_scale = h->fix_scale; P.tol = o.newton_tol; P.maxit = o.newton_maxit;
         P.st = st; P.geom = h->d_fg_geom; P.cell_start = h->d_fg_start; P.gpts = h->d_fg_pts; P.gidx = h->d_fg_idx;
         P.c = h->d_c; P.fsum_x = h->d_fsum_x; P.fsum_y = h->d_fsum_y; P.cnt = h->d_cnt;
-        P.nfar = h->d_nfar; P.far_sx = h->d_far_sx; P.far_sy = h->d_far_sy;
+        P.far_list = h->d_far_list; P.ts = h->d_ts; P.blk_far = h->d_blk_far;
         P.obs_cap = h->obs_cap; P.iters = iters;
         if (timing) CK(cudaEventRecord(h->ev[0], s));
-        k_sweep_fused<<<nblk(T, FS_OWN), FS_THREADS, h->fused_smem, s>>>(P);
+        k_sweep_fused<<<h->n_tiles, FS_THREADS, h->fused_smem, s>>>(P);
         CK(cudaGetLastError());
         if (timing) CK(cudaEventRecord(h->ev[1], s));
-        h->n_launch += 1;
         if (kout != xout) CK(cudaMemcpy2DAsync(xout, (size_t)ldout * 8, kout, (size_t)kld * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToDevice, s));
-        // new labels: one per scan that has a far observation, numbered in time order
-        k_flag_positive<<<nblk(T, 256), 256, 0, s>>>(h->d_nfar, T, h->d_flag);
+        // ---- tail (tail.cuh): new labels, Mapa.filtrar, and the grid of the new map -----------------------------
+        TailState* ts = h->d_ts;
+        k_tail_scan<<<1, 1024, 0, s>>>(h->d_blk_far, h->n_tiles, h->d_blk_prefix, st, ts, L, h->d_bb);
         CK(cudaGetLastError());
-        rc = exclusive_sum(h, h->d_flag, h->d_prefix, T);
-        if (rc) return rc;
-        k_fused_labels<<<nblk(T, 256), 256, 0, s>>>(T, h->d_off, st, h->d_nfar, h->d_prefix, h->d_far_sx, h->d_far_sy, L, h->d_c, raw_x,
-                                                    raw_y, h->d_cnt);
+        k_tail_labels<<<148, 256, 0, s>>>(ts, h->d_far_list, h->d_blk_prefix, FS_OWN, h->d_off, st, L, h->d_c, raw_x, raw_y, h->d_cnt);
         CK(cudaGetLastError());
         k_fused_means<<<nblk(L, 256), 256, 0, s>>>(st, h->d_fsum_x, h->d_fsum_y, h->d_cnt, min_x, min_y, 1.0 / h->fix_scale, h->dcfg.cota,
                                                    raw_x, raw_y, h->d_kflag, L);
         CK(cudaGetLastError());
-        h->n_launch += 3;
+        rc = exclusive_sum(h, h->d_kflag, h->d_kpos, L);
+        if (rc) return rc;
+        k_tail_compact<<<nblk(L, 256), 256, 0, s>>>(st, ts, h->d_kflag, h->d_kpos, raw_x, raw_y, h->d_cnt, h->d_kx, h->d_ky, h->d_kc,
+                                                    h->d_parent, h->d_bb, L);
+        CK(cudaGetLastError());
+        k_tail_geom<<<1, 1, 0, s>>>(h->d_bb, st, ts, h->dcfg.dist_thr, h->fg_cells, h->d_fg_geom);
+        CK(cudaGetLastError());
+        k_fgrid_count<<<nblk(L, 256), 256, 0, s>>>(h->d_kx, h->d_ky, &st->kept, h->d_fg_geom, h->d_fg_cnt);
+        CK(cudaGetLastError());
+        rc = exclusive_sum(h, h->d_fg_cnt, h->d_fg_start, h->fg_cells + 1);
+        if (rc) return rc;
+        k_fgrid_fill<<<nblk(L, 256), 256, 0, s>>>(h->d_kx, h->d_ky, &st->kept, h->d_fg_geom, h->d_fg_start, h->d_fg_cnt, h->d_fg_pts,
+                                                  h->d_fg_idx);
+        CK(cudaGetLastError());
+        k_tail_nn<<<nblk(L, 256), 256, 0, s>>>(st, ts, h->d_kx, h->d_ky, h->d_fg_geom, h->d_fg_start, h->d_fg_pts, h->d_fg_idx, h->thr2_lt,
+                                               h->d_nn, h->d_indflag, L);
+        CK(cudaGetLastError());
+        k_tail_finalize<<<nblk(L, 256), 256, 0, s>>>(st, ts, h->d_kx, h->d_ky, h->d_kc, dmap_out, out_cap, out_ld, h->d_counts, L);
+        CK(cudaGetLastError());
+        k_tail_slow<<<1, 1024, 0, s>>>(st, ts, h->dcfg.dist_thr, h->d_kx, h->d_ky, h->d_kc, h->d_parent, h->d_nn, h->d_indflag, h->d_indpos,
+                                       h->d_ind, h->d_lab, h->d_used, h->d_rank, h->d_ox, h->d_oy, h->d_oc, dmap_out, out_cap, out_ld,
+                                       h->d_counts, L, h->fg_cells, h->d_fg_geom, h->d_fg_cnt, h->d_fg_start, h->d_fg_pts, h->d_fg_idx);
+        CK(cudaGetLastError());
+        h->n_launch += 12;
+        h->grid_map = (out_ld == L && out_cap == L) ? dmap_out : nullptr;   // the grid now indexes the new map
+        h->timed_fused = true;
+        h->lact_dirty = true;
+        return ICMSLAM_OK;
     } else {
         if (xin != xout) CK(cudaMemcpy2DAsync(xout, (size_t)ldout * 8, xin, (size_t)ldin * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToDevice, s));
         double* dx = xout;
@@ -715,7 +780,8 @@ static int sweep_core(icmslam_handle* h, const double* xin, int64_t ldin, double
         }
         if (timing) CK(cudaEventRecord(h->ev[3], s));
     }
-    h->timed_fused = use_fused;
+    h->timed_fused = false;
+    h->grid_map = nullptr;
     // Mapa.filtrar (sensors.py:165-166)
     rc = run_filter(h, raw_x, raw_y, h->d_cnt, nullptr, dmap_out, out_cap, out_ld, nullptr, 1);
     if (rc) return rc;
@@ -758,6 +824,7 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
     }
     if (L_in > 0)
         CK(cudaMemcpy2DAsync(h->d_map_in, (size_t)L * 8, map_in, (size_t)ld_map_in * 8, (size_t)L_in * 8, 2, cudaMemcpyDefault, s));
+    h->grid_map = nullptr;
     const bool own_out = (memspace == ICMSLAM_HOST || !map_out);
     int rc = sweep_core(h, xin, ldin, xout, ldout, x0, o, L_in, own_out ? h->d_map_out : map_out, own_out ? L : cap_out,
                         own_out ? (int64_t)L : ld_map_out);
@@ -798,6 +865,7 @@ extern "C" int icmslam_set_map(icmslam_handle* h, const double* map, int32_t L_m
     if (L_map > 0)
         CK(cudaMemcpy2DAsync(h->d_map_in, (size_t)h->Lcap * 8, map, (size_t)ld * 8, (size_t)L_map * 8, 2, cudaMemcpyDefault, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    h->grid_map = nullptr;
     return icmslam_set_landmarks_actuales(h, L_map);
 }
 
@@ -861,12 +929,55 @@ extern "C" int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const
         CK(cudaMemcpy2DAsync(h->d_x, (size_t)T * 8, x, (size_t)ld_x * 8, (size_t)T * 8, 3, cudaMemcpyDefault, s));
         h->x_cur = 0;
     }
+    const bool fused_mode = h->fused_ok && o.fused && o.schedule == ICMSLAM_SCHED_REDBLACK && o.solver == ICMSLAM_SOLVER_NEWTON &&
+                            o.map_view == ICMSLAM_VIEW_PREV;
+    const bool graph_ok = fused_mode && h->use_graph && s != nullptr && (o.reserved & 3) == 0;
     for (int k = 0; k < n_sweeps; ++k) {
-        CK(cudaMemsetAsync(h->d_counts, 0, (size_t)L * sizeof(double), s));
         double* src = h->x_cur ? h->d_x2 : h->d_x;
         double* dst = h->x_cur ? h->d_x : h->d_x2;
-        int rc = sweep_core(h, src, T, dst, T, x0, o, -1, h->d_map_out, L, L);
-        if (rc) return rc;
+        bool launched = false;
+        if (graph_ok && h->grid_map == h->d_map_in) {
+            // steady state: the whole sweep (memsets + 15 kernels) replays as one CUDA graph
+            icmslam_handle::GraphSlot* slot = nullptr;
+            for (auto& g : h->graphs)
+                if (g.exec && g.src == src && g.map_in == h->d_map_in && g.x0[0] == x0[0] && g.x0[1] == x0[1] && g.x0[2] == x0[2] &&
+                    g.tol == o.newton_tol && g.maxit == o.newton_maxit) slot = &g;
+            if (!slot) {
+                for (auto& g : h->graphs) if (!g.exec) { slot = &g; break; }
+                if (!slot) { drop_graphs(h); slot = &h->graphs[0]; }
+                cudaGraph_t graph = nullptr;
+                const int64_t nl0 = h->n_launch;
+                const double* gm = h->grid_map;
+                CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+                int rc = cudaMemsetAsync(h->d_counts, 0, (size_t)L * sizeof(double), s) == cudaSuccess ? ICMSLAM_OK : ICMSLAM_ERR_CUDA;
+                if (!rc) rc = sweep_core(h, src, T, dst, T, x0, o, -1, h->d_map_out, L, L);
+                cudaError_t ce = cudaStreamEndCapture(s, &graph);
+                h->n_launch = nl0;
+                h->grid_map = gm;
+                if (rc || ce != cudaSuccess || !graph) {
+                    if (graph) cudaGraphDestroy(graph);
+                    cudaGetLastError();
+                    snprintf(h->err, sizeof h->err, "graph capture of the sweep failed (%s)", cudaGetErrorString(ce));
+                    return rc ? rc : ICMSLAM_ERR_CUDA;
+                }
+                ce = cudaGraphInstantiate(&slot->exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) { slot->exec = nullptr; snprintf(h->err, sizeof h->err, "cudaGraphInstantiate: %s", cudaGetErrorString(ce)); return ICMSLAM_ERR_CUDA; }
+                slot->src = src; slot->map_in = h->d_map_in; slot->x0[0] = x0[0]; slot->x0[1] = x0[1]; slot->x0[2] = x0[2];
+                slot->tol = o.newton_tol; slot->maxit = o.newton_maxit;
+            }
+            CK(cudaGraphLaunch(slot->exec, s));
+            h->n_launch += 14;                       // kernels of this library inside the graph
+            h->grid_map = h->d_map_out;
+            h->timed_fused = true;
+            h->lact_dirty = true;
+            launched = true;
+        }
+        if (!launched) {
+            CK(cudaMemsetAsync(h->d_counts, 0, (size_t)L * sizeof(double), s));
+            int rc = sweep_core(h, src, T, dst, T, x0, o, -1, h->d_map_out, L, L);
+            if (rc) return rc;
+        }
         h->x_cur ^= 1;
         double* t = h->d_map_in; h->d_map_in = h->d_map_out; h->d_map_out = t;   // mapa_viejo = mapa_refinado (sensors.py:315)
     }

@@ -1,0 +1,333 @@
+// tail.cuh -- what follows the fused sweep kernel: new labels and Mapa.filtrar (ICM_SLAM.py:204-265),
+// arranged so that the common case (no two surviving landmarks closer than dist_thr, i.e. nothing to
+// merge) is a short fixed chain of small kernels with no host round trip, capturable in a CUDA
+// graph, and so that the landmark grid built for the filter's neighbour search IS the association
+// grid of the next sweep (same points: the filtered map).
+//
+//   k_tail_scan      exclusive scan of the per-tile counts of scans with far observations
+//   k_tail_labels    one thread per far scan: label = lact0 + rank in time order (ICM_SLAM.py:174-182),
+//                    statistics of the new label, rewrite of the scan's far labels
+//   k_fused_means    (fused.cuh) raw map from the fixed-point statistics + keep flags (cota, :231-239)
+//   [cub scan]       positions of the kept landmarks
+//   k_tail_compact   kept landmarks -> dense arrays + bounding box
+//   k_fgrid_geom / k_fgrid_count / [cub scan] / k_fgrid_fill      (fastgrid.cuh)
+//   k_tail_nn        nearest other survivor of every survivor (:241-245) through the grid
+//   k_tail_finalize  nothing to merge: the survivors are the new map
+//   k_tail_slow      ONE block, only when something must be merged (or the map is degenerate): the
+//                    reference's sequential relabelling (:247-260) and a rebuild of the grid
+#pragma once
+#include "common.cuh"
+#include "assoc.cuh"
+#include "fastgrid.cuh"
+#include "mapfilter.cuh"
+
+struct __align__(16) FarRec {
+    int t, rank, n, pad;
+    double sx, sy;
+};
+
+// Device-side scalars of the fast tail (one per handle).
+struct TailState {
+    int far_count;      // far records appended by the fused kernel this sweep
+    int n_ind;          // survivors with a neighbour closer than dist_thr
+    int degenerate;     // bounding box smaller than dist_thr: the reference's zero-distance rule matters
+    int pad;
+};
+
+__global__ void __launch_bounds__(1024)
+k_tail_scan(const int* __restrict__ blk_far, int nblk_, int* __restrict__ blk_prefix, DevState* st, TailState* ts, int Lcap,
+            unsigned long long* bb)
+{
+    __shared__ int wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (nblk_ + 1023) / 1024;
+    const int lo = min(tid * per, nblk_), hi = min(lo + per, nblk_);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += blk_far[i];
+    int inc = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(FULLMASK, inc, d); if (lane >= d) inc += o; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int v = wsum[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(FULLMASK, v, d); if (lane >= d) v += o; }
+        wsum[lane] = v;
+    }
+    __syncthreads();
+    int run = inc - s + (warp ? wsum[warp - 1] : 0);
+    for (int i = lo; i < hi; ++i) { blk_prefix[i] = run; run += blk_far[i]; }
+    if (tid == 0) {
+        const int total = wsum[31];
+        st->n_far_scans = total;
+        st->raw_l = st->lact0 + total;
+        if (st->lact0 + total > Lcap) st->status = ST_LABEL_CAP;   // IndexError at ICM_SLAM.py:191
+        ts->n_ind = 0;
+        ts->degenerate = 0;
+        bb[0] = bb[1] = ~0ull;
+        bb[2] = bb[3] = 0ull;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_tail_labels(const TailState* ts, const FarRec* __restrict__ far, const int* __restrict__ blk_prefix, int tile, const int* __restrict__ off,
+              const DevState* st, int Lcap, int* __restrict__ c, double* __restrict__ raw_x, double* __restrict__ raw_y, int* __restrict__ cnt)
+{
+    const int nrec = ts->far_count;
+    const int lact0 = st->lact0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nrec; k += gridDim.x * blockDim.x) {
+        const FarRec r = far[k];
+        const int label = lact0 + blk_prefix[r.t / tile] + r.rank;
+        if (label >= Lcap) continue;
+        raw_x[label] = r.sx / (double)r.n;
+        raw_y[label] = r.sy / (double)r.n;
+        cnt[label] = r.n;
+        for (int i = off[r.t]; i < off[r.t + 1]; ++i)
+            if (c[i] < 0) c[i] = label;
+    }
+}
+
+// kept landmarks -> dense (kx, ky, kc), union-find parents, bounding box (ordered-key atomics)
+__global__ void __launch_bounds__(256)
+k_tail_compact(DevState* st, TailState* ts, const int* __restrict__ flag, const int* __restrict__ pos, const double* __restrict__ raw_x,
+               const double* __restrict__ raw_y, const int* __restrict__ cnt, double* __restrict__ kx, double* __restrict__ ky,
+               double* __restrict__ kc, int* __restrict__ parent, unsigned long long* bb, int Lcap)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    if (l < Lcap) {
+        if (flag[l]) {
+            const int p = pos[l];
+            const double x = raw_x[l], y = raw_y[l];
+            kx[p] = x; ky[p] = y; kc[p] = (double)cnt[l];
+            parent[p] = p;
+            mnx = mxx = x; mny = mxy = y;
+        }
+        if (l == Lcap - 1) {
+            st->kept = pos[l] + flag[l];
+            st->n_ind = 0;
+            if (st->kept == 0) st->status |= 4;   // ValueError in the reference (ICM_SLAM.py:241-255)
+        }
+    }
+    mnx = warp_min(mnx); mny = warp_min(mny); mxx = warp_max(mxx); mxy = warp_max(mxy);
+    if ((threadIdx.x % WARP) == 0 && mnx <= mxx) {
+        atomicMin(bb + 0, dkey(mnx)); atomicMin(bb + 1, dkey(mny));
+        atomicMax(bb + 2, dkey(mxx)); atomicMax(bb + 3, dkey(mxy));
+    }
+}
+
+// geometry of the grid over the kept landmarks + degeneracy test (extent < dist_thr)
+__global__ void k_tail_geom(const unsigned long long* bb, const DevState* st, TailState* ts, double dist_thr, int max_cells, FGeom* out)
+{
+    const int n = st->kept;
+    double mnx = 0.0, mny = 0.0, mxx = 0.0, mxy = 0.0;
+    if (n > 0 && bb[0] != ~0ull) { mnx = dkey_inv(bb[0]); mny = dkey_inv(bb[1]); mxx = dkey_inv(bb[2]); mxy = dkey_inv(bb[3]); }
+    *out = fgrid_make_geom(mnx, mny, mxx, mxy, dist_thr, max_cells);
+    ts->degenerate = (fmax(mxx - mnx, mxy - mny) >= dist_thr) ? 0 : 1;
+}
+
+// nearest OTHER survivor (zero distances are never neighbours, ICM_SLAM.py:242) within dist_thr
+__global__ void __launch_bounds__(256)
+k_tail_nn(const DevState* st, TailState* ts, const double* __restrict__ kx, const double* __restrict__ ky, const FGeom* __restrict__ geom,
+          const int* __restrict__ cell_start, const double2* __restrict__ pts, const int* __restrict__ idx, double thr2_lt,
+          int* __restrict__ nn, int* __restrict__ ind_flag, int Lcap)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Lcap) return;
+    const int K = st->kept;
+    if (j >= K || ts->degenerate) { ind_flag[j] = 0; return; }
+    const FGeom g = *geom;
+    const double xj = kx[j], yj = ky[j];
+    const int c = fgrid_cell(g, xj, yj);
+    const int s = cell_start[c], e = cell_start[c + 1];
+    double best = INFINITY, lo = INFINITY, hi = INFINITY;
+    int arg = -1;
+    for (int k = s; k < e; ++k) {
+        const double2 p = pts[k];
+        const int id = idx[k];
+        const double s2 = dist2_rn(p.x - xj, p.y - yj);
+        if (id == j || s2 == 0.0) continue;
+        bool take = s2 < lo;
+        if (!take && s2 <= hi && arg >= 0) {
+            const double dk = __dsqrt_rn(s2), db = __dsqrt_rn(best);
+            take = dk < db || (dk == db && id < arg);
+        }
+        if (take) { best = s2; arg = id; lo = s2 * (1.0 - 8.8817841970012523e-16); hi = s2 * (1.0 + 8.8817841970012523e-16); }
+    }
+    const int f = (arg >= 0 && best <= thr2_lt) ? 1 : 0;      // amin < dist_thr (strict, :245)
+    nn[j] = arg < 0 ? 0 : arg;
+    ind_flag[j] = f;
+    if (f) atomicAdd(&ts->n_ind, 1);
+}
+
+// nothing to merge: the survivors, in order, are the new map (count-weighted mean of one member, :258-260)
+__global__ void __launch_bounds__(256)
+k_tail_finalize(DevState* st, const TailState* ts, const double* __restrict__ kx, const double* __restrict__ ky, const double* __restrict__ kc,
+                double* __restrict__ map_out, int cap_out, int64_t ld_out, double* __restrict__ counts_state, int Lcap)
+{
+    if (ts->n_ind != 0 || ts->degenerate) return;   // k_tail_slow takes over
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= Lcap) return;
+    const int newL = st->kept;
+    const double c = r < newL ? kc[r] : 0.0;
+    if (r < cap_out) {
+        map_out[r] = r < newL ? mul_rn(kx[r], c) / c : 0.0;
+        map_out[ld_out + r] = r < newL ? mul_rn(ky[r], c) / c : 0.0;
+    }
+    counts_state[r] = c;
+    if (r == 0) { st->new_l = newL; st->lact = newL; st->n_ind = 0; }
+}
+
+// ---- the merge path: one block ------------------------------------------------------------------------
+// block-wide exclusive scan of v[0..n) (global memory) into out[0..n); returns the total to all threads
+__device__ int block_exclusive_scan(const int* v, int* out, int n, int* wsum /* >= 33 ints of shared memory */)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nth = blockDim.x;
+    const int per = (n + nth - 1) / nth;
+    const int lo = min(tid * per, n), hi = min(lo + per, n);
+    int s = 0;
+    for (int i = lo; i < hi; ++i) s += v[i];
+    int inc = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(FULLMASK, inc, d); if (lane >= d) inc += o; }
+    __syncthreads();
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int x = lane < (nth >> 5) ? wsum[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(FULLMASK, x, d); if (lane >= d) x += o; }
+        wsum[lane] = x;
+    }
+    __syncthreads();
+    int run = inc - s + (warp ? wsum[warp - 1] : 0);
+    for (int i = lo; i < hi; ++i) { const int a = v[i]; out[i] = run; run += a; }
+    const int total = wsum[(nth >> 5) - 1];
+    __syncthreads();
+    return total;
+}
+
+__global__ void __launch_bounds__(1024)
+k_tail_slow(DevState* st, TailState* ts, double dist_thr, double* kx, double* ky, double* kc, int* parent, int* nn, int* ind_flag,
+            int* ind_pos, int* ind, int* lab, int* used, int* rank, double* ox, double* oy, double* oc, double* map_out, int cap_out,
+            int64_t ld_out, double* counts_state, int Lcap,
+            // grid rebuild over the merged map
+            int max_cells, FGeom* geom, int* cell_cnt, int* cell_start, double2* pts, int* gidx)
+{
+    if (ts->n_ind == 0 && !ts->degenerate) return;
+    __shared__ int wsum[34];
+    __shared__ double red[4][32];
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int K = st->kept;
+    if (ts->degenerate) {
+        // the whole map fits in a dist_thr box: the reference's brute force with zero distances replaced by the
+        // map diameter (:241-245)
+        double m = 0.0;
+        for (int j = tid; j < K; j += nth)
+            for (int i = 0; i < K; ++i) m = fmax(m, dist_rn(kx[i] - kx[j], ky[i] - ky[j]));
+        m = warp_max(m);
+        if ((tid & 31) == 0) red[0][tid >> 5] = m;
+        __syncthreads();
+        double amax = 0.0;
+        for (int w = 0; w < (nth >> 5); ++w) amax = fmax(amax, red[0][w]);
+        for (int j = tid; j < K; j += nth) {
+            double best = INFINITY;
+            int arg = 0;
+            for (int i = 0; i < K; ++i) {
+                double dd = (i == j) ? 0.0 : dist_rn(kx[i] - kx[j], ky[i] - ky[j]);
+                if (dd == 0.0) dd = amax;
+                if (dd < best) { best = dd; arg = i; }
+            }
+            nn[j] = arg;
+            ind_flag[j] = best < dist_thr ? 1 : 0;
+        }
+        for (int j = K + tid; j < Lcap; j += nth) ind_flag[j] = 0;
+        __syncthreads();
+    }
+    // ordered list of the survivors that have a close neighbour
+    const int n_ind = block_exclusive_scan(ind_flag, ind_pos, K, wsum);
+    for (int j = tid; j < K; j += nth) {
+        if (ind_flag[j]) ind[ind_pos[j]] = j;
+        used[j] = 0; ox[j] = 0.0; oy[j] = 0.0; oc[j] = 0.0;
+    }
+    __syncthreads();
+    if (tid == 0) {   // :247-249 -- for i in ind ascending: c[c == c[b[i]]] = c[i]
+        for (int q = 0; q < n_ind; ++q) {
+            const int i = ind[q];
+            const int X = uf_find(parent, nn[i]), Y = uf_find(parent, i);
+            if (X != Y) parent[X] = Y;
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < K; j += nth) {
+        const int r = uf_find(parent, j);
+        lab[j] = r;
+        used[r] = 1;
+    }
+    __syncthreads();
+    const int newL = block_exclusive_scan(used, rank, K, wsum);   // :251-253 dense renumbering in ascending order
+    for (int j = tid; j < K; j += nth) {                           // :258-260 count-weighted means
+        const int r = rank[lab[j]];
+        atomicAdd(ox + r, mul_rn(kx[j], kc[j]));
+        atomicAdd(oy + r, mul_rn(ky[j], kc[j]));
+        atomicAdd(oc + r, kc[j]);
+    }
+    __syncthreads();
+    for (int r = tid; r < Lcap; r += nth) {
+        const double c = r < newL ? oc[r] : 0.0;
+        if (r < cap_out) {
+            map_out[r] = r < newL ? ox[r] / c : 0.0;
+            map_out[ld_out + r] = r < newL ? oy[r] / c : 0.0;
+        }
+        counts_state[r] = c;
+    }
+    if (tid == 0) { st->new_l = newL; st->lact = newL; st->n_ind = n_ind; }
+    __syncthreads();
+    // ---- rebuild the landmark grid over the merged map (it is the next sweep's association grid) -------------
+    {
+        double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+        for (int r = tid; r < newL; r += nth) {
+            const double x = map_out[r], y = map_out[ld_out + r];
+            mnx = fmin(mnx, x); mxx = fmax(mxx, x); mny = fmin(mny, y); mxy = fmax(mxy, y);
+        }
+        mnx = warp_min(mnx); mny = warp_min(mny); mxx = warp_max(mxx); mxy = warp_max(mxy);
+        if ((tid & 31) == 0) { red[0][tid >> 5] = mnx; red[1][tid >> 5] = mny; red[2][tid >> 5] = mxx; red[3][tid >> 5] = mxy; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < (nth >> 5); ++w) {
+                red[0][0] = fmin(red[0][0], red[0][w]); red[1][0] = fmin(red[1][0], red[1][w]);
+                red[2][0] = fmax(red[2][0], red[2][w]); red[3][0] = fmax(red[3][0], red[3][w]);
+            }
+            if (newL <= 0) { red[0][0] = red[1][0] = red[2][0] = red[3][0] = 0.0; }
+            *geom = fgrid_make_geom(red[0][0], red[1][0], red[2][0], red[3][0], dist_thr, max_cells);
+        }
+        __syncthreads();
+        const FGeom g = *geom;
+        const int ncell = g.nx * g.ny;
+        for (int c = tid; c <= max_cells; c += nth) cell_cnt[c] = 0;    // (the fill of the pre-merge grid left zeros; be explicit)
+        __syncthreads();
+        for (int r = tid; r < newL; r += nth) {
+            int cx0, cx1, cy0, cy1;
+            fgrid_cell_range(g, map_out[r], map_out[ld_out + r], cx0, cx1, cy0, cy1);
+            for (int cy = cy0; cy <= cy1; ++cy)
+                for (int cx = cx0; cx <= cx1; ++cx) atomicAdd(cell_cnt + cy * g.nx + cx, 1);
+        }
+        __syncthreads();
+        block_exclusive_scan(cell_cnt, cell_start, ncell + 1, wsum);
+        for (int c = ncell + 1 + tid; c <= max_cells; c += nth) cell_start[c] = cell_start[ncell];
+        __syncthreads();
+        for (int r = tid; r < newL; r += nth) {
+            const double x = map_out[r], y = map_out[ld_out + r];
+            int cx0, cx1, cy0, cy1;
+            fgrid_cell_range(g, x, y, cx0, cx1, cy0, cy1);
+            for (int cy = cy0; cy <= cy1; ++cy)
+                for (int cx = cx0; cx <= cx1; ++cx) {
+                    const int c = cy * g.nx + cx;
+                    const int p = cell_start[c] + atomicSub(cell_cnt + c, 1) - 1;
+                    pts[p] = make_double2(x, y);
+                    gidx[p] = r;
+                }
+        }
+    }
+}

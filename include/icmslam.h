@@ -16,8 +16,10 @@
  *  - every call returns an int status (0 = ok, <0 = error below); nothing throws or exits.
  *    The reference's failure modes are mapped to status codes (see each code).
  *  - one handle per GPU, not thread-safe (the reference solver is not re-entrant either,
- *    sensors.py:214-220).  Work is enqueued on the handle's CUDA stream; calls that return
- *    data to HOST buffers synchronise that stream before returning.
+ *    sensors.py:214-220).  Work is enqueued on the handle's CUDA stream (its own, unless
+ *    icmslam_set_stream is called); calls that return data to HOST buffers synchronise that
+ *    stream before returning.  Callers passing DEVICE buffers produced on another stream order the
+ *    two streams themselves (or share one through icmslam_set_stream).
  *  - there is NO CPU fallback: without a CUDA device icmslam_create fails with
  *    ICMSLAM_ERR_CUDA.
  */
@@ -88,7 +90,9 @@ int icmslam_destroy(icmslam_handle* h);
 int icmslam_abi_version(void);
 const char* icmslam_strerror(int status);
 const char* icmslam_last_error(const icmslam_handle* h);
-/* cudaStream_t to enqueue on (NULL = the legacy default stream). */
+/* cudaStream_t to enqueue on.  A handle is created with its own non-blocking stream; NULL switches
+ * back to it.  (Steady-state sweeps replay as a CUDA graph, which the legacy default stream cannot
+ * capture.) */
 int icmslam_set_stream(icmslam_handle* h, void* cuda_stream);
 int icmslam_synchronize(icmslam_handle* h);
 

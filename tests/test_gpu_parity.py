@@ -246,7 +246,8 @@ def test_filter_map_units_vs_reference_fixture():
     e.close()
 
 
-def test_error_codes_mirror_reference_failures():
+@pytest.mark.parametrize("fused", [False, True])
+def test_error_codes_mirror_reference_failures(fused):
     g = golden("synth_a.npz")
     z = g["observations"].astype(np.float64).copy()
     odo, u = g["odometry"], g["velocities"]
@@ -257,7 +258,7 @@ def test_error_codes_mirror_reference_failures():
     e = _engine(_cfg(**cfgd), z2, odo, u)
     e.landmarks_actuales = g["map_init"].shape[1]
     with pytest.raises(IndexError):
-        e.sweep(g["map_init"].copy(), np.ascontiguousarray(g["x_init"].copy()), odo[:, 0], fused=False)
+        e.sweep(g["map_init"].copy(), np.ascontiguousarray(g["x_init"].copy()), odo[:, 0], fused=fused)
     e.close()
     # empty first scan -> inputs returned unchanged (sensors.py:137-139)
     z3 = z.copy()
@@ -265,20 +266,20 @@ def test_error_codes_mirror_reference_failures():
     e = _engine(_cfg(**cfgd), z3, odo, u)
     e.landmarks_actuales = g["map_init"].shape[1]
     x = np.ascontiguousarray(g["x_init"].copy())
-    st, Lout, mout = e.sweep(g["map_init"].copy(), x, odo[:, 0], fused=False)
+    st, Lout, mout = e.sweep(g["map_init"].copy(), x, odo[:, 0], fused=fused)
     assert st == 1 and np.array_equal(x, g["x_init"]) and np.array_equal(mout, g["map_init"])
     e.close()
     # label capacity -> IndexError (ICM_SLAM.py:191)
     e = _engine(_cfg(L=g["map_init"].shape[1], cota=1.0), z, odo, u)
     e.landmarks_actuales = g["map_init"].shape[1]
     with pytest.raises(IndexError):
-        e.sweep(g["map_init"].copy()[:, :5] + 100.0, np.ascontiguousarray(g["x_init"].copy()), odo[:, 0], fused=False)
+        e.sweep(g["map_init"].copy()[:, :5] + 100.0, np.ascontiguousarray(g["x_init"].copy()), odo[:, 0], fused=fused)
     e.close()
     # nothing reaches cota -> ValueError (ICM_SLAM.py:255)
     e = _engine(_cfg(L=int(g["cfg_L"]), cota=1e9), z, odo, u)
     e.landmarks_actuales = g["map_init"].shape[1]
     with pytest.raises(ValueError):
-        e.sweep(g["map_init"].copy(), np.ascontiguousarray(g["x_init"].copy()), odo[:, 0], fused=False)
+        e.sweep(g["map_init"].copy(), np.ascontiguousarray(g["x_init"].copy()), odo[:, 0], fused=fused)
     e.close()
 
 
@@ -366,3 +367,44 @@ def test_fused_small_smem_budget_fallback(monkeypatch):
     monkeypatch.setenv("ICMSLAM_OBS_CAP", "64")
     d, cfgd = _synthetic_case(625, 1500, 20181 + 9)
     _fused_vs_oracle(d["observations"], d["odometry"], d["velocities"], cfgd, d["map_init"], d["x_init"], 2, False)
+
+
+def test_fused_graph_replay_many_sweeps_c1():
+    """8 chained sweeps on data_IJAC2018.mat (landmarks merge in the filter: the one-block merge path and the
+    grid rebuild run, and from the second sweep on the sweep replays as a CUDA graph) against the oracle."""
+    g = golden("c1_ref.npz")
+    z, odo, u = c1_inputs()
+    orc, ocfg, ext = _oracle(CONFIG_ROS, z, odo, u)
+    e = _engine(_cfg(), z, odo, u)
+    mo = orc.Mapa(ocfg)
+    map_o = g["p0_map"].copy()
+    mo.landmarks_actuales = map_o.shape[1]
+    xo = np.ascontiguousarray(g["p0_x"].copy())
+    e.set_map(g["p0_map"])
+    e.set_poses(xo)
+    for k in range(8):
+        r = orc.sweep(ocfg, mo, ext, odo, u, odo[:, 0], map_o, xo, "redblack", "newton", "prev")
+        map_o = r["map"]
+    e.iterate(None, odo[:, 0], 3)
+    e.iterate(None, odo[:, 0], 5)
+    xg = e.get_poses()
+    mout = e.get_map()
+    assert np.array_equal(e.associations(), r["c"])
+    assert mout.shape == map_o.shape
+    d = np.abs(xg - xo)
+    assert d[:2].max() <= TOL_XY and d[2].max() <= TOL_TH, d.max(axis=1)
+    assert np.max(np.abs(mout - map_o)) <= TOL_XY
+    e.close()
+
+
+def test_fused_launch_count_and_kernel_timer():
+    d, cfgd = _synthetic_case(625, 3000, 20181 + 11)
+    e = _engine(_cfg(**cfgd), d["observations"], d["odometry"], d["velocities"])
+    e.set_map(d["map_init"])
+    e.set_poses(d["x_init"])
+    n0 = e.launch_count()
+    e.iterate(None, d["odometry"][:, 0], 2, timing=True)
+    a, b = e.kernel_ms()
+    assert a > 0.0 and b == 0.0
+    assert e.launch_count() - n0 >= 2 * 14
+    e.close()
