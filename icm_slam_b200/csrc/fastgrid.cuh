@@ -166,6 +166,36 @@ __device__ __forceinline__ int fgrid_scan(const FGrid& G, double wx, double wy, 
     return bk;
 }
 
+// The same scan with the cell's first entry already loaded (p0, id0): lets the caller issue the first
+// gathers of several queries together before any of them is consumed.  `bid` = winner's original index.
+__device__ __forceinline__ int fgrid_scan_pre(const FGrid& G, double wx, double wy, int s, int cnt, double2 p0, int id0, double& best,
+                                              int& bid)
+{
+    best = INFINITY;
+    bid = -1;
+    if (cnt <= 0) return -1;
+    best = dist2_rn(p0.x - wx, p0.y - wy);
+    bid = id0;
+    int bk = s;
+    double lo = best * (1.0 - 8.8817841970012523e-16), hi = best * (1.0 + 8.8817841970012523e-16);
+    for (int k = s + 1; k < s + cnt; ++k) {
+        const double2 p = __ldg(G.pts + k);
+        const double s2 = dist2_rn(p.x - wx, p.y - wy);
+        bool take = s2 < lo;
+        int id = -1;
+        if (!take && s2 <= hi) {   // (almost) equidistant: decide on the rooted values like np.argmin over cdist
+            const double dk = __dsqrt_rn(s2), db = __dsqrt_rn(best);
+            id = __ldg(G.idx + k);
+            take = dk < db || (dk == db && id < bid);
+        }
+        if (take) {
+            best = s2; bk = k; bid = id >= 0 ? id : __ldg(G.idx + k);
+            lo = s2 * (1.0 - 8.8817841970012523e-16); hi = s2 * (1.0 + 8.8817841970012523e-16);
+        }
+    }
+    return bk;
+}
+
 __device__ __forceinline__ int fgrid_nearest(const FGrid& G, double wx, double wy, double& best)
 {
     const int c = fgrid_cell(G.g, wx, wy);

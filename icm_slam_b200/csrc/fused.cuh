@@ -34,12 +34,14 @@
 #include "fastgrid.cuh"
 #include "tail.cuh"
 
-#define FS_THREADS 256        // 8 warps: all of them associate (phase A) and build moments; warps 0-3 solve the poses
-#define FS_HALF 64
-#define FS_WARPS 8
-#define FS_SLOTS 128           // pose slots (thread pairs) of a block
-#define FS_OWN 126            // poses owned by a block: tb .. tb+125 (tb even)
-#define FS_XT 132             // pose-tile entries: poses tb-2 .. tb+126 (129 used)
+// Tile geometry, parametrised by HALF = pose slots per colour (64: 256 threads, 126 owned poses per block;
+// 32: 128 threads, 62 owned poses -- more, smaller blocks per SM whose phases interleave better).
+#define FS_THREADS (4 * HALF)  // a thread PAIR per pose slot
+#define FS_WARPS (FS_THREADS / 32)
+#define FS_SLOTS (2 * HALF)    // slots 0..HALF-1: odd poses tb-1+2j (slot 0 = halo); HALF..: even poses tb+2j (last = spare)
+#define FS_OWN (2 * HALF - 2)  // poses owned by a block: tb .. tb+FS_OWN-1 (tb even)
+#define FS_XT (2 * HALF + 4)   // pose-tile entries: poses tb-2 .. tb+FS_OWN (2*HALF+1 used)
+#define FS_HALF HALF
 #define FS_HASH 256           // landmark slots of the block-level statistics table
 #define FS_PROBES 8
 
@@ -63,6 +65,7 @@ struct FusedParams {
     long long* fsum_x; long long* fsum_y; int* cnt;   // per previous-map landmark statistics
     FarRec* far_list; TailState* ts; int* blk_far;    // scans with far observations (each creates one new label)
     int obs_cap;                          // shared-memory capacity in observations
+    int skip;                             // debug ablation mask (ICMSLAM_SKIP): 1 assoc, 2 pass 1, 4 pass 2, 8 statistics, 16 solve
     unsigned long long* iters;
 };
 
@@ -191,8 +194,79 @@ __device__ __forceinline__ int newton_lean(const DevCfg& cfg, const PoseIn& P, c
     return it;
 }
 
+// The same solve split over a lane pair: lane role 0 carries the x equations, role 1 the y equations.
+// With (a, b) = (cos, sin) of theta for role 0 and of (theta - pi/2) for role 1, both roles evaluate
+// IDENTICAL formulas on their own constants (derived from newton_lean: the y rows are the x rows
+// rotated by -pi/2), so the pair halves the dependent chain of every iteration and the two partial
+// derivatives meet through one shuffle each.  Returns the role's coordinate in `coord`, theta in `th`.
+__device__ __forceinline__ int newton_pair(const DevCfg& cfg, const PoseIn& P, const Mom& M, int role, double ox, double oy, double& th,
+                                           double s, double c, double tol, int maxit, double& coord, double& s_out, double& c_out)
+{
+    const double dt = cfg.dt, k = cfg.kod;
+    const double hn = P.has_next ? 1.0 : 0.0;
+    const double D1x = hn * P.D1x, D1y = hn * P.D1y;
+    const double dv = hn * dt * P.ucv;
+    // role constants
+    const double r = role ? cfg.r2 : cfg.r1, q = role ? cfg.q2 : cfg.q1;
+    const double o_ = role ? oy : ox;
+    const double a_ = (role ? P.ay : P.ax) - o_;
+    const double ga = a_ + dt * ((role ? P.sa : P.ca) * P.uav);
+    const double e0 = a_ + (role ? (P.sa * P.D0x + P.ca * P.D0y) : (P.ca * P.D0x - P.sa * P.D0y));
+    const double bp = hn * ((role ? P.by : P.bx) - o_);
+    const double iS = 1.0 / (r + k + M.n * q + hn * (r + k));
+    const double KA = r * ga + k * e0 + q * (role ? M.Yy : M.Yx) + (r + k) * bp;
+    const double P1 = (r * dv + k * D1x) + q * M.By;
+    const double P2 = q * M.Bx - k * D1y;
+    const double M1 = role ? M.Myx : M.Mxx, M2 = role ? M.Myy : M.Mxy;
+    const double dB = M.Bxx - M.Byy;
+    const double ang2 = (2.0 * cfg.r3 + 2.0 * k) * (1.0 + hn);
+    // angular residual constants: role 0 owns the terms towards t-1, role 1 those towards t+1
+    const double th_ga = P.ath + dt * P.uaw, c3 = P.dth0 + P.ath, c4 = P.dth1 - P.bth, wb = dt * P.ucw - P.bth;
+    // (a, b): role 0 = (cos th, sin th); role 1 = (sin th, -cos th)
+    double a = role ? s : c, b = role ? -c : s;
+    int it = 0;
+    for (;;) {
+        const double A = KA - a * P1 - b * P2, A1 = b * P1 - a * P2, A2 = KA - A;
+        const double ra = a * D1x - b * D1y, rb = b * D1x + a * D1y;
+        const double f2 = bp - dv * a, f21 = dv * b, f4 = bp - ra;
+        double C1 = r * f2 * f21 + k * f4 * rb;
+        double C2 = r * (f21 * f21 + f2 * (dv * a)) + k * (rb * rb + f4 * ra);
+        const double ab = a * b, aa_bb = a * a - b * b;
+        const double Dq = -ab * dB - aa_bb * M.Bxy;                 // sum_i w_x w_y in the role's frame
+        const double Eq = aa_bb * dB - 4.0 * ab * M.Bxy;            // sum_i (w_y^2 - w_x^2)
+        C1 += q * ((b * M2 - a * M1) - Dq);
+        C2 += q * (Eq + (b * M1 + a * M2));
+        double g1 = 2.0 * (C1 - A * A1 * iS);
+        double g2 = 2.0 * (C2 - (A1 * A1 + A * A2) * iS);
+        if (role == 0) g1 += 2.0 * cfg.r3 * entrepi_fast(th - th_ga) - 2.0 * k * entrepi_fast(c3 - th);
+        else if (P.has_next) g1 += 2.0 * cfg.r3 * entrepi_fast(th + wb) + 2.0 * k * entrepi_fast(c4 + th);
+        const double p1 = g1 + __shfl_xor_sync(FULLMASK, g1, 1);
+        double p2 = g2 + __shfl_xor_sync(FULLMASK, g2, 1) + ang2;
+        if (!(p2 > 0.0)) p2 = ang2;
+        const double dth = -p1 * (double)__frcp_rn((float)p2);   // quasi-Newton: 24-bit reciprocal of the curvature, same fixed point
+        th += dth;
+        ++it;
+        if (fabs(dth) <= 0.125) {
+            double sd, cd;
+            sincos_small(dth, sd, cd);
+            const double b2 = b * cd + a * sd;
+            a = a * cd - b * sd;
+            b = b2;
+        } else {
+            sincos(role ? th - ICM_HALFPI : th, &b, &a);
+        }
+        const bool done = fabs(dth) <= tol || it >= maxit;
+        if (__all_sync(FULLMASK, done)) break;
+    }
+    coord = (KA - a * P1 - b * P2) * iS + o_;
+    s_out = role ? a : b;          // sin th
+    c_out = role ? -b : a;         // cos th
+    return it;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+template <int HALF>
 struct __align__(16) FusedSmemFixed {
     double xs[3][FS_XT];           // input poses tb-2 .. tb+126, index lt = t - (tb-2)
     double2 pp[FS_XT];             // projection origin of each scan (self.x0 for scan 0)
@@ -204,15 +278,16 @@ struct __align__(16) FusedSmemFixed {
     int off[FS_XT];                // off[t] at lt (clamped)
     int hkey[FS_HASH];
     int hcnt[FS_HASH];
-    unsigned hsx[FS_HASH][2], hsy[FS_HASH][2];     // fixed-point sums as (lo, hi) 32-bit halves: native shared atomics
-    double mom[12][FS_SLOTS];      // moment sums per pose slot (pair leader -> solver thread)
-    int onum[FS_SLOTS];            // observations of the slot's scan
-    unsigned farbits[4];           // owned scans (bit t - tb) that have far observations
+    unsigned hs[FS_HASH][4];       // fixed-point sums: x (lo, hi), y (lo, hi)
+    unsigned farbits[4];           // owned scans (bit t - tb) that have far observations (FS_OWN <= 128)
     unsigned long long mbar;
 };
 
-// adds one run (label, sum of (obs - landmark), count) to the block-level table
-__device__ __forceinline__ void stat_add(FusedSmemFixed& S, const FusedParams& p, int arg, double rdx, double rdy, int rn)
+// adds one run (label, sum of (obs - landmark), count) to the block-level table.  Shared memory has no
+// native 64-bit atomic add, so a 64-bit fixed-point sum is kept as (lo, hi) 32-bit halves: the low add
+// returns the old value, from which the carry into the high half follows exactly.
+template <int HALF>
+__device__ __forceinline__ void stat_add(FusedSmemFixed<HALF>& S, const FusedParams& p, int arg, double rdx, double rdy, int rn)
 {
     const long long vx = __double2ll_rn(rdx * p.fix_scale), vy = __double2ll_rn(rdy * p.fix_scale);
     unsigned h = ((unsigned)arg * 2654435761u) >> 24;      // FS_HASH = 256
@@ -226,11 +301,11 @@ __device__ __forceinline__ void stat_add(FusedSmemFixed& S, const FusedParams& p
         if (key == arg) {
             const unsigned xl = (unsigned)vx, xh = (unsigned)((unsigned long long)vx >> 32);
             const unsigned yl = (unsigned)vy, yh = (unsigned)((unsigned long long)vy >> 32);
-            const unsigned ox = atomicAdd(&S.hsx[h][0], xl);
-            atomicAdd(&S.hsx[h][1], xh + ((unsigned)(ox + xl) < ox ? 1u : 0u));      // carry out of the low half
-            const unsigned oy = atomicAdd(&S.hsy[h][0], yl);
-            atomicAdd(&S.hsy[h][1], yh + ((unsigned)(oy + yl) < oy ? 1u : 0u));
+            const unsigned ox = atomicAdd(&S.hs[h][0], xl);
+            const unsigned oy = atomicAdd(&S.hs[h][2], yl);
             atomicAdd(&S.hcnt[h], rn);
+            atomicAdd(&S.hs[h][1], xh + ((unsigned)(ox + xl) < ox ? 1u : 0u));      // carry out of the low half
+            atomicAdd(&S.hs[h][3], yh + ((unsigned)(oy + yl) < oy ? 1u : 0u));
             return;
         }
         h = (h + 1) & (FS_HASH - 1);
@@ -249,12 +324,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t mb, uint32_t parity)
     }
 }
 
-__global__ void __launch_bounds__(FS_THREADS, 2)
+template <int HALF>
+__global__ void __launch_bounds__(FS_THREADS, 128 / HALF)
 k_sweep_fused(const FusedParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    FusedSmemFixed& S = *reinterpret_cast<FusedSmemFixed*>(smem_raw);
-    double2* sb = reinterpret_cast<double2*>(smem_raw + sizeof(FusedSmemFixed));   // staged observations; later run sums
+    FusedSmemFixed<HALF>& S = *reinterpret_cast<FusedSmemFixed<HALF>*>(smem_raw);
+    double2* sb = reinterpret_cast<double2*>(smem_raw + sizeof(FusedSmemFixed<HALF>));   // staged observations; later run sums
     int* sbk = reinterpret_cast<int*>(sb + p.obs_cap);                              // winner's grid position (-1 far)
     unsigned short* srn = reinterpret_cast<unsigned short*>(sbk + p.obs_cap);       // run length at run heads
     unsigned char* slt = reinterpret_cast<unsigned char*>(srn + p.obs_cap);         // scan (local pose index) of each observation
@@ -274,7 +350,7 @@ k_sweep_fused(const FusedParams p)
         S.u[1][li] = ok ? p.u[p.ldu + t] : 0.0;
         S.off[li] = p.off[min(max(t, 0), T)];
     }
-    for (int h = tid; h < FS_HASH; h += FS_THREADS) { S.hkey[h] = -1; S.hcnt[h] = 0; S.hsx[h][0] = S.hsx[h][1] = 0u; S.hsy[h][0] = S.hsy[h][1] = 0u; }
+    for (int h = tid; h < FS_HASH; h += FS_THREADS) { S.hkey[h] = -1; S.hcnt[h] = 0; for (int k = 0; k < 4; ++k) S.hs[h][k] = 0u; }
     const uint32_t mb = smem_u32(&S.mbar);
     if (tid < 4) S.farbits[tid] = 0u;
     if (tid == 0) {
@@ -332,7 +408,7 @@ k_sweep_fused(const FusedParams p)
         }
         const int co = S.off[c_lo], ce = S.off[c_hi + 1];
         if (tid == 0) {
-            const uint32_t bytes = (uint32_t)(ce - co) * 16u;
+            const uint32_t bytes = (p.skip & 128) ? 0u : (uint32_t)(ce - co) * 16u;
             if (bytes > 0) {
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -353,47 +429,74 @@ k_sweep_fused(const FusedParams p)
         mbar_wait(mb, parity);
         parity ^= 1u;
         __syncthreads();
-        // ---- phase A: lanes over consecutive observations: project + associate -------------------------
+        // ---- phase A: lanes over consecutive observations, four per lane in flight -----------------------
+        // pass A1: project, locate the grid cell, fetch its entry range   (one level of gathers)
+        // pass A2: fetch the candidates, pick the nearest, gate, label    (second level of gathers)
+        // Splitting the two dependent gather levels into separate sweeps over the warp's slice keeps 4
+        // (A1: 8) independent loads per lane in flight instead of one dependent chain per observation.
         {
             const int m = ce - co;
-            const int per = (((m + FS_WARPS - 1) / FS_WARPS) + 63) & ~63;
+            const int per = (((m + FS_WARPS - 1) / FS_WARPS) + 127) & ~127;
             const int wa = warp * per, wb = min(wa + per, m);
-            for (int base = wa; base < wb; base += 64) {
-                const int i0 = base + lane, i1 = i0 + 32;
-                const bool a0 = i0 < wb, a1 = i1 < wb;
-                const double2 b0 = a0 ? sb[i0] : make_double2(0.0, 0.0);
-                const double2 b1 = a1 ? sb[i1] : make_double2(0.0, 0.0);
-                const int lt0 = a0 ? slt[i0] : c_lo, lt1 = a1 ? slt[i1] : c_lo;
-                const double2 pp0 = S.pp[lt0], rc0 = S.rsc[lt0], pp1 = S.pp[lt1], rc1 = S.rsc[lt1];
-                // tras_rot_z: numpy's matmul order, acc = a0*b0; acc = fma(a1, b1, acc); + translation
-                const double wx0 = add_rn(__fma_rn(b0.y, -rc0.x, mul_rn(b0.x, rc0.y)), pp0.x);
-                const double wy0 = add_rn(__fma_rn(b0.y, rc0.y, mul_rn(b0.x, rc0.x)), pp0.y);
-                const double wx1 = add_rn(__fma_rn(b1.y, -rc1.x, mul_rn(b1.x, rc1.y)), pp1.x);
-                const double wy1 = add_rn(__fma_rn(b1.y, rc1.y, mul_rn(b1.x, rc1.x)), pp1.y);
-                int s0 = 0, e0 = 0, s1 = 0, e1 = 0;
-                if (have_map) {
-                    const int c0 = fgrid_cell(G.g, wx0, wy0), c1 = fgrid_cell(G.g, wx1, wy1);
-                    if (a0) { s0 = __ldg(G.cell_start + c0); e0 = __ldg(G.cell_start + c0 + 1); }
-                    if (a1) { s1 = __ldg(G.cell_start + c1); e1 = __ldg(G.cell_start + c1 + 1); }
+            for (int base = wa; base < wb && !(p.skip & 32); base += 128) {
+                int s_[4], e_[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + u * 32 + lane;
+                    s_[u] = 0; e_[u] = 0;
+                    if (i < wb && have_map) {
+                        const double2 bq = sb[i];
+                        const int lt = slt[i];
+                        const double2 pq = S.pp[lt], rc = S.rsc[lt];
+                        const double wx = add_rn(__fma_rn(bq.y, -rc.x, mul_rn(bq.x, rc.y)), pq.x);
+                        const double wy = add_rn(__fma_rn(bq.y, rc.y, mul_rn(bq.x, rc.x)), pq.y);
+                        const int cc = fgrid_cell(G.g, wx, wy);
+                        s_[u] = __ldg(G.cell_start + cc); e_[u] = __ldg(G.cell_start + cc + 1);
+                    }
                 }
-                double best0, best1;
-                const int bk0 = fgrid_scan(G, wx0, wy0, s0, e0, best0);
-                const int bk1 = fgrid_scan(G, wx1, wy1, s1, e1, best1);
-                const bool far0 = bk0 < 0 || best0 > p.thr2_hi;   // amin > dist_thr (ICM_SLAM.py:172)
-                const bool far1 = bk1 < 0 || best1 > p.thr2_hi;
-                if (a0) {
-                    sbk[i0] = far0 ? -1 : bk0;
-                    if (lt0 >= 2) p.c[co + i0] = far0 ? -1 : __ldg(G.idx + bk0);   // the halo scan (lt == 1) is not owned
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + u * 32 + lane;
+                    if (i < wb) { sbk[i] = s_[u]; srn[i] = (unsigned short)min(e_[u] - s_[u], 65535); }
                 }
-                if (a1) {
-                    sbk[i1] = far1 ? -1 : bk1;
-                    if (lt1 >= 2) p.c[co + i1] = far1 ? -1 : __ldg(G.idx + bk1);
+            }
+            if (p.skip & 32) for (int i = wa + lane; i < wb; i += 32) sbk[i] = -1;
+            for (int base = wa; base < wb && !(p.skip & 32); base += 128) {
+                double wx_[4], wy_[4];
+                double2 p_[4];
+                int id_[4], s_[4], n_[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + u * 32 + lane;
+                    s_[u] = 0; n_[u] = 0; id_[u] = -1; p_[u] = make_double2(0.0, 0.0); wx_[u] = 0.0; wy_[u] = 0.0;
+                    if (i < wb) {
+                        s_[u] = sbk[i]; n_[u] = (p.skip & 1) ? 0 : srn[i];
+                        const double2 bq = sb[i];
+                        const int lt = slt[i];
+                        const double2 pq = S.pp[lt], rc = S.rsc[lt];
+                        // tras_rot_z: numpy's matmul order, acc = a0*b0; acc = fma(a1, b1, acc); + translation
+                        wx_[u] = add_rn(__fma_rn(bq.y, -rc.x, mul_rn(bq.x, rc.y)), pq.x);
+                        wy_[u] = add_rn(__fma_rn(bq.y, rc.y, mul_rn(bq.x, rc.x)), pq.y);
+                        if (n_[u] > 0) { p_[u] = __ldg(G.pts + s_[u]); id_[u] = __ldg(G.idx + s_[u]); }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + u * 32 + lane;
+                    if (i < wb) {
+                        double best;
+                        int bid;
+                        const int bk = fgrid_scan_pre(G, wx_[u], wy_[u], s_[u], n_[u], p_[u], id_[u], best, bid);
+                        const bool far = bk < 0 || best > p.thr2_hi;      // amin > dist_thr (ICM_SLAM.py:172)
+                        sbk[i] = far ? -1 : bk;
+                        if (slt[i] >= 2) p.c[co + i] = far ? -1 : bid;    // the halo scan (lt == 1) is not owned
+                    }
                 }
             }
         }
         __syncthreads();     // sbk of the whole chunk visible
         // ---- phase B, pass 1 (thread pair per pose): runs of equal winners -> in-place run records --------
-        {
+        if (!(p.skip & 2)) {
             int run_start = o, cur = o < e ? sbk[o] : -1;
             double Sbx = 0.0, Sby = 0.0;
             for (int i = o; i < e; ++i) {
@@ -418,34 +521,37 @@ k_sweep_fused(const FusedParams p)
         {
             const double2 pq = mine ? S.pp[qli] : make_double2(0.0, 0.0), rc = mine ? S.rsc[qli] : make_double2(0.0, 1.0);
             const double px = pq.x, py = pq.y, st = rc.x, ct = rc.y;
-            int i = o;
+            int i = (p.skip & 6) ? e : o;
             while (__any_sync(FULLMASK, i < e)) {
-                if (i < e) {
-                    const int n = srn[i];
-                    const int bk = sbk[i];
-                    const double2 sxy = sb[i];
-                    const double dn = (double)n;
-                    const double rwx = fma(ct, sxy.x, -st * sxy.y), rwy = fma(st, sxy.x, ct * sxy.y);   // sum of rotated beams
-                    if (bk < 0) {          // far run: statistics of the scan's new label
-                        nfar += n;
-                        fsx += fma(dn, px, rwx); fsy += fma(dn, py, rwy);
-                        FBx += sxy.x; FBy += sxy.y;
-                    } else {
-                        const double2 lm = __ldg(p.gpts + bk);
-                        const double yx = lm.x - px, yy = lm.y - py;
-                        M.Yx = fma(dn, yx, M.Yx); M.Yy = fma(dn, yy, M.Yy);
-                        M.Mxx = fma(yx, sxy.x, M.Mxx); M.Mxy = fma(yx, sxy.y, M.Mxy);
-                        M.Myx = fma(yy, sxy.x, M.Myx); M.Myy = fma(yy, sxy.y, M.Myy);
-                        if (qowned) stat_add(S, p, __ldg(G.idx + bk), rwx - dn * yx, rwy - dn * yy, n);   // sum of (obs - landmark)
-                    }
-                    i += n;
+                const bool act = i < e;
+                int n = 0, bk = -1;
+                double2 sxy = make_double2(0.0, 0.0);
+                if (act) { n = srn[i]; bk = sbk[i]; sxy = sb[i]; }
+                const bool matched = act && bk >= 0;
+                double2 lm = make_double2(0.0, 0.0);
+                int lab = -1;
+                if (matched) { lm = __ldg(p.gpts + bk); lab = __ldg(G.idx + bk); }
+                const double dn = (double)n;
+                const double rwx = fma(ct, sxy.x, -st * sxy.y), rwy = fma(st, sxy.x, ct * sxy.y);   // sum of rotated beams
+                const double yx = lm.x - px, yy = lm.y - py;
+                if (act && bk < 0) {          // far run: statistics of the scan's new label
+                    nfar += n;
+                    fsx += fma(dn, px, rwx); fsy += fma(dn, py, rwy);
+                    FBx += sxy.x; FBy += sxy.y;
                 }
+                if (matched) {
+                    M.Yx = fma(dn, yx, M.Yx); M.Yy = fma(dn, yy, M.Yy);
+                    M.Mxx = fma(yx, sxy.x, M.Mxx); M.Mxy = fma(yx, sxy.y, M.Mxy);
+                    M.Myx = fma(yy, sxy.x, M.Myx); M.Myy = fma(yy, sxy.y, M.Myy);
+                }
+                if (matched && qowned && !(p.skip & 8)) stat_add(S, p, lab, rwx - dn * yx, rwy - dn * yy, n);   // sum of (obs - landmark)
+                i += n;
             }
         }
         c_lo = c_hi + 1;
         if (c_lo <= lt_last) __syncthreads();   // the next chunk overwrites the staging buffers
     }
-    // ---- combine the pair's partial sums; the pair leader publishes the slot's moments ---------------------
+    // ---- combine the pair's partial sums (both lanes end up with the scan's totals) ----------------------------
     {
 #define FS_PAIR(v) v += __shfl_xor_sync(FULLMASK, v, 1)
         FS_PAIR(M.n); FS_PAIR(M.Bx); FS_PAIR(M.By); FS_PAIR(M.Bxx); FS_PAIR(M.Byy); FS_PAIR(M.Bxy);
@@ -453,18 +559,13 @@ k_sweep_fused(const FusedParams p)
         FS_PAIR(fsx); FS_PAIR(fsy); FS_PAIR(FBx); FS_PAIR(FBy);
         nfar += __shfl_xor_sync(FULLMASK, nfar, 1);
 #undef FS_PAIR
-        if (half == 0) {
-            if (qowned && nfar > 0) atomicOr(&S.farbits[(qt - tb) >> 5], 1u << ((qt - tb) & 31));
-            if (nfar > 0) {   // far observations see the mean of the scan's new label (PREV view, raw = sum / k)
-                const double px = S.pp[qli].x, py = S.pp[qli].y;
-                const double yx = fsx / (double)nfar - px, yy = fsy / (double)nfar - py;
-                M.Yx += (double)nfar * yx; M.Yy += (double)nfar * yy;
-                M.Mxx = fma(yx, FBx, M.Mxx); M.Mxy = fma(yx, FBy, M.Mxy);
-                M.Myx = fma(yy, FBx, M.Myx); M.Myy = fma(yy, FBy, M.Myy);
-            }
-            S.mom[0][q] = M.n; S.mom[1][q] = M.Bx; S.mom[2][q] = M.By; S.mom[3][q] = M.Bxx; S.mom[4][q] = M.Byy; S.mom[5][q] = M.Bxy;
-            S.mom[6][q] = M.Yx; S.mom[7][q] = M.Yy; S.mom[8][q] = M.Mxx; S.mom[9][q] = M.Mxy; S.mom[10][q] = M.Myx; S.mom[11][q] = M.Myy;
-            S.onum[q] = qvalid ? S.off[qli + 1] - S.off[qli] : 0;
+        if (half == 0 && qowned && nfar > 0) atomicOr(&S.farbits[(qt - tb) >> 5], 1u << ((qt - tb) & 31));
+        if (nfar > 0) {   // far observations see the mean of the scan's new label (PREV view, raw = sum / k)
+            const double px = S.pp[qli].x, py = S.pp[qli].y;
+            const double yx = fsx / (double)nfar - px, yy = fsy / (double)nfar - py;
+            M.Yx += (double)nfar * yx; M.Yy += (double)nfar * yy;
+            M.Mxx = fma(yx, FBx, M.Mxx); M.Mxy = fma(yx, FBy, M.Mxy);
+            M.Myx = fma(yy, FBx, M.Myx); M.Myy = fma(yy, FBy, M.Myy);
         }
     }
     __syncthreads();
@@ -479,50 +580,59 @@ k_sweep_fused(const FusedParams p)
         p.far_list[atomicAdd(&p.ts->far_count, 1)] = r;
     }
     if (tid == 0) p.blk_far[blockIdx.x] = __popc(S.farbits[0]) + __popc(S.farbits[1]) + __popc(S.farbits[2]) + __popc(S.farbits[3]);
-    // ---- pose solve: thread q <-> slot q; warps 0-1 red (odd poses), then warps 2-3 black (even poses) --------
+    // ---- pose solve by the lane pairs: warps 0-3 red (odd poses), then warps 4-7 black (even poses) --------------
     {
-        const int sq = tid;                                         // slot solved by this thread (tid < FS_SLOTS)
-        const int grp = sq >> 6;
-        const int t = sq < FS_HALF ? tb - 1 + 2 * sq : tb + 2 * (sq - FS_HALF);
-        const int li = t - (tb - 2);
-        const bool valid = tid < FS_SLOTS && sq != FS_SLOTS - 1 && t >= 0 && t < T;
+        const int grp = q / FS_HALF;
+        const int t = qt, li = qli;
         unsigned long long my_iters = 0;
         for (int phase = 0; phase < 2; ++phase) {
-            if (valid && phase == grp) {
-                double res[3], s_new = 0.0, c_new = 1.0;
-                if (t == 0) {
-                    res[0] = S.xs[0][li]; res[1] = S.xs[1][li]; res[2] = S.xs[2][li];
-                } else {
+            if (phase == grp && !(p.skip & 64)) {       // warp-uniform: a warp holds 16 slots of one colour
+                double res = 0.0, th = 0.0, s_new = 0.0, c_new = 1.0;
+                bool write = qvalid;
+                if (qvalid) {
                     // neighbours: old poses for the odd phase, new (odd) poses for the even phase
                     double (*X)[FS_XT] = phase == 0 ? S.xs : S.xn;
                     const bool has_next = t + 1 < T;
-                    if (S.onum[sq] == 0) {     // sensors.py:147-151
-                        for (int r = 0; r < 3; ++r) {
-                            const double prev = (t == 1) ? p.x0[r] : X[r][li - 1];
-                            res[r] = (prev + X[r][li + 1]) / 2.0;
-                        }
-                        sincos(res[2], &s_new, &c_new);
-                    } else {
-                        Mom Q;
-                        Q.n = S.mom[0][sq]; Q.Bx = S.mom[1][sq]; Q.By = S.mom[2][sq]; Q.Bxx = S.mom[3][sq]; Q.Byy = S.mom[4][sq]; Q.Bxy = S.mom[5][sq];
-                        Q.Yx = S.mom[6][sq]; Q.Yy = S.mom[7][sq]; Q.Mxx = S.mom[8][sq]; Q.Mxy = S.mom[9][sq]; Q.Myx = S.mom[10][sq]; Q.Myy = S.mom[11][sq];
-                        PoseIn P;
-                        P.ax = X[0][li - 1]; P.ay = X[1][li - 1]; P.ath = X[2][li - 1];
-                        P.sa = S.sn[li - 1]; P.ca = S.cs[li - 1];
-                        P.bx = has_next ? X[0][li + 1] : 0.0; P.by = has_next ? X[1][li + 1] : 0.0; P.bth = has_next ? X[2][li + 1] : 0.0;
-                        P.uav = S.u[0][li - 1]; P.uaw = S.u[1][li - 1];
-                        P.ucv = S.u[0][li]; P.ucw = S.u[1][li];
-                        P.D0x = S.inc[0][li - 1]; P.D0y = S.inc[1][li - 1]; P.dth0 = S.inc[2][li - 1];
-                        P.D1x = S.inc[0][li]; P.D1y = S.inc[1][li]; P.dth1 = S.inc[2][li];
-                        P.has_next = has_next ? 1 : 0;
-                        // start at the pose's own input heading: its sin/cos are already known
-                        const double st = S.rsc[li].x, ct = S.rsc[li].y;
-                        const int it = newton_lean(p.cfg, P, Q, S.xs[0][li], S.xs[1][li], S.xs[2][li], ct, -st, p.tol, p.maxit, res, s_new, c_new);
-                        my_iters += (unsigned long long)it;
+                    const bool solve = t != 0 && M.n > 0.0;
+                    PoseIn P;
+                    P.ax = X[0][li - 1]; P.ay = X[1][li - 1]; P.ath = X[2][li - 1];
+                    P.sa = S.sn[li - 1]; P.ca = S.cs[li - 1];
+                    P.bx = has_next ? X[0][li + 1] : 0.0; P.by = has_next ? X[1][li + 1] : 0.0; P.bth = has_next ? X[2][li + 1] : 0.0;
+                    P.uav = S.u[0][li - 1]; P.uaw = S.u[1][li - 1];
+                    P.ucv = S.u[0][li]; P.ucw = S.u[1][li];
+                    P.D0x = S.inc[0][li - 1]; P.D0y = S.inc[1][li - 1]; P.dth0 = S.inc[2][li - 1];
+                    P.D1x = S.inc[0][li]; P.D1y = S.inc[1][li]; P.dth1 = S.inc[2][li];
+                    P.has_next = has_next ? 1 : 0;
+                    th = S.xs[2][li];
+                    if (t == 0) {
+                        res = S.xs[half][li];
+                        sincos(th, &s_new, &c_new);
+                    } else if (!solve) {       // sensors.py:147-151: no observation, average of the neighbours
+                        const double pv = (t == 1) ? p.x0[half] : X[half][li - 1];
+                        res = (pv + X[half][li + 1]) / 2.0;
+                        th = (((t == 1) ? p.x0[2] : X[2][li - 1]) + X[2][li + 1]) / 2.0;
+                        sincos(th, &s_new, &c_new);
+                    }
+                    // (lanes that do not solve still run the loop below with harmless values: the pair shuffles inside
+                    //  newton_pair need every lane of the warp)
+                    const double st = S.rsc[li].x, ct = S.rsc[li].y;
+                    double r2 = 0.0, th2 = S.xs[2][li], s2 = 0.0, c2 = 1.0;
+                    const int it = newton_pair(p.cfg, P, M, half, S.xs[0][li], S.xs[1][li], th2, ct, -st, p.tol, (solve && !(p.skip & 16)) ? p.maxit : 1, r2, s2, c2);
+                    if (solve) { res = r2; th = th2; s_new = s2; c_new = c2; my_iters += (unsigned long long)(half == 0 ? it : 0); }
+                } else {
+                    PoseIn P;
+                    P.ax = P.ay = P.ath = P.sa = 0.0; P.ca = 1.0; P.bx = P.by = P.bth = 0.0; P.uav = P.uaw = P.ucv = P.ucw = 0.0;
+                    P.D0x = P.D0y = P.dth0 = P.D1x = P.D1y = P.dth1 = 0.0; P.has_next = 0;
+                    double r2, th2 = 0.0, s2, c2;
+                    newton_pair(p.cfg, P, M, half, 0.0, 0.0, th2, 0.0, 1.0, p.tol, 1, r2, s2, c2);
+                }
+                if (write) {
+                    S.xn[half][li] = res;
+                    if (half == 0) {
+                        S.xn[2][li] = th;
+                        if (phase == 0) { S.sn[li] = s_new; S.cs[li] = c_new; }   // (old odd headings are no longer needed)
                     }
                 }
-                S.xn[0][li] = res[0]; S.xn[1][li] = res[1]; S.xn[2][li] = res[2];
-                if (phase == 0) { S.sn[li] = s_new; S.cs[li] = c_new; }   // (old odd headings are no longer needed)
             }
             __syncthreads();
         }
@@ -538,8 +648,8 @@ k_sweep_fused(const FusedParams p)
     for (int h = tid; h < FS_HASH; h += FS_THREADS) {
         const int key = S.hkey[h];
         if (key >= 0 && S.hcnt[h] > 0) {
-            atomicAdd((unsigned long long*)(p.fsum_x + key), ((unsigned long long)S.hsx[h][1] << 32) | S.hsx[h][0]);
-            atomicAdd((unsigned long long*)(p.fsum_y + key), ((unsigned long long)S.hsy[h][1] << 32) | S.hsy[h][0]);
+            atomicAdd((unsigned long long*)(p.fsum_x + key), ((unsigned long long)S.hs[h][1] << 32) | S.hs[h][0]);
+            atomicAdd((unsigned long long*)(p.fsum_y + key), ((unsigned long long)S.hs[h][3] << 32) | S.hs[h][2]);
             atomicAdd(p.cnt + key, S.hcnt[h]);
         }
     }
@@ -552,7 +662,16 @@ __global__ void k_interleave(const double* __restrict__ bx, const double* __rest
     if (i < n) out[i] = make_double2(bx[i], by[i]);
 }
 
-static size_t fused_smem_bytes(int obs_cap) { return sizeof(FusedSmemFixed) + (size_t)obs_cap * 23 + 32; }   // obs_cap is even
+static size_t fused_smem_bytes(int half, int obs_cap)   // obs_cap is even
+{
+    return (half == 32 ? sizeof(FusedSmemFixed<32>) : sizeof(FusedSmemFixed<64>)) + (size_t)obs_cap * 23 + 32;
+}
+#undef FS_THREADS
+#undef FS_WARPS
+#undef FS_SLOTS
+#undef FS_OWN
+#undef FS_XT
+#undef FS_HALF
 
 // raw map of the previous-map landmarks from the fixed-point statistics + keep flags for all labels;
 // clears the statistics for the next sweep.

@@ -79,6 +79,7 @@ struct icmslam_handle {
     FGeom* d_fg_geom = nullptr;
     unsigned long long* d_bb = nullptr;
     int obs_cap = 0, max_tile_obs = 0;
+    int tile_half = 64, tile_own = 126;   // fused-kernel tile: pose slots per colour / poses owned per block
     size_t fused_smem = 0;
     double thr2_hi = 0.0, fix_scale = 1.0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -317,7 +318,8 @@ extern "C" int icmslam_load(icmslam_handle* h, const double* scans, int32_t B, i
     CK(dalloc(&h->d_prefix, (size_t)T + 1));
     CK(dalloc(&h->d_inc, (size_t)3 * T));
     CK(dalloc(&h->d_x2, (size_t)3 * T));
-    h->n_tiles = nblk(T, FS_OWN);
+    { const char* et = getenv("ICMSLAM_TILE"); h->tile_half = (et && atoi(et) == 32) ? 32 : 64; h->tile_own = 2 * h->tile_half - 2; }
+    h->n_tiles = nblk(T, h->tile_own);
     CK(dalloc(&h->d_far_list, (size_t)T));
     CK(dalloc(&h->d_blk_far, (size_t)h->n_tiles));
     CK(dalloc(&h->d_blk_prefix, (size_t)h->n_tiles));
@@ -402,27 +404,29 @@ extern "C" int icmslam_extract(icmslam_handle* h)
     h->extracted = true;
     {   // shared-memory budget of the fused kernel: observations of one tile (FS_OWN poses + the halo scan)
         int mx = 0;
-        for (int tb = 0; tb < T; tb += FS_OWN) {
-            int t0 = tb > 0 ? tb - 1 : 0, t1 = tb + FS_OWN < T ? tb + FS_OWN : T;
+        for (int tb = 0; tb < T; tb += h->tile_own) {
+            int t0 = tb > 0 ? tb - 1 : 0, t1 = tb + h->tile_own < T ? tb + h->tile_own : T;
             int m = off[t1] - off[t0];
             if (m > mx) mx = m;
         }
         h->max_tile_obs = mx;
-        int blocks_per_sm = 2;
+        int blocks_per_sm = h->tile_half == 32 ? 4 : 2;
+        const size_t fixed = h->tile_half == 32 ? sizeof(FusedSmemFixed<32>) : sizeof(FusedSmemFixed<64>);
         const char* envb = getenv("ICMSLAM_BLOCKS_PER_SM");
         if (envb && atoi(envb) > 0) blocks_per_sm = atoi(envb);
         const size_t per_block = (size_t)233472 / blocks_per_sm - 1024 - 512;   // 228 KB per SM, 1 KB reserved per block
-        int cap = (int)((per_block - sizeof(FusedSmemFixed) - 32) / 23);
+        int cap = (int)((per_block - fixed - 32) / 23);
         const char* env = getenv("ICMSLAM_OBS_CAP");
         if (env && atoi(env) > 0) cap = atoi(env);
-        const int cap_max = (int)((232448 - sizeof(FusedSmemFixed) - 32) / 23);
+        const int cap_max = (int)((232448 - fixed - 32) / 23);
         if (cap > cap_max) cap = cap_max;
         if (cap > mx) cap = mx;                                    // the whole tile fits: one chunk
         if (cap < h->max_per_scan) cap = h->max_per_scan;          // a chunk holds at least one whole scan
         if (cap < 2) cap = 2;
         h->obs_cap = (cap + 1) & ~1;
-        h->fused_smem = fused_smem_bytes(h->obs_cap);
-        CK(cudaFuncSetAttribute(k_sweep_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
+        h->fused_smem = fused_smem_bytes(h->tile_half, h->obs_cap);
+        if (h->tile_half == 32) CK(cudaFuncSetAttribute(k_sweep_fused<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
+        else CK(cudaFuncSetAttribute(k_sweep_fused<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
         h->fused_ok = true;
     }
     return ICMSLAM_OK;
@@ -589,7 +593,7 @@ static void default_opts(icmslam_sweep_opts& o, const icmslam_sweep_opts* opts)
     o.newton_maxit = 0; o.newton_tol = 0.0; o.fused = 1; o.reserved = 0;
     if (opts) o = *opts;
     if (o.newton_maxit <= 0) o.newton_maxit = 20;
-    if (!(o.newton_tol > 0.0)) o.newton_tol = 1e-10;
+    if (!(o.newton_tol > 0.0)) o.newton_tol = 1e-7;    // Newton is quadratic: the step after |dtheta| <= 1e-7 is ~1e-14
 }
 
 // fast grid (fastgrid.cuh) over the first *n_ptr points of (px, py).  cell_cnt is all zero on entry and
@@ -661,8 +665,10 @@ static int sweep_core(icmslam_handle* h, const double* xin, int64_t ldin, double
         P.c = h->d_c; P.fsum_x = h->d_fsum_x; P.fsum_y = h->d_fsum_y; P.cnt = h->d_cnt;
         P.far_list = h->d_far_list; P.ts = h->d_ts; P.blk_far = h->d_blk_far;
         P.obs_cap = h->obs_cap; P.iters = iters;
+        { const char* es = getenv("ICMSLAM_SKIP"); P.skip = es ? atoi(es) : 0; }
         if (timing) CK(cudaEventRecord(h->ev[0], s));
-        k_sweep_fused<<<h->n_tiles, FS_THREADS, h->fused_smem, s>>>(P);
+        if (h->tile_half == 32) k_sweep_fused<32><<<h->n_tiles, 128, h->fused_smem, s>>>(P);
+        else k_sweep_fused<64><<<h->n_tiles, 256, h->fused_smem, s>>>(P);
         CK(cudaGetLastError());
         if (timing) CK(cudaEventRecord(h->ev[1], s));
         if (kout != xout) CK(cudaMemcpy2DAsync(xout, (size_t)ldout * 8, kout, (size_t)kld * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToDevice, s));
@@ -670,7 +676,7 @@ static int sweep_core(icmslam_handle* h, const double* xin, int64_t ldin, double
         TailState* ts = h->d_ts;
         k_tail_scan<<<1, 1024, 0, s>>>(h->d_blk_far, h->n_tiles, h->d_blk_prefix, st, ts, L, h->d_bb);
         CK(cudaGetLastError());
-        k_tail_labels<<<148, 256, 0, s>>>(ts, h->d_far_list, h->d_blk_prefix, FS_OWN, h->d_off, st, L, h->d_c, raw_x, raw_y, h->d_cnt);
+        k_tail_labels<<<148, 256, 0, s>>>(ts, h->d_far_list, h->d_blk_prefix, h->tile_own, h->d_off, st, L, h->d_c, raw_x, raw_y, h->d_cnt);
         CK(cudaGetLastError());
         k_fused_means<<<nblk(L, 256), 256, 0, s>>>(st, h->d_fsum_x, h->d_fsum_y, h->d_cnt, min_x, min_y, 1.0 / h->fix_scale, h->dcfg.cota,
                                                    raw_x, raw_y, h->d_kflag, L);

@@ -77,7 +77,7 @@ typedef struct icmslam_sweep_opts {
     int32_t solver;         /* ICMSLAM_SOLVER_* */
     int32_t map_view;       /* ICMSLAM_VIEW_* */
     int32_t newton_maxit;   /* <=0: default 20 */
-    double newton_tol;      /* Newton stops when |dtheta| <= tol; <=0: default 1e-10 */
+    double newton_tol;      /* Newton stops when |dtheta| <= tol; <=0: default 1e-7 (the remaining error is quadratic in it) */
     int32_t fused;          /* 1: allow the single-kernel path when (REDBLACK, NEWTON, PREV) */
     int32_t reserved;
 } icmslam_sweep_opts;
