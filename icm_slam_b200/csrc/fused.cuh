@@ -46,7 +46,9 @@
 #define FS_PROBES 8
 
 struct FusedParams {
-    int T;
+    int T;                                // columns of this handle's trajectory (a time segment incl. its halo columns)
+    int t_lo, t_hi;                       // owned poses [t_lo, t_hi): whole trajectory = [0, T); a segment owns [2, T-1) etc.
+    int first;                            // column 0 is the trajectory's first pose (pinned to self.x0, sensors.py:131)
     const int* off;                       // CSR offsets of the kept observations (T + 1)
     const double2* bxy;                   // body-frame observations (bx, by), CSR order
     const double* xin; int64_t ldin;      // 3 x T input poses
@@ -225,6 +227,7 @@ __device__ __forceinline__ int newton_pair(const DevCfg& cfg, const PoseIn& P, c
     // (a, b): role 0 = (cos th, sin th); role 1 = (sin th, -cos th)
     double a = role ? s : c, b = role ? -c : s;
     int it = 0;
+    bool done = false;
     for (;;) {
         const double A = KA - a * P1 - b * P2, A1 = b * P1 - a * P2, A2 = KA - A;
         const double ra = a * D1x - b * D1y, rb = b * D1x + a * D1y;
@@ -244,18 +247,20 @@ __device__ __forceinline__ int newton_pair(const DevCfg& cfg, const PoseIn& P, c
         double p2 = g2 + __shfl_xor_sync(FULLMASK, g2, 1) + ang2;
         if (!(p2 > 0.0)) p2 = ang2;
         const double dth = -p1 * (double)__frcp_rn((float)p2);   // quasi-Newton: 24-bit reciprocal of the curvature, same fixed point
-        th += dth;
-        ++it;
-        if (fabs(dth) <= 0.125) {
-            double sd, cd;
-            sincos_small(dth, sd, cd);
-            const double b2 = b * cd + a * sd;
-            a = a * cd - b * sd;
-            b = b2;
-        } else {
-            sincos(role ? th - ICM_HALFPI : th, &b, &a);
+        if (!done) {       // a converged pair is frozen: its result does not depend on how long its warp-mates iterate
+            th += dth;
+            ++it;
+            if (fabs(dth) <= 0.125) {
+                double sd, cd;
+                sincos_small(dth, sd, cd);
+                const double b2 = b * cd + a * sd;
+                a = a * cd - b * sd;
+                b = b2;
+            } else {
+                sincos(role ? th - ICM_HALFPI : th, &b, &a);
+            }
+            done = fabs(dth) <= tol || it >= maxit;
         }
-        const bool done = fabs(dth) <= tol || it >= maxit;
         if (__all_sync(FULLMASK, done)) break;
     }
     coord = (KA - a * P1 - b * P2) * iS + o_;
@@ -336,7 +341,7 @@ k_sweep_fused(const FusedParams p)
     unsigned char* slt = reinterpret_cast<unsigned char*>(srn + p.obs_cap);         // scan (local pose index) of each observation
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tb = blockIdx.x * FS_OWN;
+    const int tb = p.t_lo + blockIdx.x * FS_OWN;      // t_lo is even: colours stay aligned with the global time index
     const int T = p.T;
     // ---- tile loads ---------------------------------------------------------------------------
     for (int li = tid; li < FS_XT; li += FS_THREADS) {
@@ -364,7 +369,7 @@ k_sweep_fused(const FusedParams p)
         if (t >= 0 && t < T) {
             double px = S.xs[0][tid], py = S.xs[1][tid], th = S.xs[2][tid];
             double st, ct, sh, ch;
-            if (t == 0) {                                        // scan 0 is projected with self.x0; x[:,0] is only a neighbour
+            if (t == 0 && p.first) {                             // scan 0 is projected with self.x0; x[:,0] is only a neighbour
                 sincos(th, &sh, &ch);
                 px = p.x0[0]; py = p.x0[1]; th = p.x0[2];
                 sincos(sub_rn(th, ICM_HALFPI), &st, &ct);
@@ -380,7 +385,7 @@ k_sweep_fused(const FusedParams p)
     const int q = tid >> 1, half = tid & 1;
     const int qt = q < FS_HALF ? tb - 1 + 2 * q : tb + 2 * (q - FS_HALF);
     const int qli = qt - (tb - 2);
-    const bool qvalid = q != FS_SLOTS - 1 && qt >= 0 && qt < T;
+    const bool qvalid = q != FS_SLOTS - 1 && qt >= 0 && qt < p.t_hi && (qt >= p.t_lo || q == 0);
     const bool qowned = qvalid && q != 0;                       // the halo pose tb-1 is recomputed, not owned
     Mom M;
     M.n = M.Bx = M.By = M.Bxx = M.Byy = M.Bxy = M.Yx = M.Yy = M.Mxx = M.Mxy = M.Myx = M.Myy = 0.0;
@@ -391,7 +396,7 @@ k_sweep_fused(const FusedParams p)
     G.g = *p.geom;
     G.cell_start = p.cell_start; G.pts = p.gpts; G.idx = p.gidx;
     const bool have_map = p.st->lsearch > 0;
-    const int t_first = max(tb - 1, 0), t_last = min(tb + FS_OWN - 1, T - 1);     // scans processed by this block
+    const int t_first = max(tb - 1, 0), t_last = min(tb + FS_OWN - 1, p.t_hi - 1);     // scans processed by this block
     const int lt_first = t_first - (tb - 2), lt_last = t_last - (tb - 2);
     __syncthreads();
     // ---- chunks of whole scans whose observations fit the shared-memory budget (normally one) -----------
@@ -593,7 +598,7 @@ k_sweep_fused(const FusedParams p)
                     // neighbours: old poses for the odd phase, new (odd) poses for the even phase
                     double (*X)[FS_XT] = phase == 0 ? S.xs : S.xn;
                     const bool has_next = t + 1 < T;
-                    const bool solve = t != 0 && M.n > 0.0;
+                    const bool solve = !(t == 0 && p.first) && M.n > 0.0;
                     PoseIn P;
                     P.ax = X[0][li - 1]; P.ay = X[1][li - 1]; P.ath = X[2][li - 1];
                     P.sa = S.sn[li - 1]; P.ca = S.cs[li - 1];
@@ -604,13 +609,14 @@ k_sweep_fused(const FusedParams p)
                     P.D1x = S.inc[0][li]; P.D1y = S.inc[1][li]; P.dth1 = S.inc[2][li];
                     P.has_next = has_next ? 1 : 0;
                     th = S.xs[2][li];
-                    if (t == 0) {
+                    if (t == 0 && p.first) {
                         res = S.xs[half][li];
                         sincos(th, &s_new, &c_new);
                     } else if (!solve) {       // sensors.py:147-151: no observation, average of the neighbours
-                        const double pv = (t == 1) ? p.x0[half] : X[half][li - 1];
+                        const bool t1 = t == 1 && p.first;
+                        const double pv = t1 ? p.x0[half] : X[half][li - 1];
                         res = (pv + X[half][li + 1]) / 2.0;
-                        th = (((t == 1) ? p.x0[2] : X[2][li - 1]) + X[2][li + 1]) / 2.0;
+                        th = ((t1 ? p.x0[2] : X[2][li - 1]) + X[2][li + 1]) / 2.0;
                         sincos(th, &s_new, &c_new);
                     }
                     // (lanes that do not solve still run the loop below with harmless values: the pair shuffles inside
@@ -642,7 +648,7 @@ k_sweep_fused(const FusedParams p)
         }
     }
     // ---- outputs ----------------------------------------------------------------------------------
-    const int n_own = min(FS_OWN, T - tb);
+    const int n_own = min(FS_OWN, p.t_hi - tb);
     for (int r = 0; r < 3; ++r)
         for (int k = tid; k < n_own; k += FS_THREADS) p.xout[r * p.ldout + tb + k] = S.xn[r][k + 2];
     for (int h = tid; h < FS_HASH; h += FS_THREADS) {
@@ -678,6 +684,7 @@ static size_t fused_smem_bytes(int half, int obs_cap)   // obs_cap is even
 __global__ void __launch_bounds__(256)
 k_fused_means(const DevState* st, long long* __restrict__ fsum_x, long long* __restrict__ fsum_y, const int* __restrict__ cnt,
               const double* __restrict__ map_x, const double* __restrict__ map_y, double inv_scale, double cota,
+              double* __restrict__ newraw /* 2 x Lcap: means of this sweep's new labels, zero elsewhere; cleared here */,
               double* __restrict__ raw_x, double* __restrict__ raw_y, int* __restrict__ flag, int Lcap)
 {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
@@ -687,9 +694,12 @@ k_fused_means(const DevState* st, long long* __restrict__ fsum_x, long long* __r
     if (l < ls) {
         raw_x[l] = k > 0 ? map_x[l] + ((double)fsum_x[l] * inv_scale) / (double)k : 0.0;
         raw_y[l] = k > 0 ? map_y[l] + ((double)fsum_y[l] * inv_scale) / (double)k : 0.0;
-    } else if (!(l < raw_l && k > 0)) {
-        raw_x[l] = 0.0; raw_y[l] = 0.0;
+    } else {
+        const bool have = l < raw_l && k > 0;
+        raw_x[l] = have ? newraw[l] : 0.0;
+        raw_y[l] = have ? newraw[Lcap + l] : 0.0;
     }
+    newraw[l] = 0.0; newraw[Lcap + l] = 0.0;
     fsum_x[l] = 0; fsum_y[l] = 0;
     flag[l] = (l < raw_l && !((double)k < cota)) ? 1 : 0;      // ICM_SLAM.py:232-236
 }

@@ -80,6 +80,11 @@ struct icmslam_handle {
     unsigned long long* d_bb = nullptr;
     int obs_cap = 0, max_tile_obs = 0;
     int tile_half = 64, tile_own = 126;   // fused-kernel tile: pose slots per colour / poses owned per block
+    // time-segment partition (icmslam_set_segment): this handle owns columns [seg_lo, seg_hi) of its T columns
+    int seg_lo = 0, seg_hi = 0, seg_first = 1, seg_last = 1;
+    double* d_newraw = nullptr;   // 2 x Lcap: means of the sweep's new labels (zero elsewhere)
+    double* d_seg_rec = nullptr;  // SEG_REC doubles: what this segment tells its neighbours
+    double* seg_dst = nullptr;    // output pose buffer of the segment sweep in flight
     size_t fused_smem = 0;
     double thr2_hi = 0.0, fix_scale = 1.0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -158,7 +163,7 @@ extern "C" int icmslam_destroy(icmslam_handle* h)
     DFREE(h->d_cell_start); DFREE(h->d_cell_fill); DFREE(h->d_cell_id); DFREE(h->d_gidx); DFREE(h->d_glx); DFREE(h->d_gly);
     DFREE(h->d_st); DFREE(h->d_cub);
     DFREE(h->d_fsum_x); DFREE(h->d_fsum_y); DFREE(h->d_fg_cnt); DFREE(h->d_fg_start); DFREE(h->d_fg_idx);
-    DFREE(h->d_fg_pts); DFREE(h->d_fg_geom); DFREE(h->d_bb); DFREE(h->d_ts);
+    DFREE(h->d_fg_pts); DFREE(h->d_fg_geom); DFREE(h->d_bb); DFREE(h->d_ts); DFREE(h->d_newraw); DFREE(h->d_seg_rec);
     if (h->h_st) cudaFreeHost(h->h_st);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -246,6 +251,9 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     if (e == cudaSuccess) e = dalloc(&h->d_fg_geom, 1);
     if (e == cudaSuccess) e = dalloc(&h->d_bb, 4);
     if (e == cudaSuccess) e = dalloc(&h->d_ts, 1);
+    if (e == cudaSuccess) e = dalloc(&h->d_newraw, 2 * L);
+    if (e == cudaSuccess) e = cudaMemset(h->d_newraw, 0, 2 * L * sizeof(double));
+    if (e == cudaSuccess) e = dalloc(&h->d_seg_rec, SEG_REC);
     if (e == cudaSuccess) e = cudaMemset(h->d_ts, 0, sizeof(TailState));
     { const char* eg = getenv("ICMSLAM_GRAPH"); if (eg) h->use_graph = atoi(eg); }
     if (e == cudaSuccess) e = cudaMemset(h->d_fsum_x, 0, L * sizeof(long long));
@@ -319,6 +327,7 @@ extern "C" int icmslam_load(icmslam_handle* h, const double* scans, int32_t B, i
     CK(dalloc(&h->d_inc, (size_t)3 * T));
     CK(dalloc(&h->d_x2, (size_t)3 * T));
     { const char* et = getenv("ICMSLAM_TILE"); h->tile_half = (et && atoi(et) == 32) ? 32 : 64; h->tile_own = 2 * h->tile_half - 2; }
+    h->seg_lo = 0; h->seg_hi = T; h->seg_first = 1; h->seg_last = 1;
     h->n_tiles = nblk(T, h->tile_own);
     CK(dalloc(&h->d_far_list, (size_t)T));
     CK(dalloc(&h->d_blk_far, (size_t)h->n_tiles));
@@ -404,7 +413,7 @@ extern "C" int icmslam_extract(icmslam_handle* h)
     h->extracted = true;
     {   // shared-memory budget of the fused kernel: observations of one tile (FS_OWN poses + the halo scan)
         int mx = 0;
-        for (int tb = 0; tb < T; tb += h->tile_own) {
+        for (int tb = 0; tb < T; tb += 2) {   // (any even tile origin: a later icmslam_set_segment may shift the tiling)
             int t0 = tb > 0 ? tb - 1 : 0, t1 = tb + h->tile_own < T ? tb + h->tile_own : T;
             int m = off[t1] - off[t0];
             if (m > mx) mx = m;
@@ -425,8 +434,9 @@ extern "C" int icmslam_extract(icmslam_handle* h)
         if (cap < 2) cap = 2;
         h->obs_cap = (cap + 1) & ~1;
         h->fused_smem = fused_smem_bytes(h->tile_half, h->obs_cap);
-        if (h->tile_half == 32) CK(cudaFuncSetAttribute(k_sweep_fused<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
-        else CK(cudaFuncSetAttribute(k_sweep_fused<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fused_smem));
+        // (a per-function, per-device attribute shared by every handle of the process: opt in to the maximum)
+        CK(cudaFuncSetAttribute(k_sweep_fused<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        CK(cudaFuncSetAttribute(k_sweep_fused<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         h->fused_ok = true;
     }
     return ICMSLAM_OK;
@@ -619,6 +629,100 @@ static int build_fgrid(icmslam_handle* h, const double* px, const double* py, co
     return ICMSLAM_OK;
 }
 
+// ---- the fused (REDBLACK, NEWTON, PREV) sweep in three parts; a time-segmented run (one segment per GPU)
+// exchanges data with the other segments between them ----------------------------------------------------
+// part A: (grid of the previous map if it is not there yet) + the fused kernel + the scan of far-scan counts
+static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, double* kout, int64_t kld, const double* x0,
+                        const icmslam_sweep_opts& o, int n_search_cap)
+{
+    const int T = h->T, L = h->Lcap;
+    cudaStream_t s = h->stream;
+    DevState* st = h->d_st;
+    const double* min_x = h->d_map_in;
+    const double* min_y = h->d_map_in + L;
+    const bool timing = (o.reserved & 2) != 0;
+    if (h->grid_map != h->d_map_in) {      // the grid of the previous sweep's tail does not index this map: build it
+        int rc = build_fgrid(h, min_x, min_y, &st->lsearch, n_search_cap);
+        if (rc) return rc;
+    }
+    FusedParams P;
+    P.T = T; P.t_lo = h->seg_lo; P.t_hi = h->seg_hi; P.first = h->seg_first;
+    P.off = h->d_off; P.bxy = h->d_bxy;
+    P.xin = xin; P.ldin = ldin; P.xout = kout; P.ldout = kld;
+    P.x0[0] = x0[0]; P.x0[1] = x0[1]; P.x0[2] = x0[2];
+    P.inc = h->d_inc; P.ldinc = T; P.u = h->d_u; P.ldu = T;
+    P.cfg = h->dcfg; P.thr2_hi = h->thr2_hi; P.fix_scale = h->fix_scale; P.tol = o.newton_tol; P.maxit = o.newton_maxit;
+    P.st = st; P.geom = h->d_fg_geom; P.cell_start = h->d_fg_start; P.gpts = h->d_fg_pts; P.gidx = h->d_fg_idx;
+    P.c = h->d_c; P.fsum_x = h->d_fsum_x; P.fsum_y = h->d_fsum_y; P.cnt = h->d_cnt;
+    P.far_list = h->d_far_list; P.ts = h->d_ts; P.blk_far = h->d_blk_far;
+    P.obs_cap = h->obs_cap; P.iters = (o.reserved & 1) ? &st->newton_iters : nullptr;
+    { const char* es = getenv("ICMSLAM_SKIP"); P.skip = es ? atoi(es) : 0; }
+    if (timing) CK(cudaEventRecord(h->ev[0], s));
+    if (h->tile_half == 32) k_sweep_fused<32><<<h->n_tiles, 128, h->fused_smem, s>>>(P);
+    else k_sweep_fused<64><<<h->n_tiles, 256, h->fused_smem, s>>>(P);
+    CK(cudaGetLastError());
+    if (timing) CK(cudaEventRecord(h->ev[1], s));
+    k_tail_scan<<<1, 1024, 0, s>>>(h->d_blk_far, h->n_tiles, h->d_blk_prefix, st, h->d_ts, L, h->d_bb);
+    CK(cudaGetLastError());
+    h->n_launch += 2;
+    return ICMSLAM_OK;
+}
+
+// part B: the sweep's new labels (needs the label numbering: on several GPUs, after the exchange)
+static int fused_part_b(icmslam_handle* h)
+{
+    const int L = h->Lcap;
+    k_tail_labels<<<148, 256, 0, h->stream>>>(h->d_ts, h->d_far_list, h->d_blk_prefix, h->tile_own, h->seg_lo, h->d_off, h->d_st, L, h->d_c,
+                                              h->d_newraw, h->d_newraw + L, h->d_cnt);
+    CK(cudaGetLastError());
+    h->n_launch += 1;
+    return ICMSLAM_OK;
+}
+
+// part C: landmark update, Mapa.filtrar and the grid of the new map (needs the statistics of ALL segments)
+static int fused_part_c(icmslam_handle* h, double* dmap_out, int out_cap, int64_t out_ld)
+{
+    const int L = h->Lcap;
+    cudaStream_t s = h->stream;
+    DevState* st = h->d_st;
+    TailState* ts = h->d_ts;
+    const double* min_x = h->d_map_in;
+    const double* min_y = h->d_map_in + L;
+    double* raw_x = h->d_raw;
+    double* raw_y = h->d_raw + L;
+    k_fused_means<<<nblk(L, 256), 256, 0, s>>>(st, h->d_fsum_x, h->d_fsum_y, h->d_cnt, min_x, min_y, 1.0 / h->fix_scale, h->dcfg.cota,
+                                               h->d_newraw, raw_x, raw_y, h->d_kflag, L);
+    CK(cudaGetLastError());
+    int rc = exclusive_sum(h, h->d_kflag, h->d_kpos, L);
+    if (rc) return rc;
+    k_tail_compact<<<nblk(L, 256), 256, 0, s>>>(st, ts, h->d_kflag, h->d_kpos, raw_x, raw_y, h->d_cnt, h->d_kx, h->d_ky, h->d_kc,
+                                                h->d_parent, h->d_bb, L);
+    CK(cudaGetLastError());
+    k_tail_geom<<<1, 1, 0, s>>>(h->d_bb, st, ts, h->dcfg.dist_thr, h->fg_cells, h->d_fg_geom);
+    CK(cudaGetLastError());
+    k_fgrid_count<<<nblk(L, 256), 256, 0, s>>>(h->d_kx, h->d_ky, &st->kept, h->d_fg_geom, h->d_fg_cnt);
+    CK(cudaGetLastError());
+    rc = exclusive_sum(h, h->d_fg_cnt, h->d_fg_start, h->fg_cells + 1);
+    if (rc) return rc;
+    k_fgrid_fill<<<nblk(L, 256), 256, 0, s>>>(h->d_kx, h->d_ky, &st->kept, h->d_fg_geom, h->d_fg_start, h->d_fg_cnt, h->d_fg_pts,
+                                              h->d_fg_idx);
+    CK(cudaGetLastError());
+    k_tail_nn<<<nblk(L, 256), 256, 0, s>>>(st, ts, h->d_kx, h->d_ky, h->d_fg_geom, h->d_fg_start, h->d_fg_pts, h->d_fg_idx, h->thr2_lt,
+                                           h->d_nn, h->d_indflag, L);
+    CK(cudaGetLastError());
+    k_tail_finalize<<<nblk(L, 256), 256, 0, s>>>(st, ts, h->d_kx, h->d_ky, h->d_kc, dmap_out, out_cap, out_ld, h->d_counts, L);
+    CK(cudaGetLastError());
+    k_tail_slow<<<1, 1024, 0, s>>>(st, ts, h->dcfg.dist_thr, h->d_kx, h->d_ky, h->d_kc, h->d_parent, h->d_nn, h->d_indflag, h->d_indpos,
+                                   h->d_ind, h->d_lab, h->d_used, h->d_rank, h->d_ox, h->d_oy, h->d_oc, dmap_out, out_cap, out_ld,
+                                   h->d_counts, L, h->fg_cells, h->d_fg_geom, h->d_fg_cnt, h->d_fg_start, h->d_fg_pts, h->d_fg_idx);
+    CK(cudaGetLastError());
+    h->n_launch += 9;
+    h->grid_map = (out_ld == L && out_cap == L) ? dmap_out : nullptr;   // the grid now indexes the new map
+    h->timed_fused = true;
+    h->lact_dirty = true;
+    return ICMSLAM_OK;
+}
+
 // One sweep on device-resident data.  The previous map is in h->d_map_in (2 x Lcap); L_in is its
 // width known on the host, or -1 when only the device knows it (= landmarks_actuales, chained
 // sweeps).  Poses are read from xin (3 x T, ldin) and the updated poses written to xout (3 x T,
@@ -648,67 +752,15 @@ static int sweep_core(icmslam_handle* h, const double* xin, int64_t ldin, double
     CK(cudaMemsetAsync(h->d_cnt, 0, ((size_t)L + 1) * sizeof(int), s));
     int rc;
     if (use_fused) {
-        if (h->grid_map != h->d_map_in) {      // the grid of the previous sweep's tail does not index this map: build it
-            rc = build_fgrid(h, min_x, min_y, &st->lsearch, n_search_cap);
-            if (rc) return rc;
-        }
         double* kout = xout;
         int64_t kld = ldout;
         if (xin == xout) { kout = (xin == h->d_x2) ? h->d_x : h->d_x2; kld = T; }
-        FusedParams P;
-        P.T = T; P.off = h->d_off; P.bxy = h->d_bxy;
-        P.xin = xin; P.ldin = ldin; P.xout = kout; P.ldout = kld;
-        P.x0[0] = x0[0]; P.x0[1] = x0[1]; P.x0[2] = x0[2];
-        P.inc = h->d_inc; P.ldinc = T; P.u = h->d_u; P.ldu = T;
-        P.cfg = h->dcfg; P.thr2_hi = h->thr2_hi; P.fix_scale = h->fix_scale; P.tol = o.newton_tol; P.maxit = o.newton_maxit;
-        P.st = st; P.geom = h->d_fg_geom; P.cell_start = h->d_fg_start; P.gpts = h->d_fg_pts; P.gidx = h->d_fg_idx;
-        P.c = h->d_c; P.fsum_x = h->d_fsum_x; P.fsum_y = h->d_fsum_y; P.cnt = h->d_cnt;
-        P.far_list = h->d_far_list; P.ts = h->d_ts; P.blk_far = h->d_blk_far;
-        P.obs_cap = h->obs_cap; P.iters = iters;
-        { const char* es = getenv("ICMSLAM_SKIP"); P.skip = es ? atoi(es) : 0; }
-        if (timing) CK(cudaEventRecord(h->ev[0], s));
-        if (h->tile_half == 32) k_sweep_fused<32><<<h->n_tiles, 128, h->fused_smem, s>>>(P);
-        else k_sweep_fused<64><<<h->n_tiles, 256, h->fused_smem, s>>>(P);
-        CK(cudaGetLastError());
-        if (timing) CK(cudaEventRecord(h->ev[1], s));
+        rc = fused_part_a(h, xin, ldin, kout, kld, x0, o, n_search_cap);
+        if (rc) return rc;
         if (kout != xout) CK(cudaMemcpy2DAsync(xout, (size_t)ldout * 8, kout, (size_t)kld * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToDevice, s));
-        // ---- tail (tail.cuh): new labels, Mapa.filtrar, and the grid of the new map -----------------------------
-        TailState* ts = h->d_ts;
-        k_tail_scan<<<1, 1024, 0, s>>>(h->d_blk_far, h->n_tiles, h->d_blk_prefix, st, ts, L, h->d_bb);
-        CK(cudaGetLastError());
-        k_tail_labels<<<148, 256, 0, s>>>(ts, h->d_far_list, h->d_blk_prefix, h->tile_own, h->d_off, st, L, h->d_c, raw_x, raw_y, h->d_cnt);
-        CK(cudaGetLastError());
-        k_fused_means<<<nblk(L, 256), 256, 0, s>>>(st, h->d_fsum_x, h->d_fsum_y, h->d_cnt, min_x, min_y, 1.0 / h->fix_scale, h->dcfg.cota,
-                                                   raw_x, raw_y, h->d_kflag, L);
-        CK(cudaGetLastError());
-        rc = exclusive_sum(h, h->d_kflag, h->d_kpos, L);
+        rc = fused_part_b(h);
         if (rc) return rc;
-        k_tail_compact<<<nblk(L, 256), 256, 0, s>>>(st, ts, h->d_kflag, h->d_kpos, raw_x, raw_y, h->d_cnt, h->d_kx, h->d_ky, h->d_kc,
-                                                    h->d_parent, h->d_bb, L);
-        CK(cudaGetLastError());
-        k_tail_geom<<<1, 1, 0, s>>>(h->d_bb, st, ts, h->dcfg.dist_thr, h->fg_cells, h->d_fg_geom);
-        CK(cudaGetLastError());
-        k_fgrid_count<<<nblk(L, 256), 256, 0, s>>>(h->d_kx, h->d_ky, &st->kept, h->d_fg_geom, h->d_fg_cnt);
-        CK(cudaGetLastError());
-        rc = exclusive_sum(h, h->d_fg_cnt, h->d_fg_start, h->fg_cells + 1);
-        if (rc) return rc;
-        k_fgrid_fill<<<nblk(L, 256), 256, 0, s>>>(h->d_kx, h->d_ky, &st->kept, h->d_fg_geom, h->d_fg_start, h->d_fg_cnt, h->d_fg_pts,
-                                                  h->d_fg_idx);
-        CK(cudaGetLastError());
-        k_tail_nn<<<nblk(L, 256), 256, 0, s>>>(st, ts, h->d_kx, h->d_ky, h->d_fg_geom, h->d_fg_start, h->d_fg_pts, h->d_fg_idx, h->thr2_lt,
-                                               h->d_nn, h->d_indflag, L);
-        CK(cudaGetLastError());
-        k_tail_finalize<<<nblk(L, 256), 256, 0, s>>>(st, ts, h->d_kx, h->d_ky, h->d_kc, dmap_out, out_cap, out_ld, h->d_counts, L);
-        CK(cudaGetLastError());
-        k_tail_slow<<<1, 1024, 0, s>>>(st, ts, h->dcfg.dist_thr, h->d_kx, h->d_ky, h->d_kc, h->d_parent, h->d_nn, h->d_indflag, h->d_indpos,
-                                       h->d_ind, h->d_lab, h->d_used, h->d_rank, h->d_ox, h->d_oy, h->d_oc, dmap_out, out_cap, out_ld,
-                                       h->d_counts, L, h->fg_cells, h->d_fg_geom, h->d_fg_cnt, h->d_fg_start, h->d_fg_pts, h->d_fg_idx);
-        CK(cudaGetLastError());
-        h->n_launch += 12;
-        h->grid_map = (out_ld == L && out_cap == L) ? dmap_out : nullptr;   // the grid now indexes the new map
-        h->timed_fused = true;
-        h->lact_dirty = true;
-        return ICMSLAM_OK;
+        return fused_part_c(h, dmap_out, out_cap, out_ld);
     } else {
         if (xin != xout) CK(cudaMemcpy2DAsync(xout, (size_t)ldout * 8, xin, (size_t)ldin * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToDevice, s));
         double* dx = xout;
@@ -973,7 +1025,7 @@ extern "C" int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const
                 slot->tol = o.newton_tol; slot->maxit = o.newton_maxit;
             }
             CK(cudaGraphLaunch(slot->exec, s));
-            h->n_launch += 14;                       // kernels of this library inside the graph
+            h->n_launch += 13;                       // kernels of this library inside the graph
             h->grid_map = h->d_map_out;
             h->timed_fused = true;
             h->lact_dirty = true;
@@ -996,6 +1048,89 @@ extern "C" int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const
             return status_from_state(h->h_st);
         }
     }
+    return ICMSLAM_OK;
+}
+
+// ---- time-segment partition: one handle per GPU owns columns [t_lo, t_hi) of the T columns it loaded ------
+extern "C" int icmslam_set_segment(icmslam_handle* h, int32_t t_lo, int32_t t_hi, int32_t is_first, int32_t is_last)
+{
+    if (!h || !h->extracted || t_lo < 0 || t_hi > h->T || t_lo >= t_hi || (t_lo & 1)) return ICMSLAM_ERR_INVALID;
+    if ((!is_first && t_lo < 2) || (!is_last && t_hi > h->T - 1)) return ICMSLAM_ERR_INVALID;   // halo columns must exist
+    h->seg_lo = t_lo; h->seg_hi = t_hi; h->seg_first = is_first ? 1 : 0; h->seg_last = is_last ? 1 : 0;
+    h->n_tiles = nblk(t_hi - t_lo, h->tile_own);
+    drop_graphs(h);
+    return ICMSLAM_OK;
+}
+
+extern "C" int icmslam_device_ptr(icmslam_handle* h, int32_t which, void** ptr, int64_t* count)
+{
+    if (!h || !ptr || !count) return ICMSLAM_ERR_INVALID;
+    const int64_t L = h->Lcap;
+    switch (which) {
+    case ICMSLAM_PTR_SEG_REC: *ptr = h->d_seg_rec; *count = SEG_REC; break;
+    case ICMSLAM_PTR_STAT_X: *ptr = h->d_fsum_x; *count = L; break;
+    case ICMSLAM_PTR_STAT_Y: *ptr = h->d_fsum_y; *count = L; break;
+    case ICMSLAM_PTR_STAT_N: *ptr = h->d_cnt; *count = L; break;
+    case ICMSLAM_PTR_NEW_LABELS: *ptr = h->d_newraw; *count = 2 * L; break;
+    case ICMSLAM_PTR_POSES: *ptr = h->x_cur ? h->d_x2 : h->d_x; *count = 3 * (int64_t)h->T; break;
+    default: return ICMSLAM_ERR_INVALID;
+    }
+    return ICMSLAM_OK;
+}
+
+// Sweep of one segment, part 1: the fused kernel on the resident poses; leaves this segment's record
+// (boundary poses, far-scan count) in the ICMSLAM_PTR_SEG_REC buffer for the all-gather.
+extern "C" int icmslam_seg_begin(icmslam_handle* h, const double* x0, const icmslam_sweep_opts* opts)
+{
+    if (!h || !h->extracted || !x0 || !h->fused_ok) return ICMSLAM_ERR_INVALID;
+    icmslam_sweep_opts o;
+    default_opts(o, opts);
+    if (!(o.fused && o.schedule == ICMSLAM_SCHED_REDBLACK && o.solver == ICMSLAM_SOLVER_NEWTON && o.map_view == ICMSLAM_VIEW_PREV))
+        return ICMSLAM_ERR_UNSUPPORTED;     // only the restated parallel sweep partitions in time
+    CK(cudaSetDevice(h->cfg.device));
+    const int T = h->T, L = h->Lcap;
+    cudaStream_t s = h->stream;
+    if (h->seg_first && h->first_empty) return ICMSLAM_EMPTY_FIRST_SCAN;
+    if (h->seg_last && h->last_empty && T > 1) return ICMSLAM_ERR_EMPTY_LAST;
+    double* src = h->x_cur ? h->d_x2 : h->d_x;
+    double* dst = h->x_cur ? h->d_x : h->d_x2;
+    CK(cudaMemsetAsync(h->d_counts, 0, (size_t)L * sizeof(double), s));
+    k_sweep_begin<<<1, 1, 0, s>>>(h->d_st, h->d_ts, L);
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(h->d_cnt, 0, ((size_t)L + 1) * sizeof(int), s));
+    int rc = fused_part_a(h, src, T, dst, T, x0, o, L);
+    if (rc) return rc;
+    k_seg_pack<<<1, 32, 0, s>>>(dst, T, h->seg_lo, h->seg_hi, h->d_ts, h->d_seg_rec);
+    CK(cudaGetLastError());
+    h->seg_dst = dst;
+    h->n_launch += 2;
+    return ICMSLAM_OK;
+}
+
+// part 2: `gathered` = world x SEG_REC doubles (device), the all-gather of every segment's record.  Fills this
+// segment's halo poses, numbers its new labels globally and writes their statistics.  After this call the
+// caller sum-reduces ICMSLAM_PTR_STAT_X / _Y / _N / _NEW_LABELS over the segments.
+extern "C" int icmslam_seg_exchange(icmslam_handle* h, const double* gathered, int32_t rank, int32_t world)
+{
+    if (!h || !gathered || !h->seg_dst || rank < 0 || rank >= world) return ICMSLAM_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    k_seg_unpack<<<1, 32, 0, h->stream>>>(gathered, rank, world, h->seg_dst, h->T, h->T, h->d_st, h->d_ts, h->Lcap);
+    CK(cudaGetLastError());
+    h->n_launch += 1;
+    return fused_part_b(h);
+}
+
+// part 3: landmark update + Mapa.filtrar on the reduced statistics (identical on every segment).
+extern "C" int icmslam_seg_finish(icmslam_handle* h)
+{
+    if (!h || !h->seg_dst) return ICMSLAM_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    const int L = h->Lcap;
+    int rc = fused_part_c(h, h->d_map_out, L, L);
+    if (rc) return rc;
+    h->seg_dst = nullptr;
+    h->x_cur ^= 1;
+    double* t = h->d_map_in; h->d_map_in = h->d_map_out; h->d_map_out = t;   // mapa_viejo = mapa_refinado (sensors.py:315)
     return ICMSLAM_OK;
 }
 

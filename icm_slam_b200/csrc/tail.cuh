@@ -31,8 +31,14 @@ struct TailState {
     int far_count;      // far records appended by the fused kernel this sweep
     int n_ind;          // survivors with a neighbour closer than dist_thr
     int degenerate;     // bounding box smaller than dist_thr: the reference's zero-distance rule matters
-    int pad;
+    int far_total;      // scans with far observations in THIS handle's segment
+    int label_base;     // such scans in the segments before this one (0 on a single GPU)
+    int pad[3];
 };
+
+// What neighbouring time segments tell each other after a sweep (16 doubles per rank, all-gathered):
+// [0..2] first owned pose, [3..5] second-to-last owned pose, [6..8] last owned pose, [9] far_total.
+#define SEG_REC 16
 
 __global__ void __launch_bounds__(1024)
 k_tail_scan(const int* __restrict__ blk_far, int nblk_, int* __restrict__ blk_prefix, DevState* st, TailState* ts, int Lcap,
@@ -60,7 +66,9 @@ k_tail_scan(const int* __restrict__ blk_far, int nblk_, int* __restrict__ blk_pr
     for (int i = lo; i < hi; ++i) { blk_prefix[i] = run; run += blk_far[i]; }
     if (tid == 0) {
         const int total = wsum[31];
-        st->n_far_scans = total;
+        ts->far_total = total;
+        ts->label_base = 0;
+        st->n_far_scans = total;              // (a segmented run overwrites these three in k_seg_unpack)
         st->raw_l = st->lact0 + total;
         if (st->lact0 + total > Lcap) st->status = ST_LABEL_CAP;   // IndexError at ICM_SLAM.py:191
         ts->n_ind = 0;
@@ -71,14 +79,14 @@ k_tail_scan(const int* __restrict__ blk_far, int nblk_, int* __restrict__ blk_pr
 }
 
 __global__ void __launch_bounds__(256)
-k_tail_labels(const TailState* ts, const FarRec* __restrict__ far, const int* __restrict__ blk_prefix, int tile, const int* __restrict__ off,
+k_tail_labels(const TailState* ts, const FarRec* __restrict__ far, const int* __restrict__ blk_prefix, int tile, int t_lo, const int* __restrict__ off,
               const DevState* st, int Lcap, int* __restrict__ c, double* __restrict__ raw_x, double* __restrict__ raw_y, int* __restrict__ cnt)
 {
     const int nrec = ts->far_count;
-    const int lact0 = st->lact0;
+    const int lact0 = st->lact0 + ts->label_base;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nrec; k += gridDim.x * blockDim.x) {
         const FarRec r = far[k];
-        const int label = lact0 + blk_prefix[r.t / tile] + r.rank;
+        const int label = lact0 + blk_prefix[(r.t - t_lo) / tile] + r.rank;
         if (label >= Lcap) continue;
         raw_x[label] = r.sx / (double)r.n;
         raw_y[label] = r.sy / (double)r.n;
@@ -329,5 +337,48 @@ k_tail_slow(DevState* st, TailState* ts, double dist_thr, double* kx, double* ky
                     gidx[p] = r;
                 }
         }
+    }
+}
+
+
+// ---- time-segment partition (one segment per GPU) ---------------------------------------------------------
+// after the fused kernel: this segment's boundary poses and its count of scans with far observations
+__global__ void k_seg_pack(const double* __restrict__ x, int64_t ld, int t_lo, int t_hi, const TailState* ts, double* __restrict__ rec)
+{
+    const int i = threadIdx.x;
+    if (i < 3) {
+        rec[i] = x[i * ld + t_lo];
+        rec[3 + i] = x[i * ld + max(t_hi - 2, t_lo)];
+        rec[6 + i] = x[i * ld + t_hi - 1];
+    }
+    if (i == 9) rec[9] = (double)ts->far_total;
+    if (i > 9 && i < SEG_REC) rec[i] = 0.0;
+}
+
+// after the all-gather: neighbours' boundary poses into this segment's halo columns (0, 1 and T-1), and the
+// global numbering of the new labels (exclusive prefix over the ranks of far_total, ICM_SLAM.py:174-182)
+__global__ void k_seg_unpack(const double* __restrict__ all, int rank, int world, double* __restrict__ x, int64_t ld, int T, DevState* st,
+                             TailState* ts, int Lcap)
+{
+    const int i = threadIdx.x;
+    if (i < 3) {
+        if (rank > 0) {
+            const double* l = all + (size_t)(rank - 1) * SEG_REC;
+            x[i * ld + 0] = l[3 + i];
+            x[i * ld + 1] = l[6 + i];
+        }
+        if (rank + 1 < world) x[i * ld + T - 1] = all[(size_t)(rank + 1) * SEG_REC + i];
+    }
+    if (i == 0) {
+        int base = 0, total = 0;
+        for (int r = 0; r < world; ++r) {
+            const int f = (int)all[(size_t)r * SEG_REC + 9];
+            if (r < rank) base += f;
+            total += f;
+        }
+        ts->label_base = base;
+        st->n_far_scans = total;
+        st->raw_l = st->lact0 + total;
+        if (st->lact0 + total > Lcap) st->status = ST_LABEL_CAP;
     }
 }

@@ -147,6 +147,26 @@ int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const double* x0
 int icmslam_set_poses(icmslam_handle* h, const double* x, int64_t ld_x, int32_t memspace);
 int icmslam_get_poses(icmslam_handle* h, double* x, int64_t ld_x, int32_t memspace);
 
+/* -- time-segment partition over several GPUs (no reference counterpart: the reference sweep is strictly
+ * sequential in time, sensors.py:145-162; only the restated (REDBLACK, NEWTON, PREV) sweep partitions).
+ * One handle per GPU loads the columns [g_lo - 2, g_hi + 1) of the trajectory (two halo columns on the
+ * left unless it holds the first pose, one on the right unless it holds the last) and owns the local
+ * columns [t_lo, t_hi) (t_lo even).  A sweep is then
+ *     icmslam_seg_begin    -> all-gather of every segment's ICMSLAM_PTR_SEG_REC record (16 doubles)
+ *     icmslam_seg_exchange -> sum-reduction of ICMSLAM_PTR_STAT_X, _STAT_Y (int64), _STAT_N (int32) and
+ *                             ICMSLAM_PTR_NEW_LABELS (fp64, disjoint non-zeros) over the segments
+ *     icmslam_seg_finish
+ * with the collectives issued by the caller (NCCL through torch.distributed in icm_slam_b200/multigpu.py)
+ * on the handle's stream.  The landmark statistics are integers, so every segment computes bit-identical
+ * maps for any number of GPUs. */
+enum { ICMSLAM_PTR_SEG_REC = 0, ICMSLAM_PTR_STAT_X = 1, ICMSLAM_PTR_STAT_Y = 2, ICMSLAM_PTR_STAT_N = 3,
+       ICMSLAM_PTR_NEW_LABELS = 4, ICMSLAM_PTR_POSES = 5 };
+int icmslam_set_segment(icmslam_handle* h, int32_t t_lo, int32_t t_hi, int32_t is_first, int32_t is_last);
+int icmslam_device_ptr(icmslam_handle* h, int32_t which, void** ptr, int64_t* count);
+int icmslam_seg_begin(icmslam_handle* h, const double* x0, const icmslam_sweep_opts* opts);
+int icmslam_seg_exchange(icmslam_handle* h, const double* gathered, int32_t rank, int32_t world);
+int icmslam_seg_finish(icmslam_handle* h);
+
 /* -- instrumentation (no reference counterpart).  Kernel time of the last sweep run with
  * opts.reserved & 2, from CUDA events on the handle's stream: out2[0] = association (or the fused
  * sweep kernel), out2[1] = pose kernels (0 when fused), milliseconds.  Launch count = kernels of

@@ -408,3 +408,77 @@ def test_fused_launch_count_and_kernel_timer():
     assert a > 0.0 and b == 0.0
     assert e.launch_count() - n0 >= 2 * 14
     e.close()
+
+
+# ---- time-segment partition: several segments emulated on ONE GPU must reproduce the single-engine sweep -----
+def _segmented_vs_single(d, cfgd, world, nsweeps):
+    import ctypes as C
+    import torch
+    from icm_slam_b200 import _lib
+    from icm_slam_b200.multigpu import SegmentedSolver, SEG_REC
+    z, odo, u = d["observations"], d["odometry"], d["velocities"]
+    cfg = _cfg(**cfgd)
+    single = _engine(cfg, z, odo, u)
+    single.set_map(d["map_init"])
+    single.set_poses(d["x_init"])
+    sols = [SegmentedSolver(cfg, r, world, device=0) for r in range(world)]
+    for s in sols:
+        s.load(z, odo, u, precondition=True)
+        s.set_map(d["map_init"])
+        s.set_poses(d["x_init"])
+        s._bind()
+    assert sum(s.t_hi - s.t_lo for s in sols) == z.shape[1]
+    opts = _lib.SweepOpts(_lib.SCHED["redblack"], _lib.SOLVER["newton"], _lib.VIEW["prev"], 0, 0.0, 1, 0)
+    for k in range(nsweeps):
+        single.iterate(None, odo[:, 0], 1)
+        for s in sols:
+            _lib.check(s.engine.lib.icmslam_seg_begin(s.engine._h, C.c_void_p(s.x0.ctypes.data), C.byref(opts)), s.engine._h)
+        for s in sols:
+            s.engine.synchronize()
+        allrec = torch.stack([s._views["rec"].clone() for s in sols]).contiguous()          # the all-gather
+        assert allrec.shape == (world, SEG_REC)
+        for s in sols:
+            _lib.check(s.engine.lib.icmslam_seg_exchange(s.engine._h, C.c_void_p(allrec.data_ptr()), s.rank, world), s.engine._h)
+        for s in sols:
+            s.engine.synchronize()
+        for key in ("sx", "sy", "sn", "new"):                                               # the sum-reduction
+            tot = torch.stack([s._views[key] for s in sols]).sum(0)
+            for s in sols:
+                s._views[key].copy_(tot)
+        torch.cuda.synchronize()
+        for s in sols:
+            _lib.check(s.engine.lib.icmslam_seg_finish(s.engine._h), s.engine._h)
+        xs = np.concatenate([s.owned_poses() for s in sols], axis=1)
+        x1 = single.get_poses()
+        assert np.array_equal(xs, x1), (k, np.abs(xs - x1).max())
+        m1 = single.get_map()
+        for s in sols:
+            assert np.array_equal(s.get_map(), m1), k
+        off1 = single.get_extraction()["off"]
+        c1 = single.associations()
+        for s in sols:
+            g_lo, g_hi = s.segments[s.rank]
+            offs = s.engine.get_extraction()["off"]
+            cs = s.engine.associations()[offs[s.t_lo]:offs[s.t_hi]]
+            assert np.array_equal(cs, c1[off1[g_lo]:off1[g_hi]]), k
+    single.close()
+    for s in sols:
+        s.close()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_segments_reproduce_single_engine_bit_for_bit(world):
+    d, cfgd = _synthetic_case(625, 4000, 20181 + 13)
+    _segmented_vs_single(d, cfgd, world, 3)
+
+
+def test_segments_with_new_labels_and_merges():
+    """Landmarks displaced in the initial map: scans create new labels (numbered across segments) and the filter merges."""
+    d, cfgd = _synthetic_case(625, 3000, 20181 + 14)
+    d = dict(d)
+    m = d["map_init"].copy()
+    m[:, ::9] += 3.0
+    m = np.concatenate([m, m[:, :40] + 0.3], axis=1)      # near-duplicates: merged by Mapa.filtrar
+    d["map_init"] = m
+    cfgd = dict(cfgd, L=4096)
+    _segmented_vs_single(d, cfgd, 4, 3)
