@@ -83,6 +83,8 @@ struct icmslam_handle {
     // time-segment partition (icmslam_set_segment): this handle owns columns [seg_lo, seg_hi) of its T columns
     int seg_lo = 0, seg_hi = 0, seg_first = 1, seg_last = 1;
     double* d_newraw = nullptr;   // 2 x Lcap: means of the sweep's new labels (zero elsewhere)
+    long long* d_exch = nullptr;  // ONE block [fsum_x | fsum_y | newraw | cnt]: what the segments sum-reduce, viewed as int64
+    int64_t exch_words = 0;
     double* d_seg_rec = nullptr;  // SEG_REC doubles: what this segment tells its neighbours
     double* seg_dst = nullptr;    // output pose buffer of the segment sweep in flight
     size_t fused_smem = 0;
@@ -155,15 +157,15 @@ extern "C" int icmslam_destroy(icmslam_handle* h)
     if (!h) return ICMSLAM_OK;
     cudaSetDevice(h->cfg.device);
     free_dataset(h);
-    DFREE(h->d_sum_x); DFREE(h->d_sum_y); DFREE(h->d_raw); DFREE(h->d_counts); DFREE(h->d_cnt); DFREE(h->d_seg);
+    DFREE(h->d_sum_x); DFREE(h->d_sum_y); DFREE(h->d_raw); DFREE(h->d_counts); DFREE(h->d_seg);
     DFREE(h->d_kflag); DFREE(h->d_kpos); DFREE(h->d_parent); DFREE(h->d_nn); DFREE(h->d_indflag); DFREE(h->d_indpos);
     DFREE(h->d_ind); DFREE(h->d_lab); DFREE(h->d_used); DFREE(h->d_rank);
     DFREE(h->d_kx); DFREE(h->d_ky); DFREE(h->d_kc); DFREE(h->d_ox); DFREE(h->d_oy); DFREE(h->d_oc); DFREE(h->d_acc);
     DFREE(h->d_map_in); DFREE(h->d_map_out); DFREE(h->d_tmp_a); DFREE(h->d_tmp_b);
     DFREE(h->d_cell_start); DFREE(h->d_cell_fill); DFREE(h->d_cell_id); DFREE(h->d_gidx); DFREE(h->d_glx); DFREE(h->d_gly);
     DFREE(h->d_st); DFREE(h->d_cub);
-    DFREE(h->d_fsum_x); DFREE(h->d_fsum_y); DFREE(h->d_fg_cnt); DFREE(h->d_fg_start); DFREE(h->d_fg_idx);
-    DFREE(h->d_fg_pts); DFREE(h->d_fg_geom); DFREE(h->d_bb); DFREE(h->d_ts); DFREE(h->d_newraw); DFREE(h->d_seg_rec);
+    DFREE(h->d_exch); DFREE(h->d_fg_cnt); DFREE(h->d_fg_start); DFREE(h->d_fg_idx);
+    DFREE(h->d_fg_pts); DFREE(h->d_fg_geom); DFREE(h->d_bb); DFREE(h->d_ts); DFREE(h->d_seg_rec);
     if (h->h_st) cudaFreeHost(h->h_st);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -212,7 +214,13 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     if (e == cudaSuccess) e = dalloc(&h->d_sum_y, L);
     if (e == cudaSuccess) e = dalloc(&h->d_raw, 2 * L);
     if (e == cudaSuccess) e = dalloc(&h->d_counts, L);
-    if (e == cudaSuccess) e = dalloc(&h->d_cnt, L + 1);
+    {   // exchange block (see icmslam_device_ptr): 64-bit words
+        const size_t wcnt = (L + 2) / 2;
+        h->exch_words = (int64_t)(4 * L + wcnt);
+        if (e == cudaSuccess) e = dalloc(&h->d_exch, (size_t)h->exch_words);
+        if (e == cudaSuccess) e = cudaMemset(h->d_exch, 0, (size_t)h->exch_words * 8);
+        h->d_fsum_x = h->d_exch; h->d_fsum_y = h->d_exch + L; h->d_newraw = (double*)(h->d_exch + 2 * L); h->d_cnt = (int*)(h->d_exch + 4 * L);
+    }
     if (e == cudaSuccess) e = dalloc(&h->d_seg, L + 1);
     if (e == cudaSuccess) e = dalloc(&h->d_kflag, L);
     if (e == cudaSuccess) e = dalloc(&h->d_kpos, L);
@@ -242,8 +250,6 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     if (e == cudaSuccess) e = dalloc(&h->d_glx, L);
     if (e == cudaSuccess) e = dalloc(&h->d_gly, L);
     h->fg_cells = (int)(4 * L > 4096 ? 4 * L : 4096);
-    if (e == cudaSuccess) e = dalloc(&h->d_fsum_x, L);
-    if (e == cudaSuccess) e = dalloc(&h->d_fsum_y, L);
     if (e == cudaSuccess) e = dalloc(&h->d_fg_cnt, (size_t)h->fg_cells + 2);
     if (e == cudaSuccess) e = dalloc(&h->d_fg_start, (size_t)h->fg_cells + 2);
     if (e == cudaSuccess) e = dalloc(&h->d_fg_idx, 4 * L);    // replicated binning: <= 4 cells per landmark
@@ -251,13 +257,9 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     if (e == cudaSuccess) e = dalloc(&h->d_fg_geom, 1);
     if (e == cudaSuccess) e = dalloc(&h->d_bb, 4);
     if (e == cudaSuccess) e = dalloc(&h->d_ts, 1);
-    if (e == cudaSuccess) e = dalloc(&h->d_newraw, 2 * L);
-    if (e == cudaSuccess) e = cudaMemset(h->d_newraw, 0, 2 * L * sizeof(double));
     if (e == cudaSuccess) e = dalloc(&h->d_seg_rec, SEG_REC);
     if (e == cudaSuccess) e = cudaMemset(h->d_ts, 0, sizeof(TailState));
     { const char* eg = getenv("ICMSLAM_GRAPH"); if (eg) h->use_graph = atoi(eg); }
-    if (e == cudaSuccess) e = cudaMemset(h->d_fsum_x, 0, L * sizeof(long long));
-    if (e == cudaSuccess) e = cudaMemset(h->d_fsum_y, 0, L * sizeof(long long));
     if (e == cudaSuccess) e = cudaMemset(h->d_fg_cnt, 0, ((size_t)h->fg_cells + 2) * sizeof(int));
     {   // gate and fixed-point scale of the fused path
         const double thr = cfg->dist_thr;
@@ -1073,6 +1075,7 @@ extern "C" int icmslam_device_ptr(icmslam_handle* h, int32_t which, void** ptr, 
     case ICMSLAM_PTR_STAT_N: *ptr = h->d_cnt; *count = L; break;
     case ICMSLAM_PTR_NEW_LABELS: *ptr = h->d_newraw; *count = 2 * L; break;
     case ICMSLAM_PTR_POSES: *ptr = h->x_cur ? h->d_x2 : h->d_x; *count = 3 * (int64_t)h->T; break;
+    case ICMSLAM_PTR_EXCHANGE: *ptr = h->d_exch; *count = h->exch_words; break;
     default: return ICMSLAM_ERR_INVALID;
     }
     return ICMSLAM_OK;

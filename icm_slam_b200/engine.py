@@ -197,14 +197,15 @@ class Engine:
 
     def set_poses(self, x):
         """ICM.positions (3 x T) -> device; iterate(None, ...) then sweeps them in place on the device."""
-        if not _is_torch(x):
+        if not _is_torch(x) and not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.ndim == 2 and x.strides[1] == 8):
             x = np.ascontiguousarray(x, dtype=np.float64)
         px, ms = _ptr(x)
         check(self.lib.icmslam_set_poses(self._h, px, _rows(x, 3), ms), self._h)
 
-    def get_poses(self):
-        out = np.empty((3, self.T))
-        check(self.lib.icmslam_get_poses(self._h, _ptr(out)[0], self.T, HOST), self._h)
+    def get_poses(self, out=None):
+        if out is None:
+            out = np.empty((3, self.T))
+        check(self.lib.icmslam_get_poses(self._h, _ptr(out)[0], _rows(out, 3), HOST), self._h)
         return out
 
     def kernel_ms(self):

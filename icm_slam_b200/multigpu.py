@@ -24,7 +24,7 @@ import ctypes as C
 import numpy as np
 
 SEG_REC = 16
-PTR_SEG_REC, PTR_STAT_X, PTR_STAT_Y, PTR_STAT_N, PTR_NEW_LABELS, PTR_POSES = range(6)
+PTR_SEG_REC, PTR_STAT_X, PTR_STAT_Y, PTR_STAT_N, PTR_NEW_LABELS, PTR_POSES, PTR_EXCHANGE = range(7)
 
 
 # ---- partition ---------------------------------------------------------------------------------------------
@@ -142,7 +142,7 @@ class SegmentedSolver:
         self.engine.set_map(mapa)
 
     def set_poses(self, x_full):
-        self.engine.set_poses(np.ascontiguousarray(np.asarray(x_full)[:, self.c_lo:self.c_hi], dtype=np.float64))
+        self.engine.set_poses(np.asarray(x_full)[:, self.c_lo:self.c_hi])      # (a strided view: copied by the library)
 
     # -- views of the library's exchange buffers ------------------------------------------------------------------
     def _ptr(self, which):
@@ -156,7 +156,7 @@ class SegmentedSolver:
         dev = "cuda:%d" % self.device
         mk = lambda which, ts: torch.as_tensor(_DevBuf(*self._ptr(which), ts), device=dev)
         self._views = dict(rec=mk(PTR_SEG_REC, "<f8"), sx=mk(PTR_STAT_X, "<i8"), sy=mk(PTR_STAT_Y, "<i8"), sn=mk(PTR_STAT_N, "<i4"),
-                           new=mk(PTR_NEW_LABELS, "<f8"))
+                           new=mk(PTR_NEW_LABELS, "<f8"), all=mk(PTR_EXCHANGE, "<i8"))
 
     # -- one sweep ------------------------------------------------------------------------------------------------
     def sweep(self, n_sweeps: int = 1):
@@ -173,14 +173,19 @@ class SegmentedSolver:
             if self.world > 1:
                 allrec = gather_records(v["rec"], self.group)
                 check(e.lib.icmslam_seg_exchange(e._h, C.c_void_p(allrec.data_ptr()), self.rank, self.world), e._h)
-                reduce_statistics([v["sx"], v["sy"], v["sn"], v["new"]], self.group)
+                reduce_statistics([v["all"]], self.group)      # the four statistics buffers as one block of int64 words
                 self._keep = allrec      # (kept alive until the next sweep's kernels have consumed it)
             else:
                 check(e.lib.icmslam_seg_exchange(e._h, C.c_void_p(v["rec"].data_ptr()), 0, 1), e._h)
             check(e.lib.icmslam_seg_finish(e._h), e._h)
 
     # -- results --------------------------------------------------------------------------------------------------
-    def owned_poses(self):
+    def owned_poses(self, out_full=None):
+        """Owned columns of the current poses; with out_full (3 x T host array) they are written in place there."""
+        if out_full is not None:
+            g_lo, g_hi = self.segments[self.rank]
+            self.engine.get_poses(out=out_full[:, g_lo - self.t_lo:g_lo - self.t_lo + (self.c_hi - self.c_lo)])
+            return out_full[:, g_lo:g_hi]
         return self.engine.get_poses()[:, self.t_lo:self.t_hi]
 
     def gather_poses(self):
@@ -259,7 +264,7 @@ def bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, p
         _lib.check(e.lib.icmslam_seg_begin(e._h, C.c_void_p(sol.x0.ctypes.data), C.byref(opts)), e._h)
         allrec = gather_records(sol._views["rec"])
         _lib.check(e.lib.icmslam_seg_exchange(e._h, C.c_void_p(allrec.data_ptr()), rank, world), e._h)
-        reduce_statistics([sol._views[k] for k in ("sx", "sy", "sn", "new")])
+        reduce_statistics([sol._views["all"]])
         _lib.check(e.lib.icmslam_seg_finish(e._h), e._h)
         kt.append(e.kernel_ms()[0])
     k_ms = torch.tensor([float(np.mean(kt))], dtype=torch.float64, device=dev)
@@ -277,8 +282,7 @@ def bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, p
         sol.set_poses(x_host)
         h2d += mapa.nbytes + 24 * (sol.c_hi - sol.c_lo)
         sol.sweep()
-        own = sol.owned_poses()
-        x_host[:, sol.segments[rank][0]:sol.segments[rank][1]] = own
+        own = sol.owned_poses(out_full=x_host)      # D2H straight into the caller's 3 x T array
         mapa = sol.get_map()
         d2h += own.nbytes + mapa.nbytes
     torch.cuda.synchronize()

@@ -154,13 +154,16 @@ int icmslam_get_poses(icmslam_handle* h, double* x, int64_t ld_x, int32_t memspa
  * columns [t_lo, t_hi) (t_lo even).  A sweep is then
  *     icmslam_seg_begin    -> all-gather of every segment's ICMSLAM_PTR_SEG_REC record (16 doubles)
  *     icmslam_seg_exchange -> sum-reduction of ICMSLAM_PTR_STAT_X, _STAT_Y (int64), _STAT_N (int32) and
- *                             ICMSLAM_PTR_NEW_LABELS (fp64, disjoint non-zeros) over the segments
+ *                             ICMSLAM_PTR_NEW_LABELS (fp64, disjoint non-zeros) over the segments; the four
+ *                             live in one block, ICMSLAM_PTR_EXCHANGE, that may be reduced as int64 words
+ *                             in ONE all-reduce (counts never carry out of 32 bits; a new label's mean is
+ *                             non-zero on exactly one segment, so adding bit patterns reproduces it)
  *     icmslam_seg_finish
  * with the collectives issued by the caller (NCCL through torch.distributed in icm_slam_b200/multigpu.py)
  * on the handle's stream.  The landmark statistics are integers, so every segment computes bit-identical
  * maps for any number of GPUs. */
 enum { ICMSLAM_PTR_SEG_REC = 0, ICMSLAM_PTR_STAT_X = 1, ICMSLAM_PTR_STAT_Y = 2, ICMSLAM_PTR_STAT_N = 3,
-       ICMSLAM_PTR_NEW_LABELS = 4, ICMSLAM_PTR_POSES = 5 };
+       ICMSLAM_PTR_NEW_LABELS = 4, ICMSLAM_PTR_POSES = 5, ICMSLAM_PTR_EXCHANGE = 6 };
 int icmslam_set_segment(icmslam_handle* h, int32_t t_lo, int32_t t_hi, int32_t is_first, int32_t is_last);
 int icmslam_device_ptr(icmslam_handle* h, int32_t which, void** ptr, int64_t* count);
 int icmslam_seg_begin(icmslam_handle* h, const double* x0, const icmslam_sweep_opts* opts);
