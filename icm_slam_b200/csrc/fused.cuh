@@ -63,6 +63,9 @@ struct FusedParams {
     const DevState* st;
     const FGeom* geom;
     const int* cell_start; const double2* gpts; const int* gidx;
+    const LmRec* lmrec;                   // landmarks by label: position + hint radius
+    const int* remap;                     // last sweep's label -> this map's label (hints)
+    int hints;                            // c[] holds last sweep's labels for this map chain
     int* c;                               // labels per observation (out)
     long long* fsum_x; long long* fsum_y; int* cnt;   // per previous-map landmark statistics
     FarRec* far_list; TailState* ts; int* blk_far;    // scans with far observations (each creates one new label)
@@ -336,8 +339,8 @@ k_sweep_fused(const FusedParams p)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FusedSmemFixed<HALF>& S = *reinterpret_cast<FusedSmemFixed<HALF>*>(smem_raw);
     double2* sb = reinterpret_cast<double2*>(smem_raw + sizeof(FusedSmemFixed<HALF>));   // staged observations; later run sums
-    int* sbk = reinterpret_cast<int*>(sb + p.obs_cap);                              // winner's grid position (-1 far)
-    unsigned short* srn = reinterpret_cast<unsigned short*>(sbk + p.obs_cap);       // run length at run heads
+    int* sbk = reinterpret_cast<int*>(sb + p.obs_cap);                              // label of each observation (-1 far)
+    unsigned short* srn = reinterpret_cast<unsigned short*>(sbk + p.obs_cap);       // run length at run heads (phase A: cell entry count)
     unsigned char* slt = reinterpret_cast<unsigned char*>(srn + p.obs_cap);         // scan (local pose index) of each observation
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -443,13 +446,68 @@ k_sweep_fused(const FusedParams p)
             const int m = ce - co;
             const int per = (((m + FS_WARPS - 1) / FS_WARPS) + 127) & ~127;
             const int wa = warp * per, wb = min(wa + per, m);
-            for (int base = wa; base < wb && !(p.skip & 32); base += 128) {
+            // pass A0 (hints): last sweep's label of the same observation, carried through the filter's renumbering,
+            // is accepted when the observation lies inside the landmark's proven-nearest radius (tail.cuh
+            // hint_radius2): one coalesced load and one gather instead of the grid search.  Lanes it cannot settle
+            // stay pending for A1/A2.
+            unsigned long long pend = 0ull;
+            const bool use_hints = p.hints != 0 && have_map && !(p.skip & 32);
+            const bool ident = p.ts->remap_identity != 0;
+            const int lsearch = p.st->lsearch;
+            int slot = 0;
+            for (int base = wa; base < wb; base += 128, slot += 4) {
+                int h_[4];
+                double wx_[4], wy_[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + u * 32 + lane;
+                    h_[u] = -1; wx_[u] = 0.0; wy_[u] = 0.0;
+                    if (i < wb && use_hints) {
+                        h_[u] = p.c[co + i];
+                        if (h_[u] >= p.cfg.L) h_[u] = -1;          // (labels of scans this handle does not own are not maintained)
+                        const double2 bq = sb[i];
+                        const int lt = slt[i];
+                        const double2 pq = S.pp[lt], rc = S.rsc[lt];
+                        wx_[u] = add_rn(__fma_rn(bq.y, -rc.x, mul_rn(bq.x, rc.y)), pq.x);
+                        wy_[u] = add_rn(__fma_rn(bq.y, rc.y, mul_rn(bq.x, rc.x)), pq.y);
+                    }
+                }
+                if (!ident) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (h_[u] >= 0) h_[u] = __ldg(p.remap + h_[u]);
+                }
+                double2 q_[4];
+                double r2_[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    q_[u] = make_double2(0.0, 0.0); r2_[u] = -1.0;
+                    if (h_[u] >= 0 && h_[u] < lsearch) {
+                        const double2* rp = reinterpret_cast<const double2*>(p.lmrec + h_[u]);
+                        q_[u] = __ldg(rp); r2_[u] = __ldg(rp + 1).x;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + u * 32 + lane;
+                    if (i < wb) {
+                        const bool ok = dist2_rn(q_[u].x - wx_[u], q_[u].y - wy_[u]) <= r2_[u];
+                        if (ok) {
+                            sbk[i] = h_[u];
+                            if (!ident && slt[i] >= 2) p.c[co + i] = h_[u];    // (with the identity renumbering c[] already holds it)
+                        } else pend |= 1ull << (slot + u);
+                    }
+                }
+            }
+            const bool any_pend = __any_sync(FULLMASK, pend != 0ull) && !(p.skip & 32);
+            if (p.skip & 32) for (int i = wa + lane; i < wb; i += 32) sbk[i] = -1;
+            slot = 0;
+            for (int base = wa; base < wb && any_pend; base += 128, slot += 4) {
                 int s_[4], e_[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int i = base + u * 32 + lane;
                     s_[u] = 0; e_[u] = 0;
-                    if (i < wb && have_map) {
+                    if (i < wb && have_map && ((pend >> (slot + u)) & 1ull)) {
                         const double2 bq = sb[i];
                         const int lt = slt[i];
                         const double2 pq = S.pp[lt], rc = S.rsc[lt];
@@ -462,11 +520,11 @@ k_sweep_fused(const FusedParams p)
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int i = base + u * 32 + lane;
-                    if (i < wb) { sbk[i] = s_[u]; srn[i] = (unsigned short)min(e_[u] - s_[u], 65535); }
+                    if (i < wb && ((pend >> (slot + u)) & 1ull)) { sbk[i] = s_[u]; srn[i] = (unsigned short)min(e_[u] - s_[u], 65535); }
                 }
             }
-            if (p.skip & 32) for (int i = wa + lane; i < wb; i += 32) sbk[i] = -1;
-            for (int base = wa; base < wb && !(p.skip & 32); base += 128) {
+            slot = 0;
+            for (int base = wa; base < wb && any_pend; base += 128, slot += 4) {
                 double wx_[4], wy_[4];
                 double2 p_[4];
                 int id_[4], s_[4], n_[4];
@@ -474,7 +532,7 @@ k_sweep_fused(const FusedParams p)
                 for (int u = 0; u < 4; ++u) {
                     const int i = base + u * 32 + lane;
                     s_[u] = 0; n_[u] = 0; id_[u] = -1; p_[u] = make_double2(0.0, 0.0); wx_[u] = 0.0; wy_[u] = 0.0;
-                    if (i < wb) {
+                    if (i < wb && ((pend >> (slot + u)) & 1ull)) {
                         s_[u] = sbk[i]; n_[u] = (p.skip & 1) ? 0 : srn[i];
                         const double2 bq = sb[i];
                         const int lt = slt[i];
@@ -488,12 +546,12 @@ k_sweep_fused(const FusedParams p)
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int i = base + u * 32 + lane;
-                    if (i < wb) {
+                    if (i < wb && ((pend >> (slot + u)) & 1ull)) {
                         double best;
                         int bid;
                         const int bk = fgrid_scan_pre(G, wx_[u], wy_[u], s_[u], n_[u], p_[u], id_[u], best, bid);
                         const bool far = bk < 0 || best > p.thr2_hi;      // amin > dist_thr (ICM_SLAM.py:172)
-                        sbk[i] = far ? -1 : bk;
+                        sbk[i] = far ? -1 : bid;                          // the label (index in the previous map)
                         if (slt[i] >= 2) p.c[co + i] = far ? -1 : bid;    // the halo scan (lt == 1) is not owned
                     }
                 }
@@ -535,7 +593,7 @@ k_sweep_fused(const FusedParams p)
                 const bool matched = act && bk >= 0;
                 double2 lm = make_double2(0.0, 0.0);
                 int lab = -1;
-                if (matched) { lm = __ldg(p.gpts + bk); lab = __ldg(G.idx + bk); }
+                if (matched) { lm = __ldg(reinterpret_cast<const double2*>(p.lmrec + bk)); lab = bk; }
                 const double dn = (double)n;
                 const double rwx = fma(ct, sxy.x, -st * sxy.y), rwy = fma(st, sxy.x, ct * sxy.y);   // sum of rotated beams
                 const double yx = lm.x - px, yy = lm.y - py;

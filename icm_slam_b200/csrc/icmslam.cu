@@ -68,6 +68,11 @@ struct icmslam_handle {
     TailState* d_ts = nullptr;
     double thr2_lt = 0.0;        // largest s with sqrt_rn(s) < dist_thr
     const double* grid_map = nullptr;   // the map buffer the fast grid currently indexes (nullptr: rebuild)
+    const double* hint_map = nullptr;   // the map buffer for which c[] (through d_remap) holds last sweep's labels
+    LmRec* d_lmrec = nullptr;           // landmarks of the current map by label (position + hint radius)
+    int* d_remap = nullptr;             // label of the last sweep -> label in the current map
+    double* d_nnd2 = nullptr;
+    double thr1sq = 0.0;
     struct GraphSlot { cudaGraphExec_t exec = nullptr; const double* src = nullptr; const double* map_in = nullptr; double x0[3] = {0, 0, 0}; double tol = 0; int maxit = 0; };
     GraphSlot graphs[4];
     int use_graph = 1;
@@ -147,6 +152,7 @@ static void free_dataset(icmslam_handle* h)
     DFREE(h->d_inc); DFREE(h->d_x2); DFREE(h->d_far_list); DFREE(h->d_blk_far); DFREE(h->d_blk_prefix); DFREE(h->d_bxy);
     drop_graphs(h);
     h->grid_map = nullptr;
+    h->hint_map = nullptr;
     h->fused_ok = false;
     h->extracted = false;
     h->n = 0;
@@ -166,6 +172,7 @@ extern "C" int icmslam_destroy(icmslam_handle* h)
     DFREE(h->d_st); DFREE(h->d_cub);
     DFREE(h->d_exch); DFREE(h->d_fg_cnt); DFREE(h->d_fg_start); DFREE(h->d_fg_idx);
     DFREE(h->d_fg_pts); DFREE(h->d_fg_geom); DFREE(h->d_bb); DFREE(h->d_ts); DFREE(h->d_seg_rec);
+    DFREE(h->d_lmrec); DFREE(h->d_remap); DFREE(h->d_nnd2);
     if (h->h_st) cudaFreeHost(h->h_st);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -258,6 +265,11 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     if (e == cudaSuccess) e = dalloc(&h->d_bb, 4);
     if (e == cudaSuccess) e = dalloc(&h->d_ts, 1);
     if (e == cudaSuccess) e = dalloc(&h->d_seg_rec, SEG_REC);
+    if (e == cudaSuccess) e = dalloc(&h->d_lmrec, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_remap, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_nnd2, L);
+    if (e == cudaSuccess) e = cudaMemset(h->d_lmrec, 0, L * sizeof(LmRec));
+    { const double t1 = cfg->dist_thr * (1.0 + 9.5367431640625e-07); h->thr1sq = t1 * t1; }
     if (e == cudaSuccess) e = cudaMemset(h->d_ts, 0, sizeof(TailState));
     { const char* eg = getenv("ICMSLAM_GRAPH"); if (eg) h->use_graph = atoi(eg); }
     if (e == cudaSuccess) e = cudaMemset(h->d_fg_cnt, 0, ((size_t)h->fg_cells + 2) * sizeof(int));
@@ -488,6 +500,7 @@ extern "C" int icmslam_set_landmarks_actuales(icmslam_handle* h, int32_t lact)
     k_set_lact<<<1, 1, 0, h->stream>>>(h->d_st, lact);
     CK(cudaGetLastError());
     h->grid_map = nullptr;
+    h->hint_map = nullptr;
     h->lact_host = lact;
     h->lact_dirty = false;
     return ICMSLAM_OK;
@@ -646,6 +659,11 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
     if (h->grid_map != h->d_map_in) {      // the grid of the previous sweep's tail does not index this map: build it
         int rc = build_fgrid(h, min_x, min_y, &st->lsearch, n_search_cap);
         if (rc) return rc;
+        k_lmrec_build<<<nblk(n_search_cap, 256), 256, 0, s>>>(min_x, min_y, &st->lsearch, h->d_fg_geom, h->d_fg_start, h->d_fg_pts, h->d_fg_idx,
+                                                              h->thr1sq, h->thr2_hi, h->d_lmrec);
+        CK(cudaGetLastError());
+        h->n_launch += 1;
+        h->hint_map = nullptr;
     }
     FusedParams P;
     P.T = T; P.t_lo = h->seg_lo; P.t_hi = h->seg_hi; P.first = h->seg_first;
@@ -655,6 +673,8 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
     P.inc = h->d_inc; P.ldinc = T; P.u = h->d_u; P.ldu = T;
     P.cfg = h->dcfg; P.thr2_hi = h->thr2_hi; P.fix_scale = h->fix_scale; P.tol = o.newton_tol; P.maxit = o.newton_maxit;
     P.st = st; P.geom = h->d_fg_geom; P.cell_start = h->d_fg_start; P.gpts = h->d_fg_pts; P.gidx = h->d_fg_idx;
+    P.lmrec = h->d_lmrec; P.remap = h->d_remap;
+    { const char* eh = getenv("ICMSLAM_HINTS"); P.hints = (h->hint_map == h->d_map_in && !(eh && atoi(eh) == 0)) ? 1 : 0; }
     P.c = h->d_c; P.fsum_x = h->d_fsum_x; P.fsum_y = h->d_fsum_y; P.cnt = h->d_cnt;
     P.far_list = h->d_far_list; P.ts = h->d_ts; P.blk_far = h->d_blk_far;
     P.obs_cap = h->obs_cap; P.iters = (o.reserved & 1) ? &st->newton_iters : nullptr;
@@ -710,16 +730,19 @@ static int fused_part_c(icmslam_handle* h, double* dmap_out, int out_cap, int64_
                                               h->d_fg_idx);
     CK(cudaGetLastError());
     k_tail_nn<<<nblk(L, 256), 256, 0, s>>>(st, ts, h->d_kx, h->d_ky, h->d_fg_geom, h->d_fg_start, h->d_fg_pts, h->d_fg_idx, h->thr2_lt,
-                                           h->d_nn, h->d_indflag, L);
+                                           h->d_nn, h->d_indflag, h->d_nnd2, L);
     CK(cudaGetLastError());
-    k_tail_finalize<<<nblk(L, 256), 256, 0, s>>>(st, ts, h->d_kx, h->d_ky, h->d_kc, dmap_out, out_cap, out_ld, h->d_counts, L);
+    k_tail_finalize<<<nblk(L, 256), 256, 0, s>>>(st, ts, h->d_kx, h->d_ky, h->d_kc, dmap_out, out_cap, out_ld, h->d_counts, L, h->d_kflag,
+                                                 h->d_kpos, h->d_nnd2, h->thr1sq, h->thr2_hi, h->d_lmrec, h->d_remap);
     CK(cudaGetLastError());
     k_tail_slow<<<1, 1024, 0, s>>>(st, ts, h->dcfg.dist_thr, h->d_kx, h->d_ky, h->d_kc, h->d_parent, h->d_nn, h->d_indflag, h->d_indpos,
                                    h->d_ind, h->d_lab, h->d_used, h->d_rank, h->d_ox, h->d_oy, h->d_oc, dmap_out, out_cap, out_ld,
-                                   h->d_counts, L, h->fg_cells, h->d_fg_geom, h->d_fg_cnt, h->d_fg_start, h->d_fg_pts, h->d_fg_idx);
+                                   h->d_counts, L, h->fg_cells, h->d_fg_geom, h->d_fg_cnt, h->d_fg_start, h->d_fg_pts, h->d_fg_idx,
+                                   h->d_kflag, h->d_kpos, h->thr1sq, h->thr2_hi, h->d_lmrec, h->d_remap);
     CK(cudaGetLastError());
     h->n_launch += 9;
     h->grid_map = (out_ld == L && out_cap == L) ? dmap_out : nullptr;   // the grid now indexes the new map
+    h->hint_map = h->grid_map;                                          // ... and c[] / d_remap carry this sweep's labels into it
     h->timed_fused = true;
     h->lact_dirty = true;
     return ICMSLAM_OK;
@@ -842,6 +865,7 @@ static int sweep_core(icmslam_handle* h, const double* xin, int64_t ldin, double
     }
     h->timed_fused = false;
     h->grid_map = nullptr;
+    h->hint_map = nullptr;
     // Mapa.filtrar (sensors.py:165-166)
     rc = run_filter(h, raw_x, raw_y, h->d_cnt, nullptr, dmap_out, out_cap, out_ld, nullptr, 1);
     if (rc) return rc;
@@ -885,6 +909,7 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
     if (L_in > 0)
         CK(cudaMemcpy2DAsync(h->d_map_in, (size_t)L * 8, map_in, (size_t)ld_map_in * 8, (size_t)L_in * 8, 2, cudaMemcpyDefault, s));
     h->grid_map = nullptr;
+    h->hint_map = nullptr;
     const bool own_out = (memspace == ICMSLAM_HOST || !map_out);
     int rc = sweep_core(h, xin, ldin, xout, ldout, x0, o, L_in, own_out ? h->d_map_out : map_out, own_out ? L : cap_out,
                         own_out ? (int64_t)L : ld_map_out);
@@ -926,6 +951,7 @@ extern "C" int icmslam_set_map(icmslam_handle* h, const double* map, int32_t L_m
         CK(cudaMemcpy2DAsync(h->d_map_in, (size_t)h->Lcap * 8, map, (size_t)ld * 8, (size_t)L_map * 8, 2, cudaMemcpyDefault, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->grid_map = nullptr;
+    h->hint_map = nullptr;
     return icmslam_set_landmarks_actuales(h, L_map);
 }
 
@@ -1008,12 +1034,14 @@ extern "C" int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const
                 cudaGraph_t graph = nullptr;
                 const int64_t nl0 = h->n_launch;
                 const double* gm = h->grid_map;
+                const double* hm = h->hint_map;
                 CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
                 int rc = cudaMemsetAsync(h->d_counts, 0, (size_t)L * sizeof(double), s) == cudaSuccess ? ICMSLAM_OK : ICMSLAM_ERR_CUDA;
                 if (!rc) rc = sweep_core(h, src, T, dst, T, x0, o, -1, h->d_map_out, L, L);
                 cudaError_t ce = cudaStreamEndCapture(s, &graph);
                 h->n_launch = nl0;
                 h->grid_map = gm;
+                h->hint_map = hm;
                 if (rc || ce != cudaSuccess || !graph) {
                     if (graph) cudaGraphDestroy(graph);
                     cudaGetLastError();
@@ -1029,6 +1057,7 @@ extern "C" int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const
             CK(cudaGraphLaunch(slot->exec, s));
             h->n_launch += 13;                       // kernels of this library inside the graph
             h->grid_map = h->d_map_out;
+            h->hint_map = h->d_map_out;
             h->timed_fused = true;
             h->lact_dirty = true;
             launched = true;

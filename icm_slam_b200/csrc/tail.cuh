@@ -33,8 +33,27 @@ struct TailState {
     int degenerate;     // bounding box smaller than dist_thr: the reference's zero-distance rule matters
     int far_total;      // scans with far observations in THIS handle's segment
     int label_base;     // such scans in the segments before this one (0 on a single GPU)
-    int pad[3];
+    int remap_identity; // the filter kept every landmark of the previous map in place and nothing was added
+    int pad[2];
 };
+
+// A landmark as the fused kernel reads it by label: position and the squared radius inside which an
+// observation is PROVABLY nearest to it and inside the gate (see hint_radius2).
+struct __align__(32) LmRec {
+    double x, y, r2, pad;
+};
+
+// r2 = min(thr2_hi, (nnd/2)^2 (1 - 2^-30)) with nnd a lower bound of the distance to the nearest other
+// landmark: an observation with |obs - A|^2 <= r2 has |obs - B| >= nnd - |obs - A| > |obs - A| for every other
+// landmark B with a relative margin of 2^-31, far above the rounding of the distance computation, so
+// argmin(cdist) == A with no tie, and sqrt_rn(|obs - A|^2) <= dist_thr.  nnd2_seen is the squared distance to
+// the nearest other landmark found in the landmark's own grid cell list, which contains every landmark within
+// thr1 of it: if none was found, nnd > thr1.
+__device__ __forceinline__ double hint_radius2(double nnd2_seen, double thr1sq, double thr2_hi)
+{
+    const double q = 0.25 * fmin(nnd2_seen, thr1sq) * (1.0 - 9.3132257461547852e-10);
+    return fmin(q, thr2_hi);
+}
 
 // What neighbouring time segments tell each other after a sweep (16 doubles per rank, all-gathered):
 // [0..2] first owned pose, [3..5] second-to-last owned pose, [6..8] last owned pose, [9] far_total.
@@ -139,12 +158,12 @@ __global__ void k_tail_geom(const unsigned long long* bb, const DevState* st, Ta
 __global__ void __launch_bounds__(256)
 k_tail_nn(const DevState* st, TailState* ts, const double* __restrict__ kx, const double* __restrict__ ky, const FGeom* __restrict__ geom,
           const int* __restrict__ cell_start, const double2* __restrict__ pts, const int* __restrict__ idx, double thr2_lt,
-          int* __restrict__ nn, int* __restrict__ ind_flag, int Lcap)
+          int* __restrict__ nn, int* __restrict__ ind_flag, double* __restrict__ nnd2, int Lcap)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= Lcap) return;
     const int K = st->kept;
-    if (j >= K || ts->degenerate) { ind_flag[j] = 0; return; }
+    if (j >= K || ts->degenerate) { ind_flag[j] = 0; nnd2[j] = 0.0; return; }
     const FGeom g = *geom;
     const double xj = kx[j], yj = ky[j];
     const int c = fgrid_cell(g, xj, yj);
@@ -166,25 +185,55 @@ k_tail_nn(const DevState* st, TailState* ts, const double* __restrict__ kx, cons
     const int f = (arg >= 0 && best <= thr2_lt) ? 1 : 0;      // amin < dist_thr (strict, :245)
     nn[j] = arg < 0 ? 0 : arg;
     ind_flag[j] = f;
+    nnd2[j] = best;
     if (f) atomicAdd(&ts->n_ind, 1);
 }
 
 // nothing to merge: the survivors, in order, are the new map (count-weighted mean of one member, :258-260)
 __global__ void __launch_bounds__(256)
-k_tail_finalize(DevState* st, const TailState* ts, const double* __restrict__ kx, const double* __restrict__ ky, const double* __restrict__ kc,
-                double* __restrict__ map_out, int cap_out, int64_t ld_out, double* __restrict__ counts_state, int Lcap)
+k_tail_finalize(DevState* st, TailState* ts, const double* __restrict__ kx, const double* __restrict__ ky, const double* __restrict__ kc,
+                double* __restrict__ map_out, int cap_out, int64_t ld_out, double* __restrict__ counts_state, int Lcap,
+                const int* __restrict__ kflag, const int* __restrict__ kpos, const double* __restrict__ nnd2, double thr1sq, double thr2_hi,
+                LmRec* __restrict__ lmrec, int* __restrict__ remap)
 {
     if (ts->n_ind != 0 || ts->degenerate) return;   // k_tail_slow takes over
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= Lcap) return;
     const int newL = st->kept;
     const double c = r < newL ? kc[r] : 0.0;
-    if (r < cap_out) {
-        map_out[r] = r < newL ? mul_rn(kx[r], c) / c : 0.0;
-        map_out[ld_out + r] = r < newL ? mul_rn(ky[r], c) / c : 0.0;
-    }
+    const double mx = r < newL ? mul_rn(kx[r], c) / c : 0.0, my = r < newL ? mul_rn(ky[r], c) / c : 0.0;
+    if (r < cap_out) { map_out[r] = mx; map_out[ld_out + r] = my; }
     counts_state[r] = c;
-    if (r == 0) { st->new_l = newL; st->lact = newL; st->n_ind = 0; }
+    LmRec rec;
+    rec.x = mx; rec.y = my; rec.r2 = r < newL ? hint_radius2(nnd2[r], thr1sq, thr2_hi) : 0.0; rec.pad = 0.0;
+    lmrec[r] = rec;
+    remap[r] = (r < st->raw_l && kflag[r]) ? kpos[r] : -1;      // label of this sweep -> index in the new map
+    if (r == 0) {
+        st->new_l = newL; st->lact = newL; st->n_ind = 0;
+        ts->remap_identity = (newL == st->lsearch && st->raw_l == st->lsearch) ? 1 : 0;
+    }
+}
+
+// landmark records of a map whose grid has just been built (first sweep on a caller-supplied map)
+__global__ void __launch_bounds__(256)
+k_lmrec_build(const double* __restrict__ mx, const double* __restrict__ my, const int* __restrict__ n_ptr, const FGeom* __restrict__ geom,
+              const int* __restrict__ cell_start, const double2* __restrict__ pts, const int* __restrict__ idx, double thr1sq, double thr2_hi,
+              LmRec* __restrict__ lmrec)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= *n_ptr) return;
+    const FGeom g = *geom;
+    const double xj = mx[j], yj = my[j];
+    const int c = fgrid_cell(g, xj, yj);
+    double best = INFINITY;
+    for (int k = cell_start[c]; k < cell_start[c + 1]; ++k) {
+        if (idx[k] == j) continue;
+        const double2 p = pts[k];
+        best = fmin(best, dist2_rn(p.x - xj, p.y - yj));      // (a coincident landmark gives 0: its hints are never trusted)
+    }
+    LmRec rec;
+    rec.x = xj; rec.y = yj; rec.r2 = hint_radius2(best, thr1sq, thr2_hi); rec.pad = 0.0;
+    lmrec[j] = rec;
 }
 
 // ---- the merge path: one block ------------------------------------------------------------------------
@@ -221,7 +270,8 @@ k_tail_slow(DevState* st, TailState* ts, double dist_thr, double* kx, double* ky
             int* ind_pos, int* ind, int* lab, int* used, int* rank, double* ox, double* oy, double* oc, double* map_out, int cap_out,
             int64_t ld_out, double* counts_state, int Lcap,
             // grid rebuild over the merged map
-            int max_cells, FGeom* geom, int* cell_cnt, int* cell_start, double2* pts, int* gidx)
+            int max_cells, FGeom* geom, int* cell_cnt, int* cell_start, double2* pts, int* gidx,
+            const int* kflag, const int* kpos, double thr1sq, double thr2_hi, LmRec* lmrec, int* remap)
 {
     if (ts->n_ind == 0 && !ts->degenerate) return;
     __shared__ int wsum[34];
@@ -290,7 +340,8 @@ k_tail_slow(DevState* st, TailState* ts, double dist_thr, double* kx, double* ky
         }
         counts_state[r] = c;
     }
-    if (tid == 0) { st->new_l = newL; st->lact = newL; st->n_ind = n_ind; }
+    for (int l = tid; l < Lcap; l += nth) remap[l] = (l < st->raw_l && kflag[l]) ? rank[lab[kpos[l]]] : -1;
+    if (tid == 0) { st->new_l = newL; st->lact = newL; st->n_ind = n_ind; ts->remap_identity = 0; }
     __syncthreads();
     // ---- rebuild the landmark grid over the merged map (it is the next sweep's association grid) -------------
     {
@@ -336,6 +387,22 @@ k_tail_slow(DevState* st, TailState* ts, double dist_thr, double* kx, double* ky
                     pts[p] = make_double2(x, y);
                     gidx[p] = r;
                 }
+        }
+        __syncthreads();
+        for (int r = tid; r < Lcap; r += nth) {       // landmark records of the merged map
+            LmRec rec;
+            rec.x = 0.0; rec.y = 0.0; rec.r2 = 0.0; rec.pad = 0.0;
+            if (r < newL) {
+                const double x = map_out[r], y = map_out[ld_out + r];
+                const int c = fgrid_cell(g, x, y);
+                double best = INFINITY;
+                for (int k = cell_start[c]; k < cell_start[c + 1]; ++k) {
+                    if (gidx[k] == r) continue;
+                    best = fmin(best, dist2_rn(pts[k].x - x, pts[k].y - y));
+                }
+                rec.x = x; rec.y = y; rec.r2 = hint_radius2(best, thr1sq, thr2_hi);
+            }
+            lmrec[r] = rec;
         }
     }
 }

@@ -220,6 +220,8 @@ def bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, p
     import torch
     import torch.distributed as dist
 
+    import os
+    os.environ.setdefault("NCCL_DEBUG", "WARN")      # (NCCL's version banner goes to stdout: rank 0 must print ONE JSON line)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     name = args.workload
     L_true, T, desc = WORKLOADS[name]

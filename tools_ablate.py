@@ -19,6 +19,9 @@ for m in masks:
     ts = []
     for k in range(5):
         eng.set_map(d["map_init"]); eng.set_poses(d["x_init"])     # same inputs for every sample
+        os.environ["ICMSLAM_SKIP"] = "0"
+        eng.iterate(None, x0, 1)                                   # (establishes the grid, the hints and the labels)
+        os.environ["ICMSLAM_SKIP"] = str(m)
         eng.iterate(None, x0, 1, timing=True)
         ts.append(eng.kernel_ms()[0])
     print("skip=%2d  fused kernel %.3f ms (min %.3f)" % (m, float(np.median(ts[1:])), min(ts)), flush=True)
