@@ -339,9 +339,9 @@ k_sweep_fused(const FusedParams p)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FusedSmemFixed<HALF>& S = *reinterpret_cast<FusedSmemFixed<HALF>*>(smem_raw);
     double2* sb = reinterpret_cast<double2*>(smem_raw + sizeof(FusedSmemFixed<HALF>));   // staged observations; later run sums
-    int* sbk = reinterpret_cast<int*>(sb + p.obs_cap);                              // label of each observation (-1 far)
-    unsigned short* srn = reinterpret_cast<unsigned short*>(sbk + p.obs_cap);       // run length at run heads (phase A: cell entry count)
-    unsigned char* slt = reinterpret_cast<unsigned char*>(srn + p.obs_cap);         // scan (local pose index) of each observation
+    int* sbk_raw = reinterpret_cast<int*>(sb + p.obs_cap);                          // hints in (TMA), labels out; +4 ints of alignment slack
+    unsigned short* srn = reinterpret_cast<unsigned short*>(sbk_raw + p.obs_cap + 4);   // run length at run heads (phase A: cell entry count)
+    unsigned char* slt = reinterpret_cast<unsigned char*>(srn + p.obs_cap);             // scan (local pose index) of each observation
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tb = p.t_lo + blockIdx.x * FS_OWN;      // t_lo is even: colours stay aligned with the global time index
@@ -415,43 +415,47 @@ k_sweep_fused(const FusedParams p)
             c_hi = lo;
         }
         const int co = S.off[c_lo], ce = S.off[c_hi + 1];
+        const bool use_hints = p.hints != 0 && have_map && !(p.skip & 32);
+        const int co4 = co & ~3;                         // 16-byte aligned start of the labels' slice
+        int* sbk = sbk_raw + (co - co4);                 // label of each observation (-1 far), same slot as its hint
         if (tid == 0) {
             const uint32_t bytes = (p.skip & 128) ? 0u : (uint32_t)(ce - co) * 16u;
-            if (bytes > 0) {
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(smem_u32(sb)), "l"(p.bxy + co), "r"(bytes), "r"(mb) : "memory");
+            const uint32_t hbytes = (use_hints && ce > co) ? (uint32_t)((ce - co4 + 3) & ~3) * 4u : 0u;
+            if (bytes + hbytes > 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes + hbytes) : "memory");
+                if (bytes) asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                        ::"r"(smem_u32(sb)), "l"(p.bxy + co), "r"(bytes), "r"(mb) : "memory");
+                // last sweep's labels of the same observations (the hints) land in the label array itself
+                if (hbytes) asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                         ::"r"(smem_u32(sbk_raw)), "l"(p.c + co4), "r"(hbytes), "r"(mb) : "memory");
             } else {
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb) : "memory");
             }
         }
-        // the slot's half of its scan's observations (indices relative to the chunk)
+        // the slot's scan and this thread's half of it (indices relative to the chunk)
         const bool mine = qvalid && qli >= c_lo && qli <= c_hi;
-        int o = 0, e = 0;
+        int o = 0, e = 0, so = 0, se = 0;
         if (mine) {
-            const int so = S.off[qli] - co, se = S.off[qli + 1] - co, h1 = (se - so + 1) >> 1;
+            so = S.off[qli] - co; se = S.off[qli + 1] - co;
+            const int h1 = (se - so + 1) >> 1;
             o = half ? so + h1 : so;
             e = half ? se : so + h1;
         }
-        for (int i = o; i < e; ++i) slt[i] = (unsigned char)qli;     // (while the bulk copy is in flight)
+        for (int i = o; i < e; ++i) slt[i] = (unsigned char)qli;     // (while the bulk copies are in flight)
         mbar_wait(mb, parity);
         parity ^= 1u;
         __syncthreads();
-        // ---- phase A: lanes over consecutive observations, four per lane in flight -----------------------
-        // pass A1: project, locate the grid cell, fetch its entry range   (one level of gathers)
-        // pass A2: fetch the candidates, pick the nearest, gate, label    (second level of gathers)
-        // Splitting the two dependent gather levels into separate sweeps over the warp's slice keeps 4
-        // (A1: 8) independent loads per lane in flight instead of one dependent chain per observation.
+        // ---- phase A: lanes over consecutive observations (adjacent lanes = adjacent beams), four per lane in flight --
+        //   A0 (hints): last sweep's label of the same observation, carried through the filter's renumbering, is
+        //       accepted when the observation lies inside the landmark's proven-nearest radius (tail.cuh hint_radius2):
+        //       one staged value and one gather instead of the grid search.  Lanes it cannot settle stay pending for
+        //   A1: project, locate the grid cell, fetch its entry range     (first level of gathers)
+        //   A2: fetch the candidates, pick the nearest, gate, label      (second level of gathers)
         {
             const int m = ce - co;
             const int per = (((m + FS_WARPS - 1) / FS_WARPS) + 127) & ~127;
             const int wa = warp * per, wb = min(wa + per, m);
-            // pass A0 (hints): last sweep's label of the same observation, carried through the filter's renumbering,
-            // is accepted when the observation lies inside the landmark's proven-nearest radius (tail.cuh
-            // hint_radius2): one coalesced load and one gather instead of the grid search.  Lanes it cannot settle
-            // stay pending for A1/A2.
             unsigned long long pend = 0ull;
-            const bool use_hints = p.hints != 0 && have_map && !(p.skip & 32);
             const bool ident = p.ts->remap_identity != 0;
             const int lsearch = p.st->lsearch;
             int slot = 0;
@@ -463,7 +467,7 @@ k_sweep_fused(const FusedParams p)
                     const int i = base + u * 32 + lane;
                     h_[u] = -1; wx_[u] = 0.0; wy_[u] = 0.0;
                     if (i < wb && use_hints) {
-                        h_[u] = p.c[co + i];
+                        h_[u] = sbk[i];
                         if (h_[u] >= p.cfg.L) h_[u] = -1;          // (labels of scans this handle does not own are not maintained)
                         const double2 bq = sb[i];
                         const int lt = slt[i];
@@ -557,7 +561,7 @@ k_sweep_fused(const FusedParams p)
                 }
             }
         }
-        __syncthreads();     // sbk of the whole chunk visible
+        __syncthreads();     // the labels of the whole chunk are visible to the pose threads
         // ---- phase B, pass 1 (thread pair per pose): runs of equal winners -> in-place run records --------
         if (!(p.skip & 2)) {
             int run_start = o, cur = o < e ? sbk[o] : -1;
@@ -615,6 +619,7 @@ k_sweep_fused(const FusedParams p)
         if (c_lo <= lt_last) __syncthreads();   // the next chunk overwrites the staging buffers
     }
     // ---- combine the pair's partial sums (both lanes end up with the scan's totals) ----------------------------
+    int far_idx = -1;
     {
 #define FS_PAIR(v) v += __shfl_xor_sync(FULLMASK, v, 1)
         FS_PAIR(M.n); FS_PAIR(M.Bx); FS_PAIR(M.By); FS_PAIR(M.Bxx); FS_PAIR(M.Byy); FS_PAIR(M.Bxy);
@@ -622,7 +627,15 @@ k_sweep_fused(const FusedParams p)
         FS_PAIR(fsx); FS_PAIR(fsy); FS_PAIR(FBx); FS_PAIR(FBy);
         nfar += __shfl_xor_sync(FULLMASK, nfar, 1);
 #undef FS_PAIR
-        if (half == 0 && qowned && nfar > 0) atomicOr(&S.farbits[(qt - tb) >> 5], 1u << ((qt - tb) & 31));
+        if (half == 0 && qowned && nfar > 0) {
+            // a scan with far observations creates one label (ICM_SLAM.py:174-182): its record now, its rank in time
+            // order within the tile once every slot has reported (after the solve; only the record's index is kept)
+            atomicOr(&S.farbits[(qt - tb) >> 5], 1u << ((qt - tb) & 31));
+            FarRec r;
+            r.t = qt; r.rank = 0; r.n = nfar; r.pad = 0; r.sx = fsx; r.sy = fsy;
+            far_idx = atomicAdd(&p.ts->far_count, 1);
+            p.far_list[far_idx] = r;
+        }
         if (nfar > 0) {   // far observations see the mean of the scan's new label (PREV view, raw = sum / k)
             const double px = S.pp[qli].x, py = S.pp[qli].y;
             const double yx = fsx / (double)nfar - px, yy = fsy / (double)nfar - py;
@@ -631,18 +644,6 @@ k_sweep_fused(const FusedParams p)
             M.Myx = fma(yy, FBx, M.Myx); M.Myy = fma(yy, FBy, M.Myy);
         }
     }
-    __syncthreads();
-    // scans with far observations: one record each, ranked in time order within the tile (the label is
-    // lact0 + scans with far observations before it, ICM_SLAM.py:174-182)
-    if (half == 0 && qowned && nfar > 0) {
-        const int bit = qt - tb, w = bit >> 5;
-        int rank = __popc(S.farbits[w] & ((1u << (bit & 31)) - 1u));
-        for (int k = 0; k < w; ++k) rank += __popc(S.farbits[k]);
-        FarRec r;
-        r.t = qt; r.rank = rank; r.n = nfar; r.pad = 0; r.sx = fsx; r.sy = fsy;
-        p.far_list[atomicAdd(&p.ts->far_count, 1)] = r;
-    }
-    if (tid == 0) p.blk_far[blockIdx.x] = __popc(S.farbits[0]) + __popc(S.farbits[1]) + __popc(S.farbits[2]) + __popc(S.farbits[3]);
     // ---- pose solve by the lane pairs: warps 0-3 red (odd poses), then warps 4-7 black (even poses) --------------
     {
         const int grp = q / FS_HALF;
@@ -705,6 +706,13 @@ k_sweep_fused(const FusedParams p)
             if (lane == 0 && my_iters) atomicAdd(p.iters, my_iters);
         }
     }
+    if (far_idx >= 0) {
+        const int bit = qt - tb, w = bit >> 5;
+        int rank = __popc(S.farbits[w] & ((1u << (bit & 31)) - 1u));
+        for (int k = 0; k < w; ++k) rank += __popc(S.farbits[k]);
+        p.far_list[far_idx].rank = rank;
+    }
+    if (tid == 0) p.blk_far[blockIdx.x] = __popc(S.farbits[0]) + __popc(S.farbits[1]) + __popc(S.farbits[2]) + __popc(S.farbits[3]);
     // ---- outputs ----------------------------------------------------------------------------------
     const int n_own = min(FS_OWN, p.t_hi - tb);
     for (int r = 0; r < 3; ++r)
@@ -728,7 +736,7 @@ __global__ void k_interleave(const double* __restrict__ bx, const double* __rest
 
 static size_t fused_smem_bytes(int half, int obs_cap)   // obs_cap is even
 {
-    return (half == 32 ? sizeof(FusedSmemFixed<32>) : sizeof(FusedSmemFixed<64>)) + (size_t)obs_cap * 23 + 32;
+    return (half == 32 ? sizeof(FusedSmemFixed<32>) : sizeof(FusedSmemFixed<64>)) + (size_t)obs_cap * 23 + 64;
 }
 #undef FS_THREADS
 #undef FS_WARPS

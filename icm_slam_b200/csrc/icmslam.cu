@@ -413,7 +413,7 @@ extern "C" int icmslam_extract(icmslam_handle* h)
     CK(dalloc(&h->d_beam, n)); CK(dalloc(&h->d_scan_of, n)); CK(dalloc(&h->d_d, n)); CK(dalloc(&h->d_bx, n + 2)); CK(dalloc(&h->d_by, n + 2));
     CK(cudaMemsetAsync(h->d_bx, 0, (n + 2) * sizeof(double), h->stream));
     CK(cudaMemsetAsync(h->d_by, 0, (n + 2) * sizeof(double), h->stream));
-    CK(dalloc(&h->d_c, n));
+    CK(dalloc(&h->d_c, n + 8));      // (+ slack: the fused kernel stages 16-byte aligned slices of it)
     k_extract<2><<<blocks, EX_THREADS, smem, h->stream>>>(h->d_scans, B, T, T, h->d_cos, h->d_sin, h->dcfg, h->precondition,
                                                           nwords, d_masks, nullptr, h->d_off, h->d_beam, h->d_d, h->d_bx,
                                                           h->d_by, h->d_scan_of);
@@ -438,10 +438,10 @@ extern "C" int icmslam_extract(icmslam_handle* h)
         const char* envb = getenv("ICMSLAM_BLOCKS_PER_SM");
         if (envb && atoi(envb) > 0) blocks_per_sm = atoi(envb);
         const size_t per_block = (size_t)233472 / blocks_per_sm - 1024 - 512;   // 228 KB per SM, 1 KB reserved per block
-        int cap = (int)((per_block - fixed - 32) / 23);
+        int cap = (int)((per_block - fixed - 64) / 23);
         const char* env = getenv("ICMSLAM_OBS_CAP");
         if (env && atoi(env) > 0) cap = atoi(env);
-        const int cap_max = (int)((232448 - fixed - 32) / 23);
+        const int cap_max = (int)((232448 - fixed - 64) / 23);
         if (cap > cap_max) cap = cap_max;
         if (cap > mx) cap = mx;                                    // the whole tile fits: one chunk
         if (cap < h->max_per_scan) cap = h->max_per_scan;          // a chunk holds at least one whole scan
