@@ -117,6 +117,11 @@ class SegmentedSolver:
         self.config, self.rank, self.world, self.device, self.group = config, int(rank), int(world), int(device), group
         self.engine = Engine(config, device=device)
         self._views = None
+        self._graphs = {}
+        self._steady = 0
+        self._parity = 0
+        self._launches = 0
+        self._launches_per_sweep = 0
 
     # -- data -------------------------------------------------------------------------------------------------
     def load(self, scans, odometry, controls, precondition=True, weights=None):
@@ -136,12 +141,22 @@ class SegmentedSolver:
         check(e.lib.icmslam_set_segment(e._h, self.t_lo, self.t_hi, int(self.rank == 0), int(self.rank == self.world - 1)), e._h)
         self.x0 = np.ascontiguousarray(np.asarray(odometry[:, 0], dtype=np.float64).reshape(3))
         self._views = None
+        self._graphs = {}
+        self._steady = 0
+        self._parity = 0
+        self._launches = 0
+        self._launches_per_sweep = 0
         return n
 
     def set_map(self, mapa):
         self.engine.set_map(mapa)
+        self._steady = 0          # the next sweeps rebuild the grid eagerly ...
+        self._graphs = {}         # ... and a captured graph bakes in which of the ping-pong buffers is current
+        self._parity = 0
 
     def set_poses(self, x_full):
+        self._graphs = {}
+        self._parity = 0
         self.engine.set_poses(np.asarray(x_full)[:, self.c_lo:self.c_hi])      # (a strided view: copied by the library)
 
     # -- views of the library's exchange buffers ------------------------------------------------------------------
@@ -158,26 +173,73 @@ class SegmentedSolver:
         self._views = dict(rec=mk(PTR_SEG_REC, "<f8"), sx=mk(PTR_STAT_X, "<i8"), sy=mk(PTR_STAT_Y, "<i8"), sn=mk(PTR_STAT_N, "<i4"),
                            new=mk(PTR_NEW_LABELS, "<f8"), all=mk(PTR_EXCHANGE, "<i8"))
 
-    # -- one sweep ------------------------------------------------------------------------------------------------
-    def sweep(self, n_sweeps: int = 1):
+    # -- sweeps ---------------------------------------------------------------------------------------------------
+    def _sweep_once(self, opts=None):
         from . import _lib
         from ._lib import check
         e = self.engine
+        v = self._views
+        if opts is None:
+            opts = _lib.SweepOpts(_lib.SCHED["redblack"], _lib.SOLVER["newton"], _lib.VIEW["prev"], 0, 0.0, 1, 0)
+        check(e.lib.icmslam_seg_begin(e._h, C.c_void_p(self.x0.ctypes.data), C.byref(opts)), e._h)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self._allrec, v["rec"].reshape(1, SEG_REC), group=self.group)
+            check(e.lib.icmslam_seg_exchange(e._h, C.c_void_p(self._allrec.data_ptr()), self.rank, self.world), e._h)
+            dist.all_reduce(v["all"], group=self.group)      # the four statistics buffers as one block of int64 words
+        else:
+            check(e.lib.icmslam_seg_exchange(e._h, C.c_void_p(v["rec"].data_ptr()), 0, 1), e._h)
+        check(e.lib.icmslam_seg_finish(e._h), e._h)
+
+    def _prepare(self):
+        import torch
         if self._views is None:
             self._bind()
-        v = self._views
-        opts = _lib.SweepOpts(_lib.SCHED["redblack"], _lib.SOLVER["newton"], _lib.VIEW["prev"], 0, 0.0, 1, 0)
-        x0p = C.c_void_p(self.x0.ctypes.data)
-        for _ in range(n_sweeps):
-            check(e.lib.icmslam_seg_begin(e._h, x0p, C.byref(opts)), e._h)
-            if self.world > 1:
-                allrec = gather_records(v["rec"], self.group)
-                check(e.lib.icmslam_seg_exchange(e._h, C.c_void_p(allrec.data_ptr()), self.rank, self.world), e._h)
-                reduce_statistics([v["all"]], self.group)      # the four statistics buffers as one block of int64 words
-                self._keep = allrec      # (kept alive until the next sweep's kernels have consumed it)
+        if getattr(self, "_allrec", None) is None:
+            self._allrec = torch.empty((self.world, SEG_REC), dtype=torch.float64, device="cuda:%d" % self.device)
+
+    def sweep(self, n_sweeps: int = 1, use_graph: bool = True):
+        """n_sweeps sweeps of the whole trajectory (collective: every rank calls it).  In steady state two consecutive
+        sweeps -- kernels of this library AND the NCCL collectives between them -- replay as one CUDA graph (two, because
+        the pose and map buffers ping-pong)."""
+        import torch
+        self._prepare()
+        done = 0
+        while done < n_sweeps:
+            left = n_sweeps - done
+            if use_graph and left >= 2 and self._steady >= 2:
+                g = self._graphs.get(self._parity)
+                if g is None:            # one graph per ping-pong parity of the pose / map buffers
+                    cur = torch.cuda.current_stream()
+                    cur.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    side = torch.cuda.Stream(device=self.device)
+                    self.engine.set_stream(side.cuda_stream)       # (before the capture starts: set_stream synchronises)
+                    with torch.cuda.graph(g, stream=side):
+                        self._sweep_once()
+                        self._sweep_once()
+                    self.engine.set_stream(cur.cuda_stream)
+                    self._graphs[self._parity] = g                 # (capture records the work without running it)
+                g.replay()
+                self._launches += 2 * self._launches_per_sweep
+                done += 2
+                self._steady += 2
             else:
-                check(e.lib.icmslam_seg_exchange(e._h, C.c_void_p(v["rec"].data_ptr()), 0, 1), e._h)
-            check(e.lib.icmslam_seg_finish(e._h), e._h)
+                n0 = self.engine.launch_count()
+                self._sweep_once()
+                self._launches_per_sweep = self.engine.launch_count() - n0
+                self._launches += self._launches_per_sweep
+                self._steady += 1
+                self._parity ^= 1
+                done += 1
+
+    @property
+    def _graph(self):
+        return next(iter(self._graphs.values()), None)
+
+    def launch_count(self):
+        """Kernels of the library enqueued by sweep() (replayed graphs included)."""
+        return self._launches
 
     # -- results --------------------------------------------------------------------------------------------------
     def owned_poses(self, out_full=None):
@@ -242,7 +304,7 @@ def bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, p
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
-    lc0 = sol.engine.launch_count()
+    lc0 = sol.launch_count()
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -256,19 +318,13 @@ def bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, p
     dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)           # device time, max over ranks
     ms = float(ms_t.item())
     clocks = sampler.stop()
-    launches = (sol.engine.launch_count() - lc0) // max(args.steps, 1)
+    launches = (sol.launch_count() - lc0) // max(args.steps, 1)
     # fused kernel time on this rank (separate short loop: reading the events synchronises)
     kt = []
     from . import _lib
     for _ in range(5):
-        opts = _lib.SweepOpts(_lib.SCHED["redblack"], _lib.SOLVER["newton"], _lib.VIEW["prev"], 0, 0.0, 1, 2)
-        e = sol.engine
-        _lib.check(e.lib.icmslam_seg_begin(e._h, C.c_void_p(sol.x0.ctypes.data), C.byref(opts)), e._h)
-        allrec = gather_records(sol._views["rec"])
-        _lib.check(e.lib.icmslam_seg_exchange(e._h, C.c_void_p(allrec.data_ptr()), rank, world), e._h)
-        reduce_statistics([sol._views["all"]])
-        _lib.check(e.lib.icmslam_seg_finish(e._h), e._h)
-        kt.append(e.kernel_ms()[0])
+        sol._sweep_once(_lib.SweepOpts(_lib.SCHED["redblack"], _lib.SOLVER["newton"], _lib.VIEW["prev"], 0, 0.0, 1, 2))
+        kt.append(sol.engine.kernel_ms()[0])
     k_ms = torch.tensor([float(np.mean(kt))], dtype=torch.float64, device=dev)
     dist.all_reduce(k_ms, op=dist.ReduceOp.MAX)
     # end to end: host buffers in, host buffers out, every step

@@ -482,3 +482,29 @@ def test_segments_with_new_labels_and_merges():
     d["map_init"] = m
     cfgd = dict(cfgd, L=4096)
     _segmented_vs_single(d, cfgd, 4, 3)
+
+
+def test_segmented_solver_single_rank_graph_replay():
+    """SegmentedSolver with world = 1 (no collectives): eager sweeps, then CUDA-graph replays of sweep pairs,
+    equal bit for bit to the plain engine."""
+    import torch
+    from icm_slam_b200.multigpu import SegmentedSolver
+    d, cfgd = _synthetic_case(625, 4000, 20181 + 15)
+    z, odo, u = d["observations"], d["odometry"], d["velocities"]
+    cfg = _cfg(**cfgd)
+    single = _engine(cfg, z, odo, u)
+    single.set_map(d["map_init"]); single.set_poses(d["x_init"])
+    single.iterate(None, odo[:, 0], 9)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        sol = SegmentedSolver(cfg, 0, 1, device=0)
+        sol.engine.set_stream(stream.cuda_stream)
+        sol.load(z, odo, u, precondition=True)
+        sol.set_map(d["map_init"]); sol.set_poses(d["x_init"])
+        sol.sweep(7)          # 2 eager + capture + 2 replays + 1 eager
+        sol.sweep(2)          # 1 replay
+        stream.synchronize()
+        assert sol._graph is not None
+        assert np.array_equal(sol.owned_poses(), single.get_poses())
+        assert np.array_equal(sol.get_map(), single.get_map())
+    sol.close(); single.close()
