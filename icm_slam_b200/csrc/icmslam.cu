@@ -16,6 +16,7 @@
 #include "mapfilter.cuh"
 #include "fastgrid.cuh"
 #include "fused.cuh"
+#include "tail_coop.cuh"
 
 #define MAX_CELLS (1 << 22)
 
@@ -76,6 +77,8 @@ struct icmslam_handle {
     struct GraphSlot { cudaGraphExec_t exec = nullptr; const double* src = nullptr; const double* map_in = nullptr; double x0[3] = {0, 0, 0}; double tol = 0; int maxit = 0; };
     GraphSlot graphs[4];
     int use_graph = 1;
+    int coop_tail = 0, coop_blocks = 0;   // the tail as one cooperative launch (tail_coop.cuh)
+    int* d_blk_scratch = nullptr;
     double2* d_bxy = nullptr;    // interleaved (bx, by) records for the TMA staging
     long long *d_fsum_x = nullptr, *d_fsum_y = nullptr;
     int fg_cells = 0;            // cell budget of the fast grid (host constant)
@@ -172,7 +175,7 @@ extern "C" int icmslam_destroy(icmslam_handle* h)
     DFREE(h->d_st); DFREE(h->d_cub);
     DFREE(h->d_exch); DFREE(h->d_fg_cnt); DFREE(h->d_fg_start); DFREE(h->d_fg_idx);
     DFREE(h->d_fg_pts); DFREE(h->d_fg_geom); DFREE(h->d_bb); DFREE(h->d_ts); DFREE(h->d_seg_rec);
-    DFREE(h->d_lmrec); DFREE(h->d_remap); DFREE(h->d_nnd2);
+    DFREE(h->d_lmrec); DFREE(h->d_remap); DFREE(h->d_nnd2); DFREE(h->d_blk_scratch);
     if (h->h_st) cudaFreeHost(h->h_st);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -272,6 +275,17 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     { const double t1 = cfg->dist_thr * (1.0 + 9.5367431640625e-07); h->thr1sq = t1 * t1; }
     if (e == cudaSuccess) e = cudaMemset(h->d_ts, 0, sizeof(TailState));
     { const char* eg = getenv("ICMSLAM_GRAPH"); if (eg) h->use_graph = atoi(eg); }
+    if (e == cudaSuccess) {
+        int coop = 0, sms = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tail_coop, TC_THREADS, 0);
+        const char* ec = getenv("ICMSLAM_COOP_TAIL");
+        h->coop_blocks = sms;
+        // measured on B200 (profiles/README.md): same time as the kernel chain, so the chain stays the default
+        h->coop_tail = (coop && per_sm >= 1 && sms > 0 && ec && atoi(ec) == 1) ? 1 : 0;
+        e = dalloc(&h->d_blk_scratch, (size_t)2 * (sms > 0 ? sms : 1) + 8);
+    }
     if (e == cudaSuccess) e = cudaMemset(h->d_fg_cnt, 0, ((size_t)h->fg_cells + 2) * sizeof(int));
     {   // gate and fixed-point scale of the fused path
         const double thr = cfg->dist_thr;
@@ -712,6 +726,25 @@ static int fused_part_c(icmslam_handle* h, double* dmap_out, int out_cap, int64_
     const double* min_y = h->d_map_in + L;
     double* raw_x = h->d_raw;
     double* raw_y = h->d_raw + L;
+    if (h->coop_tail) {
+        TailCoopParams P;
+        P.st = st; P.ts = ts; P.fsum_x = h->d_fsum_x; P.fsum_y = h->d_fsum_y; P.cnt = h->d_cnt; P.map_x = min_x; P.map_y = min_y;
+        P.inv_scale = 1.0 / h->fix_scale; P.cota = h->dcfg.cota; P.dist_thr = h->dcfg.dist_thr; P.thr2_lt = h->thr2_lt; P.thr1sq = h->thr1sq;
+        P.thr2_hi = h->thr2_hi; P.newraw = h->d_newraw; P.raw_x = raw_x; P.raw_y = raw_y; P.kflag = h->d_kflag; P.kpos = h->d_kpos;
+        P.kx = h->d_kx; P.ky = h->d_ky; P.kc = h->d_kc; P.parent = h->d_parent; P.bb = h->d_bb; P.max_cells = h->fg_cells;
+        P.geom = h->d_fg_geom; P.cell_cnt = h->d_fg_cnt; P.cell_start = h->d_fg_start; P.pts = h->d_fg_pts; P.gidx = h->d_fg_idx;
+        P.nn = h->d_nn; P.ind_flag = h->d_indflag; P.nnd2 = h->d_nnd2; P.map_out = dmap_out; P.cap_out = out_cap; P.ld_out = out_ld;
+        P.counts_state = h->d_counts; P.lmrec = h->d_lmrec; P.remap = h->d_remap; P.ind_pos = h->d_indpos; P.ind = h->d_ind; P.lab = h->d_lab;
+        P.used = h->d_used; P.rank = h->d_rank; P.ox = h->d_ox; P.oy = h->d_oy; P.oc = h->d_oc; P.blk_scratch = h->d_blk_scratch; P.Lcap = L;
+        void* args[] = {(void*)&P};
+        CK(cudaLaunchCooperativeKernel((const void*)k_tail_coop, dim3(h->coop_blocks), dim3(TC_THREADS), args, 0, s));
+        h->n_launch += 1;
+        h->grid_map = (out_ld == L && out_cap == L) ? dmap_out : nullptr;   // the grid now indexes the new map
+        h->hint_map = h->grid_map;                                          // ... and c[] / d_remap carry this sweep's labels into it
+        h->timed_fused = true;
+        h->lact_dirty = true;
+        return ICMSLAM_OK;
+    }
     k_fused_means<<<nblk(L, 256), 256, 0, s>>>(st, h->d_fsum_x, h->d_fsum_y, h->d_cnt, min_x, min_y, 1.0 / h->fix_scale, h->dcfg.cota,
                                                h->d_newraw, raw_x, raw_y, h->d_kflag, L);
     CK(cudaGetLastError());
@@ -1055,7 +1088,7 @@ extern "C" int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const
                 slot->tol = o.newton_tol; slot->maxit = o.newton_maxit;
             }
             CK(cudaGraphLaunch(slot->exec, s));
-            h->n_launch += 13;                       // kernels of this library inside the graph
+            h->n_launch += h->coop_tail ? 5 : 13;    // kernels of this library inside the graph
             h->grid_map = h->d_map_out;
             h->hint_map = h->d_map_out;
             h->timed_fused = true;

@@ -265,15 +265,13 @@ __device__ int block_exclusive_scan(const int* v, int* out, int n, int* wsum /* 
     return total;
 }
 
-__global__ void __launch_bounds__(1024)
-k_tail_slow(DevState* st, TailState* ts, double dist_thr, double* kx, double* ky, double* kc, int* parent, int* nn, int* ind_flag,
+__device__ void tail_slow_body(DevState* st, TailState* ts, double dist_thr, double* kx, double* ky, double* kc, int* parent, int* nn, int* ind_flag,
             int* ind_pos, int* ind, int* lab, int* used, int* rank, double* ox, double* oy, double* oc, double* map_out, int cap_out,
             int64_t ld_out, double* counts_state, int Lcap,
             // grid rebuild over the merged map
             int max_cells, FGeom* geom, int* cell_cnt, int* cell_start, double2* pts, int* gidx,
             const int* kflag, const int* kpos, double thr1sq, double thr2_hi, LmRec* lmrec, int* remap)
 {
-    if (ts->n_ind == 0 && !ts->degenerate) return;
     __shared__ int wsum[34];
     __shared__ double red[4][32];
     const int tid = threadIdx.x, nth = blockDim.x;
@@ -405,6 +403,19 @@ k_tail_slow(DevState* st, TailState* ts, double dist_thr, double* kx, double* ky
             lmrec[r] = rec;
         }
     }
+}
+
+__global__ void __launch_bounds__(1024)
+k_tail_slow(DevState* st, TailState* ts, double dist_thr, double* kx, double* ky, double* kc, int* parent, int* nn, int* ind_flag,
+            int* ind_pos, int* ind, int* lab, int* used, int* rank, double* ox, double* oy, double* oc, double* map_out, int cap_out,
+            int64_t ld_out, double* counts_state, int Lcap,
+            // grid rebuild over the merged map
+            int max_cells, FGeom* geom, int* cell_cnt, int* cell_start, double2* pts, int* gidx,
+            const int* kflag, const int* kpos, double thr1sq, double thr2_hi, LmRec* lmrec, int* remap)
+{
+    if (ts->n_ind == 0 && !ts->degenerate) return;
+    tail_slow_body(st, ts, dist_thr, kx, ky, kc, parent, nn, ind_flag, ind_pos, ind, lab, used, rank, ox, oy, oc, map_out, cap_out, ld_out,
+                   counts_state, Lcap, max_cells, geom, cell_cnt, cell_start, pts, gidx, kflag, kpos, thr1sq, thr2_hi, lmrec, remap);
 }
 
 
