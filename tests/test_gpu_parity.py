@@ -528,3 +528,27 @@ def test_cooperative_tail_matches_kernel_chain(monkeypatch):
             e.close()
         for a, b in zip(*res):
             assert np.array_equal(a, b)
+
+
+def test_fused_exact_ties_and_duplicate_landmarks():
+    """Exact duplicates in the previous map make every observation near them an exact distance tie (np.argmin takes
+    the first index), near-duplicates exercise Mapa.filtrar's merge path, displaced landmarks create new labels:
+    four chained sweeps (grid search, then hints) against the oracle."""
+    d, cfgd = _synthetic_case(625, 2500, 20181 + 17)
+    m = d["map_init"].copy()
+    dup = m[:, 10:60].copy()                      # exact copies, appended AFTER the originals and also
+    m = np.concatenate([dup[:, :25], m, dup[:, 25:], m[:, 100:130] + 0.2], axis=1)   # ... BEFORE them
+    m[:, 200::11] += 2.5
+    cfgd = dict(cfgd, L=4096)
+    _fused_vs_oracle(d["observations"], d["odometry"], d["velocities"], cfgd, m, d["x_init"], 4, True)
+
+
+def test_fused_sparse_and_empty_scans():
+    """Blocks of empty scans (no kept beam): the averaging rule of sensors.py:147-151 inside the red-black order."""
+    d, cfgd = _synthetic_case(625, 3000, 20181 + 18)
+    z = d["observations"].copy()
+    z[:, 200:203] = 10.0          # three consecutive empty scans
+    z[:, 1001] = 10.0
+    z[:, 1500:1502] = 10.0
+    z[:, 2:5] = 10.0              # right after the pinned first pose
+    _fused_vs_oracle(z, d["odometry"], d["velocities"], cfgd, d["map_init"], d["x_init"], 3, True)
