@@ -17,6 +17,8 @@
 #include "fastgrid.cuh"
 #include "fused.cuh"
 #include "tail_coop.cuh"
+#include "fcluster.h"
+#include "pass0.cuh"
 
 #define MAX_CELLS (1 << 22)
 
@@ -1230,6 +1232,12 @@ extern "C" int icmslam_get_associations(icmslam_handle* h, int32_t* c, int32_t m
     return ICMSLAM_OK;
 }
 
+__global__ void k_counts_to_int(const double* __restrict__ cnt, int n, int* __restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int)cnt[i];
+}
+
 __global__ void k_counts_to_double(const int* __restrict__ cnt, int n, double* __restrict__ out)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1359,4 +1367,101 @@ extern "C" int icmslam_filtrar_obs(icmslam_handle* h, const double* obs, int32_t
     CK(cudaStreamSynchronize(s));
     cudaFree(d_in); cudaFree(d_out); cudaFree(d_a); cudaFree(d_keep); cudaFree(d_err);
     return err ? ICMSLAM_ERR_INVALID : ICMSLAM_OK;
+}
+
+// ---- pass 0: inicializar_online replayed on the loaded log (sensors.py:51-123) ---------------------------------
+// x (3 x T) receives the causal pose estimates (x[:,0] = x0), map_out the filtered map (`mapa_viejo`,
+// sensors.py:99-102), *L_out its width; landmarks_actuales / cant_obs_i are left as the reference leaves them.
+extern "C" int icmslam_pass0(icmslam_handle* h, const double* x0, double* x, int64_t ld_x, double* map_out, int32_t cap_out,
+                             int64_t ld_map_out, int32_t* L_out, int32_t memspace)
+{
+    if (!h || !h->extracted || !x0 || !x || ld_x < h->T || !L_out) return ICMSLAM_ERR_INVALID;
+    if (map_out && (cap_out <= 0 || ld_map_out < cap_out)) return ICMSLAM_ERR_INVALID;
+    if (h->max_per_scan > 1024) return ICMSLAM_ERR_UNSUPPORTED;
+    CK(cudaSetDevice(h->cfg.device));
+    const int T = h->T, L = h->Lcap;
+    const int64_t n = h->n;
+    cudaStream_t s = h->stream;
+    if (h->first_empty) return ICMSLAM_EMPTY_FIRST_SCAN;        // (the reference would fail inside tras_rot_z / linkage)
+    h->grid_map = nullptr; h->hint_map = nullptr;
+    if (!h->d_seen_x) { CK(dalloc(&h->d_seen_x, (size_t)n)); CK(dalloc(&h->d_seen_y, (size_t)n)); }
+    // ---- step 0: Branch A of Mapa.actualizar on the first scan (ICM_SLAM.py:160-165), on the host ------------------
+    std::vector<int> off2(2);
+    CK(cudaMemcpyAsync(off2.data(), h->d_off, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int n0 = off2[1] - off2[0];
+    double *d_w = nullptr;
+    CK(dalloc(&d_w, (size_t)2 * n0));
+    k_project_scan<<<nblk(n0, 128), 128, 0, s>>>(h->d_off, 0, h->d_bx, h->d_by, x0[0], x0[1], x0[2], d_w, d_w + n0);
+    CK(cudaGetLastError());
+    std::vector<double> w((size_t)2 * n0);
+    CK(cudaMemcpyAsync(w.data(), d_w, (size_t)2 * n0 * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    cudaFree(d_w);
+    std::vector<int> lab0(n0);
+    const int k0 = icm_fcluster::fcluster_inconsistent(w.data(), w.data() + n0, n0, h->cfg.dist_thr, lab0.data());
+    if (k0 > L) return ICMSLAM_ERR_LABEL_CAP;
+    std::vector<double> y0((size_t)2 * L, 0.0), cant0((size_t)L, 0.0);
+    for (int i = 0; i < k0; ++i) {                                // np.mean(obs[c==i,:], axis=0): row-order sum / count
+        double sx = 0.0, sy = 0.0;
+        int k = 0;
+        for (int j = 0; j < n0; ++j) if (lab0[j] == i) { sx += w[j]; sy += w[n0 + j]; ++k; }
+        y0[i] = sx / (double)k; y0[L + i] = sy / (double)k; cant0[i] = (double)k;
+    }
+    CK(cudaMemcpyAsync(h->d_raw, y0.data(), (size_t)2 * L * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_tmp_b, cant0.data(), (size_t)L * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_c, lab0.data(), (size_t)n0 * sizeof(int), cudaMemcpyHostToDevice, s));
+    // ---- steps 1 .. T-1 on the device -------------------------------------------------------------------------------
+    double* dx = x;
+    int64_t ldx = ld_x;
+    if (memspace == ICMSLAM_HOST) { dx = h->d_x; ldx = T; }
+    Pass0Params P;
+    P.T = T; P.Lcap = L; P.off = h->d_off; P.bx = h->d_bx; P.by = h->d_by; P.d = h->d_d; P.beam = h->d_beam; P.ang = h->d_ang;
+    P.odo = h->d_odo; P.ldo = T; P.u = h->d_u; P.ldu = T; P.cfg = h->dcfg;
+    P.x0[0] = x0[0]; P.x0[1] = x0[1]; P.x0[2] = x0[2];
+    P.x = dx; P.ldx = ldx; P.y = h->d_raw; P.cant = h->d_tmp_b; P.lact0 = k0; P.c = h->d_c; P.seen_x = h->d_seen_x; P.seen_y = h->d_seen_y;
+    P.st = h->d_st; P.nev = &h->d_st->newton_iters;
+    k_set_raw_l<<<1, 1, 0, s>>>(h->d_st, k0);                     // (also clears the status word)
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(&h->d_st->newton_iters, 0, sizeof(unsigned long long), s));
+    const size_t smem = (size_t)2 * 1024 * 8 + 1024 * 4;
+    k_pass0<<<1, 256, smem, s>>>(P);
+    CK(cudaGetLastError());
+    h->n_launch += 2;
+    int rc = sync_state(h);
+    if (rc) return rc;
+    if (h->h_st->status & ST_LABEL_CAP) return ICMSLAM_ERR_LABEL_CAP;
+    const int lact = h->h_st->lact;
+    h->x_cur = 0;
+    // ---- Mapa.filtrar on the map that was built (sensors.py:99-100) ---------------------------------------------------
+    k_counts_to_int<<<nblk(L, 256), 256, 0, s>>>(h->d_tmp_b, L, h->d_cnt);      // (get_raw_map reports integer counts)
+    CK(cudaGetLastError());
+    k_flags_from_counts<<<nblk(L, 256), 256, 0, s>>>(h->d_tmp_b, lact, h->dcfg.cota, h->d_kflag, L);
+    CK(cudaGetLastError());
+    rc = run_filter(h, h->d_raw, h->d_raw + L, nullptr, h->d_tmp_b, h->d_map_out, L, L, nullptr, 1);
+    if (rc) return rc;
+    rc = sync_state(h);
+    if (rc) return rc;
+    int status = status_from_state(h->h_st);
+    if (status) return status;
+    const int newL = h->h_st->new_l;
+    *L_out = newL;
+    if (memspace == ICMSLAM_HOST)
+        CK(cudaMemcpy2DAsync(x, (size_t)ld_x * 8, dx, (size_t)T * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToHost, s));
+    const int wd = newL < cap_out ? newL : cap_out;
+    if (map_out && wd > 0)
+        CK(cudaMemcpy2DAsync(map_out, (size_t)ld_map_out * 8, h->d_map_out, (size_t)L * 8, (size_t)wd * 8, 2, cudaMemcpyDefault, s));
+    CK(cudaStreamSynchronize(s));
+    return ICMSLAM_OK;
+}
+
+// ---- pass 0 helpers ---------------------------------------------------------------------------------------------
+// fcluster(linkage(pdist(obs)), t) - 1 as Mapa.actualizar calls it at t = 0 of pass 0 (ICM_SLAM.py:161): host code,
+// no device needed.  obs = (px[i], py[i]), labels out; returns the number of clusters in *n_clusters.
+extern "C" int icmslam_fcluster(const double* px, const double* py, int32_t n, double t, int32_t* labels, int32_t* n_clusters)
+{
+    if (n < 0 || (n > 0 && (!px || !py || !labels))) return ICMSLAM_ERR_INVALID;
+    const int k = icm_fcluster::fcluster_inconsistent(px, py, n, t, labels);
+    if (n_clusters) *n_clusters = k;
+    return ICMSLAM_OK;
 }

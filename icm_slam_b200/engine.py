@@ -218,6 +218,17 @@ class Engine:
         check(self.lib.icmslam_get_launch_count(self._h, C.byref(v)), self._h)
         return int(v.value)
 
+    # -- pass 0 -----------------------------------------------------------------------------------------
+    def pass0(self, x0):
+        """inicializar_online replayed on the loaded log (sensors.py:51-123): returns (positions 3 x T, mapa_viejo 2 x L')."""
+        x0 = np.ascontiguousarray(np.asarray(x0, dtype=np.float64).reshape(3))
+        x = np.zeros((3, self.T))
+        out = np.zeros((2, self.L))
+        Lout = C.c_int32()
+        st = self.lib.icmslam_pass0(self._h, C.c_void_p(x0.ctypes.data), _ptr(x)[0], self.T, _ptr(out)[0], self.L, self.L, C.byref(Lout), HOST)
+        check(st, self._h)
+        return x, out[:, : Lout.value].copy()
+
     def associations(self):
         c = np.empty(self.n, np.int32)
         if self.n:

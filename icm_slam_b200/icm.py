@@ -245,13 +245,24 @@ class ICM_SLAM:
         self.mapa_viejo = self._engine.get_map()
         return self.mapa_viejo, x
 
-    def inicializar(self, x):
-        """Pass 0 (sensors.py:51-123 / ICM_SLAM_old.py:266-333) is causal and strictly sequential; it is a
-        'next' row of the scope table and not implemented natively yet."""
-        raise NotImplementedError("pass 0 (inicializar / inicializar_online) is not part of the accelerated path yet; "
-                                  "start from odometry and an initial map (see DESIGN.md, scope row f1)")
+    def inicializar(self, x=None):
+        """Pass 0, the causal initialisation (ICM_method.inicializar, ICM_SLAM_old.py:266-333; the same computation as
+        ICM_ROS.inicializar_online + inicializar_online_process, sensors.py:51-123, replayed on the loaded log): returns
+        (mapa_inicial, x) and sets `mapa_viejo`, `positions` and the Mapa state like the reference does."""
+        self._sync_data()
+        xs, mapa = self._engine.pass0(np.asarray(self.x0).reshape(3))
+        if x is not None and getattr(x, "shape", None) == xs.shape:
+            x[...] = xs
+            xs = x
+        self.mapa_viejo = mapa.copy()
+        self.positions = xs.copy()
+        self.iterations_flag = True
+        return mapa, xs
 
-    inicializar_online = inicializar
+    def inicializar_online(self):
+        """sensors.py:51-104 without the ROS wait loop: x0 = odometria[:,0], then pass 0 over the log."""
+        self.x0 = np.array([np.asarray(self.odometria)[:, 0]]).T          # sensors.py:61
+        self.inicializar()
 
     @property
     def engine(self):

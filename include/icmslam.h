@@ -170,6 +170,17 @@ int icmslam_seg_begin(icmslam_handle* h, const double* x0, const icmslam_sweep_o
 int icmslam_seg_exchange(icmslam_handle* h, const double* gathered, int32_t rank, int32_t world);
 int icmslam_seg_finish(icmslam_handle* h);
 
+/* -- pass 0 (causal initialisation, sensors.py:51-123).  icmslam_fcluster is the one scipy call of its first
+ * step: c = fcluster(linkage(pdist(obs)), dist_thr) - 1 (ICM_SLAM.py:161; single linkage, inconsistency
+ * criterion, depth 2).  Host code: needs no device. */
+int icmslam_fcluster(const double* px, const double* py, int32_t n, double t, int32_t* labels, int32_t* n_clusters);
+/* icmslam_pass0 = ICM_ROS.inicializar_online replayed on the loaded log (= ICM_method.inicializar,
+ * ICM_SLAM_old.py:266-333): x (3 x T) <- causal poses with x[:,0] = x0 (`positions`, sensors.py:104), map_out
+ * (2 x cap_out) <- `mapa_viejo` = Mapa.filtrar of the map built on the way (sensors.py:99-102), *L_out its width.
+ * Sequential by construction; the inner solver is the reference's Nelder-Mead on fun_x. */
+int icmslam_pass0(icmslam_handle* h, const double* x0, double* x, int64_t ld_x, double* map_out, int32_t cap_out,
+                  int64_t ld_map_out, int32_t* L_out, int32_t memspace);
+
 /* -- instrumentation (no reference counterpart).  Kernel time of the last sweep run with
  * opts.reserved & 2, from CUDA events on the handle's stream: out2[0] = association (or the fused
  * sweep kernel), out2[1] = pose kernels (0 when fused), milliseconds.  Launch count = kernels of

@@ -552,3 +552,44 @@ def test_fused_sparse_and_empty_scans():
     z[:, 1500:1502] = 10.0
     z[:, 2:5] = 10.0              # right after the pinned first pose
     _fused_vs_oracle(z, d["odometry"], d["velocities"], cfgd, d["map_init"], d["x_init"], 3, True)
+
+
+# ---- pass 0 (causal initialisation) against the reference fixtures ------------------------------------------------
+@pytest.mark.parametrize("gname,inputs", [("c1_ref.npz", c1_inputs), ("c2_ref.npz", c2_inputs)])
+def test_pass0_vs_reference(gname, inputs):
+    """inicializar_online replayed natively: labels of every scan bit-exact (incl. the fcluster step at t = 0), raw
+    landmark count / counts exact, poses within 1e-6 m / 1e-8 rad of the reference's Nelder-Mead, map within 1e-6 m."""
+    g = golden(gname)
+    z, odo, u = inputs()
+    e = _engine(_cfg(), z, odo, u)
+    x, mapa = e.pass0(odo[:, 0])
+    assert np.array_equal(e.associations(), g["p0_labels"])
+    raw, cnt, rl = e.raw_map()
+    assert rl == int(g["p0_raw_L"])
+    assert np.array_equal(cnt, g["p0_raw_counts"])
+    assert np.max(np.abs(raw - g["p0_raw_map"])) <= 1e-9
+    d = np.abs(x - g["p0_x"])
+    assert d[:2].max() <= TOL_XY and d[2].max() <= TOL_TH, d.max(axis=1)
+    assert mapa.shape == g["p0_map"].shape
+    assert np.max(np.abs(mapa - g["p0_map"])) <= TOL_XY
+    assert e.landmarks_actuales == mapa.shape[1]
+    e.close()
+
+
+def test_offline_batch_path_through_the_reference_surface():
+    """load_data -> inicializar -> N x itererar, the legacy driver of external_options.py:58-89, on data_IJAC2018."""
+    from icm_slam_b200.icm import ICM_SLAM, Mapa, precondicionar, calc_cambio
+    g = golden("c1_ref.npz")
+    z, odo, u = c1_inputs()
+    cfg = _cfg(N=2)
+    icm = ICM_SLAM(cfg, x0=odo[:, 0])
+    icm.load_data(Mapa(cfg), precondicionar(z, cfg), u, odo)
+    mapa_inicial, x = icm.inicializar(np.zeros((3, z.shape[1])))
+    assert np.max(np.abs(mapa_inicial - g["p0_map"])) <= TOL_XY and np.abs(x - g["p0_x"])[:2].max() <= TOL_XY
+    mapa_viejo = mapa_inicial.copy()
+    for it in range(cfg.N):
+        mapa_refinado, x = icm.itererar(mapa_viejo, x)
+        cam = calc_cambio(mapa_refinado, mapa_viejo, cfg)
+        assert len(cam) == 3 and cam[0] <= cam[2] <= cam[1]
+        mapa_viejo = mapa_refinado.copy()
+    assert mapa_refinado.shape == (2, 11)         # the notebook's 11 trees (SURVEY section 4)
