@@ -36,14 +36,16 @@
 
 // Tile geometry, parametrised by HALF = pose slots per colour (64: 256 threads, 126 owned poses per block;
 // 32: 128 threads, 62 owned poses -- more, smaller blocks per SM whose phases interleave better).
-#define FS_THREADS (4 * HALF)  // a thread PAIR per pose slot
+#define FS_THREADS (2 * TPP * HALF)  // TPP threads (a pair or a quad) per pose slot
 #define FS_WARPS (FS_THREADS / 32)
 #define FS_SLOTS (2 * HALF)    // slots 0..HALF-1: odd poses tb-1+2j (slot 0 = halo); HALF..: even poses tb+2j (last = spare)
 #define FS_OWN (2 * HALF - 2)  // poses owned by a block: tb .. tb+FS_OWN-1 (tb even)
 #define FS_XT (2 * HALF + 4)   // pose-tile entries: poses tb-2 .. tb+FS_OWN (2*HALF+1 used)
 #define FS_HALF HALF
-#define FS_HASH 256           // landmark slots of the block-level statistics table
+#define FS_HASH (HALF >= 64 ? 256 : HALF >= 32 ? 128 : 64)   // landmark slots of the block-level statistics table
+#define FS_HASH_SHIFT (HALF >= 64 ? 24 : HALF >= 32 ? 25 : 26)
 #define FS_PROBES 8
+#define FS_MINBLK (OCC / FS_THREADS)   // OCC = resident threads per SM the kernel is compiled for (register budget = 65536 / OCC)
 
 struct FusedParams {
     int T;                                // columns of this handle's trajectory (a time segment incl. its halo columns)
@@ -56,6 +58,9 @@ struct FusedParams {
     double x0[3];                         // self.x0 (sensors.py:131)
     const double* inc; int64_t ldinc;     // 3 x T odometry increments (see k_odo_increments)
     const double* u; int64_t ldu;         // 2 x T controls
+    const double* bm; int64_t ldbm;       // 5 x T static body-frame moments of each scan (k_body_moments)
+    double* dyn; int64_t lddyn;           // 6 x T landmark moments of each scan (split mode: k_sweep_fused -> k_solve_colour)
+    double* sc; double* scn; int64_t ldsc;   // 2 x T (sin, cos) of the input headings / of the new odd headings (split mode)
     DevCfg cfg;
     double thr2_hi;                       // largest s with sqrt_rn(s) <= dist_thr
     double fix_scale;                     // fixed-point scale of the statistics (power of two)
@@ -72,6 +77,7 @@ struct FusedParams {
     int obs_cap;                          // shared-memory capacity in observations
     int skip;                             // debug ablation mask (ICMSLAM_SKIP): 1 assoc, 2 pass 1, 4 pass 2, 8 statistics, 16 solve
     unsigned long long* iters;
+    long long* prof;                      // debug (ICMSLAM_PROF): 16 clock stamps of warp 0 per block
 };
 
 // odometry increments, sweep-invariant: D_t = Rota(o_t.theta) (o_{t+1}.xy - o_t.xy), dtheta_t
@@ -90,6 +96,23 @@ __global__ void k_odo_increments(const double* __restrict__ odo, int64_t ldo, in
         dth = odo[2 * ldo + t + 1] - odo[2 * ldo + t];
     }
     inc[t] = dx; inc[ldi + t] = dy; inc[2 * ldi + t] = dth;
+}
+
+// body-frame moment sums of every scan's kept beams: sum bx, sum by, sum bx^2, sum by^2, sum bx*by.  They do not depend on
+// the poses or the map, so they are formed once per dataset (one thread per scan, fixed order: the result does not depend
+// on any tiling) and the sweep kernel only reads them (40 B per pose).
+__global__ void __launch_bounds__(128)
+k_body_moments(const int* __restrict__ off, const double2* __restrict__ bxy, int T, double* __restrict__ bm, int64_t ld)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    double Bx = 0.0, By = 0.0, Bxx = 0.0, Byy = 0.0, Bxy = 0.0;
+    for (int i = off[t]; i < off[t + 1]; ++i) {
+        const double2 b = bxy[i];
+        Bx += b.x; By += b.y;
+        Bxx = fma(b.x, b.x, Bxx); Byy = fma(b.y, b.y, Byy); Bxy = fma(b.x, b.y, Bxy);
+    }
+    bm[t] = Bx; bm[ld + t] = By; bm[2 * ld + t] = Bxx; bm[3 * ld + t] = Byy; bm[4 * ld + t] = Bxy;
 }
 
 __device__ __forceinline__ double entrepi_fast(double a)
@@ -272,17 +295,90 @@ __device__ __forceinline__ int newton_pair(const DevCfg& cfg, const PoseIn& P, c
     return it;
 }
 
+// The reduced 1-D problem in closed form.  Expanding newton_lean's phi'(theta) with s = sin(theta), c = cos(theta) gives a
+// trigonometric polynomial plus the (piecewise linear) angular residuals,
+//     phi'(theta)  = 2 (as s + ac c + au s c + av (c^2 - s^2)) + ang1(theta)
+//     phi''(theta) = 2 (as c - ac s + au (c^2 - s^2) - 4 av s c) + ang2,
+// whose four coefficients depend on the pose's moments and neighbours but not on theta: they are formed ONCE (lane role 0
+// contributes the x rows, role 1 the y rows, which are the x rows rotated by -pi/2; one shuffle each), and an iteration
+// costs a dozen FMAs instead of re-evaluating every term.  Same root as newton_lean / the oracle's newton_pose.
+// Both lanes of the pair iterate on identical values.  Returns the role's coordinate in `coord`, theta in `th`.
+__device__ __forceinline__ int newton_trig(const DevCfg& cfg, const PoseIn& P, const Mom& M, int role, double ox, double oy, double& th,
+                                           double s, double c, double tol, int maxit, double& coord, double& s_out, double& c_out)
+{
+    const double dt = cfg.dt, k = cfg.kod;
+    const double hn = P.has_next ? 1.0 : 0.0;
+    const double D1x = hn * P.D1x, D1y = hn * P.D1y;
+    const double dv = hn * dt * P.ucv;
+    // role constants (x rows for role 0, y rows for role 1), frame (a, b) = (c, s) resp. (s, -c)
+    const double r = role ? cfg.r2 : cfg.r1, q = role ? cfg.q2 : cfg.q1;
+    const double o_ = role ? oy : ox;
+    const double a_ = (role ? P.ay : P.ax) - o_;
+    const double ga = a_ + dt * ((role ? P.sa : P.ca) * P.uav);
+    const double e0 = a_ + (role ? (P.sa * P.D0x + P.ca * P.D0y) : (P.ca * P.D0x - P.sa * P.D0y));
+    const double bp = hn * ((role ? P.by : P.bx) - o_);
+    const double iS = 1.0 / (r + k + M.n * q + hn * (r + k));
+    const double KA = r * ga + k * e0 + q * (role ? M.Yy : M.Yx) + (r + k) * bp;
+    const double P1 = (r * dv + k * D1x) + q * M.By;
+    const double P2 = q * M.Bx - k * D1y;
+    const double M1 = role ? M.Myx : M.Mxx, M2 = role ? M.Myy : M.Mxy;
+    const double iKA = iS * KA;
+    const double ba = fma(iKA, P2, fma(k * bp, D1y, -q * M1));
+    const double bb = fma(-iKA, P1, fma(bp, fma(r, dv, k * D1x), q * M2));
+    const double bab = fma(-iS, fma(P2, P2, -P1 * P1), fma(q, M.Bxx - M.Byy, -fma(r * dv, dv, k * fma(D1x, D1x, -D1y * D1y))));
+    const double bd = fma(-iS * P1, P2, fma(q, M.Bxy, -k * D1x * D1y));
+    double as2 = role ? ba : bb, ac2 = role ? -bb : ba, au2 = role ? -bab : bab, av2 = role ? -bd : bd;
+    as2 += __shfl_xor_sync(FULLMASK, as2, 1); ac2 += __shfl_xor_sync(FULLMASK, ac2, 1);
+    au2 += __shfl_xor_sync(FULLMASK, au2, 1); av2 += __shfl_xor_sync(FULLMASK, av2, 1);
+    as2 *= 2.0; ac2 *= 2.0; au2 *= 2.0; av2 *= 2.0;
+    const double av8 = 4.0 * av2;
+    const double ang2 = (2.0 * cfg.r3 + 2.0 * k) * (1.0 + hn);
+    const double r3_2 = 2.0 * cfg.r3, k_2 = 2.0 * k;
+    const double th_ga = P.ath + dt * P.uaw, c3 = P.dth0 + P.ath, c4 = P.dth1 - P.bth, wb = dt * P.ucw - P.bth;
+    int it = 0;
+    bool done = false;
+    for (;;) {
+        const double u = s * c, v = fma(c, c, -s * s);
+        double ang1 = fma(r3_2, entrepi_fast(th - th_ga), -k_2 * entrepi_fast(c3 - th));
+        if (P.has_next) ang1 += fma(r3_2, entrepi_fast(th + wb), k_2 * entrepi_fast(c4 + th));
+        const double p1 = fma(as2, s, fma(ac2, c, fma(au2, u, fma(av2, v, ang1))));
+        double p2 = fma(as2, c, fma(-ac2, s, fma(au2, v, fma(-av8, u, ang2))));
+        if (!(p2 > 0.0)) p2 = ang2;
+        const double dth = -p1 * (double)__frcp_rn((float)p2);   // quasi-Newton: 24-bit reciprocal of the curvature, same fixed point
+        if (!done) {       // a converged pair is frozen: its result does not depend on how long its warp-mates iterate
+            th += dth;
+            ++it;
+            if (fabs(dth) <= 0.125) {
+                double sd, cd;
+                sincos_small(dth, sd, cd);
+                const double s2 = fma(s, cd, c * sd);
+                c = fma(c, cd, -s * sd);
+                s = s2;
+            } else {
+                sincos(th, &s, &c);
+            }
+            done = fabs(dth) <= tol || it >= maxit;
+        }
+        if (__all_sync(FULLMASK, done)) break;
+    }
+    const double a = role ? s : c, b = role ? -c : s;
+    coord = (KA - a * P1 - b * P2) * iS + o_;
+    s_out = s; c_out = c;
+    return it;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int HALF>
+template <int HALF, bool SPLIT = false>
 struct __align__(16) FusedSmemFixed {
     double xs[3][FS_XT];           // input poses tb-2 .. tb+126, index lt = t - (tb-2)
     double2 pp[FS_XT];             // projection origin of each scan (self.x0 for scan 0)
     double2 rsc[FS_XT];            // (sin, cos) of (projection heading - pi/2)
-    double sn[FS_XT], cs[FS_XT];   // sin/cos of the input headings (after phase B1: of the new odd headings)
-    double xn[3][FS_XT];           // new poses (same indexing)
-    double inc[3][FS_XT];          // odometry increments
-    double u[2][FS_XT];
+    // (split mode: the solve runs in k_pose_solve, so its inputs are not staged here)
+    double sn[SPLIT ? 1 : FS_XT], cs[SPLIT ? 1 : FS_XT];   // sin/cos of the input headings (after phase B1: of the new odd headings)
+    double xn[3][SPLIT ? 1 : FS_XT];           // new poses (same indexing)
+    double inc[3][SPLIT ? 1 : FS_XT];          // odometry increments
+    double u[2][SPLIT ? 1 : FS_XT];
     int off[FS_XT];                // off[t] at lt (clamped)
     int hkey[FS_HASH];
     int hcnt[FS_HASH];
@@ -294,11 +390,11 @@ struct __align__(16) FusedSmemFixed {
 // adds one run (label, sum of (obs - landmark), count) to the block-level table.  Shared memory has no
 // native 64-bit atomic add, so a 64-bit fixed-point sum is kept as (lo, hi) 32-bit halves: the low add
 // returns the old value, from which the carry into the high half follows exactly.
-template <int HALF>
-__device__ __forceinline__ void stat_add(FusedSmemFixed<HALF>& S, const FusedParams& p, int arg, double rdx, double rdy, int rn)
+template <int HALF, bool SPLIT>
+__device__ __forceinline__ void stat_add(FusedSmemFixed<HALF, SPLIT>& S, const FusedParams& p, int arg, double rdx, double rdy, int rn)
 {
     const long long vx = __double2ll_rn(rdx * p.fix_scale), vy = __double2ll_rn(rdy * p.fix_scale);
-    unsigned h = ((unsigned)arg * 2654435761u) >> 24;      // FS_HASH = 256
+    unsigned h = ((unsigned)arg * 2654435761u) >> FS_HASH_SHIFT;
 #pragma unroll 1
     for (int q = 0; q < FS_PROBES; ++q) {
         int key = ((volatile int*)S.hkey)[h];
@@ -332,18 +428,87 @@ __device__ __forceinline__ void mbar_wait(uint32_t mb, uint32_t parity)
     }
 }
 
-template <int HALF>
-__global__ void __launch_bounds__(FS_THREADS, 128 / HALF)
+// The red-black pose solve of one tile: the slots of the odd poses (warps of the first half) solve from the OLD even
+// neighbours, then, after a block barrier, the slots of the even poses solve from the NEW odd poses held in shared memory.
+// Shared by the single-launch kernel and by k_pose_solve (split mode).  S needs xs, xn, inc, u, sn, cs (FS_XT entries each).
+template <int HALF, int TPP, class SM>
+__device__ __forceinline__ void solve_phases(SM& S, const FusedParams& p, const Mom& M, int q, int sub, int t, int li, bool qvalid)
+{
+    const int half = sub & 1;
+    const int grp = q / FS_HALF;
+    const int T = p.T;
+    unsigned long long my_iters = 0;
+    for (int phase = 0; phase < 2; ++phase) {
+        if (phase == grp && !(p.skip & 64)) {       // warp-uniform: a warp holds 16 slots of one colour
+            double res = 0.0, th = 0.0, s_new = 0.0, c_new = 1.0;
+            if (qvalid) {
+                // neighbours: old poses for the odd phase, new (odd) poses for the even phase
+                double (*X)[FS_XT] = phase == 0 ? S.xs : S.xn;
+                const bool has_next = t + 1 < T;
+                const bool solve = !(t == 0 && p.first) && M.n > 0.0;
+                PoseIn P;
+                P.ax = X[0][li - 1]; P.ay = X[1][li - 1]; P.ath = X[2][li - 1];
+                P.sa = S.sn[li - 1]; P.ca = S.cs[li - 1];
+                P.bx = has_next ? X[0][li + 1] : 0.0; P.by = has_next ? X[1][li + 1] : 0.0; P.bth = has_next ? X[2][li + 1] : 0.0;
+                P.uav = S.u[0][li - 1]; P.uaw = S.u[1][li - 1];
+                P.ucv = S.u[0][li]; P.ucw = S.u[1][li];
+                P.D0x = S.inc[0][li - 1]; P.D0y = S.inc[1][li - 1]; P.dth0 = S.inc[2][li - 1];
+                P.D1x = S.inc[0][li]; P.D1y = S.inc[1][li]; P.dth1 = S.inc[2][li];
+                P.has_next = has_next ? 1 : 0;
+                th = S.xs[2][li];
+                if (t == 0 && p.first) {
+                    res = S.xs[half][li];
+                    s_new = S.sn[li]; c_new = S.cs[li];
+                } else if (!solve) {       // sensors.py:147-151: no observation, average of the neighbours
+                    const bool t1 = t == 1 && p.first;
+                    const double pv = t1 ? p.x0[half] : X[half][li - 1];
+                    res = (pv + X[half][li + 1]) / 2.0;
+                    th = ((t1 ? p.x0[2] : X[2][li - 1]) + X[2][li + 1]) / 2.0;
+                    sincos(th, &s_new, &c_new);
+                }
+                // (lanes that do not solve still run the loop below with harmless values: the pair shuffles inside
+                //  newton_trig need every lane of the warp)
+                double r2 = 0.0, th2 = S.xs[2][li], s2 = 0.0, c2 = 1.0;
+                const int it = newton_trig(p.cfg, P, M, half, S.xs[0][li], S.xs[1][li], th2, S.sn[li], S.cs[li], p.tol,
+                                           (solve && !(p.skip & 16)) ? p.maxit : 1, r2, s2, c2);
+                if (solve) { res = r2; th = th2; s_new = s2; c_new = c2; my_iters += (unsigned long long)(sub == 0 ? it : 0); }
+            } else {
+                PoseIn P;
+                P.ax = P.ay = P.ath = P.sa = 0.0; P.ca = 1.0; P.bx = P.by = P.bth = 0.0; P.uav = P.uaw = P.ucv = P.ucw = 0.0;
+                P.D0x = P.D0y = P.dth0 = P.D1x = P.D1y = P.dth1 = 0.0; P.has_next = 0;
+                double r2, th2 = 0.0, s2, c2;
+                newton_trig(p.cfg, P, M, half, 0.0, 0.0, th2, 0.0, 1.0, p.tol, 1, r2, s2, c2);
+            }
+            if (qvalid && sub < 2) {     // (with a quad per slot, lanes 2 and 3 repeat lanes 0 and 1)
+                S.xn[half][li] = res;
+                if (half == 0) {
+                    S.xn[2][li] = th;
+                    if (phase == 0) { S.sn[li] = s_new; S.cs[li] = c_new; }   // (old odd headings are no longer needed)
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (p.iters) {
+        my_iters = (unsigned long long)warp_sum_i((int)my_iters);
+        if ((threadIdx.x & 31) == 0 && my_iters) atomicAdd(p.iters, my_iters);
+    }
+}
+
+#define FS_STAMP(k) if (p.prof && threadIdx.x == 0) p.prof[(size_t)blockIdx.x * 24 + (k)] = clock64()
+template <int HALF, int TPP, int OCC, bool SPLIT>
+__global__ void __launch_bounds__(FS_THREADS, FS_MINBLK)
 k_sweep_fused(const FusedParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    FusedSmemFixed<HALF>& S = *reinterpret_cast<FusedSmemFixed<HALF>*>(smem_raw);
-    double2* sb = reinterpret_cast<double2*>(smem_raw + sizeof(FusedSmemFixed<HALF>));   // staged observations; later run sums
+    FusedSmemFixed<HALF, SPLIT>& S = *reinterpret_cast<FusedSmemFixed<HALF, SPLIT>*>(smem_raw);
+    double2* sb = reinterpret_cast<double2*>(smem_raw + sizeof(FusedSmemFixed<HALF, SPLIT>));   // staged observations; later run sums
     int* sbk_raw = reinterpret_cast<int*>(sb + p.obs_cap);                          // hints in (TMA), labels out; +4 ints of alignment slack
     unsigned short* srn = reinterpret_cast<unsigned short*>(sbk_raw + p.obs_cap + 4);   // run length at run heads (phase A: cell entry count)
     unsigned char* slt = reinterpret_cast<unsigned char*>(srn + p.obs_cap);             // scan (local pose index) of each observation
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    FS_STAMP(0);
     const int tb = p.t_lo + blockIdx.x * FS_OWN;      // t_lo is even: colours stay aligned with the global time index
     const int T = p.T;
     // ---- tile loads ---------------------------------------------------------------------------
@@ -352,10 +517,12 @@ k_sweep_fused(const FusedParams p)
         const bool ok = t >= 0 && t < T;
         for (int r = 0; r < 3; ++r) {
             S.xs[r][li] = ok ? p.xin[r * p.ldin + t] : 0.0;
-            S.inc[r][li] = ok ? p.inc[r * p.ldinc + t] : 0.0;
+            if (!SPLIT) S.inc[r][li] = ok ? p.inc[r * p.ldinc + t] : 0.0;
         }
-        S.u[0][li] = ok ? p.u[t] : 0.0;
-        S.u[1][li] = ok ? p.u[p.ldu + t] : 0.0;
+        if (!SPLIT) {
+            S.u[0][li] = ok ? p.u[t] : 0.0;
+            S.u[1][li] = ok ? p.u[p.ldu + t] : 0.0;
+        }
         S.off[li] = p.off[min(max(t, 0), T)];
     }
     for (int h = tid; h < FS_HASH; h += FS_THREADS) { S.hkey[h] = -1; S.hcnt[h] = 0; for (int k = 0; k < 4; ++k) S.hs[h][k] = 0u; }
@@ -366,6 +533,7 @@ k_sweep_fused(const FusedParams p)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    FS_STAMP(1);
     // ---- per-pose projection parameters: thread tid <-> pose tb-2+tid --------------------------------
     if (tid < FS_SLOTS) {
         const int t = tb - 2 + tid;
@@ -380,18 +548,27 @@ k_sweep_fused(const FusedParams p)
                 sincos(sub_rn(th, ICM_HALFPI), &st, &ct);        // make_rot: cos/sin of (theta - pi/2)
                 sh = ct; ch = -st;
             }
-            S.pp[tid] = make_double2(px, py); S.rsc[tid] = make_double2(st, ct); S.sn[tid] = sh; S.cs[tid] = ch;
+            S.pp[tid] = make_double2(px, py); S.rsc[tid] = make_double2(st, ct);
+            if (!SPLIT) { S.sn[tid] = sh; S.cs[tid] = ch; }
+            else if (tid >= 2 ? t < p.t_hi : blockIdx.x == 0) { p.sc[t] = sh; p.sc[p.ldsc + t] = ch; }
         }
     }
     // ---- pose slots: slot q is worked by the thread pair (2q, 2q+1) in phase B and solved by thread q -----
     //      slots 0..63: odd poses tb-1+2j (slot 0 = halo), slots 64..127: even poses tb+2j (slot 127 spare)
-    const int q = tid >> 1, half = tid & 1;
+    const int q = tid / TPP, sub = tid % TPP, half = sub & 1;   // half = the lane's role in the solve (x / y rows)
     const int qt = q < FS_HALF ? tb - 1 + 2 * q : tb + 2 * (q - FS_HALF);
     const int qli = qt - (tb - 2);
-    const bool qvalid = q != FS_SLOTS - 1 && qt >= 0 && qt < p.t_hi && (qt >= p.t_lo || q == 0);
+    // (split mode: the moments of pose tb-1 come from the tile that owns it; only a segment's first tile computes them for the
+    //  halo column t_lo-1, which no tile of this handle owns)
+    const bool qvalid = q != FS_SLOTS - 1 && qt >= 0 && qt < p.t_hi && (q == 0 ? (!SPLIT || blockIdx.x == 0) : qt >= p.t_lo);
     const bool qowned = qvalid && q != 0;                       // the halo pose tb-1 is recomputed, not owned
     Mom M;
     M.n = M.Bx = M.By = M.Bxx = M.Byy = M.Bxy = M.Yx = M.Yy = M.Mxx = M.Mxy = M.Myx = M.Myy = 0.0;
+    if (qvalid && !SPLIT) {     // static body-frame moments of the slot's scan (in flight until the solve)
+        M.n = (double)(S.off[qli + 1] - S.off[qli]);
+        M.Bx = __ldg(p.bm + qt); M.By = __ldg(p.bm + p.ldbm + qt); M.Bxx = __ldg(p.bm + 2 * p.ldbm + qt);
+        M.Byy = __ldg(p.bm + 3 * p.ldbm + qt); M.Bxy = __ldg(p.bm + 4 * p.ldbm + qt);
+    }
     int nfar = 0;
     double fsx = 0.0, fsy = 0.0, FBx = 0.0, FBy = 0.0;
 
@@ -399,9 +576,10 @@ k_sweep_fused(const FusedParams p)
     G.g = *p.geom;
     G.cell_start = p.cell_start; G.pts = p.gpts; G.idx = p.gidx;
     const bool have_map = p.st->lsearch > 0;
-    const int t_first = max(tb - 1, 0), t_last = min(tb + FS_OWN - 1, p.t_hi - 1);     // scans processed by this block
+    const int t_first = (SPLIT && blockIdx.x != 0) ? tb : max(tb - 1, 0), t_last = min(tb + FS_OWN - 1, p.t_hi - 1);     // scans processed by this block
     const int lt_first = t_first - (tb - 2), lt_last = t_last - (tb - 2);
     __syncthreads();
+    FS_STAMP(2);
     // ---- chunks of whole scans whose observations fit the shared-memory budget (normally one) -----------
     uint32_t parity = 0;
     for (int c_lo = lt_first; c_lo <= lt_last;) {
@@ -437,14 +615,16 @@ k_sweep_fused(const FusedParams p)
         int o = 0, e = 0, so = 0, se = 0;
         if (mine) {
             so = S.off[qli] - co; se = S.off[qli + 1] - co;
-            const int h1 = (se - so + 1) >> 1;
-            o = half ? so + h1 : so;
-            e = half ? se : so + h1;
+            const int h1 = (se - so + TPP - 1) / TPP;
+            o = min(so + sub * h1, se);
+            e = min(o + h1, se);
         }
         for (int i = o; i < e; ++i) slt[i] = (unsigned char)qli;     // (while the bulk copies are in flight)
+        FS_STAMP(3);
         mbar_wait(mb, parity);
         parity ^= 1u;
         __syncthreads();
+        FS_STAMP(4);
         // ---- phase A: lanes over consecutive observations (adjacent lanes = adjacent beams), four per lane in flight --
         //   A0 (hints): last sweep's label of the same observation, carried through the filter's renumbering, is
         //       accepted when the observation lies inside the landmark's proven-nearest radius (tail.cuh hint_radius2):
@@ -561,43 +741,51 @@ k_sweep_fused(const FusedParams p)
                 }
             }
         }
+        FS_STAMP(5);
         __syncthreads();     // the labels of the whole chunk are visible to the pose threads
+        FS_STAMP(6);
         // ---- phase B, pass 1 (thread pair per pose): runs of equal winners -> in-place run records --------
-        if (!(p.skip & 2)) {
-            int run_start = o, cur = o < e ? sbk[o] : -1;
+        if (!(p.skip & 2) && o < e) {
+            // (the next observation is fetched before the current one is consumed; the body-frame moments of the scan are
+            //  static and come from k_body_moments)
+            int run_start = o, bk = sbk[o];
+            double2 b = sb[o];
             double Sbx = 0.0, Sby = 0.0;
             for (int i = o; i < e; ++i) {
-                const double2 b = sb[i];
-                const int bk = sbk[i];
-                M.n += 1.0;
-                M.Bx += b.x; M.By += b.y;
-                M.Bxx = fma(b.x, b.x, M.Bxx); M.Byy = fma(b.y, b.y, M.Byy); M.Bxy = fma(b.x, b.y, M.Bxy);
-                if (bk != cur) {
-                    sb[run_start] = make_double2(Sbx, Sby);
-                    srn[run_start] = (unsigned short)(i - run_start);
-                    run_start = i; cur = bk; Sbx = 0.0; Sby = 0.0;
-                }
+                const int inx = min(i + 1, e - 1);
+                const double2 bn = sb[inx];
+                const int bkn = sbk[inx];
                 Sbx += b.x; Sby += b.y;
-            }
-            if (o < e) {
-                sb[run_start] = make_double2(Sbx, Sby);
-                srn[run_start] = (unsigned short)(e - run_start);
+                if (i + 1 == e || bkn != bk) {
+                    sb[run_start] = make_double2(Sbx, Sby);
+                    srn[run_start] = (unsigned short)(i + 1 - run_start);
+                    run_start = i + 1; Sbx = 0.0; Sby = 0.0;
+                }
+                b = bn; bk = bkn;
             }
         }
+        FS_STAMP(7);
         // ---- phase B, pass 2: one run per step, lanes in lockstep: moments + landmark statistics ---------
         {
             const double2 pq = mine ? S.pp[qli] : make_double2(0.0, 0.0), rc = mine ? S.rsc[qli] : make_double2(0.0, 1.0);
             const double px = pq.x, py = pq.y, st = rc.x, ct = rc.y;
             int i = (p.skip & 6) ? e : o;
+            int n = 0, bk = -1;
+            double2 sxy = make_double2(0.0, 0.0), lm = make_double2(0.0, 0.0);
+            if (i < e) {
+                n = srn[i]; bk = sbk[i]; sxy = sb[i];
+                if (bk >= 0) lm = __ldg(reinterpret_cast<const double2*>(p.lmrec + bk));
+            }
             while (__any_sync(FULLMASK, i < e)) {
                 const bool act = i < e;
-                int n = 0, bk = -1;
-                double2 sxy = make_double2(0.0, 0.0);
-                if (act) { n = srn[i]; bk = sbk[i]; sxy = sb[i]; }
+                const int i2 = i + n;                     // the next run's record and landmark are fetched first
+                int n2 = 0, bk2 = -1;
+                double2 sxy2 = make_double2(0.0, 0.0), lm2 = make_double2(0.0, 0.0);
+                if (act && i2 < e) {
+                    n2 = srn[i2]; bk2 = sbk[i2]; sxy2 = sb[i2];
+                    if (bk2 >= 0) lm2 = __ldg(reinterpret_cast<const double2*>(p.lmrec + bk2));
+                }
                 const bool matched = act && bk >= 0;
-                double2 lm = make_double2(0.0, 0.0);
-                int lab = -1;
-                if (matched) { lm = __ldg(reinterpret_cast<const double2*>(p.lmrec + bk)); lab = bk; }
                 const double dn = (double)n;
                 const double rwx = fma(ct, sxy.x, -st * sxy.y), rwy = fma(st, sxy.x, ct * sxy.y);   // sum of rotated beams
                 const double yx = lm.x - px, yy = lm.y - py;
@@ -611,23 +799,24 @@ k_sweep_fused(const FusedParams p)
                     M.Mxx = fma(yx, sxy.x, M.Mxx); M.Mxy = fma(yx, sxy.y, M.Mxy);
                     M.Myx = fma(yy, sxy.x, M.Myx); M.Myy = fma(yy, sxy.y, M.Myy);
                 }
-                if (matched && qowned && !(p.skip & 8)) stat_add(S, p, lab, rwx - dn * yx, rwy - dn * yy, n);   // sum of (obs - landmark)
-                i += n;
+                if (matched && qowned && !(p.skip & 8)) stat_add(S, p, bk, rwx - dn * yx, rwy - dn * yy, n);   // sum of (obs - landmark)
+                i = i2; n = n2; bk = bk2; sxy = sxy2; lm = lm2;
             }
         }
+        FS_STAMP(8);
         c_lo = c_hi + 1;
         if (c_lo <= lt_last) __syncthreads();   // the next chunk overwrites the staging buffers
     }
     // ---- combine the pair's partial sums (both lanes end up with the scan's totals) ----------------------------
     int far_idx = -1;
     {
-#define FS_PAIR(v) v += __shfl_xor_sync(FULLMASK, v, 1)
-        FS_PAIR(M.n); FS_PAIR(M.Bx); FS_PAIR(M.By); FS_PAIR(M.Bxx); FS_PAIR(M.Byy); FS_PAIR(M.Bxy);
+#define FS_PAIR(v) { v += __shfl_xor_sync(FULLMASK, v, 1); if (TPP == 4) v += __shfl_xor_sync(FULLMASK, v, 2); }
         FS_PAIR(M.Yx); FS_PAIR(M.Yy); FS_PAIR(M.Mxx); FS_PAIR(M.Mxy); FS_PAIR(M.Myx); FS_PAIR(M.Myy);
         FS_PAIR(fsx); FS_PAIR(fsy); FS_PAIR(FBx); FS_PAIR(FBy);
         nfar += __shfl_xor_sync(FULLMASK, nfar, 1);
+        if (TPP == 4) nfar += __shfl_xor_sync(FULLMASK, nfar, 2);
 #undef FS_PAIR
-        if (half == 0 && qowned && nfar > 0) {
+        if (sub == 0 && qowned && nfar > 0) {
             // a scan with far observations creates one label (ICM_SLAM.py:174-182): its record now, its rank in time
             // order within the tile once every slot has reported (after the solve; only the record's index is kept)
             atomicOr(&S.farbits[(qt - tb) >> 5], 1u << ((qt - tb) & 31));
@@ -644,79 +833,34 @@ k_sweep_fused(const FusedParams p)
             M.Myx = fma(yy, FBx, M.Myx); M.Myy = fma(yy, FBy, M.Myy);
         }
     }
-    // ---- pose solve by the lane pairs: warps 0-3 red (odd poses), then warps 4-7 black (even poses) --------------
-    {
-        const int grp = q / FS_HALF;
-        const int t = qt, li = qli;
-        unsigned long long my_iters = 0;
-        for (int phase = 0; phase < 2; ++phase) {
-            if (phase == grp && !(p.skip & 64)) {       // warp-uniform: a warp holds 16 slots of one colour
-                double res = 0.0, th = 0.0, s_new = 0.0, c_new = 1.0;
-                bool write = qvalid;
-                if (qvalid) {
-                    // neighbours: old poses for the odd phase, new (odd) poses for the even phase
-                    double (*X)[FS_XT] = phase == 0 ? S.xs : S.xn;
-                    const bool has_next = t + 1 < T;
-                    const bool solve = !(t == 0 && p.first) && M.n > 0.0;
-                    PoseIn P;
-                    P.ax = X[0][li - 1]; P.ay = X[1][li - 1]; P.ath = X[2][li - 1];
-                    P.sa = S.sn[li - 1]; P.ca = S.cs[li - 1];
-                    P.bx = has_next ? X[0][li + 1] : 0.0; P.by = has_next ? X[1][li + 1] : 0.0; P.bth = has_next ? X[2][li + 1] : 0.0;
-                    P.uav = S.u[0][li - 1]; P.uaw = S.u[1][li - 1];
-                    P.ucv = S.u[0][li]; P.ucw = S.u[1][li];
-                    P.D0x = S.inc[0][li - 1]; P.D0y = S.inc[1][li - 1]; P.dth0 = S.inc[2][li - 1];
-                    P.D1x = S.inc[0][li]; P.D1y = S.inc[1][li]; P.dth1 = S.inc[2][li];
-                    P.has_next = has_next ? 1 : 0;
-                    th = S.xs[2][li];
-                    if (t == 0 && p.first) {
-                        res = S.xs[half][li];
-                        sincos(th, &s_new, &c_new);
-                    } else if (!solve) {       // sensors.py:147-151: no observation, average of the neighbours
-                        const bool t1 = t == 1 && p.first;
-                        const double pv = t1 ? p.x0[half] : X[half][li - 1];
-                        res = (pv + X[half][li + 1]) / 2.0;
-                        th = ((t1 ? p.x0[2] : X[2][li - 1]) + X[2][li + 1]) / 2.0;
-                        sincos(th, &s_new, &c_new);
-                    }
-                    // (lanes that do not solve still run the loop below with harmless values: the pair shuffles inside
-                    //  newton_pair need every lane of the warp)
-                    const double st = S.rsc[li].x, ct = S.rsc[li].y;
-                    double r2 = 0.0, th2 = S.xs[2][li], s2 = 0.0, c2 = 1.0;
-                    const int it = newton_pair(p.cfg, P, M, half, S.xs[0][li], S.xs[1][li], th2, ct, -st, p.tol, (solve && !(p.skip & 16)) ? p.maxit : 1, r2, s2, c2);
-                    if (solve) { res = r2; th = th2; s_new = s2; c_new = c2; my_iters += (unsigned long long)(half == 0 ? it : 0); }
-                } else {
-                    PoseIn P;
-                    P.ax = P.ay = P.ath = P.sa = 0.0; P.ca = 1.0; P.bx = P.by = P.bth = 0.0; P.uav = P.uaw = P.ucv = P.ucw = 0.0;
-                    P.D0x = P.D0y = P.dth0 = P.D1x = P.D1y = P.dth1 = 0.0; P.has_next = 0;
-                    double r2, th2 = 0.0, s2, c2;
-                    newton_pair(p.cfg, P, M, half, 0.0, 0.0, th2, 0.0, 1.0, p.tol, 1, r2, s2, c2);
-                }
-                if (write) {
-                    S.xn[half][li] = res;
-                    if (half == 0) {
-                        S.xn[2][li] = th;
-                        if (phase == 0) { S.sn[li] = s_new; S.cs[li] = c_new; }   // (old odd headings are no longer needed)
-                    }
-                }
-            }
-            __syncthreads();
+    FS_STAMP(9);
+    if (SPLIT) {
+        // ---- split mode: hand the scan's landmark moments to k_pose_solve ---------------------------------------------
+        if (qvalid && sub == 0) {
+            double* d = p.dyn + qt;
+            d[0] = M.Yx; d[p.lddyn] = M.Yy; d[2 * p.lddyn] = M.Mxx; d[3 * p.lddyn] = M.Mxy; d[4 * p.lddyn] = M.Myx; d[5 * p.lddyn] = M.Myy;
         }
-        if (p.iters) {
-            my_iters = (unsigned long long)warp_sum_i((int)my_iters);
-            if (lane == 0 && my_iters) atomicAdd(p.iters, my_iters);
-        }
+        __syncthreads();     // every slot has reported its far observations
     }
+    // ---- pose solve by the lane pairs: warps 0-3 red (odd poses), then warps 4-7 black (even poses) --------------
+    if constexpr (!SPLIT) solve_phases<HALF, TPP>(S, p, M, q, sub, qt, qli, qvalid);
+    FS_STAMP(13);
     if (far_idx >= 0) {
         const int bit = qt - tb, w = bit >> 5;
         int rank = __popc(S.farbits[w] & ((1u << (bit & 31)) - 1u));
         for (int k = 0; k < w; ++k) rank += __popc(S.farbits[k]);
         p.far_list[far_idx].rank = rank;
     }
+    FS_STAMP(14);
     if (tid == 0) p.blk_far[blockIdx.x] = __popc(S.farbits[0]) + __popc(S.farbits[1]) + __popc(S.farbits[2]) + __popc(S.farbits[3]);
+    FS_STAMP(15);
     // ---- outputs ----------------------------------------------------------------------------------
-    const int n_own = min(FS_OWN, p.t_hi - tb);
-    for (int r = 0; r < 3; ++r)
-        for (int k = tid; k < n_own; k += FS_THREADS) p.xout[r * p.ldout + tb + k] = S.xn[r][k + 2];
+    if (!SPLIT) {
+        const int n_own = min(FS_OWN, p.t_hi - tb);
+        for (int r = 0; r < 3; ++r)
+            for (int k = tid; k < n_own; k += FS_THREADS) p.xout[r * p.ldout + tb + k] = S.xn[r][k + 2];
+    }
+    FS_STAMP(16);
     for (int h = tid; h < FS_HASH; h += FS_THREADS) {
         const int key = S.hkey[h];
         if (key >= 0 && S.hcnt[h] > 0) {
@@ -724,6 +868,77 @@ k_sweep_fused(const FusedParams p)
             atomicAdd((unsigned long long*)(p.fsum_y + key), ((unsigned long long)S.hs[h][3] << 32) | S.hs[h][2]);
             atomicAdd(p.cnt + key, S.hcnt[h]);
         }
+    }
+    FS_STAMP(17);
+}
+
+// ---- split mode: the pose solve as two launches, one per colour -----------------------------------------------------
+// k_sweep_fused<.., SPLIT = true> leaves, per scan, the landmark moments (p.dyn) and the sin/cos of the input heading
+// (p.sc).  The solve then needs no tile, no shared memory and no barrier: k_solve_colour<0> solves every odd pose from its
+// OLD even neighbours (a lane pair per pose, everything read straight from global memory), k_solve_colour<1> every even
+// pose from the NEW odd poses.  Same arithmetic as solve_phases, so the results are identical to the single-launch kernel.
+// A segment re-solves the odd halo pose t_lo-1 itself (its moments come from the segment's first tile).
+template <int COLOUR, int OCC>
+__global__ void __launch_bounds__(128, OCC / 128)
+k_solve_colour(const FusedParams p)
+{
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 1, half = threadIdx.x & 1;
+    const int T = p.T;
+    const int t = COLOUR == 0 ? (p.t_lo >= 2 ? p.t_lo - 1 : 1) + 2 * g : p.t_lo + 2 * g;
+    const bool qvalid = t < p.t_hi;
+    const double* X = COLOUR == 0 ? p.xin : p.xout;          // the neighbours: old poses for the odd colour, new ones for the even
+    const int64_t ldX = COLOUR == 0 ? p.ldin : p.ldout;
+    const double* SC = COLOUR == 0 ? p.sc : p.scn;           // ... and the sin/cos of the previous pose's heading
+    Mom M;
+    M.n = M.Bx = M.By = M.Bxx = M.Byy = M.Bxy = M.Yx = M.Yy = M.Mxx = M.Mxy = M.Myx = M.Myy = 0.0;
+    PoseIn P;
+    P.ax = P.ay = P.ath = P.sa = 0.0; P.ca = 1.0; P.bx = P.by = P.bth = 0.0; P.uav = P.uaw = P.ucv = P.ucw = 0.0;
+    P.D0x = P.D0y = P.dth0 = P.D1x = P.D1y = P.dth1 = 0.0; P.has_next = 0;
+    double ox = 0.0, oy = 0.0, th0 = 0.0, s0 = 0.0, c0 = 1.0;
+    bool solve = false;
+    const bool pinned = qvalid && t == 0;                    // x[:,0] is never updated (sensors.py:131)
+    if (qvalid) {
+        ox = p.xin[t]; oy = p.xin[p.ldin + t]; th0 = p.xin[2 * p.ldin + t];
+        s0 = p.sc[t]; c0 = p.sc[p.ldsc + t];
+        if (!pinned) {
+            const bool has_next = t + 1 < T;
+            P.has_next = has_next ? 1 : 0;
+            M.n = (double)(p.off[t + 1] - p.off[t]);
+            P.ax = X[t - 1]; P.ay = X[ldX + t - 1]; P.ath = X[2 * ldX + t - 1];
+            P.sa = SC[t - 1]; P.ca = SC[p.ldsc + t - 1];
+            if (has_next) { P.bx = X[t + 1]; P.by = X[ldX + t + 1]; P.bth = X[2 * ldX + t + 1]; }
+            P.uav = p.u[t - 1]; P.uaw = p.u[p.ldu + t - 1]; P.ucv = p.u[t]; P.ucw = p.u[p.ldu + t];
+            P.D0x = p.inc[t - 1]; P.D0y = p.inc[p.ldinc + t - 1]; P.dth0 = p.inc[2 * p.ldinc + t - 1];
+            P.D1x = p.inc[t]; P.D1y = p.inc[p.ldinc + t]; P.dth1 = p.inc[2 * p.ldinc + t];
+            M.Bx = __ldg(p.bm + t); M.By = __ldg(p.bm + p.ldbm + t); M.Bxx = __ldg(p.bm + 2 * p.ldbm + t);
+            M.Byy = __ldg(p.bm + 3 * p.ldbm + t); M.Bxy = __ldg(p.bm + 4 * p.ldbm + t);
+            const double* d = p.dyn + t;
+            M.Yx = d[0]; M.Yy = d[p.lddyn]; M.Mxx = d[2 * p.lddyn]; M.Mxy = d[3 * p.lddyn]; M.Myx = d[4 * p.lddyn]; M.Myy = d[5 * p.lddyn];
+            solve = M.n > 0.0;
+        }
+    }
+    double res = half ? oy : ox, th = th0, s_new = s0, c_new = c0;
+    if (qvalid && !pinned && !solve) {       // sensors.py:147-151: no observation, average of the neighbours
+        const bool t1 = t == 1 && p.first;
+        const double pv = t1 ? p.x0[half] : (half ? P.ay : P.ax);
+        res = (pv + (half ? P.by : P.bx)) / 2.0;
+        th = ((t1 ? p.x0[2] : P.ath) + P.bth) / 2.0;
+        sincos(th, &s_new, &c_new);
+    }
+    {
+        // (lanes that do not solve still run the iteration with harmless values: newton_trig's shuffles need the whole warp)
+        double r2 = 0.0, th2 = th0, s2 = 0.0, c2 = 1.0;
+        const int it = newton_trig(p.cfg, P, M, half, ox, oy, th2, s0, c0, p.tol, (solve && !(p.skip & 16)) ? p.maxit : 1, r2, s2, c2);
+        if (solve) { res = r2; th = th2; s_new = s2; c_new = c2; }
+        if (p.iters) {
+            const int tot = warp_sum_i((solve && half == 0) ? it : 0);
+            if ((threadIdx.x & 31) == 0 && tot) atomicAdd(p.iters, (unsigned long long)tot);
+        }
+    }
+    if (qvalid) {
+        p.xout[(half ? p.ldout : 0) + t] = res;
+        if (half == 0) p.xout[2 * p.ldout + t] = th;
+        if (COLOUR == 0) p.scn[(half ? p.ldsc : 0) + t] = half ? c_new : s_new;
     }
 }
 
@@ -734,16 +949,44 @@ __global__ void k_interleave(const double* __restrict__ bx, const double* __rest
     if (i < n) out[i] = make_double2(bx[i], by[i]);
 }
 
-static size_t fused_smem_bytes(int half, int obs_cap)   // obs_cap is even
+static size_t fused_smem_fixed(int half, bool split)
 {
-    return (half == 32 ? sizeof(FusedSmemFixed<32>) : sizeof(FusedSmemFixed<64>)) + (size_t)obs_cap * 23 + 64;
+    if (split) return half == 16 ? sizeof(FusedSmemFixed<16, true>) : half == 32 ? sizeof(FusedSmemFixed<32, true>) : sizeof(FusedSmemFixed<64, true>);
+    return half == 16 ? sizeof(FusedSmemFixed<16>) : half == 32 ? sizeof(FusedSmemFixed<32>) : sizeof(FusedSmemFixed<64>);
 }
+static size_t fused_smem_bytes(int half, bool split, int obs_cap)   // obs_cap is even
+{
+    return fused_smem_fixed(half, split) + (size_t)obs_cap * 23 + 64;
+}
+
+// the compiled variants: (pose slots per colour, threads per slot, resident threads per SM)
+#define FUSED_DEFAULT_HALF 64
+#define FUSED_DEFAULT_TPP 2
+#define FUSED_DEFAULT_OCC 512
+typedef void (*fused_kernel_t)(const FusedParams);
+static fused_kernel_t fused_variant(int half, int tpp, int occ, bool split)
+{
+#define FV(H, P, O) if (half == H && tpp == P && occ == O) return split ? k_sweep_fused<H, P, O, true> : k_sweep_fused<H, P, O, false>;
+    FV(64, 2, 512) FV(32, 2, 512) FV(16, 2, 512) FV(32, 2, 640) FV(32, 2, 768) FV(64, 2, 768)
+#undef FV
+    return nullptr;
+}
+static fused_kernel_t solve_variant(int colour, int occ)     // k_solve_colour: 64 poses of one colour per 128-thread block
+{
+    if (occ == 1024) return colour ? k_solve_colour<1, 1024> : k_solve_colour<0, 1024>;
+    if (occ == 512) return colour ? k_solve_colour<1, 512> : k_solve_colour<0, 512>;
+    return colour ? k_solve_colour<1, 768> : k_solve_colour<0, 768>;
+}
+#define SOLVE_THREADS 128
 #undef FS_THREADS
 #undef FS_WARPS
 #undef FS_SLOTS
 #undef FS_OWN
 #undef FS_XT
 #undef FS_HALF
+#undef FS_HASH
+#undef FS_HASH_SHIFT
+#undef FS_MINBLK
 
 // raw map of the previous-map landmarks from the fixed-point statistics + keep flags for all labels;
 // clears the statistics for the next sweep.

@@ -64,7 +64,7 @@ struct icmslam_handle {
     size_t cub_bytes = 0;
     // fused (REDBLACK, NEWTON, PREV) path
     bool fused_ok = false;
-    double *d_inc = nullptr /*3 x T odometry increments*/, *d_x2 = nullptr /*3 x T, pose double buffer*/;
+    double *d_bm = nullptr /*5 x T static body-frame moments*/, *d_inc = nullptr /*3 x T odometry increments*/, *d_x2 = nullptr /*3 x T, pose double buffer*/;
     FarRec* d_far_list = nullptr;
     int *d_blk_far = nullptr, *d_blk_prefix = nullptr;
     int n_tiles = 0;
@@ -90,6 +90,10 @@ struct icmslam_handle {
     unsigned long long* d_bb = nullptr;
     int obs_cap = 0, max_tile_obs = 0;
     int tile_half = 64, tile_own = 126;   // fused-kernel tile: pose slots per colour / poses owned per block
+    int tile_tpp = 2, tile_occ = 512;     // threads per pose slot; resident threads per SM the variant is compiled for
+    int split = 1, solve_occ = 768;      // split mode: association + moments in k_sweep_fused, pose solve in k_pose_solve
+    double* d_dyn = nullptr;              // 6 x T landmark moments of each scan (split mode)
+    double* d_sc = nullptr;               // 2 x (2 x T): sin/cos of the input headings, then of the new odd headings (split mode)
     // time-segment partition (icmslam_set_segment): this handle owns columns [seg_lo, seg_hi) of its T columns
     int seg_lo = 0, seg_hi = 0, seg_first = 1, seg_last = 1;
     double* d_newraw = nullptr;   // 2 x Lcap: means of the sweep's new labels (zero elsewhere)
@@ -154,7 +158,7 @@ static void free_dataset(icmslam_handle* h)
     DFREE(h->d_off); DFREE(h->d_beam); DFREE(h->d_scan_of); DFREE(h->d_d); DFREE(h->d_bx); DFREE(h->d_by);
     DFREE(h->d_c); DFREE(h->d_keys_out); DFREE(h->d_iota); DFREE(h->d_sorted); DFREE(h->d_seen_x); DFREE(h->d_seen_y);
     DFREE(h->d_nfar); DFREE(h->d_flag); DFREE(h->d_prefix); DFREE(h->d_x);
-    DFREE(h->d_inc); DFREE(h->d_x2); DFREE(h->d_far_list); DFREE(h->d_blk_far); DFREE(h->d_blk_prefix); DFREE(h->d_bxy);
+    DFREE(h->d_inc); DFREE(h->d_bm); DFREE(h->d_dyn); DFREE(h->d_sc); DFREE(h->d_x2); DFREE(h->d_far_list); DFREE(h->d_blk_far); DFREE(h->d_blk_prefix); DFREE(h->d_bxy);
     drop_graphs(h);
     h->grid_map = nullptr;
     h->hint_map = nullptr;
@@ -356,7 +360,14 @@ extern "C" int icmslam_load(icmslam_handle* h, const double* scans, int32_t B, i
     CK(dalloc(&h->d_prefix, (size_t)T + 1));
     CK(dalloc(&h->d_inc, (size_t)3 * T));
     CK(dalloc(&h->d_x2, (size_t)3 * T));
-    { const char* et = getenv("ICMSLAM_TILE"); h->tile_half = (et && atoi(et) == 32) ? 32 : 64; h->tile_own = 2 * h->tile_half - 2; }
+    {
+        const char* et = getenv("ICMSLAM_TILE"); const char* ep = getenv("ICMSLAM_TPP"); const char* eo = getenv("ICMSLAM_OCC");
+        int v = et ? atoi(et) : FUSED_DEFAULT_HALF, tpp = ep ? atoi(ep) : FUSED_DEFAULT_TPP, occ = eo ? atoi(eo) : FUSED_DEFAULT_OCC;
+        if (!fused_variant(v, tpp, occ, false)) { v = FUSED_DEFAULT_HALF; tpp = FUSED_DEFAULT_TPP; occ = FUSED_DEFAULT_OCC; }
+        h->tile_half = v; h->tile_tpp = tpp; h->tile_occ = occ; h->tile_own = 2 * v - 2;
+        { const char* es = getenv("ICMSLAM_SPLIT"); if (es) h->split = atoi(es) != 0; }
+        { const char* es = getenv("ICMSLAM_SOLVE_OCC"); if (es) h->solve_occ = atoi(es); }
+    }
     h->seg_lo = 0; h->seg_hi = T; h->seg_first = 1; h->seg_last = 1;
     h->n_tiles = nblk(T, h->tile_own);
     CK(dalloc(&h->d_far_list, (size_t)T));
@@ -437,6 +448,14 @@ extern "C" int icmslam_extract(icmslam_handle* h)
     CK(dalloc(&h->d_bxy, n + 2));
     k_interleave<<<nblk((int64_t)n, 256), 256, 0, h->stream>>>(h->d_bx, h->d_by, (int64_t)n, h->d_bxy);
     CK(cudaGetLastError());
+    DFREE(h->d_bm); DFREE(h->d_dyn); DFREE(h->d_sc);
+    CK(dalloc(&h->d_sc, (size_t)4 * T));
+    CK(cudaMemsetAsync(h->d_sc, 0, (size_t)4 * T * sizeof(double), h->stream));
+    CK(dalloc(&h->d_bm, (size_t)5 * T));
+    CK(dalloc(&h->d_dyn, (size_t)6 * T));
+    CK(cudaMemsetAsync(h->d_dyn, 0, (size_t)6 * T * sizeof(double), h->stream));
+    k_body_moments<<<nblk(T, 128), 128, 0, h->stream>>>(h->d_off, h->d_bxy, T, h->d_bm, T);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
     cudaFree(d_masks);
     cudaFree(d_counts);
@@ -449,8 +468,8 @@ extern "C" int icmslam_extract(icmslam_handle* h)
             if (m > mx) mx = m;
         }
         h->max_tile_obs = mx;
-        int blocks_per_sm = h->tile_half == 32 ? 4 : 2;
-        const size_t fixed = h->tile_half == 32 ? sizeof(FusedSmemFixed<32>) : sizeof(FusedSmemFixed<64>);
+        int blocks_per_sm = h->tile_occ / (2 * h->tile_tpp * h->tile_half);
+        const size_t fixed = fused_smem_fixed(h->tile_half, h->split != 0);
         const char* envb = getenv("ICMSLAM_BLOCKS_PER_SM");
         if (envb && atoi(envb) > 0) blocks_per_sm = atoi(envb);
         const size_t per_block = (size_t)233472 / blocks_per_sm - 1024 - 512;   // 228 KB per SM, 1 KB reserved per block
@@ -463,10 +482,10 @@ extern "C" int icmslam_extract(icmslam_handle* h)
         if (cap < h->max_per_scan) cap = h->max_per_scan;          // a chunk holds at least one whole scan
         if (cap < 2) cap = 2;
         h->obs_cap = (cap + 1) & ~1;
-        h->fused_smem = fused_smem_bytes(h->tile_half, h->obs_cap);
+        h->fused_smem = fused_smem_bytes(h->tile_half, h->split != 0, h->obs_cap);
+        { const char* epad = getenv("ICMSLAM_SMEM_PAD"); if (epad) h->fused_smem += (size_t)atoi(epad); }   // (debug: lowers the residency)
         // (a per-function, per-device attribute shared by every handle of the process: opt in to the maximum)
-        CK(cudaFuncSetAttribute(k_sweep_fused<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        CK(cudaFuncSetAttribute(k_sweep_fused<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        CK(cudaFuncSetAttribute(fused_variant(h->tile_half, h->tile_tpp, h->tile_occ, h->split != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         h->fused_ok = true;
     }
     return ICMSLAM_OK;
@@ -686,7 +705,7 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
     P.off = h->d_off; P.bxy = h->d_bxy;
     P.xin = xin; P.ldin = ldin; P.xout = kout; P.ldout = kld;
     P.x0[0] = x0[0]; P.x0[1] = x0[1]; P.x0[2] = x0[2];
-    P.inc = h->d_inc; P.ldinc = T; P.u = h->d_u; P.ldu = T;
+    P.inc = h->d_inc; P.ldinc = T; P.u = h->d_u; P.ldu = T; P.bm = h->d_bm; P.ldbm = T; P.dyn = h->d_dyn; P.lddyn = T; P.sc = h->d_sc; P.scn = h->d_sc + 2 * (size_t)T; P.ldsc = T;
     P.cfg = h->dcfg; P.thr2_hi = h->thr2_hi; P.fix_scale = h->fix_scale; P.tol = o.newton_tol; P.maxit = o.newton_maxit;
     P.st = st; P.geom = h->d_fg_geom; P.cell_start = h->d_fg_start; P.gpts = h->d_fg_pts; P.gidx = h->d_fg_idx;
     P.lmrec = h->d_lmrec; P.remap = h->d_remap;
@@ -694,12 +713,40 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
     P.c = h->d_c; P.fsum_x = h->d_fsum_x; P.fsum_y = h->d_fsum_y; P.cnt = h->d_cnt;
     P.far_list = h->d_far_list; P.ts = h->d_ts; P.blk_far = h->d_blk_far;
     P.obs_cap = h->obs_cap; P.iters = (o.reserved & 1) ? &st->newton_iters : nullptr;
+    P.prof = nullptr;
+    static long long* d_prof = nullptr;      // debug only (ICMSLAM_PROF=1): per-block phase stamps, summarised on stderr
+    const bool prof = getenv("ICMSLAM_PROF") && atoi(getenv("ICMSLAM_PROF")) > 0 && !h->use_graph;
+    if (prof) {
+        if (!d_prof) cudaMalloc(&d_prof, (size_t)h->n_tiles * 24 * sizeof(long long));
+        cudaMemsetAsync(d_prof, 0, (size_t)h->n_tiles * 24 * sizeof(long long), s);
+        P.prof = d_prof;
+    }
     { const char* es = getenv("ICMSLAM_SKIP"); P.skip = es ? atoi(es) : 0; }
     if (timing) CK(cudaEventRecord(h->ev[0], s));
-    if (h->tile_half == 32) k_sweep_fused<32><<<h->n_tiles, 128, h->fused_smem, s>>>(P);
-    else k_sweep_fused<64><<<h->n_tiles, 256, h->fused_smem, s>>>(P);
+    fused_variant(h->tile_half, h->tile_tpp, h->tile_occ, h->split != 0)<<<h->n_tiles, 2 * h->tile_tpp * h->tile_half, h->fused_smem, s>>>(P);
+    if (h->split) {
+        CK(cudaGetLastError());
+        const int n_pairs = (h->seg_hi - h->seg_lo) / 2 + 2;      // poses of one colour (incl. the odd halo pose of a segment)
+        solve_variant(0, h->solve_occ)<<<nblk(2 * n_pairs, SOLVE_THREADS), SOLVE_THREADS, 0, s>>>(P);
+        CK(cudaGetLastError());
+        solve_variant(1, h->solve_occ)<<<nblk(2 * n_pairs, SOLVE_THREADS), SOLVE_THREADS, 0, s>>>(P);
+        h->n_launch += 2;
+    }
     CK(cudaGetLastError());
     if (timing) CK(cudaEventRecord(h->ev[1], s));
+    if (prof) {
+        std::vector<long long> hp((size_t)h->n_tiles * 24);
+        cudaStreamSynchronize(s);
+        cudaMemcpy(hp.data(), d_prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        double acc[24] = {0};
+        for (int b = 0; b < h->n_tiles; ++b)
+            for (int k = 1; k < 18; ++k) acc[k] += (double)(hp[(size_t)b * 24 + k] - hp[(size_t)b * 24 + k - 1]);
+        static const char* nm[24] = {"", "tile loads+sync", "proj params+sync", "tma issue+slt", "mbar wait+sync", "phase A (warp 0)", "barrier A",
+                                     "pass 1", "pass 2", "combine+far", "red solve", "barrier red", "black solve", "barrier black", "iters+far rank", "blk_far", "pose writes", "stat flush", "", "", "", "", "", ""};
+        double tot = 0; for (int k = 1; k < 18; ++k) tot += acc[k];
+        fprintf(stderr, "[prof] %d blocks, mean cycles per block %.0f\n", h->n_tiles, tot / h->n_tiles);
+        for (int k = 1; k < 18; ++k) fprintf(stderr, "[prof]   %-18s %8.0f  %5.1f%%\n", nm[k], acc[k] / h->n_tiles, 100.0 * acc[k] / tot);
+    }
     k_tail_scan<<<1, 1024, 0, s>>>(h->d_blk_far, h->n_tiles, h->d_blk_prefix, st, h->d_ts, L, h->d_bb);
     CK(cudaGetLastError());
     h->n_launch += 2;
