@@ -61,6 +61,16 @@ struct FusedParams {
     const double* bm; int64_t ldbm;       // 5 x T static body-frame moments of each scan (k_body_moments)
     double* dyn; int64_t lddyn;           // 6 x T landmark moments of each scan (split mode: k_sweep_fused -> k_solve_colour)
     double* sc; double* scn; int64_t ldsc;   // 2 x T (sin, cos) of the input headings / of the new odd headings (split mode)
+    // label certificates and the run cache (split mode; see "Label certificates" below)
+    int cert;                             // certificates may be used this sweep (c[] and the stamps belong to this map chain)
+    int stamp;                            // full passes stamp certificates and fill the run cache
+    double rho, marg_scale;               // bound on |b| of a kept beam; 65535 / (2 sqrt(thr2_hi) dist_thr) rounded down
+    double slack_unit;                    // one 8-bit slack step: dist_thr / 256, rounded down
+    double2* rsum; int4* rmeta;           // run records: (sum bx, sum by) / (label, beams, landmark odometer when stamped, slack [float bits]);
+                                          // a scan's first-half runs are stored from off[t] up, its second-half runs from off[t+1]-1 down
+    int* rcnt;                            // runs of each scan: first half | second half << 16
+    int* echk;                            // epoch in which the scan was stamped
+    double* xchk; int64_t ldchk;          // 3 x T pose the scan was projected with when it was stamped
     DevCfg cfg;
     double thr2_hi;                       // largest s with sqrt_rn(s) <= dist_thr
     double fix_scale;                     // fixed-point scale of the statistics (power of two)
@@ -390,9 +400,12 @@ struct __align__(16) FusedSmemFixed {
 // adds one run (label, sum of (obs - landmark), count) to the block-level table.  Shared memory has no
 // native 64-bit atomic add, so a 64-bit fixed-point sum is kept as (lo, hi) 32-bit halves: the low add
 // returns the old value, from which the carry into the high half follows exactly.
+// (Tried and dropped: grouping the warp's lanes by label with __match_any + __reduce_add before touching the table --
+//  the partial-mask reductions cost ten times what the conflicting atomics do.)
 template <int HALF, bool SPLIT>
-__device__ __forceinline__ void stat_add(FusedSmemFixed<HALF, SPLIT>& S, const FusedParams& p, int arg, double rdx, double rdy, int rn)
+__device__ __forceinline__ void stat_add(FusedSmemFixed<HALF, SPLIT>& S, const FusedParams& p, bool active, int arg, double rdx, double rdy, int rn)
 {
+    if (!active) return;
     const long long vx = __double2ll_rn(rdx * p.fix_scale), vy = __double2ll_rn(rdy * p.fix_scale);
     unsigned h = ((unsigned)arg * 2654435761u) >> FS_HASH_SHIFT;
 #pragma unroll 1
@@ -495,6 +508,18 @@ __device__ __forceinline__ void solve_phases(SM& S, const FusedParams& p, const 
     }
 }
 
+// Label certificates (split mode).  When phase A accepts last sweep's label l for an observation at distance d from the
+// landmark, inside its proven-nearest radius r (d^2 <= r^2), the label stays the strict argmin inside the gate for as long as
+// the observation's world position and the landmark record together move by less than r - d >= (r^2 - d^2) / (2 sqrt(thr2_hi)).
+// A run of beams keeps the least such slack of its observations (0 if one of them went through the grid search or is far)
+// and the landmark's odometer g (LmRec::g, tail.cuh: how far the record has moved in total) at that time; the scan keeps the
+// pose it was projected with.  On a later sweep the labels of a run -- hence its cached record (label, beams, sum of the
+// body-frame points) -- are PROVABLY what phase A would produce if
+//     (|dx| + |dy| + |dtheta| rho + (g_now - g_then)) (1 + 1e-6) + 1e-9 < slack,
+// rho bounding the beam length.  A tile whose runs all pass skips staging, association and the run pass: it forms the
+// moments from ~5 cached run records per scan instead of ~25 observations.  The attempt is speculative (it only touches the
+// block's shared-memory table); a tile that fails it runs the full path, which re-stamps its scans.  Anything that
+// renumbers landmarks bumps the epoch and voids every certificate.
 #define FS_STAMP(k) if (p.prof && threadIdx.x == 0) p.prof[(size_t)blockIdx.x * 24 + (k)] = clock64()
 template <int HALF, int TPP, int OCC, bool SPLIT>
 __global__ void __launch_bounds__(FS_THREADS, FS_MINBLK)
@@ -578,11 +603,118 @@ k_sweep_fused(const FusedParams p)
     const bool have_map = p.st->lsearch > 0;
     const int t_first = (SPLIT && blockIdx.x != 0) ? tb : max(tb - 1, 0), t_last = min(tb + FS_OWN - 1, p.t_hi - 1);     // scans processed by this block
     const int lt_first = t_first - (tb - 2), lt_last = t_last - (tb - 2);
-    __syncthreads();
+    // ---- label certificates: try to form the tile's moments from the cached run records ------------------------------
+    constexpr bool CERT = SPLIT && TPP == 2;
+    bool fast = false;
+    int epoch = 0;
+    double pth_ = 0.0;                      // heading the slot's scan is projected with
+    if constexpr (CERT) {
+        epoch = p.ts->epoch;
+        bool ok_all = true;
+        double dpose = 0.0;
+        if (qvalid) {
+            const bool pin = qt == 0 && p.first;
+            const double ppx = pin ? p.x0[0] : S.xs[0][qli], ppy = pin ? p.x0[1] : S.xs[1][qli];
+            pth_ = pin ? p.x0[2] : S.xs[2][qli];
+            if (p.cert) {
+                dpose = fabs(ppx - p.xchk[qt]) + fabs(ppy - p.xchk[p.ldchk + qt]) + fabs(pth_ - p.xchk[2 * p.ldchk + qt]) * p.rho;
+                ok_all = p.echk[qt] == epoch && dpose < 1e30;
+            }
+        }
+        __syncthreads();        // (the projection parameters are in place)
+        FS_STAMP(18);
+        if (__syncthreads_and(ok_all && p.cert)) {
+            FS_STAMP(19);
+            // The slot's cached run records, then the landmark records they name, are brought into shared memory with
+            // 16-byte asynchronous copies (every copy of a stage is in flight at once: one memory round trip per stage,
+            // whatever the number of runs); the moments are then formed from shared memory.
+            struct __align__(16) RunSlot { double2 sum; int4 meta; double2 lm; double2 lg; };
+            RunSlot* rs = reinterpret_cast<RunSlot*>(sb);
+            const int cap_runs = (int)(((size_t)p.obs_cap * 23) / sizeof(RunSlot));
+            int nr = 0, gi = 0;
+            const int step = sub == 0 ? 1 : -1;
+            if (qvalid) {
+                const int rcw = __ldg(p.rcnt + qt);
+                nr = sub == 0 ? (rcw & 0xffff) : (rcw >> 16);
+                gi = sub == 0 ? S.off[qli] : S.off[qli + 1] - 1;
+            }
+            // block-wide exclusive scan of the run counts: compact slots
+            int inc = nr;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULLMASK, inc, d); if (lane >= d) inc += v; }
+            int* wsum = reinterpret_cast<int*>(S.hcnt);          // (the statistics table is empty at this point; restored below)
+            if (lane == 31) wsum[warp] = inc;
+            __syncthreads();
+            int base = inc - nr, total = 0;
+            for (int w = 0; w < FS_WARPS; ++w) { const int v = wsum[w]; if (w < warp) base += v; total += v; }
+            __syncthreads();
+            if (tid < FS_WARPS) wsum[tid] = 0;
+            __syncthreads();
+            FS_STAMP(20);
+            if (total <= cap_runs) {
+                for (int k = 0; k < nr; ++k) {
+                    const uint32_t d0 = smem_u32(&rs[base + k]);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(p.rsum + gi + k * step) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + 16u), "l"(p.rmeta + gi + k * step) : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                FS_STAMP(21);
+                for (int k = 0; k < nr; ++k) {
+                    const int lab = rs[base + k].meta.x;
+                    if (lab >= 0) {
+                        const uint32_t d0 = smem_u32(&rs[base + k].lm);
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(p.lmrec + lab) : "memory");
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d0 + 16u), "l"(reinterpret_cast<const double2*>(p.lmrec + lab) + 1) : "memory");
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                FS_STAMP(22);
+                const double2 pq = qvalid ? S.pp[qli] : make_double2(0.0, 0.0), rc = qvalid ? S.rsc[qli] : make_double2(0.0, 1.0);
+                const double px = pq.x, py = pq.y, st = rc.x, ct = rc.y;
+                int k = 0;
+                while (__any_sync(FULLMASK, k < nr)) {
+                    const bool act = k < nr;
+                    double2 sxy = make_double2(0.0, 0.0), lm = make_double2(0.0, 0.0), lg = make_double2(0.0, 0.0);
+                    int4 meta = make_int4(-1, 0, 0, 0);
+                    if (act) {
+                        const RunSlot& r = rs[base + k];
+                        sxy = r.sum; meta = r.meta;
+                        if (meta.x >= 0) { lm = r.lm; lg = r.lg; }
+                        // the run's certificate
+                        const double drift = (dpose + (lg.y - (double)__int_as_float(meta.z))) * (1.0 + 1e-6) + 1e-9;
+                        ok_all = ok_all && meta.x >= 0 && drift < (double)__int_as_float(meta.w);
+                    }
+                    const bool matched = act && meta.x >= 0;
+                    const double dn = (double)meta.y;
+                    const double rwx = fma(ct, sxy.x, -st * sxy.y), rwy = fma(st, sxy.x, ct * sxy.y);
+                    const double yx = lm.x - px, yy = lm.y - py;
+                    if (matched) {
+                        M.Yx = fma(dn, yx, M.Yx); M.Yy = fma(dn, yy, M.Yy);
+                        M.Mxx = fma(yx, sxy.x, M.Mxx); M.Mxy = fma(yx, sxy.y, M.Mxy);
+                        M.Myx = fma(yy, sxy.x, M.Myx); M.Myy = fma(yy, sxy.y, M.Myy);
+                    }
+                    stat_add(S, p, matched && qowned && !(p.skip & 8), meta.x, rwx - dn * yx, rwy - dn * yy, meta.y);
+                    if (act) ++k;
+                }
+            } else ok_all = false;
+            FS_STAMP(23);
+            fast = __syncthreads_and(ok_all) != 0;
+            if (!fast) {       // some run lost its certificate: undo the attempt, the full path follows
+                M.Yx = M.Yy = M.Mxx = M.Mxy = M.Myx = M.Myy = 0.0;
+                for (int h = tid; h < FS_HASH; h += FS_THREADS) { S.hkey[h] = -1; S.hcnt[h] = 0; for (int kk = 0; kk < 4; ++kk) S.hs[h][kk] = 0u; }
+                __syncthreads();
+            } else if (tid == 0) atomicAdd(&const_cast<DevState*>(p.st)->cert_tiles, 1);
+        }
+    } else {
+        __syncthreads();
+    }
     FS_STAMP(2);
     // ---- chunks of whole scans whose observations fit the shared-memory budget (normally one) -----------
     uint32_t parity = 0;
-    for (int c_lo = lt_first; c_lo <= lt_last;) {
+    int myruns = 0;
+    for (int c_lo = fast ? lt_last + 1 : lt_first; c_lo <= lt_last;) {
         int c_hi = lt_last;
         if (S.off[lt_last + 1] - S.off[c_lo] > p.obs_cap) {
             int lo = c_lo, hi = lt_last;
@@ -674,9 +806,12 @@ k_sweep_fused(const FusedParams p)
                 for (int u = 0; u < 4; ++u) {
                     const int i = base + u * 32 + lane;
                     if (i < wb) {
-                        const bool ok = dist2_rn(q_[u].x - wx_[u], q_[u].y - wy_[u]) <= r2_[u];
+                        const double d2 = dist2_rn(q_[u].x - wx_[u], q_[u].y - wy_[u]);
+                        const bool ok = d2 <= r2_[u];
                         if (ok) {
                             sbk[i] = h_[u];
+                            // certified slack of this label, in 1/65535 of dist_thr, rounded down (the grid search below leaves 0)
+                            if constexpr (CERT) if (p.stamp) srn[i] = (unsigned short)min(__double2int_rd((r2_[u] - d2) * p.marg_scale), 65535);
                             if (!ident && slt[i] >= 2) p.c[co + i] = h_[u];    // (with the identity renumbering c[] already holds it)
                         } else pend |= 1ull << (slot + u);
                     }
@@ -736,6 +871,7 @@ k_sweep_fused(const FusedParams p)
                         const int bk = fgrid_scan_pre(G, wx_[u], wy_[u], s_[u], n_[u], p_[u], id_[u], best, bid);
                         const bool far = bk < 0 || best > p.thr2_hi;      // amin > dist_thr (ICM_SLAM.py:172)
                         sbk[i] = far ? -1 : bid;                          // the label (index in the previous map)
+                        if constexpr (CERT) srn[i] = 0;                   // (no certificate for a searched label)
                         if (slt[i] >= 2) p.c[co + i] = far ? -1 : bid;    // the halo scan (lt == 1) is not owned
                     }
                 }
@@ -745,23 +881,28 @@ k_sweep_fused(const FusedParams p)
         __syncthreads();     // the labels of the whole chunk are visible to the pose threads
         FS_STAMP(6);
         // ---- phase B, pass 1 (thread pair per pose): runs of equal winners -> in-place run records --------
+        const bool stamping = CERT && p.stamp;
         if (!(p.skip & 2) && o < e) {
             // (the next observation is fetched before the current one is consumed; the body-frame moments of the scan are
-            //  static and come from k_body_moments)
+            //  static and come from k_body_moments).  When certificates are stamped, srn[] holds each observation's slack
+            //  (16 bits) on entry; a run head leaves with beams | (least slack of the run >> 8) << 8.
             int run_start = o, bk = sbk[o];
             double2 b = sb[o];
+            int sl = stamping ? srn[o] : 0, rsl = 65535;
             double Sbx = 0.0, Sby = 0.0;
             for (int i = o; i < e; ++i) {
                 const int inx = min(i + 1, e - 1);
                 const double2 bn = sb[inx];
                 const int bkn = sbk[inx];
+                const int sln = stamping ? srn[inx] : 0;
                 Sbx += b.x; Sby += b.y;
+                rsl = min(rsl, sl);
                 if (i + 1 == e || bkn != bk) {
                     sb[run_start] = make_double2(Sbx, Sby);
-                    srn[run_start] = (unsigned short)(i + 1 - run_start);
-                    run_start = i + 1; Sbx = 0.0; Sby = 0.0;
+                    srn[run_start] = stamping ? (unsigned short)((i + 1 - run_start) | (rsl & 0xff00)) : (unsigned short)(i + 1 - run_start);
+                    run_start = i + 1; Sbx = 0.0; Sby = 0.0; rsl = 65535;
                 }
-                b = bn; bk = bkn;
+                b = bn; bk = bkn; sl = sln;
             }
         }
         FS_STAMP(7);
@@ -769,21 +910,31 @@ k_sweep_fused(const FusedParams p)
         {
             const double2 pq = mine ? S.pp[qli] : make_double2(0.0, 0.0), rc = mine ? S.rsc[qli] : make_double2(0.0, 1.0);
             const double px = pq.x, py = pq.y, st = rc.x, ct = rc.y;
+            const int nmask = stamping ? 0xff : 0xffff;       // (beams <= 255 whenever certificates are stamped: checked on the host)
             int i = (p.skip & 6) ? e : o;
-            int n = 0, bk = -1;
-            double2 sxy = make_double2(0.0, 0.0), lm = make_double2(0.0, 0.0);
+            int nw = 0, bk = -1;
+            double2 sxy = make_double2(0.0, 0.0), lm = make_double2(0.0, 0.0), lg = make_double2(0.0, 0.0);
             if (i < e) {
-                n = srn[i]; bk = sbk[i]; sxy = sb[i];
-                if (bk >= 0) lm = __ldg(reinterpret_cast<const double2*>(p.lmrec + bk));
+                nw = srn[i]; bk = sbk[i]; sxy = sb[i];
+                if (bk >= 0) {
+                    const double2* rp = reinterpret_cast<const double2*>(p.lmrec + bk);
+                    lm = __ldg(rp);
+                    if (stamping) lg = __ldg(rp + 1);
+                }
             }
             while (__any_sync(FULLMASK, i < e)) {
                 const bool act = i < e;
+                const int n = nw & nmask;
                 const int i2 = i + n;                     // the next run's record and landmark are fetched first
-                int n2 = 0, bk2 = -1;
-                double2 sxy2 = make_double2(0.0, 0.0), lm2 = make_double2(0.0, 0.0);
+                int nw2 = 0, bk2 = -1;
+                double2 sxy2 = make_double2(0.0, 0.0), lm2 = make_double2(0.0, 0.0), lg2 = make_double2(0.0, 0.0);
                 if (act && i2 < e) {
-                    n2 = srn[i2]; bk2 = sbk[i2]; sxy2 = sb[i2];
-                    if (bk2 >= 0) lm2 = __ldg(reinterpret_cast<const double2*>(p.lmrec + bk2));
+                    nw2 = srn[i2]; bk2 = sbk[i2]; sxy2 = sb[i2];
+                    if (bk2 >= 0) {
+                        const double2* rp = reinterpret_cast<const double2*>(p.lmrec + bk2);
+                        lm2 = __ldg(rp);
+                        if (stamping) lg2 = __ldg(rp + 1);
+                    }
                 }
                 const bool matched = act && bk >= 0;
                 const double dn = (double)n;
@@ -799,9 +950,28 @@ k_sweep_fused(const FusedParams p)
                     M.Mxx = fma(yx, sxy.x, M.Mxx); M.Mxy = fma(yx, sxy.y, M.Mxy);
                     M.Myx = fma(yy, sxy.x, M.Myx); M.Myy = fma(yy, sxy.y, M.Myy);
                 }
-                if (matched && qowned && !(p.skip & 8)) stat_add(S, p, bk, rwx - dn * yx, rwy - dn * yy, n);   // sum of (obs - landmark)
-                i = i2; n = n2; bk = bk2; sxy = sxy2; lm = lm2;
+                stat_add(S, p, matched && qowned && !(p.skip & 8), bk, rwx - dn * yx, rwy - dn * yy, n);   // sum of (obs - landmark)
+                if constexpr (CERT) if (stamping && act) {
+                    // the run cache: this half's records in order, from its end of the scan's slice.  The landmark's odometer is
+                    // rounded DOWN and the slack was rounded down, so the certificate errs on the side of the full path.
+                    const int gi = sub == 0 ? co + so + myruns : co + se - 1 - myruns;
+                    const float slack = bk >= 0 ? __double2float_rd((double)(nw >> 8) * p.slack_unit) : 0.0f;
+                    p.rsum[gi] = sxy;
+                    p.rmeta[gi] = make_int4(bk, n, __float_as_int(__double2float_rd(lg.y)), __float_as_int(slack));
+                    ++myruns;
+                }
+                i = i2; nw = nw2; bk = bk2; sxy = sxy2; lm = lm2; lg = lg2;
             }
+        }
+        if constexpr (CERT) {     // stamp the scans of this chunk
+            const int rpart = __shfl_xor_sync(FULLMASK, myruns, 1);
+            if (mine && sub == 0 && p.stamp) {
+                const bool pin = qt == 0 && p.first;
+                p.rcnt[qt] = myruns | (rpart << 16);
+                p.echk[qt] = epoch;
+                p.xchk[qt] = pin ? p.x0[0] : S.xs[0][qli]; p.xchk[p.ldchk + qt] = pin ? p.x0[1] : S.xs[1][qli]; p.xchk[2 * p.ldchk + qt] = pth_;
+            }
+            myruns = 0;
         }
         FS_STAMP(8);
         c_lo = c_hi + 1;

@@ -94,6 +94,12 @@ struct icmslam_handle {
     int split = 1, solve_occ = 768;      // split mode: association + moments in k_sweep_fused, pose solve in k_pose_solve
     double* d_dyn = nullptr;              // 6 x T landmark moments of each scan (split mode)
     double* d_sc = nullptr;               // 2 x (2 x T): sin/cos of the input headings, then of the new odd headings (split mode)
+    // label certificates + run cache (split mode, fused.cuh)
+    // host-memspace sweeps: copy of the map returned by the last one (a caller that feeds it back continues the device-side
+    // map chain: grid, hints and labels stay valid, sensors.py:315 `mapa_viejo = mapa_refinado`)
+    std::vector<double> last_map_host; int last_map_L = -1;
+    int use_cert = 0;                     // experimental (ICMSLAM_CERT=1): see fused.cuh "Label certificates" and profiles/README.md
+    double2* d_rsum = nullptr; int4* d_rmeta = nullptr; int* d_rcnt = nullptr; int* d_echk = nullptr; double* d_xchk = nullptr;
     // time-segment partition (icmslam_set_segment): this handle owns columns [seg_lo, seg_hi) of its T columns
     int seg_lo = 0, seg_hi = 0, seg_first = 1, seg_last = 1;
     double* d_newraw = nullptr;   // 2 x Lcap: means of the sweep's new labels (zero elsewhere)
@@ -158,10 +164,11 @@ static void free_dataset(icmslam_handle* h)
     DFREE(h->d_off); DFREE(h->d_beam); DFREE(h->d_scan_of); DFREE(h->d_d); DFREE(h->d_bx); DFREE(h->d_by);
     DFREE(h->d_c); DFREE(h->d_keys_out); DFREE(h->d_iota); DFREE(h->d_sorted); DFREE(h->d_seen_x); DFREE(h->d_seen_y);
     DFREE(h->d_nfar); DFREE(h->d_flag); DFREE(h->d_prefix); DFREE(h->d_x);
-    DFREE(h->d_inc); DFREE(h->d_bm); DFREE(h->d_dyn); DFREE(h->d_sc); DFREE(h->d_x2); DFREE(h->d_far_list); DFREE(h->d_blk_far); DFREE(h->d_blk_prefix); DFREE(h->d_bxy);
+    DFREE(h->d_inc); DFREE(h->d_bm); DFREE(h->d_dyn); DFREE(h->d_sc); DFREE(h->d_rsum); DFREE(h->d_rmeta); DFREE(h->d_rcnt); DFREE(h->d_echk); DFREE(h->d_xchk); DFREE(h->d_x2); DFREE(h->d_far_list); DFREE(h->d_blk_far); DFREE(h->d_blk_prefix); DFREE(h->d_bxy);
     drop_graphs(h);
     h->grid_map = nullptr;
     h->hint_map = nullptr;
+    h->last_map_L = -1;
     h->fused_ok = false;
     h->extracted = false;
     h->n = 0;
@@ -367,6 +374,7 @@ extern "C" int icmslam_load(icmslam_handle* h, const double* scans, int32_t B, i
         h->tile_half = v; h->tile_tpp = tpp; h->tile_occ = occ; h->tile_own = 2 * v - 2;
         { const char* es = getenv("ICMSLAM_SPLIT"); if (es) h->split = atoi(es) != 0; }
         { const char* es = getenv("ICMSLAM_SOLVE_OCC"); if (es) h->solve_occ = atoi(es); }
+        { const char* es = getenv("ICMSLAM_CERT"); if (es) h->use_cert = atoi(es) != 0; }
     }
     h->seg_lo = 0; h->seg_hi = T; h->seg_first = 1; h->seg_last = 1;
     h->n_tiles = nblk(T, h->tile_own);
@@ -449,6 +457,12 @@ extern "C" int icmslam_extract(icmslam_handle* h)
     k_interleave<<<nblk((int64_t)n, 256), 256, 0, h->stream>>>(h->d_bx, h->d_by, (int64_t)n, h->d_bxy);
     CK(cudaGetLastError());
     DFREE(h->d_bm); DFREE(h->d_dyn); DFREE(h->d_sc);
+    DFREE(h->d_rsum); DFREE(h->d_rmeta); DFREE(h->d_rcnt); DFREE(h->d_echk); DFREE(h->d_xchk);
+    CK(dalloc(&h->d_rsum, n + 2)); CK(dalloc(&h->d_rmeta, n + 2)); CK(dalloc(&h->d_rcnt, (size_t)T));
+    CK(dalloc(&h->d_echk, (size_t)T)); CK(dalloc(&h->d_xchk, (size_t)3 * T));
+    CK(cudaMemsetAsync(h->d_echk, 0xff, (size_t)T * sizeof(int), h->stream));       // epoch -1: no scan holds a certificate
+    CK(cudaMemsetAsync(h->d_rcnt, 0, (size_t)T * sizeof(int), h->stream));
+    CK(cudaMemsetAsync(h->d_xchk, 0, (size_t)3 * T * sizeof(double), h->stream));
     CK(dalloc(&h->d_sc, (size_t)4 * T));
     CK(cudaMemsetAsync(h->d_sc, 0, (size_t)4 * T * sizeof(double), h->stream));
     CK(dalloc(&h->d_bm, (size_t)5 * T));
@@ -536,6 +550,7 @@ extern "C" int icmslam_set_landmarks_actuales(icmslam_handle* h, int32_t lact)
     CK(cudaGetLastError());
     h->grid_map = nullptr;
     h->hint_map = nullptr;
+    h->last_map_L = -1;
     h->lact_host = lact;
     h->lact_dirty = false;
     return ICMSLAM_OK;
@@ -638,6 +653,7 @@ __global__ void k_sweep_begin(DevState* st, TailState* ts, int L_in)
     st->n_far_scans = 0;
     st->newton_iters = 0ull;
     st->solved = 0ull;
+    st->cert_tiles = 0;
 }
 
 static int status_from_state(const DevState* s)
@@ -710,6 +726,14 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
     P.st = st; P.geom = h->d_fg_geom; P.cell_start = h->d_fg_start; P.gpts = h->d_fg_pts; P.gidx = h->d_fg_idx;
     P.lmrec = h->d_lmrec; P.remap = h->d_remap;
     { const char* eh = getenv("ICMSLAM_HINTS"); P.hints = (h->hint_map == h->d_map_in && !(eh && atoi(eh) == 0)) ? 1 : 0; }
+    const bool cert_able = h->use_cert && h->split && !h->coop_tail && h->B <= 255;
+    P.cert = (P.hints && cert_able) ? 1 : 0;
+    P.stamp = cert_able ? 1 : 0;
+    P.rho = h->dcfg.rmax * (1.0 + 1e-9);
+    P.marg_scale = (1.0 - 1e-9) * 65535.0 / (2.0 * sqrt(h->thr2_hi) * h->dcfg.dist_thr);
+    P.slack_unit = (1.0 - 1e-9) * h->dcfg.dist_thr / 256.0;
+    P.rsum = h->d_rsum; P.rmeta = h->d_rmeta; P.rcnt = h->d_rcnt; P.echk = h->d_echk;
+    P.xchk = h->d_xchk; P.ldchk = T;
     P.c = h->d_c; P.fsum_x = h->d_fsum_x; P.fsum_y = h->d_fsum_y; P.cnt = h->d_cnt;
     P.far_list = h->d_far_list; P.ts = h->d_ts; P.blk_far = h->d_blk_far;
     P.obs_cap = h->obs_cap; P.iters = (o.reserved & 1) ? &st->newton_iters : nullptr;
@@ -746,6 +770,19 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
         double tot = 0; for (int k = 1; k < 18; ++k) tot += acc[k];
         fprintf(stderr, "[prof] %d blocks, mean cycles per block %.0f\n", h->n_tiles, tot / h->n_tiles);
         for (int k = 1; k < 18; ++k) fprintf(stderr, "[prof]   %-18s %8.0f  %5.1f%%\n", nm[k], acc[k] / h->n_tiles, 100.0 * acc[k] / tot);
+        {   // the certified attempt (stamps 18..23), over the tiles that went through it
+            double a2[6] = {0}; int nfast = 0;
+            for (int b = 0; b < h->n_tiles; ++b) {
+                const long long* q = &hp[(size_t)b * 24];
+                if (!q[23]) continue;
+                ++nfast;
+                a2[0] += (double)(q[18] - q[1]); a2[1] += (double)(q[19] - q[18]); a2[2] += (double)(q[20] - q[19]);
+                a2[3] += (double)(q[21] - q[20]); a2[4] += (double)(q[22] - q[21]); a2[5] += (double)(q[23] - q[22]);
+            }
+            static const char* n2[6] = {"proj+cert loads", "epoch vote", "scan", "records in", "landmarks in", "moments"};
+            fprintf(stderr, "[prof] certified attempts: %d tiles\n", nfast);
+            for (int k = 0; k < 6 && nfast; ++k) fprintf(stderr, "[prof]   %-18s %8.0f\n", n2[k], a2[k] / nfast);
+        }
     }
     k_tail_scan<<<1, 1024, 0, s>>>(h->d_blk_far, h->n_tiles, h->d_blk_prefix, st, h->d_ts, L, h->d_bb);
     CK(cudaGetLastError());
@@ -988,10 +1025,23 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
         xin = h->d_x; ldin = T;
         xout = h->d_x2; ldout = T;
     }
-    if (L_in > 0)
-        CK(cudaMemcpy2DAsync(h->d_map_in, (size_t)L * 8, map_in, (size_t)ld_map_in * 8, (size_t)L_in * 8, 2, cudaMemcpyDefault, s));
-    h->grid_map = nullptr;
-    h->hint_map = nullptr;
+    bool continued = false;
+    if (memspace == ICMSLAM_HOST && L_in > 0 && L_in == h->last_map_L && h->grid_map != nullptr && h->grid_map == h->d_map_out &&
+        memcmp(map_in, h->last_map_host.data(), (size_t)L_in * 8) == 0 &&
+        memcmp(map_in + ld_map_in, h->last_map_host.data() + L_in, (size_t)L_in * 8) == 0) {
+        // the caller hands back the map the previous sweep returned: it is already on the device, with its grid and hints
+        double* t = h->d_map_in; h->d_map_in = h->d_map_out; h->d_map_out = t;
+        h->grid_map = h->d_map_in;
+        if (h->hint_map) h->hint_map = h->d_map_in;
+        continued = true;
+    }
+    h->last_map_L = -1;
+    if (!continued) {
+        if (L_in > 0)
+            CK(cudaMemcpy2DAsync(h->d_map_in, (size_t)L * 8, map_in, (size_t)ld_map_in * 8, (size_t)L_in * 8, 2, cudaMemcpyDefault, s));
+        h->grid_map = nullptr;
+        h->hint_map = nullptr;
+    }
     const bool own_out = (memspace == ICMSLAM_HOST || !map_out);
     int rc = sweep_core(h, xin, ldin, xout, ldout, x0, o, L_in, own_out ? h->d_map_out : map_out, own_out ? L : cap_out,
                         own_out ? (int64_t)L : ld_map_out);
@@ -1008,6 +1058,12 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
             if (w > 0) {
                 CK(cudaMemcpy2DAsync(map_out, (size_t)ld_map_out * 8, h->d_map_out, (size_t)L * 8, (size_t)w * 8, 2, cudaMemcpyDeviceToHost, s));
                 CK(cudaStreamSynchronize(s));
+                if (w == newL) {       // remember what the caller received (see `continued` above)
+                    h->last_map_host.resize((size_t)2 * newL);
+                    memcpy(h->last_map_host.data(), map_out, (size_t)newL * 8);
+                    memcpy(h->last_map_host.data() + newL, map_out + ld_map_out, (size_t)newL * 8);
+                    h->last_map_L = newL;
+                }
             }
         }
         if (L_out) *L_out = newL;
@@ -1091,6 +1147,7 @@ extern "C" int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const
     CK(cudaSetDevice(h->cfg.device));
     const int T = h->T, L = h->Lcap;
     cudaStream_t s = h->stream;
+    h->last_map_L = -1;
     if (h->first_empty) return ICMSLAM_EMPTY_FIRST_SCAN;
     if (h->last_empty && T > 1) return ICMSLAM_ERR_EMPTY_LAST;
     if (x) {
@@ -1137,7 +1194,7 @@ extern "C" int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const
                 slot->tol = o.newton_tol; slot->maxit = o.newton_maxit;
             }
             CK(cudaGraphLaunch(slot->exec, s));
-            h->n_launch += h->coop_tail ? 5 : 13;    // kernels of this library inside the graph
+            h->n_launch += (h->coop_tail ? 5 : 13) + (h->split ? 2 : 0);    // kernels of this library inside the graph
             h->grid_map = h->d_map_out;
             h->hint_map = h->d_map_out;
             h->timed_fused = true;
@@ -1201,6 +1258,7 @@ extern "C" int icmslam_seg_begin(icmslam_handle* h, const double* x0, const icms
     default_opts(o, opts);
     if (!(o.fused && o.schedule == ICMSLAM_SCHED_REDBLACK && o.solver == ICMSLAM_SOLVER_NEWTON && o.map_view == ICMSLAM_VIEW_PREV))
         return ICMSLAM_ERR_UNSUPPORTED;     // only the restated parallel sweep partitions in time
+    h->last_map_L = -1;
     CK(cudaSetDevice(h->cfg.device));
     const int T = h->T, L = h->Lcap;
     cudaStream_t s = h->stream;
@@ -1320,8 +1378,11 @@ extern "C" int icmslam_get_sweep_stats(icmslam_handle* h, int64_t* stats, int32_
     int rc = sync_state(h);
     if (rc) return rc;
     const DevState* s = h->h_st;
-    int64_t v[8] = {(int64_t)s->newton_iters, s->n_far_scans, s->raw_l, s->kept, s->new_l, s->n_ind, s->lsearch, s->status};
-    for (int i = 0; i < n && i < 8; ++i) stats[i] = v[i];
+    TailState hts;
+    CK(cudaMemcpy(&hts, h->d_ts, sizeof(TailState), cudaMemcpyDeviceToHost));
+    int64_t v[12] = {(int64_t)s->newton_iters, s->n_far_scans, s->raw_l, s->kept, s->new_l, s->n_ind, s->lsearch, s->status, s->cert_tiles,
+                     hts.epoch, (int64_t)(hts.G * 1e12), hts.remap_identity};
+    for (int i = 0; i < n && i < 12; ++i) stats[i] = v[i];
     return ICMSLAM_OK;
 }
 

@@ -33,14 +33,18 @@ struct TailState {
     int degenerate;     // bounding box smaller than dist_thr: the reference's zero-distance rule matters
     int far_total;      // scans with far observations in THIS handle's segment
     int label_base;     // such scans in the segments before this one (0 on a single GPU)
-    int remap_identity; // the filter kept every landmark of the previous map in place and nothing was added
-    int pad[2];
+    int remap_identity; // the filter kept every landmark of the previous map in place and no new label survived: labels below
+                        // lsearch keep their meaning (labels created in the sweep may have come and gone)
+    int epoch;          // certificates (fused.cuh) stamped in another epoch are void: bumped whenever landmark indices change
+    int pad;
+    double G;           // (unused)
+    unsigned long long drift_bits;
 };
 
 // A landmark as the fused kernel reads it by label: position and the squared radius inside which an
 // observation is PROVABLY nearest to it and inside the gate (see hint_radius2).
 struct __align__(32) LmRec {
-    double x, y, r2, pad;
+    double x, y, r2, g;     // g: odometer of this record (label certificates, fused.cuh): total motion of (x, y) plus loss of radius
 };
 
 // r2 = min(thr2_hi, (nnd/2)^2 (1 - 2^-30)) with nnd a lower bound of the distance to the nearest other
@@ -198,19 +202,27 @@ k_tail_finalize(DevState* st, TailState* ts, const double* __restrict__ kx, cons
 {
     if (ts->n_ind != 0 || ts->degenerate) return;   // k_tail_slow takes over
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= Lcap) return;
     const int newL = st->kept;
-    const double c = r < newL ? kc[r] : 0.0;
-    const double mx = r < newL ? mul_rn(kx[r], c) / c : 0.0, my = r < newL ? mul_rn(ky[r], c) / c : 0.0;
-    if (r < cap_out) { map_out[r] = mx; map_out[ld_out + r] = my; }
-    counts_state[r] = c;
-    LmRec rec;
-    rec.x = mx; rec.y = my; rec.r2 = r < newL ? hint_radius2(nnd2[r], thr1sq, thr2_hi) : 0.0; rec.pad = 0.0;
-    lmrec[r] = rec;
-    remap[r] = (r < st->raw_l && kflag[r]) ? kpos[r] : -1;      // label of this sweep -> index in the new map
-    if (r == 0) {
-        st->new_l = newL; st->lact = newL; st->n_ind = 0;
-        ts->remap_identity = (newL == st->lsearch && st->raw_l == st->lsearch) ? 1 : 0;
+    double dl = 0.0;
+    if (r < Lcap) {
+        const double c = r < newL ? kc[r] : 0.0;
+        const double mx = r < newL ? mul_rn(kx[r], c) / c : 0.0, my = r < newL ? mul_rn(ky[r], c) / c : 0.0;
+        if (r < cap_out) { map_out[r] = mx; map_out[ld_out + r] = my; }
+        counts_state[r] = c;
+        LmRec rec;
+        rec.x = mx; rec.y = my; rec.r2 = r < newL ? hint_radius2(nnd2[r], thr1sq, thr2_hi) : 0.0; rec.g = 0.0;
+        if (r < newL) {       // how far this landmark's record moved (position in the 1-norm, plus any loss of hint radius)
+            const LmRec old = lmrec[r];
+            dl = fabs(mx - old.x) + fabs(my - old.y) + fmax(sqrt(old.r2) - sqrt(rec.r2), 0.0);
+            if (!(dl >= 0.0)) dl = INFINITY;
+            rec.g = old.g + dl * (1.0 + 1e-9);
+        }
+        lmrec[r] = rec;
+        remap[r] = (r < st->raw_l && kflag[r]) ? kpos[r] : -1;      // label of this sweep -> index in the new map
+        if (r == 0) { st->new_l = newL; st->lact = newL; st->n_ind = 0; }
+        // every old label survived in place (its position in the scan of the keep flags is its index) and nothing was added
+        if (r == max(st->lsearch - 1, 0))
+            ts->remap_identity = (st->lsearch > 0 && newL == st->lsearch && kflag[r] && kpos[r] == r) ? 1 : 0;
     }
 }
 
@@ -232,7 +244,7 @@ k_lmrec_build(const double* __restrict__ mx, const double* __restrict__ my, cons
         best = fmin(best, dist2_rn(p.x - xj, p.y - yj));      // (a coincident landmark gives 0: its hints are never trusted)
     }
     LmRec rec;
-    rec.x = xj; rec.y = yj; rec.r2 = hint_radius2(best, thr1sq, thr2_hi); rec.pad = 0.0;
+    rec.x = xj; rec.y = yj; rec.r2 = hint_radius2(best, thr1sq, thr2_hi); rec.g = 0.0;
     lmrec[j] = rec;
 }
 
@@ -389,7 +401,7 @@ __device__ void tail_slow_body(DevState* st, TailState* ts, double dist_thr, dou
         __syncthreads();
         for (int r = tid; r < Lcap; r += nth) {       // landmark records of the merged map
             LmRec rec;
-            rec.x = 0.0; rec.y = 0.0; rec.r2 = 0.0; rec.pad = 0.0;
+            rec.x = 0.0; rec.y = 0.0; rec.r2 = 0.0; rec.g = 0.0;
             if (r < newL) {
                 const double x = map_out[r], y = map_out[ld_out + r];
                 const int c = fgrid_cell(g, x, y);
@@ -413,6 +425,12 @@ k_tail_slow(DevState* st, TailState* ts, double dist_thr, double* kx, double* ky
             int max_cells, FGeom* geom, int* cell_cnt, int* cell_start, double2* pts, int* gidx,
             const int* kflag, const int* kpos, double thr1sq, double thr2_hi, LmRec* lmrec, int* remap)
 {
+    // certificates: void every one of them when landmark indices changed
+    // (k_tail_finalize has completed: this launch follows it on the stream)
+    if (threadIdx.x == 0) {
+        const bool fast = ts->n_ind == 0 && !ts->degenerate;
+        if (!(fast && ts->remap_identity)) ts->epoch += 1;
+    }
     if (ts->n_ind == 0 && !ts->degenerate) return;
     tail_slow_body(st, ts, dist_thr, kx, ky, kc, parent, nn, ind_flag, ind_pos, ind, lab, used, rank, ox, oy, oc, map_out, cap_out, ld_out,
                    counts_state, Lcap, max_cells, geom, cell_cnt, cell_start, pts, gidx, kflag, kpos, thr1sq, thr2_hi, lmrec, remap);

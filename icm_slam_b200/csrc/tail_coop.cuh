@@ -231,7 +231,7 @@ k_tail_coop(const TailCoopParams p)
             if (r < p.cap_out) { p.map_out[r] = mx; p.map_out[p.ld_out + r] = my; }
             p.counts_state[r] = c;
             LmRec rec;
-            rec.x = mx; rec.y = my; rec.r2 = r < K ? hint_radius2(p.nnd2[r], p.thr1sq, p.thr2_hi) : 0.0; rec.pad = 0.0;
+            rec.x = mx; rec.y = my; rec.r2 = r < K ? hint_radius2(p.nnd2[r], p.thr1sq, p.thr2_hi) : 0.0; rec.g = 0.0;
             p.lmrec[r] = rec;
             p.remap[r] = (r < raw_l && p.kflag[r]) ? p.kpos[r] : -1;
             if (r == 0) {

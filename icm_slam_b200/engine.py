@@ -243,9 +243,10 @@ class Engine:
         return raw[:, : rl.value].copy(), cnt[: rl.value].copy(), int(rl.value)
 
     def sweep_stats(self):
-        v = (C.c_int64 * 8)()
-        check(self.lib.icmslam_get_sweep_stats(self._h, v, 8), self._h)
-        keys = ["newton_iters", "n_far_scans", "raw_L", "kept", "new_L", "n_ind", "lsearch", "status"]
+        v = (C.c_int64 * 12)()
+        check(self.lib.icmslam_get_sweep_stats(self._h, v, 12), self._h)
+        keys = ["newton_iters", "n_far_scans", "raw_L", "kept", "new_L", "n_ind", "lsearch", "status", "cert_tiles", "cert_epoch",
+                "cert_G_pm", "stable_ids"]
         return dict(zip(keys, [int(t) for t in v]))
 
     # -- map utilities --------------------------------------------------------------------------

@@ -1,6 +1,5 @@
-"""Per-phase clock profile of the fused kernel (ICMSLAM_PROF=1, graphs off): prints the library's [prof] summary for the 3rd sweep."""
 import os, sys
-os.environ["ICMSLAM_GRAPH"] = "0"
+import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from icm_slam_b200.engine import Engine
@@ -13,8 +12,12 @@ eng.load(d["observations"], d["odometry"], d["velocities"], precondition=True)
 eng.extract()
 x0 = d["odometry"][:, 0].copy()
 eng.set_map(d["map_init"]); eng.set_poses(d["x_init"])
-for k in range(int(os.environ.get("WARM", "3"))):
-    eng.iterate(None, x0, 1)
-os.environ["ICMSLAM_PROF"] = "1"
-eng.iterate(None, x0, 1, timing=True)
-print("kernel ms", eng.kernel_ms())
+xp = d["x_init"]
+for k in range(12):
+    eng.iterate(None, x0, 1, timing=True)
+    st = eng.sweep_stats()
+    x = eng.get_poses()
+    print("sweep %2d  kernel %.3f ms  cert_tiles %6d  far scans %6d  L %d->%d  epoch %d  G %.3e  stable %d  max|dx| %.2e" % (
+        k + 1, eng.kernel_ms()[0], st["cert_tiles"], st["n_far_scans"], st["lsearch"], st["new_L"], st["cert_epoch"], st["cert_G_pm"] * 1e-12, st["stable_ids"],
+        np.abs(x - xp).max()), flush=True)
+    xp = x

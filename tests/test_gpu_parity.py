@@ -593,3 +593,55 @@ def test_offline_batch_path_through_the_reference_surface():
         assert len(cam) == 3 and cam[0] <= cam[2] <= cam[1]
         mapa_viejo = mapa_refinado.copy()
     assert mapa_refinado.shape == (2, 11)         # the notebook's 11 trees
+
+
+# ---- label certificates + run cache (fused.cuh): a certified sweep must equal the uncertified one bit for bit ----
+def _chain(z, odo, u, cfgd, map0, x_init, nsweeps, env):
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        e = _engine(_cfg(**cfgd), z, odo, u)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    e.set_map(map0)
+    e.set_poses(np.ascontiguousarray(x_init.copy()))
+    out = []
+    for k in range(nsweeps):
+        e.iterate(None, odo[:, 0], 1, fused=True)
+        st = e.sweep_stats()
+        out.append((e.get_poses().copy(), e.get_map().copy(), e.associations().copy(), st["cert_tiles"]))
+    e.close()
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gname", ["synth_a.npz", "synth_b.npz"])
+def test_certified_sweeps_equal_uncertified_synthetic(gname):
+    g = golden(gname)
+    z, odo, u = g["observations"].astype(np.float64), g["odometry"], g["velocities"]
+    cfgd = dict(L=int(g["cfg_L"]), cota=float(g["cfg_cota"]))
+    a = _chain(z, odo, u, cfgd, g["map_init"], g["x_init"], 8, {"ICMSLAM_CERT": "0"})
+    b = _chain(z, odo, u, cfgd, g["map_init"], g["x_init"], 8, {"ICMSLAM_CERT": "1"})
+    for k, (ra, rb) in enumerate(zip(a, b)):
+        assert np.array_equal(ra[2], rb[2]), k
+        assert np.array_equal(ra[0], rb[0]), k          # poses: bit for bit
+        assert np.array_equal(ra[1], rb[1]), k          # map: bit for bit
+        assert ra[3] == 0
+    assert any(r[3] > 0 for r in b), "no tile ever ran on certificates: %r" % ([r[3] for r in b],)
+
+
+@pytest.mark.gpu
+def test_certified_sweeps_equal_uncertified_c1():
+    g = golden("c1_ref.npz")
+    z, odo, u = c1_inputs()
+    a = _chain(z, odo, u, dict(CONFIG_ROS), g["p0_map"], g["p0_x"], 6, {"ICMSLAM_CERT": "0"})
+    b = _chain(z, odo, u, dict(CONFIG_ROS), g["p0_map"], g["p0_x"], 6, {"ICMSLAM_CERT": "1"})
+    for k, (ra, rb) in enumerate(zip(a, b)):
+        assert np.array_equal(ra[2], rb[2]), k
+        assert np.array_equal(ra[0], rb[0]), k
+        assert np.array_equal(ra[1], rb[1]), k
