@@ -560,24 +560,29 @@ k_sweep_fused(const FusedParams p)
     __syncthreads();
     FS_STAMP(1);
     // ---- per-pose projection parameters: thread tid <-> pose tb-2+tid --------------------------------
-    if (tid < FS_SLOTS) {
-        const int t = tb - 2 + tid;
-        if (t >= 0 && t < T) {
-            double px = S.xs[0][tid], py = S.xs[1][tid], th = S.xs[2][tid];
-            double st, ct, sh, ch;
-            if (t == 0 && p.first) {                             // scan 0 is projected with self.x0; x[:,0] is only a neighbour
-                sincos(th, &sh, &ch);
-                px = p.x0[0]; py = p.x0[1]; th = p.x0[2];
-                sincos(sub_rn(th, ICM_HALFPI), &st, &ct);
-            } else {
-                sincos(sub_rn(th, ICM_HALFPI), &st, &ct);        // make_rot: cos/sin of (theta - pi/2)
-                sh = ct; ch = -st;
+    // (split mode without certificates: deferred until the observations' bulk copy is in flight, see below)
+    auto proj_params = [&]() {
+        if (tid < FS_SLOTS) {
+            const int t = tb - 2 + tid;
+            if (t >= 0 && t < T) {
+                double px = S.xs[0][tid], py = S.xs[1][tid], th = S.xs[2][tid];
+                double st, ct, sh, ch;
+                if (t == 0 && p.first) {                             // scan 0 is projected with self.x0; x[:,0] is only a neighbour
+                    sincos(th, &sh, &ch);
+                    px = p.x0[0]; py = p.x0[1]; th = p.x0[2];
+                    sincos(sub_rn(th, ICM_HALFPI), &st, &ct);
+                } else {
+                    sincos(sub_rn(th, ICM_HALFPI), &st, &ct);        // make_rot: cos/sin of (theta - pi/2)
+                    sh = ct; ch = -st;
+                }
+                S.pp[tid] = make_double2(px, py); S.rsc[tid] = make_double2(st, ct);
+                if (!SPLIT) { S.sn[tid] = sh; S.cs[tid] = ch; }
+                else if (tid >= 2 ? t < p.t_hi : blockIdx.x == 0) { p.sc[t] = sh; p.sc[p.ldsc + t] = ch; }
             }
-            S.pp[tid] = make_double2(px, py); S.rsc[tid] = make_double2(st, ct);
-            if (!SPLIT) { S.sn[tid] = sh; S.cs[tid] = ch; }
-            else if (tid >= 2 ? t < p.t_hi : blockIdx.x == 0) { p.sc[t] = sh; p.sc[p.ldsc + t] = ch; }
         }
-    }
+    };
+    const bool proj_early = !SPLIT || p.cert != 0;
+    if (proj_early) proj_params();
     // ---- pose slots: slot q is worked by the thread pair (2q, 2q+1) in phase B and solved by thread q -----
     //      slots 0..63: odd poses tb-1+2j (slot 0 = halo), slots 64..127: even poses tb+2j (slot 127 spare)
     const int q = tid / TPP, sub = tid % TPP, half = sub & 1;   // half = the lane's role in the solve (x / y rows)
@@ -621,9 +626,10 @@ k_sweep_fused(const FusedParams p)
                 ok_all = p.echk[qt] == epoch && dpose < 1e30;
             }
         }
-        __syncthreads();        // (the projection parameters are in place)
+        if (p.cert) __syncthreads();        // (the projection parameters are in place)
         FS_STAMP(18);
-        if (__syncthreads_and(ok_all && p.cert)) {
+        // (without certificates no barrier is needed here: nothing was written to shared memory since the last one)
+        if (p.cert && __syncthreads_and(ok_all)) {
             FS_STAMP(19);
             // The slot's cached run records, then the landmark records they name, are brought into shared memory with
             // 16-byte asynchronous copies (every copy of a stage is in flight at once: one memory round trip per stage,
@@ -752,6 +758,7 @@ k_sweep_fused(const FusedParams p)
             e = min(o + h1, se);
         }
         for (int i = o; i < e; ++i) slt[i] = (unsigned char)qli;     // (while the bulk copies are in flight)
+        if (!proj_early && c_lo == lt_first) proj_params();          // (likewise; the barrier below publishes them)
         FS_STAMP(3);
         mbar_wait(mb, parity);
         parity ^= 1u;

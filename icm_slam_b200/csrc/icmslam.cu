@@ -750,6 +750,7 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
     fused_variant(h->tile_half, h->tile_tpp, h->tile_occ, h->split != 0)<<<h->n_tiles, 2 * h->tile_tpp * h->tile_half, h->fused_smem, s>>>(P);
     if (h->split) {
         CK(cudaGetLastError());
+        if (timing) CK(cudaEventRecord(h->ev[2], s));      // (split mode: ev[0]..ev[2] = k_sweep_fused, ev[2]..ev[1] = the two solve kernels)
         const int n_pairs = (h->seg_hi - h->seg_lo) / 2 + 2;      // poses of one colour (incl. the odd halo pose of a segment)
         solve_variant(0, h->solve_occ)<<<nblk(2 * n_pairs, SOLVE_THREADS), SOLVE_THREADS, 0, s>>>(P);
         CK(cudaGetLastError());
@@ -1314,8 +1315,13 @@ extern "C" int icmslam_get_kernel_ms(icmslam_handle* h, double* out2)
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->stream));
     float a = 0.f, b = 0.f;
-    CK(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
-    if (!h->timed_fused) CK(cudaEventElapsedTime(&b, h->ev[2], h->ev[3]));
+    if (h->timed_fused && h->split) {      // fused path, split mode: k_sweep_fused | k_solve_colour x 2
+        CK(cudaEventElapsedTime(&a, h->ev[0], h->ev[2]));
+        CK(cudaEventElapsedTime(&b, h->ev[2], h->ev[1]));
+    } else {
+        CK(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
+        if (!h->timed_fused) CK(cudaEventElapsedTime(&b, h->ev[2], h->ev[3]));
+    }
     out2[0] = a; out2[1] = b;
     return ICMSLAM_OK;
 }

@@ -5,6 +5,7 @@ buffers used in place).  All numerics happen in libicmslam.so; this file only ma
 """
 from __future__ import annotations
 
+import os
 import ctypes as C
 
 import numpy as np
@@ -241,6 +242,11 @@ class Engine:
         rl = C.c_int32()
         check(self.lib.icmslam_get_raw_map(self._h, _ptr(raw)[0], self.L, self.L, _ptr(cnt)[0], C.byref(rl), HOST), self._h)
         return raw[:, : rl.value].copy(), cnt[: rl.value].copy(), int(rl.value)
+
+    def fused_split(self):
+        """True when the fused path runs as k_sweep_fused + two k_solve_colour launches (the default; ICMSLAM_SPLIT=0 selects the
+        single-launch kernel)."""
+        return os.environ.get("ICMSLAM_SPLIT", "1") != "0"
 
     def sweep_stats(self):
         v = (C.c_int64 * 12)()

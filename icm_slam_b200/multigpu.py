@@ -355,7 +355,11 @@ def bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, p
         B_sweep = sweep_bytes(T, n_tot, L_true)
         peak, peak_src = peaks()
         # the dominant kernel's share of the sweep on one rank: its segment's bytes over its time
-        seg_bytes = sweep_bytes(sol.t_hi - sol.t_lo, n_local, L_true)
+        Tseg = sol.t_hi - sol.t_lo
+        if sol.engine.fused_split():     # k_sweep_fused's own share (poses, offsets, observations, map in; labels, statistics out)
+            seg_bytes = 24 * Tseg + 4 * (Tseg + 1) + 16 * n_local + 16 * L_true + 4 * n_local + 24 * L_true
+        else:
+            seg_bytes = sweep_bytes(Tseg, n_local, L_true)
         achieved = seg_bytes / (float(k_ms.item()) * 1e-3) / 1e9
         sweep_achieved = B_sweep / (ms * 1e-3) / 1e9
         out = {
