@@ -649,3 +649,60 @@ def test_certified_sweeps_equal_uncertified_c1():
         assert np.array_equal(ra[2], rb[2]), k
         assert np.array_equal(ra[0], rb[0]), k
         assert np.array_equal(ra[1], rb[1]), k
+
+
+# ---- C5: independent trajectories, one handle each (batch.py) == the same trajectories run one at a time ---------
+def test_trajectory_batch_equals_individual_runs():
+    from icm_slam_b200.batch import TrajectoryBatch
+    from icm_slam_b200.synthetic import make_synthetic
+    cfgd = dict(L=2 * 256 + 64, cota=20.0)
+    cfg = _cfg(**cfgd)
+    data = [make_synthetic(256, T=1024, seed=20181 + 100 + i) for i in range(5)]
+    world = 2
+    got = {}
+    for rank in range(world):                  # both ranks emulated on this GPU
+        b = TrajectoryBatch(cfg, rank, world, device=0)
+        for i in b.owned(len(data)):
+            d = data[i]
+            b.add(i, d["observations"], d["odometry"], d["velocities"], d["map_init"], d["x_init"])
+        b.iterate(4)
+        got.update(b.results())
+        b.close()
+    assert sorted(got) == list(range(len(data)))
+    for i, d in enumerate(data):
+        e = _engine(cfg, d["observations"], d["odometry"], d["velocities"])
+        e.set_map(d["map_init"])
+        e.set_poses(d["x_init"])
+        e.iterate(None, d["odometry"][:, 0], 4)
+        assert np.array_equal(e.get_poses(), got[i][0]) and np.array_equal(e.get_map(), got[i][1])
+        e.close()
+
+
+# ---- row f2: .mat -> filtrar_obs -> pass 0 -> N sweeps -> result files, in one call (offline.py) -------------------
+def test_run_offline_one_call_matches_stepwise(tmp_path):
+    import scipy.io as sio
+    from icm_slam_b200.offline import run_offline, save_result, load_result
+    from icm_slam_b200.icm import ICM_SLAM, Mapa, calc_cambio, precondicionar
+    raw, odo, u = c2_inputs()                                   # the raw log (datos_palomar1.mat layout)
+    path = str(tmp_path / "datos.mat")
+    sio.savemat(path, {"datos": {"observaciones": raw, "odometria": odo, "control": u}})
+    cfg = _cfg(N=3)
+    res = run_offline(path, cfg)
+    assert res["x"].shape == (3, raw.shape[1]) and res["cambios"].shape == (3, 3)
+    # stepwise: the filtered log is data_IJAC2018.mat (the dataset pair), then the facade's own calls
+    z1, _, _ = c1_inputs()
+    icm = ICM_SLAM(cfg, x0=odo[:, 0])
+    icm.load_data(Mapa(cfg), precondicionar(z1, cfg), u, odo)
+    mapa, x = icm.inicializar()
+    assert np.array_equal(np.array(mapa), res["mapa_inicial"]) and np.array_equal(np.array(x), res["x_inicial"])
+    mapa = np.array(mapa)
+    x = np.ascontiguousarray(np.array(x))
+    for k in range(3):
+        nuevo, x = icm.iterations_process_offline(mapa, x)
+        assert np.allclose(calc_cambio(nuevo, mapa, cfg), res["cambios"][k], rtol=0, atol=1e-12)
+        mapa = nuevo
+    assert np.max(np.abs(x - res["x"])[:2]) <= TOL_XY and np.max(np.abs(x - res["x"])[2]) <= TOL_TH
+    assert mapa.shape == res["mapa"].shape and np.max(np.abs(mapa - res["mapa"])) <= TOL_XY
+    for ext in ("mat", "npz"):
+        back = load_result(save_result(str(tmp_path / ("out." + ext)), res))
+        assert np.array_equal(back["x"], res["x"]) and np.array_equal(back["mapa"], res["mapa"])

@@ -125,3 +125,40 @@ def test_two_rank_exchange_gloo():
     for p in ps:
         p.join(timeout=60)
     assert all(r[1] == "ok" for r in res), res
+
+
+# ---- C5: a batch of independent trajectories shards round-robin with no data-path collective ----------------------
+def test_trajectory_batch_sharding_is_a_partition():
+    from icm_slam_b200.batch import owned_indices
+    for n, world in ((4096, 8), (10, 3), (5, 8), (0, 2)):
+        parts = [owned_indices(n, r, world) for r in range(world)]
+        flat = sorted(i for p in parts for i in p)
+        assert flat == list(range(n))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    with pytest.raises(ValueError):
+        owned_indices(4, 2, 2)
+
+
+def _gather_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from icm_slam_b200.batch import owned_indices, gather_results
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    local = {i: (np.full((3, 4), float(i)), np.full((2, 2), -float(i))) for i in owned_indices(7, rank, world)}
+    allr = gather_results(local)
+    q.put((rank, sorted(allr), all(float(allr[i][0][0, 0]) == float(i) for i in allr)))
+    dist.destroy_process_group()
+
+
+def test_trajectory_batch_gather_two_ranks_gloo():
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 400) + 37
+    ps = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+    for rank, keys, ok in got:
+        assert keys == list(range(7)) and ok
