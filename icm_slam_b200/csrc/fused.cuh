@@ -45,6 +45,9 @@
 #define FS_HASH (HALF >= 64 ? 256 : HALF >= 32 ? 128 : 64)   // landmark slots of the block-level statistics table
 #define FS_HASH_SHIFT (HALF >= 64 ? 24 : HALF >= 32 ? 25 : 26)
 #define FS_PROBES 8
+#ifndef FS_U
+#define FS_U 4                 // observations per lane in flight in phase A (pend bitmask: 64 / FS_U iterations per warp)
+#endif
 #define FS_MINBLK (OCC / FS_THREADS)   // OCC = resident threads per SM the kernel is compiled for (register budget = 65536 / OCC)
 
 struct FusedParams {
@@ -58,9 +61,13 @@ struct FusedParams {
     double x0[3];                         // self.x0 (sensors.py:131)
     const double* inc; int64_t ldinc;     // 3 x T odometry increments (see k_odo_increments)
     const double* u; int64_t ldu;         // 2 x T controls
-    const double* bm; int64_t ldbm;       // 5 x T static body-frame moments of each scan (k_body_moments)
-    double* dyn; int64_t lddyn;           // 6 x T landmark moments of each scan (split mode: k_sweep_fused -> k_solve_colour)
-    double* sc; double* scn; int64_t ldsc;   // 2 x T (sin, cos) of the input headings / of the new odd headings (split mode)
+    // Arrays that only the pose solve reads are stored COLOUR-MAJOR: pose t lives at cm(t) = (t & 1) * Th + (t >> 1), even poses
+    // first, so that a launch solving one colour reads contiguous memory (in time order it would use half of every sector).
+    int Th;                               // (T + 1) / 2
+    const double* bm; int64_t ldbm;       // 6 x T static body-frame moments of each scan + its beam count (k_body_moments), colour-major
+    const double* inc_cm; const double* u_cm;   // colour-major copies of inc (3 x T) and u (2 x T), leading dimension ldbm
+    double* dyn; int64_t lddyn;           // 6 x T landmark moments of each scan (split mode: k_sweep_fused -> k_solve_colour), colour-major
+    double* sc; double* scn; int64_t ldsc;   // 2 x T (sin, cos) of the input headings / of the new odd headings (split mode), colour-major
     // label certificates and the run cache (split mode; see "Label certificates" below)
     int cert;                             // certificates may be used this sweep (c[] and the stamps belong to this map chain)
     int stamp;                            // full passes stamp certificates and fill the run cache
@@ -111,18 +118,32 @@ __global__ void k_odo_increments(const double* __restrict__ odo, int64_t ldo, in
 // body-frame moment sums of every scan's kept beams: sum bx, sum by, sum bx^2, sum by^2, sum bx*by.  They do not depend on
 // the poses or the map, so they are formed once per dataset (one thread per scan, fixed order: the result does not depend
 // on any tiling) and the sweep kernel only reads them (40 B per pose).
-__global__ void __launch_bounds__(128)
-k_body_moments(const int* __restrict__ off, const double2* __restrict__ bxy, int T, double* __restrict__ bm, int64_t ld)
+__device__ __forceinline__ int64_t cm_index(int t, int Th) { return (int64_t)(t & 1) * Th + (t >> 1); }
+
+// rows x T array in time order -> colour-major (see FusedParams::Th)
+__global__ void k_to_colour_major(const double* __restrict__ src, int64_t lds, int rows, int T, double* __restrict__ dst, int64_t ldd)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
+    const int64_t c = cm_index(t, (T + 1) >> 1);
+    for (int r = 0; r < rows; ++r) dst[r * ldd + c] = src[r * lds + t];
+}
+
+__global__ void __launch_bounds__(128)
+k_body_moments(const int* __restrict__ off, const double2* __restrict__ bxy, int T, double* __restrict__ bm, int64_t ld)
+{
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t0 >= T) return;
+    const int t = t0;
     double Bx = 0.0, By = 0.0, Bxx = 0.0, Byy = 0.0, Bxy = 0.0;
     for (int i = off[t]; i < off[t + 1]; ++i) {
         const double2 b = bxy[i];
         Bx += b.x; By += b.y;
         Bxx = fma(b.x, b.x, Bxx); Byy = fma(b.y, b.y, Byy); Bxy = fma(b.x, b.y, Bxy);
     }
-    bm[t] = Bx; bm[ld + t] = By; bm[2 * ld + t] = Bxx; bm[3 * ld + t] = Byy; bm[4 * ld + t] = Bxy;
+    const int64_t c = cm_index(t, (T + 1) >> 1);      // colour-major, + the beam count as a sixth row
+    bm[c] = Bx; bm[ld + c] = By; bm[2 * ld + c] = Bxx; bm[3 * ld + c] = Byy; bm[4 * ld + c] = Bxy;
+    bm[5 * ld + c] = (double)(off[t + 1] - off[t]);
 }
 
 __device__ __forceinline__ double entrepi_fast(double a)
@@ -577,7 +598,7 @@ k_sweep_fused(const FusedParams p)
                 }
                 S.pp[tid] = make_double2(px, py); S.rsc[tid] = make_double2(st, ct);
                 if (!SPLIT) { S.sn[tid] = sh; S.cs[tid] = ch; }
-                else if (tid >= 2 ? t < p.t_hi : blockIdx.x == 0) { p.sc[t] = sh; p.sc[p.ldsc + t] = ch; }
+                else if (tid >= 2 ? t < p.t_hi : blockIdx.x == 0) { const int64_t c = cm_index(t, p.Th); p.sc[c] = sh; p.sc[p.ldsc + c] = ch; }
             }
         }
     };
@@ -596,8 +617,9 @@ k_sweep_fused(const FusedParams p)
     M.n = M.Bx = M.By = M.Bxx = M.Byy = M.Bxy = M.Yx = M.Yy = M.Mxx = M.Mxy = M.Myx = M.Myy = 0.0;
     if (qvalid && !SPLIT) {     // static body-frame moments of the slot's scan (in flight until the solve)
         M.n = (double)(S.off[qli + 1] - S.off[qli]);
-        M.Bx = __ldg(p.bm + qt); M.By = __ldg(p.bm + p.ldbm + qt); M.Bxx = __ldg(p.bm + 2 * p.ldbm + qt);
-        M.Byy = __ldg(p.bm + 3 * p.ldbm + qt); M.Bxy = __ldg(p.bm + 4 * p.ldbm + qt);
+        const double* bmq = p.bm + cm_index(qt, p.Th);
+        M.Bx = __ldg(bmq); M.By = __ldg(bmq + p.ldbm); M.Bxx = __ldg(bmq + 2 * p.ldbm);
+        M.Byy = __ldg(bmq + 3 * p.ldbm); M.Bxy = __ldg(bmq + 4 * p.ldbm);
     }
     int nfar = 0;
     double fsx = 0.0, fsy = 0.0, FBx = 0.0, FBy = 0.0;
@@ -772,17 +794,17 @@ k_sweep_fused(const FusedParams p)
         //   A2: fetch the candidates, pick the nearest, gate, label      (second level of gathers)
         {
             const int m = ce - co;
-            const int per = (((m + FS_WARPS - 1) / FS_WARPS) + 127) & ~127;
+            const int per = ((((m + FS_WARPS - 1) / FS_WARPS) + FS_U * 32 - 1) / (FS_U * 32)) * (FS_U * 32);
             const int wa = warp * per, wb = min(wa + per, m);
             unsigned long long pend = 0ull;
             const bool ident = p.ts->remap_identity != 0;
             const int lsearch = p.st->lsearch;
             int slot = 0;
-            for (int base = wa; base < wb; base += 128, slot += 4) {
-                int h_[4];
-                double wx_[4], wy_[4];
+            for (int base = wa; base < wb; base += FS_U * 32, slot += FS_U) {
+                int h_[FS_U];
+                double wx_[FS_U], wy_[FS_U];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < FS_U; ++u) {
                     const int i = base + u * 32 + lane;
                     h_[u] = -1; wx_[u] = 0.0; wy_[u] = 0.0;
                     if (i < wb && use_hints) {
@@ -797,12 +819,12 @@ k_sweep_fused(const FusedParams p)
                 }
                 if (!ident) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) if (h_[u] >= 0) h_[u] = __ldg(p.remap + h_[u]);
+                    for (int u = 0; u < FS_U; ++u) if (h_[u] >= 0) h_[u] = __ldg(p.remap + h_[u]);
                 }
-                double2 q_[4];
-                double r2_[4];
+                double2 q_[FS_U];
+                double r2_[FS_U];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < FS_U; ++u) {
                     q_[u] = make_double2(0.0, 0.0); r2_[u] = -1.0;
                     if (h_[u] >= 0 && h_[u] < lsearch) {
                         const double2* rp = reinterpret_cast<const double2*>(p.lmrec + h_[u]);
@@ -810,7 +832,7 @@ k_sweep_fused(const FusedParams p)
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < FS_U; ++u) {
                     const int i = base + u * 32 + lane;
                     if (i < wb) {
                         const double d2 = dist2_rn(q_[u].x - wx_[u], q_[u].y - wy_[u]);
@@ -827,10 +849,10 @@ k_sweep_fused(const FusedParams p)
             const bool any_pend = __any_sync(FULLMASK, pend != 0ull) && !(p.skip & 32);
             if (p.skip & 32) for (int i = wa + lane; i < wb; i += 32) sbk[i] = -1;
             slot = 0;
-            for (int base = wa; base < wb && any_pend; base += 128, slot += 4) {
-                int s_[4], e_[4];
+            for (int base = wa; base < wb && any_pend; base += FS_U * 32, slot += FS_U) {
+                int s_[FS_U], e_[FS_U];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < FS_U; ++u) {
                     const int i = base + u * 32 + lane;
                     s_[u] = 0; e_[u] = 0;
                     if (i < wb && have_map && ((pend >> (slot + u)) & 1ull)) {
@@ -844,18 +866,18 @@ k_sweep_fused(const FusedParams p)
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < FS_U; ++u) {
                     const int i = base + u * 32 + lane;
                     if (i < wb && ((pend >> (slot + u)) & 1ull)) { sbk[i] = s_[u]; srn[i] = (unsigned short)min(e_[u] - s_[u], 65535); }
                 }
             }
             slot = 0;
-            for (int base = wa; base < wb && any_pend; base += 128, slot += 4) {
-                double wx_[4], wy_[4];
-                double2 p_[4];
-                int id_[4], s_[4], n_[4];
+            for (int base = wa; base < wb && any_pend; base += FS_U * 32, slot += FS_U) {
+                double wx_[FS_U], wy_[FS_U];
+                double2 p_[FS_U];
+                int id_[FS_U], s_[FS_U], n_[FS_U];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < FS_U; ++u) {
                     const int i = base + u * 32 + lane;
                     s_[u] = 0; n_[u] = 0; id_[u] = -1; p_[u] = make_double2(0.0, 0.0); wx_[u] = 0.0; wy_[u] = 0.0;
                     if (i < wb && ((pend >> (slot + u)) & 1ull)) {
@@ -870,7 +892,7 @@ k_sweep_fused(const FusedParams p)
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < FS_U; ++u) {
                     const int i = base + u * 32 + lane;
                     if (i < wb && ((pend >> (slot + u)) & 1ull)) {
                         double best;
@@ -1014,7 +1036,7 @@ k_sweep_fused(const FusedParams p)
     if (SPLIT) {
         // ---- split mode: hand the scan's landmark moments to k_pose_solve ---------------------------------------------
         if (qvalid && sub == 0) {
-            double* d = p.dyn + qt;
+            double* d = p.dyn + cm_index(qt, p.Th);
             d[0] = M.Yx; d[p.lddyn] = M.Yy; d[2 * p.lddyn] = M.Mxx; d[3 * p.lddyn] = M.Mxy; d[4 * p.lddyn] = M.Myx; d[5 * p.lddyn] = M.Myy;
         }
         __syncthreads();     // every slot has reported its far observations
@@ -1074,22 +1096,24 @@ k_solve_colour(const FusedParams p)
     double ox = 0.0, oy = 0.0, th0 = 0.0, s0 = 0.0, c0 = 1.0;
     bool solve = false;
     const bool pinned = qvalid && t == 0;                    // x[:,0] is never updated (sensors.py:131)
+    const int64_t ct = cm_index(t, p.Th), cp = cm_index(t - 1, p.Th);     // colour-major positions of pose t and of pose t-1
     if (qvalid) {
         ox = p.xin[t]; oy = p.xin[p.ldin + t]; th0 = p.xin[2 * p.ldin + t];
-        s0 = p.sc[t]; c0 = p.sc[p.ldsc + t];
+        s0 = p.sc[ct]; c0 = p.sc[p.ldsc + ct];
         if (!pinned) {
             const bool has_next = t + 1 < T;
             P.has_next = has_next ? 1 : 0;
-            M.n = (double)(p.off[t + 1] - p.off[t]);
+            const double* bmq = p.bm + ct;
+            M.n = __ldg(bmq + 5 * p.ldbm);
             P.ax = X[t - 1]; P.ay = X[ldX + t - 1]; P.ath = X[2 * ldX + t - 1];
-            P.sa = SC[t - 1]; P.ca = SC[p.ldsc + t - 1];
+            P.sa = SC[cp]; P.ca = SC[p.ldsc + cp];
             if (has_next) { P.bx = X[t + 1]; P.by = X[ldX + t + 1]; P.bth = X[2 * ldX + t + 1]; }
-            P.uav = p.u[t - 1]; P.uaw = p.u[p.ldu + t - 1]; P.ucv = p.u[t]; P.ucw = p.u[p.ldu + t];
-            P.D0x = p.inc[t - 1]; P.D0y = p.inc[p.ldinc + t - 1]; P.dth0 = p.inc[2 * p.ldinc + t - 1];
-            P.D1x = p.inc[t]; P.D1y = p.inc[p.ldinc + t]; P.dth1 = p.inc[2 * p.ldinc + t];
-            M.Bx = __ldg(p.bm + t); M.By = __ldg(p.bm + p.ldbm + t); M.Bxx = __ldg(p.bm + 2 * p.ldbm + t);
-            M.Byy = __ldg(p.bm + 3 * p.ldbm + t); M.Bxy = __ldg(p.bm + 4 * p.ldbm + t);
-            const double* d = p.dyn + t;
+            P.uav = __ldg(p.u_cm + cp); P.uaw = __ldg(p.u_cm + p.ldbm + cp); P.ucv = __ldg(p.u_cm + ct); P.ucw = __ldg(p.u_cm + p.ldbm + ct);
+            P.D0x = __ldg(p.inc_cm + cp); P.D0y = __ldg(p.inc_cm + p.ldbm + cp); P.dth0 = __ldg(p.inc_cm + 2 * p.ldbm + cp);
+            P.D1x = __ldg(p.inc_cm + ct); P.D1y = __ldg(p.inc_cm + p.ldbm + ct); P.dth1 = __ldg(p.inc_cm + 2 * p.ldbm + ct);
+            M.Bx = __ldg(bmq); M.By = __ldg(bmq + p.ldbm); M.Bxx = __ldg(bmq + 2 * p.ldbm);
+            M.Byy = __ldg(bmq + 3 * p.ldbm); M.Bxy = __ldg(bmq + 4 * p.ldbm);
+            const double* d = p.dyn + ct;
             M.Yx = d[0]; M.Yy = d[p.lddyn]; M.Mxx = d[2 * p.lddyn]; M.Mxy = d[3 * p.lddyn]; M.Myx = d[4 * p.lddyn]; M.Myy = d[5 * p.lddyn];
             solve = M.n > 0.0;
         }
@@ -1115,7 +1139,7 @@ k_solve_colour(const FusedParams p)
     if (qvalid) {
         p.xout[(half ? p.ldout : 0) + t] = res;
         if (half == 0) p.xout[2 * p.ldout + t] = th;
-        if (COLOUR == 0) p.scn[(half ? p.ldsc : 0) + t] = half ? c_new : s_new;
+        if (COLOUR == 0) p.scn[(half ? p.ldsc : 0) + ct] = half ? c_new : s_new;
     }
 }
 

@@ -27,6 +27,9 @@ struct icmslam_handle {
     DevCfg dcfg;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;   // created with the handle; replaced by icmslam_set_stream
+    // the pose solve does not feed the tail (labels, landmark update, Mapa.filtrar): on one GPU the two run concurrently,
+    // the solve forked onto a side stream after k_sweep_fused and joined at the end of the sweep (also inside the CUDA graph)
+    cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool join_pending = false; int overlap_solve = 1;
     char err[512];
     // dataset
     int B = 0, T = 0, precondition = 0;
@@ -93,6 +96,7 @@ struct icmslam_handle {
     int tile_tpp = 2, tile_occ = 512;     // threads per pose slot; resident threads per SM the variant is compiled for
     int split = 1, solve_occ = 768;      // split mode: association + moments in k_sweep_fused, pose solve in k_pose_solve
     double* d_dyn = nullptr;              // 6 x T landmark moments of each scan (split mode)
+    double* d_inc_cm = nullptr; double* d_u_cm = nullptr;   // colour-major copies of d_inc / d_u for the solve kernels
     double* d_sc = nullptr;               // 2 x (2 x T): sin/cos of the input headings, then of the new odd headings (split mode)
     // label certificates + run cache (split mode, fused.cuh)
     // host-memspace sweeps: copy of the map returned by the last one (a caller that feeds it back continues the device-side
@@ -164,7 +168,7 @@ static void free_dataset(icmslam_handle* h)
     DFREE(h->d_off); DFREE(h->d_beam); DFREE(h->d_scan_of); DFREE(h->d_d); DFREE(h->d_bx); DFREE(h->d_by);
     DFREE(h->d_c); DFREE(h->d_keys_out); DFREE(h->d_iota); DFREE(h->d_sorted); DFREE(h->d_seen_x); DFREE(h->d_seen_y);
     DFREE(h->d_nfar); DFREE(h->d_flag); DFREE(h->d_prefix); DFREE(h->d_x);
-    DFREE(h->d_inc); DFREE(h->d_bm); DFREE(h->d_dyn); DFREE(h->d_sc); DFREE(h->d_rsum); DFREE(h->d_rmeta); DFREE(h->d_rcnt); DFREE(h->d_echk); DFREE(h->d_xchk); DFREE(h->d_x2); DFREE(h->d_far_list); DFREE(h->d_blk_far); DFREE(h->d_blk_prefix); DFREE(h->d_bxy);
+    DFREE(h->d_inc); DFREE(h->d_bm); DFREE(h->d_dyn); DFREE(h->d_sc); DFREE(h->d_inc_cm); DFREE(h->d_u_cm); DFREE(h->d_rsum); DFREE(h->d_rmeta); DFREE(h->d_rcnt); DFREE(h->d_echk); DFREE(h->d_xchk); DFREE(h->d_x2); DFREE(h->d_far_list); DFREE(h->d_blk_far); DFREE(h->d_blk_prefix); DFREE(h->d_bxy);
     drop_graphs(h);
     h->grid_map = nullptr;
     h->hint_map = nullptr;
@@ -192,6 +196,9 @@ extern "C" int icmslam_destroy(icmslam_handle* h)
     if (h->h_st) cudaFreeHost(h->h_st);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
     return ICMSLAM_OK;
 }
@@ -318,6 +325,14 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) h->stream = h->own_stream;
+    if (e == cudaSuccess) {     // lowest priority: the tail's tiny kernels on the main stream are dispatched ahead of the solve's waves
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        e = cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, lo);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    { const char* eo = getenv("ICMSLAM_OVERLAP"); if (eo) h->overlap_solve = atoi(eo) != 0; }
     if (e == cudaSuccess) e = cudaMemset(h->d_st, 0, sizeof(DevState));
     if (e == cudaSuccess) e = cudaMemset(h->d_counts, 0, L * sizeof(double));
     if (e != cudaSuccess) {
@@ -399,6 +414,10 @@ extern "C" int icmslam_load(icmslam_handle* h, const double* scans, int32_t B, i
         sb[i] = sin_tab ? sin_tab[i] : sin(ang[i]);
     }
     k_odo_increments<<<nblk(T, 256), 256, 0, h->stream>>>(h->d_odo, T, T, h->d_inc, T);
+    DFREE(h->d_inc_cm); DFREE(h->d_u_cm);
+    CK(dalloc(&h->d_inc_cm, (size_t)3 * T)); CK(dalloc(&h->d_u_cm, (size_t)2 * T));
+    k_to_colour_major<<<nblk(T, 256), 256, 0, h->stream>>>(h->d_inc, T, 3, T, h->d_inc_cm, T);
+    k_to_colour_major<<<nblk(T, 256), 256, 0, h->stream>>>(h->d_u, T, 2, T, h->d_u_cm, T);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->d_ang, ang.data(), B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_cos, cb.data(), B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -465,7 +484,7 @@ extern "C" int icmslam_extract(icmslam_handle* h)
     CK(cudaMemsetAsync(h->d_xchk, 0, (size_t)3 * T * sizeof(double), h->stream));
     CK(dalloc(&h->d_sc, (size_t)4 * T));
     CK(cudaMemsetAsync(h->d_sc, 0, (size_t)4 * T * sizeof(double), h->stream));
-    CK(dalloc(&h->d_bm, (size_t)5 * T));
+    CK(dalloc(&h->d_bm, (size_t)6 * T));
     CK(dalloc(&h->d_dyn, (size_t)6 * T));
     CK(cudaMemsetAsync(h->d_dyn, 0, (size_t)6 * T * sizeof(double), h->stream));
     k_body_moments<<<nblk(T, 128), 128, 0, h->stream>>>(h->d_off, h->d_bxy, T, h->d_bm, T);
@@ -699,7 +718,7 @@ static int build_fgrid(icmslam_handle* h, const double* px, const double* py, co
 // exchanges data with the other segments between them ----------------------------------------------------
 // part A: (grid of the previous map if it is not there yet) + the fused kernel + the scan of far-scan counts
 static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, double* kout, int64_t kld, const double* x0,
-                        const icmslam_sweep_opts& o, int n_search_cap)
+                        const icmslam_sweep_opts& o, int n_search_cap, bool overlap = false)
 {
     const int T = h->T, L = h->Lcap;
     cudaStream_t s = h->stream;
@@ -721,7 +740,7 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
     P.off = h->d_off; P.bxy = h->d_bxy;
     P.xin = xin; P.ldin = ldin; P.xout = kout; P.ldout = kld;
     P.x0[0] = x0[0]; P.x0[1] = x0[1]; P.x0[2] = x0[2];
-    P.inc = h->d_inc; P.ldinc = T; P.u = h->d_u; P.ldu = T; P.bm = h->d_bm; P.ldbm = T; P.dyn = h->d_dyn; P.lddyn = T; P.sc = h->d_sc; P.scn = h->d_sc + 2 * (size_t)T; P.ldsc = T;
+    P.inc = h->d_inc; P.ldinc = T; P.u = h->d_u; P.ldu = T; P.Th = (T + 1) >> 1; P.bm = h->d_bm; P.ldbm = T; P.inc_cm = h->d_inc_cm; P.u_cm = h->d_u_cm; P.dyn = h->d_dyn; P.lddyn = T; P.sc = h->d_sc; P.scn = h->d_sc + 2 * (size_t)T; P.ldsc = T;
     P.cfg = h->dcfg; P.thr2_hi = h->thr2_hi; P.fix_scale = h->fix_scale; P.tol = o.newton_tol; P.maxit = o.newton_maxit;
     P.st = st; P.geom = h->d_fg_geom; P.cell_start = h->d_fg_start; P.gpts = h->d_fg_pts; P.gidx = h->d_fg_idx;
     P.lmrec = h->d_lmrec; P.remap = h->d_remap;
@@ -752,9 +771,21 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
         CK(cudaGetLastError());
         if (timing) CK(cudaEventRecord(h->ev[2], s));      // (split mode: ev[0]..ev[2] = k_sweep_fused, ev[2]..ev[1] = the two solve kernels)
         const int n_pairs = (h->seg_hi - h->seg_lo) / 2 + 2;      // poses of one colour (incl. the odd halo pose of a segment)
-        solve_variant(0, h->solve_occ)<<<nblk(2 * n_pairs, SOLVE_THREADS), SOLVE_THREADS, 0, s>>>(P);
+        cudaStream_t ss = s;
+        const bool fork = overlap && h->overlap_solve && !timing && !prof && h->side_stream;
+        if (fork) {      // the tail does not depend on the new poses: solve beside it
+            CK(cudaEventRecord(h->ev_fork, s));
+            CK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+            ss = h->side_stream;
+        }
+        solve_variant(0, h->solve_occ)<<<nblk(2 * n_pairs, SOLVE_THREADS), SOLVE_THREADS, 0, ss>>>(P);
         CK(cudaGetLastError());
-        solve_variant(1, h->solve_occ)<<<nblk(2 * n_pairs, SOLVE_THREADS), SOLVE_THREADS, 0, s>>>(P);
+        solve_variant(1, h->solve_occ)<<<nblk(2 * n_pairs, SOLVE_THREADS), SOLVE_THREADS, 0, ss>>>(P);
+        if (fork) {
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(h->ev_join, ss));
+            h->join_pending = true;
+        }
         h->n_launch += 2;
     }
     CK(cudaGetLastError());
@@ -830,6 +861,7 @@ static int fused_part_c(icmslam_handle* h, double* dmap_out, int out_cap, int64_
         h->hint_map = h->grid_map;                                          // ... and c[] / d_remap carry this sweep's labels into it
         h->timed_fused = true;
         h->lact_dirty = true;
+        if (h->join_pending) { CK(cudaStreamWaitEvent(s, h->ev_join, 0)); h->join_pending = false; }
         return ICMSLAM_OK;
     }
     k_fused_means<<<nblk(L, 256), 256, 0, s>>>(st, h->d_fsum_x, h->d_fsum_y, h->d_cnt, min_x, min_y, 1.0 / h->fix_scale, h->dcfg.cota,
@@ -865,6 +897,7 @@ static int fused_part_c(icmslam_handle* h, double* dmap_out, int out_cap, int64_
     h->hint_map = h->grid_map;                                          // ... and c[] / d_remap carry this sweep's labels into it
     h->timed_fused = true;
     h->lact_dirty = true;
+    if (h->join_pending) { CK(cudaStreamWaitEvent(s, h->ev_join, 0)); h->join_pending = false; }
     return ICMSLAM_OK;
 }
 
@@ -900,7 +933,7 @@ static int sweep_core(icmslam_handle* h, const double* xin, int64_t ldin, double
         double* kout = xout;
         int64_t kld = ldout;
         if (xin == xout) { kout = (xin == h->d_x2) ? h->d_x : h->d_x2; kld = T; }
-        rc = fused_part_a(h, xin, ldin, kout, kld, x0, o, n_search_cap);
+        rc = fused_part_a(h, xin, ldin, kout, kld, x0, o, n_search_cap, /*overlap=*/kout == xout);
         if (rc) return rc;
         if (kout != xout) CK(cudaMemcpy2DAsync(xout, (size_t)ldout * 8, kout, (size_t)kld * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToDevice, s));
         rc = fused_part_b(h);
