@@ -285,14 +285,14 @@ def run_gpu(args, rank, world, local_rank):
     for _ in range(2):
         mapa_w, _ = icm.iterations_process_offline(mapa, x_host)
     torch.cuda.synchronize()
-    h2d = d2h = 0
+    tb0 = eng.transfer_bytes()                 # bytes the library actually copies (a map fed back unchanged is not re-uploaded)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        h2d += x_host.nbytes + mapa.nbytes
         mapa, _ = icm.iterations_process_offline(mapa, x_host)
-        d2h += x_host.nbytes + mapa.nbytes + 4
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    tb1 = eng.transfer_bytes()
+    h2d, d2h = tb1[0] - tb0[0], tb1[1] - tb0[1]
 
     # ---- CPU baseline (rank 0, N = 1): bounded sample -----------------------------------------------
     cpu = None

@@ -101,6 +101,7 @@ def lib():
     L.icmslam_pass0.argtypes = [vp, vp, vp, i64, vp, i32, i64, _ip, i32]
     L.icmslam_get_kernel_ms.argtypes = [vp, vp]
     L.icmslam_get_launch_count.argtypes = [vp, C.POINTER(i64)]
+    L.icmslam_get_transfer_bytes.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     L.icmslam_get_associations.argtypes = [vp, vp, i32]
     L.icmslam_get_raw_map.argtypes = [vp, vp, i32, i64, vp, _ip, i32]
     L.icmslam_get_sweep_stats.argtypes = [vp, C.POINTER(i64), i32]
@@ -121,7 +122,7 @@ EXPORTS = [
     "icmslam_get_extraction", "icmslam_set_landmarks_actuales", "icmslam_get_landmarks_actuales", "icmslam_get_counts",
     "icmslam_sweep", "icmslam_get_associations", "icmslam_get_raw_map", "icmslam_get_sweep_stats", "icmslam_filter_map",
     "icmslam_calc_cambio", "icmslam_filtrar_obs", "icmslam_set_map", "icmslam_get_map", "icmslam_iterate",
-    "icmslam_get_kernel_ms", "icmslam_get_launch_count", "icmslam_set_poses", "icmslam_get_poses", "icmslam_set_segment", "icmslam_device_ptr", "icmslam_seg_begin",
+    "icmslam_get_kernel_ms", "icmslam_get_launch_count", "icmslam_get_transfer_bytes", "icmslam_set_poses", "icmslam_get_poses", "icmslam_set_segment", "icmslam_device_ptr", "icmslam_seg_begin",
     "icmslam_seg_exchange", "icmslam_seg_finish", "icmslam_fcluster", "icmslam_pass0",
 ]
 

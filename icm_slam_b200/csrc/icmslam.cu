@@ -102,6 +102,7 @@ struct icmslam_handle {
     // host-memspace sweeps: copy of the map returned by the last one (a caller that feeds it back continues the device-side
     // map chain: grid, hints and labels stay valid, sensors.py:315 `mapa_viejo = mapa_refinado`)
     std::vector<double> last_map_host; int last_map_L = -1;
+    int64_t bytes_h2d = 0, bytes_d2h = 0;      // copied by host-memspace sweeps (icmslam_get_transfer_bytes)
     int use_cert = 0;                     // experimental (ICMSLAM_CERT=1): see fused.cuh "Label certificates" and profiles/README.md
     double2* d_rsum = nullptr; int4* d_rmeta = nullptr; int* d_rcnt = nullptr; int* d_echk = nullptr; double* d_xchk = nullptr;
     // time-segment partition (icmslam_set_segment): this handle owns columns [seg_lo, seg_hi) of its T columns
@@ -565,6 +566,10 @@ extern "C" int icmslam_set_landmarks_actuales(icmslam_handle* h, int32_t lact)
 {
     if (!h || lact < 0 || lact > h->Lcap) return ICMSLAM_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));
+    if (h->last_map_L >= 0 && lact == h->last_map_L) {      // what the last host-memspace sweep left on the device: nothing to do,
+        h->lact_host = lact;                                 // and the map chain stays alive (see icmslam_sweep)
+        return ICMSLAM_OK;
+    }
     k_set_lact<<<1, 1, 0, h->stream>>>(h->d_st, lact);
     CK(cudaGetLastError());
     h->grid_map = nullptr;
@@ -1056,6 +1061,7 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
     int64_t ldin = ld_x, ldout = ld_x;
     if (memspace == ICMSLAM_HOST) {
         CK(cudaMemcpy2DAsync(h->d_x, (size_t)T * 8, x, (size_t)ld_x * 8, (size_t)T * 8, 3, cudaMemcpyHostToDevice, s));
+        h->bytes_h2d += (int64_t)3 * T * 8;
         xin = h->d_x; ldin = T;
         xout = h->d_x2; ldout = T;
     }
@@ -1071,8 +1077,10 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
     }
     h->last_map_L = -1;
     if (!continued) {
-        if (L_in > 0)
+        if (L_in > 0) {
             CK(cudaMemcpy2DAsync(h->d_map_in, (size_t)L * 8, map_in, (size_t)ld_map_in * 8, (size_t)L_in * 8, 2, cudaMemcpyDefault, s));
+            if (memspace == ICMSLAM_HOST) h->bytes_h2d += (int64_t)2 * L_in * 8;
+        }
         h->grid_map = nullptr;
         h->hint_map = nullptr;
     }
@@ -1082,6 +1090,7 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
     if (rc) return rc;
     if (memspace == ICMSLAM_HOST) {
         CK(cudaMemcpy2DAsync(x, (size_t)ld_x * 8, xout, (size_t)T * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToHost, s));
+        h->bytes_d2h += (int64_t)3 * T * 8 + (int64_t)sizeof(DevState);
         rc = sync_state(h);
         if (rc) return rc;
         int status = status_from_state(h->h_st);
@@ -1092,6 +1101,7 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
             if (w > 0) {
                 CK(cudaMemcpy2DAsync(map_out, (size_t)ld_map_out * 8, h->d_map_out, (size_t)L * 8, (size_t)w * 8, 2, cudaMemcpyDeviceToHost, s));
                 CK(cudaStreamSynchronize(s));
+                h->bytes_d2h += (int64_t)2 * w * 8;
                 if (w == newL) {       // remember what the caller received (see `continued` above)
                     h->last_map_host.resize((size_t)2 * newL);
                     memcpy(h->last_map_host.data(), map_out, (size_t)newL * 8);
@@ -1356,6 +1366,13 @@ extern "C" int icmslam_get_kernel_ms(icmslam_handle* h, double* out2)
         if (!h->timed_fused) CK(cudaEventElapsedTime(&b, h->ev[2], h->ev[3]));
     }
     out2[0] = a; out2[1] = b;
+    return ICMSLAM_OK;
+}
+
+extern "C" int icmslam_get_transfer_bytes(icmslam_handle* h, int64_t* h2d, int64_t* d2h)
+{
+    if (!h || !h2d || !d2h) return ICMSLAM_ERR_INVALID;
+    *h2d = h->bytes_h2d; *d2h = h->bytes_d2h;
     return ICMSLAM_OK;
 }
 

@@ -243,6 +243,12 @@ class Engine:
         check(self.lib.icmslam_get_raw_map(self._h, _ptr(raw)[0], self.L, self.L, _ptr(cnt)[0], C.byref(rl), HOST), self._h)
         return raw[:, : rl.value].copy(), cnt[: rl.value].copy(), int(rl.value)
 
+    def transfer_bytes(self):
+        """(host->device, device->host) bytes copied so far by host-memory sweeps."""
+        a, b = C.c_int64(), C.c_int64()
+        check(self.lib.icmslam_get_transfer_bytes(self._h, C.byref(a), C.byref(b)), self._h)
+        return int(a.value), int(b.value)
+
     def fused_split(self):
         """True when the fused path runs as k_sweep_fused + two k_solve_colour launches (the default; ICMSLAM_SPLIT=0 selects the
         single-launch kernel)."""

@@ -187,6 +187,9 @@ int icmslam_pass0(icmslam_handle* h, const double* x0, double* x, int64_t ld_x, 
  * this library enqueued since icmslam_create. */
 int icmslam_get_kernel_ms(icmslam_handle* h, double* out2);
 int icmslam_get_launch_count(icmslam_handle* h, int64_t* n);
+/* bytes icmslam_sweep has copied host->device / device->host so far for HOST-memspace callers (poses, maps, status words);
+ * a map the caller feeds back unchanged is not re-uploaded (sensors.py:315, `mapa_viejo = mapa_refinado`). */
+int icmslam_get_transfer_bytes(icmslam_handle* h, int64_t* h2d, int64_t* d2h);
 
 /* -- results of the last sweep (all optional; mirror what Mapa / actualizar expose).
  * c: association label of every kept observation, CSR order (`c` of ICM_SLAM.py:201).
