@@ -706,3 +706,25 @@ def test_run_offline_one_call_matches_stepwise(tmp_path):
     for ext in ("mat", "npz"):
         back = load_result(save_result(str(tmp_path / ("out." + ext)), res))
         assert np.array_equal(back["x"], res["x"]) and np.array_equal(back["mapa"], res["mapa"])
+
+
+# ---- the sweep's variants: same labels; poses / map identical where the same compiled kernels run (scheduling variants) and
+#      equal to rounding where another template instantiation does the arithmetic (nvcc contracts FMAs per instantiation) -----
+@pytest.mark.gpu
+@pytest.mark.parametrize("env,exact", [({"ICMSLAM_OVERLAP": "0"}, True), ({"ICMSLAM_GRAPH": "0"}, True),
+                                       ({"ICMSLAM_SPLIT": "0"}, False), ({"ICMSLAM_TILE": "32"}, False),
+                                       ({"ICMSLAM_TILE": "16", "ICMSLAM_SOLVE_OCC": "512"}, False),
+                                       ({"ICMSLAM_SPLIT": "0", "ICMSLAM_TILE": "32"}, False)])
+def test_sweep_variants_agree(env, exact):
+    g = golden("synth_b.npz")
+    z, odo, u = g["observations"].astype(np.float64), g["odometry"], g["velocities"]
+    cfgd = dict(L=int(g["cfg_L"]), cota=float(g["cfg_cota"]))
+    base = {"ICMSLAM_SPLIT": "1", "ICMSLAM_TILE": "64", "ICMSLAM_OVERLAP": "1", "ICMSLAM_GRAPH": "1", "ICMSLAM_SOLVE_OCC": "768"}
+    a = _chain(z, odo, u, cfgd, g["map_init"], g["x_init"], 5, dict(base))
+    b = _chain(z, odo, u, cfgd, g["map_init"], g["x_init"], 5, dict(base, **env))
+    for k, (ra, rb) in enumerate(zip(a, b)):
+        assert np.array_equal(ra[2], rb[2]), (env, k)
+        if exact:
+            assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1]), (env, k)
+        else:
+            assert np.max(np.abs(ra[0] - rb[0])) <= 1e-10 and ra[1].shape == rb[1].shape and np.max(np.abs(ra[1] - rb[1])) <= 1e-10, (env, k)
