@@ -1192,9 +1192,10 @@ static fused_kernel_t solve_variant(int colour, int occ)     // k_solve_colour: 
 // raw map of the previous-map landmarks from the fixed-point statistics + keep flags for all labels;
 // clears the statistics for the next sweep.
 __global__ void __launch_bounds__(256)
-k_fused_means(const DevState* st, long long* __restrict__ fsum_x, long long* __restrict__ fsum_y, const int* __restrict__ cnt,
+k_fused_means(const DevState* st, long long* fsum_x, long long* fsum_y, const int* __restrict__ cnt,
               const double* __restrict__ map_x, const double* __restrict__ map_y, double inv_scale, double cota,
-              double* __restrict__ newraw /* 2 x Lcap: means of this sweep's new labels, zero elsewhere; cleared here */,
+              double* newraw /* 2 x Lcap: means of this sweep's new labels, zero elsewhere; cleared here.  ALIASES fsum_x / fsum_y
+                                (old labels use a word as int64 sum, new labels as double mean: disjoint index ranges) */,
               double* __restrict__ raw_x, double* __restrict__ raw_y, int* __restrict__ flag, int Lcap)
 {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;

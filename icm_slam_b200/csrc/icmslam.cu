@@ -108,7 +108,7 @@ struct icmslam_handle {
     // time-segment partition (icmslam_set_segment): this handle owns columns [seg_lo, seg_hi) of its T columns
     int seg_lo = 0, seg_hi = 0, seg_first = 1, seg_last = 1;
     double* d_newraw = nullptr;   // 2 x Lcap: means of the sweep's new labels (zero elsewhere)
-    long long* d_exch = nullptr;  // ONE block [fsum_x | fsum_y | newraw | cnt]: what the segments sum-reduce, viewed as int64
+    long long* d_exch = nullptr;  // ONE block [fsum_x | fsum_y | cnt] (newraw aliases the first two): what the segments sum-reduce, viewed as int64
     int64_t exch_words = 0;
     double* d_seg_rec = nullptr;  // SEG_REC doubles: what this segment tells its neighbours
     double* seg_dst = nullptr;    // output pose buffer of the segment sweep in flight
@@ -247,10 +247,14 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     if (e == cudaSuccess) e = dalloc(&h->d_counts, L);
     {   // exchange block (see icmslam_device_ptr): 64-bit words
         const size_t wcnt = (L + 2) / 2;
-        h->exch_words = (int64_t)(4 * L + wcnt);
+        // [fsum_x | fsum_y | cnt].  The means of the sweep's NEW labels (doubles, indices >= lsearch) live in the same words as the
+        // fixed-point sums of the OLD labels (int64, indices < lsearch): the two index ranges are disjoint, every new label is
+        // written by exactly one segment, and adding the all-zero words of the other segments to a double's bit pattern as an
+        // integer leaves it unchanged -- so the segments sum-reduce 2.5 words per landmark instead of 4.5.
+        h->exch_words = (int64_t)(2 * L + wcnt);
         if (e == cudaSuccess) e = dalloc(&h->d_exch, (size_t)h->exch_words);
         if (e == cudaSuccess) e = cudaMemset(h->d_exch, 0, (size_t)h->exch_words * 8);
-        h->d_fsum_x = h->d_exch; h->d_fsum_y = h->d_exch + L; h->d_newraw = (double*)(h->d_exch + 2 * L); h->d_cnt = (int*)(h->d_exch + 4 * L);
+        h->d_fsum_x = h->d_exch; h->d_fsum_y = h->d_exch + L; h->d_newraw = (double*)h->d_exch; h->d_cnt = (int*)(h->d_exch + 2 * L);
     }
     if (e == cudaSuccess) e = dalloc(&h->d_seg, L + 1);
     if (e == cudaSuccess) e = dalloc(&h->d_kflag, L);

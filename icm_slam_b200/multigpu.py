@@ -368,7 +368,7 @@ def bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, p
             "config": {"workload": desc, "T": T, "L_true": L_true, "n_obs": n_tot, "landmarks_after": int(L_now), "beams": 181,
                        "seed": SEED, "mode": "redblack/newton/prev",
                        "partition": "%d contiguous time segments (2+1 halo poses each), per sweep: 1 all-gather of 128 B/rank + "
-                                    "sum-reduction of %d landmark statistics (int64/int32/fp64)" % (world, L_true * 2),
+                                    "sum-reduction of one block of 2.5 words per landmark slot (%d slots: int64 sums / fp64 new-label means sharing words, int32 counts)" % (world, L_true * 2),
                        "segments": [list(s) for s in sol.segments],
                        "l2": "inputs larger than L2 (observations %.0f MB per rank vs 126 MB L2)" % (16 * n_tot / world / 1e6)},
             "clocks": clocks,

@@ -445,7 +445,7 @@ def _segmented_vs_single(d, cfgd, world, nsweeps):
             _lib.check(s.engine.lib.icmslam_seg_exchange(s.engine._h, C.c_void_p(allrec.data_ptr()), s.rank, world), s.engine._h)
         for s in sols:
             s.engine.synchronize()
-        for key in ("sx", "sy", "sn", "new"):                                               # the sum-reduction
+        for key in ("all",):                                               # the sum-reduction: ONE block of int64 words, as in production
             tot = torch.stack([s._views[key] for s in sols]).sum(0)
             for s in sols:
                 s._views[key].copy_(tot)
