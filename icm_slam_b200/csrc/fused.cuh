@@ -1,33 +1,31 @@
-// fused.cuh -- the single-pass (REDBLACK, NEWTON, PREV) sweep kernel.
+// fused.cuh -- the (REDBLACK, NEWTON, PREV) sweep: k_sweep_fused + k_solve_colour<0|1>.
 //
-// One launch does, for every pose t of the trajectory (sensors.py:145-162 restated per SURVEY.md
-// App. A): projection of the scan's kept beams with the sweep's INPUT pose (tras_rot_z,
-// ICM_SLAM.py:465-480), nearest-landmark association against the previous map with the dist_thr
-// gate (Mapa.actualizar Branch B, ICM_SLAM.py:169-182), per-landmark statistics for the landmark
-// update (:191-194), and the pose's conditional minimiser of fun_xn / fun_x (sensors.py:224-282)
-// in red-black order.  Every observation is read from HBM exactly once.
+// For every pose t of the trajectory (sensors.py:145-162 restated per SURVEY.md App. A): projection of the scan's kept
+// beams with the sweep's INPUT pose (tras_rot_z, ICM_SLAM.py:465-480), nearest-landmark association against the previous
+// map with the dist_thr gate (Mapa.actualizar Branch B, ICM_SLAM.py:169-182), per-landmark statistics for the landmark
+// update (:191-194), and the pose's conditional minimiser of fun_xn / fun_x (sensors.py:224-282) in red-black order.
+// Every observation is read from HBM exactly once.
 //
-// Work decomposition (block = 128 threads, 126 owned poses, one launch for the whole sweep):
-//   * the block's contiguous slice of the observation records (bx, by) is staged in shared memory with
-//     ONE TMA bulk copy (cp.async.bulk + mbarrier); tiles whose observations exceed the budget are
-//     processed in chunks of whole scans;
-//   * phase A -- LANES OVER CONSECUTIVE OBSERVATIONS (two per lane in flight): project, associate
-//     (fastgrid.cuh), write the label.  Adjacent lanes hold adjacent beams, i.e. mostly the same trunk,
-//     so the grid look-ups are coherent and every lane is busy;
-//   * phase B -- THREAD PER POSE over the staged data.  Pass 1 walks the scan once, summing the
-//     body-frame moments and collapsing each run of beams that hit the same landmark into an in-place
-//     record (run length, sum of bx, sum of by).  Pass 2 visits one RUN per step with the lanes in
-//     lockstep: everything that depends on the landmark is linear in the run sums, so the landmark
-//     moments and the landmark statistics cost one update per run, not per beam.  Statistics are
-//     added as int64 fixed point of (observation - previous landmark) to a block-level shared-memory
-//     hash table (32-bit halves with carry: native shared atomics) and flushed with one global integer
-//     atomic per (block, landmark): integer addition is associative, so the landmark update is
-//     bit-reproducible for any block order or GPU count.  Then the exact 1-D Newton solve: the two
-//     odd warps solve from the OLD even neighbours; after one __syncthreads the two even warps solve
-//     from the NEW odd neighbours held in shared memory.  The odd pose just left of the tile is
-//     recomputed locally (halo), so no block waits on another;
-//   * new poses are staged in shared memory and written coalesced.
-// Poses are double-buffered (xin -> xout): neighbouring tiles read each other's input poses.
+// k_sweep_fused (block = 256 threads, 126 owned poses, one launch for the whole sweep):
+//   * the block's contiguous slice of the observation records (bx, by) and last sweep's labels are staged in shared
+//     memory with TMA bulk copies (cp.async.bulk + mbarrier); tiles whose observations exceed the budget are processed in
+//     chunks of whole scans;
+//   * phase A -- LANES OVER CONSECUTIVE OBSERVATIONS (four per lane in flight): validate last sweep's label inside the
+//     landmark's proven-nearest radius, or project / associate through the grid (fastgrid.cuh); write the label.  Adjacent
+//     lanes hold adjacent beams, i.e. mostly the same trunk, so the look-ups are coherent and every lane is busy;
+//   * phase B -- THREAD PAIR PER POSE over the staged data.  Pass 1 collapses each run of beams that hit the same
+//     landmark into an in-place record (run length, sum of bx, sum of by).  Pass 2 visits one RUN per step with the lanes
+//     in lockstep: everything that depends on the landmark is linear in the run sums, so the landmark moments and the
+//     landmark statistics cost one update per run, not per beam.  Statistics are added as int64 fixed point of
+//     (observation - previous landmark) to a block-level shared-memory hash table (32-bit halves with carry: native shared
+//     atomics) and flushed with one global integer atomic per (block, landmark): integer addition is associative, so the
+//     landmark update is bit-reproducible for any block order or GPU count;
+//   * split mode (default): the scan's six landmark moments and sin/cos of its input heading go to global memory and
+//     k_solve_colour<0>, <1> (a lane pair per pose, no tile, no barrier) solve the odd poses from the OLD even neighbours
+//     and then the even poses from the NEW odd ones.  ICMSLAM_SPLIT=0 keeps the solve inside this kernel (solve_phases:
+//     odd warps, block barrier, even warps; the odd pose left of the tile is recomputed locally).
+// The body-frame moments of a scan do not depend on poses or map: k_body_moments forms them once per dataset.
+// Poses are double-buffered (xin -> xout).  Experimental, off by default: label certificates + run cache (see below).
 #pragma once
 #include "common.cuh"
 #include "assoc.cuh"
