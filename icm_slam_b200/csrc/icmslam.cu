@@ -94,7 +94,7 @@ struct icmslam_handle {
     int obs_cap = 0, max_tile_obs = 0;
     int tile_half = 64, tile_own = 126;   // fused-kernel tile: pose slots per colour / poses owned per block
     int tile_tpp = 2, tile_occ = 512;     // threads per pose slot; resident threads per SM the variant is compiled for
-    int split = 1, solve_occ = 768;      // split mode: association + moments in k_sweep_fused, pose solve in k_pose_solve
+    int split = 1, solve_occ = 512;      // split mode: association + moments in k_sweep_fused, pose solve in k_solve_colour<0|1> (512: 106 registers, no spills)
     double* d_dyn = nullptr;              // 6 x T landmark moments of each scan (split mode)
     double* d_inc_cm = nullptr; double* d_u_cm = nullptr;   // colour-major copies of d_inc / d_u for the solve kernels
     double* d_sc = nullptr;               // 2 x (2 x T): sin/cos of the input headings, then of the new odd headings (split mode)

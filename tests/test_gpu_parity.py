@@ -713,13 +713,13 @@ def test_run_offline_one_call_matches_stepwise(tmp_path):
 @pytest.mark.gpu
 @pytest.mark.parametrize("env,exact", [({"ICMSLAM_OVERLAP": "0"}, True), ({"ICMSLAM_GRAPH": "0"}, True),
                                        ({"ICMSLAM_SPLIT": "0"}, False), ({"ICMSLAM_TILE": "32"}, False),
-                                       ({"ICMSLAM_TILE": "16", "ICMSLAM_SOLVE_OCC": "512"}, False),
+                                       ({"ICMSLAM_TILE": "16", "ICMSLAM_SOLVE_OCC": "768"}, False),
                                        ({"ICMSLAM_SPLIT": "0", "ICMSLAM_TILE": "32"}, False)])
 def test_sweep_variants_agree(env, exact):
     g = golden("synth_b.npz")
     z, odo, u = g["observations"].astype(np.float64), g["odometry"], g["velocities"]
     cfgd = dict(L=int(g["cfg_L"]), cota=float(g["cfg_cota"]))
-    base = {"ICMSLAM_SPLIT": "1", "ICMSLAM_TILE": "64", "ICMSLAM_OVERLAP": "1", "ICMSLAM_GRAPH": "1", "ICMSLAM_SOLVE_OCC": "768"}
+    base = {"ICMSLAM_SPLIT": "1", "ICMSLAM_TILE": "64", "ICMSLAM_OVERLAP": "1", "ICMSLAM_GRAPH": "1", "ICMSLAM_SOLVE_OCC": "512"}
     a = _chain(z, odo, u, cfgd, g["map_init"], g["x_init"], 5, dict(base))
     b = _chain(z, odo, u, cfgd, g["map_init"], g["x_init"], 5, dict(base, **env))
     for k, (ra, rb) in enumerate(zip(a, b)):
