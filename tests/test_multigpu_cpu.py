@@ -162,3 +162,44 @@ def test_trajectory_batch_gather_two_ranks_gloo():
         p.join(timeout=60)
     for rank, keys, ok in got:
         assert keys == list(range(7)) and ok
+
+
+# ---- the statistics exchange sums ONE block of int64 words in which new-label means (fp64) share words with the old labels'
+#      fixed-point sums: a double contributed by exactly one rank survives an integer sum with the other ranks' zero words ----
+def _alias_worker(rank, world, port, q):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    L, ls = 64, 40                                   # 40 old labels (int64 sums from every rank), 24 slots for new labels
+    rng = np.random.default_rng(100 + rank)
+    words = np.zeros(2 * L, dtype=np.int64)
+    words[:ls] = rng.integers(-2**45, 2**45, ls)      # fsum_x of the old labels
+    words[L:L + ls] = rng.integers(-2**45, 2**45, ls)
+    mine = np.arange(ls + rank, L, world)             # new labels are numbered disjointly across ranks
+    words.view(np.float64)[mine] = rng.normal(size=mine.size) * 50.0
+    words.view(np.float64)[L + mine] = rng.normal(size=mine.size) * 50.0
+    t = torch.from_numpy(words.copy())
+    dist.all_reduce(t)
+    q.put((rank, words, t.numpy().copy(), mine))
+    dist.destroy_process_group()
+
+
+def test_exchange_block_int64_sum_preserves_disjoint_doubles_gloo():
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 400) + 71
+    world = 2
+    ps = [ctx.Process(target=_alias_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    got = sorted([q.get(timeout=120) for _ in ps], key=lambda r: r[0])
+    for p in ps:
+        p.join(timeout=60)
+    L, ls = 64, 40
+    total = got[0][2]
+    assert np.array_equal(total, got[1][2])
+    assert np.array_equal(total[:ls], got[0][1][:ls] + got[1][1][:ls])                      # old labels: exact integer sums
+    assert np.array_equal(total[L:L + ls], got[0][1][L:L + ls] + got[1][1][L:L + ls])
+    for rank, words, _, mine in got:                                                        # new labels: the owner's double, bit for bit
+        assert np.array_equal(total.view(np.float64)[mine], words.view(np.float64)[mine])
+        assert np.array_equal(total.view(np.float64)[L + mine], words.view(np.float64)[L + mine])
