@@ -238,14 +238,14 @@ def run_gpu(args, rank, world, local_rank):
         kt.append(eng.kernel_ms())
     k_assoc_ms = float(np.mean([a for a, _ in kt]))
     k_pose_ms = float(np.mean([b for _, b in kt]))
-    fused = eng.fused_split() or k_pose_ms == 0.0
+    fused = True
     B_sweep = sweep_bytes(T, n, L_true)
     peak, peak_src = peaks()
     if fused and k_pose_ms > 0.0:
         # split mode: k_sweep_fused (association + moments + landmark statistics; reads poses 24T, offsets 4(T+1), observations
         # 16n, map 16L; writes labels 4n, statistics 24L) and two k_solve_colour launches (poses, odometry, controls in; poses
         # out).  The dominant kernel is reported with ITS share of the sweep's algorithmic bytes.
-        dom_name, dom_ms = "k_sweep_fused", k_assoc_ms
+        dom_name, dom_ms = "k_runs+k_assoc_tiles", k_assoc_ms
         dom_bytes = 24 * T + 4 * (T + 1) + 16 * n + 16 * L_true + 4 * n + 24 * L_true
     elif fused:
         dom_name, dom_ms, dom_bytes = "k_sweep_fused", k_assoc_ms, B_sweep

@@ -14,7 +14,7 @@ struct DevState {
     int kept;        // landmarks surviving cota
     int new_l;       // landmarks after filtrar
     int n_ind;       // landmarks with a neighbour closer than dist_thr
-    int cert_tiles;  // tiles of the fused kernel that ran on label certificates this sweep (fused.cuh)
+    int dirty_tiles; // record tiles that went through the association kernel this sweep (runs.cuh; filled on request)
     unsigned long long newton_iters;
     unsigned long long solved;
     // grid parameters of the association grid / filter grid

@@ -56,6 +56,22 @@ __device__ __forceinline__ void project(const Rot& r, double px, double py, doub
     wy = add_rn(__fma_rn(by, r.ct, mul_rn(bx, r.st)), py);
 }
 
+// Projection parameters of a pose: (x, y, sin(theta - pi/2), cos(theta - pi/2)) exactly as tras_rot_z forms them
+// (ICM_SLAM.py:466-468; the subtraction rounded once, then libm-accurate sin/cos).  The sin/cos of the heading itself are
+// (cos(theta - pi/2), -sin(theta - pi/2)).  One record per pose, rewritten by the solve for the poses it moves.
+__device__ __forceinline__ double4 make_ppar(double x, double y, double th)
+{
+    double st, ct;
+    sincos(sub_rn(th, ICM_HALFPI), &st, &ct);
+    return make_double4(x, y, st, ct);
+}
+
+__device__ __forceinline__ double4 ldg_ppar(const double4* p)
+{
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll

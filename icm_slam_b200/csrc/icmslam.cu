@@ -15,8 +15,10 @@
 #include "pose.cuh"
 #include "mapfilter.cuh"
 #include "fastgrid.cuh"
-#include "fused.cuh"
-#include "tail_coop.cuh"
+#include "tail.cuh"
+#include "solve.cuh"
+#include "runs.cuh"
+#include "assoc_tiles.cuh"
 #include "fcluster.h"
 #include "pass0.cuh"
 
@@ -65,12 +67,18 @@ struct icmslam_handle {
     bool lact_dirty = false;
     void* d_cub = nullptr;
     size_t cub_bytes = 0;
-    // fused (REDBLACK, NEWTON, PREV) path
+    // fused (REDBLACK, NEWTON, PREV) path: run records (runs.cuh) + association of dirty tiles (assoc_tiles.cuh) + solve (solve.cuh)
     bool fused_ok = false;
-    double *d_bm = nullptr /*5 x T static body-frame moments*/, *d_inc = nullptr /*3 x T odometry increments*/, *d_x2 = nullptr /*3 x T, pose double buffer*/;
+    double *d_bm = nullptr /*6 x T static body-frame moments + beam count*/, *d_inc = nullptr /*3 x T odometry increments*/, *d_x2 = nullptr /*3 x T, pose double buffer*/;
+    double4* d_ppar[2] = {nullptr, nullptr};   // projection parameters of the poses in d_x / d_x2 (solve.cuh make_ppar)
+    const double* ppar_of = nullptr;           // the pose buffer whose projection parameters are current (nullptr: recompute)
     FarRec* d_far_list = nullptr;
-    int *d_blk_far = nullptr, *d_blk_prefix = nullptr;
-    int n_tiles = 0;
+    int* d_blk_prefix = nullptr;
+    unsigned* d_farbits = nullptr;             // 4 words per record tile: scans that created a label this sweep
+    int n_tiles = 0, n_solve_tiles = 0;        // record tiles (RT_TILE scans) / solve tiles (ST_OWN poses)
+    RunRec* d_rec = nullptr; int64_t rec_slots = 0;
+    int *d_tile_nchunks = nullptr, *d_tile_epoch = nullptr, *d_tile_flag = nullptr, *d_dirty_list = nullptr, *d_scan_dirty = nullptr, *d_ticket = nullptr;
+    double *d_dyn = nullptr /*6 per pose*/, *d_dynx = nullptr /*12 per chunk slot (long scans)*/;
     TailState* d_ts = nullptr;
     double thr2_lt = 0.0;        // largest s with sqrt_rn(s) < dist_thr
     const double* grid_map = nullptr;   // the map buffer the fast grid currently indexes (nullptr: rebuild)
@@ -81,9 +89,9 @@ struct icmslam_handle {
     double thr1sq = 0.0;
     struct GraphSlot { cudaGraphExec_t exec = nullptr; const double* src = nullptr; const double* map_in = nullptr; double x0[3] = {0, 0, 0}; double tol = 0; int maxit = 0; };
     GraphSlot graphs[4];
-    int use_graph = 1;
-    int coop_tail = 0, coop_blocks = 0;   // the tail as one cooperative launch (tail_coop.cuh)
-    int* d_blk_scratch = nullptr;
+    int use_graph = 1, graph_launches = 0;
+    int use_runs = 1;            // ICMSLAM_RUNS=0: every tile goes through the association kernel every sweep (no steady-state shortcut)
+    int assoc_blocks = 0;        // grid of the (persistent) association kernel
     double2* d_bxy = nullptr;    // interleaved (bx, by) records for the TMA staging
     long long *d_fsum_x = nullptr, *d_fsum_y = nullptr;
     int fg_cells = 0;            // cell budget of the fast grid (host constant)
@@ -92,19 +100,10 @@ struct icmslam_handle {
     FGeom* d_fg_geom = nullptr;
     unsigned long long* d_bb = nullptr;
     int obs_cap = 0, max_tile_obs = 0;
-    int tile_half = 64, tile_own = 126;   // fused-kernel tile: pose slots per colour / poses owned per block
-    int tile_tpp = 2, tile_occ = 512;     // threads per pose slot; resident threads per SM the variant is compiled for
-    int split = 1, solve_occ = 512;      // split mode: association + moments in k_sweep_fused, pose solve in k_solve_colour<0|1> (512: 106 registers, no spills)
-    double* d_dyn = nullptr;              // 6 x T landmark moments of each scan (split mode)
-    double* d_inc_cm = nullptr; double* d_u_cm = nullptr;   // colour-major copies of d_inc / d_u for the solve kernels
-    double* d_sc = nullptr;               // 2 x (2 x T): sin/cos of the input headings, then of the new odd headings (split mode)
-    // label certificates + run cache (split mode, fused.cuh)
     // host-memspace sweeps: copy of the map returned by the last one (a caller that feeds it back continues the device-side
     // map chain: grid, hints and labels stay valid, sensors.py:315 `mapa_viejo = mapa_refinado`)
     std::vector<double> last_map_host; int last_map_L = -1;
     int64_t bytes_h2d = 0, bytes_d2h = 0;      // copied by host-memspace sweeps (icmslam_get_transfer_bytes)
-    int use_cert = 0;                     // experimental (ICMSLAM_CERT=1): see fused.cuh "Label certificates" and profiles/README.md
-    double2* d_rsum = nullptr; int4* d_rmeta = nullptr; int* d_rcnt = nullptr; int* d_echk = nullptr; double* d_xchk = nullptr;
     // time-segment partition (icmslam_set_segment): this handle owns columns [seg_lo, seg_hi) of its T columns
     int seg_lo = 0, seg_hi = 0, seg_first = 1, seg_last = 1;
     double* d_newraw = nullptr;   // 2 x Lcap: means of the sweep's new labels (zero elsewhere)
@@ -116,6 +115,7 @@ struct icmslam_handle {
     double thr2_hi = 0.0, fix_scale = 1.0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool timed_fused = false;
+    double last_runs_ms = 0.0;   // k_runs alone in the last timed fused sweep
     int64_t n_launch = 0;   // kernels of this library launched so far (cub's not counted)
     int x_cur = 0;          // which pose buffer (d_x / d_x2) holds the resident poses
 };
@@ -169,7 +169,10 @@ static void free_dataset(icmslam_handle* h)
     DFREE(h->d_off); DFREE(h->d_beam); DFREE(h->d_scan_of); DFREE(h->d_d); DFREE(h->d_bx); DFREE(h->d_by);
     DFREE(h->d_c); DFREE(h->d_keys_out); DFREE(h->d_iota); DFREE(h->d_sorted); DFREE(h->d_seen_x); DFREE(h->d_seen_y);
     DFREE(h->d_nfar); DFREE(h->d_flag); DFREE(h->d_prefix); DFREE(h->d_x);
-    DFREE(h->d_inc); DFREE(h->d_bm); DFREE(h->d_dyn); DFREE(h->d_sc); DFREE(h->d_inc_cm); DFREE(h->d_u_cm); DFREE(h->d_rsum); DFREE(h->d_rmeta); DFREE(h->d_rcnt); DFREE(h->d_echk); DFREE(h->d_xchk); DFREE(h->d_x2); DFREE(h->d_far_list); DFREE(h->d_blk_far); DFREE(h->d_blk_prefix); DFREE(h->d_bxy);
+    DFREE(h->d_inc); DFREE(h->d_bm); DFREE(h->d_dyn); DFREE(h->d_dynx); DFREE(h->d_x2); DFREE(h->d_far_list); DFREE(h->d_blk_prefix); DFREE(h->d_bxy);
+    DFREE(h->d_ppar[0]); DFREE(h->d_ppar[1]); DFREE(h->d_farbits); DFREE(h->d_rec); DFREE(h->d_tile_nchunks); DFREE(h->d_tile_epoch);
+    DFREE(h->d_tile_flag); DFREE(h->d_dirty_list); DFREE(h->d_scan_dirty); DFREE(h->d_ticket);
+    h->ppar_of = nullptr;
     drop_graphs(h);
     h->grid_map = nullptr;
     h->hint_map = nullptr;
@@ -193,7 +196,7 @@ extern "C" int icmslam_destroy(icmslam_handle* h)
     DFREE(h->d_st); DFREE(h->d_cub);
     DFREE(h->d_exch); DFREE(h->d_fg_cnt); DFREE(h->d_fg_start); DFREE(h->d_fg_idx);
     DFREE(h->d_fg_pts); DFREE(h->d_fg_geom); DFREE(h->d_bb); DFREE(h->d_ts); DFREE(h->d_seg_rec);
-    DFREE(h->d_lmrec); DFREE(h->d_remap); DFREE(h->d_nnd2); DFREE(h->d_blk_scratch);
+    DFREE(h->d_lmrec); DFREE(h->d_remap); DFREE(h->d_nnd2);
     if (h->h_st) cudaFreeHost(h->h_st);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -300,16 +303,11 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     { const double t1 = cfg->dist_thr * (1.0 + 9.5367431640625e-07); h->thr1sq = t1 * t1; }
     if (e == cudaSuccess) e = cudaMemset(h->d_ts, 0, sizeof(TailState));
     { const char* eg = getenv("ICMSLAM_GRAPH"); if (eg) h->use_graph = atoi(eg); }
+    { const char* er = getenv("ICMSLAM_RUNS"); if (er) h->use_runs = atoi(er) != 0; }
     if (e == cudaSuccess) {
-        int coop = 0, sms = 0, per_sm = 0;
-        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device);
+        int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tail_coop, TC_THREADS, 0);
-        const char* ec = getenv("ICMSLAM_COOP_TAIL");
-        h->coop_blocks = sms;
-        // measured on B200 (profiles/README.md): same time as the kernel chain, so the chain stays the default
-        h->coop_tail = (coop && per_sm >= 1 && sms > 0 && ec && atoi(ec) == 1) ? 1 : 0;
-        e = dalloc(&h->d_blk_scratch, (size_t)2 * (sms > 0 ? sms : 1) + 8);
+        h->assoc_blocks = 2 * (sms > 0 ? sms : 1);
     }
     if (e == cudaSuccess) e = cudaMemset(h->d_fg_cnt, 0, ((size_t)h->fg_cells + 2) * sizeof(int));
     {   // gate and fixed-point scale of the fused path
@@ -387,20 +385,11 @@ extern "C" int icmslam_load(icmslam_handle* h, const double* scans, int32_t B, i
     CK(dalloc(&h->d_prefix, (size_t)T + 1));
     CK(dalloc(&h->d_inc, (size_t)3 * T));
     CK(dalloc(&h->d_x2, (size_t)3 * T));
-    {
-        const char* et = getenv("ICMSLAM_TILE"); const char* ep = getenv("ICMSLAM_TPP"); const char* eo = getenv("ICMSLAM_OCC");
-        int v = et ? atoi(et) : FUSED_DEFAULT_HALF, tpp = ep ? atoi(ep) : FUSED_DEFAULT_TPP, occ = eo ? atoi(eo) : FUSED_DEFAULT_OCC;
-        if (!fused_variant(v, tpp, occ, false)) { v = FUSED_DEFAULT_HALF; tpp = FUSED_DEFAULT_TPP; occ = FUSED_DEFAULT_OCC; }
-        h->tile_half = v; h->tile_tpp = tpp; h->tile_occ = occ; h->tile_own = 2 * v - 2;
-        { const char* es = getenv("ICMSLAM_SPLIT"); if (es) h->split = atoi(es) != 0; }
-        { const char* es = getenv("ICMSLAM_SOLVE_OCC"); if (es) h->solve_occ = atoi(es); }
-        { const char* es = getenv("ICMSLAM_CERT"); if (es) h->use_cert = atoi(es) != 0; }
-    }
     h->seg_lo = 0; h->seg_hi = T; h->seg_first = 1; h->seg_last = 1;
-    h->n_tiles = nblk(T, h->tile_own);
+    h->n_tiles = nblk(T, RT_TILE);
+    h->n_solve_tiles = nblk(T, ST_OWN);
     CK(dalloc(&h->d_far_list, (size_t)T));
-    CK(dalloc(&h->d_blk_far, (size_t)h->n_tiles));
-    CK(dalloc(&h->d_blk_prefix, (size_t)h->n_tiles));
+    CK(dalloc(&h->d_blk_prefix, (size_t)nblk(T + 1, RT_TILE) + 2));
     {   // scan workspace for the largest scan of a sweep, so that nothing allocates inside a graph capture
         size_t need = 0, b = 0;
         const int lens[3] = {h->Lcap + 1, h->fg_cells + 2, T + 1};
@@ -419,10 +408,6 @@ extern "C" int icmslam_load(icmslam_handle* h, const double* scans, int32_t B, i
         sb[i] = sin_tab ? sin_tab[i] : sin(ang[i]);
     }
     k_odo_increments<<<nblk(T, 256), 256, 0, h->stream>>>(h->d_odo, T, T, h->d_inc, T);
-    DFREE(h->d_inc_cm); DFREE(h->d_u_cm);
-    CK(dalloc(&h->d_inc_cm, (size_t)3 * T)); CK(dalloc(&h->d_u_cm, (size_t)2 * T));
-    k_to_colour_major<<<nblk(T, 256), 256, 0, h->stream>>>(h->d_inc, T, 3, T, h->d_inc_cm, T);
-    k_to_colour_major<<<nblk(T, 256), 256, 0, h->stream>>>(h->d_u, T, 2, T, h->d_u_cm, T);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->d_ang, ang.data(), B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_cos, cb.data(), B * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -480,15 +465,26 @@ extern "C" int icmslam_extract(icmslam_handle* h)
     CK(dalloc(&h->d_bxy, n + 2));
     k_interleave<<<nblk((int64_t)n, 256), 256, 0, h->stream>>>(h->d_bx, h->d_by, (int64_t)n, h->d_bxy);
     CK(cudaGetLastError());
-    DFREE(h->d_bm); DFREE(h->d_dyn); DFREE(h->d_sc);
-    DFREE(h->d_rsum); DFREE(h->d_rmeta); DFREE(h->d_rcnt); DFREE(h->d_echk); DFREE(h->d_xchk);
-    CK(dalloc(&h->d_rsum, n + 2)); CK(dalloc(&h->d_rmeta, n + 2)); CK(dalloc(&h->d_rcnt, (size_t)T));
-    CK(dalloc(&h->d_echk, (size_t)T)); CK(dalloc(&h->d_xchk, (size_t)3 * T));
-    CK(cudaMemsetAsync(h->d_echk, 0xff, (size_t)T * sizeof(int), h->stream));       // epoch -1: no scan holds a certificate
-    CK(cudaMemsetAsync(h->d_rcnt, 0, (size_t)T * sizeof(int), h->stream));
-    CK(cudaMemsetAsync(h->d_xchk, 0, (size_t)3 * T * sizeof(double), h->stream));
-    CK(dalloc(&h->d_sc, (size_t)4 * T));
-    CK(cudaMemsetAsync(h->d_sc, 0, (size_t)4 * T * sizeof(double), h->stream));
+    DFREE(h->d_bm); DFREE(h->d_dyn); DFREE(h->d_dynx);
+    DFREE(h->d_ppar[0]); DFREE(h->d_ppar[1]); DFREE(h->d_farbits); DFREE(h->d_rec); DFREE(h->d_tile_nchunks); DFREE(h->d_tile_epoch);
+    DFREE(h->d_tile_flag); DFREE(h->d_dirty_list); DFREE(h->d_scan_dirty); DFREE(h->d_ticket);
+    {   // run records and their bookkeeping (runs.cuh): region of tile i at run_tile_base, 2 slots per observation + 64 per tile
+        const size_t nt = (size_t)nblk(T + 1, RT_TILE) + 2;      // (+1 scan: a segment's tiling may start one scan earlier)
+        h->rec_slots = (int64_t)(2 * n + 64 * nt + 64);
+        CK(dalloc(&h->d_rec, (size_t)h->rec_slots));
+        CK(dalloc(&h->d_dynx, (size_t)(h->rec_slots / 32 + 1) * 12));
+        CK(dalloc(&h->d_ppar[0], (size_t)T)); CK(dalloc(&h->d_ppar[1], (size_t)T));
+        CK(dalloc(&h->d_farbits, nt * 4)); CK(dalloc(&h->d_tile_nchunks, nt)); CK(dalloc(&h->d_tile_epoch, nt));
+        CK(dalloc(&h->d_tile_flag, nt)); CK(dalloc(&h->d_dirty_list, nt));
+        CK(dalloc(&h->d_scan_dirty, (size_t)T + 1)); CK(dalloc(&h->d_ticket, (size_t)T + 1));
+        CK(cudaMemsetAsync(h->d_tile_nchunks, 0, nt * sizeof(int), h->stream));
+        CK(cudaMemsetAsync(h->d_tile_epoch, 0xff, nt * sizeof(int), h->stream));       // epoch -1: no tile holds records
+        CK(cudaMemsetAsync(h->d_tile_flag, 0, nt * sizeof(int), h->stream));
+        CK(cudaMemsetAsync(h->d_farbits, 0, nt * 4 * sizeof(unsigned), h->stream));
+        CK(cudaMemsetAsync(h->d_scan_dirty, 0, ((size_t)T + 1) * sizeof(int), h->stream));
+        CK(cudaMemsetAsync(h->d_ticket, 0, ((size_t)T + 1) * sizeof(int), h->stream));
+        h->ppar_of = nullptr;
+    }
     CK(dalloc(&h->d_bm, (size_t)6 * T));
     CK(dalloc(&h->d_dyn, (size_t)6 * T));
     CK(cudaMemsetAsync(h->d_dyn, 0, (size_t)6 * T * sizeof(double), h->stream));
@@ -498,33 +494,32 @@ extern "C" int icmslam_extract(icmslam_handle* h)
     cudaFree(d_masks);
     cudaFree(d_counts);
     h->extracted = true;
-    {   // shared-memory budget of the fused kernel: observations of one tile (FS_OWN poses + the halo scan)
+    {   // shared-memory budget of the association kernel: observations of one tile of RT_TILE scans
         int mx = 0;
-        for (int tb = 0; tb < T; tb += 2) {   // (any even tile origin: a later icmslam_set_segment may shift the tiling)
-            int t0 = tb > 0 ? tb - 1 : 0, t1 = tb + h->tile_own < T ? tb + h->tile_own : T;
-            int m = off[t1] - off[t0];
+        for (int tb = 0; tb < T; ++tb) {   // (any tile origin: a later icmslam_set_segment may shift the tiling)
+            int t1 = tb + RT_TILE < T ? tb + RT_TILE : T;
+            int m = off[t1] - off[tb];
             if (m > mx) mx = m;
         }
         h->max_tile_obs = mx;
-        int blocks_per_sm = h->tile_occ / (2 * h->tile_tpp * h->tile_half);
-        const size_t fixed = fused_smem_fixed(h->tile_half, h->split != 0);
+        int blocks_per_sm = 2;
+        const size_t fixed = sizeof(AssocSmem);
         const char* envb = getenv("ICMSLAM_BLOCKS_PER_SM");
         if (envb && atoi(envb) > 0) blocks_per_sm = atoi(envb);
         const size_t per_block = (size_t)233472 / blocks_per_sm - 1024 - 512;   // 228 KB per SM, 1 KB reserved per block
-        int cap = (int)((per_block - fixed - 64) / 23);
+        int cap = (int)((per_block - fixed - 96) / AT_OBS_BYTES);
         const char* env = getenv("ICMSLAM_OBS_CAP");
         if (env && atoi(env) > 0) cap = atoi(env);
-        const int cap_max = (int)((232448 - fixed - 64) / 23);
+        const int cap_max = (int)((232448 - fixed - 96) / AT_OBS_BYTES);
         if (cap > cap_max) cap = cap_max;
         if (cap > mx) cap = mx;                                    // the whole tile fits: one chunk
         if (cap < h->max_per_scan) cap = h->max_per_scan;          // a chunk holds at least one whole scan
         if (cap < 2) cap = 2;
         h->obs_cap = (cap + 1) & ~1;
-        h->fused_smem = fused_smem_bytes(h->tile_half, h->split != 0, h->obs_cap);
-        { const char* epad = getenv("ICMSLAM_SMEM_PAD"); if (epad) h->fused_smem += (size_t)atoi(epad); }   // (debug: lowers the residency)
+        h->fused_smem = assoc_smem_bytes(h->obs_cap);
         // (a per-function, per-device attribute shared by every handle of the process: opt in to the maximum)
-        CK(cudaFuncSetAttribute(fused_variant(h->tile_half, h->tile_tpp, h->tile_occ, h->split != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        h->fused_ok = true;
+        CK(cudaFuncSetAttribute(k_assoc_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        h->fused_ok = h->max_per_scan <= 65535 && RT_TILE <= 256;
     }
     return ICMSLAM_OK;
 }
@@ -674,6 +669,7 @@ static int run_filter(icmslam_handle* h, const double* raw_x, const double* raw_
 __global__ void k_sweep_begin(DevState* st, TailState* ts, int L_in)
 {
     ts->far_count = 0;
+    ts->n_dirty = 0;
     st->lact0 = st->lact;
     st->lsearch = min(st->lact, L_in);
     st->raw_l = st->lact;
@@ -681,7 +677,7 @@ __global__ void k_sweep_begin(DevState* st, TailState* ts, int L_in)
     st->n_far_scans = 0;
     st->newton_iters = 0ull;
     st->solved = 0ull;
-    st->cert_tiles = 0;
+    st->dirty_tiles = 0;
 }
 
 static int status_from_state(const DevState* s)
@@ -723,9 +719,24 @@ static int build_fgrid(icmslam_handle* h, const double* px, const double* py, co
     return ICMSLAM_OK;
 }
 
+__global__ void k_epoch_bump(TailState* ts) { ts->epoch += 1; }
+__global__ void k_note_dirty(DevState* st, const TailState* ts) { st->dirty_tiles = ts->n_dirty; }
+
+// projection parameters (solve.cuh make_ppar) of the poses in `x`, unless the solve of the previous sweep already left them
+static int ensure_ppar(icmslam_handle* h, const double* x, int64_t ldx, const double* x0, double4* dst)
+{
+    if (h->ppar_of == x && x != nullptr) return ICMSLAM_OK;
+    k_ppar_init<<<nblk(h->T, 256), 256, 0, h->stream>>>(x, ldx, 0, h->T, h->seg_first, x0[0], x0[1], x0[2], dst);
+    CK(cudaGetLastError());
+    h->n_launch += 1;
+    h->ppar_of = x;
+    return ICMSLAM_OK;
+}
+
 // ---- the fused (REDBLACK, NEWTON, PREV) sweep in three parts; a time-segmented run (one segment per GPU)
 // exchanges data with the other segments between them ----------------------------------------------------
-// part A: (grid of the previous map if it is not there yet) + the fused kernel + the scan of far-scan counts
+// part A: (grid of the previous map if it is not there yet) + the run kernel + the association kernel over the tiles the run
+// kernel could not certify + the pose solve (forked beside the tail when `overlap`) + the scan of far-scan counts
 static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, double* kout, int64_t kld, const double* x0,
                         const icmslam_sweep_opts& o, int n_search_cap, bool overlap = false)
 {
@@ -741,93 +752,76 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
         k_lmrec_build<<<nblk(n_search_cap, 256), 256, 0, s>>>(min_x, min_y, &st->lsearch, h->d_fg_geom, h->d_fg_start, h->d_fg_pts, h->d_fg_idx,
                                                               h->thr1sq, h->thr2_hi, h->d_lmrec);
         CK(cudaGetLastError());
-        h->n_launch += 1;
+        k_epoch_bump<<<1, 1, 0, s>>>(h->d_ts);      // a map from outside: its labels are a new numbering, run records are void
+        CK(cudaGetLastError());
+        h->n_launch += 2;
         h->hint_map = nullptr;
     }
-    FusedParams P;
-    P.T = T; P.t_lo = h->seg_lo; P.t_hi = h->seg_hi; P.first = h->seg_first;
-    P.off = h->d_off; P.bxy = h->d_bxy;
-    P.xin = xin; P.ldin = ldin; P.xout = kout; P.ldout = kld;
-    P.x0[0] = x0[0]; P.x0[1] = x0[1]; P.x0[2] = x0[2];
-    P.inc = h->d_inc; P.ldinc = T; P.u = h->d_u; P.ldu = T; P.Th = (T + 1) >> 1; P.bm = h->d_bm; P.ldbm = T; P.inc_cm = h->d_inc_cm; P.u_cm = h->d_u_cm; P.dyn = h->d_dyn; P.lddyn = T; P.sc = h->d_sc; P.scn = h->d_sc + 2 * (size_t)T; P.ldsc = T;
-    P.cfg = h->dcfg; P.thr2_hi = h->thr2_hi; P.fix_scale = h->fix_scale; P.tol = o.newton_tol; P.maxit = o.newton_maxit;
-    P.st = st; P.geom = h->d_fg_geom; P.cell_start = h->d_fg_start; P.gpts = h->d_fg_pts; P.gidx = h->d_fg_idx;
-    P.lmrec = h->d_lmrec; P.remap = h->d_remap;
-    { const char* eh = getenv("ICMSLAM_HINTS"); P.hints = (h->hint_map == h->d_map_in && !(eh && atoi(eh) == 0)) ? 1 : 0; }
-    const bool cert_able = h->use_cert && h->split && !h->coop_tail && h->B <= 255;
-    P.cert = (P.hints && cert_able) ? 1 : 0;
-    P.stamp = cert_able ? 1 : 0;
-    P.rho = h->dcfg.rmax * (1.0 + 1e-9);
-    P.marg_scale = (1.0 - 1e-9) * 65535.0 / (2.0 * sqrt(h->thr2_hi) * h->dcfg.dist_thr);
-    P.slack_unit = (1.0 - 1e-9) * h->dcfg.dist_thr / 256.0;
-    P.rsum = h->d_rsum; P.rmeta = h->d_rmeta; P.rcnt = h->d_rcnt; P.echk = h->d_echk;
-    P.xchk = h->d_xchk; P.ldchk = T;
-    P.c = h->d_c; P.fsum_x = h->d_fsum_x; P.fsum_y = h->d_fsum_y; P.cnt = h->d_cnt;
-    P.far_list = h->d_far_list; P.ts = h->d_ts; P.blk_far = h->d_blk_far;
-    P.obs_cap = h->obs_cap; P.iters = (o.reserved & 1) ? &st->newton_iters : nullptr;
-    P.prof = nullptr;
-    static long long* d_prof = nullptr;      // debug only (ICMSLAM_PROF=1): per-block phase stamps, summarised on stderr
-    const bool prof = getenv("ICMSLAM_PROF") && atoi(getenv("ICMSLAM_PROF")) > 0 && !h->use_graph;
-    if (prof) {
-        if (!d_prof) cudaMalloc(&d_prof, (size_t)h->n_tiles * 24 * sizeof(long long));
-        cudaMemsetAsync(d_prof, 0, (size_t)h->n_tiles * 24 * sizeof(long long), s);
-        P.prof = d_prof;
+    // the pose buffers ping-pong, and so do their projection parameters
+    double4* pp_in = h->d_ppar[xin == h->d_x2 ? 1 : 0];
+    double4* pp_out = h->d_ppar[xin == h->d_x2 ? 0 : 1];
+    {
+        int rc = ensure_ppar(h, xin, ldin, x0, pp_in);
+        if (rc) return rc;
     }
-    { const char* es = getenv("ICMSLAM_SKIP"); P.skip = es ? atoi(es) : 0; }
+    const int t_start = h->seg_lo - (h->seg_first ? 0 : 1);     // a later segment also forms the moments of its odd halo pose
+    RunParams R;
+    R.t_start = t_start; R.t_hi = h->seg_hi; R.off = h->d_off; R.ppar = pp_in; R.lmrec = h->d_lmrec; R.rec = h->d_rec;
+    R.tile_nchunks = h->d_tile_nchunks; R.tile_epoch = h->d_tile_epoch; R.dyn = h->d_dyn; R.dynx = h->d_dynx; R.ticket = h->d_ticket;
+    R.fsum_x = h->d_fsum_x; R.fsum_y = h->d_fsum_y; R.cnt = h->d_cnt; R.fix_scale = h->fix_scale;
+    R.far_list = h->d_far_list; R.ts = h->d_ts; R.farbits = h->d_farbits;
+    R.scan_dirty = h->d_scan_dirty; R.tile_flag = h->d_tile_flag; R.dirty_list = h->d_dirty_list;
+    AssocParams A;
+    A.first_halo = h->seg_first ? 0 : 1; A.bxy = h->d_bxy; A.cfg = h->dcfg; A.thr2_hi = h->thr2_hi; A.st = st; A.geom = h->d_fg_geom;
+    A.cell_start = h->d_fg_start; A.gpts = h->d_fg_pts; A.gidx = h->d_fg_idx; A.remap = h->d_remap;
+    { const char* eh = getenv("ICMSLAM_HINTS"); A.skip_hints = (eh && atoi(eh) == 0) ? 1 : 0; }
+    A.hints = (h->hint_map == h->d_map_in) ? 1 : 0;
+    A.c = h->d_c; A.obs_cap = h->obs_cap; A.R = R;
+    CK(cudaMemsetAsync(h->d_farbits, 0, (size_t)h->n_tiles * 4 * sizeof(unsigned), s));
     if (timing) CK(cudaEventRecord(h->ev[0], s));
-    fused_variant(h->tile_half, h->tile_tpp, h->tile_occ, h->split != 0)<<<h->n_tiles, 2 * h->tile_tpp * h->tile_half, h->fused_smem, s>>>(P);
-    if (h->split) {
+    if (h->use_runs) {
+        k_runs<<<h->n_tiles, RUNS_THREADS, 0, s>>>(R);
+    } else {
+        k_all_dirty<<<nblk(h->n_tiles, 256), 256, 0, s>>>(h->d_tile_flag, h->d_dirty_list, h->d_ts, h->n_tiles);
+    }
+    CK(cudaGetLastError());
+    if (timing) CK(cudaEventRecord(h->ev[2], s));
+    {
+        int nb = h->assoc_blocks < h->n_tiles ? h->assoc_blocks : h->n_tiles;
+        k_assoc_tiles<<<nb, AT_THREADS, h->fused_smem, s>>>(A);
         CK(cudaGetLastError());
-        if (timing) CK(cudaEventRecord(h->ev[2], s));      // (split mode: ev[0]..ev[2] = k_sweep_fused, ev[2]..ev[1] = the two solve kernels)
-        const int n_pairs = (h->seg_hi - h->seg_lo) / 2 + 2;      // poses of one colour (incl. the odd halo pose of a segment)
+    }
+    if (o.reserved & 1) { k_note_dirty<<<1, 1, 0, s>>>(st, h->d_ts); CK(cudaGetLastError()); }
+    if (timing) CK(cudaEventRecord(h->ev[3], s));
+    h->n_launch += 2;
+    {
+        SolveParams P;
+        P.T = T; P.t_lo = h->seg_lo; P.t_hi = h->seg_hi; P.first = h->seg_first;
+        P.xin = xin; P.ldin = ldin; P.xout = kout; P.ldout = kld;
+        P.x0[0] = x0[0]; P.x0[1] = x0[1]; P.x0[2] = x0[2];
+        P.inc = h->d_inc; P.ldinc = T; P.u = h->d_u; P.ldu = T; P.bm = h->d_bm; P.ldbm = T; P.dyn = h->d_dyn;
+        P.ppin = pp_in; P.ppout = pp_out; P.cfg = h->dcfg; P.tol = o.newton_tol; P.maxit = o.newton_maxit;
+        P.iters = (o.reserved & 1) ? &st->newton_iters : nullptr;
         cudaStream_t ss = s;
-        const bool fork = overlap && h->overlap_solve && !timing && !prof && h->side_stream;
+        const bool fork = overlap && h->overlap_solve && !timing && h->side_stream;
         if (fork) {      // the tail does not depend on the new poses: solve beside it
             CK(cudaEventRecord(h->ev_fork, s));
             CK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
             ss = h->side_stream;
         }
-        solve_variant(0, h->solve_occ)<<<nblk(2 * n_pairs, SOLVE_THREADS), SOLVE_THREADS, 0, ss>>>(P);
+        k_solve_tile<<<h->n_solve_tiles, ST_THREADS, 0, ss>>>(P);
         CK(cudaGetLastError());
-        solve_variant(1, h->solve_occ)<<<nblk(2 * n_pairs, SOLVE_THREADS), SOLVE_THREADS, 0, ss>>>(P);
         if (fork) {
-            CK(cudaGetLastError());
             CK(cudaEventRecord(h->ev_join, ss));
             h->join_pending = true;
         }
-        h->n_launch += 2;
+        h->n_launch += 1;
+        h->ppar_of = kout;      // the solve leaves the projection parameters of the new poses (all columns but a segment's halo)
     }
-    CK(cudaGetLastError());
     if (timing) CK(cudaEventRecord(h->ev[1], s));
-    if (prof) {
-        std::vector<long long> hp((size_t)h->n_tiles * 24);
-        cudaStreamSynchronize(s);
-        cudaMemcpy(hp.data(), d_prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-        double acc[24] = {0};
-        for (int b = 0; b < h->n_tiles; ++b)
-            for (int k = 1; k < 18; ++k) acc[k] += (double)(hp[(size_t)b * 24 + k] - hp[(size_t)b * 24 + k - 1]);
-        static const char* nm[24] = {"", "tile loads+sync", "proj params+sync", "tma issue+slt", "mbar wait+sync", "phase A (warp 0)", "barrier A",
-                                     "pass 1", "pass 2", "combine+far", "red solve", "barrier red", "black solve", "barrier black", "iters+far rank", "blk_far", "pose writes", "stat flush", "", "", "", "", "", ""};
-        double tot = 0; for (int k = 1; k < 18; ++k) tot += acc[k];
-        fprintf(stderr, "[prof] %d blocks, mean cycles per block %.0f\n", h->n_tiles, tot / h->n_tiles);
-        for (int k = 1; k < 18; ++k) fprintf(stderr, "[prof]   %-18s %8.0f  %5.1f%%\n", nm[k], acc[k] / h->n_tiles, 100.0 * acc[k] / tot);
-        {   // the certified attempt (stamps 18..23), over the tiles that went through it
-            double a2[6] = {0}; int nfast = 0;
-            for (int b = 0; b < h->n_tiles; ++b) {
-                const long long* q = &hp[(size_t)b * 24];
-                if (!q[23]) continue;
-                ++nfast;
-                a2[0] += (double)(q[18] - q[1]); a2[1] += (double)(q[19] - q[18]); a2[2] += (double)(q[20] - q[19]);
-                a2[3] += (double)(q[21] - q[20]); a2[4] += (double)(q[22] - q[21]); a2[5] += (double)(q[23] - q[22]);
-            }
-            static const char* n2[6] = {"proj+cert loads", "epoch vote", "scan", "records in", "landmarks in", "moments"};
-            fprintf(stderr, "[prof] certified attempts: %d tiles\n", nfast);
-            for (int k = 0; k < 6 && nfast; ++k) fprintf(stderr, "[prof]   %-18s %8.0f\n", n2[k], a2[k] / nfast);
-        }
-    }
-    k_tail_scan<<<1, 1024, 0, s>>>(h->d_blk_far, h->n_tiles, h->d_blk_prefix, st, h->d_ts, L, h->d_bb);
+    k_tail_scan<<<1, 1024, 0, s>>>(h->d_farbits, h->n_tiles, h->d_blk_prefix, st, h->d_ts, L, h->d_bb);
     CK(cudaGetLastError());
-    h->n_launch += 2;
+    h->n_launch += 1;
     return ICMSLAM_OK;
 }
 
@@ -835,7 +829,8 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
 static int fused_part_b(icmslam_handle* h)
 {
     const int L = h->Lcap;
-    k_tail_labels<<<148, 256, 0, h->stream>>>(h->d_ts, h->d_far_list, h->d_blk_prefix, h->tile_own, h->seg_lo, h->d_off, h->d_st, L, h->d_c,
+    const int t_start = h->seg_lo - (h->seg_first ? 0 : 1);
+    k_tail_labels<<<148, 256, 0, h->stream>>>(h->d_ts, h->d_far_list, h->d_blk_prefix, h->d_farbits, RT_TILE, t_start, h->d_off, h->d_st, L, h->d_c,
                                               h->d_newraw, h->d_newraw + L, h->d_cnt);
     CK(cudaGetLastError());
     h->n_launch += 1;
@@ -853,26 +848,6 @@ static int fused_part_c(icmslam_handle* h, double* dmap_out, int out_cap, int64_
     const double* min_y = h->d_map_in + L;
     double* raw_x = h->d_raw;
     double* raw_y = h->d_raw + L;
-    if (h->coop_tail) {
-        TailCoopParams P;
-        P.st = st; P.ts = ts; P.fsum_x = h->d_fsum_x; P.fsum_y = h->d_fsum_y; P.cnt = h->d_cnt; P.map_x = min_x; P.map_y = min_y;
-        P.inv_scale = 1.0 / h->fix_scale; P.cota = h->dcfg.cota; P.dist_thr = h->dcfg.dist_thr; P.thr2_lt = h->thr2_lt; P.thr1sq = h->thr1sq;
-        P.thr2_hi = h->thr2_hi; P.newraw = h->d_newraw; P.raw_x = raw_x; P.raw_y = raw_y; P.kflag = h->d_kflag; P.kpos = h->d_kpos;
-        P.kx = h->d_kx; P.ky = h->d_ky; P.kc = h->d_kc; P.parent = h->d_parent; P.bb = h->d_bb; P.max_cells = h->fg_cells;
-        P.geom = h->d_fg_geom; P.cell_cnt = h->d_fg_cnt; P.cell_start = h->d_fg_start; P.pts = h->d_fg_pts; P.gidx = h->d_fg_idx;
-        P.nn = h->d_nn; P.ind_flag = h->d_indflag; P.nnd2 = h->d_nnd2; P.map_out = dmap_out; P.cap_out = out_cap; P.ld_out = out_ld;
-        P.counts_state = h->d_counts; P.lmrec = h->d_lmrec; P.remap = h->d_remap; P.ind_pos = h->d_indpos; P.ind = h->d_ind; P.lab = h->d_lab;
-        P.used = h->d_used; P.rank = h->d_rank; P.ox = h->d_ox; P.oy = h->d_oy; P.oc = h->d_oc; P.blk_scratch = h->d_blk_scratch; P.Lcap = L;
-        void* args[] = {(void*)&P};
-        CK(cudaLaunchCooperativeKernel((const void*)k_tail_coop, dim3(h->coop_blocks), dim3(TC_THREADS), args, 0, s));
-        h->n_launch += 1;
-        h->grid_map = (out_ld == L && out_cap == L) ? dmap_out : nullptr;   // the grid now indexes the new map
-        h->hint_map = h->grid_map;                                          // ... and c[] / d_remap carry this sweep's labels into it
-        h->timed_fused = true;
-        h->lact_dirty = true;
-        if (h->join_pending) { CK(cudaStreamWaitEvent(s, h->ev_join, 0)); h->join_pending = false; }
-        return ICMSLAM_OK;
-    }
     k_fused_means<<<nblk(L, 256), 256, 0, s>>>(st, h->d_fsum_x, h->d_fsum_y, h->d_cnt, min_x, min_y, 1.0 / h->fix_scale, h->dcfg.cota,
                                                h->d_newraw, raw_x, raw_y, h->d_kflag, L);
     CK(cudaGetLastError());
@@ -1066,6 +1041,7 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
     if (memspace == ICMSLAM_HOST) {
         CK(cudaMemcpy2DAsync(h->d_x, (size_t)T * 8, x, (size_t)ld_x * 8, (size_t)T * 8, 3, cudaMemcpyHostToDevice, s));
         h->bytes_h2d += (int64_t)3 * T * 8;
+        h->ppar_of = nullptr;
         xin = h->d_x; ldin = T;
         xout = h->d_x2; ldout = T;
     }
@@ -1171,6 +1147,7 @@ extern "C" int icmslam_set_poses(icmslam_handle* h, const double* x, int64_t ld_
     CK(cudaMemcpy2DAsync(h->d_x, (size_t)T * 8, x, (size_t)ld_x * 8, (size_t)T * 8, 3, cudaMemcpyDefault, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->x_cur = 0;
+    h->ppar_of = nullptr;
     return ICMSLAM_OK;
 }
 
@@ -1201,6 +1178,7 @@ extern "C" int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const
     if (x) {
         CK(cudaMemcpy2DAsync(h->d_x, (size_t)T * 8, x, (size_t)ld_x * 8, (size_t)T * 8, 3, cudaMemcpyDefault, s));
         h->x_cur = 0;
+        h->ppar_of = nullptr;
     }
     const bool fused_mode = h->fused_ok && o.fused && o.schedule == ICMSLAM_SCHED_REDBLACK && o.solver == ICMSLAM_SOLVER_NEWTON &&
                             o.map_view == ICMSLAM_VIEW_PREV;
@@ -1209,6 +1187,10 @@ extern "C" int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const
         double* src = h->x_cur ? h->d_x2 : h->d_x;
         double* dst = h->x_cur ? h->d_x : h->d_x2;
         bool launched = false;
+        if (fused_mode) {      // projection parameters of poses that did not come out of the previous sweep's solve (outside the graph)
+            int rc = ensure_ppar(h, src, T, x0, h->d_ppar[src == h->d_x2 ? 1 : 0]);
+            if (rc) return rc;
+        }
         if (graph_ok && h->grid_map == h->d_map_in) {
             // steady state: the whole sweep (memsets + 15 kernels) replays as one CUDA graph
             icmslam_handle::GraphSlot* slot = nullptr;
@@ -1220,13 +1202,16 @@ extern "C" int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const
                 if (!slot) { drop_graphs(h); slot = &h->graphs[0]; }
                 cudaGraph_t graph = nullptr;
                 const int64_t nl0 = h->n_launch;
+                const double* pof = h->ppar_of;
                 const double* gm = h->grid_map;
                 const double* hm = h->hint_map;
                 CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
                 int rc = cudaMemsetAsync(h->d_counts, 0, (size_t)L * sizeof(double), s) == cudaSuccess ? ICMSLAM_OK : ICMSLAM_ERR_CUDA;
                 if (!rc) rc = sweep_core(h, src, T, dst, T, x0, o, -1, h->d_map_out, L, L);
                 cudaError_t ce = cudaStreamEndCapture(s, &graph);
+                h->graph_launches = (int)(h->n_launch - nl0);
                 h->n_launch = nl0;
+                h->ppar_of = pof;
                 h->grid_map = gm;
                 h->hint_map = hm;
                 if (rc || ce != cudaSuccess || !graph) {
@@ -1242,7 +1227,8 @@ extern "C" int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const
                 slot->tol = o.newton_tol; slot->maxit = o.newton_maxit;
             }
             CK(cudaGraphLaunch(slot->exec, s));
-            h->n_launch += (h->coop_tail ? 5 : 13) + (h->split ? 2 : 0);    // kernels of this library inside the graph
+            h->n_launch += h->graph_launches;    // kernels of this library inside the graph
+            h->ppar_of = dst;
             h->grid_map = h->d_map_out;
             h->hint_map = h->d_map_out;
             h->timed_fused = true;
@@ -1275,7 +1261,10 @@ extern "C" int icmslam_set_segment(icmslam_handle* h, int32_t t_lo, int32_t t_hi
     if (!h || !h->extracted || t_lo < 0 || t_hi > h->T || t_lo >= t_hi || (t_lo & 1)) return ICMSLAM_ERR_INVALID;
     if ((!is_first && t_lo < 2) || (!is_last && t_hi > h->T - 1)) return ICMSLAM_ERR_INVALID;   // halo columns must exist
     h->seg_lo = t_lo; h->seg_hi = t_hi; h->seg_first = is_first ? 1 : 0; h->seg_last = is_last ? 1 : 0;
-    h->n_tiles = nblk(t_hi - t_lo, h->tile_own);
+    h->n_tiles = nblk(t_hi - (t_lo - (is_first ? 0 : 1)), RT_TILE);
+    h->n_solve_tiles = nblk(t_hi - t_lo, ST_OWN);
+    // the record tiling moved: no tile holds records (epoch -1)
+    CK(cudaMemsetAsync(h->d_tile_epoch, 0xff, ((size_t)nblk(h->T + 1, RT_TILE) + 2) * sizeof(int), h->stream));
     drop_graphs(h);
     return ICMSLAM_OK;
 }
@@ -1334,7 +1323,8 @@ extern "C" int icmslam_seg_exchange(icmslam_handle* h, const double* gathered, i
 {
     if (!h || !gathered || !h->seg_dst || rank < 0 || rank >= world) return ICMSLAM_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));
-    k_seg_unpack<<<1, 32, 0, h->stream>>>(gathered, rank, world, h->seg_dst, h->T, h->T, h->d_st, h->d_ts, h->Lcap);
+    k_seg_unpack<<<1, 32, 0, h->stream>>>(gathered, rank, world, h->seg_dst, h->T, h->T, h->d_st, h->d_ts, h->Lcap,
+                                          h->d_ppar[h->seg_dst == h->d_x2 ? 1 : 0]);
     CK(cudaGetLastError());
     h->n_launch += 1;
     return fused_part_b(h);
@@ -1362,9 +1352,12 @@ extern "C" int icmslam_get_kernel_ms(icmslam_handle* h, double* out2)
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->stream));
     float a = 0.f, b = 0.f;
-    if (h->timed_fused && h->split) {      // fused path, split mode: k_sweep_fused | k_solve_colour x 2
-        CK(cudaEventElapsedTime(&a, h->ev[0], h->ev[2]));
-        CK(cudaEventElapsedTime(&b, h->ev[2], h->ev[1]));
+    if (h->timed_fused) {      // fused path: k_runs + k_assoc_tiles | k_solve_tile
+        CK(cudaEventElapsedTime(&a, h->ev[0], h->ev[3]));
+        CK(cudaEventElapsedTime(&b, h->ev[3], h->ev[1]));
+        float r = 0.f;
+        CK(cudaEventElapsedTime(&r, h->ev[0], h->ev[2]));
+        h->last_runs_ms = r;
     } else {
         CK(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
         if (!h->timed_fused) CK(cudaEventElapsedTime(&b, h->ev[2], h->ev[3]));
@@ -1440,9 +1433,9 @@ extern "C" int icmslam_get_sweep_stats(icmslam_handle* h, int64_t* stats, int32_
     const DevState* s = h->h_st;
     TailState hts;
     CK(cudaMemcpy(&hts, h->d_ts, sizeof(TailState), cudaMemcpyDeviceToHost));
-    int64_t v[12] = {(int64_t)s->newton_iters, s->n_far_scans, s->raw_l, s->kept, s->new_l, s->n_ind, s->lsearch, s->status, s->cert_tiles,
-                     hts.epoch, (int64_t)(hts.G * 1e12), hts.remap_identity};
-    for (int i = 0; i < n && i < 12; ++i) stats[i] = v[i];
+    int64_t v[16] = {(int64_t)s->newton_iters, s->n_far_scans, s->raw_l, s->kept, s->new_l, s->n_ind, s->lsearch, s->status, s->dirty_tiles,
+                     hts.epoch, (int64_t)h->n_tiles, hts.remap_identity, (int64_t)(h->last_runs_ms * 1e6), hts.n_dirty, hts.far_count, 0};
+    for (int i = 0; i < n && i < 16; ++i) stats[i] = v[i];
     return ICMSLAM_OK;
 }
 
@@ -1601,6 +1594,7 @@ extern "C" int icmslam_pass0(icmslam_handle* h, const double* x0, double* x, int
     if (h->h_st->status & ST_LABEL_CAP) return ICMSLAM_ERR_LABEL_CAP;
     const int lact = h->h_st->lact;
     h->x_cur = 0;
+    h->ppar_of = nullptr;
     // ---- Mapa.filtrar on the map that was built (sensors.py:99-100) ---------------------------------------------------
     k_counts_to_int<<<nblk(L, 256), 256, 0, s>>>(h->d_tmp_b, L, h->d_cnt);      // (get_raw_map reports integer counts)
     CK(cudaGetLastError());

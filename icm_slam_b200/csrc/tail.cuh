@@ -7,7 +7,7 @@
 //   k_tail_scan      exclusive scan of the per-tile counts of scans with far observations
 //   k_tail_labels    one thread per far scan: label = lact0 + rank in time order (ICM_SLAM.py:174-182),
 //                    statistics of the new label, rewrite of the scan's far labels
-//   k_fused_means    (fused.cuh) raw map from the fixed-point statistics + keep flags (cota, :231-239)
+//   k_fused_means    raw map from the fixed-point statistics + keep flags (cota, :231-239)
 //   [cub scan]       positions of the kept landmarks
 //   k_tail_compact   kept landmarks -> dense arrays + bounding box
 //   k_fgrid_geom / k_fgrid_count / [cub scan] / k_fgrid_fill      (fastgrid.cuh)
@@ -35,36 +35,65 @@ struct TailState {
     int label_base;     // such scans in the segments before this one (0 on a single GPU)
     int remap_identity; // the filter kept every landmark of the previous map in place and no new label survived: labels below
                         // lsearch keep their meaning (labels created in the sweep may have come and gone)
-    int epoch;          // certificates (fused.cuh) stamped in another epoch are void: bumped whenever landmark indices change
-    int pad;
-    double G;           // (unused)
-    unsigned long long drift_bits;
+    int epoch;          // label-numbering epoch: run records (runs.cuh) built in another epoch are void; bumped whenever landmark
+                        // indices change (a merge or a drop in Mapa.filtrar, a map supplied by the caller)
+    int n_dirty;        // tiles the steady-state kernel handed to the association kernel this sweep
 };
 
 // A landmark as the fused kernel reads it by label: position and the squared radius inside which an
 // observation is PROVABLY nearest to it and inside the gate (see hint_radius2).
 struct __align__(32) LmRec {
-    double x, y, r2, g;     // g: odometer of this record (label certificates, fused.cuh): total motion of (x, y) plus loss of radius
+    double x, y, r2, r;     // r = sqrt(r2) rounded down: the radius the run records are certified against (runs.cuh)
 };
 
 // r2 = min(thr2_hi, (nnd/2)^2 (1 - 2^-30)) with nnd a lower bound of the distance to the nearest other
 // landmark: an observation with |obs - A|^2 <= r2 has |obs - B| >= nnd - |obs - A| > |obs - A| for every other
 // landmark B with a relative margin of 2^-31, far above the rounding of the distance computation, so
 // argmin(cdist) == A with no tie, and sqrt_rn(|obs - A|^2) <= dist_thr.  nnd2_seen is the squared distance to
-// the nearest other landmark found in the landmark's own grid cell list, which contains every landmark within
-// thr1 of it: if none was found, nnd > thr1.
-__device__ __forceinline__ double hint_radius2(double nnd2_seen, double thr1sq, double thr2_hi)
+// the nearest other landmark found in the cells that were searched, reach2 the squared distance within which those
+// cells are known to contain EVERY landmark (thr1^2 for the landmark's own cell list, (2 thr1)^2 for the 3 x 3 block
+// around it, see nearest_other_wide): if none was found, nnd^2 > reach2.
+__device__ __forceinline__ double hint_radius2(double nnd2_seen, double reach2, double thr2_hi)
 {
-    const double q = 0.25 * fmin(nnd2_seen, thr1sq) * (1.0 - 9.3132257461547852e-10);
+    const double q = 0.25 * fmin(nnd2_seen, reach2) * (1.0 - 9.3132257461547852e-10);
     return fmin(q, thr2_hi);
+}
+
+// Squared distance from landmark j at (xj, yj) to the nearest OTHER landmark registered in the 3 x 3 block of cells around
+// its own cell.  A cell is at least 2 thr1 wide and every landmark is registered (at least) in the cell that contains it,
+// so the block holds every landmark within 2 thr1 of j: a landmark whose neighbours are all farther than that is the
+// nearest landmark of every point within thr1 of it, i.e. its proven radius reaches the gate.
+__device__ __forceinline__ double nearest_other_wide(const FGeom& g, const int* __restrict__ cell_start, const double2* __restrict__ pts,
+                                                     const int* __restrict__ idx, int j, double xj, double yj)
+{
+    int cx = __double2int_rd((xj - g.x0) * g.inv_h), cy = __double2int_rd((yj - g.y0) * g.inv_h);
+    cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1);
+    double best = INFINITY;
+    for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.ny - 1); ++yy)
+        for (int xx = max(cx - 1, 0); xx <= min(cx + 1, g.nx - 1); ++xx) {
+            const int c = yy * g.nx + xx;
+            for (int k = cell_start[c]; k < cell_start[c + 1]; ++k) {
+                if (idx[k] == j) continue;
+                const double2 p = pts[k];
+                best = fmin(best, dist2_rn(p.x - xj, p.y - yj));      // (a coincident landmark gives 0: its hints are never trusted)
+            }
+        }
+    return best;
 }
 
 // What neighbouring time segments tell each other after a sweep (16 doubles per rank, all-gathered):
 // [0..2] first owned pose, [3..5] second-to-last owned pose, [6..8] last owned pose, [9] far_total.
 #define SEG_REC 16
 
+// scans of tile i that created a label this sweep: one bit per scan of the tile (runs.cuh finalize_scan)
+__device__ __forceinline__ int tile_far_count(const unsigned* __restrict__ farbits, int i)
+{
+    const uint4 w = *reinterpret_cast<const uint4*>(farbits + (size_t)i * 4);
+    return __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+}
+
 __global__ void __launch_bounds__(1024)
-k_tail_scan(const int* __restrict__ blk_far, int nblk_, int* __restrict__ blk_prefix, DevState* st, TailState* ts, int Lcap,
+k_tail_scan(const unsigned* __restrict__ farbits, int nblk_, int* __restrict__ blk_prefix, DevState* st, TailState* ts, int Lcap,
             unsigned long long* bb)
 {
     __shared__ int wsum[32];
@@ -72,7 +101,7 @@ k_tail_scan(const int* __restrict__ blk_far, int nblk_, int* __restrict__ blk_pr
     const int per = (nblk_ + 1023) / 1024;
     const int lo = min(tid * per, nblk_), hi = min(lo + per, nblk_);
     int s = 0;
-    for (int i = lo; i < hi; ++i) s += blk_far[i];
+    for (int i = lo; i < hi; ++i) s += tile_far_count(farbits, i);
     int inc = s;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(FULLMASK, inc, d); if (lane >= d) inc += o; }
@@ -86,7 +115,7 @@ k_tail_scan(const int* __restrict__ blk_far, int nblk_, int* __restrict__ blk_pr
     }
     __syncthreads();
     int run = inc - s + (warp ? wsum[warp - 1] : 0);
-    for (int i = lo; i < hi; ++i) { blk_prefix[i] = run; run += blk_far[i]; }
+    for (int i = lo; i < hi; ++i) { blk_prefix[i] = run; run += tile_far_count(farbits, i); }
     if (tid == 0) {
         const int total = wsum[31];
         ts->far_total = total;
@@ -102,14 +131,19 @@ k_tail_scan(const int* __restrict__ blk_far, int nblk_, int* __restrict__ blk_pr
 }
 
 __global__ void __launch_bounds__(256)
-k_tail_labels(const TailState* ts, const FarRec* __restrict__ far, const int* __restrict__ blk_prefix, int tile, int t_lo, const int* __restrict__ off,
-              const DevState* st, int Lcap, int* __restrict__ c, double* __restrict__ raw_x, double* __restrict__ raw_y, int* __restrict__ cnt)
+k_tail_labels(const TailState* ts, const FarRec* __restrict__ far, const int* __restrict__ blk_prefix, const unsigned* __restrict__ farbits, int tile,
+              int t_start, const int* __restrict__ off, const DevState* st, int Lcap, int* __restrict__ c, double* __restrict__ raw_x,
+              double* __restrict__ raw_y, int* __restrict__ cnt)
 {
     const int nrec = ts->far_count;
     const int lact0 = st->lact0 + ts->label_base;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nrec; k += gridDim.x * blockDim.x) {
         const FarRec r = far[k];
-        const int label = lact0 + blk_prefix[(r.t - t_lo) / tile] + r.rank;
+        // rank in time order: label-creating scans of the tiles before this one + those of this tile before the scan
+        const int ti = (r.t - t_start) / tile, lt = (r.t - t_start) % tile;
+        int rank = __popc(farbits[(size_t)ti * 4 + (lt >> 5)] & ((1u << (lt & 31)) - 1u));
+        for (int k = 0; k < (lt >> 5); ++k) rank += __popc(farbits[(size_t)ti * 4 + k]);
+        const int label = lact0 + blk_prefix[ti] + rank;
         if (label >= Lcap) continue;
         raw_x[label] = r.sx / (double)r.n;
         raw_y[label] = r.sy / (double)r.n;
@@ -117,6 +151,32 @@ k_tail_labels(const TailState* ts, const FarRec* __restrict__ far, const int* __
         for (int i = off[r.t]; i < off[r.t + 1]; ++i)
             if (c[i] < 0) c[i] = label;
     }
+}
+
+// raw map of the previous-map landmarks from the fixed-point statistics + keep flags for all labels;
+// clears the statistics for the next sweep.
+__global__ void __launch_bounds__(256)
+k_fused_means(const DevState* st, long long* fsum_x, long long* fsum_y, const int* __restrict__ cnt,
+              const double* __restrict__ map_x, const double* __restrict__ map_y, double inv_scale, double cota,
+              double* newraw /* 2 x Lcap: means of this sweep's new labels, zero elsewhere; cleared here.  ALIASES fsum_x / fsum_y
+                                (old labels use a word as int64 sum, new labels as double mean: disjoint index ranges) */,
+              double* __restrict__ raw_x, double* __restrict__ raw_y, int* __restrict__ flag, int Lcap)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= Lcap) return;
+    const int raw_l = st->raw_l, ls = st->lsearch;
+    const int k = l < raw_l ? cnt[l] : 0;
+    if (l < ls) {
+        raw_x[l] = k > 0 ? map_x[l] + ((double)fsum_x[l] * inv_scale) / (double)k : 0.0;
+        raw_y[l] = k > 0 ? map_y[l] + ((double)fsum_y[l] * inv_scale) / (double)k : 0.0;
+    } else {
+        const bool have = l < raw_l && k > 0;
+        raw_x[l] = have ? newraw[l] : 0.0;
+        raw_y[l] = have ? newraw[Lcap + l] : 0.0;
+    }
+    newraw[l] = 0.0; newraw[Lcap + l] = 0.0;
+    fsum_x[l] = 0; fsum_y[l] = 0;
+    flag[l] = (l < raw_l && !((double)k < cota)) ? 1 : 0;      // ICM_SLAM.py:232-236
 }
 
 // kept landmarks -> dense (kx, ky, kc), union-find parents, bounding box (ordered-key atomics)
@@ -189,7 +249,8 @@ k_tail_nn(const DevState* st, TailState* ts, const double* __restrict__ kx, cons
     const int f = (arg >= 0 && best <= thr2_lt) ? 1 : 0;      // amin < dist_thr (strict, :245)
     nn[j] = arg < 0 ? 0 : arg;
     ind_flag[j] = f;
-    nnd2[j] = best;
+    // for the hint radius: the nearest other survivor within 2 thr1 (only searched when none is closer than the gate)
+    nnd2[j] = f ? best : nearest_other_wide(g, cell_start, pts, idx, j, xj, yj);
     if (f) atomicAdd(&ts->n_ind, 1);
 }
 
@@ -203,20 +264,13 @@ k_tail_finalize(DevState* st, TailState* ts, const double* __restrict__ kx, cons
     if (ts->n_ind != 0 || ts->degenerate) return;   // k_tail_slow takes over
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     const int newL = st->kept;
-    double dl = 0.0;
     if (r < Lcap) {
         const double c = r < newL ? kc[r] : 0.0;
         const double mx = r < newL ? mul_rn(kx[r], c) / c : 0.0, my = r < newL ? mul_rn(ky[r], c) / c : 0.0;
         if (r < cap_out) { map_out[r] = mx; map_out[ld_out + r] = my; }
         counts_state[r] = c;
         LmRec rec;
-        rec.x = mx; rec.y = my; rec.r2 = r < newL ? hint_radius2(nnd2[r], thr1sq, thr2_hi) : 0.0; rec.g = 0.0;
-        if (r < newL) {       // how far this landmark's record moved (position in the 1-norm, plus any loss of hint radius)
-            const LmRec old = lmrec[r];
-            dl = fabs(mx - old.x) + fabs(my - old.y) + fmax(sqrt(old.r2) - sqrt(rec.r2), 0.0);
-            if (!(dl >= 0.0)) dl = INFINITY;
-            rec.g = old.g + dl * (1.0 + 1e-9);
-        }
+        rec.x = mx; rec.y = my; rec.r2 = r < newL ? hint_radius2(nnd2[r], 4.0 * thr1sq, thr2_hi) : 0.0; rec.r = __dsqrt_rd(rec.r2);
         lmrec[r] = rec;
         remap[r] = (r < st->raw_l && kflag[r]) ? kpos[r] : -1;      // label of this sweep -> index in the new map
         if (r == 0) { st->new_l = newL; st->lact = newL; st->n_ind = 0; }
@@ -236,15 +290,9 @@ k_lmrec_build(const double* __restrict__ mx, const double* __restrict__ my, cons
     if (j >= *n_ptr) return;
     const FGeom g = *geom;
     const double xj = mx[j], yj = my[j];
-    const int c = fgrid_cell(g, xj, yj);
-    double best = INFINITY;
-    for (int k = cell_start[c]; k < cell_start[c + 1]; ++k) {
-        if (idx[k] == j) continue;
-        const double2 p = pts[k];
-        best = fmin(best, dist2_rn(p.x - xj, p.y - yj));      // (a coincident landmark gives 0: its hints are never trusted)
-    }
+    const double best = nearest_other_wide(g, cell_start, pts, idx, j, xj, yj);
     LmRec rec;
-    rec.x = xj; rec.y = yj; rec.r2 = hint_radius2(best, thr1sq, thr2_hi); rec.g = 0.0;
+    rec.x = xj; rec.y = yj; rec.r2 = hint_radius2(best, 4.0 * thr1sq, thr2_hi); rec.r = __dsqrt_rd(rec.r2);
     lmrec[j] = rec;
 }
 
@@ -401,16 +449,11 @@ __device__ void tail_slow_body(DevState* st, TailState* ts, double dist_thr, dou
         __syncthreads();
         for (int r = tid; r < Lcap; r += nth) {       // landmark records of the merged map
             LmRec rec;
-            rec.x = 0.0; rec.y = 0.0; rec.r2 = 0.0; rec.g = 0.0;
+            rec.x = 0.0; rec.y = 0.0; rec.r2 = 0.0; rec.r = 0.0;
             if (r < newL) {
                 const double x = map_out[r], y = map_out[ld_out + r];
-                const int c = fgrid_cell(g, x, y);
-                double best = INFINITY;
-                for (int k = cell_start[c]; k < cell_start[c + 1]; ++k) {
-                    if (gidx[k] == r) continue;
-                    best = fmin(best, dist2_rn(pts[k].x - x, pts[k].y - y));
-                }
-                rec.x = x; rec.y = y; rec.r2 = hint_radius2(best, thr1sq, thr2_hi);
+                const double best = nearest_other_wide(g, cell_start, pts, gidx, r, x, y);
+                rec.x = x; rec.y = y; rec.r2 = hint_radius2(best, 4.0 * thr1sq, thr2_hi); rec.r = __dsqrt_rd(rec.r2);
             }
             lmrec[r] = rec;
         }
@@ -425,7 +468,7 @@ k_tail_slow(DevState* st, TailState* ts, double dist_thr, double* kx, double* ky
             int max_cells, FGeom* geom, int* cell_cnt, int* cell_start, double2* pts, int* gidx,
             const int* kflag, const int* kpos, double thr1sq, double thr2_hi, LmRec* lmrec, int* remap)
 {
-    // certificates: void every one of them when landmark indices changed
+    // run records (runs.cuh) name landmarks by index: void every one of them when landmark indices changed
     // (k_tail_finalize has completed: this launch follows it on the stream)
     if (threadIdx.x == 0) {
         const bool fast = ts->n_ind == 0 && !ts->degenerate;
@@ -454,7 +497,7 @@ __global__ void k_seg_pack(const double* __restrict__ x, int64_t ld, int t_lo, i
 // after the all-gather: neighbours' boundary poses into this segment's halo columns (0, 1 and T-1), and the
 // global numbering of the new labels (exclusive prefix over the ranks of far_total, ICM_SLAM.py:174-182)
 __global__ void k_seg_unpack(const double* __restrict__ all, int rank, int world, double* __restrict__ x, int64_t ld, int T, DevState* st,
-                             TailState* ts, int Lcap)
+                             TailState* ts, int Lcap, double4* __restrict__ ppar)
 {
     const int i = threadIdx.x;
     if (i < 3) {
@@ -465,6 +508,10 @@ __global__ void k_seg_unpack(const double* __restrict__ all, int rank, int world
         }
         if (rank + 1 < world) x[i * ld + T - 1] = all[(size_t)(rank + 1) * SEG_REC + i];
     }
+    // projection parameters of the halo poses (the same expression the owner's solve used: bit-identical)
+    if (i == 3 && rank > 0) { const double* l = all + (size_t)(rank - 1) * SEG_REC; ppar[0] = make_ppar(l[3], l[4], l[5]); }
+    if (i == 4 && rank > 0) { const double* l = all + (size_t)(rank - 1) * SEG_REC; ppar[1] = make_ppar(l[6], l[7], l[8]); }
+    if (i == 5 && rank + 1 < world) { const double* l = all + (size_t)(rank + 1) * SEG_REC; ppar[T - 1] = make_ppar(l[0], l[1], l[2]); }
     if (i == 0) {
         int base = 0, total = 0;
         for (int r = 0; r < world; ++r) {

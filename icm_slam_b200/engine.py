@@ -249,16 +249,11 @@ class Engine:
         check(self.lib.icmslam_get_transfer_bytes(self._h, C.byref(a), C.byref(b)), self._h)
         return int(a.value), int(b.value)
 
-    def fused_split(self):
-        """True when the fused path runs as k_sweep_fused + two k_solve_colour launches (the default; ICMSLAM_SPLIT=0 selects the
-        single-launch kernel)."""
-        return os.environ.get("ICMSLAM_SPLIT", "1") != "0"
-
     def sweep_stats(self):
-        v = (C.c_int64 * 12)()
-        check(self.lib.icmslam_get_sweep_stats(self._h, v, 12), self._h)
-        keys = ["newton_iters", "n_far_scans", "raw_L", "kept", "new_L", "n_ind", "lsearch", "status", "cert_tiles", "cert_epoch",
-                "cert_G_pm", "stable_ids"]
+        v = (C.c_int64 * 16)()
+        check(self.lib.icmslam_get_sweep_stats(self._h, v, 16), self._h)
+        keys = ["newton_iters", "n_far_scans", "raw_L", "kept", "new_L", "n_ind", "lsearch", "status", "dirty_tiles", "epoch",
+                "n_tiles", "stable_ids", "k_runs_ns", "n_dirty_now", "far_count", "_"]
         return dict(zip(keys, [int(t) for t in v]))
 
     # -- map utilities --------------------------------------------------------------------------

@@ -197,6 +197,12 @@ class SegmentedSolver:
             self._bind()
         if getattr(self, "_allrec", None) is None:
             self._allrec = torch.empty((self.world, SEG_REC), dtype=torch.float64, device="cuda:%d" % self.device)
+        # The collectives run on torch's current stream over zero-copy views of the library's buffers, so the library must
+        # enqueue on that same stream, or nothing orders its kernels against the collectives.  The solver owns one stream
+        # for both (the legacy default stream cannot be captured into a graph) and orders it against the caller's.
+        if getattr(self, "_stream", None) is None:
+            self._stream = torch.cuda.Stream(device=self.device)
+            self.engine.set_stream(self._stream.cuda_stream)
 
     def sweep(self, n_sweeps: int = 1, use_graph: bool = True):
         """n_sweeps sweeps of the whole trajectory (collective: every rank calls it).  In steady state two consecutive
@@ -204,34 +210,37 @@ class SegmentedSolver:
         the pose and map buffers ping-pong)."""
         import torch
         self._prepare()
-        done = 0
-        while done < n_sweeps:
-            left = n_sweeps - done
-            if use_graph and left >= 2 and self._steady >= 2:
-                g = self._graphs.get(self._parity)
-                if g is None:            # one graph per ping-pong parity of the pose / map buffers
-                    cur = torch.cuda.current_stream()
-                    cur.synchronize()
-                    g = torch.cuda.CUDAGraph()
-                    side = torch.cuda.Stream(device=self.device)
-                    self.engine.set_stream(side.cuda_stream)       # (before the capture starts: set_stream synchronises)
-                    with torch.cuda.graph(g, stream=side):
-                        self._sweep_once()
-                        self._sweep_once()
-                    self.engine.set_stream(cur.cuda_stream)
-                    self._graphs[self._parity] = g                 # (capture records the work without running it)
-                g.replay()
-                self._launches += 2 * self._launches_per_sweep
-                done += 2
-                self._steady += 2
-            else:
-                n0 = self.engine.launch_count()
-                self._sweep_once()
-                self._launches_per_sweep = self.engine.launch_count() - n0
-                self._launches += self._launches_per_sweep
-                self._steady += 1
-                self._parity ^= 1
-                done += 1
+        caller = torch.cuda.current_stream(self.device)
+        self._stream.wait_stream(caller)
+        with torch.cuda.stream(self._stream):
+            done = 0
+            while done < n_sweeps:
+                left = n_sweeps - done
+                if use_graph and left >= 2 and self._steady >= 2:
+                    g = self._graphs.get(self._parity)
+                    if g is None:            # one graph per ping-pong parity of the pose / map buffers
+                        self._stream.synchronize()
+                        g = torch.cuda.CUDAGraph()
+                        side = torch.cuda.Stream(device=self.device)
+                        self.engine.set_stream(side.cuda_stream)       # (before the capture starts: set_stream synchronises)
+                        with torch.cuda.graph(g, stream=side):
+                            self._sweep_once()
+                            self._sweep_once()
+                        self.engine.set_stream(self._stream.cuda_stream)
+                        self._graphs[self._parity] = g                 # (capture records the work without running it)
+                    g.replay()
+                    self._launches += 2 * self._launches_per_sweep
+                    done += 2
+                    self._steady += 2
+                else:
+                    n0 = self.engine.launch_count()
+                    self._sweep_once()
+                    self._launches_per_sweep = self.engine.launch_count() - n0
+                    self._launches += self._launches_per_sweep
+                    self._steady += 1
+                    self._parity ^= 1
+                    done += 1
+        caller.wait_stream(self._stream)
 
     @property
     def _graph(self):
@@ -293,7 +302,6 @@ def bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, p
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     sol = SegmentedSolver(cfg, rank, world, device=local_rank)
-    sol.engine.set_stream(stream.cuda_stream)
     n_local = sol.load(d["observations"], d["odometry"], d["velocities"], precondition=True)
     sol.set_map(d["map_init"])
     sol.set_poses(d["x_init"])
@@ -359,7 +367,7 @@ def bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, p
         peak, peak_src = peaks()
         # the dominant kernel's share of the sweep on one rank: its segment's bytes over its time
         Tseg = sol.t_hi - sol.t_lo
-        if sol.engine.fused_split():     # k_sweep_fused's own share (poses, offsets, observations, map in; labels, statistics out)
+        if True:     # k_runs' own share (poses, offsets, observations, map in; labels, statistics out)
             seg_bytes = 24 * Tseg + 4 * (Tseg + 1) + 16 * n_local + 16 * L_true + 4 * n_local + 24 * L_true
         else:
             seg_bytes = sweep_bytes(Tseg, n_local, L_true)

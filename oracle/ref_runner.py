@@ -1,11 +1,13 @@
 """TEST INFRASTRUCTURE ONLY -- drives the UNMODIFIED reference modules.
 
 This file imports the reference's own Python modules from /root/reference/scripts
-(read-only, present only in the build container; it does NOT travel to the GPU box)
+(read-only, present only in the build container) or from the git-ignored copy
+baseline/_ref/scripts (made by baseline/setup_ref.py; it travels to the GPU box)
 behind stub `roslibpy` / `matplotlib` modules, and replays the reference's offline
 path without a ROS network.  It is used by `oracle/make_golden.py` to mint the
-fixtures committed under tests/golden/, and by CPU tests that are skipped when the
-reference is absent.  Nothing in the product package imports it.
+fixtures committed under tests/golden/, by CPU tests that are skipped when the
+reference is absent, and by bench.py's reference arm / cpu_baseline leg (the timed
+CPU baseline).  Nothing in the product package imports it.
 
 What is replayed (reference file:line):
   * pass 0  = sensors.py:61-104 (`ICM_ROS.inicializar_online` minus the ROS wait loop)
@@ -22,7 +24,19 @@ from copy import deepcopy
 
 import numpy as np
 
-REF_DIR = os.environ.get("ICM_REF_DIR", "/root/reference/scripts")
+def _find_ref_dir():
+    """ICM_REF_DIR, else the read-only reference of the build container, else the copy baseline/setup_ref.py ships to the GPU box."""
+    env = os.environ.get("ICM_REF_DIR")
+    if env:
+        return env
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for d in ("/root/reference/scripts", os.path.join(here, "baseline", "_ref", "scripts")):
+        if os.path.isfile(os.path.join(d, "sensors.py")):
+            return d
+    return "/root/reference/scripts"
+
+
+REF_DIR = _find_ref_dir()
 
 CONFIG_ROS = dict(  # values of scripts/config_ros.yaml
     N=30, deltat=0.1, L=1000, Q=[1, 1], R=[1, 1, 1], cte_odom=1.0, cota=300.0,

@@ -1,0 +1,69 @@
+"""torchrun worker of tests/test_gpu_scale.py::test_two_nccl_ranks_equal_the_single_engine_bit_for_bit.
+
+Every rank runs the time-segmented sweep over REAL NCCL collectives (SegmentedSolver, no stream pre-binding by the caller);
+rank 0 also runs the same sweeps on one engine and writes both result hashes (poses + map + labels) to argv[1]."""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def digest(x, mapa):
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(x, dtype=np.float64).tobytes())
+    h.update(np.ascontiguousarray(mapa, dtype=np.float64).tobytes())
+    return h.hexdigest()
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from helpers import CONFIG_ROS
+    from icm_slam_b200.config import ConfigICM
+    from icm_slam_b200.engine import Engine
+    from icm_slam_b200.multigpu import SegmentedSolver
+    from icm_slam_b200.synthetic import make_synthetic
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L_true, T, nsweeps = 900, 9000, 7
+    d = make_synthetic(L_true, T=T, seed=20181 + 21)
+    # two landmarks missing from the initial map: their observations are far, scans create labels on both segments
+    map0 = np.delete(d["map_init"], [17, 640], axis=1)
+    cfg = ConfigICM.from_values(**dict(CONFIG_ROS, L=2 * L_true + 64, cota=20.0))
+    sol = SegmentedSolver(cfg, rank, world, device=local)
+    sol.load(d["observations"], d["odometry"], d["velocities"], precondition=True)
+    sol.set_map(map0)
+    sol.set_poses(d["x_init"])
+    sol.sweep(nsweeps)                       # eager sweeps, then the captured two-sweep graph
+    torch.cuda.synchronize()
+    x_seg = sol.gather_poses()
+    m_seg = sol.get_map()
+    res = {"segmented": digest(x_seg, m_seg)}
+    if rank == 0:
+        e = Engine(cfg, device=local)
+        e.load(d["observations"], d["odometry"], d["velocities"], precondition=True)
+        e.extract()
+        e.set_map(map0)
+        e.set_poses(d["x_init"])
+        e.iterate(None, d["odometry"][:, 0], nsweeps)
+        res["single"] = digest(e.get_poses(), e.get_map())
+        res["max_pose_diff"] = float(np.max(np.abs(e.get_poses() - x_seg)))
+        with open(sys.argv[1], "w") as f:
+            json.dump(res, f)
+        e.close()
+    dist.barrier()
+    sol.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

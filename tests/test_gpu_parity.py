@@ -405,12 +405,8 @@ def test_fused_launch_count_and_kernel_timer():
     n0 = e.launch_count()
     e.iterate(None, d["odometry"][:, 0], 2, timing=True)
     a, b = e.kernel_ms()
-    if e.fused_split():      # k_sweep_fused | the two k_solve_colour launches
-        assert a > 0.0 and b > 0.0
-        assert e.launch_count() - n0 >= 2 * 15
-    else:
-        assert a > 0.0 and b == 0.0
-        assert e.launch_count() - n0 >= 2 * 13
+    assert a > 0.0 and b > 0.0      # k_runs + k_assoc_tiles | k_solve_tile
+    assert e.launch_count() - n0 >= 2 * 14
     e.close()
 
 
@@ -514,26 +510,6 @@ def test_segmented_solver_single_rank_graph_replay():
     sol.close(); single.close()
 
 
-def test_cooperative_tail_matches_kernel_chain(monkeypatch):
-    """ICMSLAM_COOP_TAIL=1: landmark update + Mapa.filtrar + grid as ONE cooperative launch, same results bit for bit
-    (with merges on the real log and without on the synthetic one)."""
-    g = golden("c1_ref.npz")
-    z, odo, u = c1_inputs()
-    d, cfgd = _synthetic_case(625, 3000, 20181 + 16)
-    for (zz, oo, uu, cd, m0, x0p) in ((z, odo, u, dict(CONFIG_ROS), g["p0_map"], g["p0_x"]),
-                                     (d["observations"], d["odometry"], d["velocities"], cfgd, d["map_init"], d["x_init"])):
-        res = []
-        for coop in ("0", "1"):
-            monkeypatch.setenv("ICMSLAM_COOP_TAIL", coop)
-            e = _engine(_cfg(**cd), zz, oo, uu)
-            e.set_map(m0); e.set_poses(x0p)
-            e.iterate(None, oo[:, 0], 5)
-            res.append((e.get_poses(), e.get_map(), e.associations(), e.counts(e.landmarks_actuales)))
-            e.close()
-        for a, b in zip(*res):
-            assert np.array_equal(a, b)
-
-
 def test_fused_exact_ties_and_duplicate_landmarks():
     """Exact duplicates in the previous map make every observation near them an exact distance tie (np.argmin takes
     the first index), near-duplicates exercise Mapa.filtrar's merge path, displaced landmarks create new labels:
@@ -599,8 +575,8 @@ def test_offline_batch_path_through_the_reference_surface():
     assert mapa_refinado.shape == (2, 11)         # the notebook's 11 trees
 
 
-# ---- label certificates + run cache (fused.cuh): a certified sweep must equal the uncertified one bit for bit ----
-def _chain(z, odo, u, cfgd, map0, x_init, nsweeps, env):
+# ---- run records (runs.cuh): steady-state sweeps on certified run records must equal full re-association bit for bit ----
+def _chain(z, odo, u, cfgd, map0, x_init, nsweeps, env, stats=False):
     import os
     old = {k: os.environ.get(k) for k in env}
     os.environ.update(env)
@@ -616,35 +592,36 @@ def _chain(z, odo, u, cfgd, map0, x_init, nsweeps, env):
     e.set_poses(np.ascontiguousarray(x_init.copy()))
     out = []
     for k in range(nsweeps):
-        e.iterate(None, odo[:, 0], 1, fused=True)
+        e.iterate(None, odo[:, 0], 1, fused=True, stats=stats)
         st = e.sweep_stats()
-        out.append((e.get_poses().copy(), e.get_map().copy(), e.associations().copy(), st["cert_tiles"]))
+        out.append((e.get_poses().copy(), e.get_map().copy(), e.associations().copy(), st["dirty_tiles"], st["n_tiles"]))
     e.close()
     return out
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("gname", ["synth_a.npz", "synth_b.npz"])
-def test_certified_sweeps_equal_uncertified_synthetic(gname):
+def test_run_record_sweeps_equal_full_association_synthetic(gname):
     g = golden(gname)
     z, odo, u = g["observations"].astype(np.float64), g["odometry"], g["velocities"]
     cfgd = dict(L=int(g["cfg_L"]), cota=float(g["cfg_cota"]))
-    a = _chain(z, odo, u, cfgd, g["map_init"], g["x_init"], 8, {"ICMSLAM_CERT": "0"})
-    b = _chain(z, odo, u, cfgd, g["map_init"], g["x_init"], 8, {"ICMSLAM_CERT": "1"})
+    a = _chain(z, odo, u, cfgd, g["map_init"], g["x_init"], 8, {"ICMSLAM_RUNS": "0"}, stats=True)
+    b = _chain(z, odo, u, cfgd, g["map_init"], g["x_init"], 8, {"ICMSLAM_RUNS": "1"}, stats=True)
     for k, (ra, rb) in enumerate(zip(a, b)):
         assert np.array_equal(ra[2], rb[2]), k
         assert np.array_equal(ra[0], rb[0]), k          # poses: bit for bit
         assert np.array_equal(ra[1], rb[1]), k          # map: bit for bit
-        assert ra[3] == 0
-    assert any(r[3] > 0 for r in b), "no tile ever ran on certificates: %r" % ([r[3] for r in b],)
+        assert ra[3] == ra[4]                           # RUNS=0: every tile through the association kernel
+    assert b[0][3] == b[0][4], "the first sweep has no records to run on"
+    assert any(r[3] < r[4] for r in b[1:]), "no tile ever ran on its run records: %r" % ([r[3:] for r in b],)
 
 
 @pytest.mark.gpu
-def test_certified_sweeps_equal_uncertified_c1():
+def test_run_record_sweeps_equal_full_association_c1():
     g = golden("c1_ref.npz")
     z, odo, u = c1_inputs()
-    a = _chain(z, odo, u, dict(CONFIG_ROS), g["p0_map"], g["p0_x"], 6, {"ICMSLAM_CERT": "0"})
-    b = _chain(z, odo, u, dict(CONFIG_ROS), g["p0_map"], g["p0_x"], 6, {"ICMSLAM_CERT": "1"})
+    a = _chain(z, odo, u, dict(CONFIG_ROS), g["p0_map"], g["p0_x"], 6, {"ICMSLAM_RUNS": "0"})
+    b = _chain(z, odo, u, dict(CONFIG_ROS), g["p0_map"], g["p0_x"], 6, {"ICMSLAM_RUNS": "1"})
     for k, (ra, rb) in enumerate(zip(a, b)):
         assert np.array_equal(ra[2], rb[2]), k
         assert np.array_equal(ra[0], rb[0]), k
@@ -708,23 +685,17 @@ def test_run_offline_one_call_matches_stepwise(tmp_path):
         assert np.array_equal(back["x"], res["x"]) and np.array_equal(back["mapa"], res["mapa"])
 
 
-# ---- the sweep's variants: same labels; poses / map identical where the same compiled kernels run (scheduling variants) and
-#      equal to rounding where another template instantiation does the arithmetic (nvcc contracts FMAs per instantiation) -----
+# ---- the sweep's variants: scheduling and staging switches change nothing (bit for bit) ---------------------------------
 @pytest.mark.gpu
-@pytest.mark.parametrize("env,exact", [({"ICMSLAM_OVERLAP": "0"}, True), ({"ICMSLAM_GRAPH": "0"}, True),
-                                       ({"ICMSLAM_SPLIT": "0"}, False), ({"ICMSLAM_TILE": "32"}, False),
-                                       ({"ICMSLAM_TILE": "16", "ICMSLAM_SOLVE_OCC": "768"}, False),
-                                       ({"ICMSLAM_SPLIT": "0", "ICMSLAM_TILE": "32"}, False)])
-def test_sweep_variants_agree(env, exact):
+@pytest.mark.parametrize("env", [{"ICMSLAM_OVERLAP": "0"}, {"ICMSLAM_GRAPH": "0"}, {"ICMSLAM_RUNS": "0"}, {"ICMSLAM_OBS_CAP": "96"},
+                                 {"ICMSLAM_BLOCKS_PER_SM": "1"}])
+def test_sweep_variants_agree(env):
     g = golden("synth_b.npz")
     z, odo, u = g["observations"].astype(np.float64), g["odometry"], g["velocities"]
     cfgd = dict(L=int(g["cfg_L"]), cota=float(g["cfg_cota"]))
-    base = {"ICMSLAM_SPLIT": "1", "ICMSLAM_TILE": "64", "ICMSLAM_OVERLAP": "1", "ICMSLAM_GRAPH": "1", "ICMSLAM_SOLVE_OCC": "512"}
+    base = {"ICMSLAM_OVERLAP": "1", "ICMSLAM_GRAPH": "1", "ICMSLAM_RUNS": "1"}
     a = _chain(z, odo, u, cfgd, g["map_init"], g["x_init"], 5, dict(base))
     b = _chain(z, odo, u, cfgd, g["map_init"], g["x_init"], 5, dict(base, **env))
     for k, (ra, rb) in enumerate(zip(a, b)):
         assert np.array_equal(ra[2], rb[2]), (env, k)
-        if exact:
-            assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1]), (env, k)
-        else:
-            assert np.max(np.abs(ra[0] - rb[0])) <= 1e-10 and ra[1].shape == rb[1].shape and np.max(np.abs(ra[1] - rb[1])) <= 1e-10, (env, k)
+        assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1]), (env, k)
