@@ -1,26 +1,34 @@
 #!/usr/bin/env python
-"""bench.py -- ICM sweeps/s on synthetic range-bearing data (BASELINE.json metric).
+"""bench.py -- ICM sweeps/s (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c1] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c1|c5|ijac|palomar] [--impl reference]
 
 One "step" = one ICM sweep (iterations_process_offline, sensors.py:125-168) over the whole
 trajectory: projection, association, landmark statistics, pose update, map filter.  Scan
-extraction (filtrar_z) is sweep-invariant and cached, as SURVEY.md 8(d) defines the metric.
+extraction (filtrar_z) is sweep-invariant and cached, as SURVEY.md 8(d) defines the metric; its
+throughput is reported separately (`extraction`).
 
-* `value`    : sweeps/s with poses, observations and map resident in HBM (icmslam_iterate).
+* `value`    : sweeps/s with poses, observations and map resident in HBM (icmslam_iterate), steady
+               state (the sweeps after the first run on certified run records, runs.cuh); the first
+               sweep of a map chain -- every tile through the association kernel -- is `cold_sweep_ms`.
 * `e2e`      : the same sweep through the reference-facing call
                ICM_SLAM.iterations_process_offline(mapa_viejo, x) with HOST numpy buffers:
                poses + map go host->device and come back inside the timed region.
 * `roofline` : the dominant kernel's algorithmic bytes / its CUDA-event duration vs the measured
                HBM copy bandwidth (MEASURED_PEAKS.json).
-* `cpu_baseline` / `--impl reference`: the CPU oracle port of the reference's own semantics
-               (sequential Gauss-Seidel + Nelder-Mead + running means) on a bounded prefix.
+* `cpu_baseline` / `--impl reference`: the UNMODIFIED reference (baseline/_ref, copied by
+               baseline/setup_ref.py; imported through oracle/ref_runner.py) on the host cores, on a
+               bounded prefix of the same workload against the full map; extrapolated numbers say so.
+* `result_sha256`: hash of poses + map + labels after warm-up + steps: identical for 1/2/4/8 GPUs.
 
+Workloads: c4 (default, the metric's configuration), c3, c1 (synthetic smoke), c5 (4096 independent
+trajectories), ijac / palomar (the reference's two real logs: pass 0 + sweeps, as shipped).
 Under torchrun (N > 1) the trajectory is split into N contiguous time segments, one per GPU.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -39,9 +47,15 @@ WORKLOADS = {
     "c4": (316 * 316, 1_000_000, "synthetic 2D range-bearing: 1M poses / 99 856 (316^2) landmarks, 181-beam scans"),
     "c3": (100 * 100, 100_000, "synthetic 2D range-bearing: 100k poses / 10k landmarks, 181-beam scans"),
     "c1": (16 * 16, 2048, "synthetic 2D range-bearing: 2048 poses / 256 landmarks (smoke size)"),
+    "c5": (16, 2048, "batch of independent synthetic trajectories (T = 2048, 16 landmarks each), 512 per GPU"),
+    "ijac": (11, 1833, "data_IJAC2018.mat as shipped (T = 1833, 181 beams), config_ros.yaml values, pass 0 + sweeps"),
+    "palomar": (11, 1833, "datos_palomar1.mat as shipped (raw log: filtrar_obs pre-pass), config_ros.yaml values, pass 0 + sweeps"),
 }
+REAL_LOGS = {"ijac": "data_IJAC2018.mat", "palomar": "datos_palomar1.mat"}
 SEED = 20181
 METRIC = "ICM sweeps/sec (1M poses,100k lmk) at 1/2/4/8 B200; % HBM roofline"
+CONFIG_ROS = dict(N=30, deltat=0.1, L=1000, Q=[1, 1], R=[1, 1, 1], cte_odom=1.0, cota=300.0, dist_thr=1.0, dist_thr_obs=1.0,
+                  rango_laser_max=10.0, radio=0.137)
 
 
 def peaks():
@@ -52,18 +66,44 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def config_for(L_true):
+def config_for(L_true, name="c4"):
     from icm_slam_b200.config import ConfigICM
+    if name in REAL_LOGS:
+        return ConfigICM.from_values(**CONFIG_ROS)
     return ConfigICM.from_values(N=1, L=2 * L_true, cota=20.0)
 
 
+def ref_dir():
+    for d in (os.path.join(ROOT, "baseline", "_ref", "scripts"), "/root/reference/scripts"):
+        if os.path.isfile(os.path.join(d, "sensors.py")):
+            return d
+    return None
+
+
 def make_data(name):
-    from icm_slam_b200.synthetic import make_synthetic
-    L_true, T, _ = WORKLOADS[name]
+    """Synthetic workloads: the generator; real logs: the .mat file of the reference copy (baseline/_ref)."""
     t0 = time.time()
-    d = make_synthetic(L_true, T=T, seed=SEED + {"c1": 1, "c3": 3, "c4": 4}[name])
+    if name in REAL_LOGS:
+        from icm_slam_b200.icm import load_mat
+        rd = ref_dir()
+        if rd is None:
+            raise SystemExit("workload %s needs the reference's logs under baseline/_ref (python baseline/setup_ref.py)" % name)
+        z, odo, u = load_mat(os.path.join(rd, REAL_LOGS[name]))
+        d = dict(observations=z, odometry=odo, velocities=u)
+    else:
+        from icm_slam_b200.synthetic import make_synthetic
+        L_true, T, _ = WORKLOADS[name]
+        d = make_synthetic(L_true, T=T, seed=SEED + {"c1": 1, "c3": 3, "c4": 4}[name])
     d["gen_s"] = time.time() - t0
     return d
+
+
+def result_hash(x, mapa, c):
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(x, dtype=np.float64).tobytes())
+    h.update(np.ascontiguousarray(mapa, dtype=np.float64).tobytes())
+    h.update(np.ascontiguousarray(c, dtype=np.int32).tobytes())
+    return h.hexdigest()
 
 
 class ClockSampler:
@@ -120,58 +160,87 @@ def sweep_bytes(T, n, L):
     return 92 * T + 20 * n + 40 * L + 4
 
 
+def runs_bytes(T, n, L):
+    """Share of the run / association kernels: poses 24T + offsets 4(T+1) + observations 16n + map 16L in, labels 4n +
+    statistics 24L out (the solve moves the rest: odometry 24T + controls 16T in, poses 24T out)."""
+    return 24 * T + 4 * (T + 1) + 16 * n + 16 * L + 4 * n + 24 * L
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_arm(name, d, budget_poses=None):
-    """Times the CPU oracle in the reference's own mode on a prefix of the workload.  Returns
-    (sweeps_per_s_extrapolated, sample description, seconds, P)."""
-    from oracle import oracle as orc
+    """Times the UNMODIFIED reference (`ICM_ROS.iterations_process_offline`, sensors.py:125-168, imported from baseline/_ref)
+    on the host.  Synthetic workloads: one sweep over a prefix of P poses against the FULL map (the reference cannot run
+    the full size: ~0.2 s per pose at 1e5 landmarks), scaled linearly to T.  Real logs: one full sweep after its own pass 0.
+    Returns (sweeps_per_s, sample, seconds, P, extrapolated)."""
+    from oracle import ref_runner as rr
+    import scipy
     L_true, T, _ = WORKLOADS[name]
-    cfg = config_for(L_true)
-    ocfg = orc.make_cfg(cfg)
-    P = budget_poses or {"c4": 1500, "c3": 12000, "c1": 2048}[name]
-    P = min(P, T)
-    z = d["observations"][:, :P]
-    ext = orc.extract_all(orc.precondition(z, ocfg.radio, ocfg.rango_laser_max), ocfg)
-    while P > 2 and ext["off"][P] == ext["off"][P - 1]:      # the reference needs a non-empty last scan
+    versions = "numpy %s / scipy %s, %d host cores, 1 used (the reference is single-threaded)" % (np.__version__, scipy.__version__, os.cpu_count())
+    if name in REAL_LOGS:
+        cfg = rr.make_config(**CONFIG_ROS)
+        z = d["observations"]
+        if name == "palomar":
+            from oracle import oracle as orc
+            z, _ = orc.filtrar_obs(z, 10.0, 15)       # (filtrar_obs.m is MATLAB: the restated pre-pass; not timed)
+        s = rr.make_solver(cfg, rr.precondition(z, cfg), d["odometry"], d["velocities"])
+        key = "_ref_p0_" + name
+        if key not in d:
+            t0 = time.perf_counter()
+            d[key] = rr.pass0(s)
+            d[key]["seconds"] = time.perf_counter() - t0
+        else:
+            s.mapa_obj.landmarks_actuales = d[key]["mapa"].shape[1]
+        x = np.ascontiguousarray(d[key]["x"].copy())
+        t0 = time.perf_counter()
+        rr.sweep(s, d[key]["mapa"], x)
+        dt = time.perf_counter() - t0
+        sample = ("unmodified reference iterations_process_offline on the whole log (T = %d), %.1f s per sweep (after its own pass 0, "
+                  "%.1f s, untimed); %s" % (T, dt, d[key]["seconds"], versions))
+        return 1.0 / dt, sample, dt, T, False
+    P = min(budget_poses or {"c4": 26, "c3": 60, "c1": 150}.get(name, 26), T)
+    cfg = rr.make_config(L=2 * L_true, cota=20.0, N=1)
+    zc = rr.precondition(d["observations"][:, :P + 1], cfg)
+    import ICM_SLAM as ref_icm
+    while P > 2 and np.size(ref_icm.filtrar_z(zc[:, P - 1], cfg)) == 0:      # the reference needs a non-empty last scan
         P -= 1
-    if P != z.shape[1]:
-        z = d["observations"][:, :P]
-        ext = orc.extract_all(orc.precondition(z, ocfg.radio, ocfg.rango_laser_max), ocfg)
-    odo = np.ascontiguousarray(d["odometry"][:, :P])
-    u = np.ascontiguousarray(d["velocities"][:, :P])
+    s = rr.make_solver(cfg, zc[:, :P], d["odometry"][:, :P], d["velocities"][:, :P])
+    s.mapa_obj.landmarks_actuales = d["map_init"].shape[1]
     x = np.ascontiguousarray(d["x_init"][:, :P].copy())
-    m = orc.Mapa(ocfg)
-    m.landmarks_actuales = d["map_init"].shape[1]
     t0 = time.perf_counter()
     try:
-        orc.sweep(ocfg, m, ext, odo, u, odo[:, 0], d["map_init"], x, "sequential", "nm", "running")
+        rr.sweep(s, d["map_init"], x)
     except ValueError:
-        pass   # a short prefix may leave no landmark above cota; the timed work is already done
+        pass   # a short prefix may leave no landmark above cota (ICM_SLAM.py:255); the timed work is already done
     dt = time.perf_counter() - t0
-    sweeps_per_s = 1.0 / (dt * (T / P))
-    sample = ("oracle C port of the reference semantics (sequential Gauss-Seidel, Nelder-Mead xtol=1e-3, running means, "
-              "brute-force association against all %d landmarks) on the first %d of %d poses (%d observations), %.2f s; "
-              "sweeps/s extrapolated linearly to the full trajectory" % (d["map_init"].shape[1], P, T, ext["n"], dt))
-    return sweeps_per_s, sample, dt, P
+    sample = ("unmodified reference iterations_process_offline on the first %d of %d poses against the full %d-landmark map, %.2f s; "
+              "sweeps/s EXTRAPOLATED linearly to the full trajectory (the reference cannot run this size); %s"
+              % (P, T, d["map_init"].shape[1], dt, versions))
+    return 1.0 / (dt * (T / P)), sample, dt, P, True
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     name = args.workload
+    if ref_dir() is None:
+        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref is missing (python baseline/setup_ref.py copies the reference where /root/reference exists)"}), flush=True)
+        return
     d = make_data(name)
-    vals = []
-    sample = ""
-    for i in range(args.warmup + args.steps):
-        v, sample, dt, P = cpu_reference_arm(name, d, args.ref_poses)
-        if i >= args.warmup:
-            vals.append((v, dt))
-    v = float(np.mean([a for a, _ in vals]))
+    real = name in REAL_LOGS
+    steps, warm = (min(args.steps, 2), min(args.warmup, 0)) if real else (args.steps, args.warmup)
+    vals, sample, extrap, P = [], "", True, 0
+    for i in range(warm + steps):
+        v, sample, dt, P, extrap = cpu_reference_arm(name, d, args.ref_poses)
+        if i >= warm:
+            vals.append(v)
+    v = float(np.mean(vals))
     L_true, T, desc = WORKLOADS[name]
-    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "sweeps/s", "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-           "dtype": "f64", "data": "synthetic", "config": {"workload": desc, "T": T, "L_true": L_true, "seed": SEED},
-           "cpu_baseline": {"value": v, "unit": "sweeps/s", "cores": 1, "kind": "port", "sample": sample},
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": "sweeps/s", "n_gpus": args.gpus, "steps": steps,
+           "warmup": warm, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f64", "data": "real log" if real else "synthetic",
+           "config": {"workload": desc, "T": T, "L_true": L_true, "seed": SEED, "sample_poses": P, "steps_requested": args.steps},
+           "extrapolated": bool(extrap),
+           "cpu_baseline": {"value": v, "unit": "sweeps/s", "cores": 1, "kind": "reference", "sample": sample, "extrapolated": bool(extrap)},
            "e2e": {"value": v, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
@@ -179,39 +248,68 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 def run_gpu(args, rank, world, local_rank):
     import torch
-    import torch.distributed as dist
-    from icm_slam_b200.config import ConfigICM   # noqa: F401
     from icm_slam_b200.engine import Engine
-    from icm_slam_b200.icm import ICM_SLAM, Mapa, precondicionar
+    from icm_slam_b200.icm import ICM_SLAM, Mapa
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libicmslam has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    name = args.workload
+    if name == "c5":
+        from icm_slam_b200 import batch
+        return batch.bench(args, rank, world, local_rank, SEED, METRIC, peaks, ClockSampler, sweep_bytes)
     if world > 1:
         from icm_slam_b200 import multigpu
         return multigpu.bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, peaks, ClockSampler, make_data,
-                              config_for)
+                              config_for, result_hash, runs_bytes)
 
-    name = args.workload
     L_true, T, desc = WORKLOADS[name]
+    real = name in REAL_LOGS
     d = make_data(name)
-    cfg = config_for(L_true)
+    cfg = config_for(L_true, name)
     x0 = d["odometry"][:, 0].copy()
     dev = torch.device("cuda", local_rank)
+    B = int(d["observations"].shape[0])
 
     # ---- device-resident arm --------------------------------------------------------------------
     eng = Engine(cfg, device=local_rank)
     stream = torch.cuda.Stream(device=dev)          # (the legacy default stream cannot capture CUDA graphs)
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
+    z = d["observations"]
+    if name == "palomar":
+        z = eng.filtrar_obs(z, float(cfg.rango_laser_max), 15)       # filtrar_obs.m pre-pass on the GPU (row a1)
     t0 = time.time()
-    eng.load(d["observations"], d["odometry"], d["velocities"], precondition=True)
+    eng.load(z, d["odometry"], d["velocities"], precondition=True)
+    load_s = time.time() - t0
+    # extraction (filtrar_z of every scan, once per dataset): CUDA events around the two passes, scans already in HBM
+    ex0, ex1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ex0.record(stream)
     n = eng.extract()
-    prep_s = time.time() - t0
-    eng.set_poses(d["x_init"])                 # ICM.positions resident on the device
-    eng.set_map(d["map_init"])
-    x_dev = None
+    ex1.record(stream)
+    torch.cuda.synchronize()
+    extract_ms = ex0.elapsed_time(ex1)
+    if real:
+        x_init, map_init = eng.pass0(x0)              # the causal initialisation (sensors.py:51-123), native
+    else:
+        x_init, map_init = d["x_init"], d["map_init"]
     mode = dict(schedule="redblack", solver="newton", view="prev")
+    # cold sweeps: a fresh map chain, every tile through the association kernel (what a 2-sweep config_default.yaml user gets)
+    cold = []
+    for _ in range(3):
+        eng.set_poses(x_init)
+        eng.set_map(map_init)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        eng.iterate(None, x0, 1, **mode)
+        c1.record(stream)
+        torch.cuda.synchronize()
+        cold.append(c0.elapsed_time(c1))
+    eng.set_poses(x_init)                 # ICM.positions resident on the device
+    eng.set_map(map_init)
+    x_dev = None
     for _ in range(args.warmup):
         eng.iterate(x_dev, x0, 1, **mode)
     torch.cuda.synchronize()
@@ -219,7 +317,6 @@ def run_gpu(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kms = []
     torch.cuda.synchronize()
     ev0.record(stream)
     for _ in range(args.steps):
@@ -230,34 +327,21 @@ def run_gpu(args, rank, world, local_rank):
     clocks = sampler.stop()
     launches = (eng.launch_count() - lc0) // max(args.steps, 1)
     L_now = eng.landmarks_actuales
+    sha = result_hash(eng.get_poses(), eng.get_map(), eng.associations())
     # kernel time of the dominant kernels, measured live with CUDA events on the handle's stream in a
     # separate short loop (reading the events synchronises, so it stays out of the timed region)
-    kt = []
+    kt, dirty = [], []
     for _ in range(max(3, min(args.steps, 10))):
-        eng.iterate(x_dev, x0, 1, timing=True, **mode)
+        eng.iterate(x_dev, x0, 1, timing=True, stats=True, **mode)
         kt.append(eng.kernel_ms())
-    k_assoc_ms = float(np.mean([a for a, _ in kt]))
-    k_pose_ms = float(np.mean([b for _, b in kt]))
-    fused = True
+        st = eng.sweep_stats()
+        dirty.append(st["dirty_tiles"])
+        k_runs_only = st["k_runs_ns"] * 1e-6
+    k_runs_ms = float(np.mean([a for a, _ in kt]))
+    k_solve_ms = float(np.mean([b for _, b in kt]))
     B_sweep = sweep_bytes(T, n, L_true)
     peak, peak_src = peaks()
-    if fused and k_pose_ms > 0.0:
-        # split mode: k_sweep_fused (association + moments + landmark statistics; reads poses 24T, offsets 4(T+1), observations
-        # 16n, map 16L; writes labels 4n, statistics 24L) and two k_solve_colour launches (poses, odometry, controls in; poses
-        # out).  The dominant kernel is reported with ITS share of the sweep's algorithmic bytes.
-        dom_name, dom_ms = "k_runs+k_assoc_tiles", k_assoc_ms
-        dom_bytes = 24 * T + 4 * (T + 1) + 16 * n + 16 * L_true + 4 * n + 24 * L_true
-    elif fused:
-        dom_name, dom_ms, dom_bytes = "k_sweep_fused", k_assoc_ms, B_sweep
-    else:
-        # two kernels share the sweep's bytes: association (reads poses 24T, obs 16n, map; writes c 4n) and the
-        # pose kernels (read poses/odometry/controls/obs/c, write poses).  The dominant one is reported.
-        b_assoc = 24 * T + 4 * (T + 1) + 16 * n + 16 * L_true + 4 * n
-        b_pose = 24 * T + 24 * T + 16 * T + 4 * (T + 1) + 16 * n + 4 * n + 16 * L_true + 24 * T
-        if k_assoc_ms >= k_pose_ms:
-            dom_name, dom_ms, dom_bytes = "k_assoc", k_assoc_ms, b_assoc
-        else:
-            dom_name, dom_ms, dom_bytes = "k_pose_colour(x2)", k_pose_ms, b_pose
+    dom_name, dom_ms, dom_bytes = "k_runs (+ k_assoc_tiles on the %d dirty of %d tiles)" % (int(np.max(dirty)), st["n_tiles"]), k_runs_ms, runs_bytes(T, n, L_true)
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     sweep_achieved = B_sweep / (ms * 1e-3) / 1e9
     traffic = None
@@ -265,58 +349,70 @@ def run_gpu(args, rank, world, local_rank):
     if os.path.isfile(tp):
         try:
             with open(tp) as f:
-                traffic = json.load(f).get(name, {}).get(dom_name)
+                traffic = json.load(f).get(name, {}).get("k_runs")
         except Exception:
             traffic = None
+    B_extract = 8 * B * T + 20 * n
 
     # ---- end-to-end arm: the reference-facing call with HOST buffers --------------------------------
     icm = ICM_SLAM(cfg, x0=x0)
-    icm._engine.close()
-    icm._engine = eng                                      # same device dataset; only the call path differs
     icm.mediciones, icm.odometria, icm.u = d["observations"], d["odometry"], d["velocities"]
-    icm._loaded = (id(icm.mediciones), id(icm.u), id(icm.odometria), np.shape(icm.mediciones))
     icm.mapa_obj = Mapa(cfg)
-    icm.mapa_obj._attach(eng)
-    x_host_t = torch.from_numpy(d["x_init"].copy()).pin_memory()
-    x_host = x_host_t.numpy()
-    mapa = d["map_init"].copy()
-    icm.mapa_obj.landmarks_actuales = mapa.shape[1]
+    icm.adopt_engine(eng)                                  # same device dataset; only the call path differs
     e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        mapa_w, _ = icm.iterations_process_offline(mapa, x_host)
-    torch.cuda.synchronize()
-    tb0 = eng.transfer_bytes()                 # bytes the library actually copies (a map fed back unchanged is not re-uploaded)
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        mapa, _ = icm.iterations_process_offline(mapa, x_host)
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    tb1 = eng.transfer_bytes()
-    h2d, d2h = tb1[0] - tb0[0], tb1[1] - tb0[1]
 
-    # ---- CPU baseline (rank 0, N = 1): bounded sample -----------------------------------------------
+    def e2e_loop(x_host):
+        mapa = np.array(map_init, copy=True)
+        icm.mapa_obj.landmarks_actuales = mapa.shape[1]
+        for _ in range(2):
+            mapa, _ = icm.iterations_process_offline(mapa, x_host)
+        torch.cuda.synchronize()
+        tb0 = eng.transfer_bytes()             # bytes the library actually copies (a map fed back unchanged is not re-uploaded)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            mapa, _ = icm.iterations_process_offline(mapa, x_host)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        tb1 = eng.transfer_bytes()
+        return dt, (tb1[0] - tb0[0]) // e2e_steps, (tb1[1] - tb0[1]) // e2e_steps
+
+    x_pinned = torch.from_numpy(np.array(x_init, copy=True)).pin_memory().numpy()
+    e2e_s, h2d, d2h = e2e_loop(x_pinned)
+    e2e_pageable_s, _, _ = e2e_loop(np.array(x_init, copy=True))
+
+    # ---- CPU baseline (rank 0, N = 1): bounded sample of the unmodified reference ---------------------------------
     cpu = None
-    if not args.no_cpu_baseline:
-        v, sample, dt, P = cpu_reference_arm(name, d, args.ref_poses)
-        cpu = {"value": v, "unit": "sweeps/s", "cores": 1, "kind": "port", "sample": sample}
+    if not args.no_cpu_baseline and ref_dir() is not None:
+        budget = args.ref_poses or {"c4": 100, "c3": 250, "c1": 600}.get(name)
+        v, sample, dt, P, extrap = cpu_reference_arm(name, d, budget)
+        cpu = {"value": v, "unit": "sweeps/s", "cores": 1, "kind": "reference", "sample": sample, "extrapolated": bool(extrap)}
+    elif not args.no_cpu_baseline:
+        cpu = {"value": None, "unit": "sweeps/s", "cores": 0, "kind": "reference", "sample": "baseline/_ref missing"}
 
     out = {
         "metric": METRIC, "value": 1000.0 / ms, "unit": "sweeps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "T": T, "L_true": L_true, "n_obs": int(n), "landmarks_after": int(L_now), "beams": 181,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "real log" if real else "synthetic",
+        "config": {"workload": desc, "T": T, "L_true": L_true, "n_obs": int(n), "landmarks_after": int(L_now), "beams": B,
                    "seed": SEED, "mode": "redblack/newton/prev", "partition": "1 time segment",
-                   "l2": "inputs larger than L2 (observations %.0f MB + poses/odometry/controls %.0f MB vs 126 MB L2)"
-                         % (16 * n / 1e6, 64 * T / 1e6),
-                   "prep_s": {"synthetic_gen": round(d["gen_s"], 2), "load_extract": round(prep_s, 2)}},
+                   "l2": "inputs larger than L2 (run records %.0f MB + observations %.0f MB + poses/odometry/controls %.0f MB vs 126 MB L2)"
+                         % (32 * 0.35 * n / 1e6, 16 * n / 1e6, 64 * T / 1e6) if not real else "whole problem L2-resident (a real log of 1833 scans)",
+                   "prep_s": {"data": round(d["gen_s"], 2), "load_h2d": round(load_s, 2)}},
         "clocks": clocks,
-        "e2e": {"value": 1.0 / e2e_s, "unit": "sweeps/s", "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
-                "steps": e2e_steps, "call": "ICM_SLAM.iterations_process_offline(mapa_viejo, x) with pinned host numpy buffers"},
+        "cold_sweep_ms": float(np.min(cold)),
+        "extraction": {"scans_per_s": T / (extract_ms * 1e-3), "ms": extract_ms, "algorithmic_bytes": int(B_extract),
+                       "achieved_gbs": B_extract / (extract_ms * 1e-3) / 1e9, "frac": B_extract / (extract_ms * 1e-3) / 1e9 / peak,
+                       "note": "filtrar_z of all T scans (two passes over the fp64 scan array + CSR build + host sync for the sizes), 8*B*T + 20*n bytes"},
+        "e2e": {"value": 1.0 / e2e_s, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_steps, "pageable_caller_buffers": 1.0 / e2e_pageable_s,
+                "call": "ICM_SLAM.iterations_process_offline(mapa_viejo, x) with pinned host numpy poses (value) / pageable ones"},
         "gpu_launches": int(launches) * args.steps,
         "gpu_launches_per_step": int(launches),
+        "result_sha256": sha,
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel_ms": dom_ms, "algorithmic_bytes": int(dom_bytes),
                      "sweep": {"algorithmic_bytes": int(B_sweep), "achieved": sweep_achieved, "frac": sweep_achieved / peak,
-                               "kernel_ms": {"assoc_or_fused": k_assoc_ms, "pose": k_pose_ms},
+                               "kernel_ms": {"k_runs": k_runs_only, "k_runs+k_assoc_tiles": k_runs_ms, "k_solve_tile": k_solve_ms},
                                "note": "whole sweep (all kernels of the graph replay) against the sweep's algorithmic bytes"}},
         "cpu_baseline": cpu,
     }
@@ -327,15 +423,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--ref-poses", type=int, default=None, help="prefix length for the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--kernel-times", action="store_true")
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "b200":
-        args.warmup = max(args.warmup, 1)
+    if args.impl == "b200":
+        args.warmup = max(args.warmup, 3)          # the first sweeps build the run records; steady state needs them
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

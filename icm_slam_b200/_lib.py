@@ -108,6 +108,8 @@ def lib():
     L.icmslam_filter_map.argtypes = [vp, vp, i64, vp, i32, vp, i32, i64, vp, _ip, i32]
     L.icmslam_calc_cambio.argtypes = [vp, vp, i32, i64, vp, i32, i64, vp, i32]
     L.icmslam_filtrar_obs.argtypes = [vp, vp, i32, i32, i64, dbl, i32, vp, i64, i32]
+    L.icmslam_associate.argtypes = [vp, vp, i32, i64, vp, vp, i32, vp, i32, i64, vp, i32]
+    L.icmslam_iterate_until.argtypes = [vp, vp, i32, dbl, C.POINTER(SweepOpts), vp, _ip]
     for name in EXPORTS:
         getattr(L, name)  # fail loudly if the header and the library disagree
         if name not in ("icmslam_strerror", "icmslam_last_error"):
@@ -123,7 +125,7 @@ EXPORTS = [
     "icmslam_sweep", "icmslam_get_associations", "icmslam_get_raw_map", "icmslam_get_sweep_stats", "icmslam_filter_map",
     "icmslam_calc_cambio", "icmslam_filtrar_obs", "icmslam_set_map", "icmslam_get_map", "icmslam_iterate",
     "icmslam_get_kernel_ms", "icmslam_get_launch_count", "icmslam_get_transfer_bytes", "icmslam_set_poses", "icmslam_get_poses", "icmslam_set_segment", "icmslam_device_ptr", "icmslam_seg_begin",
-    "icmslam_seg_exchange", "icmslam_seg_finish", "icmslam_fcluster", "icmslam_pass0",
+    "icmslam_seg_exchange", "icmslam_seg_finish", "icmslam_fcluster", "icmslam_pass0", "icmslam_associate", "icmslam_iterate_until",
 ]
 
 

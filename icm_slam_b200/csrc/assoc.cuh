@@ -23,7 +23,9 @@ struct DevState {
     double fx0, fy0, finv_h;
     int fnx, fny;
     double f_extent;  // max bbox extent of the kept landmarks
-    double cambio[3];
+    double cambio[3]; // calc_cambio of the sweep's map against the previous one, accumulated by the fast tail: min, max, sum
+    int cambio_unres; // new landmarks whose nearest old landmark the tail could not certify (then cambio[] is not usable)
+    int cambio_pad;
 };
 
 // ---- grid construction ---------------------------------------------------------------------

@@ -12,10 +12,9 @@
 //     (fastgrid.cuh) gives the nearest landmark by squared distance with the rooted values formed only inside a 2^-50 tie
 //     window, and the gate s > thr2_hi <=> sqrt(s) > dist_thr: bit-exact cdist + argmin + gate (ICM_SLAM.py:169-172);
 //   * pass 1 -- THREAD PAIR PER SCAN: each maximal group of beams with the same label becomes a run (sum of the body-frame
-//     points, beam count, largest distance of a beam from the centroid as the bound rho of runs.cuh);
-//   * the runs are packed scan by scan into 32-record chunks (a scan never straddles a chunk unless it has more than 32
-//     runs) and written to the tile's region of the record array;
-//   * the chunks are then processed by the SAME code as the steady state (process_chunk), so moments and statistics do not
+//     points, beam count, a bound rho on the distance of a beam from the centroid, runs.cuh), written to the scan's column of
+//     its slice of the record arrays together with the landmark's slot in the tile's statistics table;
+//   * the slices are then processed by the SAME code as the steady state (process_slice), so moments and statistics do not
 //     depend on which of the two kernels handled a scan.
 #pragma once
 #include "common.cuh"
@@ -27,10 +26,13 @@
 #define AT_THREADS (2 * RT_TILE)   // a thread pair per scan of the tile
 #define AT_WARPS (AT_THREADS / 32)
 #define AT_U 4                     // observations per lane in flight in phase A (pend bitmask: 64 / AT_U iterations per warp)
-#define AT_OBS_BYTES 25            // staged bytes per observation: (bx, by) 16, label 4, run length 2, rho code 2, scan 1
+#define AT_OBS_BYTES 23            // staged bytes per observation: (bx, by) 16, label 4, cell entry count 2, scan 1
+static_assert(AT_THREADS == 2 * RUNS_THREADS, "a tile's slices are processed by the first warps of the block");
 
 struct AssocParams {
     int first_halo;                       // the first scan of tile 0 is the halo scan of a time segment (moments only)
+    int T;                                // columns of the handle's trajectory
+    const int* off;                       // CSR offsets of the kept observations (T + 1)
     const double2* bxy;                   // body-frame observations (bx, by), CSR order
     DevCfg cfg;
     double thr2_hi;                       // largest s with sqrt_rn(s) <= dist_thr
@@ -49,12 +51,30 @@ struct __align__(16) AssocSmem {
     double2 pp[RT_TILE];           // projection origin of each scan (self.x0 for scan 0)
     double2 rsc[RT_TILE];          // (sin, cos) of (projection heading - pi/2)
     int off[RT_TILE + 4];          // off[t] of the tile's scans
-    int rcnt[RT_TILE];             // runs of each scan
-    int rstart[RT_TILE];           // slot of the scan's first run, relative to the tile's region
-    int gap[RT_TILE + 2][2];       // padding slots [begin, end)
-    int ngap, pos;
+    int hkey[RS_SLOTS];            // the tile's statistics slots: landmark of each slot (-1: free), assigned while the runs are written
+    int hcnt[RS_SLOTS];            // runs that name the slot
+    unsigned acc[RS_SLOTS][5];     // the statistics table itself (runs.cuh chunk_statistics)
     unsigned long long mbar;
 };
+
+// slot of landmark `label` in the tile's statistics table (open addressing, at most 8 probes); RS_NOSLOT when the table is
+// crowded or the slot already serves RS_MAX_ADDS runs (their statistics go straight to the global sums)
+__device__ __forceinline__ int slot_of(AssocSmem& S, int label)
+{
+    unsigned h = ((unsigned)label * 2654435761u) >> 24;
+#pragma unroll 1
+    for (int q = 0; q < 8; ++q) {
+        if (h == RS_NOSLOT) h = 0;
+        int key = ((volatile int*)S.hkey)[h];
+        if (key == -1) {
+            const int prev = atomicCAS(&S.hkey[h], -1, label);
+            key = (prev == -1) ? label : prev;
+        }
+        if (key == label) return atomicAdd(&S.hcnt[h], 1) < RS_MAX_ADDS ? (int)h : RS_NOSLOT;
+        h = (h + 1) & (RS_SLOTS - 1);
+    }
+    return RS_NOSLOT;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -74,9 +94,8 @@ k_assoc_tiles(const AssocParams p)
     AssocSmem& S = *reinterpret_cast<AssocSmem*>(smem_raw);
     double2* sb = reinterpret_cast<double2*>(smem_raw + sizeof(AssocSmem));             // staged observations; later run sums
     int* sbk_raw = reinterpret_cast<int*>(sb + p.obs_cap);                               // hints in (TMA), labels out; +4 ints of alignment slack
-    unsigned short* srn = reinterpret_cast<unsigned short*>(sbk_raw + p.obs_cap + 4);    // run length at run heads (phase A: cell entry count)
-    unsigned short* srho = srn + p.obs_cap;                                              // rho code at run heads
-    unsigned char* slt = reinterpret_cast<unsigned char*>(srho + p.obs_cap);             // scan (relative to the tile) of each observation
+    unsigned short* srn = reinterpret_cast<unsigned short*>(sbk_raw + p.obs_cap + 4);    // phase A: entries of the observation's grid cell
+    unsigned char* slt = reinterpret_cast<unsigned char*>(srn + p.obs_cap);              // scan (relative to the tile) of each observation
 
     const RunParams& R = p.R;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -104,14 +123,14 @@ k_assoc_tiles(const AssocParams p)
         const int nsc = min(RT_TILE, R.t_hi - tb);
         const bool commit_all = R.tile_flag[tile] == 2;
         const bool halo_tile = p.first_halo && tile == 0;
-        const int64_t base = run_tile_base(R.off, R.t_start, tile);
         // ---- tile loads -------------------------------------------------------------------------------------------
-        for (int li = tid; li <= nsc; li += AT_THREADS) S.off[li] = R.off[tb + li];
+        for (int li = tid; li <= nsc; li += AT_THREADS) S.off[li] = p.off[tb + li];
         if (tid < nsc) {
             const double4 pq = ldg_ppar(R.ppar + tb + tid);
             S.pp[tid] = make_double2(pq.x, pq.y); S.rsc[tid] = make_double2(pq.z, pq.w);
         }
-        if (tid == 0) { S.pos = 0; S.ngap = 0; }
+        for (int hh = tid; hh < RS_SLOTS; hh += AT_THREADS) { S.hkey[hh] = -1; S.hcnt[hh] = 0; }
+        stats_clear(S.acc);
         __syncthreads();
         // ---- chunks of whole scans whose observations fit the shared-memory budget (normally one) -----------------
         for (int c_lo = 0; c_lo < nsc;) {
@@ -268,98 +287,63 @@ k_assoc_tiles(const AssocParams p)
                 }
             }
             __syncthreads();     // the labels of the whole chunk are visible to the scan threads
-            // ---- pass 1 (thread pair per scan): runs of equal labels -> in-place run records --------------------------
+            // ---- pass 1 (thread pair per scan): runs of equal labels -> run records ------------------------------------------
+            // Each run goes straight to its slot: column (scan) of the scan's slice, row = index of the run in the scan.  rho: every
+            // beam and the centroid lie in the run's bounding box, so the farthest box corner from the centroid bounds
+            // |b_i - centroid| (float arithmetic with its rounding covered by the margins, then rounded up to 1/2048 m).
             int nr = 0;
+            const size_t slot0 = ((size_t)(tile * RT_SLICES + (q >> 5)) * R.maxr) * 32 + (q & 31);
+            // (the first half's run count is needed for the second half's row offset: count first, then write)
+            if (o < e) {
+                int bk = sbk[o];
+                for (int i = o + 1; i < e; ++i) { const int b2 = sbk[i]; nr += b2 != bk; bk = b2; }
+                ++nr;
+            }
+            const int nr_other = __shfl_xor_sync(FULLMASK, nr, 1);
+            const int rtot = nr + nr_other;
             if (o < e) {
                 // (the next observation is fetched before the current one is consumed)
+                int k = sub ? nr_other : 0;
                 int run_start = o, bk = sbk[o];
-                double2 b = sb[o], bfirst = b;
+                double2 b = sb[o];
                 double Sbx = 0.0, Sby = 0.0;
+                float mnx = INFINITY, mxx = -INFINITY, mny = INFINITY, mxy = -INFINITY;
                 for (int i = o; i < e; ++i) {
                     const int inx = min(i + 1, e - 1);
                     const double2 bn = sb[inx];
                     const int bkn = sbk[inx];
                     Sbx += b.x; Sby += b.y;
+                    const float fx = (float)b.x, fy = (float)b.y;
+                    mnx = fminf(mnx, fx); mxx = fmaxf(mxx, fx); mny = fminf(mny, fy); mxy = fmaxf(mxy, fy);
                     if (i + 1 == e || bkn != bk) {
-                        // rho = max |b_i - centroid| over the run's beams (second walk: the run's other beams are still staged)
-                        const double inv = 1.0 / (double)(i + 1 - run_start), cx = Sbx * inv, cy = Sby * inv;
-                        double r2m = fma(bfirst.x - cx, bfirst.x - cx, (bfirst.y - cy) * (bfirst.y - cy));
-                        for (int j = run_start + 1; j <= i; ++j) {
-                            const double2 bj = sb[j];
-                            r2m = fmax(r2m, fma(bj.x - cx, bj.x - cx, (bj.y - cy) * (bj.y - cy)));
+                        const int n = i + 1 - run_start;
+                        const float inv = 1.0f / (float)n, cx = (float)Sbx * inv, cy = (float)Sby * inv;
+                        const float ex = fmaxf(mxx - cx, cx - mnx), ey = fmaxf(mxy - cy, cy - mny);
+                        const float rho = sqrtf(fmaf(ex, ex, ey * ey)) * 1.0001f + 2e-5f;
+                        const int rcode = min(__float2int_ru(rho * (float)RT_RHO_UNIT), RT_RHO_INF);
+                        const int slot = (bk >= 0 && !(halo_tile && q == 0)) ? slot_of(S, bk) : RS_NOSLOT;
+                        if (k < R.maxr) {
+                            R.rec_sb[slot0 + (size_t)k * 32] = make_double2(Sbx, Sby);
+                            R.rec_meta[slot0 + (size_t)k * 32] = run_meta_pack(bk, slot, rcode, n);
                         }
-                        const double rho = sqrt(r2m) * (1.0 + 1e-6) + 1e-9;
-                        sb[run_start] = make_double2(Sbx, Sby);
-                        srn[run_start] = (unsigned short)(i + 1 - run_start);
-                        srho[run_start] = (unsigned short)min(__double2int_ru(rho * RT_RHO_UNIT), 65535);
-                        ++nr;
-                        run_start = i + 1; Sbx = 0.0; Sby = 0.0; bfirst = bn;
+                        ++k;
+                        run_start = i + 1; Sbx = 0.0; Sby = 0.0; mnx = INFINITY; mxx = -INFINITY; mny = INFINITY; mxy = -INFINITY;
                     }
                     b = bn; bk = bkn;
                 }
             }
-            const int nr_other = __shfl_xor_sync(FULLMASK, nr, 1);
-            const int rtot = nr + nr_other, kbase = sub ? nr_other : 0;
-            if (mine && sub == 0) S.rcnt[q] = rtot;
-            __syncthreads();
-            // ---- packing: scans in time order into chunks of 32 slots -------------------------------------------------
-            if (tid == 0) {
-                int pos = S.pos, ng = S.ngap;
-                for (int lt = c_lo; lt <= c_hi; ++lt) {
-                    const int r = S.rcnt[lt];
-                    const int fill = pos & 31;
-                    if (r > 0 && fill != 0 && r > 32 - fill) {       // does not fit (a scan of more than 32 runs starts a chunk)
-                        S.gap[ng][0] = pos; S.gap[ng][1] = pos + 32 - fill; ++ng;
-                        pos += 32 - fill;
-                    }
-                    S.rstart[lt] = pos;
-                    pos += r;
-                }
-                S.pos = pos; S.ngap = ng;
-            }
-            __syncthreads();
-            // ---- emission: the pair's runs to the tile's region ---------------------------------------------------------
-            if (o < e) {
-                const int s0 = S.rstart[q];
-                const bool lng = rtot > 32;
-                const int npieces = (rtot + 31) >> 5;
-                int k = kbase;
-                for (int i = o; i < e; ++k) {
-                    const int n = srn[i];
-                    const int piece = lng ? (k >> 5) : 0, kk = lng ? (k & 31) : k;
-                    const int plen = lng ? min(32, rtot - 32 * piece) : rtot;
-                    const unsigned rc = srho[i];
-                    const float rho = rc >= 65535u ? INFINITY : (float)rc * (float)(1.0 / RT_RHO_UNIT);
-                    const int flags = (kk == 0 ? RF_LEADER : 0) | (lng ? RF_LONG : 0) | ((halo_tile && q == 0) ? RF_HALO : 0);
-                    RunRec* rp = R.rec + base + s0 + k;
-                    *reinterpret_cast<double2*>(rp) = sb[i];
-                    *(reinterpret_cast<int4*>(rp) + 1) = make_int4(sbk[i], __float_as_int(rho), n | (q << 16) | ((plen - 1 - kk) << 24),
-                                                                   piece | (flags << 8) | (npieces << 16));
-                    i += n;
-                }
-            }
+            if (mine && sub == 0) R.nruns[tb + q] = (unsigned short)rtot;
             c_lo = c_hi + 1;
             if (c_lo < nsc) __syncthreads();   // the next chunk overwrites the staging buffers
         }
         __syncthreads();
-        // ---- padding slots, tile header --------------------------------------------------------------------------------
-        {
-            const int pos = S.pos, fill = pos & 31;
-            const int nch = (pos + 31) >> 5;
-            const int ng = S.ngap;
-            for (int g = 0; g <= ng; ++g) {
-                const int gb = g < ng ? S.gap[g][0] : pos, ge = g < ng ? S.gap[g][1] : (fill ? pos + 32 - fill : pos);
-                for (int s = gb + tid; s < ge; s += AT_THREADS) {
-                    RunRec* rp = R.rec + base + s;
-                    *reinterpret_cast<double2*>(rp) = make_double2(0.0, 0.0);
-                    *(reinterpret_cast<int4*>(rp) + 1) = make_int4(RUN_PAD, 0, 0, 0);
-                }
-            }
-            if (tid == 0) { R.tile_nchunks[tile] = nch; R.tile_epoch[tile] = epoch; }
-            __syncthreads();     // the block's records are visible to its warps
-            for (int c = warp; c < nch; c += AT_WARPS)
-                process_chunk<false>(R, R.rec + base + (int64_t)c * 32, (base >> 5) + c, tb, tile, commit_all);
-        }
+        // ---- tile header, then the slices through the same code as the steady state -------------------------------------------
+        if (tid == 0) R.tile_epoch[tile] = epoch;
+        for (int hh = tid; hh < RS_SLOTS; hh += AT_THREADS) R.tile_slots[(size_t)tile * RS_SLOTS + hh] = S.hkey[hh];
+        __syncthreads();     // the block's records are visible to its warps
+        if (warp < RT_SLICES) process_slice<false>(R, S.acc, tile * RT_SLICES + warp, tile, commit_all);
+        __syncthreads();
+        stats_flush(R, S.acc, tile);
         __syncthreads();
         if (tid < nsc) R.scan_dirty[tb + tid] = 0;
         if (tid == 0) R.tile_flag[tile] = 0;

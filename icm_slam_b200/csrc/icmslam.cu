@@ -67,6 +67,8 @@ struct icmslam_handle {
     bool lact_dirty = false;
     void* d_cub = nullptr;
     size_t cub_bytes = 0;
+    void* d_sort_ws = nullptr;
+    size_t sort_bytes = 0;
     // fused (REDBLACK, NEWTON, PREV) path: run records (runs.cuh) + association of dirty tiles (assoc_tiles.cuh) + solve (solve.cuh)
     bool fused_ok = false;
     double *d_bm = nullptr /*6 x T static body-frame moments + beam count*/, *d_inc = nullptr /*3 x T odometry increments*/, *d_x2 = nullptr /*3 x T, pose double buffer*/;
@@ -76,20 +78,24 @@ struct icmslam_handle {
     int* d_blk_prefix = nullptr;
     unsigned* d_farbits = nullptr;             // 4 words per record tile: scans that created a label this sweep
     int n_tiles = 0, n_solve_tiles = 0;        // record tiles (RT_TILE scans) / solve tiles (ST_OWN poses)
-    RunRec* d_rec = nullptr; int64_t rec_slots = 0;
-    int *d_tile_nchunks = nullptr, *d_tile_epoch = nullptr, *d_tile_flag = nullptr, *d_dirty_list = nullptr, *d_scan_dirty = nullptr, *d_ticket = nullptr;
-    double *d_dyn = nullptr /*6 per pose*/, *d_dynx = nullptr /*12 per chunk slot (long scans)*/;
+    double2* d_rec_sb = nullptr; int2* d_rec_meta = nullptr; int64_t rec_slots = 0; int rec_maxr = 1;   // run records (runs.cuh)
+    unsigned short* d_nruns = nullptr;         // runs of each scan
+    int* d_tile_slots = nullptr;               // RS_SLOTS labels per record tile
+    int *d_tile_epoch = nullptr, *d_tile_flag = nullptr, *d_dirty_list = nullptr, *d_scan_dirty = nullptr;
+    double* d_dyn = nullptr;                   // 6 landmark moments per pose
     TailState* d_ts = nullptr;
     double thr2_lt = 0.0;        // largest s with sqrt_rn(s) < dist_thr
     const double* grid_map = nullptr;   // the map buffer the fast grid currently indexes (nullptr: rebuild)
     const double* hint_map = nullptr;   // the map buffer for which c[] (through d_remap) holds last sweep's labels
     LmRec* d_lmrec = nullptr;           // landmarks of the current map by label (position + hint radius)
     int* d_remap = nullptr;             // label of the last sweep -> label in the current map
+    int* d_klab = nullptr;              // raw label of each kept landmark (fast tail)
     double* d_nnd2 = nullptr;
     double thr1sq = 0.0;
     struct GraphSlot { cudaGraphExec_t exec = nullptr; const double* src = nullptr; const double* map_in = nullptr; double x0[3] = {0, 0, 0}; double tol = 0; int maxit = 0; };
     GraphSlot graphs[4];
     int use_graph = 1, graph_launches = 0;
+    int runs_occ = 8;            // resident 128-thread blocks per SM k_runs is compiled for (8: 64 registers; ICMSLAM_RUNS_OCC=6: 80)
     int use_runs = 1;            // ICMSLAM_RUNS=0: every tile goes through the association kernel every sweep (no steady-state shortcut)
     int assoc_blocks = 0;        // grid of the (persistent) association kernel
     double2* d_bxy = nullptr;    // interleaved (bx, by) records for the TMA staging
@@ -169,9 +175,9 @@ static void free_dataset(icmslam_handle* h)
     DFREE(h->d_off); DFREE(h->d_beam); DFREE(h->d_scan_of); DFREE(h->d_d); DFREE(h->d_bx); DFREE(h->d_by);
     DFREE(h->d_c); DFREE(h->d_keys_out); DFREE(h->d_iota); DFREE(h->d_sorted); DFREE(h->d_seen_x); DFREE(h->d_seen_y);
     DFREE(h->d_nfar); DFREE(h->d_flag); DFREE(h->d_prefix); DFREE(h->d_x);
-    DFREE(h->d_inc); DFREE(h->d_bm); DFREE(h->d_dyn); DFREE(h->d_dynx); DFREE(h->d_x2); DFREE(h->d_far_list); DFREE(h->d_blk_prefix); DFREE(h->d_bxy);
-    DFREE(h->d_ppar[0]); DFREE(h->d_ppar[1]); DFREE(h->d_farbits); DFREE(h->d_rec); DFREE(h->d_tile_nchunks); DFREE(h->d_tile_epoch);
-    DFREE(h->d_tile_flag); DFREE(h->d_dirty_list); DFREE(h->d_scan_dirty); DFREE(h->d_ticket);
+    DFREE(h->d_inc); DFREE(h->d_bm); DFREE(h->d_dyn); DFREE(h->d_x2); DFREE(h->d_far_list); DFREE(h->d_blk_prefix); DFREE(h->d_bxy);
+    DFREE(h->d_ppar[0]); DFREE(h->d_ppar[1]); DFREE(h->d_farbits); DFREE(h->d_rec_sb); DFREE(h->d_rec_meta); DFREE(h->d_nruns); DFREE(h->d_tile_epoch);
+    DFREE(h->d_tile_flag); DFREE(h->d_dirty_list); DFREE(h->d_scan_dirty); DFREE(h->d_tile_slots);
     h->ppar_of = nullptr;
     drop_graphs(h);
     h->grid_map = nullptr;
@@ -193,10 +199,10 @@ extern "C" int icmslam_destroy(icmslam_handle* h)
     DFREE(h->d_kx); DFREE(h->d_ky); DFREE(h->d_kc); DFREE(h->d_ox); DFREE(h->d_oy); DFREE(h->d_oc); DFREE(h->d_acc);
     DFREE(h->d_map_in); DFREE(h->d_map_out); DFREE(h->d_tmp_a); DFREE(h->d_tmp_b);
     DFREE(h->d_cell_start); DFREE(h->d_cell_fill); DFREE(h->d_cell_id); DFREE(h->d_gidx); DFREE(h->d_glx); DFREE(h->d_gly);
-    DFREE(h->d_st); DFREE(h->d_cub);
+    DFREE(h->d_st); DFREE(h->d_cub); DFREE(h->d_sort_ws);
     DFREE(h->d_exch); DFREE(h->d_fg_cnt); DFREE(h->d_fg_start); DFREE(h->d_fg_idx);
     DFREE(h->d_fg_pts); DFREE(h->d_fg_geom); DFREE(h->d_bb); DFREE(h->d_ts); DFREE(h->d_seg_rec);
-    DFREE(h->d_lmrec); DFREE(h->d_remap); DFREE(h->d_nnd2);
+    DFREE(h->d_lmrec); DFREE(h->d_remap); DFREE(h->d_nnd2); DFREE(h->d_klab);
     if (h->h_st) cudaFreeHost(h->h_st);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -210,6 +216,13 @@ extern "C" int icmslam_destroy(icmslam_handle* h)
 static int ensure_cub(icmslam_handle* h, size_t bytes)
 {
     if (bytes <= h->cub_bytes) return ICMSLAM_OK;
+    // captured graphs have the old workspace pointer baked in: they must not be replayed after it is freed
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (h->stream && cudaStreamIsCapturing(h->stream, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) {
+        snprintf(h->err, sizeof h->err, "scan workspace too small inside a graph capture (%zu > %zu bytes)", bytes, h->cub_bytes);
+        return ICMSLAM_ERR_CUDA;
+    }
+    drop_graphs(h);
     DFREE(h->d_cub);
     h->cub_bytes = 0;
     CK(cudaMalloc(&h->d_cub, bytes));
@@ -298,12 +311,14 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     if (e == cudaSuccess) e = dalloc(&h->d_seg_rec, SEG_REC);
     if (e == cudaSuccess) e = dalloc(&h->d_lmrec, L);
     if (e == cudaSuccess) e = dalloc(&h->d_remap, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_klab, L);
     if (e == cudaSuccess) e = dalloc(&h->d_nnd2, L);
     if (e == cudaSuccess) e = cudaMemset(h->d_lmrec, 0, L * sizeof(LmRec));
     { const double t1 = cfg->dist_thr * (1.0 + 9.5367431640625e-07); h->thr1sq = t1 * t1; }
     if (e == cudaSuccess) e = cudaMemset(h->d_ts, 0, sizeof(TailState));
     { const char* eg = getenv("ICMSLAM_GRAPH"); if (eg) h->use_graph = atoi(eg); }
     { const char* er = getenv("ICMSLAM_RUNS"); if (er) h->use_runs = atoi(er) != 0; }
+    { const char* er = getenv("ICMSLAM_RUNS_OCC"); if (er && atoi(er) == 6) h->runs_occ = 6; }
     if (e == cudaSuccess) {
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
@@ -321,7 +336,7 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
         while (sqrt(nextafter(s3, INFINITY)) < thr) s3 = nextafter(s3, INFINITY);
         h->thr2_lt = s3;
         int ex = thr > 1.0 ? ilogb(thr) + 1 : 0;
-        h->fix_scale = ldexp(1.0, 40 - ex);
+        h->fix_scale = ldexp(1.0, 34 - ex);      // 2^-34 m per unit: a run's sum fits the two 32-bit limbs of runs.cuh
     }
     if (e == cudaSuccess) e = dalloc(&h->d_st, 1);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_st, sizeof(DevState));
@@ -392,8 +407,8 @@ extern "C" int icmslam_load(icmslam_handle* h, const double* scans, int32_t B, i
     CK(dalloc(&h->d_blk_prefix, (size_t)nblk(T + 1, RT_TILE) + 2));
     {   // scan workspace for the largest scan of a sweep, so that nothing allocates inside a graph capture
         size_t need = 0, b = 0;
-        const int lens[3] = {h->Lcap + 1, h->fg_cells + 2, T + 1};
-        for (int k = 0; k < 3; ++k) { CK(cub::DeviceScan::ExclusiveSum(nullptr, b, (const int*)nullptr, (int*)nullptr, lens[k], h->stream)); if (b > need) need = b; }
+        const int lens[4] = {h->Lcap + 1, h->fg_cells + 2, T + 1, MAX_CELLS + 2};      // (the generic grid scans MAX_CELLS + 1 cells)
+        for (int k = 0; k < 4; ++k) { CK(cub::DeviceScan::ExclusiveSum(nullptr, b, (const int*)nullptr, (int*)nullptr, lens[k], h->stream)); if (b > need) need = b; }
         int rcw = ensure_cub(h, need);
         if (rcw) return rcw;
     }
@@ -465,24 +480,24 @@ extern "C" int icmslam_extract(icmslam_handle* h)
     CK(dalloc(&h->d_bxy, n + 2));
     k_interleave<<<nblk((int64_t)n, 256), 256, 0, h->stream>>>(h->d_bx, h->d_by, (int64_t)n, h->d_bxy);
     CK(cudaGetLastError());
-    DFREE(h->d_bm); DFREE(h->d_dyn); DFREE(h->d_dynx);
-    DFREE(h->d_ppar[0]); DFREE(h->d_ppar[1]); DFREE(h->d_farbits); DFREE(h->d_rec); DFREE(h->d_tile_nchunks); DFREE(h->d_tile_epoch);
-    DFREE(h->d_tile_flag); DFREE(h->d_dirty_list); DFREE(h->d_scan_dirty); DFREE(h->d_ticket);
-    {   // run records and their bookkeeping (runs.cuh): region of tile i at run_tile_base, 2 slots per observation + 64 per tile
+    DFREE(h->d_bm); DFREE(h->d_dyn);
+    DFREE(h->d_ppar[0]); DFREE(h->d_ppar[1]); DFREE(h->d_farbits); DFREE(h->d_rec_sb); DFREE(h->d_rec_meta); DFREE(h->d_nruns); DFREE(h->d_tile_epoch);
+    DFREE(h->d_tile_flag); DFREE(h->d_dirty_list); DFREE(h->d_scan_dirty); DFREE(h->d_tile_slots);
+    {   // run records and their bookkeeping (runs.cuh): slice s (32 scans) owns slots [s * maxr * 32, (s + 1) * maxr * 32)
         const size_t nt = (size_t)nblk(T + 1, RT_TILE) + 2;      // (+1 scan: a segment's tiling may start one scan earlier)
-        h->rec_slots = (int64_t)(2 * n + 64 * nt + 64);
-        CK(dalloc(&h->d_rec, (size_t)h->rec_slots));
-        CK(dalloc(&h->d_dynx, (size_t)(h->rec_slots / 32 + 1) * 12));
+        h->rec_maxr = h->max_per_scan > 0 ? h->max_per_scan : 1;
+        h->rec_slots = (int64_t)(nt * RT_SLICES) * h->rec_maxr * 32;
+        CK(dalloc(&h->d_rec_sb, (size_t)h->rec_slots)); CK(dalloc(&h->d_rec_meta, (size_t)h->rec_slots));
+        CK(dalloc(&h->d_nruns, nt * RT_TILE));
         CK(dalloc(&h->d_ppar[0], (size_t)T)); CK(dalloc(&h->d_ppar[1], (size_t)T));
-        CK(dalloc(&h->d_farbits, nt * 4)); CK(dalloc(&h->d_tile_nchunks, nt)); CK(dalloc(&h->d_tile_epoch, nt));
-        CK(dalloc(&h->d_tile_flag, nt)); CK(dalloc(&h->d_dirty_list, nt));
-        CK(dalloc(&h->d_scan_dirty, (size_t)T + 1)); CK(dalloc(&h->d_ticket, (size_t)T + 1));
-        CK(cudaMemsetAsync(h->d_tile_nchunks, 0, nt * sizeof(int), h->stream));
+        CK(dalloc(&h->d_farbits, nt * 4)); CK(dalloc(&h->d_tile_epoch, nt));
+        CK(dalloc(&h->d_tile_flag, nt)); CK(dalloc(&h->d_dirty_list, nt)); CK(dalloc(&h->d_tile_slots, nt * RS_SLOTS));
+        CK(dalloc(&h->d_scan_dirty, nt * RT_TILE));
+        CK(cudaMemsetAsync(h->d_nruns, 0, nt * RT_TILE * sizeof(unsigned short), h->stream));
         CK(cudaMemsetAsync(h->d_tile_epoch, 0xff, nt * sizeof(int), h->stream));       // epoch -1: no tile holds records
         CK(cudaMemsetAsync(h->d_tile_flag, 0, nt * sizeof(int), h->stream));
         CK(cudaMemsetAsync(h->d_farbits, 0, nt * 4 * sizeof(unsigned), h->stream));
-        CK(cudaMemsetAsync(h->d_scan_dirty, 0, ((size_t)T + 1) * sizeof(int), h->stream));
-        CK(cudaMemsetAsync(h->d_ticket, 0, ((size_t)T + 1) * sizeof(int), h->stream));
+        CK(cudaMemsetAsync(h->d_scan_dirty, 0, nt * RT_TILE * sizeof(int), h->stream));
         h->ppar_of = nullptr;
     }
     CK(dalloc(&h->d_bm, (size_t)6 * T));
@@ -519,7 +534,7 @@ extern "C" int icmslam_extract(icmslam_handle* h)
         h->fused_smem = assoc_smem_bytes(h->obs_cap);
         // (a per-function, per-device attribute shared by every handle of the process: opt in to the maximum)
         CK(cudaFuncSetAttribute(k_assoc_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        h->fused_ok = h->max_per_scan <= 65535 && RT_TILE <= 256;
+        h->fused_ok = h->max_per_scan <= 65535 && h->Lcap <= RUN_MAX_LABEL;
     }
     return ICMSLAM_OK;
 }
@@ -670,6 +685,7 @@ __global__ void k_sweep_begin(DevState* st, TailState* ts, int L_in)
 {
     ts->far_count = 0;
     ts->n_dirty = 0;
+    st->cambio[0] = INFINITY; st->cambio[1] = 0.0; st->cambio[2] = 0.0; st->cambio_unres = 0;
     st->lact0 = st->lact;
     st->lsearch = min(st->lact, L_in);
     st->raw_l = st->lact;
@@ -766,13 +782,14 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
     }
     const int t_start = h->seg_lo - (h->seg_first ? 0 : 1);     // a later segment also forms the moments of its odd halo pose
     RunParams R;
-    R.t_start = t_start; R.t_hi = h->seg_hi; R.off = h->d_off; R.ppar = pp_in; R.lmrec = h->d_lmrec; R.rec = h->d_rec;
-    R.tile_nchunks = h->d_tile_nchunks; R.tile_epoch = h->d_tile_epoch; R.dyn = h->d_dyn; R.dynx = h->d_dynx; R.ticket = h->d_ticket;
-    R.fsum_x = h->d_fsum_x; R.fsum_y = h->d_fsum_y; R.cnt = h->d_cnt; R.fix_scale = h->fix_scale;
+    R.t_start = t_start; R.t_hi = h->seg_hi; R.halo_t = h->seg_first ? -1 : t_start; R.maxr = h->rec_maxr; R.ppar = pp_in; R.lmrec = h->d_lmrec;
+    R.rec_sb = h->d_rec_sb; R.rec_meta = h->d_rec_meta; R.nruns = h->d_nruns; R.tile_epoch = h->d_tile_epoch; R.dyn = h->d_dyn;
+    R.fsum_x = h->d_fsum_x; R.fsum_y = h->d_fsum_y; R.cnt = h->d_cnt; R.fix_scale = h->fix_scale; R.tile_slots = h->d_tile_slots;
     R.far_list = h->d_far_list; R.ts = h->d_ts; R.farbits = h->d_farbits;
     R.scan_dirty = h->d_scan_dirty; R.tile_flag = h->d_tile_flag; R.dirty_list = h->d_dirty_list;
+    R.geom = h->d_fg_geom; R.cell_start = h->d_fg_start; R.gpts = h->d_fg_pts; R.dist_thr = h->dcfg.dist_thr;
     AssocParams A;
-    A.first_halo = h->seg_first ? 0 : 1; A.bxy = h->d_bxy; A.cfg = h->dcfg; A.thr2_hi = h->thr2_hi; A.st = st; A.geom = h->d_fg_geom;
+    A.first_halo = h->seg_first ? 0 : 1; A.T = T; A.off = h->d_off; A.bxy = h->d_bxy; A.cfg = h->dcfg; A.thr2_hi = h->thr2_hi; A.st = st; A.geom = h->d_fg_geom;
     A.cell_start = h->d_fg_start; A.gpts = h->d_fg_pts; A.gidx = h->d_fg_idx; A.remap = h->d_remap;
     { const char* eh = getenv("ICMSLAM_HINTS"); A.skip_hints = (eh && atoi(eh) == 0) ? 1 : 0; }
     A.hints = (h->hint_map == h->d_map_in) ? 1 : 0;
@@ -780,7 +797,8 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
     CK(cudaMemsetAsync(h->d_farbits, 0, (size_t)h->n_tiles * 4 * sizeof(unsigned), s));
     if (timing) CK(cudaEventRecord(h->ev[0], s));
     if (h->use_runs) {
-        k_runs<<<h->n_tiles, RUNS_THREADS, 0, s>>>(R);
+        if (h->runs_occ == 6) k_runs<6><<<h->n_tiles, RUNS_THREADS, 0, s>>>(R);
+        else k_runs<8><<<h->n_tiles, RUNS_THREADS, 0, s>>>(R);
     } else {
         k_all_dirty<<<nblk(h->n_tiles, 256), 256, 0, s>>>(h->d_tile_flag, h->d_dirty_list, h->d_ts, h->n_tiles);
     }
@@ -854,7 +872,7 @@ static int fused_part_c(icmslam_handle* h, double* dmap_out, int out_cap, int64_
     int rc = exclusive_sum(h, h->d_kflag, h->d_kpos, L);
     if (rc) return rc;
     k_tail_compact<<<nblk(L, 256), 256, 0, s>>>(st, ts, h->d_kflag, h->d_kpos, raw_x, raw_y, h->d_cnt, h->d_kx, h->d_ky, h->d_kc,
-                                                h->d_parent, h->d_bb, L);
+                                                h->d_parent, h->d_bb, L, h->d_klab);
     CK(cudaGetLastError());
     k_tail_geom<<<1, 1, 0, s>>>(h->d_bb, st, ts, h->dcfg.dist_thr, h->fg_cells, h->d_fg_geom);
     CK(cudaGetLastError());
@@ -866,7 +884,7 @@ static int fused_part_c(icmslam_handle* h, double* dmap_out, int out_cap, int64_
                                               h->d_fg_idx);
     CK(cudaGetLastError());
     k_tail_nn<<<nblk(L, 256), 256, 0, s>>>(st, ts, h->d_kx, h->d_ky, h->d_fg_geom, h->d_fg_start, h->d_fg_pts, h->d_fg_idx, h->thr2_lt,
-                                           h->d_nn, h->d_indflag, h->d_nnd2, L);
+                                           h->d_nn, h->d_indflag, h->d_nnd2, L, h->d_klab, h->d_kc, h->d_lmrec);
     CK(cudaGetLastError());
     k_tail_finalize<<<nblk(L, 256), 256, 0, s>>>(st, ts, h->d_kx, h->d_ky, h->d_kc, dmap_out, out_cap, out_ld, h->d_counts, L, h->d_kflag,
                                                  h->d_kpos, h->d_nnd2, h->thr1sq, h->thr2_hi, h->d_lmrec, h->d_remap);
@@ -966,9 +984,13 @@ static int sweep_core(icmslam_handle* h, const double* xin, int64_t ldin, double
             size_t bytes = 0;
             CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned*)h->d_c, (unsigned*)h->d_keys_out, h->d_iota, h->d_sorted,
                                                (int)n, 0, end_bit, s));
-            rc = ensure_cub(h, bytes);
-            if (rc) return rc;
-            CK(cub::DeviceRadixSort::SortPairs(h->d_cub, bytes, (const unsigned*)h->d_c, (unsigned*)h->d_keys_out, h->d_iota, h->d_sorted,
+            if (bytes > h->sort_bytes) {      // (its own workspace: never invalidates the scans' one that captured graphs use)
+                DFREE(h->d_sort_ws);
+                h->sort_bytes = 0;
+                CK(cudaMalloc(&h->d_sort_ws, bytes));
+                h->sort_bytes = bytes;
+            }
+            CK(cub::DeviceRadixSort::SortPairs(h->d_sort_ws, bytes, (const unsigned*)h->d_c, (unsigned*)h->d_keys_out, h->d_iota, h->d_sorted,
                                                (int)n, 0, end_bit, s));
             k_running_mean<<<nblk(L, 128), 128, 0, s>>>(st, h->d_seg, h->d_cnt, h->d_sorted, h->d_scan_of, h->d_bx, h->d_by, dx, ldx,
                                                         x0[0], x0[1], x0[2], h->d_seen_x, h->d_seen_y, raw_x, raw_y, L);
@@ -1046,13 +1068,11 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
         xout = h->d_x2; ldout = T;
     }
     bool continued = false;
-    if (memspace == ICMSLAM_HOST && L_in > 0 && L_in == h->last_map_L && h->grid_map != nullptr && h->grid_map == h->d_map_out &&
+    if (memspace == ICMSLAM_HOST && L_in > 0 && L_in == h->last_map_L && h->grid_map != nullptr && h->grid_map == h->d_map_in &&
         memcmp(map_in, h->last_map_host.data(), (size_t)L_in * 8) == 0 &&
         memcmp(map_in + ld_map_in, h->last_map_host.data() + L_in, (size_t)L_in * 8) == 0) {
-        // the caller hands back the map the previous sweep returned: it is already on the device, with its grid and hints
-        double* t = h->d_map_in; h->d_map_in = h->d_map_out; h->d_map_out = t;
-        h->grid_map = h->d_map_in;
-        if (h->hint_map) h->hint_map = h->d_map_in;
+        // the caller hands back the map the previous sweep returned: it is already on the device (the current map buffer),
+        // with its grid, hints and run records
         continued = true;
     }
     h->last_map_L = -1;
@@ -1068,6 +1088,9 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
     int rc = sweep_core(h, xin, ldin, xout, ldout, x0, o, L_in, own_out ? h->d_map_out : map_out, own_out ? L : cap_out,
                         own_out ? (int64_t)L : ld_map_out);
     if (rc) return rc;
+    if (own_out) {      // mapa_refinado becomes the handle's current map (icmslam_get_map, and the map chain a caller may continue)
+        double* t = h->d_map_in; h->d_map_in = h->d_map_out; h->d_map_out = t;
+    }
     if (memspace == ICMSLAM_HOST) {
         CK(cudaMemcpy2DAsync(x, (size_t)ld_x * 8, xout, (size_t)T * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToHost, s));
         h->bytes_d2h += (int64_t)3 * T * 8 + (int64_t)sizeof(DevState);
@@ -1079,7 +1102,7 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
         if (map_out) {
             int w = newL < cap_out ? newL : cap_out;
             if (w > 0) {
-                CK(cudaMemcpy2DAsync(map_out, (size_t)ld_map_out * 8, h->d_map_out, (size_t)L * 8, (size_t)w * 8, 2, cudaMemcpyDeviceToHost, s));
+                CK(cudaMemcpy2DAsync(map_out, (size_t)ld_map_out * 8, h->d_map_in, (size_t)L * 8, (size_t)w * 8, 2, cudaMemcpyDeviceToHost, s));
                 CK(cudaStreamSynchronize(s));
                 h->bytes_d2h += (int64_t)2 * w * 8;
                 if (w == newL) {       // remember what the caller received (see `continued` above)
@@ -1455,6 +1478,9 @@ extern "C" int icmslam_filter_map(icmslam_handle* h, const double* map_in, int64
     CK(cudaGetLastError());
     k_flags_from_counts<<<nblk(L, 256), 256, 0, s>>>(h->d_tmp_b, L_in, h->dcfg.cota, h->d_kflag, L);
     CK(cudaGetLastError());
+    // (the result goes through the handle's spare map buffer and rewrites the Mapa state: whatever map chain the handle was
+    //  continuing -- grid, hints, run records, the copy of the last returned map -- no longer describes that buffer)
+    h->grid_map = nullptr; h->hint_map = nullptr; h->last_map_L = -1;
     int rc = run_filter(h, h->d_tmp_a, h->d_tmp_a + L, nullptr, h->d_tmp_b, h->d_map_out, L, L, h->d_tmp_b + L, 1);
     if (rc) return rc;
     rc = sync_state(h);
@@ -1498,6 +1524,164 @@ extern "C" int icmslam_calc_cambio(icmslam_handle* h, const double* map_new, int
     CK(cudaMemcpyAsync(res, h->d_acc, sizeof res, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     out3[0] = res[0]; out3[1] = res[1]; out3[2] = res[2] / (double)L_new;
+    return ICMSLAM_OK;
+}
+
+// ---- Mapa.actualizar for one scan (ICM_SLAM.py:128-201) -------------------------------------------------------------------
+// nearest landmark of one observation per block: cdist + argmin + gate, exactly (rooted distances, first index on ties)
+__global__ void __launch_bounds__(128)
+k_actualizar_nearest(const double* __restrict__ rx, const double* __restrict__ ry, int Ls, const double* __restrict__ ox,
+                     const double* __restrict__ oy, double dist_thr, int* __restrict__ c)
+{
+    __shared__ double bd[4];
+    __shared__ int bi[4];
+    const int i = blockIdx.x;
+    const double wx = ox[i], wy = oy[i];
+    double best = INFINITY;
+    int arg = 0x7fffffff;
+    for (int l = threadIdx.x; l < Ls; l += blockDim.x) {
+        const double d = dist_rn(rx[l] - wx, ry[l] - wy);
+        if (d < best) { best = d; arg = l; }          // (ascending l within a thread: the first minimum stays)
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(FULLMASK, best, o);
+        const int oa = __shfl_xor_sync(FULLMASK, arg, o);
+        if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    if ((threadIdx.x & 31) == 0) { bd[threadIdx.x >> 5] = best; bi[threadIdx.x >> 5] = arg; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 4; ++w) if (bd[w] < best || (bd[w] == best && bi[w] < arg)) { best = bd[w]; arg = bi[w]; }
+        c[i] = (Ls <= 0 || best > dist_thr) ? -1 : arg;          // amin > dist_thr -> far (ICM_SLAM.py:172)
+    }
+}
+
+// labels of the far observations, then the running means and counts of every label present, in the reference's order
+__global__ void __launch_bounds__(256)
+k_actualizar_update(DevState* st, int Lcap, int n, const double* __restrict__ ox, const double* __restrict__ oy, int* __restrict__ c,
+                    double* __restrict__ mapa, int cap, int64_t ld, double* __restrict__ cant)
+{
+    __shared__ int anyfar;
+    if (threadIdx.x == 0) anyfar = 0;
+    __syncthreads();
+    const int lact = st->lact;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) if (c[i] < 0) anyfar = 1;
+    __syncthreads();
+    const int newl = lact + (anyfar ? 1 : 0);        // every far observation of the scan gets the ONE new label (:174-180)
+    if (newl > Lcap || newl > cap) { if (threadIdx.x == 0) st->status |= ST_LABEL_CAP; return; }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) if (c[i] < 0) c[i] = lact;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int l = c[i];
+        bool first = true;
+        for (int j = 0; j < i; ++j) if (c[j] == l) { first = false; break; }
+        if (!first) continue;
+        double sx = 0.0, sy = 0.0;
+        int k = 0;
+        for (int j = i; j < n; ++j) if (c[j] == l) { sx = add_rn(sx, ox[j]); sy = add_rn(sy, oy[j]); ++k; }     // np.sum(obs[c==i], axis=0)
+        const double cn = cant[l], tot = add_rn(cn, (double)k);
+        mapa[l] = add_rn(sx / tot, mul_rn(mapa[l], cn) / tot);                                                   // :191-192
+        mapa[ld + l] = add_rn(sy / tot, mul_rn(mapa[ld + l], cn) / tot);
+        cant[l] = tot;
+    }
+    if (threadIdx.x == 0) st->lact = newl;
+}
+
+extern "C" int icmslam_associate(icmslam_handle* h, const double* map_ref, int32_t L_ref, int64_t ld_ref, const double* obs_x,
+                                 const double* obs_y, int32_t n_obs, double* mapa, int32_t cap, int64_t ld_mapa, int32_t* c,
+                                 int32_t memspace)
+{
+    if (!h || n_obs < 0 || !mapa || cap <= 0 || cap > h->Lcap || ld_mapa < cap || L_ref < 0 || L_ref > h->Lcap || (L_ref > 0 && (!map_ref || ld_ref < L_ref)))
+        return ICMSLAM_ERR_INVALID;
+    if (n_obs == 0) return ICMSLAM_OK;
+    if (!obs_x || !obs_y || !c) return ICMSLAM_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    const int L = h->Lcap;
+    cudaStream_t s = h->stream;
+    int rc = sync_state(h);
+    if (rc) return rc;
+    const int lact = h->h_st->lact;
+    h->grid_map = nullptr; h->hint_map = nullptr; h->last_map_L = -1;      // (the Mapa state changes under any map chain in flight)
+    if (lact == 0) {
+        // Branch A (ICM_SLAM.py:160-165): clusters of the first scan, on the host like icmslam_pass0's first step
+        std::vector<double> wx(n_obs), wy(n_obs);
+        CK(cudaMemcpyAsync(wx.data(), obs_x, (size_t)n_obs * 8, cudaMemcpyDefault, s));
+        CK(cudaMemcpyAsync(wy.data(), obs_y, (size_t)n_obs * 8, cudaMemcpyDefault, s));
+        CK(cudaStreamSynchronize(s));
+        std::vector<int> lab(n_obs);
+        const int k0 = icm_fcluster::fcluster_inconsistent(wx.data(), wy.data(), n_obs, h->cfg.dist_thr, lab.data());
+        if (k0 > L || k0 > cap) return ICMSLAM_ERR_LABEL_CAP;
+        std::vector<double> mx(k0), my(k0), cn(k0);
+        for (int i = 0; i < k0; ++i) {                                // np.mean(obs[c==i,:], axis=0)
+            double sx = 0.0, sy = 0.0;
+            int k = 0;
+            for (int j = 0; j < n_obs; ++j) if (lab[j] == i) { sx += wx[j]; sy += wy[j]; ++k; }
+            mx[i] = sx / (double)k; my[i] = sy / (double)k; cn[i] = (double)k;
+        }
+        CK(cudaMemcpyAsync(mapa, mx.data(), (size_t)k0 * 8, cudaMemcpyDefault, s));
+        CK(cudaMemcpyAsync(mapa + ld_mapa, my.data(), (size_t)k0 * 8, cudaMemcpyDefault, s));
+        CK(cudaMemcpyAsync(h->d_counts, cn.data(), (size_t)k0 * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(c, lab.data(), (size_t)n_obs * sizeof(int), cudaMemcpyDefault, s));
+        k_set_lact<<<1, 1, 0, s>>>(h->d_st, k0);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(s));
+        h->lact_host = k0; h->lact_dirty = false;
+        (void)memspace;
+        return ICMSLAM_OK;
+    }
+    // Branch B: device copies of the reference map (d_tmp_a), the observations (d_kx / d_ky as scratch would clash with the
+    // filter: d_ox / d_oy) and the map under construction (d_tmp_b)
+    const int Ls = lact < L_ref ? lact : L_ref;
+    if (n_obs > L) return ICMSLAM_ERR_UNSUPPORTED;                   // (scratch sized by the label capacity)
+    if (Ls > 0) CK(cudaMemcpy2DAsync(h->d_tmp_a, (size_t)L * 8, map_ref, (size_t)ld_ref * 8, (size_t)Ls * 8, 2, cudaMemcpyDefault, s));
+    CK(cudaMemcpyAsync(h->d_ox, obs_x, (size_t)n_obs * 8, cudaMemcpyDefault, s));
+    CK(cudaMemcpyAsync(h->d_oy, obs_y, (size_t)n_obs * 8, cudaMemcpyDefault, s));
+    CK(cudaMemcpy2DAsync(h->d_tmp_b, (size_t)L * 8, mapa, (size_t)ld_mapa * 8, (size_t)cap * 8, 2, cudaMemcpyDefault, s));
+    k_set_raw_l<<<1, 1, 0, s>>>(h->d_st, lact);                      // (clears the status word)
+    CK(cudaGetLastError());
+    k_actualizar_nearest<<<n_obs, 128, 0, s>>>(h->d_tmp_a, h->d_tmp_a + L, Ls, h->d_ox, h->d_oy, h->dcfg.dist_thr, h->d_lab);
+    CK(cudaGetLastError());
+    k_actualizar_update<<<1, 256, 0, s>>>(h->d_st, L, n_obs, h->d_ox, h->d_oy, h->d_lab, h->d_tmp_b, cap, L, h->d_counts);
+    CK(cudaGetLastError());
+    h->n_launch += 3;
+    rc = sync_state(h);
+    if (rc) return rc;
+    if (h->h_st->status & ST_LABEL_CAP) return ICMSLAM_ERR_LABEL_CAP;
+    CK(cudaMemcpy2DAsync(mapa, (size_t)ld_mapa * 8, h->d_tmp_b, (size_t)L * 8, (size_t)cap * 8, 2, cudaMemcpyDefault, s));
+    CK(cudaMemcpyAsync(c, h->d_lab, (size_t)n_obs * sizeof(int), cudaMemcpyDefault, s));
+    CK(cudaStreamSynchronize(s));
+    return ICMSLAM_OK;
+}
+
+// ---- the driver loop with the convergence monitor (sensors.py:302-315) -------------------------------------------------
+extern "C" int icmslam_iterate_until(icmslam_handle* h, const double* x0, int32_t max_sweeps, double tol_max_change,
+                                     const icmslam_sweep_opts* opts, double* cambios, int32_t* n_done)
+{
+    if (!h || !x0 || max_sweeps < 0 || !n_done) return ICMSLAM_ERR_INVALID;
+    *n_done = 0;
+    const int L = h->Lcap;
+    for (int k = 0; k < max_sweeps; ++k) {
+        int rc = sync_state(h);
+        if (rc) return rc;
+        const int L_old = h->h_st->lact;
+        rc = icmslam_iterate(h, nullptr, 0, x0, 1, opts, ICMSLAM_DEVICE);
+        if (rc) return rc;
+        rc = sync_state(h);
+        if (rc) return rc;
+        rc = status_from_state(h->h_st);
+        if (rc) return rc;
+        const DevState* st = h->h_st;
+        double tri[3];
+        if (h->timed_fused && st->cambio_unres == 0 && st->new_l > 0) {
+            tri[0] = st->cambio[0]; tri[1] = st->cambio[1]; tri[2] = st->cambio[2] / (double)st->new_l;
+        } else {        // landmarks merged / appeared, or another sweep mode: the full search (new map = d_map_in, old = d_map_out)
+            rc = icmslam_calc_cambio(h, h->d_map_in, st->new_l, L, h->d_map_out, L_old > 0 ? L_old : 1, L, tri, ICMSLAM_DEVICE);
+            if (rc) return rc;
+        }
+        if (cambios) { cambios[k] = tri[0]; cambios[max_sweeps + k] = tri[1]; cambios[2 * max_sweeps + k] = tri[2]; }
+        *n_done = k + 1;
+        if (tol_max_change > 0.0 && tri[1] <= tol_max_change) break;
+    }
     return ICMSLAM_OK;
 }
 

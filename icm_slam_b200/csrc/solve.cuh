@@ -6,17 +6,16 @@
 // schedule of DESIGN.md section 2): odd poses from the OLD even neighbours, then even poses from the NEW odd ones.
 //
 // A block owns ST_OWN = 126 consecutive poses tb .. tb+125 (tb even) and stages poses tb-2 .. tb+126, their odometry
-// increments, controls and heading sin/cos in shared memory.  Thread pair per pose (role 0 = x rows, role 1 = y rows):
-// the warps of the first half solve the odd poses tb-1, tb+1, .. (tb-1 is the halo: it is owned by the previous tile, which
-// computes the identical value from the identical inputs), a block barrier, the warps of the second half solve the even
-// poses from the new odd ones in shared memory.  Every input is read once; the new poses and their projection parameters
+// increments, controls and heading sin/cos in shared memory.  A lane pair (role 0 = x rows, role 1 = y rows) solves one odd
+// pose tb-1+2q (q = 0: the halo tb-1, owned by the previous tile, which computes the identical value from the identical
+// inputs), then, after a block barrier, the even pose tb+2q from the new odd poses in shared memory: every warp works in
+// both colour phases.  Every input is read once; the new poses and their projection parameters
 // (x, y, sin/cos of theta - pi/2: what tras_rot_z needs next sweep, ICM_SLAM.py:465-480) are written coalesced.
 #pragma once
 #include "common.cuh"
 
 #define ST_HALF 64
-#define ST_THREADS (4 * ST_HALF)   // a lane pair per pose slot
-#define ST_SLOTS (2 * ST_HALF)     // slots 0..63: odd poses tb-1+2j (slot 0 = halo); 64..127: even poses tb+2j (last = spare)
+#define ST_THREADS (2 * ST_HALF)   // a lane pair per pose slot; a slot solves one odd and one even pose
 #define ST_OWN (2 * ST_HALF - 2)
 #define ST_XT (2 * ST_HALF + 4)    // pose-tile entries: poses tb-2 .. tb+ST_OWN (2*ST_HALF+1 used)
 
@@ -199,13 +198,45 @@ struct __align__(16) SolveSmem {
     double sn[ST_XT], cs[ST_XT];   // sin/cos of the input headings (after the odd phase: of the new odd headings)
 };
 
-__global__ void __launch_bounds__(ST_THREADS, 2)
+// the pose a lane pair solves in one colour phase: everything it needs beyond the tile's shared arrays
+struct SlotMom {
+    Mom M;
+    bool valid, pinned;
+    int t, li;
+};
+
+__device__ __forceinline__ SlotMom solve_slot_load(const SolveParams& p, int tb, int q, int half, int phase)
+{
+    SlotMom s;
+    s.t = phase == 0 ? tb - 1 + 2 * q : tb + 2 * q;
+    s.li = s.t - (tb - 2);
+    // (phase 0, slot 0 = the odd pose tb-1 left of the tile: re-solved here because the even pose tb needs its NEW value;
+    //  phase 1, last slot = tb+126: the next tile's)
+    s.valid = s.t >= 0 && s.t < p.t_hi && (phase == 0 ? (q == 0 || s.t >= p.t_lo) : (q != ST_HALF - 1 && s.t >= p.t_lo));
+    s.pinned = s.valid && s.t == 0 && p.first;
+    Mom& M = s.M;
+    M.n = M.Bx = M.By = M.Bxx = M.Byy = M.Bxy = M.Yx = M.Yy = M.Mxx = M.Mxy = M.Myx = M.Myy = 0.0;
+    if (s.valid && !s.pinned) {
+        const double* bmq = p.bm + s.t;
+        M.n = __ldg(bmq + 5 * p.ldbm);
+        M.Bx = __ldg(bmq); M.By = __ldg(bmq + p.ldbm); M.Bxx = __ldg(bmq + 2 * p.ldbm);
+        M.Byy = __ldg(bmq + 3 * p.ldbm); M.Bxy = __ldg(bmq + 4 * p.ldbm);
+        const double* d = p.dyn + (size_t)s.t * 6 + 3 * half;     // the role's three moments (stale where the scan is empty: unused)
+        const double y = d[0], m1 = d[1], m2 = d[2];
+        if (half) { M.Yy = y; M.Myx = m1; M.Myy = m2; } else { M.Yx = y; M.Mxx = m1; M.Mxy = m2; }
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(ST_THREADS, 4)
 k_solve_tile(const SolveParams p)
 {
     __shared__ SolveSmem S;
     const int tid = threadIdx.x;
     const int tb = p.t_lo + blockIdx.x * ST_OWN;      // t_lo is even: colours stay aligned with the global time index
     const int T = p.T;
+    const int q = tid >> 1, half = tid & 1;
+    SlotMom cur = solve_slot_load(p, tb, q, half, 0);      // (in flight while the tile is staged)
     for (int li = tid; li < ST_XT; li += ST_THREADS) {
         const int t = tb - 2 + li;
         const bool ok = t >= 0 && t < T;
@@ -221,88 +252,71 @@ k_solve_tile(const SolveParams p)
         double sh = 0.0, ch = 1.0;
         if (ok) {
             if (t == 0 && p.first) sincos(th, &sh, &ch);       // (ppar[0] belongs to self.x0; x[:,0] is only a neighbour)
-            else { const double4 q = ldg_ppar(p.ppin + t); sh = q.w; ch = -q.z; }
+            else { const double4 pq = ldg_ppar(p.ppin + t); sh = pq.w; ch = -pq.z; }
         }
         S.sn[li] = sh; S.cs[li] = ch;
     }
     __syncthreads();
-    const int q = tid >> 1, half = tid & 1;
-    const int grp = q / ST_HALF;
-    const int t = q < ST_HALF ? tb - 1 + 2 * q : tb + 2 * (q - ST_HALF);
-    const int li = t - (tb - 2);
-    // (slot 0 = the odd pose tb-1 left of the tile: re-solved here because the even pose tb needs its NEW value)
-    const bool qvalid = q != ST_SLOTS - 1 && t >= 0 && t < p.t_hi && (q == 0 || t >= p.t_lo);
-    Mom M;
-    M.n = M.Bx = M.By = M.Bxx = M.Byy = M.Bxy = M.Yx = M.Yy = M.Mxx = M.Mxy = M.Myx = M.Myy = 0.0;
-    const bool pinned = qvalid && t == 0 && p.first;
-    if (qvalid && !pinned) {
-        const double* bmq = p.bm + t;
-        M.n = __ldg(bmq + 5 * p.ldbm);
-        M.Bx = __ldg(bmq); M.By = __ldg(bmq + p.ldbm); M.Bxx = __ldg(bmq + 2 * p.ldbm);
-        M.Byy = __ldg(bmq + 3 * p.ldbm); M.Bxy = __ldg(bmq + 4 * p.ldbm);
-        if (M.n > 0.0) {
-            const double* d = p.dyn + (size_t)t * 6 + 3 * half;     // the role's three moments
-            const double y = d[0], m1 = d[1], m2 = d[2];
-            if (half) { M.Yy = y; M.Myx = m1; M.Myy = m2; } else { M.Yx = y; M.Mxx = m1; M.Mxy = m2; }
-        }
-    }
     unsigned long long my_iters = 0;
     for (int phase = 0; phase < 2; ++phase) {
-        if (phase == grp) {       // warp-uniform: a warp holds 16 slots of one colour
-            double res = 0.0, th = 0.0, s_new = 0.0, c_new = 1.0;
-            PoseIn P;
-            P.ax = P.ay = P.ath = P.sa = 0.0; P.ca = 1.0; P.bx = P.by = P.bth = 0.0; P.uav = P.uaw = P.ucv = P.ucw = 0.0;
-            P.D0x = P.D0y = P.dth0 = P.D1x = P.D1y = P.dth1 = 0.0; P.has_next = 0;
-            bool solve = false;
-            double ox = 0.0, oy = 0.0, th0 = 0.0, s0 = 0.0, c0 = 1.0;
-            if (qvalid) {
-                // neighbours: old poses for the odd phase, new (odd) poses for the even phase
-                double (*X)[ST_XT] = phase == 0 ? S.xs : S.xn;
-                const bool has_next = t + 1 < T;
-                solve = !pinned && M.n > 0.0;
-                ox = S.xs[0][li]; oy = S.xs[1][li]; th0 = S.xs[2][li]; s0 = S.sn[li]; c0 = S.cs[li];
-                th = th0;
-                if (pinned) {
-                    res = S.xs[half][li];
-                } else {
-                    P.ax = X[0][li - 1]; P.ay = X[1][li - 1]; P.ath = X[2][li - 1];
-                    P.sa = S.sn[li - 1]; P.ca = S.cs[li - 1];
-                    if (has_next) { P.bx = X[0][li + 1]; P.by = X[1][li + 1]; P.bth = X[2][li + 1]; }
-                    P.uav = S.u[0][li - 1]; P.uaw = S.u[1][li - 1];
-                    P.ucv = S.u[0][li]; P.ucw = S.u[1][li];
-                    P.D0x = S.inc[0][li - 1]; P.D0y = S.inc[1][li - 1]; P.dth0 = S.inc[2][li - 1];
-                    P.D1x = S.inc[0][li]; P.D1y = S.inc[1][li]; P.dth1 = S.inc[2][li];
-                    P.has_next = has_next ? 1 : 0;
-                    if (!solve) {       // sensors.py:147-151: no observation, average of the neighbours
-                        const bool t1 = t == 1 && p.first;
-                        const double pv = t1 ? p.x0[half] : X[half][li - 1];
-                        res = (pv + X[half][li + 1]) / 2.0;
-                        th = ((t1 ? p.x0[2] : X[2][li - 1]) + X[2][li + 1]) / 2.0;
-                    }
+        // every lane pair solves one pose per colour phase: the odd pose tb-1+2q from the OLD even neighbours, then, after the
+        // block barrier, the even pose tb+2q from the NEW odd ones
+        const Mom& M = cur.M;
+        const int t = cur.t, li = cur.li;
+        const bool qvalid = cur.valid, pinned = cur.pinned;
+        double res = 0.0, th = 0.0;
+        PoseIn P;
+        P.ax = P.ay = P.ath = P.sa = 0.0; P.ca = 1.0; P.bx = P.by = P.bth = 0.0; P.uav = P.uaw = P.ucv = P.ucw = 0.0;
+        P.D0x = P.D0y = P.dth0 = P.D1x = P.D1y = P.dth1 = 0.0; P.has_next = 0;
+        bool solve = false;
+        double ox = 0.0, oy = 0.0, th0 = 0.0, s0 = 0.0, c0 = 1.0;
+        if (qvalid) {
+            // neighbours: old poses for the odd phase, new (odd) poses for the even phase
+            double (*X)[ST_XT] = phase == 0 ? S.xs : S.xn;
+            const bool has_next = t + 1 < T;
+            solve = !pinned && M.n > 0.0;
+            ox = S.xs[0][li]; oy = S.xs[1][li]; th0 = S.xs[2][li]; s0 = S.sn[li]; c0 = S.cs[li];
+            th = th0;
+            if (pinned) {
+                res = S.xs[half][li];
+            } else {
+                P.ax = X[0][li - 1]; P.ay = X[1][li - 1]; P.ath = X[2][li - 1];
+                P.sa = S.sn[li - 1]; P.ca = S.cs[li - 1];
+                if (has_next) { P.bx = X[0][li + 1]; P.by = X[1][li + 1]; P.bth = X[2][li + 1]; }
+                P.uav = S.u[0][li - 1]; P.uaw = S.u[1][li - 1];
+                P.ucv = S.u[0][li]; P.ucw = S.u[1][li];
+                P.D0x = S.inc[0][li - 1]; P.D0y = S.inc[1][li - 1]; P.dth0 = S.inc[2][li - 1];
+                P.D1x = S.inc[0][li]; P.D1y = S.inc[1][li]; P.dth1 = S.inc[2][li];
+                P.has_next = has_next ? 1 : 0;
+                if (!solve) {       // sensors.py:147-151: no observation, average of the neighbours
+                    const bool t1 = t == 1 && p.first;
+                    const double pv = t1 ? p.x0[half] : X[half][li - 1];
+                    res = (pv + X[half][li + 1]) / 2.0;
+                    th = ((t1 ? p.x0[2] : X[2][li - 1]) + X[2][li + 1]) / 2.0;
                 }
             }
-            {
-                // (lanes that do not solve still run the loop with harmless values: the pair shuffles inside newton_trig
-                //  need every lane of the warp)
-                double r2 = 0.0, th2 = th0;
-                const int it = newton_trig(p.cfg, P, M, half, ox, oy, th2, s0, c0, p.tol, solve ? p.maxit : 1, r2);
-                if (solve) { res = r2; th = th2; my_iters += (unsigned long long)(half == 0 ? it : 0); }
-            }
-            if (qvalid && !pinned) {
-                // the new heading's sin/cos exactly as next sweep's projection forms them (one sincos per pose per sweep)
-                if (phase == 0) {
-                    double st, ct;
-                    sincos(sub_rn(th, ICM_HALFPI), &st, &ct);
-                    s_new = ct; c_new = -st;
-                }
-                S.xn[half][li] = res;
-                if (half == 0) {
-                    S.xn[2][li] = th;
-                    if (phase == 0) { S.sn[li] = s_new; S.cs[li] = c_new; }   // (old odd headings are no longer needed)
-                }
+        }
+        {
+            // (lanes that do not solve still run the loop with harmless values: the pair shuffles inside newton_trig
+            //  need every lane of the warp)
+            double r2 = 0.0, th2 = th0;
+            const int it = newton_trig(p.cfg, P, M, half, ox, oy, th2, s0, c0, p.tol, solve ? p.maxit : 1, r2);
+            if (solve) { res = r2; th = th2; my_iters += (unsigned long long)(half == 0 ? it : 0); }
+        }
+        SlotMom nxt = cur;
+        if (phase == 0) nxt = solve_slot_load(p, tb, q, half, 1);      // (the even pose's moments arrive during the barrier)
+        if (qvalid && !pinned) {
+            // the new heading's sin/cos exactly as next sweep's projection forms them (one sincos per pose per sweep)
+            double st, ct;
+            sincos(sub_rn(th, ICM_HALFPI), &st, &ct);
+            S.xn[half][li] = res;
+            if (half == 0) {
+                S.xn[2][li] = th;
+                S.sn[li] = ct; S.cs[li] = -st;      // (the old headings of this colour are no longer needed)
             }
         }
         __syncthreads();
+        cur = nxt;
     }
     if (p.iters) {
         my_iters = (unsigned long long)warp_sum_i((int)my_iters);
@@ -312,10 +326,9 @@ k_solve_tile(const SolveParams p)
     const int n_own = min(ST_OWN, p.t_hi - tb);
     for (int r = 0; r < 3; ++r)
         for (int k = tid; k < n_own; k += ST_THREADS) p.xout[r * p.ldout + tb + k] = S.xn[r][k + 2];
-    if (tid < n_own) {
-        const int tt = tb + tid, l2 = tid + 2;
+    for (int k = tid; k < n_own; k += ST_THREADS) {
+        const int tt = tb + k, l2 = k + 2;
         if (tt == 0 && p.first) p.ppout[0] = make_ppar(p.x0[0], p.x0[1], p.x0[2]);
-        else if (tt & 1) p.ppout[tt] = make_double4(S.xn[0][l2], S.xn[1][l2], -S.cs[l2], S.sn[l2]);   // (formed in the odd phase)
-        else p.ppout[tt] = make_ppar(S.xn[0][l2], S.xn[1][l2], S.xn[2][l2]);
+        else p.ppout[tt] = make_double4(S.xn[0][l2], S.xn[1][l2], -S.cs[l2], S.sn[l2]);
     }
 }

@@ -148,8 +148,11 @@ k_tail_labels(const TailState* ts, const FarRec* __restrict__ far, const int* __
         raw_x[label] = r.sx / (double)r.n;
         raw_y[label] = r.sy / (double)r.n;
         cnt[label] = r.n;
+        // the scan's far observations: -1 from the association kernel, or the label an earlier sweep gave them when the scan
+        // was certified on its run records (labels >= lsearch are exactly the labels created inside a sweep)
+        const int ls = st->lsearch;
         for (int i = off[r.t]; i < off[r.t + 1]; ++i)
-            if (c[i] < 0) c[i] = label;
+            if (c[i] < 0 || c[i] >= ls) c[i] = label;
     }
 }
 
@@ -183,7 +186,7 @@ k_fused_means(const DevState* st, long long* fsum_x, long long* fsum_y, const in
 __global__ void __launch_bounds__(256)
 k_tail_compact(DevState* st, TailState* ts, const int* __restrict__ flag, const int* __restrict__ pos, const double* __restrict__ raw_x,
                const double* __restrict__ raw_y, const int* __restrict__ cnt, double* __restrict__ kx, double* __restrict__ ky,
-               double* __restrict__ kc, int* __restrict__ parent, unsigned long long* bb, int Lcap)
+               double* __restrict__ kc, int* __restrict__ parent, unsigned long long* bb, int Lcap, int* __restrict__ klab)
 {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
@@ -193,6 +196,7 @@ k_tail_compact(DevState* st, TailState* ts, const int* __restrict__ flag, const 
             const double x = raw_x[l], y = raw_y[l];
             kx[p] = x; ky[p] = y; kc[p] = (double)cnt[l];
             parent[p] = p;
+            klab[p] = l;
             mnx = mxx = x; mny = mxy = y;
         }
         if (l == Lcap - 1) {
@@ -218,40 +222,72 @@ __global__ void k_tail_geom(const unsigned long long* bb, const DevState* st, Ta
     ts->degenerate = (fmax(mxx - mnx, mxy - mny) >= dist_thr) ? 0 : 1;
 }
 
-// nearest OTHER survivor (zero distances are never neighbours, ICM_SLAM.py:242) within dist_thr
+// nearest OTHER survivor (zero distances are never neighbours, ICM_SLAM.py:242) within dist_thr; and, for free, calc_cambio
+// (ICM_SLAM.py:490-495) of the new map against the previous one: the landmark a new landmark was updated from is its nearest
+// old landmark whenever it stayed inside that landmark's proven radius r (<= half the distance to any other old landmark:
+// |new - other| >= 2 r - d > d).  lmrec still holds the previous map here.
 __global__ void __launch_bounds__(256)
-k_tail_nn(const DevState* st, TailState* ts, const double* __restrict__ kx, const double* __restrict__ ky, const FGeom* __restrict__ geom,
+k_tail_nn(DevState* st, TailState* ts, const double* __restrict__ kx, const double* __restrict__ ky, const FGeom* __restrict__ geom,
           const int* __restrict__ cell_start, const double2* __restrict__ pts, const int* __restrict__ idx, double thr2_lt,
-          int* __restrict__ nn, int* __restrict__ ind_flag, double* __restrict__ nnd2, int Lcap)
+          int* __restrict__ nn, int* __restrict__ ind_flag, double* __restrict__ nnd2, int Lcap, const int* __restrict__ klab,
+          const double* __restrict__ kc, const LmRec* __restrict__ lmrec_old)
 {
+    __shared__ double red[3][8];
+    __shared__ int redn[2][8];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= Lcap) return;
     const int K = st->kept;
-    if (j >= K || ts->degenerate) { ind_flag[j] = 0; nnd2[j] = 0.0; return; }
-    const FGeom g = *geom;
-    const double xj = kx[j], yj = ky[j];
-    const int c = fgrid_cell(g, xj, yj);
-    const int s = cell_start[c], e = cell_start[c + 1];
-    double best = INFINITY, lo = INFINITY, hi = INFINITY;
-    int arg = -1;
-    for (int k = s; k < e; ++k) {
-        const double2 p = pts[k];
-        const int id = idx[k];
-        const double s2 = dist2_rn(p.x - xj, p.y - yj);
-        if (id == j || s2 == 0.0) continue;
-        bool take = s2 < lo;
-        if (!take && s2 <= hi && arg >= 0) {
-            const double dk = __dsqrt_rn(s2), db = __dsqrt_rn(best);
-            take = dk < db || (dk == db && id < arg);
+    const bool act = j < Lcap && j < K && !ts->degenerate;
+    double cd = 0.0;
+    int cres = 0, cun = 0, nind = 0;
+    if (j < Lcap && !act) { ind_flag[j] = 0; nnd2[j] = 0.0; if (j == 0 && K > 0) cun = K; }
+    if (act) {
+        const int l = klab[j];
+        if (l < st->lsearch) {
+            const LmRec o = lmrec_old[l];
+            const double c = kc[j];
+            const double d = dist_rn(mul_rn(kx[j], c) / c - o.x, mul_rn(ky[j], c) / c - o.y);      // (the map's own rounding, k_tail_finalize)
+            if (d < o.r * (1.0 - 1e-9)) { cres = 1; cd = d; }
         }
-        if (take) { best = s2; arg = id; lo = s2 * (1.0 - 8.8817841970012523e-16); hi = s2 * (1.0 + 8.8817841970012523e-16); }
+        cun = 1 - cres;
+        const FGeom g = *geom;
+        const double xj = kx[j], yj = ky[j];
+        const int c = fgrid_cell(g, xj, yj);
+        const int s = cell_start[c], e = cell_start[c + 1];
+        double best = INFINITY, lo = INFINITY, hi = INFINITY;
+        int arg = -1;
+        for (int k = s; k < e; ++k) {
+            const double2 p = pts[k];
+            const int id = idx[k];
+            const double s2 = dist2_rn(p.x - xj, p.y - yj);
+            if (id == j || s2 == 0.0) continue;
+            bool take = s2 < lo;
+            if (!take && s2 <= hi && arg >= 0) {
+                const double dk = __dsqrt_rn(s2), db = __dsqrt_rn(best);
+                take = dk < db || (dk == db && id < arg);
+            }
+            if (take) { best = s2; arg = id; lo = s2 * (1.0 - 8.8817841970012523e-16); hi = s2 * (1.0 + 8.8817841970012523e-16); }
+        }
+        const int f = (arg >= 0 && best <= thr2_lt) ? 1 : 0;      // amin < dist_thr (strict, :245)
+        nn[j] = arg < 0 ? 0 : arg;
+        ind_flag[j] = f;
+        // for the hint radius: the nearest other survivor within 2 thr1 (only searched when none is closer than the gate)
+        nnd2[j] = f ? best : nearest_other_wide(g, cell_start, pts, idx, j, xj, yj);
+        nind = f;
     }
-    const int f = (arg >= 0 && best <= thr2_lt) ? 1 : 0;      // amin < dist_thr (strict, :245)
-    nn[j] = arg < 0 ? 0 : arg;
-    ind_flag[j] = f;
-    // for the hint radius: the nearest other survivor within 2 thr1 (only searched when none is closer than the gate)
-    nnd2[j] = f ? best : nearest_other_wide(g, cell_start, pts, idx, j, xj, yj);
-    if (f) atomicAdd(&ts->n_ind, 1);
+    // block totals -> one set of atomics per block
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const double mn = warp_min(cres ? cd : INFINITY), mx = warp_max(cres ? cd : 0.0), sm = warp_sum(cd);
+    const int un = warp_sum_i(cun), ni = warp_sum_i(nind);
+    if (lane == 0) { red[0][w] = mn; red[1][w] = mx; red[2][w] = sm; redn[0][w] = un; redn[1][w] = ni; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = red[0][0], b = red[1][0], c = red[2][0];
+        int u = redn[0][0], n2 = redn[1][0];
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) { a = fmin(a, red[0][k]); b = fmax(b, red[1][k]); c += red[2][k]; u += redn[0][k]; n2 += redn[1][k]; }
+        if (a < INFINITY) { atomic_min_pos(st->cambio + 0, a); atomic_max_pos(st->cambio + 1, b); atomicAdd(st->cambio + 2, c); }
+        if (u) atomicAdd(&st->cambio_unres, u);
+        if (n2) atomicAdd(&ts->n_ind, n2);
+    }
 }
 
 // nothing to merge: the survivors, in order, are the new map (count-weighted mean of one member, :258-260)
@@ -399,7 +435,7 @@ __device__ void tail_slow_body(DevState* st, TailState* ts, double dist_thr, dou
         counts_state[r] = c;
     }
     for (int l = tid; l < Lcap; l += nth) remap[l] = (l < st->raw_l && kflag[l]) ? rank[lab[kpos[l]]] : -1;
-    if (tid == 0) { st->new_l = newL; st->lact = newL; st->n_ind = n_ind; ts->remap_identity = 0; }
+    if (tid == 0) { st->new_l = newL; st->lact = newL; st->n_ind = n_ind; ts->remap_identity = 0; st->cambio_unres += 1; }   // (merged map: calc_cambio needs the full search)
     __syncthreads();
     // ---- rebuild the landmark grid over the merged map (it is the next sweep's association grid) -------------
     {

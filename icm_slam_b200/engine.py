@@ -196,6 +196,35 @@ class Engine:
                                       C.byref(opts), ms)
         return check(st, self._h)
 
+    def iterate_until(self, x0, max_sweeps, tol_max_change=0.0, schedule="redblack", solver="newton", view="prev", newton_tol=0.0,
+                      newton_maxit=0, fused=True):
+        """The driver loop with the convergence monitor (sensors.py:302-315): sweeps of the resident poses / map until the
+        largest landmark change of a sweep (calc_cambio's maximum) is <= tol_max_change, at most max_sweeps.  Returns
+        (sweeps run, cambios (n, 3): min / max / mean per sweep)."""
+        opts = SweepOpts(_lib.SCHED[schedule], _lib.SOLVER[solver], _lib.VIEW[view], int(newton_maxit), float(newton_tol),
+                         int(bool(fused)), 0)
+        x0 = np.ascontiguousarray(np.asarray(x0, dtype=np.float64).reshape(3))
+        n = C.c_int32(0)
+        cam = np.zeros((3, max(int(max_sweeps), 1)))
+        check(self.lib.icmslam_iterate_until(self._h, C.c_void_p(x0.ctypes.data), int(max_sweeps), float(tol_max_change), C.byref(opts),
+                                             _ptr(cam)[0], C.byref(n)), self._h)
+        return int(n.value), np.ascontiguousarray(cam[:, : n.value].T)
+
+    def associate(self, mapa, mapa_referencia, obs):
+        """Mapa.actualizar for one scan (ICM_SLAM.py:128-201): `mapa` (2 x L, updated in place), `mapa_referencia` (2 x Lref),
+        `obs` (n, 2) projected observations.  Returns the labels c (int64, like np.argmin).  landmarks_actuales and
+        cant_obs_i live in the handle."""
+        assert isinstance(mapa, np.ndarray) and mapa.dtype == np.float64 and mapa.ndim == 2 and mapa.shape[0] == 2 and mapa.strides[1] == 8
+        ref = np.ascontiguousarray(mapa_referencia, dtype=np.float64)
+        obs = np.asarray(obs, dtype=np.float64)
+        n = int(obs.shape[0])
+        ox, oy = np.ascontiguousarray(obs[:, 0]), np.ascontiguousarray(obs[:, 1])
+        c = np.zeros(n, np.int32)
+        Lr = int(ref.shape[1]) if ref.ndim == 2 else 0
+        check(self.lib.icmslam_associate(self._h, _ptr(ref)[0] if Lr else None, Lr, _rows(ref, 2) if Lr else 1, _ptr(ox)[0], _ptr(oy)[0], n,
+                                         _ptr(mapa)[0], min(int(mapa.shape[1]), self.L), _rows(mapa, 2), _ptr(c)[0], HOST), self._h)
+        return c.astype(np.int64)
+
     def set_poses(self, x):
         """ICM.positions (3 x T) -> device; iterate(None, ...) then sweeps them in place on the device."""
         if not _is_torch(x) and not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.ndim == 2 and x.strides[1] == 8):

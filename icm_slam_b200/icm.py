@@ -13,8 +13,15 @@ module:
   (ICM_SLAM.py:104-265).
 * `filtrar_z(z, config)`, `tras_rot_z`, `calc_cambio`, `entrepi`, `Rota` (ICM_SLAM.py:22-58, :455-495).
 
-Everything numeric runs in the CUDA library through the C ABI (include/icmslam.h); there is no
-CPU fallback -- without the built library or without a GPU these calls raise.
+The sweep, extraction, association, map filter, pass 0 and calc_cambio run in the CUDA library through the C ABI
+(include/icmslam.h); there is no CPU fallback -- without the built library or without a GPU these calls raise.  The
+four geometry helpers `entrepi`, `Rota`, `tras_rot_z`, `precondicionar` are host numpy one-liners, as in the reference
+(a handful of flops on one pose / one array; the sweep kernels have their own device versions).
+
+DEFAULT MODE.  `ICM_SLAM(config)` runs the restated parallel sweep (red-black schedule, exact Newton solve, previous-map
+view: config.schedule / solver / map_view = 'redblack' / 'newton' / 'prev'), which converges to the same fixed point as the
+reference but is NOT the reference's iteration: a reference YAML gives the reference's own poses sweep by sweep only with
+schedule='sequential', solver='nm', map_view='running' (DESIGN.md section 2).
 """
 from __future__ import annotations
 
@@ -154,6 +161,23 @@ class Mapa:
     def clear_obs(self):
         self._cant = np.zeros(self.L)
 
+    def actualizar(self, mapa, mapa_referencia, obs):
+        """ICM_SLAM.py:128-201 for one scan: nearest landmark of `mapa_referencia` (its first landmarks_actuales columns) for
+        every row of `obs` (n, 2), gate dist_thr, one new label for the scan's far observations, running means written into
+        `mapa` (2 x L, in place), counts into cant_obs_i.  Returns (mapa, c) like the reference.  The very first call of a
+        fresh Mapa (landmarks_actuales == 0) clusters the scan as scipy's fcluster does (:160-165)."""
+        e = self._engine if self._engine is not None else _scratch_engine(self._config)
+        if self._engine is None:       # a detached Mapa keeps its state on the host: mirror it into the scratch engine
+            e.landmarks_actuales = self._lact
+            e.set_counts(self._cant)
+        if not (isinstance(mapa, np.ndarray) and mapa.dtype == np.float64 and mapa.ndim == 2 and mapa.strides[1] == 8):
+            raise TypeError("mapa must be a (2, L) float64 array (it is updated in place, like the reference's)")
+        c = e.associate(mapa, mapa_referencia, obs)
+        if self._engine is None:
+            self._lact = e.landmarks_actuales
+            self._cant = e.counts(self.L)
+        return mapa, c
+
     def filtrar(self, mapa, cant_obs_i=None):
         """ICM_SLAM.py:204-265 on a 2 x L map; counts default to the attached solver's last sweep.
         Returns the 2 x L buffer (caller slices [:, :landmarks_actuales]) like the reference."""
@@ -186,6 +210,7 @@ class ICM_SLAM:
         self.positions = None
         self._engine = Engine(config, device=int(getattr(config, "device", 0)))
         self._loaded = None
+        self._attached = None
 
     # ---- data ---------------------------------------------------------------------------------
     def load_data(self, mapa_obj, mediciones, u, odometria, x0=""):
@@ -201,16 +226,53 @@ class ICM_SLAM:
             pass   # the legacy API keeps zeros; ICM_ROS sets x0 = odometria[:,0] in inicializar_online (sensors.py:61)
         self._sync_data()
 
-    def _sync_data(self):
-        key = (id(self.mediciones), id(self.u), id(self.odometria), np.shape(self.mediciones))
-        if self._loaded == key:
-            return
-        self._engine.load(self.mediciones, self.odometria, self.u, precondition=False)
-        self._engine.extract()
-        self._loaded = key
+    @staticmethod
+    def _fingerprint(a):
+        """Cheap content fingerprint of an input array: where it lives, its shape, and a CRC of a strided sample (<= 1k
+        values incl. the first and last column: ~0.1 ms even for a GB-sized log).  Catches a new array, an array of another shape, a freed-and-reused
+        address and in-place edits that touch the sample; after other in-place edits call `invalidate()`."""
+        import zlib
+        a = np.asarray(a)
+        if a.size == 0:
+            return (0,)
+        flat = a.reshape(-1)
+        step = max(1, flat.size // 1024)
+        sample = np.ascontiguousarray(flat[::step])
+        edge = np.ascontiguousarray(a[..., [0, -1]]) if a.ndim == 2 else sample[:1]
+        return (a.__array_interface__["data"][0], a.shape, a.strides, zlib.crc32(sample.tobytes()), zlib.crc32(edge.tobytes()))
+
+    def _data_key(self):
+        return (self._fingerprint(self.mediciones), self._fingerprint(self.u), self._fingerprint(self.odometria))
+
+    def adopt_engine(self, engine):
+        """Use an Engine that already holds (mediciones, odometria, u) -- loaded and extracted through the Engine API --
+        instead of uploading the dataset again."""
+        if self._engine is not engine:
+            self._engine.close()
+            self._engine = engine
+        self._loaded = self._data_key()
         if self.mapa_obj is None:
             self.mapa_obj = Mapa(self.config)
-        self.mapa_obj._attach(self._engine)
+        self.mapa_obj._attach(engine)
+        self._attached = self.mapa_obj
+
+    def invalidate(self):
+        """Forget the device copy of the dataset: the next call uploads and re-extracts it (after in-place edits of
+        `mediciones` / `u` / `odometria`, e.g. appending into a preallocated buffer)."""
+        self._loaded = None
+
+    def _sync_data(self):
+        key = self._data_key()
+        if self._loaded != key:
+            self._engine.load(self.mediciones, self.odometria, self.u, precondition=False)
+            self._engine.extract()
+            self._loaded = key
+            self._attached = None
+        if self.mapa_obj is None:
+            self.mapa_obj = Mapa(self.config)
+        if self._attached is not self.mapa_obj:       # a Mapa the caller replaced (or a fresh dataset): attach it to the engine
+            self.mapa_obj._attach(self._engine)
+            self._attached = self.mapa_obj
 
     # ---- the sweep ------------------------------------------------------------------------------
     def iterations_process_offline(self, mapa_viejo, x):

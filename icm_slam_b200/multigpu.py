@@ -276,6 +276,23 @@ class SegmentedSolver:
         dist.all_gather(out, buf, group=self.group)
         return np.concatenate([o.cpu().numpy()[:, :n] for o, n in zip(out, lens)], axis=1)
 
+    def gather_ragged_int32(self, mine):
+        """Concatenation over the ranks (in rank order) of one int32 vector per rank (host)."""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return np.asarray(mine, dtype=np.int32)
+        dev = "cuda:%d" % self.device if dist.get_backend(self.group) == "nccl" else "cpu"
+        n = torch.tensor([int(mine.shape[0])], dtype=torch.int64, device=dev)
+        ns = [torch.zeros_like(n) for _ in range(self.world)]
+        dist.all_gather(ns, n, group=self.group)
+        lens = [int(v.item()) for v in ns]
+        buf = torch.zeros(max(lens), dtype=torch.int32, device=dev)
+        buf[: mine.shape[0]] = torch.from_numpy(np.ascontiguousarray(mine, dtype=np.int32)).to(dev)
+        out = [torch.empty_like(buf) for _ in range(self.world)]
+        dist.all_gather(out, buf, group=self.group)
+        return np.concatenate([o.cpu().numpy()[:k] for o, k in zip(out, lens)])
+
     def get_map(self):
         return self.engine.get_map()
 
@@ -284,7 +301,8 @@ class SegmentedSolver:
 
 
 # ---- bench arm for N > 1 (called by bench.py under torchrun) -----------------------------------------------------
-def bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, peaks, ClockSampler, make_data, config_for):
+def bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, peaks, ClockSampler, make_data, config_for, result_hash,
+          runs_bytes):
     import json
     import time
 
@@ -297,7 +315,7 @@ def bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, p
     name = args.workload
     L_true, T, desc = WORKLOADS[name]
     d = make_data(name)
-    cfg = config_for(L_true)
+    cfg = config_for(L_true, name)
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
@@ -330,11 +348,18 @@ def bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, p
     ms = float(ms_t.item())
     clocks = sampler.stop()
     launches = (sol.launch_count() - lc0) // max(args.steps, 1)
-    # fused kernel time on this rank (separate short loop: reading the events synchronises)
+    # result hash: poses (gathered), map, labels of the owned scans (gathered) -- identical for any number of segments
+    x_all = sol.gather_poses()
+    offs = sol.engine.get_extraction()["off"]
+    c_own = np.ascontiguousarray(sol.engine.associations()[offs[sol.t_lo]:offs[sol.t_hi]])
+    c_all = sol.gather_ragged_int32(c_own)
+    sha = result_hash(x_all, sol.get_map(), c_all)
+    # run kernel time on this rank (separate short loop: reading the events synchronises)
     kt = []
     from . import _lib
     for _ in range(5):
-        sol._sweep_once(_lib.SweepOpts(_lib.SCHED["redblack"], _lib.SOLVER["newton"], _lib.VIEW["prev"], 0, 0.0, 1, 2))
+        with torch.cuda.stream(sol._stream):
+            sol._sweep_once(_lib.SweepOpts(_lib.SCHED["redblack"], _lib.SOLVER["newton"], _lib.VIEW["prev"], 0, 0.0, 1, 2))
         kt.append(sol.engine.kernel_ms()[0])
     k_ms = torch.tensor([float(np.mean(kt))], dtype=torch.float64, device=dev)
     dist.all_reduce(k_ms, op=dist.ReduceOp.MAX)
@@ -367,10 +392,7 @@ def bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, p
         peak, peak_src = peaks()
         # the dominant kernel's share of the sweep on one rank: its segment's bytes over its time
         Tseg = sol.t_hi - sol.t_lo
-        if True:     # k_runs' own share (poses, offsets, observations, map in; labels, statistics out)
-            seg_bytes = 24 * Tseg + 4 * (Tseg + 1) + 16 * n_local + 16 * L_true + 4 * n_local + 24 * L_true
-        else:
-            seg_bytes = sweep_bytes(Tseg, n_local, L_true)
+        seg_bytes = runs_bytes(Tseg, n_local, L_true)     # the run kernels' own share of this segment
         achieved = seg_bytes / (float(k_ms.item()) * 1e-3) / 1e9
         sweep_achieved = B_sweep / (ms * 1e-3) / 1e9
         out = {
@@ -387,7 +409,8 @@ def bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, p
                     "d2h_bytes_per_step": int(bytes_t[1].item()), "steps": e2e_steps,
                     "call": "SegmentedSolver.set_map/set_poses/sweep/owned_poses/get_map with host numpy buffers on every rank"},
             "gpu_launches": int(launches) * args.steps * world, "gpu_launches_per_step": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_sweep_fused (rank 0's segment)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "result_sha256": sha,
+            "roofline": {"bound": "hbm", "kernel": "k_runs + k_assoc_tiles (rank 0's segment)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": float(k_ms.item()),
                          "algorithmic_bytes": int(seg_bytes),
                          "sweep": {"algorithmic_bytes": int(B_sweep), "achieved": sweep_achieved, "frac": sweep_achieved / (peak * world),

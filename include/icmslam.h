@@ -212,6 +212,26 @@ int icmslam_filter_map(icmslam_handle* h, const double* map_in, int64_t ld_in, c
 int icmslam_calc_cambio(icmslam_handle* h, const double* map_new, int32_t L_new, int64_t ld_new,
                         const double* map_old, int32_t L_old, int64_t ld_old, double* out3, int32_t memspace);
 
+/* -- Mapa.actualizar(mapa, mapa_referencia, obs) for ONE scan (ICM_SLAM.py:128-201): the step pass 0 and the sweep take per
+ * scan, exposed for callers that drive the scan loop themselves.  obs_x / obs_y: the scan's n_obs projected observations
+ * (world frame).  map_ref: 2 x L_ref reference map (searched over its first min(landmarks_actuales, L_ref) columns).
+ * mapa: 2 x cap map under construction, updated in place (running means, ICM_SLAM.py:191-194).  c: n_obs labels out
+ * (int32; the reference returns int64).  State read and updated: landmarks_actuales, cant_obs_i.  Branch A
+ * (landmarks_actuales == 0: scipy's fcluster, ICM_SLAM.py:160-165) runs through icmslam_fcluster.
+ * ICMSLAM_ERR_LABEL_CAP where the reference raises IndexError (:191). */
+int icmslam_associate(icmslam_handle* h, const double* map_ref, int32_t L_ref, int64_t ld_ref, const double* obs_x,
+                      const double* obs_y, int32_t n_obs, double* mapa, int32_t cap, int64_t ld_mapa, int32_t* c,
+                      int32_t memspace);
+
+/* -- the driver loop with the convergence monitor the reference only prints (sensors.py:302-315: calc_cambio of every
+ * pass): at most max_sweeps sweeps of the resident poses / map (icmslam_set_poses, icmslam_set_map), stopping after the first
+ * sweep whose largest landmark change (calc_cambio's maximum, ICM_SLAM.py:490-495) is <= tol_max_change (<= 0: never).
+ * cambios (host, 3 x max_sweeps, row-major rows min / max / mean; may be NULL) receives every pass's triple; *n_done the
+ * number of sweeps run.  The triple comes out of the sweep's own map filter (one 200-byte read-back per sweep); the
+ * full search of icmslam_calc_cambio is only needed when landmarks merged or appeared in that sweep. */
+int icmslam_iterate_until(icmslam_handle* h, const double* x0, int32_t max_sweeps, double tol_max_change,
+                          const icmslam_sweep_opts* opts, double* cambios, int32_t* n_done);
+
 /* -- filtrar_obs.m (scripts/filtrar_obs.m:6-50), the offline scan gate: keep the k(t) nearest
  * returns per scan.  obs / out: B x T. */
 int icmslam_filtrar_obs(icmslam_handle* h, const double* obs, int32_t B, int32_t T, int64_t ld, double max_dist,
