@@ -1,5 +1,6 @@
-"""CPU checks of bench.py's reference arm (the one place besides tests/ and smoke() that may execute oracle/) and of the
-result writers: the JSON contract the driver parses, no GPU needed."""
+"""CPU checks of bench.py's reference arm (the unmodified reference from baseline/_ref or /root/reference, driven through
+oracle/ref_runner.py -- the one place besides tests/ and smoke() that may execute oracle/) and of the result writers: the JSON
+contract the driver parses, no GPU needed."""
 import json
 import os
 import subprocess
@@ -18,7 +19,8 @@ def test_reference_arm_prints_one_contract_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "sweeps/s" and d["higher_is_better"] is True and d["n_gpus"] == 1
-    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 1
+    assert d["extrapolated"] is True and d["cpu_baseline"]["extrapolated"] is True and "EXTRAPOLATED" in d["cpu_baseline"]["sample"]
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"] and "model" not in d["config"]
