@@ -51,26 +51,46 @@ struct __align__(16) AssocSmem {
     double2 pp[RT_TILE];           // projection origin of each scan (self.x0 for scan 0)
     double2 rsc[RT_TILE];          // (sin, cos) of (projection heading - pi/2)
     int off[RT_TILE + 4];          // off[t] of the tile's scans
-    int hkey[RS_SLOTS];            // the tile's statistics slots: landmark of each slot (-1: free), assigned while the runs are written
-    int hcnt[RS_SLOTS];            // runs that name the slot
-    unsigned acc[RS_SLOTS][5];     // the statistics table itself (runs.cuh chunk_statistics)
+    // the tile's statistics slots: a small hash (landmark -> slot) filled while the runs are counted; slots are numbered densely
+    int hkey[RS_SLOTS];            // landmark at each hash position (-1: free)
+    int hid[RS_SLOTS];             // its slot (-1: not numbered yet)
+    int hcnt[RS_SLOTS];            // runs that name it
+    int slot_label[RS_SLOTS];      // landmark of each slot
+    int nslots;
+    TileSmem tile;                 // the statistics table and the staged landmark records (runs.cuh)
     unsigned long long mbar;
 };
 
-// slot of landmark `label` in the tile's statistics table (open addressing, at most 8 probes); RS_NOSLOT when the table is
-// crowded or the slot already serves RS_MAX_ADDS runs (their statistics go straight to the global sums)
-__device__ __forceinline__ int slot_of(AssocSmem& S, int label)
+// registers landmark `label` in the tile's hash (open addressing, at most 8 probes; a crowded table leaves it out)
+__device__ __forceinline__ void slot_insert(AssocSmem& S, int label)
 {
     unsigned h = ((unsigned)label * 2654435761u) >> 24;
 #pragma unroll 1
     for (int q = 0; q < 8; ++q) {
-        if (h == RS_NOSLOT) h = 0;
         int key = ((volatile int*)S.hkey)[h];
         if (key == -1) {
             const int prev = atomicCAS(&S.hkey[h], -1, label);
             key = (prev == -1) ? label : prev;
         }
-        if (key == label) return atomicAdd(&S.hcnt[h], 1) < RS_MAX_ADDS ? (int)h : RS_NOSLOT;
+        if (key == label) return;
+        h = (h + 1) & (RS_SLOTS - 1);
+    }
+}
+
+// slot of landmark `label` for a run of n beams; RS_NOSLOT when the landmark is not in the table, the run is too long for the
+// limbs or the slot already serves RS_MAX_ADDS runs (their statistics go straight to the global sums)
+__device__ __forceinline__ int slot_of(AssocSmem& S, int label, int n)
+{
+    if (n > RS_MAX_BEAMS) return RS_NOSLOT;
+    unsigned h = ((unsigned)label * 2654435761u) >> 24;
+#pragma unroll 1
+    for (int q = 0; q < 8; ++q) {
+        const int key = S.hkey[h];
+        if (key == label) {
+            const int id = S.hid[h];
+            return (id >= 0 && id < RS_NOSLOT && atomicAdd(&S.hcnt[h], 1) < RS_MAX_ADDS) ? id : RS_NOSLOT;
+        }
+        if (key == -1) return RS_NOSLOT;
         h = (h + 1) & (RS_SLOTS - 1);
     }
     return RS_NOSLOT;
@@ -129,8 +149,8 @@ k_assoc_tiles(const AssocParams p)
             const double4 pq = ldg_ppar(R.ppar + tb + tid);
             S.pp[tid] = make_double2(pq.x, pq.y); S.rsc[tid] = make_double2(pq.z, pq.w);
         }
-        for (int hh = tid; hh < RS_SLOTS; hh += AT_THREADS) { S.hkey[hh] = -1; S.hcnt[hh] = 0; }
-        stats_clear(S.acc);
+        for (int hh = tid; hh < RS_SLOTS; hh += AT_THREADS) { S.hkey[hh] = -1; S.hid[hh] = -1; S.hcnt[hh] = 0; }
+        if (tid == 0) S.nslots = 0;
         __syncthreads();
         // ---- chunks of whole scans whose observations fit the shared-memory budget (normally one) -----------------
         for (int c_lo = 0; c_lo < nsc;) {
@@ -294,13 +314,27 @@ k_assoc_tiles(const AssocParams p)
             int nr = 0;
             const size_t slot0 = ((size_t)(tile * RT_SLICES + (q >> 5)) * R.maxr) * 32 + (q & 31);
             // (the first half's run count is needed for the second half's row offset: count first, then write)
+            const bool halo_scan = halo_tile && q == 0;
             if (o < e) {
                 int bk = sbk[o];
-                for (int i = o + 1; i < e; ++i) { const int b2 = sbk[i]; nr += b2 != bk; bk = b2; }
+                if (bk >= 0 && !halo_scan) slot_insert(S, bk);
+                for (int i = o + 1; i < e; ++i) {
+                    const int b2 = sbk[i];
+                    if (b2 != bk) { ++nr; if (b2 >= 0 && !halo_scan) slot_insert(S, b2); }
+                    bk = b2;
+                }
                 ++nr;
             }
             const int nr_other = __shfl_xor_sync(FULLMASK, nr, 1);
             const int rtot = nr + nr_other;
+            __syncthreads();
+            // number the landmarks that entered the hash in this chunk
+            if (tid < RS_SLOTS && S.hkey[tid] != -1 && S.hid[tid] < 0) {
+                const int id = atomicAdd(&S.nslots, 1);
+                S.hid[tid] = id;
+                if (id < RS_NOSLOT) S.slot_label[id] = S.hkey[tid];
+            }
+            __syncthreads();
             if (o < e) {
                 // (the next observation is fetched before the current one is consumed)
                 int k = sub ? nr_other : 0;
@@ -321,7 +355,7 @@ k_assoc_tiles(const AssocParams p)
                         const float ex = fmaxf(mxx - cx, cx - mnx), ey = fmaxf(mxy - cy, cy - mny);
                         const float rho = sqrtf(fmaf(ex, ex, ey * ey)) * 1.0001f + 2e-5f;
                         const int rcode = min(__float2int_ru(rho * (float)RT_RHO_UNIT), RT_RHO_INF);
-                        const int slot = (bk >= 0 && !(halo_tile && q == 0)) ? slot_of(S, bk) : RS_NOSLOT;
+                        const int slot = (bk >= 0 && !halo_scan) ? slot_of(S, bk, n) : RS_NOSLOT;
                         if (k < R.maxr) {
                             R.rec_sb[slot0 + (size_t)k * 32] = make_double2(Sbx, Sby);
                             R.rec_meta[slot0 + (size_t)k * 32] = run_meta_pack(bk, slot, rcode, n);
@@ -338,12 +372,15 @@ k_assoc_tiles(const AssocParams p)
         }
         __syncthreads();
         // ---- tile header, then the slices through the same code as the steady state -------------------------------------------
-        if (tid == 0) R.tile_epoch[tile] = epoch;
-        for (int hh = tid; hh < RS_SLOTS; hh += AT_THREADS) R.tile_slots[(size_t)tile * RS_SLOTS + hh] = S.hkey[hh];
-        __syncthreads();     // the block's records are visible to its warps
-        if (warp < RT_SLICES) process_slice<false>(R, S.acc, tile * RT_SLICES + warp, tile, commit_all);
+        const int nslots = min(S.nslots, RS_NOSLOT);
+        if (tid == 0) { R.tile_epoch[tile] = epoch; R.tile_nslots[tile] = nslots; }
+        for (int hh = tid; hh < nslots; hh += AT_THREADS) R.tile_slots[(size_t)tile * RS_SLOTS + hh] = S.slot_label[hh];
+        __syncthreads();     // the block's records and slot table are visible to its warps
+        tile_stage(R, S.tile, tile, nslots);
         __syncthreads();
-        stats_flush(R, S.acc, tile);
+        if (warp < RT_SLICES) process_slice<false>(R, S.tile, tile * RT_SLICES + warp, tile, commit_all);
+        __syncthreads();
+        stats_flush(R, S.tile, tile, nslots);
         __syncthreads();
         if (tid < nsc) R.scan_dirty[tb + tid] = 0;
         if (tid == 0) R.tile_flag[tile] = 0;

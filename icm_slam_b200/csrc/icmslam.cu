@@ -23,6 +23,7 @@
 #include "pass0.cuh"
 
 #define MAX_CELLS (1 << 22)
+#define ASSOC_MAX_OBS 4096      // observations of one scan icmslam_associate accepts (a scan has at most B <= 1024 beams)
 
 struct icmslam_handle {
     icmslam_config cfg;
@@ -80,7 +81,7 @@ struct icmslam_handle {
     int n_tiles = 0, n_solve_tiles = 0;        // record tiles (RT_TILE scans) / solve tiles (ST_OWN poses)
     double2* d_rec_sb = nullptr; int2* d_rec_meta = nullptr; int64_t rec_slots = 0; int rec_maxr = 1;   // run records (runs.cuh)
     unsigned short* d_nruns = nullptr;         // runs of each scan
-    int* d_tile_slots = nullptr;               // RS_SLOTS labels per record tile
+    int* d_tile_slots = nullptr; int* d_tile_nslots = nullptr;   // RS_SLOTS labels per record tile, slots in use
     int *d_tile_epoch = nullptr, *d_tile_flag = nullptr, *d_dirty_list = nullptr, *d_scan_dirty = nullptr;
     double* d_dyn = nullptr;                   // 6 landmark moments per pose
     TailState* d_ts = nullptr;
@@ -90,12 +91,14 @@ struct icmslam_handle {
     LmRec* d_lmrec = nullptr;           // landmarks of the current map by label (position + hint radius)
     int* d_remap = nullptr;             // label of the last sweep -> label in the current map
     int* d_klab = nullptr;              // raw label of each kept landmark (fast tail)
+    double* d_aobs = nullptr; int* d_ac = nullptr;   // icmslam_associate: one scan's observations (2 x ASSOC_MAX_OBS) and labels
     double* d_nnd2 = nullptr;
     double thr1sq = 0.0;
     struct GraphSlot { cudaGraphExec_t exec = nullptr; const double* src = nullptr; const double* map_in = nullptr; double x0[3] = {0, 0, 0}; double tol = 0; int maxit = 0; };
     GraphSlot graphs[4];
     int use_graph = 1, graph_launches = 0;
     int runs_occ = 8;            // resident 128-thread blocks per SM k_runs is compiled for (8: 64 registers; ICMSLAM_RUNS_OCC=6: 80)
+    int solve_occ = 5;           // resident 128-thread blocks per SM k_solve_tile is compiled for (ICMSLAM_SOLVE_OCC=4|5|6)
     int use_runs = 1;            // ICMSLAM_RUNS=0: every tile goes through the association kernel every sweep (no steady-state shortcut)
     int assoc_blocks = 0;        // grid of the (persistent) association kernel
     double2* d_bxy = nullptr;    // interleaved (bx, by) records for the TMA staging
@@ -177,7 +180,7 @@ static void free_dataset(icmslam_handle* h)
     DFREE(h->d_nfar); DFREE(h->d_flag); DFREE(h->d_prefix); DFREE(h->d_x);
     DFREE(h->d_inc); DFREE(h->d_bm); DFREE(h->d_dyn); DFREE(h->d_x2); DFREE(h->d_far_list); DFREE(h->d_blk_prefix); DFREE(h->d_bxy);
     DFREE(h->d_ppar[0]); DFREE(h->d_ppar[1]); DFREE(h->d_farbits); DFREE(h->d_rec_sb); DFREE(h->d_rec_meta); DFREE(h->d_nruns); DFREE(h->d_tile_epoch);
-    DFREE(h->d_tile_flag); DFREE(h->d_dirty_list); DFREE(h->d_scan_dirty); DFREE(h->d_tile_slots);
+    DFREE(h->d_tile_flag); DFREE(h->d_dirty_list); DFREE(h->d_scan_dirty); DFREE(h->d_tile_slots); DFREE(h->d_tile_nslots);
     h->ppar_of = nullptr;
     drop_graphs(h);
     h->grid_map = nullptr;
@@ -202,7 +205,7 @@ extern "C" int icmslam_destroy(icmslam_handle* h)
     DFREE(h->d_st); DFREE(h->d_cub); DFREE(h->d_sort_ws);
     DFREE(h->d_exch); DFREE(h->d_fg_cnt); DFREE(h->d_fg_start); DFREE(h->d_fg_idx);
     DFREE(h->d_fg_pts); DFREE(h->d_fg_geom); DFREE(h->d_bb); DFREE(h->d_ts); DFREE(h->d_seg_rec);
-    DFREE(h->d_lmrec); DFREE(h->d_remap); DFREE(h->d_nnd2); DFREE(h->d_klab);
+    DFREE(h->d_lmrec); DFREE(h->d_remap); DFREE(h->d_nnd2); DFREE(h->d_klab); DFREE(h->d_aobs); DFREE(h->d_ac);
     if (h->h_st) cudaFreeHost(h->h_st);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -312,12 +315,15 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     if (e == cudaSuccess) e = dalloc(&h->d_lmrec, L);
     if (e == cudaSuccess) e = dalloc(&h->d_remap, L);
     if (e == cudaSuccess) e = dalloc(&h->d_klab, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_aobs, (size_t)2 * ASSOC_MAX_OBS);
+    if (e == cudaSuccess) e = dalloc(&h->d_ac, (size_t)ASSOC_MAX_OBS);
     if (e == cudaSuccess) e = dalloc(&h->d_nnd2, L);
     if (e == cudaSuccess) e = cudaMemset(h->d_lmrec, 0, L * sizeof(LmRec));
     { const double t1 = cfg->dist_thr * (1.0 + 9.5367431640625e-07); h->thr1sq = t1 * t1; }
     if (e == cudaSuccess) e = cudaMemset(h->d_ts, 0, sizeof(TailState));
     { const char* eg = getenv("ICMSLAM_GRAPH"); if (eg) h->use_graph = atoi(eg); }
     { const char* er = getenv("ICMSLAM_RUNS"); if (er) h->use_runs = atoi(er) != 0; }
+    { const char* er = getenv("ICMSLAM_SOLVE_OCC"); if (er && (atoi(er) == 4 || atoi(er) == 6)) h->solve_occ = atoi(er); }
     { const char* er = getenv("ICMSLAM_RUNS_OCC"); if (er && atoi(er) == 6) h->runs_occ = 6; }
     if (e == cudaSuccess) {
         int sms = 0;
@@ -482,7 +488,7 @@ extern "C" int icmslam_extract(icmslam_handle* h)
     CK(cudaGetLastError());
     DFREE(h->d_bm); DFREE(h->d_dyn);
     DFREE(h->d_ppar[0]); DFREE(h->d_ppar[1]); DFREE(h->d_farbits); DFREE(h->d_rec_sb); DFREE(h->d_rec_meta); DFREE(h->d_nruns); DFREE(h->d_tile_epoch);
-    DFREE(h->d_tile_flag); DFREE(h->d_dirty_list); DFREE(h->d_scan_dirty); DFREE(h->d_tile_slots);
+    DFREE(h->d_tile_flag); DFREE(h->d_dirty_list); DFREE(h->d_scan_dirty); DFREE(h->d_tile_slots); DFREE(h->d_tile_nslots);
     {   // run records and their bookkeeping (runs.cuh): slice s (32 scans) owns slots [s * maxr * 32, (s + 1) * maxr * 32)
         const size_t nt = (size_t)nblk(T + 1, RT_TILE) + 2;      // (+1 scan: a segment's tiling may start one scan earlier)
         h->rec_maxr = h->max_per_scan > 0 ? h->max_per_scan : 1;
@@ -491,7 +497,8 @@ extern "C" int icmslam_extract(icmslam_handle* h)
         CK(dalloc(&h->d_nruns, nt * RT_TILE));
         CK(dalloc(&h->d_ppar[0], (size_t)T)); CK(dalloc(&h->d_ppar[1], (size_t)T));
         CK(dalloc(&h->d_farbits, nt * 4)); CK(dalloc(&h->d_tile_epoch, nt));
-        CK(dalloc(&h->d_tile_flag, nt)); CK(dalloc(&h->d_dirty_list, nt)); CK(dalloc(&h->d_tile_slots, nt * RS_SLOTS));
+        CK(dalloc(&h->d_tile_flag, nt)); CK(dalloc(&h->d_dirty_list, nt)); CK(dalloc(&h->d_tile_slots, nt * RS_SLOTS)); CK(dalloc(&h->d_tile_nslots, nt));
+        CK(cudaMemsetAsync(h->d_tile_nslots, 0, nt * sizeof(int), h->stream));
         CK(dalloc(&h->d_scan_dirty, nt * RT_TILE));
         CK(cudaMemsetAsync(h->d_nruns, 0, nt * RT_TILE * sizeof(unsigned short), h->stream));
         CK(cudaMemsetAsync(h->d_tile_epoch, 0xff, nt * sizeof(int), h->stream));       // epoch -1: no tile holds records
@@ -610,6 +617,17 @@ extern "C" int icmslam_get_counts(icmslam_handle* h, double* out, int32_t n, int
     (void)memspace;
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaMemcpyAsync(out, h->d_counts, (size_t)n * sizeof(double), cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return ICMSLAM_OK;
+}
+
+extern "C" int icmslam_set_counts(icmslam_handle* h, const double* in, int32_t n, int32_t memspace)
+{
+    if (!h || n < 0 || n > h->Lcap || (n > 0 && !in)) return ICMSLAM_ERR_INVALID;
+    (void)memspace;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemsetAsync(h->d_counts, 0, (size_t)h->Lcap * sizeof(double), h->stream));      // Mapa.clear_obs (ICM_SLAM.py:119-126) + the given prefix
+    if (n > 0) CK(cudaMemcpyAsync(h->d_counts, in, (size_t)n * sizeof(double), cudaMemcpyDefault, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return ICMSLAM_OK;
 }
@@ -784,7 +802,7 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
     RunParams R;
     R.t_start = t_start; R.t_hi = h->seg_hi; R.halo_t = h->seg_first ? -1 : t_start; R.maxr = h->rec_maxr; R.ppar = pp_in; R.lmrec = h->d_lmrec;
     R.rec_sb = h->d_rec_sb; R.rec_meta = h->d_rec_meta; R.nruns = h->d_nruns; R.tile_epoch = h->d_tile_epoch; R.dyn = h->d_dyn;
-    R.fsum_x = h->d_fsum_x; R.fsum_y = h->d_fsum_y; R.cnt = h->d_cnt; R.fix_scale = h->fix_scale; R.tile_slots = h->d_tile_slots;
+    R.fsum_x = h->d_fsum_x; R.fsum_y = h->d_fsum_y; R.cnt = h->d_cnt; R.fix_scale = h->fix_scale; R.tile_slots = h->d_tile_slots; R.tile_nslots = h->d_tile_nslots;
     R.far_list = h->d_far_list; R.ts = h->d_ts; R.farbits = h->d_farbits;
     R.scan_dirty = h->d_scan_dirty; R.tile_flag = h->d_tile_flag; R.dirty_list = h->d_dirty_list;
     R.geom = h->d_fg_geom; R.cell_start = h->d_fg_start; R.gpts = h->d_fg_pts; R.dist_thr = h->dcfg.dist_thr;
@@ -827,7 +845,9 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
             CK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
             ss = h->side_stream;
         }
-        k_solve_tile<<<h->n_solve_tiles, ST_THREADS, 0, ss>>>(P);
+        if (h->solve_occ == 4) k_solve_tile<4><<<h->n_solve_tiles, ST_THREADS, 0, ss>>>(P);
+        else if (h->solve_occ == 6) k_solve_tile<6><<<h->n_solve_tiles, ST_THREADS, 0, ss>>>(P);
+        else k_solve_tile<5><<<h->n_solve_tiles, ST_THREADS, 0, ss>>>(P);
         CK(cudaGetLastError());
         if (fork) {
             CK(cudaEventRecord(h->ev_join, ss));
@@ -1632,23 +1652,24 @@ extern "C" int icmslam_associate(icmslam_handle* h, const double* map_ref, int32
     // Branch B: device copies of the reference map (d_tmp_a), the observations (d_kx / d_ky as scratch would clash with the
     // filter: d_ox / d_oy) and the map under construction (d_tmp_b)
     const int Ls = lact < L_ref ? lact : L_ref;
-    if (n_obs > L) return ICMSLAM_ERR_UNSUPPORTED;                   // (scratch sized by the label capacity)
+    if (n_obs > ASSOC_MAX_OBS) return ICMSLAM_ERR_UNSUPPORTED;
     if (Ls > 0) CK(cudaMemcpy2DAsync(h->d_tmp_a, (size_t)L * 8, map_ref, (size_t)ld_ref * 8, (size_t)Ls * 8, 2, cudaMemcpyDefault, s));
-    CK(cudaMemcpyAsync(h->d_ox, obs_x, (size_t)n_obs * 8, cudaMemcpyDefault, s));
-    CK(cudaMemcpyAsync(h->d_oy, obs_y, (size_t)n_obs * 8, cudaMemcpyDefault, s));
+    double *aox = h->d_aobs, *aoy = h->d_aobs + ASSOC_MAX_OBS;
+    CK(cudaMemcpyAsync(aox, obs_x, (size_t)n_obs * 8, cudaMemcpyDefault, s));
+    CK(cudaMemcpyAsync(aoy, obs_y, (size_t)n_obs * 8, cudaMemcpyDefault, s));
     CK(cudaMemcpy2DAsync(h->d_tmp_b, (size_t)L * 8, mapa, (size_t)ld_mapa * 8, (size_t)cap * 8, 2, cudaMemcpyDefault, s));
     k_set_raw_l<<<1, 1, 0, s>>>(h->d_st, lact);                      // (clears the status word)
     CK(cudaGetLastError());
-    k_actualizar_nearest<<<n_obs, 128, 0, s>>>(h->d_tmp_a, h->d_tmp_a + L, Ls, h->d_ox, h->d_oy, h->dcfg.dist_thr, h->d_lab);
+    k_actualizar_nearest<<<n_obs, 128, 0, s>>>(h->d_tmp_a, h->d_tmp_a + L, Ls, aox, aoy, h->dcfg.dist_thr, h->d_ac);
     CK(cudaGetLastError());
-    k_actualizar_update<<<1, 256, 0, s>>>(h->d_st, L, n_obs, h->d_ox, h->d_oy, h->d_lab, h->d_tmp_b, cap, L, h->d_counts);
+    k_actualizar_update<<<1, 256, 0, s>>>(h->d_st, L, n_obs, aox, aoy, h->d_ac, h->d_tmp_b, cap, L, h->d_counts);
     CK(cudaGetLastError());
     h->n_launch += 3;
     rc = sync_state(h);
     if (rc) return rc;
     if (h->h_st->status & ST_LABEL_CAP) return ICMSLAM_ERR_LABEL_CAP;
     CK(cudaMemcpy2DAsync(mapa, (size_t)ld_mapa * 8, h->d_tmp_b, (size_t)L * 8, (size_t)cap * 8, 2, cudaMemcpyDefault, s));
-    CK(cudaMemcpyAsync(c, h->d_lab, (size_t)n_obs * sizeof(int), cudaMemcpyDefault, s));
+    CK(cudaMemcpyAsync(c, h->d_ac, (size_t)n_obs * sizeof(int), cudaMemcpyDefault, s));
     CK(cudaStreamSynchronize(s));
     return ICMSLAM_OK;
 }

@@ -22,9 +22,10 @@
 // kept beams of a scan.  A warp walks one slice, step k = run k of each of its 32 scans: the loads of a step are contiguous,
 // slots past a scan's last run are never written nor read, and every lane accumulates ITS scan's moments in registers in run
 // order -- no cross-lane reduction, and a result that depends on nothing but the scan (bit-identical for any tiling or GPU
-// count).  The fixed-point statistics of a run go to the tile's table in shared memory -- the record names the landmark's SLOT
-// in that table (assigned when the records were built), the 64-bit sums are two carry-free 32-bit limbs, so the adds are plain
-// non-returning shared-memory atomics -- and the block adds one int64 pair + count per (tile, landmark) to the global
+// count).  The record names its landmark by the SLOT it has in the tile's table (assigned when the records were built): the
+// block stages the landmark records of its slots in shared memory once, so a step's landmark look-up is a shared-memory read,
+// and the fixed-point statistics of a run go to the slot's sums there -- 64-bit sums as two carry-free 32-bit limbs, so the adds
+// are plain non-returning shared-memory atomics.  The block then adds one int64 pair + count per (tile, landmark) to the global
 // statistics: integer addition is associative, so the landmark update is bit-reproducible as well.
 #pragma once
 #include "common.cuh"
@@ -43,7 +44,15 @@
 #define RS_MAX_ADDS 500     // runs per slot and tile (enforced when the records are built): with every one of them added and
                             // taken back once, a low limb stays below 2^32
 #define RS_LO_BITS 22       // a sum is kept as (low 22 bits: unsigned limb, the rest: signed limb)
-#define RS_VMAX (1ll << 42) // |value| of one run beyond which it goes straight to the global sums (high limb: < 2^20 * 1000)
+#define RS_MAX_BEAMS 255    // beams of a run that may use a slot: |S| <= n dist_thr, so its fixed-point value stays below 2^42 and
+                            // the high limb below 2^20 * 1000 (longer runs go straight to the global sums)
+
+// what a block keeps in shared memory for its tile: the statistics table and the landmark records of the table's slots
+struct TileSmem {
+    unsigned acc[RS_SLOTS][5];     // per slot: sum x (low, high limb), sum y (low, high limb), beams
+    double2 lxy[RS_SLOTS];         // the slot's landmark
+    double lr[RS_SLOTS];           // ... and its proven radius
+};
 
 // packed half of a run record: x = label (24 bits) | slot << 24, y = rho code (16 bits) | beams << 16
 __device__ __forceinline__ int2 run_meta_pack(int label, int slot, int rho_code, int n)
@@ -64,7 +73,7 @@ struct RunParams {
     double* dyn;                          // 6 doubles per pose: (Yx, Mxx, Mxy, Yy, Myx, Myy)
     long long* fsum_x; long long* fsum_y; int* cnt;   // per previous-map landmark statistics (fixed point)
     double fix_scale;
-    int* tile_slots;                      // RS_SLOTS labels per tile: which landmark each slot of its statistics table stands for
+    int* tile_slots; int* tile_nslots;    // RS_SLOTS labels per tile: which landmark each slot of its statistics table stands for; slots in use
     FarRec* far_list; TailState* ts; unsigned* farbits;   // scans with far observations (each creates one label)
     int* scan_dirty; int* tile_flag; int* dirty_list;     // steady state: what failed validation (tile_flag: 1 some scans, 2 all)
     const FGeom* geom; const int* cell_start; const double2* gpts;   // the landmark grid (fastgrid.cuh), for the far runs
@@ -94,16 +103,15 @@ __device__ __forceinline__ bool run_provably_far(const RunParams& p, double wx, 
 
 // The run's statistics S = sum_i (w_i - y) in fixed point -> the tile's table in shared memory (sign = -1 takes a
 // contribution back: the limbs are linear).
-__device__ __forceinline__ void run_statistics(const RunParams& p, unsigned (*acc)[5], int label, int slot, double Sx, double Sy, int n, int sign)
+__device__ __forceinline__ void run_statistics(const RunParams& p, TileSmem& S, int label, int slot, double Sx, double Sy, int n, int sign)
 {
     long long vx = __double2ll_rn(Sx * p.fix_scale), vy = __double2ll_rn(Sy * p.fix_scale);
-    const long long ax = vx < 0 ? -vx : vx, ay = vy < 0 ? -vy : vy;
     if (sign < 0) { vx = -vx; vy = -vy; n = -n; }
-    if (slot != RS_NOSLOT && ax < RS_VMAX && ay < RS_VMAX) {
+    if (slot != RS_NOSLOT) {
         const unsigned m = (1u << RS_LO_BITS) - 1u;
-        atomicAdd(&acc[slot][0], (unsigned)vx & m); atomicAdd((int*)&acc[slot][1], (int)(vx >> RS_LO_BITS));
-        atomicAdd(&acc[slot][2], (unsigned)vy & m); atomicAdd((int*)&acc[slot][3], (int)(vy >> RS_LO_BITS));
-        atomicAdd((int*)&acc[slot][4], n);
+        atomicAdd(&S.acc[slot][0], (unsigned)vx & m); atomicAdd((int*)&S.acc[slot][1], (int)(vx >> RS_LO_BITS));
+        atomicAdd(&S.acc[slot][2], (unsigned)vy & m); atomicAdd((int*)&S.acc[slot][3], (int)(vy >> RS_LO_BITS));
+        atomicAdd((int*)&S.acc[slot][4], n);
     } else {
         atomicAdd((unsigned long long*)(p.fsum_x + label), (unsigned long long)vx);
         atomicAdd((unsigned long long*)(p.fsum_y + label), (unsigned long long)vy);
@@ -112,12 +120,12 @@ __device__ __forceinline__ void run_statistics(const RunParams& p, unsigned (*ac
 }
 
 // the tile's table -> the global statistics: one int64 pair + count per landmark the tile saw (call between block barriers)
-__device__ __forceinline__ void stats_flush(const RunParams& p, unsigned (*acc)[5], int tile)
+__device__ __forceinline__ void stats_flush(const RunParams& p, TileSmem& S, int tile, int nslots)
 {
-    for (int h = threadIdx.x; h < RS_SLOTS; h += blockDim.x) {
-        const int c = (int)acc[h][4];
-        const long long vx = ((long long)(int)acc[h][1] << RS_LO_BITS) + (long long)acc[h][0];
-        const long long vy = ((long long)(int)acc[h][3] << RS_LO_BITS) + (long long)acc[h][2];
+    for (int h = threadIdx.x; h < nslots; h += blockDim.x) {
+        const int c = (int)S.acc[h][4];
+        const long long vx = ((long long)(int)S.acc[h][1] << RS_LO_BITS) + (long long)S.acc[h][0];
+        const long long vy = ((long long)(int)S.acc[h][3] << RS_LO_BITS) + (long long)S.acc[h][2];
         if (c != 0 || vx != 0 || vy != 0) {
             const int label = p.tile_slots[(size_t)tile * RS_SLOTS + h];
             atomicAdd((unsigned long long*)(p.fsum_x + label), (unsigned long long)vx);
@@ -127,9 +135,17 @@ __device__ __forceinline__ void stats_flush(const RunParams& p, unsigned (*acc)[
     }
 }
 
-__device__ __forceinline__ void stats_clear(unsigned (*acc)[5])
+// clears the table and stages the landmark records of the tile's slots (call before a block barrier)
+__device__ __forceinline__ void tile_stage(const RunParams& p, TileSmem& S, int tile, int nslots)
 {
-    for (int h = threadIdx.x; h < RS_SLOTS * 5; h += blockDim.x) (&acc[0][0])[h] = 0u;
+    for (int h = threadIdx.x; h < nslots; h += blockDim.x) {
+        const int label = p.tile_slots[(size_t)tile * RS_SLOTS + h];
+        const double2* lp = reinterpret_cast<const double2*>(p.lmrec + label);
+        S.lxy[h] = __ldg(lp);
+        S.lr[h] = __ldg(lp + 1).y;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) S.acc[h][k] = 0u;
+    }
 }
 
 // everything one run contributes, from its record and the pose / landmark it names
@@ -140,18 +156,22 @@ struct RunEval {
     double r;               // the landmark's proven radius
 };
 
-__device__ __forceinline__ RunEval run_eval(const RunParams& p, const double2 sb, int label, bool matched, double nd, const double4 pp)
+__device__ __forceinline__ RunEval run_eval(const RunParams& p, const TileSmem& S, const double2 sb, int label, int slot, bool matched, double nd,
+                                            const double4 pp)
 {
     RunEval e;
-    double2 lm = make_double2(0.0, 0.0), lr = make_double2(0.0, 0.0);
+    double2 lm = make_double2(0.0, 0.0);
+    e.r = 0.0;
     if (matched) {
-        const double2* lp = reinterpret_cast<const double2*>(p.lmrec + label);
-        lm = __ldg(lp); lr = __ldg(lp + 1);
+        if (slot != RS_NOSLOT) { lm = S.lxy[slot]; e.r = S.lr[slot]; }       // (staged with the tile)
+        else {
+            const double2* lp = reinterpret_cast<const double2*>(p.lmrec + label);
+            lm = __ldg(lp); e.r = __ldg(lp + 1).y;
+        }
     }
     e.rwx = fma(pp.w, sb.x, -pp.z * sb.y); e.rwy = fma(pp.z, sb.x, pp.w * sb.y);
     e.yx = lm.x - pp.x; e.yy = lm.y - pp.y;
     e.Sx = e.rwx - nd * e.yx; e.Sy = e.rwy - nd * e.yy;
-    e.r = lr.y;
     return e;
 }
 
@@ -160,7 +180,7 @@ __device__ __forceinline__ RunEval run_eval(const RunParams& p, const double2 sb
 // association kernel has just written the records): no certification; only the scans with commit_all or a dirty flag are
 // committed.
 template <bool STEADY>
-__device__ __forceinline__ bool process_slice(const RunParams& p, unsigned (*acc)[5], int slice, int tile, bool commit_all)
+__device__ __forceinline__ bool process_slice(const RunParams& p, TileSmem& S, int slice, int tile, bool commit_all)
 {
     const int lane = threadIdx.x & 31;
     const int t = p.t_start + slice * 32 + lane;
@@ -194,7 +214,7 @@ __device__ __forceinline__ bool process_slice(const RunParams& p, unsigned (*acc
             const int label = (int)lab24, slot = (int)((unsigned)mt_c.x >> 24);
             const int rcode = (int)((unsigned)mt_c.y & 0xffffu), n = (int)((unsigned)mt_c.y >> 16);
             const double nd = (double)n;
-            const RunEval e = run_eval(p, sb_c, label, matched, nd, pp);
+            const RunEval e = run_eval(p, S, sb_c, label, slot, matched, nd, pp);
             if (STEADY) {
                 const double rho = (double)rcode * (1.0 / RT_RHO_UNIT);
                 if (rcode >= RT_RHO_INF) ok = false;
@@ -206,7 +226,7 @@ __device__ __forceinline__ bool process_slice(const RunParams& p, unsigned (*acc
                 if (matched) {
                     m0 = fma(nd, e.yx, m0); m1 = fma(e.yx, sb_c.x, m1); m2 = fma(e.yx, sb_c.y, m2);
                     m3 = fma(nd, e.yy, m3); m4 = fma(e.yy, sb_c.x, m4); m5 = fma(e.yy, sb_c.y, m5);
-                    if (!halo) run_statistics(p, acc, label, slot, e.Sx, e.Sy, n, 1);
+                    if (!halo) run_statistics(p, S, label, slot, e.Sx, e.Sy, n, 1);
                 } else {      // far run: statistics of the scan's new label (ICM_SLAM.py:174-194)
                     nfar += nd; fsx += fma(nd, pp.x, e.rwx); fsy += fma(nd, pp.y, e.rwy); FBx += sb_c.x; FBy += sb_c.y;
                 }
@@ -222,8 +242,9 @@ __device__ __forceinline__ bool process_slice(const RunParams& p, unsigned (*acc
                 const unsigned lab24 = (unsigned)m2_.x & 0xffffffu;
                 if (lab24 == RUN_FAR) continue;
                 const int n = (int)((unsigned)m2_.y >> 16);
-                const RunEval e = run_eval(p, s2, (int)lab24, true, (double)n, pp);
-                run_statistics(p, acc, (int)lab24, (int)((unsigned)m2_.x >> 24), e.Sx, e.Sy, n, -1);
+                const int slot = (int)((unsigned)m2_.x >> 24);
+                const RunEval e = run_eval(p, S, s2, (int)lab24, slot, true, (double)n, pp);
+                run_statistics(p, S, (int)lab24, slot, e.Sx, e.Sy, n, -1);
             }
         }
         p.scan_dirty[t] = 1;
@@ -258,17 +279,18 @@ template <int MINB>      // resident blocks per SM the kernel is compiled for
 __global__ void __launch_bounds__(RUNS_THREADS, MINB)
 k_runs(const RunParams p)
 {
-    __shared__ unsigned acc[RS_SLOTS][5];
+    __shared__ TileSmem S;
     const int tile = blockIdx.x;
+    const int nslots = p.tile_nslots[tile];
     if (p.tile_epoch[tile] != p.ts->epoch) {      // no records for this label numbering: the whole tile goes to the association kernel
         if (threadIdx.x == 0) { p.tile_flag[tile] = 2; p.dirty_list[atomicAdd(&p.ts->n_dirty, 1)] = tile; }
         return;
     }
-    stats_clear(acc);
+    tile_stage(p, S, tile, nslots);
     __syncthreads();
-    process_slice<true>(p, acc, tile * RT_SLICES + (threadIdx.x >> 5), tile, true);
+    process_slice<true>(p, S, tile * RT_SLICES + (threadIdx.x >> 5), tile, true);
     __syncthreads();
-    stats_flush(p, acc, tile);
+    stats_flush(p, S, tile, nslots);
 }
 
 // every tile to the association kernel (ICMSLAM_RUNS=0: no steady-state shortcut)

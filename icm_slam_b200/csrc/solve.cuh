@@ -228,7 +228,8 @@ __device__ __forceinline__ SlotMom solve_slot_load(const SolveParams& p, int tb,
     return s;
 }
 
-__global__ void __launch_bounds__(ST_THREADS, 4)
+template <int MINB>      // resident blocks per SM the kernel is compiled for (4: 117 registers, 5: 96, 6: 80)
+__global__ void __launch_bounds__(ST_THREADS, MINB)
 k_solve_tile(const SolveParams p)
 {
     __shared__ SolveSmem S;

@@ -136,6 +136,12 @@ class Engine:
             check(self.lib.icmslam_get_counts(self._h, _ptr(out)[0], n, HOST), self._h)
         return out
 
+    def set_counts(self, counts=None):
+        """cant_obs_i <- counts (rest zero); None: Mapa.clear_obs."""
+        c = np.zeros(0) if counts is None else np.ascontiguousarray(counts, dtype=np.float64)
+        n = min(int(c.shape[0]), self.L)
+        check(self.lib.icmslam_set_counts(self._h, _ptr(c)[0] if n else None, n, HOST), self._h)
+
     # -- the sweep ------------------------------------------------------------------------------
     def sweep(self, map_in, x, x0, map_out=None, schedule="redblack", solver="newton", view="prev", newton_tol=0.0,
               newton_maxit=0, fused=True, want_L=True, stats=False):

@@ -126,8 +126,8 @@ def calc_cambio(y, mapa_viejo, config=None):
 
 
 class Mapa:
-    """ICM_SLAM.py:104-265.  Holds `landmarks_actuales` and `cant_obs_i`; when attached to a solver
-    the state lives in the solver's device handle and these attributes are views of it."""
+    """ICM_SLAM.py:104-265.  `landmarks_actuales` and `cant_obs_i` live in a device handle: the solver's once the Mapa is
+    attached to one (ICM_SLAM.load_data / mapa_obj), else a private handle created on first use."""
 
     def __init__(self, config):
         self.L = config.L
@@ -135,59 +135,69 @@ class Mapa:
         self.dist_thr = config.dist_thr
         self._config = config
         self._engine = None
+        self._own = None
         self._lact = 0
-        self.clear_obs()
+
+    def _eng(self):
+        if self._engine is not None:
+            return self._engine
+        if self._own is None:
+            self._own = Engine(self._config, device=int(getattr(self._config, "device", 0)))
+            self._own.landmarks_actuales = self._lact
+        return self._own
 
     def _attach(self, engine):
+        if self._own is not None:                  # carry the state over
+            self._lact = self._own.landmarks_actuales
+            cant = self._own.counts(self.L)
+            self._own.close()
+            self._own = None
+            engine.set_counts(cant)
         self._engine = engine
         engine.landmarks_actuales = self._lact
 
     @property
     def landmarks_actuales(self):
-        return self._engine.landmarks_actuales if self._engine is not None else self._lact
+        if self._engine is None and self._own is None:
+            return self._lact
+        return self._eng().landmarks_actuales
 
     @landmarks_actuales.setter
     def landmarks_actuales(self, v):
         self._lact = int(v)
-        if self._engine is not None:
-            self._engine.landmarks_actuales = int(v)
+        if self._engine is not None or self._own is not None:
+            self._eng().landmarks_actuales = int(v)
 
     @property
     def cant_obs_i(self):
-        if self._engine is not None:
-            return self._engine.counts()
-        return self._cant
+        if self._engine is None and self._own is None:
+            return np.zeros(self.L)
+        return self._eng().counts(min(self.L, self._eng().L))
 
     def clear_obs(self):
-        self._cant = np.zeros(self.L)
+        """ICM_SLAM.py:119-126."""
+        if self._engine is not None or self._own is not None:
+            self._eng().set_counts(None)
 
     def actualizar(self, mapa, mapa_referencia, obs):
         """ICM_SLAM.py:128-201 for one scan: nearest landmark of `mapa_referencia` (its first landmarks_actuales columns) for
         every row of `obs` (n, 2), gate dist_thr, one new label for the scan's far observations, running means written into
         `mapa` (2 x L, in place), counts into cant_obs_i.  Returns (mapa, c) like the reference.  The very first call of a
         fresh Mapa (landmarks_actuales == 0) clusters the scan as scipy's fcluster does (:160-165)."""
-        e = self._engine if self._engine is not None else _scratch_engine(self._config)
-        if self._engine is None:       # a detached Mapa keeps its state on the host: mirror it into the scratch engine
-            e.landmarks_actuales = self._lact
-            e.set_counts(self._cant)
         if not (isinstance(mapa, np.ndarray) and mapa.dtype == np.float64 and mapa.ndim == 2 and mapa.strides[1] == 8):
             raise TypeError("mapa must be a (2, L) float64 array (it is updated in place, like the reference's)")
-        c = e.associate(mapa, mapa_referencia, obs)
-        if self._engine is None:
-            self._lact = e.landmarks_actuales
-            self._cant = e.counts(self.L)
+        c = self._eng().associate(mapa, mapa_referencia, obs)
         return mapa, c
 
     def filtrar(self, mapa, cant_obs_i=None):
-        """ICM_SLAM.py:204-265 on a 2 x L map; counts default to the attached solver's last sweep.
+        """ICM_SLAM.py:204-265 on a 2 x L map; counts default to the handle's (the last sweep's / actualizar's).
         Returns the 2 x L buffer (caller slices [:, :landmarks_actuales]) like the reference."""
-        e = self._engine if self._engine is not None else _scratch_engine(self._config)
+        e = self._eng()
         mapa = np.ascontiguousarray(mapa, dtype=np.float64)
         cnt = np.ascontiguousarray(self.cant_obs_i if cant_obs_i is None else cant_obs_i, dtype=np.float64)
         n = min(mapa.shape[1], cnt.shape[0], self.landmarks_actuales if cant_obs_i is None else cnt.shape[0])
         out, cout, Lout = e.filter_map(mapa[:, :n], cnt[:n])
         self._lact = Lout
-        self._cant = cout
         return out
 
 

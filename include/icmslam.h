@@ -121,6 +121,8 @@ int icmslam_get_extraction(icmslam_handle* h, int32_t* off, int32_t* beam, doubl
 int icmslam_set_landmarks_actuales(icmslam_handle* h, int32_t lact);
 int icmslam_get_landmarks_actuales(const icmslam_handle* h, int32_t* lact);
 int icmslam_get_counts(icmslam_handle* h, double* cant_obs_i, int32_t n, int32_t memspace);
+/* cant_obs_i[:n] = counts, the rest zero (n = 0: Mapa.clear_obs, ICM_SLAM.py:119-126) */
+int icmslam_set_counts(icmslam_handle* h, const double* cant_obs_i, int32_t n, int32_t memspace);
 
 /* -- one ICM sweep = ICM_ROS.iterations_process_offline(mapa_viejo, x) (sensors.py:125-168).
  * map_in: 2 x L_in (ld_map_in).  x: 3 x T (ld_x), updated IN PLACE like the reference.

@@ -699,3 +699,75 @@ def test_sweep_variants_agree(env):
     for k, (ra, rb) in enumerate(zip(a, b)):
         assert np.array_equal(ra[2], rb[2]), (env, k)
         assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1]), (env, k)
+
+
+# ---- the per-scan step on the reference's surface: Mapa.actualizar (ICM_SLAM.py:128-201) through icmslam_associate ----------
+def test_mapa_actualizar_vs_reference_units():
+    from icm_slam_b200.icm import Mapa
+    u = golden("units.npz")
+    cfg = _cfg(L=60)
+    for q in range(int(u["ac_nseq"])):
+        ref = u[f"ac{q}_ref"]
+        m = Mapa(cfg)
+        m.landmarks_actuales = ref.shape[1]
+        m.clear_obs()
+        y = np.zeros((2, 60))
+        for r in range(int(u[f"ac{q}_ncall"])):
+            y2, c = m.actualizar(y, ref, u[f"ac{q}_{r}_obs"])
+            assert y2 is y and c.dtype == np.int64
+            assert np.array_equal(c, u[f"ac{q}_{r}_c"]), (q, r)
+            assert m.landmarks_actuales == int(u[f"ac{q}_{r}_Lact"])
+            assert np.array_equal(m.cant_obs_i, u[f"ac{q}_{r}_cant"])
+            assert np.max(np.abs(y - u[f"ac{q}_{r}_y"])) <= 1e-13
+
+
+def test_mapa_actualizar_first_scan_clusters_like_scipy():
+    """landmarks_actuales == 0: Branch A (fcluster of the first scan, ICM_SLAM.py:160-165), then Branch B against the map it made,
+    then the label cap (IndexError, :191)."""
+    from icm_slam_b200.icm import Mapa
+    g = golden("c1_ref.npz")
+    z, odo, u_ = c1_inputs()
+    from oracle import oracle as orc
+    ocfg = orc.make_cfg(**CONFIG_ROS)
+    zz, _ = orc.filtrar_z(orc.precondition(z[:, 0:1], ocfg.radio, ocfg.rango_laser_max)[:, 0], ocfg)
+    wx, wy = orc.tras_rot(odo[:, 0], zz[:, 2], zz[:, 3])
+    obs = np.stack([wx, wy], axis=1)
+    m = Mapa(_cfg())
+    y = np.zeros((2, 1000))
+    y, c = m.actualizar(y, y, obs)
+    k = int(c.max()) + 1
+    assert m.landmarks_actuales == k and np.array_equal(c, g["p0_labels"][: len(c)])
+    for i in range(k):
+        assert np.max(np.abs(y[:, i] - obs[c == i].mean(axis=0))) <= 1e-13 and m.cant_obs_i[i] == (c == i).sum()
+    y, c2 = m.actualizar(y, y, obs + 0.01)
+    assert np.array_equal(c2, c)
+    small = Mapa(_cfg(L=k))
+    small.landmarks_actuales = k
+    with pytest.raises(IndexError):
+        small.actualizar(np.zeros((2, k)), y[:, :k], obs + 50.0)
+
+
+def test_iterate_until_monitors_calc_cambio_and_stops():
+    """The convergence monitor (sensors.py:302-315): every pass's calc_cambio triple from the sweep's own filter equals the
+    full search of the reference's calc_cambio on the same maps, and the loop stops at the requested change."""
+    from oracle import oracle as orc
+    d, cfgd = _synthetic_case(625, 4000, 20181 + 23)
+    z, odo, u = d["observations"], d["odometry"], d["velocities"]
+    e = _engine(_cfg(**cfgd), z, odo, u)
+    e.set_map(d["map_init"]); e.set_poses(d["x_init"])
+    maps = [d["map_init"]]
+    n, cam = e.iterate_until(odo[:, 0], 6, 0.0)
+    assert n == 6 and cam.shape == (6, 3)
+    e2 = _engine(_cfg(**cfgd), z, odo, u)
+    e2.set_map(d["map_init"]); e2.set_poses(d["x_init"])
+    for k in range(6):
+        e2.iterate(None, odo[:, 0], 1)
+        maps.append(e2.get_map())
+        ref = orc.calc_cambio(maps[-1], maps[-2])
+        assert np.max(np.abs(np.array(ref) - cam[k])) <= 1e-9, (k, ref, cam[k])
+    assert np.array_equal(e.get_map(), e2.get_map()) and np.array_equal(e.get_poses(), e2.get_poses())
+    e.set_map(d["map_init"]); e.set_poses(d["x_init"])
+    tol = float(cam[2, 1]) * 1.0001
+    n2, cam2 = e.iterate_until(odo[:, 0], 6, tol)
+    assert n2 == 3 and np.allclose(cam2, cam[:3], rtol=0, atol=1e-12)
+    e.close(); e2.close()
