@@ -97,7 +97,7 @@ struct icmslam_handle {
     struct GraphSlot { cudaGraphExec_t exec = nullptr; const double* src = nullptr; const double* map_in = nullptr; double x0[3] = {0, 0, 0}; double tol = 0; int maxit = 0; };
     GraphSlot graphs[4];
     int use_graph = 1, graph_launches = 0;
-    int runs_occ = 8;            // resident 128-thread blocks per SM k_runs is compiled for (8: 64 registers; ICMSLAM_RUNS_OCC=6: 80)
+    int runs_occ = 6;            // resident 128-thread blocks per SM k_runs is compiled for (6: 80 registers, no spills; ICMSLAM_RUNS_OCC=8: 64)
     int solve_occ = 5;           // resident 128-thread blocks per SM k_solve_tile is compiled for (ICMSLAM_SOLVE_OCC=4|5|6)
     int use_runs = 1;            // ICMSLAM_RUNS=0: every tile goes through the association kernel every sweep (no steady-state shortcut)
     int assoc_blocks = 0;        // grid of the (persistent) association kernel
@@ -324,7 +324,7 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     { const char* eg = getenv("ICMSLAM_GRAPH"); if (eg) h->use_graph = atoi(eg); }
     { const char* er = getenv("ICMSLAM_RUNS"); if (er) h->use_runs = atoi(er) != 0; }
     { const char* er = getenv("ICMSLAM_SOLVE_OCC"); if (er && (atoi(er) == 4 || atoi(er) == 6)) h->solve_occ = atoi(er); }
-    { const char* er = getenv("ICMSLAM_RUNS_OCC"); if (er && atoi(er) == 6) h->runs_occ = 6; }
+    { const char* er = getenv("ICMSLAM_RUNS_OCC"); if (er && atoi(er) == 8) h->runs_occ = 8; }
     if (e == cudaSuccess) {
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);

@@ -47,12 +47,31 @@
 #define RS_MAX_BEAMS 255    // beams of a run that may use a slot: |S| <= n dist_thr, so its fixed-point value stays below 2^42 and
                             // the high limb below 2^20 * 1000 (longer runs go straight to the global sums)
 
+#define RUN_RING 4          // steps of a slice in flight (cp.async ring, steady-state kernel)
+
 // what a block keeps in shared memory for its tile: the statistics table and the landmark records of the table's slots
 struct TileSmem {
     unsigned acc[RS_SLOTS][5];     // per slot: sum x (low, high limb), sum y (low, high limb), beams
     double2 lxy[RS_SLOTS];         // the slot's landmark
     double lr[RS_SLOTS];           // ... and its proven radius
 };
+
+// the records of the next RUN_RING steps of a warp's slice, brought in with cp.async: every lane copies and reads its own column
+struct SliceRing {
+    double2 sb[RUN_RING][32];
+    int2 mt[RUN_RING][32];
+};
+
+__device__ __forceinline__ void ring_issue(SliceRing* R, const double2* sbp, const int2* mtp, int k, int nr, int lane)
+{
+    if (k < nr) {
+        const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(&R->sb[k % RUN_RING][lane]);
+        const uint32_t d1 = (uint32_t)__cvta_generic_to_shared(&R->mt[k % RUN_RING][lane]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(sbp + (size_t)k * 32) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d1), "l"(mtp + (size_t)k * 32) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
 
 // packed half of a run record: x = label (24 bits) | slot << 24, y = rho code (16 bits) | beams << 16
 __device__ __forceinline__ int2 run_meta_pack(int label, int slot, int rho_code, int n)
@@ -180,7 +199,7 @@ __device__ __forceinline__ RunEval run_eval(const RunParams& p, const TileSmem& 
 // association kernel has just written the records): no certification; only the scans with commit_all or a dirty flag are
 // committed.
 template <bool STEADY>
-__device__ __forceinline__ bool process_slice(const RunParams& p, TileSmem& S, int slice, int tile, bool commit_all)
+__device__ __forceinline__ bool process_slice(const RunParams& p, TileSmem& S, int slice, int tile, bool commit_all, SliceRing* ring = nullptr)
 {
     const int lane = threadIdx.x & 31;
     const int t = p.t_start + slice * 32 + lane;
@@ -199,15 +218,23 @@ __device__ __forceinline__ bool process_slice(const RunParams& p, TileSmem& S, i
     double nfar = 0.0, fsx = 0.0, fsy = 0.0, FBx = 0.0, FBy = 0.0;
     bool ok = true;
     int kfail = 0;
-    // (the next step's record is in flight while a step is worked)
+    // (the records of the next steps are in flight while a step is worked: RUN_RING steps through the cp.async ring in the
+    //  steady-state kernel, one step in registers otherwise)
     double2 sb = make_double2(0.0, 0.0);
     int2 mt = make_int2(0, 0);
-    if (0 < nr) { sb = __ldcg(sbp); mt = __ldcg(mtp); }
+    if (ring) {
+#pragma unroll
+        for (int k = 0; k < RUN_RING; ++k) ring_issue(ring, sbp, mtp, k, nr, lane);
+    } else if (0 < nr) { sb = __ldcg(sbp); mt = __ldcg(mtp); }
     const int steps = __reduce_max_sync(FULLMASK, nr);
     for (int k = 0; k < steps; ++k) {
-        const double2 sb_c = sb;
-        const int2 mt_c = mt;
-        if (k + 1 < nr) { sb = __ldcg(sbp + (size_t)(k + 1) * 32); mt = __ldcg(mtp + (size_t)(k + 1) * 32); }
+        double2 sb_c = sb;
+        int2 mt_c = mt;
+        if (ring) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(RUN_RING - 1) : "memory");
+            sb_c = ring->sb[k % RUN_RING][lane]; mt_c = ring->mt[k % RUN_RING][lane];
+            ring_issue(ring, sbp, mtp, k + RUN_RING, nr, lane);
+        } else if (k + 1 < nr) { sb = __ldcg(sbp + (size_t)(k + 1) * 32); mt = __ldcg(mtp + (size_t)(k + 1) * 32); }
         if (k < nr && commit && ok) {
             const unsigned lab24 = (unsigned)mt_c.x & 0xffffffu;
             const bool matched = lab24 != RUN_FAR;
@@ -280,6 +307,7 @@ __global__ void __launch_bounds__(RUNS_THREADS, MINB)
 k_runs(const RunParams p)
 {
     __shared__ TileSmem S;
+    __shared__ SliceRing ring[RT_SLICES];
     const int tile = blockIdx.x;
     const int nslots = p.tile_nslots[tile];
     if (p.tile_epoch[tile] != p.ts->epoch) {      // no records for this label numbering: the whole tile goes to the association kernel
@@ -288,7 +316,7 @@ k_runs(const RunParams p)
     }
     tile_stage(p, S, tile, nslots);
     __syncthreads();
-    process_slice<true>(p, S, tile * RT_SLICES + (threadIdx.x >> 5), tile, true);
+    process_slice<true>(p, S, tile * RT_SLICES + (threadIdx.x >> 5), tile, true, &ring[threadIdx.x >> 5]);
     __syncthreads();
     stats_flush(p, S, tile, nslots);
 }
