@@ -27,7 +27,8 @@
 #define AT_WARPS (AT_THREADS / 32)
 #define AT_U 4                     // observations per lane in flight in phase A (pend bitmask: 64 / AT_U iterations per warp)
 #define AT_OBS_BYTES 23            // staged bytes per observation: (bx, by) 16, label 4, cell entry count 2, scan 1
-static_assert(AT_THREADS == 2 * RUNS_THREADS, "a tile's slices are processed by the first warps of the block");
+static_assert(AT_THREADS >= 32 * RT_SLICES, "a tile's slices are processed by the first warps of the block");
+#define AT_HASH 256                // positions of the tile's landmark -> slot hash
 
 struct AssocParams {
     int first_halo;                       // the first scan of tile 0 is the halo scan of a time segment (moments only)
@@ -52,11 +53,13 @@ struct __align__(16) AssocSmem {
     double2 rsc[RT_TILE];          // (sin, cos) of (projection heading - pi/2)
     int off[RT_TILE + 4];          // off[t] of the tile's scans
     // the tile's statistics slots: a small hash (landmark -> slot) filled while the runs are counted; slots are numbered densely
-    int hkey[RS_SLOTS];            // landmark at each hash position (-1: free)
-    int hid[RS_SLOTS];             // its slot (-1: not numbered yet)
-    int hcnt[RS_SLOTS];            // runs that name it
+    int hkey[AT_HASH];             // landmark at each hash position (-1: free)
+    int hid[AT_HASH];              // its slot (-1: not numbered yet)
+    int hcnt[AT_HASH];             // runs that name it
     int slot_label[RS_SLOTS];      // landmark of each slot
     int nslots;
+    int rtot[RT_TILE];             // runs of each scan
+    unsigned char pos[RT_TILE];    // (slice, lane) position of each scan: its rank by number of runs (identity when the tile is staged in pieces)
     TileSmem tile;                 // the statistics table and the staged landmark records (runs.cuh)
     unsigned long long mbar;
 };
@@ -73,7 +76,7 @@ __device__ __forceinline__ void slot_insert(AssocSmem& S, int label)
             key = (prev == -1) ? label : prev;
         }
         if (key == label) return;
-        h = (h + 1) & (RS_SLOTS - 1);
+        h = (h + 1) & (AT_HASH - 1);
     }
 }
 
@@ -88,10 +91,10 @@ __device__ __forceinline__ int slot_of(AssocSmem& S, int label, int n)
         const int key = S.hkey[h];
         if (key == label) {
             const int id = S.hid[h];
-            return (id >= 0 && id < RS_NOSLOT && atomicAdd(&S.hcnt[h], 1) < RS_MAX_ADDS) ? id : RS_NOSLOT;
+            return (id >= 0 && id < RS_SLOTS && atomicAdd(&S.hcnt[h], 1) < RS_MAX_ADDS) ? id : RS_NOSLOT;
         }
         if (key == -1) return RS_NOSLOT;
-        h = (h + 1) & (RS_SLOTS - 1);
+        h = (h + 1) & (AT_HASH - 1);
     }
     return RS_NOSLOT;
 }
@@ -149,7 +152,7 @@ k_assoc_tiles(const AssocParams p)
             const double4 pq = ldg_ppar(R.ppar + tb + tid);
             S.pp[tid] = make_double2(pq.x, pq.y); S.rsc[tid] = make_double2(pq.z, pq.w);
         }
-        for (int hh = tid; hh < RS_SLOTS; hh += AT_THREADS) { S.hkey[hh] = -1; S.hid[hh] = -1; S.hcnt[hh] = 0; }
+        for (int hh = tid; hh < AT_HASH; hh += AT_THREADS) { S.hkey[hh] = -1; S.hid[hh] = -1; S.hcnt[hh] = 0; }
         if (tid == 0) S.nslots = 0;
         __syncthreads();
         // ---- chunks of whole scans whose observations fit the shared-memory budget (normally one) -----------------
@@ -312,7 +315,7 @@ k_assoc_tiles(const AssocParams p)
             // beam and the centroid lie in the run's bounding box, so the farthest box corner from the centroid bounds
             // |b_i - centroid| (float arithmetic with its rounding covered by the margins, then rounded up to 1/2048 m).
             int nr = 0;
-            const size_t slot0 = ((size_t)(tile * RT_SLICES + (q >> 5)) * R.maxr) * 32 + (q & 31);
+            // (slot0 depends on the scan's position, known after the counting pass below)
             // (the first half's run count is needed for the second half's row offset: count first, then write)
             const bool halo_scan = halo_tile && q == 0;
             if (o < e) {
@@ -327,16 +330,33 @@ k_assoc_tiles(const AssocParams p)
             }
             const int nr_other = __shfl_xor_sync(FULLMASK, nr, 1);
             const int rtot = nr + nr_other;
+            const bool whole = c_lo == 0 && c_hi == nsc - 1;      // the tile is staged in one piece: every scan's run count is known
+            if (sub == 0 && q < RT_TILE) S.rtot[q] = mine ? rtot : 0;
             __syncthreads();
             // number the landmarks that entered the hash in this chunk
-            if (tid < RS_SLOTS && S.hkey[tid] != -1 && S.hid[tid] < 0) {
+            if (tid < AT_HASH && S.hkey[tid] != -1 && S.hid[tid] < 0) {
                 const int id = atomicAdd(&S.nslots, 1);
                 S.hid[tid] = id;
-                if (id < RS_NOSLOT) S.slot_label[id] = S.hkey[tid];
+                if (id < RS_SLOTS) S.slot_label[id] = S.hkey[tid];
+            }
+            // position of every scan: scans with fewer runs first (stable), so that a warp's 32 scans need about the same
+            // number of steps
+            if (c_lo == 0 && tid < RT_TILE) {
+                int rank = tid;
+                if (whole) {
+                    const int mine_r = S.rtot[tid];
+                    rank = 0;
+                    for (int j = 0; j < RT_TILE; ++j) { const int rj = S.rtot[j]; rank += (rj < mine_r) || (rj == mine_r && j < tid); }
+                }
+                S.pos[tid] = (unsigned char)rank;
+                R.tile_perm[(size_t)tile * RT_TILE + rank] = (unsigned char)tid;
+                if (whole) R.pos_nruns[(size_t)tile * RT_TILE + rank] = (unsigned short)S.rtot[tid];
             }
             __syncthreads();
             if (o < e) {
                 // (the next observation is fetched before the current one is consumed)
+                const int ps = S.pos[q];
+                const size_t slot0 = ((size_t)(tile * RT_SLICES + (ps >> 5)) * R.maxr) * 32 + (ps & 31);
                 int k = sub ? nr_other : 0;
                 int run_start = o, bk = sbk[o];
                 double2 b = sb[o];
@@ -366,13 +386,16 @@ k_assoc_tiles(const AssocParams p)
                     b = bn; bk = bkn;
                 }
             }
-            if (mine && sub == 0) R.nruns[tb + q] = (unsigned short)rtot;
+            if (mine && sub == 0) {
+                R.nruns[tb + q] = (unsigned short)rtot;
+                if (!whole) R.pos_nruns[(size_t)tile * RT_TILE + q] = (unsigned short)rtot;      // (identity positions)
+            }
             c_lo = c_hi + 1;
             if (c_lo < nsc) __syncthreads();   // the next chunk overwrites the staging buffers
         }
         __syncthreads();
         // ---- tile header, then the slices through the same code as the steady state -------------------------------------------
-        const int nslots = min(S.nslots, RS_NOSLOT);
+        const int nslots = min(S.nslots, RS_SLOTS);
         if (tid == 0) { R.tile_epoch[tile] = epoch; R.tile_nslots[tile] = nslots; }
         for (int hh = tid; hh < nslots; hh += AT_THREADS) R.tile_slots[(size_t)tile * RS_SLOTS + hh] = S.slot_label[hh];
         __syncthreads();     // the block's records and slot table are visible to its warps

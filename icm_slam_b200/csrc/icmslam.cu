@@ -81,6 +81,8 @@ struct icmslam_handle {
     int n_tiles = 0, n_solve_tiles = 0;        // record tiles (RT_TILE scans) / solve tiles (ST_OWN poses)
     double2* d_rec_sb = nullptr; int2* d_rec_meta = nullptr; int64_t rec_slots = 0; int rec_maxr = 1;   // run records (runs.cuh)
     unsigned short* d_nruns = nullptr;         // runs of each scan
+    unsigned char* d_tile_perm = nullptr;      // RT_TILE scan positions per record tile (runs.cuh)
+    unsigned short* d_pos_nruns = nullptr;     // ... and the runs of the scan at each position
     int* d_tile_slots = nullptr; int* d_tile_nslots = nullptr;   // RS_SLOTS labels per record tile, slots in use
     int *d_tile_epoch = nullptr, *d_tile_flag = nullptr, *d_dirty_list = nullptr, *d_scan_dirty = nullptr;
     double* d_dyn = nullptr;                   // 6 landmark moments per pose
@@ -91,13 +93,14 @@ struct icmslam_handle {
     LmRec* d_lmrec = nullptr;           // landmarks of the current map by label (position + hint radius)
     int* d_remap = nullptr;             // label of the last sweep -> label in the current map
     int* d_klab = nullptr;              // raw label of each kept landmark (fast tail)
+    int traj_T = 0, traj_K = 0; double* d_x0s = nullptr;   // batch of independent trajectories laid end to end (icmslam_set_batch)
     double* d_aobs = nullptr; int* d_ac = nullptr;   // icmslam_associate: one scan's observations (2 x ASSOC_MAX_OBS) and labels
     double* d_nnd2 = nullptr;
     double thr1sq = 0.0;
     struct GraphSlot { cudaGraphExec_t exec = nullptr; const double* src = nullptr; const double* map_in = nullptr; double x0[3] = {0, 0, 0}; double tol = 0; int maxit = 0; };
     GraphSlot graphs[4];
     int use_graph = 1, graph_launches = 0;
-    int runs_occ = 6;            // resident 128-thread blocks per SM k_runs is compiled for (6: 80 registers, no spills; ICMSLAM_RUNS_OCC=8: 64)
+    int runs_occ = 24;           // resident one-warp blocks per SM k_runs is compiled for (24: 80 registers; ICMSLAM_RUNS_OCC=32: 64)
     int solve_occ = 5;           // resident 128-thread blocks per SM k_solve_tile is compiled for (ICMSLAM_SOLVE_OCC=4|5|6)
     int use_runs = 1;            // ICMSLAM_RUNS=0: every tile goes through the association kernel every sweep (no steady-state shortcut)
     int assoc_blocks = 0;        // grid of the (persistent) association kernel
@@ -113,6 +116,7 @@ struct icmslam_handle {
     // map chain: grid, hints and labels stay valid, sensors.py:315 `mapa_viejo = mapa_refinado`)
     std::vector<double> last_map_host; int last_map_L = -1;
     int64_t bytes_h2d = 0, bytes_d2h = 0;      // copied by host-memspace sweeps (icmslam_get_transfer_bytes)
+    double* d2h_x = nullptr; int64_t d2h_ld = 0; bool d2h_done = false;   // host destination of the sweep in flight's poses (fused path)
     // time-segment partition (icmslam_set_segment): this handle owns columns [seg_lo, seg_hi) of its T columns
     int seg_lo = 0, seg_hi = 0, seg_first = 1, seg_last = 1;
     double* d_newraw = nullptr;   // 2 x Lcap: means of the sweep's new labels (zero elsewhere)
@@ -180,12 +184,14 @@ static void free_dataset(icmslam_handle* h)
     DFREE(h->d_nfar); DFREE(h->d_flag); DFREE(h->d_prefix); DFREE(h->d_x);
     DFREE(h->d_inc); DFREE(h->d_bm); DFREE(h->d_dyn); DFREE(h->d_x2); DFREE(h->d_far_list); DFREE(h->d_blk_prefix); DFREE(h->d_bxy);
     DFREE(h->d_ppar[0]); DFREE(h->d_ppar[1]); DFREE(h->d_farbits); DFREE(h->d_rec_sb); DFREE(h->d_rec_meta); DFREE(h->d_nruns); DFREE(h->d_tile_epoch);
-    DFREE(h->d_tile_flag); DFREE(h->d_dirty_list); DFREE(h->d_scan_dirty); DFREE(h->d_tile_slots); DFREE(h->d_tile_nslots);
+    DFREE(h->d_tile_flag); DFREE(h->d_dirty_list); DFREE(h->d_scan_dirty); DFREE(h->d_tile_slots); DFREE(h->d_tile_nslots); DFREE(h->d_tile_perm); DFREE(h->d_pos_nruns);
     h->ppar_of = nullptr;
     drop_graphs(h);
     h->grid_map = nullptr;
     h->hint_map = nullptr;
     h->last_map_L = -1;
+    h->traj_T = 0; h->traj_K = 0;
+    DFREE(h->d_x0s);
     h->fused_ok = false;
     h->extracted = false;
     h->n = 0;
@@ -324,7 +330,7 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     { const char* eg = getenv("ICMSLAM_GRAPH"); if (eg) h->use_graph = atoi(eg); }
     { const char* er = getenv("ICMSLAM_RUNS"); if (er) h->use_runs = atoi(er) != 0; }
     { const char* er = getenv("ICMSLAM_SOLVE_OCC"); if (er && (atoi(er) == 4 || atoi(er) == 6)) h->solve_occ = atoi(er); }
-    { const char* er = getenv("ICMSLAM_RUNS_OCC"); if (er && atoi(er) == 8) h->runs_occ = 8; }
+    { const char* er = getenv("ICMSLAM_RUNS_OCC"); if (er && atoi(er) == 32) h->runs_occ = 32; }
     if (e == cudaSuccess) {
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
@@ -488,13 +494,17 @@ extern "C" int icmslam_extract(icmslam_handle* h)
     CK(cudaGetLastError());
     DFREE(h->d_bm); DFREE(h->d_dyn);
     DFREE(h->d_ppar[0]); DFREE(h->d_ppar[1]); DFREE(h->d_farbits); DFREE(h->d_rec_sb); DFREE(h->d_rec_meta); DFREE(h->d_nruns); DFREE(h->d_tile_epoch);
-    DFREE(h->d_tile_flag); DFREE(h->d_dirty_list); DFREE(h->d_scan_dirty); DFREE(h->d_tile_slots); DFREE(h->d_tile_nslots);
+    DFREE(h->d_tile_flag); DFREE(h->d_dirty_list); DFREE(h->d_scan_dirty); DFREE(h->d_tile_slots); DFREE(h->d_tile_nslots); DFREE(h->d_tile_perm); DFREE(h->d_pos_nruns);
     {   // run records and their bookkeeping (runs.cuh): slice s (32 scans) owns slots [s * maxr * 32, (s + 1) * maxr * 32)
         const size_t nt = (size_t)nblk(T + 1, RT_TILE) + 2;      // (+1 scan: a segment's tiling may start one scan earlier)
         h->rec_maxr = h->max_per_scan > 0 ? h->max_per_scan : 1;
         h->rec_slots = (int64_t)(nt * RT_SLICES) * h->rec_maxr * 32;
         CK(dalloc(&h->d_rec_sb, (size_t)h->rec_slots)); CK(dalloc(&h->d_rec_meta, (size_t)h->rec_slots));
         CK(dalloc(&h->d_nruns, nt * RT_TILE));
+        CK(dalloc(&h->d_tile_perm, nt * RT_TILE));
+        CK(dalloc(&h->d_pos_nruns, nt * RT_TILE));
+        CK(cudaMemsetAsync(h->d_pos_nruns, 0, nt * RT_TILE * sizeof(unsigned short), h->stream));
+        CK(cudaMemsetAsync(h->d_tile_perm, 0, nt * RT_TILE, h->stream));      // (rewritten with every tile's records; never read before)
         CK(dalloc(&h->d_ppar[0], (size_t)T)); CK(dalloc(&h->d_ppar[1], (size_t)T));
         CK(dalloc(&h->d_farbits, nt * 4)); CK(dalloc(&h->d_tile_epoch, nt));
         CK(dalloc(&h->d_tile_flag, nt)); CK(dalloc(&h->d_dirty_list, nt)); CK(dalloc(&h->d_tile_slots, nt * RS_SLOTS)); CK(dalloc(&h->d_tile_nslots, nt));
@@ -756,11 +766,19 @@ static int build_fgrid(icmslam_handle* h, const double* px, const double* py, co
 __global__ void k_epoch_bump(TailState* ts) { ts->epoch += 1; }
 __global__ void k_note_dirty(DevState* st, const TailState* ts) { st->dirty_tiles = ts->n_dirty; }
 
+static TrajLayout traj_layout(const icmslam_handle* h, const double* x0)
+{
+    TrajLayout L;
+    L.first = h->seg_first; L.traj_T = h->traj_T; L.x0s = h->d_x0s; L.ldx0s = h->traj_K;
+    L.x0[0] = x0[0]; L.x0[1] = x0[1]; L.x0[2] = x0[2];
+    return L;
+}
+
 // projection parameters (solve.cuh make_ppar) of the poses in `x`, unless the solve of the previous sweep already left them
 static int ensure_ppar(icmslam_handle* h, const double* x, int64_t ldx, const double* x0, double4* dst)
 {
     if (h->ppar_of == x && x != nullptr) return ICMSLAM_OK;
-    k_ppar_init<<<nblk(h->T, 256), 256, 0, h->stream>>>(x, ldx, 0, h->T, h->seg_first, x0[0], x0[1], x0[2], dst);
+    k_ppar_init<<<nblk(h->T, 256), 256, 0, h->stream>>>(x, ldx, 0, h->T, traj_layout(h, x0), dst);
     CK(cudaGetLastError());
     h->n_launch += 1;
     h->ppar_of = x;
@@ -801,7 +819,7 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
     const int t_start = h->seg_lo - (h->seg_first ? 0 : 1);     // a later segment also forms the moments of its odd halo pose
     RunParams R;
     R.t_start = t_start; R.t_hi = h->seg_hi; R.halo_t = h->seg_first ? -1 : t_start; R.maxr = h->rec_maxr; R.ppar = pp_in; R.lmrec = h->d_lmrec;
-    R.rec_sb = h->d_rec_sb; R.rec_meta = h->d_rec_meta; R.nruns = h->d_nruns; R.tile_epoch = h->d_tile_epoch; R.dyn = h->d_dyn;
+    R.rec_sb = h->d_rec_sb; R.rec_meta = h->d_rec_meta; R.nruns = h->d_nruns; R.tile_perm = h->d_tile_perm; R.pos_nruns = h->d_pos_nruns; R.tile_epoch = h->d_tile_epoch; R.dyn = h->d_dyn;
     R.fsum_x = h->d_fsum_x; R.fsum_y = h->d_fsum_y; R.cnt = h->d_cnt; R.fix_scale = h->fix_scale; R.tile_slots = h->d_tile_slots; R.tile_nslots = h->d_tile_nslots;
     R.far_list = h->d_far_list; R.ts = h->d_ts; R.farbits = h->d_farbits;
     R.scan_dirty = h->d_scan_dirty; R.tile_flag = h->d_tile_flag; R.dirty_list = h->d_dirty_list;
@@ -815,8 +833,8 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
     CK(cudaMemsetAsync(h->d_farbits, 0, (size_t)h->n_tiles * 4 * sizeof(unsigned), s));
     if (timing) CK(cudaEventRecord(h->ev[0], s));
     if (h->use_runs) {
-        if (h->runs_occ == 6) k_runs<6><<<h->n_tiles, RUNS_THREADS, 0, s>>>(R);
-        else k_runs<8><<<h->n_tiles, RUNS_THREADS, 0, s>>>(R);
+        if (h->runs_occ == 32) k_runs<32><<<h->n_tiles * RT_SLICES, RUNS_THREADS, 0, s>>>(R);
+        else k_runs<24><<<h->n_tiles * RT_SLICES, RUNS_THREADS, 0, s>>>(R);
     } else {
         k_all_dirty<<<nblk(h->n_tiles, 256), 256, 0, s>>>(h->d_tile_flag, h->d_dirty_list, h->d_ts, h->n_tiles);
     }
@@ -832,9 +850,8 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
     h->n_launch += 2;
     {
         SolveParams P;
-        P.T = T; P.t_lo = h->seg_lo; P.t_hi = h->seg_hi; P.first = h->seg_first;
+        P.T = T; P.t_lo = h->seg_lo; P.t_hi = h->seg_hi; P.lay = traj_layout(h, x0);
         P.xin = xin; P.ldin = ldin; P.xout = kout; P.ldout = kld;
-        P.x0[0] = x0[0]; P.x0[1] = x0[1]; P.x0[2] = x0[2];
         P.inc = h->d_inc; P.ldinc = T; P.u = h->d_u; P.ldu = T; P.bm = h->d_bm; P.ldbm = T; P.dyn = h->d_dyn;
         P.ppin = pp_in; P.ppout = pp_out; P.cfg = h->dcfg; P.tol = o.newton_tol; P.maxit = o.newton_maxit;
         P.iters = (o.reserved & 1) ? &st->newton_iters : nullptr;
@@ -849,6 +866,10 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
         else if (h->solve_occ == 6) k_solve_tile<6><<<h->n_solve_tiles, ST_THREADS, 0, ss>>>(P);
         else k_solve_tile<5><<<h->n_solve_tiles, ST_THREADS, 0, ss>>>(P);
         CK(cudaGetLastError());
+        if (h->d2h_x) {      // a host-memory caller: its poses start their way back as soon as they are solved, beside the tail
+            CK(cudaMemcpy2DAsync(h->d2h_x, (size_t)h->d2h_ld * 8, kout, (size_t)kld * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToHost, ss));
+            h->d2h_done = true;
+        }
         if (fork) {
             CK(cudaEventRecord(h->ev_join, ss));
             h->join_pending = true;
@@ -1105,14 +1126,17 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
         h->hint_map = nullptr;
     }
     const bool own_out = (memspace == ICMSLAM_HOST || !map_out);
+    h->d2h_done = false;
+    if (memspace == ICMSLAM_HOST) { h->d2h_x = x; h->d2h_ld = ld_x; }
     int rc = sweep_core(h, xin, ldin, xout, ldout, x0, o, L_in, own_out ? h->d_map_out : map_out, own_out ? L : cap_out,
                         own_out ? (int64_t)L : ld_map_out);
+    h->d2h_x = nullptr;
     if (rc) return rc;
     if (own_out) {      // mapa_refinado becomes the handle's current map (icmslam_get_map, and the map chain a caller may continue)
         double* t = h->d_map_in; h->d_map_in = h->d_map_out; h->d_map_out = t;
     }
     if (memspace == ICMSLAM_HOST) {
-        CK(cudaMemcpy2DAsync(x, (size_t)ld_x * 8, xout, (size_t)T * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToHost, s));
+        if (!h->d2h_done) CK(cudaMemcpy2DAsync(x, (size_t)ld_x * 8, xout, (size_t)T * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToHost, s));
         h->bytes_d2h += (int64_t)3 * T * 8 + (int64_t)sizeof(DevState);
         rc = sync_state(h);
         if (rc) return rc;
@@ -1295,6 +1319,32 @@ extern "C" int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const
             return status_from_state(h->h_st);
         }
     }
+    return ICMSLAM_OK;
+}
+
+// ---- a batch of independent trajectories in one handle (BASELINE configs[4]) ---------------------------------------------
+extern "C" int icmslam_set_batch(icmslam_handle* h, int32_t traj_T, const double* x0s, int64_t ld_x0s, int32_t K)
+{
+    if (!h || !h->extracted) return ICMSLAM_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    if (traj_T <= 0) { h->traj_T = 0; h->traj_K = 0; DFREE(h->d_x0s); h->ppar_of = nullptr; drop_graphs(h); return ICMSLAM_OK; }
+    if (!x0s || K <= 0 || ld_x0s < K || (int64_t)traj_T * K != h->T || traj_T < 3 || !h->fused_ok) return ICMSLAM_ERR_INVALID;
+    // every trajectory needs a non-empty first and last scan (the reference returns early / raises otherwise, sensors.py:137, :148)
+    std::vector<int> off((size_t)h->T + 1);
+    CK(cudaMemcpyAsync(off.data(), h->d_off, ((size_t)h->T + 1) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < K; ++k) {
+        const int a = k * traj_T, b = (k + 1) * traj_T - 1;
+        if (off[a + 1] == off[a] || off[b + 1] == off[b]) return ICMSLAM_ERR_UNSUPPORTED;
+    }
+    DFREE(h->d_x0s);
+    CK(dalloc(&h->d_x0s, (size_t)3 * K));
+    CK(cudaMemcpy2DAsync(h->d_x0s, (size_t)K * 8, x0s, (size_t)ld_x0s * 8, (size_t)K * 8, 3, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->traj_T = traj_T; h->traj_K = K;
+    h->first_empty = false; h->last_empty = false;
+    h->ppar_of = nullptr;
+    drop_graphs(h);
     return ICMSLAM_OK;
 }
 

@@ -17,7 +17,8 @@
 // the landmark grid (run_provably_far).  A scan with a run that fails is marked dirty; the association kernel re-associates
 // dirty tiles observation by observation in the same sweep and commits the dirty scans.
 //
-// LAYOUT: lanes are SCANS.  A slice is 32 consecutive scans; run k of the slice's scan j lives at slot
+// LAYOUT: lanes are SCANS.  A slice is 32 scans of a tile (the tile's scans sorted by their number of runs, so that the lanes
+// of a warp finish together: tile_perm); run k of the slice's scan j lives at slot
 // (slice * maxr + k) * 32 + j of two arrays (sum(b): 16 B, packed label / slot / rho / n: 8 B), maxr = the largest number of
 // kept beams of a scan.  A warp walks one slice, step k = run k of each of its 32 scans: the loads of a step are contiguous,
 // slots past a scan's last run are never written nor read, and every lane accumulates ITS scan's moments in registers in run
@@ -39,7 +40,7 @@
 #define RT_RHO_INF 65535
 #define RUN_FAR 0xffffffu   // label field of a run of far observations (its scan creates a new label, ICM_SLAM.py:172-182)
 #define RUN_MAX_LABEL 0xfffff0
-#define RS_SLOTS 256        // landmark slots of a tile's statistics table; slot RS_NOSLOT: straight to the global sums
+#define RS_SLOTS 128        // landmark slots of a tile's statistics table; slot RS_NOSLOT: straight to the global sums
 #define RS_NOSLOT 255
 #define RS_MAX_ADDS 500     // runs per slot and tile (enforced when the records are built): with every one of them added and
                             // taken back once, a low limb stays below 2^32
@@ -64,7 +65,7 @@ struct SliceRing {
 
 __device__ __forceinline__ void ring_issue(SliceRing* R, const double2* sbp, const int2* mtp, int k, int nr, int lane)
 {
-    if (k < nr) {
+    if (k < nr) {       // (nr = the slice's reserved steps for the first RUN_RING issues: they start before the scan's own count is known)
         const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(&R->sb[k % RUN_RING][lane]);
         const uint32_t d1 = (uint32_t)__cvta_generic_to_shared(&R->mt[k % RUN_RING][lane]);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(sbp + (size_t)k * 32) : "memory");
@@ -88,6 +89,9 @@ struct RunParams {
     const LmRec* lmrec;                   // landmarks by label: position, hint radius^2, hint radius
     double2* rec_sb; int2* rec_meta;      // run records, slot (slice * maxr + k) * 32 + lane
     unsigned short* nruns;                // runs of each scan
+    unsigned short* pos_nruns;            // RT_TILE entries per tile: runs of the scan at each (slice, lane) position
+    unsigned char* tile_perm;             // RT_TILE entries per tile: the scan (relative to the tile) worked by each (slice, lane) position --
+                                          // scans sorted by their number of runs, so that the lanes of a warp finish together
     int* tile_epoch;                      // label-numbering epoch the tile's records belong to
     double* dyn;                          // 6 doubles per pose: (Yx, Mxx, Mxy, Yy, Myx, Myy)
     long long* fsum_x; long long* fsum_y; int* cnt;   // per previous-map landmark statistics (fixed point)
@@ -202,18 +206,24 @@ template <bool STEADY>
 __device__ __forceinline__ bool process_slice(const RunParams& p, TileSmem& S, int slice, int tile, bool commit_all, SliceRing* ring = nullptr)
 {
     const int lane = threadIdx.x & 31;
-    const int t = p.t_start + slice * 32 + lane;
+    const size_t base = (size_t)slice * p.maxr * 32 + lane;
+    const double2* sbp = p.rec_sb + base;
+    const int2* mtp = p.rec_meta + base;
+    if (ring) {       // the first steps' records start their way before anything else is known about the slice
+#pragma unroll
+        for (int k = 0; k < RUN_RING; ++k) ring_issue(ring, sbp, mtp, k, p.maxr, lane);
+    }
+    const size_t ppos = (size_t)tile * RT_TILE + (slice - tile * RT_SLICES) * 32 + lane;
+    const int lt = p.tile_perm[ppos];
+    const int nr0 = p.pos_nruns[ppos];
+    const int t = p.t_start + tile * RT_TILE + lt;
     const bool in = t < p.t_hi;
-    const int nr = in ? (int)p.nruns[t] : 0;
+    const int nr = in ? nr0 : 0;
     const bool halo = t == p.halo_t;
-    const int lt = t - (p.t_start + tile * RT_TILE);
     bool commit = in && nr > 0;
     if (!STEADY) commit = commit && (commit_all || p.scan_dirty[t] != 0);
     double4 pp = make_double4(0.0, 0.0, 0.0, 1.0);
     if (nr > 0) pp = ldg_ppar(p.ppar + t);
-    const size_t base = (size_t)slice * p.maxr * 32 + lane;
-    const double2* sbp = p.rec_sb + base;
-    const int2* mtp = p.rec_meta + base;
     double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0, m4 = 0.0, m5 = 0.0;
     double nfar = 0.0, fsx = 0.0, fsy = 0.0, FBx = 0.0, FBy = 0.0;
     bool ok = true;
@@ -222,11 +232,9 @@ __device__ __forceinline__ bool process_slice(const RunParams& p, TileSmem& S, i
     //  steady-state kernel, one step in registers otherwise)
     double2 sb = make_double2(0.0, 0.0);
     int2 mt = make_int2(0, 0);
-    if (ring) {
-#pragma unroll
-        for (int k = 0; k < RUN_RING; ++k) ring_issue(ring, sbp, mtp, k, nr, lane);
-    } else if (0 < nr) { sb = __ldcg(sbp); mt = __ldcg(mtp); }
-    const int steps = __reduce_max_sync(FULLMASK, nr);
+    if (!ring && 0 < nr) { sb = __ldcg(sbp); mt = __ldcg(mtp); }
+    const int steps = __reduce_max_sync(FULLMASK, nr);      // (also orders the staging of the tile's table before its first use)
+    __syncwarp();
     for (int k = 0; k < steps; ++k) {
         double2 sb_c = sb;
         int2 mt_c = mt;
@@ -299,25 +307,25 @@ __device__ __forceinline__ bool process_slice(const RunParams& p, TileSmem& S, i
     return true;
 }
 
-#define RUNS_THREADS (32 * RT_SLICES)
+#define RUNS_THREADS 32
 
-// steady state: one block per record tile, a warp per slice
+// steady state: one WARP per slice and block (no block barrier: a slice that needs more steps than its neighbours holds nobody
+// up); every block stages its tile's slot table
 template <int MINB>      // resident blocks per SM the kernel is compiled for
 __global__ void __launch_bounds__(RUNS_THREADS, MINB)
 k_runs(const RunParams p)
 {
     __shared__ TileSmem S;
-    __shared__ SliceRing ring[RT_SLICES];
-    const int tile = blockIdx.x;
+    __shared__ SliceRing ring;
+    const int slice = blockIdx.x, tile = slice / RT_SLICES;
     const int nslots = p.tile_nslots[tile];
     if (p.tile_epoch[tile] != p.ts->epoch) {      // no records for this label numbering: the whole tile goes to the association kernel
-        if (threadIdx.x == 0) { p.tile_flag[tile] = 2; p.dirty_list[atomicAdd(&p.ts->n_dirty, 1)] = tile; }
+        if (threadIdx.x == 0 && slice == tile * RT_SLICES) { p.tile_flag[tile] = 2; p.dirty_list[atomicAdd(&p.ts->n_dirty, 1)] = tile; }
         return;
     }
-    tile_stage(p, S, tile, nslots);
-    __syncthreads();
-    process_slice<true>(p, S, tile * RT_SLICES + (threadIdx.x >> 5), tile, true, &ring[threadIdx.x >> 5]);
-    __syncthreads();
+    tile_stage(p, S, tile, nslots);      // (its two dependent loads overlap those of process_slice's prologue: no barrier in between)
+    process_slice<true>(p, S, slice, tile, true, &ring);
+    __syncwarp();
     stats_flush(p, S, tile, nslots);
 }
 

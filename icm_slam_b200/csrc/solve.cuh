@@ -62,14 +62,29 @@ __global__ void k_interleave(const double* __restrict__ bx, const double* __rest
     if (i < n) out[i] = make_double2(bx[i], by[i]);
 }
 
-// ppar of poses given from outside (set_poses, host sweeps, halo columns).  Column 0 of the trajectory's first segment is
-// projected with self.x0 (sensors.py:131,141), not with x[:,0].
-__global__ void k_ppar_init(const double* __restrict__ x, int64_t ld, int t_begin, int t_end, int first, double x0x, double x0y, double x0t,
-                            double4* __restrict__ ppar)
+// Which columns are pinned first poses (sensors.py:131: x[:,0] is never updated, scan 0 is projected with self.x0): column 0
+// of the trajectory's first segment, or -- a batch of independent trajectories of traj_T columns each laid end to end in one
+// handle (BASELINE configs[4]) -- the first column of every trajectory, each with its own x0.  A trajectory's last pose has no
+// successor.
+struct TrajLayout {
+    int first;                 // column 0 is the trajectory's first pose
+    int traj_T;                // > 0: batch of trajectories of this many columns
+    const double* x0s;         // batch: 3 x K first poses (row-major, leading dimension ldx0s)
+    int64_t ldx0s;
+    double x0[3];              // single trajectory: self.x0
+    __device__ __forceinline__ bool pinned(int t) const { return traj_T > 0 ? (t % traj_T) == 0 : (t == 0 && first); }
+    __device__ __forceinline__ bool after_pinned(int t) const { return traj_T > 0 ? (t % traj_T) == 1 : (t == 1 && first); }
+    __device__ __forceinline__ bool has_next(int t, int T) const { return t + 1 < T && (traj_T == 0 || ((t + 1) % traj_T) != 0); }
+    __device__ __forceinline__ double x0_of(int t, int r) const { return traj_T > 0 ? x0s[r * ldx0s + t / traj_T] : x0[r]; }
+};
+
+// ppar of poses given from outside (set_poses, host sweeps, halo columns).  A pinned column is projected with its x0
+// (sensors.py:131,141), not with x[:,t].
+__global__ void k_ppar_init(const double* __restrict__ x, int64_t ld, int t_begin, int t_end, const TrajLayout L, double4* __restrict__ ppar)
 {
     const int t = t_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= t_end) return;
-    if (t == 0 && first) ppar[0] = make_ppar(x0x, x0y, x0t);
+    if (L.pinned(t)) ppar[t] = make_ppar(L.x0_of(t, 0), L.x0_of(t, 1), L.x0_of(t, 2));
     else ppar[t] = make_ppar(x[t], x[ld + t], x[2 * ld + t]);
 }
 
@@ -176,10 +191,9 @@ __device__ __forceinline__ int newton_trig(const DevCfg& cfg, const PoseIn& P, c
 struct SolveParams {
     int T;                                // columns of this handle's trajectory (a time segment incl. its halo columns)
     int t_lo, t_hi;                       // owned poses [t_lo, t_hi), t_lo even
-    int first;                            // column 0 is the trajectory's first pose (pinned, sensors.py:131)
+    TrajLayout lay;                       // pinned first poses (self.x0) and trajectory ends
     const double* xin; int64_t ldin;      // 3 x T input poses
     double* xout; int64_t ldout;          // 3 x T output poses
-    double x0[3];                         // self.x0
     const double* inc; int64_t ldinc;     // 3 x T odometry increments
     const double* u; int64_t ldu;         // 2 x T controls
     const double* bm; int64_t ldbm;       // 6 x T static body-frame moments + beam count
@@ -213,7 +227,7 @@ __device__ __forceinline__ SlotMom solve_slot_load(const SolveParams& p, int tb,
     // (phase 0, slot 0 = the odd pose tb-1 left of the tile: re-solved here because the even pose tb needs its NEW value;
     //  phase 1, last slot = tb+126: the next tile's)
     s.valid = s.t >= 0 && s.t < p.t_hi && (phase == 0 ? (q == 0 || s.t >= p.t_lo) : (q != ST_HALF - 1 && s.t >= p.t_lo));
-    s.pinned = s.valid && s.t == 0 && p.first;
+    s.pinned = s.valid && p.lay.pinned(s.t);
     Mom& M = s.M;
     M.n = M.Bx = M.By = M.Bxx = M.Byy = M.Bxy = M.Yx = M.Yy = M.Mxx = M.Mxy = M.Myx = M.Myy = 0.0;
     if (s.valid && !s.pinned) {
@@ -252,7 +266,7 @@ k_solve_tile(const SolveParams p)
         S.u[1][li] = ok ? p.u[p.ldu + t] : 0.0;
         double sh = 0.0, ch = 1.0;
         if (ok) {
-            if (t == 0 && p.first) sincos(th, &sh, &ch);       // (ppar[0] belongs to self.x0; x[:,0] is only a neighbour)
+            if (p.lay.pinned(t)) sincos(th, &sh, &ch);       // (a pinned column's ppar belongs to its x0; x[:,t] is only a neighbour)
             else { const double4 pq = ldg_ppar(p.ppin + t); sh = pq.w; ch = -pq.z; }
         }
         S.sn[li] = sh; S.cs[li] = ch;
@@ -274,7 +288,7 @@ k_solve_tile(const SolveParams p)
         if (qvalid) {
             // neighbours: old poses for the odd phase, new (odd) poses for the even phase
             double (*X)[ST_XT] = phase == 0 ? S.xs : S.xn;
-            const bool has_next = t + 1 < T;
+            const bool has_next = p.lay.has_next(t, T);
             solve = !pinned && M.n > 0.0;
             ox = S.xs[0][li]; oy = S.xs[1][li]; th0 = S.xs[2][li]; s0 = S.sn[li]; c0 = S.cs[li];
             th = th0;
@@ -290,10 +304,10 @@ k_solve_tile(const SolveParams p)
                 P.D1x = S.inc[0][li]; P.D1y = S.inc[1][li]; P.dth1 = S.inc[2][li];
                 P.has_next = has_next ? 1 : 0;
                 if (!solve) {       // sensors.py:147-151: no observation, average of the neighbours
-                    const bool t1 = t == 1 && p.first;
-                    const double pv = t1 ? p.x0[half] : X[half][li - 1];
+                    const bool t1 = p.lay.after_pinned(t);
+                    const double pv = t1 ? p.lay.x0_of(t - 1, half) : X[half][li - 1];
                     res = (pv + X[half][li + 1]) / 2.0;
-                    th = ((t1 ? p.x0[2] : X[2][li - 1]) + X[2][li + 1]) / 2.0;
+                    th = ((t1 ? p.lay.x0_of(t - 1, 2) : X[2][li - 1]) + X[2][li + 1]) / 2.0;
                 }
             }
         }
@@ -329,7 +343,7 @@ k_solve_tile(const SolveParams p)
         for (int k = tid; k < n_own; k += ST_THREADS) p.xout[r * p.ldout + tb + k] = S.xn[r][k + 2];
     for (int k = tid; k < n_own; k += ST_THREADS) {
         const int tt = tb + k, l2 = k + 2;
-        if (tt == 0 && p.first) p.ppout[0] = make_ppar(p.x0[0], p.x0[1], p.x0[2]);
+        if (p.lay.pinned(tt)) p.ppout[tt] = make_ppar(p.lay.x0_of(tt, 0), p.lay.x0_of(tt, 1), p.lay.x0_of(tt, 2));
         else p.ppout[tt] = make_double4(S.xn[0][l2], S.xn[1][l2], -S.cs[l2], S.sn[l2]);
     }
 }

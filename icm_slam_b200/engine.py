@@ -136,6 +136,15 @@ class Engine:
             check(self.lib.icmslam_get_counts(self._h, _ptr(out)[0], n, HOST), self._h)
         return out
 
+    def set_batch(self, traj_T, x0s):
+        """The loaded columns are K independent trajectories of traj_T columns each (x0s: 3 x K pinned first poses); traj_T = 0
+        switches back to one trajectory."""
+        if not traj_T:
+            check(self.lib.icmslam_set_batch(self._h, 0, None, 0, 0), self._h)
+            return
+        x0s = np.ascontiguousarray(x0s, dtype=np.float64)
+        check(self.lib.icmslam_set_batch(self._h, int(traj_T), _ptr(x0s)[0], _rows(x0s, 3), int(x0s.shape[1])), self._h)
+
     def set_counts(self, counts=None):
         """cant_obs_i <- counts (rest zero); None: Mapa.clear_obs."""
         c = np.zeros(0) if counts is None else np.ascontiguousarray(counts, dtype=np.float64)
@@ -162,7 +171,7 @@ class Engine:
                 import torch
                 map_out = torch.zeros((2, self.L), dtype=torch.float64, device=x.device)
             else:
-                map_out = np.zeros((2, self.L))
+                map_out = np.empty((2, self.L))       # (only the first L_out columns are written and returned)
         po, mso = _ptr(map_out)
         assert mso == ms
         cap = int(map_out.shape[1])

@@ -301,7 +301,7 @@ class ICM_SLAM:
             xin[...] = xc
         if st == 1:   # empty first scan: inputs returned unchanged (sensors.py:137-139)
             return mapa_viejo, xin
-        return np.array(mapa), xin
+        return mapa, xin          # (a fresh array owned by the caller, like the reference's deepcopy, sensors.py:167)
 
     itererar = iterations_process_offline          # ICM_SLAM_old.py:336
 

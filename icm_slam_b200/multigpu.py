@@ -174,22 +174,60 @@ class SegmentedSolver:
                            new=mk(PTR_NEW_LABELS, "<f8"), all=mk(PTR_EXCHANGE, "<i8"))
 
     # -- sweeps ---------------------------------------------------------------------------------------------------
-    def _sweep_once(self, opts=None):
+    def _sweep_once(self, opts=None, stamps=None):
+        """One sweep.  `stamps` (a list) receives CUDA events after each stage: begin (run / association / solve kernels),
+        all-gather, exchange (label numbering), all-reduce, finish (map filter)."""
         from . import _lib
         from ._lib import check
+        import torch
         e = self.engine
         v = self._views
+
+        def stamp():
+            if stamps is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(torch.cuda.current_stream(self.device))
+                stamps.append(ev)
+
         if opts is None:
             opts = _lib.SweepOpts(_lib.SCHED["redblack"], _lib.SOLVER["newton"], _lib.VIEW["prev"], 0, 0.0, 1, 0)
+        stamp()
         check(e.lib.icmslam_seg_begin(e._h, C.c_void_p(self.x0.ctypes.data), C.byref(opts)), e._h)
+        stamp()
         if self.world > 1:
             import torch.distributed as dist
             dist.all_gather_into_tensor(self._allrec, v["rec"].reshape(1, SEG_REC), group=self.group)
+            stamp()
             check(e.lib.icmslam_seg_exchange(e._h, C.c_void_p(self._allrec.data_ptr()), self.rank, self.world), e._h)
+            stamp()
             dist.all_reduce(v["all"], group=self.group)      # the four statistics buffers as one block of int64 words
+            stamp()
         else:
             check(e.lib.icmslam_seg_exchange(e._h, C.c_void_p(v["rec"].data_ptr()), 0, 1), e._h)
         check(e.lib.icmslam_seg_finish(e._h), e._h)
+        stamp()
+
+    def stage_times(self, n=5):
+        """Mean milliseconds per stage over n eager sweeps (CUDA events on the solver's stream): what a step is made of."""
+        import torch
+        self._prepare()
+        names = ["begin: k_runs + k_assoc_tiles + k_solve_tile + far scan", "all-gather (128 B per rank)", "exchange: halo unpack + new labels",
+                 "all-reduce (statistics block)", "finish: landmark update + Mapa.filtrar + grid"] if self.world > 1 else \
+                ["begin: k_runs + k_assoc_tiles + k_solve_tile + far scan", "exchange + finish"]
+        acc = np.zeros(len(names))
+        caller = torch.cuda.current_stream(self.device)
+        self._stream.wait_stream(caller)
+        with torch.cuda.stream(self._stream):
+            for _ in range(n):
+                st = []
+                self._sweep_once(stamps=st)
+                self._steady += 1
+                self._parity ^= 1
+                torch.cuda.synchronize()
+                acc += np.array([st[i].elapsed_time(st[i + 1]) for i in range(len(st) - 1)])
+        caller.wait_stream(self._stream)
+        self._graphs = {}          # (an odd number of eager sweeps flips the ping-pong parity the graphs were captured for)
+        return dict(zip(names, (acc / n).tolist()))
 
     def _prepare(self):
         import torch
@@ -361,6 +399,7 @@ def bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, p
         with torch.cuda.stream(sol._stream):
             sol._sweep_once(_lib.SweepOpts(_lib.SCHED["redblack"], _lib.SOLVER["newton"], _lib.VIEW["prev"], 0, 0.0, 1, 2))
         kt.append(sol.engine.kernel_ms()[0])
+    stages = sol.stage_times(6)
     k_ms = torch.tensor([float(np.mean(kt))], dtype=torch.float64, device=dev)
     dist.all_reduce(k_ms, op=dist.ReduceOp.MAX)
     # end to end: host buffers in, host buffers out, every step
@@ -409,7 +448,7 @@ def bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, p
                     "d2h_bytes_per_step": int(bytes_t[1].item()), "steps": e2e_steps,
                     "call": "SegmentedSolver.set_map/set_poses/sweep/owned_poses/get_map with host numpy buffers on every rank"},
             "gpu_launches": int(launches) * args.steps * world, "gpu_launches_per_step": int(launches),
-            "result_sha256": sha,
+            "result_sha256": sha, "stages_ms_rank0_eager": stages,
             "roofline": {"bound": "hbm", "kernel": "k_runs + k_assoc_tiles (rank 0's segment)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": float(k_ms.item()),
                          "algorithmic_bytes": int(seg_bytes),

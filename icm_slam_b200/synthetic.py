@@ -167,3 +167,40 @@ def make_synthetic(L_true: int, T: int | None = None, seed: int = 20181, beams: 
                             row_spacing=ROW_SPACING, speed=SPEED, dt=DT, trunk_radius=TRUNK_RADIUS,
                             range_noise=range_noise, ctrl_noise=list(ctrl_noise),
                             init_pose_noise=list(init_pose_noise), init_map_noise=init_map_noise))
+
+
+def make_synthetic_loop(L_true: int = 16, T: int = 2048, seed: int = 20181, beams: int = 181, range_noise: float = 0.02,
+                        ctrl_noise=(0.02, 0.01), init_pose_noise=(0.05, 0.01), init_map_noise: float = 0.1):
+    """One trajectory of the BATCH workload (BASELINE configs[4], SURVEY.md 8d "C5": T = 2048 poses, 16 landmarks, per-trajectory
+    seed): the same sensor and noise model as make_synthetic, but the robot CIRCLES through a small G x G field (pitch 4 m,
+    G = sqrt(L_true)) -- radius 0.3 of the field's width around its centre -- so that every one of the T scans sees landmarks."""
+    G = int(round(np.sqrt(L_true)))
+    if G * G != L_true:
+        raise ValueError("L_true must be a perfect square (G x G landmark grid)")
+    rng = np.random.default_rng(seed)
+    gx, gy = np.meshgrid(np.arange(G), np.arange(G), indexing="xy")
+    lm = np.stack([PITCH * gx.ravel() + rng.uniform(-JITTER, JITTER, L_true),
+                   PITCH * gy.ravel() + rng.uniform(-JITTER, JITTER, L_true)])
+    width = PITCH * (G - 1)
+    radius = max(0.3 * width, 2.0)
+    centre = np.array([width / 2.0, width / 2.0])
+    n_loop = int(round(2 * np.pi * radius / (SPEED * DT)))
+    w_true = 2 * np.pi / (n_loop * DT)                      # an exact loop in n_loop Euler steps
+    v = np.full(T, radius * w_true)
+    w = np.full(T, w_true)
+    start = np.array([centre[0] + radius, centre[1], np.pi / 2.0])
+    x_true = _integrate(v, w, start)
+    scans = _raycast_chunked(x_true, lm, G, beams)
+    hit = scans < RANGE_MAX
+    scans[hit] += rng.normal(0.0, range_noise, int(hit.sum()))
+    scans = np.maximum(np.minimum(scans, RANGE_MAX), 0.05).astype(np.float32).astype(np.float64)
+    vn = v + rng.normal(0.0, ctrl_noise[0], T)
+    wn = w + rng.normal(0.0, ctrl_noise[1], T)
+    odo = _integrate(vn, wn, start)
+    x_init = x_true.copy()
+    x_init[0:2] += rng.normal(0.0, init_pose_noise[0], (2, T))
+    x_init[2] += rng.normal(0.0, init_pose_noise[1], T)
+    x_init[:, 0] = odo[:, 0]
+    map_init = lm + rng.normal(0.0, init_map_noise, lm.shape)
+    return dict(observations=np.ascontiguousarray(scans.T), odometry=odo, velocities=np.stack([vn, wn]), x_true=x_true, x_init=x_init,
+                landmarks_true=lm, map_init=map_init, params=dict(L_true=L_true, T=T, seed=seed, beams=beams, radius=radius))

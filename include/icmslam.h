@@ -149,6 +149,15 @@ int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const double* x0
 int icmslam_set_poses(icmslam_handle* h, const double* x, int64_t ld_x, int32_t memspace);
 int icmslam_get_poses(icmslam_handle* h, double* x, int64_t ld_x, int32_t memspace);
 
+/* -- a batch of INDEPENDENT trajectories in one handle (BASELINE.json configs[4]: Monte-Carlo multi-start; no reference
+ * counterpart beyond running the reference once per trajectory).  The caller loads K trajectories of traj_T columns each laid
+ * end to end (T = K * traj_T), each translated to its own region of the plane so that their landmarks are farther apart than
+ * any gate (icm_slam_b200/batch.py does both); x0s (HOST, 3 x K) are their pinned first poses.  Every trajectory's first pose is
+ * then pinned to its own x0, its last pose has no successor, and one sweep of the handle is one sweep of every trajectory: ONE
+ * launch of each kernel for the whole batch.  (REDBLACK, NEWTON, PREV) sweeps only; the x0 argument of icmslam_iterate is
+ * ignored.  traj_T <= 0 switches back to a single trajectory. */
+int icmslam_set_batch(icmslam_handle* h, int32_t traj_T, const double* x0s, int64_t ld_x0s, int32_t K);
+
 /* -- time-segment partition over several GPUs (no reference counterpart: the reference sweep is strictly
  * sequential in time, sensors.py:145-162; only the restated (REDBLACK, NEWTON, PREV) sweep partitions).
  * One handle per GPU loads the columns [g_lo - 2, g_hi + 1) of the trajectory (two halo columns on the

@@ -772,3 +772,33 @@ def test_iterate_until_monitors_calc_cambio_and_stops():
     n2, cam2 = e.iterate_until(odo[:, 0], 6, tol)
     assert n2 == expect <= 3 and np.allclose(cam2, cam[:expect], rtol=0, atol=1e-12)
     e.close(); e2.close()
+
+
+# ---- C5 as ONE handle: K trajectories laid end to end (icmslam_set_batch) == the same trajectories run one at a time -----------
+def test_concatenated_batch_equals_individual_runs():
+    from icm_slam_b200.batch import ConcatBatch
+    from icm_slam_b200.synthetic import make_synthetic_loop
+    cfgd = dict(L=2048, cota=20.0)      # (room for the labels the scans of trajectory 2 create every sweep)
+    cfg = _cfg(**cfgd)
+    K, Tk, nsw = 7, 1024, 5
+    data = [make_synthetic_loop(16, T=Tk, seed=20181 + 200 + i) for i in range(K)]
+    data[2]["map_init"] = np.delete(data[2]["map_init"], 5, axis=1)            # a missing landmark: far observations, new labels
+    data[4]["observations"][:, 300:310] = 10.0                                 # empty scans inside a trajectory
+    b = ConcatBatch(cfg, 0, 1, device=0)
+    for i, d in enumerate(data):
+        b.add(i, d["observations"], d["odometry"], d["velocities"], d["map_init"], d["x_init"])
+    b.finalize()
+    b.iterate(nsw)
+    got = b.results()
+    b.close()
+    for i, d in enumerate(data):
+        e = _engine(cfg, d["observations"], d["odometry"], d["velocities"])
+        e.set_map(d["map_init"])
+        e.set_poses(d["x_init"])
+        e.iterate(None, d["odometry"][:, 0], nsw)
+        x1, m1 = e.get_poses(), e.get_map()
+        e.close()
+        dx = np.abs(got[i][0] - x1)
+        assert dx[:2].max() <= 1e-9 and dx[2].max() <= 1e-11, (i, dx.max(axis=1))
+        assert got[i][1].shape == m1.shape, (i, got[i][1].shape, m1.shape)
+        assert np.abs(got[i][1] - m1).max() <= 1e-9, i
