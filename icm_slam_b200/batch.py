@@ -204,7 +204,7 @@ def bench(args, rank, world, local_rank, SEED, METRIC, peaks, ClockSampler, swee
         d = make_synthetic_loop(L_true, T=Tk, seed=SEED + i)        # per-trajectory seeds 20181 + i
         b.add(i, d["observations"], d["odometry"], d["velocities"], d["map_init"], d["x_init"])
     gen_s = time.time() - t0
-    stream = torch.cuda.Stream(device=dev)
+    stream = torch.cuda.Stream(device=dev, priority=-1)
     torch.cuda.set_stream(stream)
     n_obs = b.finalize()
     b.engine.set_stream(stream.cuda_stream)

@@ -45,6 +45,8 @@ struct AssocParams {
     int* c;                               // labels per observation (out)
     int obs_cap;                          // shared-memory capacity in observations
     int skip_hints;                       // debug (ICMSLAM_HINTS=0)
+    int n_tiles; int* blk_prefix; int Lcap; unsigned long long* bb;      // for the scan of the far counts (tail.cuh far_scan_block)
+    DevState* stw;                        // (= st, writable: the sweep's label bookkeeping)
     RunParams R;
 };
 
@@ -408,6 +410,17 @@ k_assoc_tiles(const AssocParams p)
         if (tid < nsc) R.scan_dirty[tb + tid] = 0;
         if (tid == 0) R.tile_flag[tile] = 0;
     }
+    // ---- the last block to finish numbers the sweep's label-creating scans (every tile's far bits are final by then) ----
+    // (the tile loop's shared arrays are free again: no static shared memory, the dynamic allocation is the whole budget)
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const int last = atomicAdd(&R.ts->assoc_ticket, 1) == (int)gridDim.x - 1;
+        if (last) { __threadfence(); R.ts->assoc_ticket = 0; }
+        S.nslots = last;
+    }
+    __syncthreads();
+    if (S.nslots) far_scan_block(R.farbits, p.n_tiles, p.blk_prefix, p.stw, R.ts, p.Lcap, p.bb, S.rtot, reinterpret_cast<unsigned char*>(sb), p.obs_cap * 16);
 }
 
 static size_t assoc_smem_bytes(int obs_cap)   // obs_cap is even

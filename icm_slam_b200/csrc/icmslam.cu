@@ -32,7 +32,7 @@ struct icmslam_handle {
     cudaStream_t own_stream = nullptr;   // created with the handle; replaced by icmslam_set_stream
     // the pose solve does not feed the tail (labels, landmark update, Mapa.filtrar): on one GPU the two run concurrently,
     // the solve forked onto a side stream after k_sweep_fused and joined at the end of the sweep (also inside the CUDA graph)
-    cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool join_pending = false; int overlap_solve = 1;
+    cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_tail = nullptr; bool join_pending = false; int overlap_solve = 1;
     char err[512];
     // dataset
     int B = 0, T = 0, precondition = 0;
@@ -78,6 +78,8 @@ struct icmslam_handle {
     FarRec* d_far_list = nullptr;
     int* d_blk_prefix = nullptr;
     unsigned* d_farbits = nullptr;             // 4 words per record tile: scans that created a label this sweep
+    int begin_L = 0;                           // landmarks_actuales bound of the sweep being issued (k_sweep_begin / sweep_begin_state)
+    int n_tiles_alloc = 0;                     // tiles the per-tile arrays were allocated for
     int n_tiles = 0, n_solve_tiles = 0;        // record tiles (RT_TILE scans) / solve tiles (ST_OWN poses)
     double2* d_rec_sb = nullptr; int2* d_rec_meta = nullptr; int64_t rec_slots = 0; int rec_maxr = 1;   // run records (runs.cuh)
     unsigned short* d_nruns = nullptr;         // runs of each scan
@@ -90,14 +92,20 @@ struct icmslam_handle {
     double thr2_lt = 0.0;        // largest s with sqrt_rn(s) < dist_thr
     const double* grid_map = nullptr;   // the map buffer the fast grid currently indexes (nullptr: rebuild)
     const double* hint_map = nullptr;   // the map buffer for which c[] (through d_remap) holds last sweep's labels
-    LmRec* d_lmrec = nullptr;           // landmarks of the current map by label (position + hint radius)
+    LmRec* d_lmrec2[2] = {nullptr, nullptr};   // landmarks of a map by label (position + hint radius): the current map's in
+    int lm_cur = 0;                            // d_lmrec2[lm_cur], the tail writes the new map's into the other one
+    int* d_blk_kept = nullptr;                 // kept landmarks per block of k_fused_means
+    int* d_rawcnt = nullptr;                   // observation counts of the last fused sweep's raw map (the tail clears d_cnt)
+    bool rawcnt_valid = false;
+    unsigned long long* d_scan_state = nullptr; // block totals of k_cell_scan
+    bool stats_clean = false;                  // statistics / counts / far bits are all zero (the fused tail leaves them so)
     int* d_remap = nullptr;             // label of the last sweep -> label in the current map
     int* d_klab = nullptr;              // raw label of each kept landmark (fast tail)
     int traj_T = 0, traj_K = 0; double* d_x0s = nullptr;   // batch of independent trajectories laid end to end (icmslam_set_batch)
     double* d_aobs = nullptr; int* d_ac = nullptr;   // icmslam_associate: one scan's observations (2 x ASSOC_MAX_OBS) and labels
     double* d_nnd2 = nullptr;
     double thr1sq = 0.0;
-    struct GraphSlot { cudaGraphExec_t exec = nullptr; const double* src = nullptr; const double* map_in = nullptr; double x0[3] = {0, 0, 0}; double tol = 0; int maxit = 0; };
+    struct GraphSlot { cudaGraphExec_t exec = nullptr; const double* src = nullptr; const double* map_in = nullptr; double x0[3] = {0, 0, 0}; double tol = 0; int maxit = 0; int lm = 0; };
     GraphSlot graphs[4];
     int use_graph = 1, graph_launches = 0;
     int runs_occ = 24;           // resident one-warp blocks per SM k_runs is compiled for (24: 80 registers; ICMSLAM_RUNS_OCC=32: 64)
@@ -211,13 +219,14 @@ extern "C" int icmslam_destroy(icmslam_handle* h)
     DFREE(h->d_st); DFREE(h->d_cub); DFREE(h->d_sort_ws);
     DFREE(h->d_exch); DFREE(h->d_fg_cnt); DFREE(h->d_fg_start); DFREE(h->d_fg_idx);
     DFREE(h->d_fg_pts); DFREE(h->d_fg_geom); DFREE(h->d_bb); DFREE(h->d_ts); DFREE(h->d_seg_rec);
-    DFREE(h->d_lmrec); DFREE(h->d_remap); DFREE(h->d_nnd2); DFREE(h->d_klab); DFREE(h->d_aobs); DFREE(h->d_ac);
+    DFREE(h->d_lmrec2[0]); DFREE(h->d_lmrec2[1]); DFREE(h->d_blk_kept); DFREE(h->d_rawcnt); DFREE(h->d_scan_state); DFREE(h->d_remap); DFREE(h->d_nnd2); DFREE(h->d_klab); DFREE(h->d_aobs); DFREE(h->d_ac);
     if (h->h_st) cudaFreeHost(h->h_st);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_tail) cudaEventDestroy(h->ev_tail);
     delete h;
     return ICMSLAM_OK;
 }
@@ -318,15 +327,22 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     if (e == cudaSuccess) e = dalloc(&h->d_bb, 4);
     if (e == cudaSuccess) e = dalloc(&h->d_ts, 1);
     if (e == cudaSuccess) e = dalloc(&h->d_seg_rec, SEG_REC);
-    if (e == cudaSuccess) e = dalloc(&h->d_lmrec, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_lmrec2[0], L);
+    if (e == cudaSuccess) e = dalloc(&h->d_lmrec2[1], L);
+    if (e == cudaSuccess) e = dalloc(&h->d_blk_kept, (size_t)nblk((int)L, 256) + 1);
+    if (e == cudaSuccess) e = dalloc(&h->d_rawcnt, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_scan_state, (size_t)nblk(h->fg_cells + 1, CS_THREADS * CS_ITEMS) + 1);
     if (e == cudaSuccess) e = dalloc(&h->d_remap, L);
     if (e == cudaSuccess) e = dalloc(&h->d_klab, L);
     if (e == cudaSuccess) e = dalloc(&h->d_aobs, (size_t)2 * ASSOC_MAX_OBS);
     if (e == cudaSuccess) e = dalloc(&h->d_ac, (size_t)ASSOC_MAX_OBS);
     if (e == cudaSuccess) e = dalloc(&h->d_nnd2, L);
-    if (e == cudaSuccess) e = cudaMemset(h->d_lmrec, 0, L * sizeof(LmRec));
+    if (e == cudaSuccess) e = cudaMemset(h->d_lmrec2[0], 0, L * sizeof(LmRec));
+    if (e == cudaSuccess) e = cudaMemset(h->d_lmrec2[1], 0, L * sizeof(LmRec));
+    if (e == cudaSuccess) e = cudaMemset(h->d_scan_state, 0, ((size_t)nblk(h->fg_cells + 1, CS_THREADS * CS_ITEMS) + 1) * sizeof(unsigned long long));
     { const double t1 = cfg->dist_thr * (1.0 + 9.5367431640625e-07); h->thr1sq = t1 * t1; }
     if (e == cudaSuccess) e = cudaMemset(h->d_ts, 0, sizeof(TailState));
+    if (e == cudaSuccess) { const unsigned one = 1u; e = cudaMemcpy(&h->d_ts->scan_seq, &one, sizeof one, cudaMemcpyHostToDevice); }
     { const char* eg = getenv("ICMSLAM_GRAPH"); if (eg) h->use_graph = atoi(eg); }
     { const char* er = getenv("ICMSLAM_RUNS"); if (er) h->use_runs = atoi(er) != 0; }
     { const char* er = getenv("ICMSLAM_SOLVE_OCC"); if (er && (atoi(er) == 4 || atoi(er) == 6)) h->solve_occ = atoi(er); }
@@ -353,15 +369,16 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     if (e == cudaSuccess) e = dalloc(&h->d_st, 1);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_st, sizeof(DevState));
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) h->stream = h->own_stream;
-    if (e == cudaSuccess) {     // lowest priority: the tail's tiny kernels on the main stream are dispatched ahead of the solve's waves
-        int lo = 0, hi = 0;
+    if (e == cudaSuccess) {     // the tail's small kernels (main stream, highest priority) are dispatched ahead of the waves of the solve
+        int lo = 0, hi = 0;     // (side stream, lowest): with equal priorities the solve's pending blocks keep the tail out until it ends
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        e = cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, lo);
+        e = cudaStreamCreateWithPriority(&h->own_stream, cudaStreamNonBlocking, hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, lo);
     }
+    if (e == cudaSuccess) h->stream = h->own_stream;
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_tail, cudaEventDisableTiming);
     { const char* eo = getenv("ICMSLAM_OVERLAP"); if (eo) h->overlap_solve = atoi(eo) != 0; }
     if (e == cudaSuccess) e = cudaMemset(h->d_st, 0, sizeof(DevState));
     if (e == cudaSuccess) e = cudaMemset(h->d_counts, 0, L * sizeof(double));
@@ -497,6 +514,8 @@ extern "C" int icmslam_extract(icmslam_handle* h)
     DFREE(h->d_tile_flag); DFREE(h->d_dirty_list); DFREE(h->d_scan_dirty); DFREE(h->d_tile_slots); DFREE(h->d_tile_nslots); DFREE(h->d_tile_perm); DFREE(h->d_pos_nruns);
     {   // run records and their bookkeeping (runs.cuh): slice s (32 scans) owns slots [s * maxr * 32, (s + 1) * maxr * 32)
         const size_t nt = (size_t)nblk(T + 1, RT_TILE) + 2;      // (+1 scan: a segment's tiling may start one scan earlier)
+        h->n_tiles_alloc = (int)nt;
+        h->stats_clean = false;
         h->rec_maxr = h->max_per_scan > 0 ? h->max_per_scan : 1;
         h->rec_slots = (int64_t)(nt * RT_SLICES) * h->rec_maxr * 32;
         CK(dalloc(&h->d_rec_sb, (size_t)h->rec_slots)); CK(dalloc(&h->d_rec_meta, (size_t)h->rec_slots));
@@ -709,19 +728,13 @@ static int run_filter(icmslam_handle* h, const double* raw_x, const double* raw_
     return ICMSLAM_OK;
 }
 
+// (a fused sweep on a map whose grid is in place does without this launch: k_runs' first block resets the sweep's state,
+// tail.cuh sweep_begin_state, and the tail's last block has left the two counters at zero)
 __global__ void k_sweep_begin(DevState* st, TailState* ts, int L_in)
 {
     ts->far_count = 0;
     ts->n_dirty = 0;
-    st->cambio[0] = INFINITY; st->cambio[1] = 0.0; st->cambio[2] = 0.0; st->cambio_unres = 0;
-    st->lact0 = st->lact;
-    st->lsearch = min(st->lact, L_in);
-    st->raw_l = st->lact;
-    st->status = ST_OK;
-    st->n_far_scans = 0;
-    st->newton_iters = 0ull;
-    st->solved = 0ull;
-    st->dirty_tiles = 0;
+    sweep_begin_state(st, L_in);
 }
 
 static int status_from_state(const DevState* s)
@@ -785,6 +798,19 @@ static int ensure_ppar(icmslam_handle* h, const double* x, int64_t ldx, const do
     return ICMSLAM_OK;
 }
 
+// The fused tail zeroes the landmark statistics, the observation counts and the far bits as it consumes them; anything else that
+// wrote them (the reference-mode sweep, pass 0, a fresh extraction) leaves a memset to the next fused sweep.
+static int ensure_stats_clean(icmslam_handle* h)
+{
+    if (h->stats_clean) return ICMSLAM_OK;
+    cudaStream_t s = h->stream;
+    CK(cudaMemsetAsync(h->d_cnt, 0, ((size_t)h->Lcap + 1) * sizeof(int), s));
+    if (h->d_fsum_x) CK(cudaMemsetAsync(h->d_fsum_x, 0, (size_t)2 * h->Lcap * sizeof(long long), s));
+    if (h->d_farbits) CK(cudaMemsetAsync(h->d_farbits, 0, (size_t)h->n_tiles_alloc * 4 * sizeof(unsigned), s));
+    h->stats_clean = true;
+    return ICMSLAM_OK;
+}
+
 // ---- the fused (REDBLACK, NEWTON, PREV) sweep in three parts; a time-segmented run (one segment per GPU)
 // exchanges data with the other segments between them ----------------------------------------------------
 // part A: (grid of the previous map if it is not there yet) + the run kernel + the association kernel over the tiles the run
@@ -802,7 +828,7 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
         int rc = build_fgrid(h, min_x, min_y, &st->lsearch, n_search_cap);
         if (rc) return rc;
         k_lmrec_build<<<nblk(n_search_cap, 256), 256, 0, s>>>(min_x, min_y, &st->lsearch, h->d_fg_geom, h->d_fg_start, h->d_fg_pts, h->d_fg_idx,
-                                                              h->thr1sq, h->thr2_hi, h->d_lmrec);
+                                                              h->thr1sq, h->thr2_hi, h->d_lmrec2[h->lm_cur]);
         CK(cudaGetLastError());
         k_epoch_bump<<<1, 1, 0, s>>>(h->d_ts);      // a map from outside: its labels are a new numbering, run records are void
         CK(cudaGetLastError());
@@ -818,25 +844,26 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
     }
     const int t_start = h->seg_lo - (h->seg_first ? 0 : 1);     // a later segment also forms the moments of its odd halo pose
     RunParams R;
-    R.t_start = t_start; R.t_hi = h->seg_hi; R.halo_t = h->seg_first ? -1 : t_start; R.maxr = h->rec_maxr; R.ppar = pp_in; R.lmrec = h->d_lmrec;
+    R.t_start = t_start; R.t_hi = h->seg_hi; R.halo_t = h->seg_first ? -1 : t_start; R.maxr = h->rec_maxr; R.ppar = pp_in; R.lmrec = h->d_lmrec2[h->lm_cur];
     R.rec_sb = h->d_rec_sb; R.rec_meta = h->d_rec_meta; R.nruns = h->d_nruns; R.tile_perm = h->d_tile_perm; R.pos_nruns = h->d_pos_nruns; R.tile_epoch = h->d_tile_epoch; R.dyn = h->d_dyn;
     R.fsum_x = h->d_fsum_x; R.fsum_y = h->d_fsum_y; R.cnt = h->d_cnt; R.fix_scale = h->fix_scale; R.tile_slots = h->d_tile_slots; R.tile_nslots = h->d_tile_nslots;
     R.far_list = h->d_far_list; R.ts = h->d_ts; R.farbits = h->d_farbits;
     R.scan_dirty = h->d_scan_dirty; R.tile_flag = h->d_tile_flag; R.dirty_list = h->d_dirty_list;
     R.geom = h->d_fg_geom; R.cell_start = h->d_fg_start; R.gpts = h->d_fg_pts; R.dist_thr = h->dcfg.dist_thr;
+    R.st = st; R.L_in = h->begin_L;
     AssocParams A;
     A.first_halo = h->seg_first ? 0 : 1; A.T = T; A.off = h->d_off; A.bxy = h->d_bxy; A.cfg = h->dcfg; A.thr2_hi = h->thr2_hi; A.st = st; A.geom = h->d_fg_geom;
     A.cell_start = h->d_fg_start; A.gpts = h->d_fg_pts; A.gidx = h->d_fg_idx; A.remap = h->d_remap;
     { const char* eh = getenv("ICMSLAM_HINTS"); A.skip_hints = (eh && atoi(eh) == 0) ? 1 : 0; }
     A.hints = (h->hint_map == h->d_map_in) ? 1 : 0;
     A.c = h->d_c; A.obs_cap = h->obs_cap; A.R = R;
-    CK(cudaMemsetAsync(h->d_farbits, 0, (size_t)h->n_tiles * 4 * sizeof(unsigned), s));
+    A.n_tiles = h->n_tiles; A.blk_prefix = h->d_blk_prefix; A.Lcap = L; A.bb = h->d_bb; A.stw = st;
     if (timing) CK(cudaEventRecord(h->ev[0], s));
     if (h->use_runs) {
         if (h->runs_occ == 32) k_runs<32><<<h->n_tiles * RT_SLICES, RUNS_THREADS, 0, s>>>(R);
         else k_runs<24><<<h->n_tiles * RT_SLICES, RUNS_THREADS, 0, s>>>(R);
     } else {
-        k_all_dirty<<<nblk(h->n_tiles, 256), 256, 0, s>>>(h->d_tile_flag, h->d_dirty_list, h->d_ts, h->n_tiles);
+        k_all_dirty<<<nblk(h->n_tiles, 256), 256, 0, s>>>(h->d_tile_flag, h->d_dirty_list, h->d_ts, h->n_tiles, st, h->begin_L);
     }
     CK(cudaGetLastError());
     if (timing) CK(cudaEventRecord(h->ev[2], s));
@@ -878,18 +905,15 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
         h->ppar_of = kout;      // the solve leaves the projection parameters of the new poses (all columns but a segment's halo)
     }
     if (timing) CK(cudaEventRecord(h->ev[1], s));
-    k_tail_scan<<<1, 1024, 0, s>>>(h->d_farbits, h->n_tiles, h->d_blk_prefix, st, h->d_ts, L, h->d_bb);
-    CK(cudaGetLastError());
-    h->n_launch += 1;
     return ICMSLAM_OK;
 }
 
 // part B: the sweep's new labels (needs the label numbering: on several GPUs, after the exchange)
-static int fused_part_b(icmslam_handle* h)
+static int fused_part_b(icmslam_handle* h, cudaStream_t s)
 {
     const int L = h->Lcap;
     const int t_start = h->seg_lo - (h->seg_first ? 0 : 1);
-    k_tail_labels<<<148, 256, 0, h->stream>>>(h->d_ts, h->d_far_list, h->d_blk_prefix, h->d_farbits, RT_TILE, t_start, h->d_off, h->d_st, L, h->d_c,
+    k_tail_labels<<<148, 256, 0, s>>>(h->d_ts, h->d_far_list, h->d_blk_prefix, h->d_farbits, RT_TILE, t_start, h->d_off, h->d_st, L, h->d_c,
                                               h->d_newraw, h->d_newraw + L, h->d_cnt);
     CK(cudaGetLastError());
     h->n_launch += 1;
@@ -897,10 +921,9 @@ static int fused_part_b(icmslam_handle* h)
 }
 
 // part C: landmark update, Mapa.filtrar and the grid of the new map (needs the statistics of ALL segments)
-static int fused_part_c(icmslam_handle* h, double* dmap_out, int out_cap, int64_t out_ld)
+static int fused_part_c(icmslam_handle* h, double* dmap_out, int out_cap, int64_t out_ld, cudaStream_t s)
 {
     const int L = h->Lcap;
-    cudaStream_t s = h->stream;
     DevState* st = h->d_st;
     TailState* ts = h->d_ts;
     const double* min_x = h->d_map_in;
@@ -908,34 +931,32 @@ static int fused_part_c(icmslam_handle* h, double* dmap_out, int out_cap, int64_
     double* raw_x = h->d_raw;
     double* raw_y = h->d_raw + L;
     k_fused_means<<<nblk(L, 256), 256, 0, s>>>(st, h->d_fsum_x, h->d_fsum_y, h->d_cnt, min_x, min_y, 1.0 / h->fix_scale, h->dcfg.cota,
-                                               h->d_newraw, raw_x, raw_y, h->d_kflag, L);
+                                               h->d_newraw, raw_x, raw_y, h->d_kflag, L, h->d_blk_kept, h->d_farbits, h->n_tiles * 4);
     CK(cudaGetLastError());
-    int rc = exclusive_sum(h, h->d_kflag, h->d_kpos, L);
-    if (rc) return rc;
-    k_tail_compact<<<nblk(L, 256), 256, 0, s>>>(st, ts, h->d_kflag, h->d_kpos, raw_x, raw_y, h->d_cnt, h->d_kx, h->d_ky, h->d_kc,
-                                                h->d_parent, h->d_bb, L, h->d_klab);
+    k_tail_compact<<<nblk(L, 256), 256, 0, s>>>(st, h->d_kflag, h->d_blk_kept, h->d_kpos, raw_x, raw_y, h->d_cnt, h->d_kx, h->d_ky, h->d_kc,
+                                                h->d_parent, h->d_bb, L, h->d_klab, h->d_rawcnt);
     CK(cudaGetLastError());
-    k_tail_geom<<<1, 1, 0, s>>>(h->d_bb, st, ts, h->dcfg.dist_thr, h->fg_cells, h->d_fg_geom);
+    k_tail_count<<<nblk(L, 256), 256, 0, s>>>(h->d_kx, h->d_ky, st, ts, h->d_bb, h->dcfg.dist_thr, h->fg_cells, h->d_fg_geom, h->d_fg_cnt);
     CK(cudaGetLastError());
-    k_fgrid_count<<<nblk(L, 256), 256, 0, s>>>(h->d_kx, h->d_ky, &st->kept, h->d_fg_geom, h->d_fg_cnt);
+    k_cell_scan<<<nblk(h->fg_cells + 1, CS_THREADS * CS_ITEMS), CS_THREADS, 0, s>>>(h->d_fg_cnt, h->d_fg_start, h->fg_cells + 1, h->d_scan_state, ts);
     CK(cudaGetLastError());
-    rc = exclusive_sum(h, h->d_fg_cnt, h->d_fg_start, h->fg_cells + 1);
-    if (rc) return rc;
     k_fgrid_fill<<<nblk(L, 256), 256, 0, s>>>(h->d_kx, h->d_ky, &st->kept, h->d_fg_geom, h->d_fg_start, h->d_fg_cnt, h->d_fg_pts,
                                               h->d_fg_idx);
     CK(cudaGetLastError());
-    k_tail_nn<<<nblk(L, 256), 256, 0, s>>>(st, ts, h->d_kx, h->d_ky, h->d_fg_geom, h->d_fg_start, h->d_fg_pts, h->d_fg_idx, h->thr2_lt,
-                                           h->d_nn, h->d_indflag, h->d_nnd2, L, h->d_klab, h->d_kc, h->d_lmrec);
-    CK(cudaGetLastError());
-    k_tail_finalize<<<nblk(L, 256), 256, 0, s>>>(st, ts, h->d_kx, h->d_ky, h->d_kc, dmap_out, out_cap, out_ld, h->d_counts, L, h->d_kflag,
-                                                 h->d_kpos, h->d_nnd2, h->thr1sq, h->thr2_hi, h->d_lmrec, h->d_remap);
-    CK(cudaGetLastError());
-    k_tail_slow<<<1, 1024, 0, s>>>(st, ts, h->dcfg.dist_thr, h->d_kx, h->d_ky, h->d_kc, h->d_parent, h->d_nn, h->d_indflag, h->d_indpos,
-                                   h->d_ind, h->d_lab, h->d_used, h->d_rank, h->d_ox, h->d_oy, h->d_oc, dmap_out, out_cap, out_ld,
-                                   h->d_counts, L, h->fg_cells, h->d_fg_geom, h->d_fg_cnt, h->d_fg_start, h->d_fg_pts, h->d_fg_idx,
-                                   h->d_kflag, h->d_kpos, h->thr1sq, h->thr2_hi, h->d_lmrec, h->d_remap);
-    CK(cudaGetLastError());
-    h->n_launch += 9;
+    {
+        SlowArgs sa;
+        sa.dist_thr = h->dcfg.dist_thr; sa.parent = h->d_parent; sa.ind_pos = h->d_indpos; sa.ind = h->d_ind; sa.lab = h->d_lab; sa.used = h->d_used;
+        sa.rank = h->d_rank; sa.ox = h->d_ox; sa.oy = h->d_oy; sa.oc = h->d_oc; sa.max_cells = h->fg_cells; sa.geom = h->d_fg_geom;
+        sa.cell_cnt = h->d_fg_cnt; sa.cell_start = h->d_fg_start; sa.pts = h->d_fg_pts; sa.gidx = h->d_fg_idx;
+        k_tail_nn<<<nblk(L, 256), 256, 0, s>>>(st, ts, h->d_kx, h->d_ky, h->d_kc, h->d_fg_geom, h->d_fg_start, h->d_fg_pts, h->d_fg_idx, h->thr2_lt,
+                                               h->d_nn, h->d_indflag, L, h->d_klab, h->d_kflag, h->d_kpos, h->d_lmrec2[h->lm_cur],
+                                               h->d_lmrec2[h->lm_cur ^ 1], dmap_out, out_cap, out_ld, h->d_counts, h->thr1sq, h->thr2_hi, h->d_remap, sa);
+        CK(cudaGetLastError());
+    }
+    h->lm_cur ^= 1;
+    h->stats_clean = true;
+    h->rawcnt_valid = true;
+    h->n_launch += 6;
     h->grid_map = (out_ld == L && out_cap == L) ? dmap_out : nullptr;   // the grid now indexes the new map
     h->hint_map = h->grid_map;                                          // ... and c[] / d_remap carry this sweep's labels into it
     h->timed_fused = true;
@@ -967,22 +988,40 @@ static int sweep_core(icmslam_handle* h, const double* xin, int64_t ldin, double
                            o.map_view == ICMSLAM_VIEW_PREV;
     const int n_search_cap = L_in < 0 ? L : (L_in > 0 ? L_in : 1);
 
-    k_sweep_begin<<<1, 1, 0, s>>>(st, h->d_ts, L_in < 0 ? L : L_in);
-    CK(cudaGetLastError());
-    h->n_launch += 1;
-    CK(cudaMemsetAsync(h->d_cnt, 0, ((size_t)L + 1) * sizeof(int), s));
+    h->begin_L = L_in < 0 ? L : L_in;
+    if (!(use_fused && h->grid_map == h->d_map_in)) {
+        k_sweep_begin<<<1, 1, 0, s>>>(st, h->d_ts, h->begin_L);
+        CK(cudaGetLastError());
+        h->n_launch += 1;
+    }
     int rc;
     if (use_fused) {
+        rc = ensure_stats_clean(h);
+        if (rc) return rc;
         double* kout = xout;
         int64_t kld = ldout;
         if (xin == xout) { kout = (xin == h->d_x2) ? h->d_x : h->d_x2; kld = T; }
         rc = fused_part_a(h, xin, ldin, kout, kld, x0, o, n_search_cap, /*overlap=*/kout == xout);
         if (rc) return rc;
         if (kout != xout) CK(cudaMemcpy2DAsync(xout, (size_t)ldout * 8, kout, (size_t)kld * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToDevice, s));
-        rc = fused_part_b(h);
+        // The tail's chain of small kernels runs beside the solve's waves only if the block scheduler prefers it: on the handle's
+        // own highest-priority stream (the solve is on the lowest-priority side stream).  A caller's stream joins both at the end.
+        cudaStream_t ts_ = s;
+        if (h->join_pending && h->own_stream && s != h->own_stream) {
+            ts_ = h->own_stream;
+            CK(cudaStreamWaitEvent(ts_, h->ev_fork, 0));
+        }
+        rc = fused_part_b(h, ts_);
         if (rc) return rc;
-        return fused_part_c(h, dmap_out, out_cap, out_ld);
+        rc = fused_part_c(h, dmap_out, out_cap, out_ld, ts_);
+        if (rc) return rc;
+        if (ts_ != s) { CK(cudaEventRecord(h->ev_tail, ts_)); CK(cudaStreamWaitEvent(s, h->ev_tail, 0)); }
+        return ICMSLAM_OK;
     } else {
+        h->stats_clean = false;
+        h->rawcnt_valid = false;
+        CK(cudaMemsetAsync(h->d_cnt, 0, ((size_t)L + 1) * sizeof(int), s));
+        CK(cudaMemsetAsync(h->d_counts, 0, (size_t)L * sizeof(double), s));
         if (xin != xout) CK(cudaMemcpy2DAsync(xout, (size_t)ldout * 8, xin, (size_t)ldin * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToDevice, s));
         double* dx = xout;
         const int64_t ldx = ldout;
@@ -1086,9 +1125,9 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
     CK(cudaSetDevice(h->cfg.device));
     const int T = h->T, L = h->Lcap;
     cudaStream_t s = h->stream;
-    // Mapa.clear_obs (sensors.py:133) happens before the early return of :137-139
-    CK(cudaMemsetAsync(h->d_counts, 0, (size_t)L * sizeof(double), s));
     if (h->first_empty) {   // sensors.py:137-139: inputs returned unchanged
+        // Mapa.clear_obs (sensors.py:133) happens before the early return of :137-139 (a sweep rewrites every count itself)
+        CK(cudaMemsetAsync(h->d_counts, 0, (size_t)L * sizeof(double), s));
         if (map_out && L_in > 0) {
             int w = L_in < cap_out ? L_in : cap_out;
             CK(cudaMemcpy2DAsync(map_out, (size_t)ld_map_out * 8, map_in, (size_t)ld_map_in * 8, (size_t)w * 8, 2, cudaMemcpyDefault, s));
@@ -1258,12 +1297,13 @@ extern "C" int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const
             int rc = ensure_ppar(h, src, T, x0, h->d_ppar[src == h->d_x2 ? 1 : 0]);
             if (rc) return rc;
         }
+        if (fused_mode) { int rc = ensure_stats_clean(h); if (rc) return rc; }
         if (graph_ok && h->grid_map == h->d_map_in) {
             // steady state: the whole sweep (memsets + 15 kernels) replays as one CUDA graph
             icmslam_handle::GraphSlot* slot = nullptr;
             for (auto& g : h->graphs)
                 if (g.exec && g.src == src && g.map_in == h->d_map_in && g.x0[0] == x0[0] && g.x0[1] == x0[1] && g.x0[2] == x0[2] &&
-                    g.tol == o.newton_tol && g.maxit == o.newton_maxit) slot = &g;
+                    g.tol == o.newton_tol && g.maxit == o.newton_maxit && g.lm == h->lm_cur) slot = &g;
             if (!slot) {
                 for (auto& g : h->graphs) if (!g.exec) { slot = &g; break; }
                 if (!slot) { drop_graphs(h); slot = &h->graphs[0]; }
@@ -1272,38 +1312,41 @@ extern "C" int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const
                 const double* pof = h->ppar_of;
                 const double* gm = h->grid_map;
                 const double* hm = h->hint_map;
+                const int lm = h->lm_cur;
                 CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-                int rc = cudaMemsetAsync(h->d_counts, 0, (size_t)L * sizeof(double), s) == cudaSuccess ? ICMSLAM_OK : ICMSLAM_ERR_CUDA;
-                if (!rc) rc = sweep_core(h, src, T, dst, T, x0, o, -1, h->d_map_out, L, L);
+                int rc = sweep_core(h, src, T, dst, T, x0, o, -1, h->d_map_out, L, L);
                 cudaError_t ce = cudaStreamEndCapture(s, &graph);
                 h->graph_launches = (int)(h->n_launch - nl0);
                 h->n_launch = nl0;
                 h->ppar_of = pof;
                 h->grid_map = gm;
                 h->hint_map = hm;
+                h->lm_cur = lm;
                 if (rc || ce != cudaSuccess || !graph) {
                     if (graph) cudaGraphDestroy(graph);
                     cudaGetLastError();
                     snprintf(h->err, sizeof h->err, "graph capture of the sweep failed (%s)", cudaGetErrorString(ce));
                     return rc ? rc : ICMSLAM_ERR_CUDA;
                 }
-                ce = cudaGraphInstantiate(&slot->exec, graph, 0);
+                ce = cudaGraphInstantiate(&slot->exec, graph, cudaGraphInstantiateFlagUseNodePriority);   // (nodes keep the priority of the stream they were captured on)
                 cudaGraphDestroy(graph);
                 if (ce != cudaSuccess) { slot->exec = nullptr; snprintf(h->err, sizeof h->err, "cudaGraphInstantiate: %s", cudaGetErrorString(ce)); return ICMSLAM_ERR_CUDA; }
                 slot->src = src; slot->map_in = h->d_map_in; slot->x0[0] = x0[0]; slot->x0[1] = x0[1]; slot->x0[2] = x0[2];
-                slot->tol = o.newton_tol; slot->maxit = o.newton_maxit;
+                slot->tol = o.newton_tol; slot->maxit = o.newton_maxit; slot->lm = lm;
             }
             CK(cudaGraphLaunch(slot->exec, s));
             h->n_launch += h->graph_launches;    // kernels of this library inside the graph
             h->ppar_of = dst;
             h->grid_map = h->d_map_out;
             h->hint_map = h->d_map_out;
+            h->lm_cur ^= 1;
+            h->stats_clean = true;
+            h->rawcnt_valid = true;
             h->timed_fused = true;
             h->lact_dirty = true;
             launched = true;
         }
         if (!launched) {
-            CK(cudaMemsetAsync(h->d_counts, 0, (size_t)L * sizeof(double), s));
             int rc = sweep_core(h, src, T, dst, T, x0, o, -1, h->d_map_out, L, L);
             if (rc) return rc;
         }
@@ -1396,11 +1439,14 @@ extern "C" int icmslam_seg_begin(icmslam_handle* h, const double* x0, const icms
     if (h->seg_last && h->last_empty && T > 1) return ICMSLAM_ERR_EMPTY_LAST;
     double* src = h->x_cur ? h->d_x2 : h->d_x;
     double* dst = h->x_cur ? h->d_x : h->d_x2;
-    CK(cudaMemsetAsync(h->d_counts, 0, (size_t)L * sizeof(double), s));
-    k_sweep_begin<<<1, 1, 0, s>>>(h->d_st, h->d_ts, L);
-    CK(cudaGetLastError());
-    CK(cudaMemsetAsync(h->d_cnt, 0, ((size_t)L + 1) * sizeof(int), s));
-    int rc = fused_part_a(h, src, T, dst, T, x0, o, L);
+    int rc = ensure_stats_clean(h);
+    if (rc) return rc;
+    h->begin_L = L;
+    if (h->grid_map != h->d_map_in) {
+        k_sweep_begin<<<1, 1, 0, s>>>(h->d_st, h->d_ts, L);
+        CK(cudaGetLastError());
+    }
+    rc = fused_part_a(h, src, T, dst, T, x0, o, L);
     if (rc) return rc;
     k_seg_pack<<<1, 32, 0, s>>>(dst, T, h->seg_lo, h->seg_hi, h->d_ts, h->d_seg_rec);
     CK(cudaGetLastError());
@@ -1420,7 +1466,7 @@ extern "C" int icmslam_seg_exchange(icmslam_handle* h, const double* gathered, i
                                           h->d_ppar[h->seg_dst == h->d_x2 ? 1 : 0]);
     CK(cudaGetLastError());
     h->n_launch += 1;
-    return fused_part_b(h);
+    return fused_part_b(h, h->stream);
 }
 
 // part 3: landmark update + Mapa.filtrar on the reduced statistics (identical on every segment).
@@ -1429,7 +1475,7 @@ extern "C" int icmslam_seg_finish(icmslam_handle* h)
     if (!h || !h->seg_dst) return ICMSLAM_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));
     const int L = h->Lcap;
-    int rc = fused_part_c(h, h->d_map_out, L, L);
+    int rc = fused_part_c(h, h->d_map_out, L, L, h->stream);
     if (rc) return rc;
     h->seg_dst = nullptr;
     h->x_cur ^= 1;
@@ -1509,7 +1555,7 @@ extern "C" int icmslam_get_raw_map(icmslam_handle* h, double* raw_map, int32_t c
     if (raw_map && w > 0)
         CK(cudaMemcpy2DAsync(raw_map, (size_t)ld * 8, h->d_raw, (size_t)h->Lcap * 8, (size_t)w * 8, 2, cudaMemcpyDefault, h->stream));
     if (raw_counts && w > 0) {
-        k_counts_to_double<<<nblk(w, 256), 256, 0, h->stream>>>(h->d_cnt, w, h->d_tmp_a);
+        k_counts_to_double<<<nblk(w, 256), 256, 0, h->stream>>>(h->rawcnt_valid ? h->d_rawcnt : h->d_cnt, w, h->d_tmp_a);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(raw_counts, h->d_tmp_a, (size_t)w * 8, cudaMemcpyDefault, h->stream));
     }
@@ -1851,6 +1897,8 @@ extern "C" int icmslam_pass0(icmslam_handle* h, const double* x0, double* x, int
     h->x_cur = 0;
     h->ppar_of = nullptr;
     // ---- Mapa.filtrar on the map that was built (sensors.py:99-100) ---------------------------------------------------
+    h->stats_clean = false;
+    h->rawcnt_valid = false;
     k_counts_to_int<<<nblk(L, 256), 256, 0, s>>>(h->d_tmp_b, L, h->d_cnt);      // (get_raw_map reports integer counts)
     CK(cudaGetLastError());
     k_flags_from_counts<<<nblk(L, 256), 256, 0, s>>>(h->d_tmp_b, lact, h->dcfg.cota, h->d_kflag, L);

@@ -98,6 +98,7 @@ struct RunParams {
     double fix_scale;
     int* tile_slots; int* tile_nslots;    // RS_SLOTS labels per tile: which landmark each slot of its statistics table stands for; slots in use
     FarRec* far_list; TailState* ts; unsigned* farbits;   // scans with far observations (each creates one label)
+    DevState* st; int L_in;                               // the sweep's state, reset by the first block (tail.cuh sweep_begin_state)
     int* scan_dirty; int* tile_flag; int* dirty_list;     // steady state: what failed validation (tile_flag: 1 some scans, 2 all)
     const FGeom* geom; const int* cell_start; const double2* gpts;   // the landmark grid (fastgrid.cuh), for the far runs
     double dist_thr;
@@ -318,6 +319,7 @@ k_runs(const RunParams p)
     __shared__ TileSmem S;
     __shared__ SliceRing ring;
     const int slice = blockIdx.x, tile = slice / RT_SLICES;
+    if (slice == 0 && threadIdx.x == 0) sweep_begin_state(p.st, p.L_in);      // (nothing in this launch reads it)
     const int nslots = p.tile_nslots[tile];
     if (p.tile_epoch[tile] != p.ts->epoch) {      // no records for this label numbering: the whole tile goes to the association kernel
         if (threadIdx.x == 0 && slice == tile * RT_SLICES) { p.tile_flag[tile] = 2; p.dirty_list[atomicAdd(&p.ts->n_dirty, 1)] = tile; }
@@ -330,9 +332,9 @@ k_runs(const RunParams p)
 }
 
 // every tile to the association kernel (ICMSLAM_RUNS=0: no steady-state shortcut)
-__global__ void k_all_dirty(int* __restrict__ tile_flag, int* __restrict__ dirty_list, TailState* ts, int n_tiles)
+__global__ void k_all_dirty(int* __restrict__ tile_flag, int* __restrict__ dirty_list, TailState* ts, int n_tiles, DevState* st, int L_in)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_tiles) { tile_flag[i] = 2; dirty_list[i] = i; }
-    if (i == 0) ts->n_dirty = n_tiles;
+    if (i == 0) { ts->n_dirty = n_tiles; sweep_begin_state(st, L_in); }
 }

@@ -4,17 +4,21 @@
 // graph, and so that the landmark grid built for the filter's neighbour search IS the association
 // grid of the next sweep (same points: the filtered map).
 //
-//   k_tail_scan      exclusive scan of the per-tile counts of scans with far observations
+//   far_scan_block   (by the last block of the association kernel to finish) exclusive scan of the per-tile counts of
+//                    scans with far observations
 //   k_tail_labels    one thread per far scan: label = lact0 + rank in time order (ICM_SLAM.py:174-182),
 //                    statistics of the new label, rewrite of the scan's far labels
-//   k_fused_means    raw map from the fixed-point statistics + keep flags (cota, :231-239)
-//   [cub scan]       positions of the kept landmarks
-//   k_tail_compact   kept landmarks -> dense arrays + bounding box
-//   k_fgrid_geom / k_fgrid_count / [cub scan] / k_fgrid_fill      (fastgrid.cuh)
-//   k_tail_nn        nearest other survivor of every survivor (:241-245) through the grid
-//   k_tail_finalize  nothing to merge: the survivors are the new map
-//   k_tail_slow      ONE block, only when something must be merged (or the map is degenerate): the
-//                    reference's sequential relabelling (:247-260) and a rebuild of the grid
+//   k_fused_means    raw map from the fixed-point statistics + keep flags (cota, :231-239) + kept landmarks per block
+//   k_tail_compact   positions of the kept landmarks (each block sums the counts of the blocks before it), kept
+//                    landmarks -> dense arrays + bounding box
+//   k_tail_count     geometry of the grid over the survivors + entries per cell
+//   k_cell_scan      single-pass exclusive scan of the cell counts (chained blocks)
+//   k_fgrid_fill     (fastgrid.cuh)
+//   k_tail_nn        nearest other survivor of every survivor (:241-245) through the grid; the survivors written as the
+//                    new map on the assumption that nothing merges; the LAST block to finish checks the assumption and
+//                    otherwise runs the reference's sequential relabelling (:247-260) and rebuilds the grid
+// The chain keeps its own inputs clean for the next sweep (statistics, counts, far bits are zeroed by the kernel that
+// consumes them last): a sweep needs no memset.
 #pragma once
 #include "common.cuh"
 #include "assoc.cuh"
@@ -38,6 +42,10 @@ struct TailState {
     int epoch;          // label-numbering epoch: run records (runs.cuh) built in another epoch are void; bumped whenever landmark
                         // indices change (a merge or a drop in Mapa.filtrar, a map supplied by the caller)
     int n_dirty;        // tiles the steady-state kernel handed to the association kernel this sweep
+    int assoc_ticket;   // blocks of the association kernel that have finished (the last one scans the far counts)
+    int nn_ticket;      // blocks of k_tail_nn that have finished (the last one closes the sweep)
+    int scan_ticket;    // blocks of k_cell_scan that have finished
+    unsigned scan_seq;  // launch number of k_cell_scan: tags the block totals published through global memory (starts at 1)
 };
 
 // A landmark as the fused kernel reads it by label: position and the squared radius inside which an
@@ -45,6 +53,21 @@ struct TailState {
 struct __align__(32) LmRec {
     double x, y, r2, r;     // r = sqrt(r2) rounded down: the radius the run records are certified against (runs.cuh)
 };
+
+// The per-sweep part of the device state (Mapa.clear_obs + the label bookkeeping of sensors.py:133-145): by k_sweep_begin, or by
+// the first block of the run kernel when the sweep is a link of a chain.
+__device__ __forceinline__ void sweep_begin_state(DevState* st, int L_in)
+{
+    st->cambio[0] = INFINITY; st->cambio[1] = 0.0; st->cambio[2] = 0.0; st->cambio_unres = 0;
+    st->lact0 = st->lact;
+    st->lsearch = min(st->lact, L_in);
+    st->raw_l = st->lact;
+    st->status = ST_OK;
+    st->n_far_scans = 0;
+    st->newton_iters = 0ull;
+    st->solved = 0ull;
+    st->dirty_tiles = 0;
+}
 
 // r2 = min(thr2_hi, (nnd/2)^2 (1 - 2^-30)) with nnd a lower bound of the distance to the nearest other
 // landmark: an observation with |obs - A|^2 <= r2 has |obs - B| >= nnd - |obs - A| > |obs - A| for every other
@@ -92,32 +115,57 @@ __device__ __forceinline__ int tile_far_count(const unsigned* __restrict__ farbi
     return __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
 }
 
-__global__ void __launch_bounds__(1024)
-k_tail_scan(const unsigned* __restrict__ farbits, int nblk_, int* __restrict__ blk_prefix, DevState* st, TailState* ts, int Lcap,
-            unsigned long long* bb)
+__device__ __forceinline__ int tile_far_count_cg(const unsigned* farbits, int i)     // (written by other blocks of the same launch)
 {
-    __shared__ int wsum[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (nblk_ + 1023) / 1024;
-    const int lo = min(tid * per, nblk_), hi = min(lo + per, nblk_);
-    int s = 0;
-    for (int i = lo; i < hi; ++i) s += tile_far_count(farbits, i);
-    int inc = s;
+    const uint4 w = __ldcg(reinterpret_cast<const uint4*>(farbits + (size_t)i * 4));
+    return __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+}
+
+// One block: exclusive scan over the tiles of the number of label-creating scans, and the sweep's label bookkeeping.
+// The counts are first gathered into shared memory (cntb, cap bytes; every thread keeps 8 independent loads in flight), then
+// each thread scans a contiguous range of them.  With at most FAR_DIRECT label-creating scans (every steady-state sweep) the
+// scan is skipped: k_tail_labels counts the bits before each of them itself, and the total is the number of far records.
+#define FAR_DIRECT 64
+__device__ void far_scan_block(const unsigned* farbits, int n, int* __restrict__ blk_prefix, DevState* st, TailState* ts, int Lcap,
+                               unsigned long long* bb, int* wsum /* >= 32 ints of shared memory */, unsigned char* cntb, int cap)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nth = blockDim.x, nw = nth >> 5;
+    int carry = 0;
+    const int nrec = *(volatile int*)&ts->far_count;
+    if (nrec <= FAR_DIRECT) { carry = nrec; n = 0; }
+    for (int s0 = 0; s0 < n; s0 += cap) {
+        const int m = min(cap, n - s0);
+        for (int i0 = tid; i0 < m; i0 += 8 * nth) {
+            int c[8];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(FULLMASK, inc, d); if (lane >= d) inc += o; }
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        int v = wsum[lane];
+            for (int k = 0; k < 8; ++k) { const int i = i0 + k * nth; c[k] = i < m ? tile_far_count_cg(farbits, s0 + i) : 0; }
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(FULLMASK, v, d); if (lane >= d) v += o; }
-        wsum[lane] = v;
+            for (int k = 0; k < 8; ++k) { const int i = i0 + k * nth; if (i < m) cntb[i] = (unsigned char)c[k]; }     // (<= 128)
+        }
+        __syncthreads();
+        const int per = (m + nth - 1) / nth;
+        const int lo = min(tid * per, m), hi = min(lo + per, m);
+        int sum = 0;
+        for (int i = lo; i < hi; ++i) sum += cntb[i];
+        int inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULLMASK, inc, d); if (lane >= d) inc += o; }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int x = lane < nw ? wsum[lane] : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULLMASK, x, d); if (lane >= d) x += o; }
+            wsum[lane] = x;
+        }
+        __syncthreads();
+        int run = carry + inc - sum + (warp ? wsum[warp - 1] : 0);
+        for (int i = lo; i < hi; ++i) { blk_prefix[s0 + i] = run; run += cntb[i]; }
+        carry += wsum[nw - 1];
+        __syncthreads();
     }
-    __syncthreads();
-    int run = inc - s + (warp ? wsum[warp - 1] : 0);
-    for (int i = lo; i < hi; ++i) { blk_prefix[i] = run; run += tile_far_count(farbits, i); }
     if (tid == 0) {
-        const int total = wsum[31];
+        const int total = carry;
         ts->far_total = total;
         ts->label_base = 0;
         st->n_far_scans = total;              // (a segmented run overwrites these three in k_seg_unpack)
@@ -130,27 +178,58 @@ k_tail_scan(const unsigned* __restrict__ farbits, int nblk_, int* __restrict__ b
     }
 }
 
+__device__ __forceinline__ void far_label_write(const FarRec& r, int label, int Lcap, double* __restrict__ raw_x, double* __restrict__ raw_y,
+                                                int* __restrict__ cnt)
+{
+    if (label >= Lcap) return;
+    raw_x[label] = r.sx / (double)r.n;
+    raw_y[label] = r.sy / (double)r.n;
+    cnt[label] = r.n;
+}
+
 __global__ void __launch_bounds__(256)
 k_tail_labels(const TailState* ts, const FarRec* __restrict__ far, const int* __restrict__ blk_prefix, const unsigned* __restrict__ farbits, int tile,
               int t_start, const int* __restrict__ off, const DevState* st, int Lcap, int* __restrict__ c, double* __restrict__ raw_x,
               double* __restrict__ raw_y, int* __restrict__ cnt)
 {
+    __shared__ int wsum[8];
     const int nrec = ts->far_count;
     const int lact0 = st->lact0 + ts->label_base;
+    // the scan's far observations: -1 from the association kernel, or the label an earlier sweep gave them when the scan
+    // was certified on its run records (labels >= lsearch are exactly the labels created inside a sweep)
+    const int ls = st->lsearch;
+    if (nrec <= FAR_DIRECT) {
+        // a block per record: rank in time order = label-creating scans of the tiles before its tile (counted here, all threads) +
+        // those of its tile before the scan
+        for (int k = blockIdx.x; k < nrec; k += gridDim.x) {
+            const FarRec r = far[k];
+            const int ti = (r.t - t_start) / tile, lt = (r.t - t_start) % tile;
+            int part = 0;
+            for (int i = threadIdx.x; i < ti; i += blockDim.x) part += tile_far_count(farbits, i);
+            part = warp_sum_i(part);
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = part;
+            __syncthreads();
+            int rank = __popc(farbits[(size_t)ti * 4 + (lt >> 5)] & ((1u << (lt & 31)) - 1u));
+            for (int q = 0; q < (lt >> 5); ++q) rank += __popc(farbits[(size_t)ti * 4 + q]);
+            for (int q = 0; q < (int)(blockDim.x >> 5); ++q) rank += wsum[q];
+            const int label = lact0 + rank;
+            if (label >= Lcap) continue;
+            if (threadIdx.x == 0) far_label_write(r, label, Lcap, raw_x, raw_y, cnt);
+            for (int i = off[r.t] + threadIdx.x; i < off[r.t + 1]; i += blockDim.x)
+                if (c[i] < 0 || c[i] >= ls) c[i] = label;
+        }
+        return;
+    }
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nrec; k += gridDim.x * blockDim.x) {
         const FarRec r = far[k];
         // rank in time order: label-creating scans of the tiles before this one + those of this tile before the scan
         const int ti = (r.t - t_start) / tile, lt = (r.t - t_start) % tile;
         int rank = __popc(farbits[(size_t)ti * 4 + (lt >> 5)] & ((1u << (lt & 31)) - 1u));
-        for (int k = 0; k < (lt >> 5); ++k) rank += __popc(farbits[(size_t)ti * 4 + k]);
+        for (int q = 0; q < (lt >> 5); ++q) rank += __popc(farbits[(size_t)ti * 4 + q]);
         const int label = lact0 + blk_prefix[ti] + rank;
         if (label >= Lcap) continue;
-        raw_x[label] = r.sx / (double)r.n;
-        raw_y[label] = r.sy / (double)r.n;
-        cnt[label] = r.n;
-        // the scan's far observations: -1 from the association kernel, or the label an earlier sweep gave them when the scan
-        // was certified on its run records (labels >= lsearch are exactly the labels created inside a sweep)
-        const int ls = st->lsearch;
+        far_label_write(r, label, Lcap, raw_x, raw_y, cnt);
         for (int i = off[r.t]; i < off[r.t + 1]; ++i)
             if (c[i] < 0 || c[i] >= ls) c[i] = label;
     }
@@ -163,10 +242,13 @@ k_fused_means(const DevState* st, long long* fsum_x, long long* fsum_y, const in
               const double* __restrict__ map_x, const double* __restrict__ map_y, double inv_scale, double cota,
               double* newraw /* 2 x Lcap: means of this sweep's new labels, zero elsewhere; cleared here.  ALIASES fsum_x / fsum_y
                                 (old labels use a word as int64 sum, new labels as double mean: disjoint index ranges) */,
-              double* __restrict__ raw_x, double* __restrict__ raw_y, int* __restrict__ flag, int Lcap)
+              double* __restrict__ raw_x, double* __restrict__ raw_y, int* __restrict__ flag, int Lcap, int* __restrict__ blk_kept,
+              unsigned* __restrict__ farbits, int n_far_words)
 {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= Lcap) return;
+    for (int wd = l; wd < n_far_words; wd += gridDim.x * blockDim.x) farbits[wd] = 0u;      // (k_tail_labels was their last reader)
+    int keep = 0;
+    if (l < Lcap) {
     const int raw_l = st->raw_l, ls = st->lsearch;
     const int k = l < raw_l ? cnt[l] : 0;
     if (l < ls) {
@@ -179,100 +261,252 @@ k_fused_means(const DevState* st, long long* fsum_x, long long* fsum_y, const in
     }
     newraw[l] = 0.0; newraw[Lcap + l] = 0.0;
     fsum_x[l] = 0; fsum_y[l] = 0;
-    flag[l] = (l < raw_l && !((double)k < cota)) ? 1 : 0;      // ICM_SLAM.py:232-236
+    keep = (l < raw_l && !((double)k < cota)) ? 1 : 0;      // ICM_SLAM.py:232-236
+    flag[l] = keep;
+    }
+    const int total = __syncthreads_count(keep);
+    if (threadIdx.x == 0) blk_kept[blockIdx.x] = total;
 }
 
-// kept landmarks -> dense (kx, ky, kc), union-find parents, bounding box (ordered-key atomics)
+// kept landmarks -> dense (kx, ky, kc), union-find parents, bounding box (ordered-key atomics, one set per block).  The position
+// of a kept landmark = kept landmarks of the blocks before this one (blk_kept, from k_fused_means' grid of the same shape) +
+// those before it in the block.  Clears the observation counts for the next sweep.
 __global__ void __launch_bounds__(256)
-k_tail_compact(DevState* st, TailState* ts, const int* __restrict__ flag, const int* __restrict__ pos, const double* __restrict__ raw_x,
-               const double* __restrict__ raw_y, const int* __restrict__ cnt, double* __restrict__ kx, double* __restrict__ ky,
-               double* __restrict__ kc, int* __restrict__ parent, unsigned long long* bb, int Lcap, int* __restrict__ klab)
+k_tail_compact(DevState* st, const int* __restrict__ flag, const int* __restrict__ blk_kept, int* __restrict__ pos,
+               const double* __restrict__ raw_x, const double* __restrict__ raw_y, int* __restrict__ cnt, double* __restrict__ kx,
+               double* __restrict__ ky, double* __restrict__ kc, int* __restrict__ parent, unsigned long long* bb, int Lcap,
+               int* __restrict__ klab, int* __restrict__ rawcnt)
 {
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ int wpart[8], wcnt[8];
+    __shared__ double red[4][8];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int l = blockIdx.x * blockDim.x + tid;
+    int part = 0;
+    for (int b = tid; b < (int)blockIdx.x; b += blockDim.x) part += blk_kept[b];
+    part = warp_sum_i(part);
+    const int f = l < Lcap ? flag[l] : 0;
+    const unsigned m = __ballot_sync(FULLMASK, f);
+    if (lane == 0) { wpart[w] = part; wcnt[w] = __popc(m); }
+    __syncthreads();
+    int p = __popc(m & ((1u << lane) - 1u));
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { p += wpart[k]; if (k < w) p += wcnt[k]; }
     double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
     if (l < Lcap) {
-        if (flag[l]) {
-            const int p = pos[l];
+        pos[l] = p;
+        const int k = cnt[l];
+        rawcnt[l] = k;
+        if (f) {
             const double x = raw_x[l], y = raw_y[l];
-            kx[p] = x; ky[p] = y; kc[p] = (double)cnt[l];
+            kx[p] = x; ky[p] = y; kc[p] = (double)k;
             parent[p] = p;
             klab[p] = l;
             mnx = mxx = x; mny = mxy = y;
         }
+        cnt[l] = 0;
         if (l == Lcap - 1) {
-            st->kept = pos[l] + flag[l];
+            cnt[Lcap] = 0;
+            st->kept = p + f;
             st->n_ind = 0;
-            if (st->kept == 0) st->status |= 4;   // ValueError in the reference (ICM_SLAM.py:241-255)
+            if (p + f == 0) st->status |= 4;   // ValueError in the reference (ICM_SLAM.py:241-255)
         }
     }
     mnx = warp_min(mnx); mny = warp_min(mny); mxx = warp_max(mxx); mxy = warp_max(mxy);
-    if ((threadIdx.x % WARP) == 0 && mnx <= mxx) {
-        atomicMin(bb + 0, dkey(mnx)); atomicMin(bb + 1, dkey(mny));
-        atomicMax(bb + 2, dkey(mxx)); atomicMax(bb + 3, dkey(mxy));
+    if (lane == 0) { red[0][w] = mnx; red[1][w] = mny; red[2][w] = mxx; red[3][w] = mxy; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+            mnx = fmin(mnx, red[0][k]); mny = fmin(mny, red[1][k]); mxx = fmax(mxx, red[2][k]); mxy = fmax(mxy, red[3][k]);
+        }
+        if (mnx <= mxx) {
+            atomicMin(bb + 0, dkey(mnx)); atomicMin(bb + 1, dkey(mny));
+            atomicMax(bb + 2, dkey(mxx)); atomicMax(bb + 3, dkey(mxy));
+        }
     }
 }
 
-// geometry of the grid over the kept landmarks + degeneracy test (extent < dist_thr)
-__global__ void k_tail_geom(const unsigned long long* bb, const DevState* st, TailState* ts, double dist_thr, int max_cells, FGeom* out)
+// geometry of the grid over the kept landmarks (every block derives it from the bounding box; block 0 records it, with the
+// degeneracy test: extent < dist_thr) and the number of entries of each cell
+__global__ void __launch_bounds__(256)
+k_tail_count(const double* __restrict__ kx, const double* __restrict__ ky, const DevState* st, TailState* ts, const unsigned long long* bb,
+             double dist_thr, int max_cells, FGeom* out, int* __restrict__ cell_cnt)
 {
+    __shared__ FGeom sg;
     const int n = st->kept;
-    double mnx = 0.0, mny = 0.0, mxx = 0.0, mxy = 0.0;
-    if (n > 0 && bb[0] != ~0ull) { mnx = dkey_inv(bb[0]); mny = dkey_inv(bb[1]); mxx = dkey_inv(bb[2]); mxy = dkey_inv(bb[3]); }
-    *out = fgrid_make_geom(mnx, mny, mxx, mxy, dist_thr, max_cells);
-    ts->degenerate = (fmax(mxx - mnx, mxy - mny) >= dist_thr) ? 0 : 1;
+    if (threadIdx.x == 0) {
+        double mnx = 0.0, mny = 0.0, mxx = 0.0, mxy = 0.0;
+        if (n > 0 && bb[0] != ~0ull) { mnx = dkey_inv(bb[0]); mny = dkey_inv(bb[1]); mxx = dkey_inv(bb[2]); mxy = dkey_inv(bb[3]); }
+        sg = fgrid_make_geom(mnx, mny, mxx, mxy, dist_thr, max_cells);
+        if (blockIdx.x == 0) { *out = sg; ts->degenerate = (fmax(mxx - mnx, mxy - mny) >= dist_thr) ? 0 : 1; }
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const FGeom g = sg;
+    int cx0, cx1, cy0, cy1;
+    fgrid_cell_range(g, kx[i], ky[i], cx0, cx1, cy0, cy1);
+    for (int cy = cy0; cy <= cy1; ++cy)
+        for (int cx = cx0; cx <= cx1; ++cx) atomicAdd(cell_cnt + cy * g.nx + cx, 1);
 }
 
-// nearest OTHER survivor (zero distances are never neighbours, ICM_SLAM.py:242) within dist_thr; and, for free, calc_cambio
-// (ICM_SLAM.py:490-495) of the new map against the previous one: the landmark a new landmark was updated from is its nearest
-// old landmark whenever it stayed inside that landmark's proven radius r (<= half the distance to any other old landmark:
-// |new - other| >= 2 r - d > d).  lmrec still holds the previous map here.
+// Exclusive scan of in[0..n) in one pass: a block scans its CS_THREADS * CS_ITEMS elements, publishes its total tagged with the
+// launch number, and adds up the totals of the blocks before it as they appear (blocks start in index order, so the ones waited
+// for are running or done).  The last block to finish advances the launch number.
+#define CS_THREADS 1024
+#define CS_ITEMS 8
+__global__ void __launch_bounds__(CS_THREADS)
+k_cell_scan(const int* __restrict__ in, int* __restrict__ out, int n, unsigned long long* state, TailState* ts)
+{
+    __shared__ int wsum[32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
+    const unsigned seq = *(volatile unsigned*)&ts->scan_seq;
+    const int i0 = (b * CS_THREADS + tid) * CS_ITEMS;
+    int v[CS_ITEMS];
+    if (i0 + CS_ITEMS <= n) {
+        const int4 a = *reinterpret_cast<const int4*>(in + i0), c = *reinterpret_cast<const int4*>(in + i0 + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < CS_ITEMS; ++k) v[k] = (i0 + k < n) ? in[i0 + k] : 0;
+    }
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < CS_ITEMS; ++k) s += v[k];
+    int inc = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULLMASK, inc, d); if (lane >= d) inc += o; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int x = wsum[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULLMASK, x, d); if (lane >= d) x += o; }
+        wsum[lane] = x;
+        const int total = __shfl_sync(FULLMASK, x, 31);
+        if (lane == 0) *(volatile unsigned long long*)(state + b) = ((unsigned long long)seq << 32) | (unsigned)total;
+        int acc = 0;
+        for (int p0 = 0; p0 < b; p0 += 32) {
+            const int pb = p0 + lane;
+            if (pb < b) {
+                unsigned long long wv;
+                do { wv = *(volatile unsigned long long*)(state + pb); } while ((unsigned)(wv >> 32) != seq);
+                acc += (int)(unsigned)wv;
+            }
+        }
+        acc = warp_sum_i(acc);
+        if (lane == 0) s_base = acc;
+    }
+    __syncthreads();
+    int run = s_base + (warp ? wsum[warp - 1] : 0) + inc - s;
+    if (i0 + CS_ITEMS <= n) {
+        int4 a, c;
+        a.x = run; run += v[0]; a.y = run; run += v[1]; a.z = run; run += v[2]; a.w = run; run += v[3];
+        c.x = run; run += v[4]; c.y = run; run += v[5]; c.z = run; run += v[6]; c.w = run;
+        *reinterpret_cast<int4*>(out + i0) = a; *reinterpret_cast<int4*>(out + i0 + 4) = c;
+    } else {
+#pragma unroll
+        for (int k = 0; k < CS_ITEMS; ++k) { if (i0 + k < n) out[i0 + k] = run; run += v[k]; }
+    }
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(&ts->scan_ticket, 1) == (int)gridDim.x - 1) { ts->scan_ticket = 0; ts->scan_seq = seq + 1u; }
+    }
+}
+
+// What the merge path (tail_slow_body) needs beyond the arguments of k_tail_nn.
+struct SlowArgs {
+    double dist_thr;
+    int* parent; int* ind_pos; int* ind; int* lab; int* used; int* rank;
+    double* ox; double* oy; double* oc;
+    int max_cells; FGeom* geom; int* cell_cnt; int* cell_start; double2* pts; int* gidx;
+};
+
+__device__ void tail_slow_body(DevState* st, TailState* ts, double dist_thr, double* kx, double* ky, double* kc, int* parent, int* nn, int* ind_flag,
+            int* ind_pos, int* ind, int* lab, int* used, int* rank, double* ox, double* oy, double* oc, double* map_out, int cap_out,
+            int64_t ld_out, double* counts_state, int Lcap, int max_cells, FGeom* geom, int* cell_cnt, int* cell_start, double2* pts, int* gidx,
+            const int* kflag, const int* kpos, double thr1sq, double thr2_hi, LmRec* lmrec, int* remap);
+
+// Nearest OTHER survivor (zero distances are never neighbours, ICM_SLAM.py:242) within dist_thr, searched in the 3 x 3 block
+// of cells around the survivor (three contiguous runs of the cell-sorted arrays, one per row of cells): the block holds
+// every landmark within 2 thr1, so the same pass yields the distance the hint radius is derived from (see
+// nearest_other_wide).  And, for free, calc_cambio (ICM_SLAM.py:490-495) of the new map against the previous one: the
+// landmark a new landmark was updated from is its nearest old landmark whenever it stayed inside that landmark's proven
+// radius r (<= half the distance to any other old landmark: |new - other| >= 2 r - d > d).
+// The survivors are written as the new map (count-weighted mean of one member, :258-260) on the assumption that nothing
+// merges; the last block to finish knows whether that held (n_ind == 0 and the map is not degenerate), closes the sweep's
+// bookkeeping and, if it did not, runs the reference's sequential relabelling over what the other blocks left.
 __global__ void __launch_bounds__(256)
-k_tail_nn(DevState* st, TailState* ts, const double* __restrict__ kx, const double* __restrict__ ky, const FGeom* __restrict__ geom,
-          const int* __restrict__ cell_start, const double2* __restrict__ pts, const int* __restrict__ idx, double thr2_lt,
-          int* __restrict__ nn, int* __restrict__ ind_flag, double* __restrict__ nnd2, int Lcap, const int* __restrict__ klab,
-          const double* __restrict__ kc, const LmRec* __restrict__ lmrec_old)
+k_tail_nn(DevState* st, TailState* ts, double* __restrict__ kx, double* __restrict__ ky, double* __restrict__ kc, const FGeom* geom,
+          const int* cell_start, const double2* pts, const int* idx, double thr2_lt, int* nn, int* ind_flag, int Lcap,
+          const int* __restrict__ klab, const int* __restrict__ kflag, const int* __restrict__ kpos, const LmRec* __restrict__ lmrec_old,
+          LmRec* lmrec_new, double* map_out, int cap_out, int64_t ld_out, double* counts_state, double thr1sq, double thr2_hi,
+          int* remap, const SlowArgs sa)
 {
     __shared__ double red[3][8];
     __shared__ int redn[2][8];
+    __shared__ int s_last, s_slow;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int K = st->kept;
     const bool act = j < Lcap && j < K && !ts->degenerate;
-    double cd = 0.0;
+    double cd = 0.0, wide = 0.0;
     int cres = 0, cun = 0, nind = 0;
-    if (j < Lcap && !act) { ind_flag[j] = 0; nnd2[j] = 0.0; if (j == 0 && K > 0) cun = K; }
+    if (j < Lcap && !act) { ind_flag[j] = 0; if (j == 0 && K > 0) cun = K; }
     if (act) {
         const int l = klab[j];
+        const double xj = kx[j], yj = ky[j];
         if (l < st->lsearch) {
             const LmRec o = lmrec_old[l];
             const double c = kc[j];
-            const double d = dist_rn(mul_rn(kx[j], c) / c - o.x, mul_rn(ky[j], c) / c - o.y);      // (the map's own rounding, k_tail_finalize)
+            const double d = dist_rn(mul_rn(xj, c) / c - o.x, mul_rn(yj, c) / c - o.y);      // (the map's own rounding, below)
             if (d < o.r * (1.0 - 1e-9)) { cres = 1; cd = d; }
         }
         cun = 1 - cres;
         const FGeom g = *geom;
-        const double xj = kx[j], yj = ky[j];
-        const int c = fgrid_cell(g, xj, yj);
-        const int s = cell_start[c], e = cell_start[c + 1];
+        int cx = __double2int_rd((xj - g.x0) * g.inv_h), cy = __double2int_rd((yj - g.y0) * g.inv_h);
+        cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1);
+        const int xa = max(cx - 1, 0), xb = min(cx + 1, g.nx - 1);
+        int rs[3], re[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int yy = cy - 1 + q;
+            const bool in = yy >= 0 && yy < g.ny;
+            rs[q] = in ? cell_start[yy * g.nx + xa] : 0;
+            re[q] = in ? cell_start[yy * g.nx + xb + 1] : 0;
+        }
         double best = INFINITY, lo = INFINITY, hi = INFINITY;
         int arg = -1;
-        for (int k = s; k < e; ++k) {
-            const double2 p = pts[k];
-            const int id = idx[k];
-            const double s2 = dist2_rn(p.x - xj, p.y - yj);
-            if (id == j || s2 == 0.0) continue;
-            bool take = s2 < lo;
-            if (!take && s2 <= hi && arg >= 0) {
-                const double dk = __dsqrt_rn(s2), db = __dsqrt_rn(best);
-                take = dk < db || (dk == db && id < arg);
+        wide = INFINITY;
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            for (int k = rs[q]; k < re[q]; ++k) {
+                const double2 p = pts[k];
+                const int id = idx[k];
+                if (id == j) continue;
+                const double s2 = dist2_rn(p.x - xj, p.y - yj);
+                wide = fmin(wide, s2);                  // (a coincident landmark gives 0: its hints are never trusted)
+                if (s2 == 0.0) continue;
+                bool take = s2 < lo;
+                if (!take && s2 <= hi && arg >= 0) {
+                    const double dk = __dsqrt_rn(s2), db = __dsqrt_rn(best);
+                    take = dk < db || (dk == db && id < arg);
+                }
+                if (take) { best = s2; arg = id; lo = s2 * (1.0 - 8.8817841970012523e-16); hi = s2 * (1.0 + 8.8817841970012523e-16); }
             }
-            if (take) { best = s2; arg = id; lo = s2 * (1.0 - 8.8817841970012523e-16); hi = s2 * (1.0 + 8.8817841970012523e-16); }
-        }
         const int f = (arg >= 0 && best <= thr2_lt) ? 1 : 0;      // amin < dist_thr (strict, :245)
         nn[j] = arg < 0 ? 0 : arg;
         ind_flag[j] = f;
-        // for the hint radius: the nearest other survivor within 2 thr1 (only searched when none is closer than the gate)
-        nnd2[j] = f ? best : nearest_other_wide(g, cell_start, pts, idx, j, xj, yj);
         nind = f;
+    }
+    if (j < Lcap) {      // the new map if nothing merges
+        const bool have = j < K;
+        const double c = have ? kc[j] : 0.0;
+        const double mx = have ? mul_rn(kx[j], c) / c : 0.0, my = have ? mul_rn(ky[j], c) / c : 0.0;
+        if (j < cap_out) { map_out[j] = mx; map_out[ld_out + j] = my; }
+        counts_state[j] = c;
+        LmRec rec;
+        rec.x = mx; rec.y = my; rec.r2 = act ? hint_radius2(wide, 4.0 * thr1sq, thr2_hi) : 0.0; rec.r = __dsqrt_rd(rec.r2);
+        lmrec_new[j] = rec;
+        remap[j] = (j < st->raw_l && kflag[j]) ? kpos[j] : -1;      // label of this sweep -> index in the new map
     }
     // block totals -> one set of atomics per block
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -287,33 +521,29 @@ k_tail_nn(DevState* st, TailState* ts, const double* __restrict__ kx, const doub
         if (a < INFINITY) { atomic_min_pos(st->cambio + 0, a); atomic_max_pos(st->cambio + 1, b); atomicAdd(st->cambio + 2, c); }
         if (u) atomicAdd(&st->cambio_unres, u);
         if (n2) atomicAdd(&ts->n_ind, n2);
+        __threadfence();
+        const int last = atomicAdd(&ts->nn_ticket, 1) == (int)gridDim.x - 1;
+        int slow = 0;
+        if (last) {      // every other block's results are in global memory
+            __threadfence();
+            ts->nn_ticket = 0;
+            ts->far_count = 0; ts->n_dirty = 0;      // (consumed by k_tail_labels / the association kernel: ready for the next sweep)
+            const int n_ind = atomicAdd(&ts->n_ind, 0);
+            slow = (n_ind != 0 || ts->degenerate) ? 1 : 0;
+            // every old label survived in place (its position among the kept landmarks is its index) and nothing was added
+            const int ls = st->lsearch, e = max(ls - 1, 0);
+            const int identity = (!slow && ls > 0 && K == ls && kflag[e] && kpos[e] == e) ? 1 : 0;
+            // run records (runs.cuh) name landmarks by index: void every one of them when landmark indices changed
+            if (!identity) ts->epoch += 1;
+            if (!slow) { st->new_l = K; st->lact = K; st->n_ind = 0; ts->remap_identity = identity; }
+        }
+        s_last = last; s_slow = slow;
     }
-}
-
-// nothing to merge: the survivors, in order, are the new map (count-weighted mean of one member, :258-260)
-__global__ void __launch_bounds__(256)
-k_tail_finalize(DevState* st, TailState* ts, const double* __restrict__ kx, const double* __restrict__ ky, const double* __restrict__ kc,
-                double* __restrict__ map_out, int cap_out, int64_t ld_out, double* __restrict__ counts_state, int Lcap,
-                const int* __restrict__ kflag, const int* __restrict__ kpos, const double* __restrict__ nnd2, double thr1sq, double thr2_hi,
-                LmRec* __restrict__ lmrec, int* __restrict__ remap)
-{
-    if (ts->n_ind != 0 || ts->degenerate) return;   // k_tail_slow takes over
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    const int newL = st->kept;
-    if (r < Lcap) {
-        const double c = r < newL ? kc[r] : 0.0;
-        const double mx = r < newL ? mul_rn(kx[r], c) / c : 0.0, my = r < newL ? mul_rn(ky[r], c) / c : 0.0;
-        if (r < cap_out) { map_out[r] = mx; map_out[ld_out + r] = my; }
-        counts_state[r] = c;
-        LmRec rec;
-        rec.x = mx; rec.y = my; rec.r2 = r < newL ? hint_radius2(nnd2[r], 4.0 * thr1sq, thr2_hi) : 0.0; rec.r = __dsqrt_rd(rec.r2);
-        lmrec[r] = rec;
-        remap[r] = (r < st->raw_l && kflag[r]) ? kpos[r] : -1;      // label of this sweep -> index in the new map
-        if (r == 0) { st->new_l = newL; st->lact = newL; st->n_ind = 0; }
-        // every old label survived in place (its position in the scan of the keep flags is its index) and nothing was added
-        if (r == max(st->lsearch - 1, 0))
-            ts->remap_identity = (st->lsearch > 0 && newL == st->lsearch && kflag[r] && kpos[r] == r) ? 1 : 0;
-    }
+    __syncthreads();
+    if (!s_last || !s_slow) return;
+    tail_slow_body(st, ts, sa.dist_thr, kx, ky, kc, sa.parent, nn, ind_flag, sa.ind_pos, sa.ind, sa.lab, sa.used, sa.rank, sa.ox, sa.oy, sa.oc,
+                   map_out, cap_out, ld_out, counts_state, Lcap, sa.max_cells, sa.geom, sa.cell_cnt, sa.cell_start, sa.pts, sa.gidx, kflag, kpos,
+                   thr1sq, thr2_hi, lmrec_new, remap);
 }
 
 // landmark records of a map whose grid has just been built (first sweep on a caller-supplied map)
@@ -368,6 +598,7 @@ __device__ void tail_slow_body(DevState* st, TailState* ts, double dist_thr, dou
             int max_cells, FGeom* geom, int* cell_cnt, int* cell_start, double2* pts, int* gidx,
             const int* kflag, const int* kpos, double thr1sq, double thr2_hi, LmRec* lmrec, int* remap)
 {
+    // (runs in the last block of k_tail_nn: everything it reads was written by other blocks of the same launch or before)
     __shared__ int wsum[34];
     __shared__ double red[4][32];
     const int tid = threadIdx.x, nth = blockDim.x;
@@ -494,25 +725,6 @@ __device__ void tail_slow_body(DevState* st, TailState* ts, double dist_thr, dou
             lmrec[r] = rec;
         }
     }
-}
-
-__global__ void __launch_bounds__(1024)
-k_tail_slow(DevState* st, TailState* ts, double dist_thr, double* kx, double* ky, double* kc, int* parent, int* nn, int* ind_flag,
-            int* ind_pos, int* ind, int* lab, int* used, int* rank, double* ox, double* oy, double* oc, double* map_out, int cap_out,
-            int64_t ld_out, double* counts_state, int Lcap,
-            // grid rebuild over the merged map
-            int max_cells, FGeom* geom, int* cell_cnt, int* cell_start, double2* pts, int* gidx,
-            const int* kflag, const int* kpos, double thr1sq, double thr2_hi, LmRec* lmrec, int* remap)
-{
-    // run records (runs.cuh) name landmarks by index: void every one of them when landmark indices changed
-    // (k_tail_finalize has completed: this launch follows it on the stream)
-    if (threadIdx.x == 0) {
-        const bool fast = ts->n_ind == 0 && !ts->degenerate;
-        if (!(fast && ts->remap_identity)) ts->epoch += 1;
-    }
-    if (ts->n_ind == 0 && !ts->degenerate) return;
-    tail_slow_body(st, ts, dist_thr, kx, ky, kc, parent, nn, ind_flag, ind_pos, ind, lab, used, rank, ox, oy, oc, map_out, cap_out, ld_out,
-                   counts_state, Lcap, max_cells, geom, cell_cnt, cell_start, pts, gidx, kflag, kpos, thr1sq, thr2_hi, lmrec, remap);
 }
 
 

@@ -239,7 +239,7 @@ class SegmentedSolver:
         # enqueue on that same stream, or nothing orders its kernels against the collectives.  The solver owns one stream
         # for both (the legacy default stream cannot be captured into a graph) and orders it against the caller's.
         if getattr(self, "_stream", None) is None:
-            self._stream = torch.cuda.Stream(device=self.device)
+            self._stream = torch.cuda.Stream(device=self.device, priority=-1)   # (above the handle's low-priority solve stream)
             self.engine.set_stream(self._stream.cuda_stream)
 
     def sweep(self, n_sweeps: int = 1, use_graph: bool = True):
