@@ -47,6 +47,8 @@ struct AssocParams {
     int skip_hints;                       // debug (ICMSLAM_HINTS=0)
     int n_tiles; int* blk_prefix; int Lcap; unsigned long long* bb;      // for the scan of the far counts (tail.cuh far_scan_block)
     DevState* stw;                        // (= st, writable: the sweep's label bookkeeping)
+    int final;                            // last launch of the sweep (a host-memory sweep launches one per chunk of tiles, each over the
+                                          // tiles that turned dirty since the one before): scan the far counts
     RunParams R;
 };
 
@@ -140,9 +142,10 @@ k_assoc_tiles(const AssocParams p)
     const bool use_hints = p.hints != 0 && have_map && !p.skip_hints;
     const int epoch = R.ts->epoch;
     const int n_dirty = R.ts->n_dirty;
+    const int d_first = R.ts->dirty_done;
     const int q = tid >> 1, sub = tid & 1;          // scan of the tile worked by this thread pair, and the thread's half of it
 
-    for (int di = blockIdx.x; di < n_dirty; di += gridDim.x) {
+    for (int di = d_first + blockIdx.x; di < n_dirty; di += gridDim.x) {
         const int tile = R.dirty_list[di];
         const int tb = R.t_start + tile * RT_TILE;
         const int nsc = min(RT_TILE, R.t_hi - tb);
@@ -416,8 +419,8 @@ k_assoc_tiles(const AssocParams p)
     if (tid == 0) {
         __threadfence();
         const int last = atomicAdd(&R.ts->assoc_ticket, 1) == (int)gridDim.x - 1;
-        if (last) { __threadfence(); R.ts->assoc_ticket = 0; }
-        S.nslots = last;
+        if (last) { __threadfence(); R.ts->assoc_ticket = 0; R.ts->dirty_done = p.final ? 0 : n_dirty; }
+        S.nslots = last && p.final;
     }
     __syncthreads();
     if (S.nslots) far_scan_block(R.farbits, p.n_tiles, p.blk_prefix, p.stw, R.ts, p.Lcap, p.bb, S.rtot, reinterpret_cast<unsigned char*>(sb), p.obs_cap * 16);

@@ -124,6 +124,9 @@ struct icmslam_handle {
     // map chain: grid, hints and labels stay valid, sensors.py:315 `mapa_viejo = mapa_refinado`)
     std::vector<double> last_map_host; int last_map_L = -1;
     int64_t bytes_h2d = 0, bytes_d2h = 0;      // copied by host-memspace sweeps (icmslam_get_transfer_bytes)
+    // a host-memory sweep of a map chain goes through in chunks of tiles: upload, run kernel, solve and read-back of successive
+    // chunks overlap (fused_part_a, HostPipe)
+    cudaStream_t h2d_stream = nullptr; cudaEvent_t ev_in[16] = {}, ev_out[16] = {}; int pipe_chunks = 8; bool pipe_events = false;
     double* d2h_x = nullptr; int64_t d2h_ld = 0; bool d2h_done = false;   // host destination of the sweep in flight's poses (fused path)
     // time-segment partition (icmslam_set_segment): this handle owns columns [seg_lo, seg_hi) of its T columns
     int seg_lo = 0, seg_hi = 0, seg_first = 1, seg_last = 1;
@@ -131,6 +134,8 @@ struct icmslam_handle {
     long long* d_exch = nullptr;  // ONE block [fsum_x | fsum_y | cnt] (newraw aliases the first two): what the segments sum-reduce, viewed as int64
     int64_t exch_words = 0;
     double* d_seg_rec = nullptr;  // SEG_REC doubles: what this segment tells its neighbours
+    double* d_seg_rec_pose = nullptr;   // ... the boundary poses on their own when they are gathered beside the tail (icmslam_seg_halo)
+    bool seg_split = false;       // the sweep in flight exchanges its halo poses through icmslam_seg_halo
     double* seg_dst = nullptr;    // output pose buffer of the segment sweep in flight
     size_t fused_smem = 0;
     double thr2_hi = 0.0, fix_scale = 1.0;
@@ -218,7 +223,7 @@ extern "C" int icmslam_destroy(icmslam_handle* h)
     DFREE(h->d_cell_start); DFREE(h->d_cell_fill); DFREE(h->d_cell_id); DFREE(h->d_gidx); DFREE(h->d_glx); DFREE(h->d_gly);
     DFREE(h->d_st); DFREE(h->d_cub); DFREE(h->d_sort_ws);
     DFREE(h->d_exch); DFREE(h->d_fg_cnt); DFREE(h->d_fg_start); DFREE(h->d_fg_idx);
-    DFREE(h->d_fg_pts); DFREE(h->d_fg_geom); DFREE(h->d_bb); DFREE(h->d_ts); DFREE(h->d_seg_rec);
+    DFREE(h->d_fg_pts); DFREE(h->d_fg_geom); DFREE(h->d_bb); DFREE(h->d_ts); DFREE(h->d_seg_rec); DFREE(h->d_seg_rec_pose);
     DFREE(h->d_lmrec2[0]); DFREE(h->d_lmrec2[1]); DFREE(h->d_blk_kept); DFREE(h->d_rawcnt); DFREE(h->d_scan_state); DFREE(h->d_remap); DFREE(h->d_nnd2); DFREE(h->d_klab); DFREE(h->d_aobs); DFREE(h->d_ac);
     if (h->h_st) cudaFreeHost(h->h_st);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -227,6 +232,8 @@ extern "C" int icmslam_destroy(icmslam_handle* h)
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_tail) cudaEventDestroy(h->ev_tail);
+    if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+    for (int i = 0; i < 16; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]); }
     delete h;
     return ICMSLAM_OK;
 }
@@ -327,6 +334,8 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     if (e == cudaSuccess) e = dalloc(&h->d_bb, 4);
     if (e == cudaSuccess) e = dalloc(&h->d_ts, 1);
     if (e == cudaSuccess) e = dalloc(&h->d_seg_rec, SEG_REC);
+    if (e == cudaSuccess) e = dalloc(&h->d_seg_rec_pose, SEG_REC);
+    if (e == cudaSuccess) e = cudaMemset(h->d_seg_rec_pose, 0, SEG_REC * sizeof(double));
     if (e == cudaSuccess) e = dalloc(&h->d_lmrec2[0], L);
     if (e == cudaSuccess) e = dalloc(&h->d_lmrec2[1], L);
     if (e == cudaSuccess) e = dalloc(&h->d_blk_kept, (size_t)nblk((int)L, 256) + 1);
@@ -815,8 +824,10 @@ static int ensure_stats_clean(icmslam_handle* h)
 // exchanges data with the other segments between them ----------------------------------------------------
 // part A: (grid of the previous map if it is not there yet) + the run kernel + the association kernel over the tiles the run
 // kernel could not certify + the pose solve (forked beside the tail when `overlap`) + the scan of far-scan counts
+struct HostPipe { double* x; int64_t ld; int chunks; };      // the caller's host poses (in and out) of a chunk-pipelined sweep
+
 static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, double* kout, int64_t kld, const double* x0,
-                        const icmslam_sweep_opts& o, int n_search_cap, bool overlap = false)
+                        const icmslam_sweep_opts& o, int n_search_cap, bool overlap = false, const HostPipe* hp = nullptr)
 {
     const int T = h->T, L = h->Lcap;
     cudaStream_t s = h->stream;
@@ -838,7 +849,7 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
     // the pose buffers ping-pong, and so do their projection parameters
     double4* pp_in = h->d_ppar[xin == h->d_x2 ? 1 : 0];
     double4* pp_out = h->d_ppar[xin == h->d_x2 ? 0 : 1];
-    {
+    if (!hp) {
         int rc = ensure_ppar(h, xin, ldin, x0, pp_in);
         if (rc) return rc;
     }
@@ -850,14 +861,74 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
     R.far_list = h->d_far_list; R.ts = h->d_ts; R.farbits = h->d_farbits;
     R.scan_dirty = h->d_scan_dirty; R.tile_flag = h->d_tile_flag; R.dirty_list = h->d_dirty_list;
     R.geom = h->d_fg_geom; R.cell_start = h->d_fg_start; R.gpts = h->d_fg_pts; R.dist_thr = h->dcfg.dist_thr;
-    R.st = st; R.L_in = h->begin_L;
+    R.st = st; R.L_in = h->begin_L; R.slice0 = 0;
     AssocParams A;
     A.first_halo = h->seg_first ? 0 : 1; A.T = T; A.off = h->d_off; A.bxy = h->d_bxy; A.cfg = h->dcfg; A.thr2_hi = h->thr2_hi; A.st = st; A.geom = h->d_fg_geom;
     A.cell_start = h->d_fg_start; A.gpts = h->d_fg_pts; A.gidx = h->d_fg_idx; A.remap = h->d_remap;
     { const char* eh = getenv("ICMSLAM_HINTS"); A.skip_hints = (eh && atoi(eh) == 0) ? 1 : 0; }
     A.hints = (h->hint_map == h->d_map_in) ? 1 : 0;
     A.c = h->d_c; A.obs_cap = h->obs_cap; A.R = R;
-    A.n_tiles = h->n_tiles; A.blk_prefix = h->d_blk_prefix; A.Lcap = L; A.bb = h->d_bb; A.stw = st;
+    A.n_tiles = h->n_tiles; A.blk_prefix = h->d_blk_prefix; A.Lcap = L; A.bb = h->d_bb; A.stw = st; A.final = 1;
+    if (hp) {
+        // ---- chunks of tiles: upload | projection parameters, run kernel, association of the tiles it hands over, solve of the
+        //      poses whose moments are complete | read-back, on three streams ---------------------------------------------------
+        SolveParams P;
+        P.T = T; P.t_lo = h->seg_lo; P.t_hi = h->seg_hi; P.lay = traj_layout(h, x0);
+        P.xin = xin; P.ldin = ldin; P.xout = kout; P.ldout = kld;
+        P.inc = h->d_inc; P.ldinc = T; P.u = h->d_u; P.ldu = T; P.bm = h->d_bm; P.ldbm = T; P.dyn = h->d_dyn;
+        P.ppin = pp_in; P.ppout = pp_out; P.cfg = h->dcfg; P.tol = o.newton_tol; P.maxit = o.newton_maxit; P.iters = nullptr; P.tile0 = 0;
+        const int C = hp->chunks, per = (h->n_tiles + C - 1) / C;
+        cudaStream_t sin = h->h2d_stream, sout = h->side_stream;
+        CK(cudaEventRecord(h->ev_fork, s));
+        CK(cudaStreamWaitEvent(sin, h->ev_fork, 0));
+        CK(cudaStreamWaitEvent(sout, h->ev_fork, 0));
+        for (int c = 0; c < C; ++c) {
+            const int a = c * per * RT_TILE, b = (c + 1) * per * RT_TILE < T ? (c + 1) * per * RT_TILE : T;
+            if (b > a) CK(cudaMemcpy2DAsync((double*)xin + a, (size_t)ldin * 8, hp->x + a, (size_t)hp->ld * 8, (size_t)(b - a) * 8, 3, cudaMemcpyHostToDevice, sin));
+            CK(cudaEventRecord(h->ev_in[c], sin));
+        }
+        const int nb = h->assoc_blocks < h->n_tiles ? h->assoc_blocks : h->n_tiles;
+        int solved = 0;
+        for (int c = 0; c < C; ++c) {
+            const int tile_a = c * per, tile_b = (c + 1) * per < h->n_tiles ? (c + 1) * per : h->n_tiles;
+            const int a = tile_a * RT_TILE, b = tile_b * RT_TILE < T ? tile_b * RT_TILE : T;
+            const bool last = c == C - 1;
+            CK(cudaStreamWaitEvent(s, h->ev_in[c], 0));
+            if (tile_b > tile_a) {
+                k_ppar_init<<<nblk(b - a, 256), 256, 0, s>>>(xin, ldin, a, b, P.lay, pp_in);
+                R.slice0 = tile_a * RT_SLICES;
+                if (h->runs_occ == 32) k_runs<32><<<(tile_b - tile_a) * RT_SLICES, RUNS_THREADS, 0, s>>>(R);
+                else k_runs<24><<<(tile_b - tile_a) * RT_SLICES, RUNS_THREADS, 0, s>>>(R);
+                h->n_launch += 2;
+            }
+            A.final = last ? 1 : 0;
+            k_assoc_tiles<<<nb, AT_THREADS, h->fused_smem, s>>>(A);
+            CK(cudaGetLastError());
+            h->n_launch += 1;
+            // solve tiles whose poses (own range + the staged margin) are uploaded and whose moments are final
+            int ready = last ? h->n_solve_tiles : (b >= ST_XT ? (b - ST_XT) / ST_OWN + 1 : 0);
+            if (ready > h->n_solve_tiles) ready = h->n_solve_tiles;
+            if (ready > solved) {
+                P.tile0 = solved;
+                if (h->solve_occ == 4) k_solve_tile<4><<<ready - solved, ST_THREADS, 0, s>>>(P);
+                else if (h->solve_occ == 6) k_solve_tile<6><<<ready - solved, ST_THREADS, 0, s>>>(P);
+                else k_solve_tile<5><<<ready - solved, ST_THREADS, 0, s>>>(P);
+                CK(cudaGetLastError());
+                h->n_launch += 1;
+                CK(cudaEventRecord(h->ev_out[c], s));
+                CK(cudaStreamWaitEvent(sout, h->ev_out[c], 0));
+                const int ca = h->seg_lo + solved * ST_OWN, cb = h->seg_lo + ready * ST_OWN < h->seg_hi ? h->seg_lo + ready * ST_OWN : h->seg_hi;
+                if (cb > ca) CK(cudaMemcpy2DAsync(hp->x + ca, (size_t)hp->ld * 8, kout + ca, (size_t)kld * 8, (size_t)(cb - ca) * 8, 3, cudaMemcpyDeviceToHost, sout));
+                solved = ready;
+            }
+        }
+        CK(cudaEventRecord(h->ev_join, sout));
+        CK(cudaEventRecord(h->ev_fork, s));      // (what a tail on another stream waits for: the last chunk's kernels)
+        h->join_pending = true;
+        h->d2h_done = true;
+        h->ppar_of = kout;
+        return ICMSLAM_OK;
+    }
     if (timing) CK(cudaEventRecord(h->ev[0], s));
     if (h->use_runs) {
         if (h->runs_occ == 32) k_runs<32><<<h->n_tiles * RT_SLICES, RUNS_THREADS, 0, s>>>(R);
@@ -881,7 +952,7 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
         P.xin = xin; P.ldin = ldin; P.xout = kout; P.ldout = kld;
         P.inc = h->d_inc; P.ldinc = T; P.u = h->d_u; P.ldu = T; P.bm = h->d_bm; P.ldbm = T; P.dyn = h->d_dyn;
         P.ppin = pp_in; P.ppout = pp_out; P.cfg = h->dcfg; P.tol = o.newton_tol; P.maxit = o.newton_maxit;
-        P.iters = (o.reserved & 1) ? &st->newton_iters : nullptr;
+        P.iters = (o.reserved & 1) ? &st->newton_iters : nullptr; P.tile0 = 0;
         cudaStream_t ss = s;
         const bool fork = overlap && h->overlap_solve && !timing && h->side_stream;
         if (fork) {      // the tail does not depend on the new poses: solve beside it
@@ -965,13 +1036,28 @@ static int fused_part_c(icmslam_handle* h, double* dmap_out, int out_cap, int64_
     return ICMSLAM_OK;
 }
 
+// streams and events of the chunk-pipelined host sweep, created on first use
+static bool pipe_ready(icmslam_handle* h)
+{
+    if (h->pipe_events) return true;
+    const char* ec = getenv("ICMSLAM_PIPE_CHUNKS");
+    if (ec) { int c = atoi(ec); h->pipe_chunks = c < 1 ? 1 : (c > 16 ? 16 : c); }
+    if (h->pipe_chunks <= 1) return false;
+    if (cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking) != cudaSuccess) { h->pipe_chunks = 1; return false; }
+    for (int i = 0; i < 16; ++i)
+        if (cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming) != cudaSuccess) { h->pipe_chunks = 1; return false; }
+    h->pipe_events = true;
+    return true;
+}
+
 // One sweep on device-resident data.  The previous map is in h->d_map_in (2 x Lcap); L_in is its
 // width known on the host, or -1 when only the device knows it (= landmarks_actuales, chained
 // sweeps).  Poses are read from xin (3 x T, ldin) and the updated poses written to xout (3 x T,
 // ldout); xin == xout is allowed (the fused path then goes through the internal double buffer).
 // The filtered map goes to dmap_out.
 static int sweep_core(icmslam_handle* h, const double* xin, int64_t ldin, double* xout, int64_t ldout, const double* x0,
-                      const icmslam_sweep_opts& o, int L_in, double* dmap_out, int out_cap, int64_t out_ld)
+                      const icmslam_sweep_opts& o, int L_in, double* dmap_out, int out_cap, int64_t out_ld, const HostPipe* hp = nullptr)
 {
     const int T = h->T, L = h->Lcap;
     const int64_t n = h->n;
@@ -1001,7 +1087,7 @@ static int sweep_core(icmslam_handle* h, const double* xin, int64_t ldin, double
         double* kout = xout;
         int64_t kld = ldout;
         if (xin == xout) { kout = (xin == h->d_x2) ? h->d_x : h->d_x2; kld = T; }
-        rc = fused_part_a(h, xin, ldin, kout, kld, x0, o, n_search_cap, /*overlap=*/kout == xout);
+        rc = fused_part_a(h, xin, ldin, kout, kld, x0, o, n_search_cap, /*overlap=*/kout == xout, hp);
         if (rc) return rc;
         if (kout != xout) CK(cudaMemcpy2DAsync(xout, (size_t)ldout * 8, kout, (size_t)kld * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToDevice, s));
         // The tail's chain of small kernels runs beside the solve's waves only if the block scheduler prefers it: on the handle's
@@ -1140,13 +1226,6 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
     const double* xin = x;
     double* xout = x;
     int64_t ldin = ld_x, ldout = ld_x;
-    if (memspace == ICMSLAM_HOST) {
-        CK(cudaMemcpy2DAsync(h->d_x, (size_t)T * 8, x, (size_t)ld_x * 8, (size_t)T * 8, 3, cudaMemcpyHostToDevice, s));
-        h->bytes_h2d += (int64_t)3 * T * 8;
-        h->ppar_of = nullptr;
-        xin = h->d_x; ldin = T;
-        xout = h->d_x2; ldout = T;
-    }
     bool continued = false;
     if (memspace == ICMSLAM_HOST && L_in > 0 && L_in == h->last_map_L && h->grid_map != nullptr && h->grid_map == h->d_map_in &&
         memcmp(map_in, h->last_map_host.data(), (size_t)L_in * 8) == 0 &&
@@ -1156,6 +1235,19 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
         continued = true;
     }
     h->last_map_L = -1;
+    // a link of a map chain in the default mode: the poses go up, through the kernels and back in chunks (fused_part_a)
+    HostPipe pipe;
+    const bool piped = continued && h->fused_ok && o.fused && o.schedule == ICMSLAM_SCHED_REDBLACK && o.solver == ICMSLAM_SOLVER_NEWTON &&
+                       o.map_view == ICMSLAM_VIEW_PREV && o.reserved == 0 && h->use_runs && h->side_stream && h->seg_first && h->seg_last &&
+                       h->seg_lo == 0 && h->pipe_chunks > 1 && h->n_tiles >= 64 * h->pipe_chunks && pipe_ready(h);
+    if (memspace == ICMSLAM_HOST) {
+        if (!piped) CK(cudaMemcpy2DAsync(h->d_x, (size_t)T * 8, x, (size_t)ld_x * 8, (size_t)T * 8, 3, cudaMemcpyHostToDevice, s));
+        h->bytes_h2d += (int64_t)3 * T * 8;
+        h->ppar_of = nullptr;
+        xin = h->d_x; ldin = T;
+        xout = h->d_x2; ldout = T;
+        pipe.x = x; pipe.ld = ld_x; pipe.chunks = h->pipe_chunks;
+    }
     if (!continued) {
         if (L_in > 0) {
             CK(cudaMemcpy2DAsync(h->d_map_in, (size_t)L * 8, map_in, (size_t)ld_map_in * 8, (size_t)L_in * 8, 2, cudaMemcpyDefault, s));
@@ -1168,7 +1260,7 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
     h->d2h_done = false;
     if (memspace == ICMSLAM_HOST) { h->d2h_x = x; h->d2h_ld = ld_x; }
     int rc = sweep_core(h, xin, ldin, xout, ldout, x0, o, L_in, own_out ? h->d_map_out : map_out, own_out ? L : cap_out,
-                        own_out ? (int64_t)L : ld_map_out);
+                        own_out ? (int64_t)L : ld_map_out, piped ? &pipe : nullptr);
     h->d2h_x = nullptr;
     if (rc) return rc;
     if (own_out) {      // mapa_refinado becomes the handle's current map (icmslam_get_map, and the map chain a caller may continue)
@@ -1417,6 +1509,8 @@ extern "C" int icmslam_device_ptr(icmslam_handle* h, int32_t which, void** ptr, 
     case ICMSLAM_PTR_NEW_LABELS: *ptr = h->d_newraw; *count = 2 * L; break;
     case ICMSLAM_PTR_POSES: *ptr = h->x_cur ? h->d_x2 : h->d_x; *count = 3 * (int64_t)h->T; break;
     case ICMSLAM_PTR_EXCHANGE: *ptr = h->d_exch; *count = h->exch_words; break;
+    case ICMSLAM_PTR_SEG_REC_POSE: *ptr = h->d_seg_rec_pose; *count = SEG_REC; break;
+    case ICMSLAM_PTR_SIDE_STREAM: *ptr = (void*)h->side_stream; *count = 1; break;
     default: return ICMSLAM_ERR_INVALID;
     }
     return ICMSLAM_OK;
@@ -1446,12 +1540,39 @@ extern "C" int icmslam_seg_begin(icmslam_handle* h, const double* x0, const icms
         k_sweep_begin<<<1, 1, 0, s>>>(h->d_st, h->d_ts, L);
         CK(cudaGetLastError());
     }
-    rc = fused_part_a(h, src, T, dst, T, x0, o, L);
+    // opts.reserved & 4: the caller gathers the boundary poses separately (icmslam_seg_halo) on the side stream, where the solve
+    // then runs beside the label exchange, the reduction of the statistics and the tail
+    h->seg_split = (o.reserved & 4) != 0 && h->side_stream && h->overlap_solve && (o.reserved & 2) == 0;
+    rc = fused_part_a(h, src, T, dst, T, x0, o, L, /*overlap=*/h->seg_split);
     if (rc) return rc;
-    k_seg_pack<<<1, 32, 0, s>>>(dst, T, h->seg_lo, h->seg_hi, h->d_ts, h->d_seg_rec);
-    CK(cudaGetLastError());
+    if (h->seg_split) {
+        k_seg_pack<<<1, 32, 0, s>>>(dst, T, h->seg_lo, h->seg_hi, h->d_ts, h->d_seg_rec, 0, 1);
+        CK(cudaGetLastError());
+        k_seg_pack<<<1, 32, 0, h->side_stream>>>(dst, T, h->seg_lo, h->seg_hi, h->d_ts, h->d_seg_rec_pose, 1, 0);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(h->ev_join, h->side_stream));
+        h->n_launch += 1;
+    } else {
+        k_seg_pack<<<1, 32, 0, s>>>(dst, T, h->seg_lo, h->seg_hi, h->d_ts, h->d_seg_rec, 1, 1);
+        CK(cudaGetLastError());
+    }
     h->seg_dst = dst;
-    h->n_launch += 2;
+    h->n_launch += 1;
+    return ICMSLAM_OK;
+}
+
+// part 1b (only after icmslam_seg_begin with opts.reserved & 4): `gathered` = the all-gather of every segment's
+// ICMSLAM_PTR_SEG_REC_POSE record, issued by the caller on the handle's side stream (ICMSLAM_PTR_SIDE_STREAM).  Fills this
+// segment's halo poses there; icmslam_seg_finish joins the side stream.
+extern "C" int icmslam_seg_halo(icmslam_handle* h, const double* gathered, int32_t rank, int32_t world)
+{
+    if (!h || !gathered || !h->seg_dst || !h->seg_split || rank < 0 || rank >= world) return ICMSLAM_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    k_seg_unpack<<<1, 32, 0, h->side_stream>>>(gathered, rank, world, h->seg_dst, h->T, h->T, h->d_st, h->d_ts, h->Lcap,
+                                               h->d_ppar[h->seg_dst == h->d_x2 ? 1 : 0], 1, 0);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev_join, h->side_stream));
+    h->n_launch += 1;
     return ICMSLAM_OK;
 }
 
@@ -1463,7 +1584,7 @@ extern "C" int icmslam_seg_exchange(icmslam_handle* h, const double* gathered, i
     if (!h || !gathered || !h->seg_dst || rank < 0 || rank >= world) return ICMSLAM_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));
     k_seg_unpack<<<1, 32, 0, h->stream>>>(gathered, rank, world, h->seg_dst, h->T, h->T, h->d_st, h->d_ts, h->Lcap,
-                                          h->d_ppar[h->seg_dst == h->d_x2 ? 1 : 0]);
+                                          h->d_ppar[h->seg_dst == h->d_x2 ? 1 : 0], h->seg_split ? 0 : 1, 1);
     CK(cudaGetLastError());
     h->n_launch += 1;
     return fused_part_b(h, h->stream);

@@ -99,6 +99,7 @@ struct RunParams {
     int* tile_slots; int* tile_nslots;    // RS_SLOTS labels per tile: which landmark each slot of its statistics table stands for; slots in use
     FarRec* far_list; TailState* ts; unsigned* farbits;   // scans with far observations (each creates one label)
     DevState* st; int L_in;                               // the sweep's state, reset by the first block (tail.cuh sweep_begin_state)
+    int slice0;                                           // first slice of this launch (a host-memory sweep launches the tiles in chunks)
     int* scan_dirty; int* tile_flag; int* dirty_list;     // steady state: what failed validation (tile_flag: 1 some scans, 2 all)
     const FGeom* geom; const int* cell_start; const double2* gpts;   // the landmark grid (fastgrid.cuh), for the far runs
     double dist_thr;
@@ -318,7 +319,7 @@ k_runs(const RunParams p)
 {
     __shared__ TileSmem S;
     __shared__ SliceRing ring;
-    const int slice = blockIdx.x, tile = slice / RT_SLICES;
+    const int slice = p.slice0 + blockIdx.x, tile = slice / RT_SLICES;
     if (slice == 0 && threadIdx.x == 0) sweep_begin_state(p.st, p.L_in);      // (nothing in this launch reads it)
     const int nslots = p.tile_nslots[tile];
     if (p.tile_epoch[tile] != p.ts->epoch) {      // no records for this label numbering: the whole tile goes to the association kernel

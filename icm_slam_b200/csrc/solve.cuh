@@ -202,6 +202,7 @@ struct SolveParams {
     DevCfg cfg;
     double tol; int maxit;
     unsigned long long* iters;
+    int tile0;                            // first tile of this launch
 };
 
 struct __align__(16) SolveSmem {
@@ -248,7 +249,7 @@ k_solve_tile(const SolveParams p)
 {
     __shared__ SolveSmem S;
     const int tid = threadIdx.x;
-    const int tb = p.t_lo + blockIdx.x * ST_OWN;      // t_lo is even: colours stay aligned with the global time index
+    const int tb = p.t_lo + (p.tile0 + blockIdx.x) * ST_OWN;      // t_lo is even: colours stay aligned with the global time index
     const int T = p.T;
     const int q = tid >> 1, half = tid & 1;
     SlotMom cur = solve_slot_load(p, tb, q, half, 0);      // (in flight while the tile is staged)

@@ -43,6 +43,7 @@ struct TailState {
                         // indices change (a merge or a drop in Mapa.filtrar, a map supplied by the caller)
     int n_dirty;        // tiles the steady-state kernel handed to the association kernel this sweep
     int assoc_ticket;   // blocks of the association kernel that have finished (the last one scans the far counts)
+    int dirty_done;     // entries of the dirty list handled by earlier association launches of the same sweep
     int nn_ticket;      // blocks of k_tail_nn that have finished (the last one closes the sweep)
     int scan_ticket;    // blocks of k_cell_scan that have finished
     unsigned scan_seq;  // launch number of k_cell_scan: tags the block totals published through global memory (starts at 1)
@@ -729,38 +730,42 @@ __device__ void tail_slow_body(DevState* st, TailState* ts, double dist_thr, dou
 
 
 // ---- time-segment partition (one segment per GPU) ---------------------------------------------------------
-// after the fused kernel: this segment's boundary poses and its count of scans with far observations
-__global__ void k_seg_pack(const double* __restrict__ x, int64_t ld, int t_lo, int t_hi, const TailState* ts, double* __restrict__ rec)
+// after the run / association kernels: this segment's count of scans with far observations; after the solve: its boundary poses.
+// `pose` and `far` select the part written (the two parts may be gathered separately: the poses beside the tail, on another stream)
+__global__ void k_seg_pack(const double* __restrict__ x, int64_t ld, int t_lo, int t_hi, const TailState* ts, double* __restrict__ rec, int pose,
+                           int far)
 {
     const int i = threadIdx.x;
-    if (i < 3) {
+    if (pose && i < 3) {
         rec[i] = x[i * ld + t_lo];
         rec[3 + i] = x[i * ld + max(t_hi - 2, t_lo)];
         rec[6 + i] = x[i * ld + t_hi - 1];
     }
-    if (i == 9) rec[9] = (double)ts->far_total;
-    if (i > 9 && i < SEG_REC) rec[i] = 0.0;
+    if (far && i == 9) rec[9] = (double)ts->far_total;
+    if (far && i > 9 && i < SEG_REC) rec[i] = 0.0;
 }
 
 // after the all-gather: neighbours' boundary poses into this segment's halo columns (0, 1 and T-1), and the
 // global numbering of the new labels (exclusive prefix over the ranks of far_total, ICM_SLAM.py:174-182)
 __global__ void k_seg_unpack(const double* __restrict__ all, int rank, int world, double* __restrict__ x, int64_t ld, int T, DevState* st,
-                             TailState* ts, int Lcap, double4* __restrict__ ppar)
+                             TailState* ts, int Lcap, double4* __restrict__ ppar, int pose, int far)
 {
     const int i = threadIdx.x;
-    if (i < 3) {
-        if (rank > 0) {
-            const double* l = all + (size_t)(rank - 1) * SEG_REC;
-            x[i * ld + 0] = l[3 + i];
-            x[i * ld + 1] = l[6 + i];
+    if (pose) {
+        if (i < 3) {
+            if (rank > 0) {
+                const double* l = all + (size_t)(rank - 1) * SEG_REC;
+                x[i * ld + 0] = l[3 + i];
+                x[i * ld + 1] = l[6 + i];
+            }
+            if (rank + 1 < world) x[i * ld + T - 1] = all[(size_t)(rank + 1) * SEG_REC + i];
         }
-        if (rank + 1 < world) x[i * ld + T - 1] = all[(size_t)(rank + 1) * SEG_REC + i];
+        // projection parameters of the halo poses (the same expression the owner's solve used: bit-identical)
+        if (i == 3 && rank > 0) { const double* l = all + (size_t)(rank - 1) * SEG_REC; ppar[0] = make_ppar(l[3], l[4], l[5]); }
+        if (i == 4 && rank > 0) { const double* l = all + (size_t)(rank - 1) * SEG_REC; ppar[1] = make_ppar(l[6], l[7], l[8]); }
+        if (i == 5 && rank + 1 < world) { const double* l = all + (size_t)(rank + 1) * SEG_REC; ppar[T - 1] = make_ppar(l[0], l[1], l[2]); }
     }
-    // projection parameters of the halo poses (the same expression the owner's solve used: bit-identical)
-    if (i == 3 && rank > 0) { const double* l = all + (size_t)(rank - 1) * SEG_REC; ppar[0] = make_ppar(l[3], l[4], l[5]); }
-    if (i == 4 && rank > 0) { const double* l = all + (size_t)(rank - 1) * SEG_REC; ppar[1] = make_ppar(l[6], l[7], l[8]); }
-    if (i == 5 && rank + 1 < world) { const double* l = all + (size_t)(rank + 1) * SEG_REC; ppar[T - 1] = make_ppar(l[0], l[1], l[2]); }
-    if (i == 0) {
+    if (far && i == 0) {
         int base = 0, total = 0;
         for (int r = 0; r < world; ++r) {
             const int f = (int)all[(size_t)r * SEG_REC + 9];

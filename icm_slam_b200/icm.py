@@ -238,18 +238,14 @@ class ICM_SLAM:
 
     @staticmethod
     def _fingerprint(a):
-        """Cheap content fingerprint of an input array: where it lives, its shape, and a CRC of a strided sample (<= 1k
-        values incl. the first and last column: ~0.1 ms even for a GB-sized log).  Catches a new array, an array of another shape, a freed-and-reused
-        address and in-place edits that touch the sample; after other in-place edits call `invalidate()`."""
-        import zlib
+        """Identity of an input array: where it lives, its shape and strides, and its four corner values.  The reference
+        REPLACES its logs when they grow (np.concatenate, sensors.py:266-270), which this catches; after in-place edits
+        call `invalidate()`.  (A few microseconds per call: it runs on every sweep.)"""
         a = np.asarray(a)
         if a.size == 0:
             return (0,)
-        flat = a.reshape(-1)
-        step = max(1, flat.size // 1024)
-        sample = np.ascontiguousarray(flat[::step])
-        edge = np.ascontiguousarray(a[..., [0, -1]]) if a.ndim == 2 else sample[:1]
-        return (a.__array_interface__["data"][0], a.shape, a.strides, zlib.crc32(sample.tobytes()), zlib.crc32(edge.tobytes()))
+        corners = (float(a.flat[0]), float(a.flat[-1])) if a.ndim != 2 else (float(a[0, 0]), float(a[0, -1]), float(a[-1, 0]), float(a[-1, -1]))
+        return (a.__array_interface__["data"][0], a.shape, a.strides) + corners
 
     def _data_key(self):
         return (self._fingerprint(self.mediciones), self._fingerprint(self.u), self._fingerprint(self.odometria))

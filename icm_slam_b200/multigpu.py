@@ -7,12 +7,14 @@ the restated (red-black, exact inner solve, previous-map view) sweep does (DESIG
   of valid beams; segment r loads its own columns plus two halo columns on the left and one on the
   right (the poses its boundary poses are coupled to through the odometry terms);
 * per sweep each rank runs the fused kernel on its segment, then the ranks
-    1. all-gather a 16-double record (boundary poses of the new trajectory + number of scans that
-       created a label), which gives every rank its halo poses for the next sweep and the global
-       numbering of the new labels (ICM_SLAM.py:174-182 is an exclusive prefix over time);
+    1. all-gather a 16-double record with the number of scans that created a label, which gives the
+       global numbering of the new labels (ICM_SLAM.py:174-182 is an exclusive prefix over time);
     2. sum-reduce the per-landmark statistics (int64 fixed point + int32 counts: exact and
        order-free, so the map is bit-identical for any number of GPUs) and the new labels' means;
-  and every rank applies the same landmark update + Mapa.filtrar to the reduced statistics.
+  and every rank applies the same landmark update + Mapa.filtrar to the reduced statistics;
+* BESIDE 1-2 and the map update (none of which reads the new poses), on the library's low-priority side
+  stream and a second communicator: the pose solve of the segment, then an all-gather of its boundary
+  poses (another 16-double record) that gives every rank its halo poses for the next sweep.
 
 Collectives go through torch.distributed (NCCL on GPUs; the host logic is exercised with gloo in
 tests/test_multigpu_cpu.py).  All device work happens in libicmslam.so; this module only moves pointers.
@@ -24,7 +26,7 @@ import ctypes as C
 import numpy as np
 
 SEG_REC = 16
-PTR_SEG_REC, PTR_STAT_X, PTR_STAT_Y, PTR_STAT_N, PTR_NEW_LABELS, PTR_POSES, PTR_EXCHANGE = range(7)
+PTR_SEG_REC, PTR_STAT_X, PTR_STAT_Y, PTR_STAT_N, PTR_NEW_LABELS, PTR_POSES, PTR_EXCHANGE, PTR_SEG_REC_POSE, PTR_SIDE_STREAM = range(9)
 
 
 # ---- partition ---------------------------------------------------------------------------------------------
@@ -112,9 +114,14 @@ class _DevBuf:
 class SegmentedSolver:
     """One instance per rank.  `group` is a torch.distributed process group (default: the world)."""
 
-    def __init__(self, config, rank: int, world: int, device: int = 0, group=None):
+    def __init__(self, config, rank: int, world: int, device: int = 0, group=None, halo_group=None, split_exchange=True):
+        """halo_group: a second process group over the same ranks for the boundary-pose exchange that runs beside the label /
+        statistics exchange (created with dist.new_group when None and world > 1: a collective call, like the constructor itself
+        must then be).  split_exchange=False keeps everything on one stream and one communicator."""
         from .engine import Engine
         self.config, self.rank, self.world, self.device, self.group = config, int(rank), int(world), int(device), group
+        self.halo_group = halo_group
+        self.split_exchange = bool(split_exchange)
         self.engine = Engine(config, device=device)
         self._views = None
         self._graphs = {}
@@ -171,7 +178,7 @@ class SegmentedSolver:
         dev = "cuda:%d" % self.device
         mk = lambda which, ts: torch.as_tensor(_DevBuf(*self._ptr(which), ts), device=dev)
         self._views = dict(rec=mk(PTR_SEG_REC, "<f8"), sx=mk(PTR_STAT_X, "<i8"), sy=mk(PTR_STAT_Y, "<i8"), sn=mk(PTR_STAT_N, "<i4"),
-                           new=mk(PTR_NEW_LABELS, "<f8"), all=mk(PTR_EXCHANGE, "<i8"))
+                           new=mk(PTR_NEW_LABELS, "<f8"), all=mk(PTR_EXCHANGE, "<i8"), recp=mk(PTR_SEG_REC_POSE, "<f8"))
 
     # -- sweeps ---------------------------------------------------------------------------------------------------
     def _sweep_once(self, opts=None, stamps=None):
@@ -189,13 +196,18 @@ class SegmentedSolver:
                 ev.record(torch.cuda.current_stream(self.device))
                 stamps.append(ev)
 
+        split = self.split_exchange and self.world > 1 and stamps is None and opts is None
         if opts is None:
-            opts = _lib.SweepOpts(_lib.SCHED["redblack"], _lib.SOLVER["newton"], _lib.VIEW["prev"], 0, 0.0, 1, 0)
+            opts = _lib.SweepOpts(_lib.SCHED["redblack"], _lib.SOLVER["newton"], _lib.VIEW["prev"], 0, 0.0, 1, 4 if split else 0)
         stamp()
         check(e.lib.icmslam_seg_begin(e._h, C.c_void_p(self.x0.ctypes.data), C.byref(opts)), e._h)
         stamp()
         if self.world > 1:
             import torch.distributed as dist
+            if split:      # the solve is on the side stream: its boundary poses follow it there, beside everything below
+                with torch.cuda.stream(self._side):
+                    dist.all_gather_into_tensor(self._allpose, v["recp"].reshape(1, SEG_REC), group=self.halo_group)
+                check(e.lib.icmslam_seg_halo(e._h, C.c_void_p(self._allpose.data_ptr()), self.rank, self.world), e._h)
             dist.all_gather_into_tensor(self._allrec, v["rec"].reshape(1, SEG_REC), group=self.group)
             stamp()
             check(e.lib.icmslam_seg_exchange(e._h, C.c_void_p(self._allrec.data_ptr()), self.rank, self.world), e._h)
@@ -235,6 +247,14 @@ class SegmentedSolver:
             self._bind()
         if getattr(self, "_allrec", None) is None:
             self._allrec = torch.empty((self.world, SEG_REC), dtype=torch.float64, device="cuda:%d" % self.device)
+            self._allpose = torch.empty((self.world, SEG_REC), dtype=torch.float64, device="cuda:%d" % self.device)
+            self._side = torch.cuda.ExternalStream(self._ptr(PTR_SIDE_STREAM)[0], device=self.device)
+            if self.split_exchange and self.world > 1 and self.halo_group is None:
+                import torch.distributed as dist
+                self.halo_group = dist.new_group(ranks=list(range(self.world))) if self.group is None else None
+                self._own_halo_group = self.halo_group is not None
+                if self.halo_group is None:
+                    self.split_exchange = False        # (a sub-group solver must be given its halo group)
         # The collectives run on torch's current stream over zero-copy views of the library's buffers, so the library must
         # enqueue on that same stream, or nothing orders its kernels against the collectives.  The solver owns one stream
         # for both (the legacy default stream cannot be captured into a graph) and orders it against the caller's.
@@ -259,7 +279,7 @@ class SegmentedSolver:
                     if g is None:            # one graph per ping-pong parity of the pose / map buffers
                         self._stream.synchronize()
                         g = torch.cuda.CUDAGraph()
-                        side = torch.cuda.Stream(device=self.device)
+                        side = torch.cuda.Stream(device=self.device, priority=-1)
                         self.engine.set_stream(side.cuda_stream)       # (before the capture starts: set_stream synchronises)
                         with torch.cuda.graph(g, stream=side):
                             self._sweep_once()
@@ -335,6 +355,16 @@ class SegmentedSolver:
         return self.engine.get_map()
 
     def close(self):
+        """Collective when the solver created its own halo group.  Captured graphs hold NCCL work of both communicators: they are
+        dropped before a communicator goes (destroy_process_group otherwise waits forever on them)."""
+        import torch
+        self._graphs = {}
+        if torch.cuda.is_available():
+            torch.cuda.synchronize(self.device)
+        if getattr(self, "_own_halo_group", False):
+            import torch.distributed as dist
+            dist.destroy_process_group(self.halo_group)
+            self.halo_group, self._own_halo_group = None, False
         self.engine.close()
 
 
@@ -458,4 +488,10 @@ def bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, p
         }
         print(json.dumps(out), flush=True)
     dist.barrier()
+    sol.close()
+    # (the line is out and every rank is past the barrier: a communicator teardown that stalls must not hold the job)
+    import threading
+    guard = threading.Timer(30.0, lambda: os._exit(0))
+    guard.daemon = True
+    guard.start()
     dist.destroy_process_group()

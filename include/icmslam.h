@@ -172,12 +172,19 @@ int icmslam_set_batch(icmslam_handle* h, int32_t traj_T, const double* x0s, int6
  *     icmslam_seg_finish
  * with the collectives issued by the caller (NCCL through torch.distributed in icm_slam_b200/multigpu.py)
  * on the handle's stream.  The landmark statistics are integers, so every segment computes bit-identical
- * maps for any number of GPUs. */
+ * maps for any number of GPUs.
+ * With opts.reserved & 4 in icmslam_seg_begin the boundary poses travel on their own: the solve runs on the handle's
+ * low-priority side stream (ICMSLAM_PTR_SIDE_STREAM: a cudaStream_t, not device memory), the caller all-gathers
+ * ICMSLAM_PTR_SEG_REC_POSE on THAT stream (a second communicator) and hands the result to icmslam_seg_halo, while the
+ * ICMSLAM_PTR_SEG_REC gather (now only the label counts), icmslam_seg_exchange, the reduction and icmslam_seg_finish proceed
+ * on the handle's stream; icmslam_seg_finish joins the two. */
 enum { ICMSLAM_PTR_SEG_REC = 0, ICMSLAM_PTR_STAT_X = 1, ICMSLAM_PTR_STAT_Y = 2, ICMSLAM_PTR_STAT_N = 3,
-       ICMSLAM_PTR_NEW_LABELS = 4, ICMSLAM_PTR_POSES = 5, ICMSLAM_PTR_EXCHANGE = 6 };
+       ICMSLAM_PTR_NEW_LABELS = 4, ICMSLAM_PTR_POSES = 5, ICMSLAM_PTR_EXCHANGE = 6, ICMSLAM_PTR_SEG_REC_POSE = 7,
+       ICMSLAM_PTR_SIDE_STREAM = 8 };
 int icmslam_set_segment(icmslam_handle* h, int32_t t_lo, int32_t t_hi, int32_t is_first, int32_t is_last);
 int icmslam_device_ptr(icmslam_handle* h, int32_t which, void** ptr, int64_t* count);
 int icmslam_seg_begin(icmslam_handle* h, const double* x0, const icmslam_sweep_opts* opts);
+int icmslam_seg_halo(icmslam_handle* h, const double* gathered, int32_t rank, int32_t world);
 int icmslam_seg_exchange(icmslam_handle* h, const double* gathered, int32_t rank, int32_t world);
 int icmslam_seg_finish(icmslam_handle* h);
 

@@ -22,6 +22,9 @@ def digest(x, mapa):
 
 
 def main():
+    if os.environ.get("ICMSLAM_TEST_WATCHDOG"):      # (debugging aid: dump every thread's stack and exit instead of hanging)
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["ICMSLAM_TEST_WATCHDOG"]), exit=True)
     import torch
     import torch.distributed as dist
     from helpers import CONFIG_ROS
@@ -61,7 +64,7 @@ def main():
             json.dump(res, f)
         e.close()
     dist.barrier()
-    sol.close()
+    sol.close()                      # (drops the captured graphs and the solver's own halo group before the default group goes)
     dist.destroy_process_group()
 
 
