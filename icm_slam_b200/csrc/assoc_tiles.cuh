@@ -47,6 +47,7 @@ struct AssocParams {
     int skip_hints;                       // debug (ICMSLAM_HINTS=0)
     int n_tiles; int* blk_prefix; int Lcap; unsigned long long* bb;      // for the scan of the far counts (tail.cuh far_scan_block)
     DevState* stw;                        // (= st, writable: the sweep's label bookkeeping)
+    P2PDev p2p;                           // peer windows of a time-segmented run (p2p.cuh): the far count goes straight to every rank
     int final;                            // last launch of the sweep (a host-memory sweep launches one per chunk of tiles, each over the
                                           // tiles that turned dirty since the one before): scan the far counts
     RunParams R;
@@ -423,7 +424,13 @@ k_assoc_tiles(const AssocParams p)
         S.nslots = last && p.final;
     }
     __syncthreads();
-    if (S.nslots) far_scan_block(R.farbits, p.n_tiles, p.blk_prefix, p.stw, R.ts, p.Lcap, p.bb, S.rtot, reinterpret_cast<unsigned char*>(sb), p.obs_cap * 16);
+    if (S.nslots) {
+        far_scan_block(R.farbits, p.n_tiles, p.blk_prefix, p.stw, R.ts, p.Lcap, p.bb, S.rtot, reinterpret_cast<unsigned char*>(sb), p.obs_cap * 16);
+        if (p.p2p.on) {
+            __syncthreads();
+            p2p_post_far(p.p2p, *(volatile unsigned*)&R.ts->p2p_seq, *(volatile int*)&R.ts->far_total);
+        }
+    }
 }
 
 static size_t assoc_smem_bytes(int obs_cap)   // obs_cap is even

@@ -20,7 +20,7 @@ struct DevCfg {
 };
 
 // Status word written by kernels (checked by the host after the sweep).
-enum { ST_OK = 0, ST_LABEL_CAP = 1 };
+enum { ST_OK = 0, ST_LABEL_CAP = 1, /* 4: empty map */ ST_P2P_TIMEOUT = 8 };
 
 // ---- exact (non-contracted) arithmetic: nvcc fuses a*b+c into DFMA by default; where a result
 // must be bit-identical to numpy/scipy we spell out the roundings.

@@ -135,6 +135,11 @@ struct icmslam_handle {
     int64_t exch_words = 0;
     double* d_seg_rec = nullptr;  // SEG_REC doubles: what this segment tells its neighbours
     double* d_seg_rec_pose = nullptr;   // ... the boundary poses on their own when they are gathered beside the tail (icmslam_seg_halo)
+    // peer-memory exchange of a time-segmented run (p2p.cuh): this rank's window and result buffer, every rank's pointers
+    P2PDev p2p = {0, 0, 1, nullptr, nullptr, nullptr, nullptr, 0, 0};
+    P2PWin* d_win = nullptr; long long* d_res = nullptr;
+    void* p2p_opened[3 * P2P_MAX_WORLD] = {};      // mappings of the other ranks' buffers (cudaIpcOpenMemHandle)
+    void** d_p2p_ptrs = nullptr;                   // device copy of the three pointer tables
     bool seg_split = false;       // the sweep in flight exchanges its halo poses through icmslam_seg_halo
     double* seg_dst = nullptr;    // output pose buffer of the segment sweep in flight
     size_t fused_smem = 0;
@@ -232,6 +237,8 @@ extern "C" int icmslam_destroy(icmslam_handle* h)
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_tail) cudaEventDestroy(h->ev_tail);
+    for (void*& q : h->p2p_opened) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+    DFREE(h->d_win); DFREE(h->d_res); DFREE(h->d_p2p_ptrs);
     if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
     for (int i = 0; i < 16; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]); }
     delete h;
@@ -352,6 +359,8 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     { const double t1 = cfg->dist_thr * (1.0 + 9.5367431640625e-07); h->thr1sq = t1 * t1; }
     if (e == cudaSuccess) e = cudaMemset(h->d_ts, 0, sizeof(TailState));
     if (e == cudaSuccess) { const unsigned one = 1u; e = cudaMemcpy(&h->d_ts->scan_seq, &one, sizeof one, cudaMemcpyHostToDevice); }
+    if (e == cudaSuccess) { const unsigned one = 1u; e = cudaMemcpy(&h->d_ts->p2p_seq, &one, sizeof one, cudaMemcpyHostToDevice); }
+    if (e == cudaSuccess) { const unsigned one = 1u; e = cudaMemcpy(&h->d_ts->halo_seq, &one, sizeof one, cudaMemcpyHostToDevice); }
     { const char* eg = getenv("ICMSLAM_GRAPH"); if (eg) h->use_graph = atoi(eg); }
     { const char* er = getenv("ICMSLAM_RUNS"); if (er) h->use_runs = atoi(er) != 0; }
     { const char* er = getenv("ICMSLAM_SOLVE_OCC"); if (er && (atoi(er) == 4 || atoi(er) == 6)) h->solve_occ = atoi(er); }
@@ -748,6 +757,7 @@ __global__ void k_sweep_begin(DevState* st, TailState* ts, int L_in)
 
 static int status_from_state(const DevState* s)
 {
+    if (s->status & ST_P2P_TIMEOUT) return ICMSLAM_ERR_CUDA;      // a peer never posted its flag (p2p.cuh): the ranks are out of step
     if (s->status & ST_LABEL_CAP) return ICMSLAM_ERR_LABEL_CAP;
     if (s->status & 4) return ICMSLAM_ERR_EMPTY_MAP;
     return ICMSLAM_OK;
@@ -868,7 +878,7 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
     { const char* eh = getenv("ICMSLAM_HINTS"); A.skip_hints = (eh && atoi(eh) == 0) ? 1 : 0; }
     A.hints = (h->hint_map == h->d_map_in) ? 1 : 0;
     A.c = h->d_c; A.obs_cap = h->obs_cap; A.R = R;
-    A.n_tiles = h->n_tiles; A.blk_prefix = h->d_blk_prefix; A.Lcap = L; A.bb = h->d_bb; A.stw = st; A.final = 1;
+    A.n_tiles = h->n_tiles; A.blk_prefix = h->d_blk_prefix; A.Lcap = L; A.bb = h->d_bb; A.stw = st; A.final = 1; A.p2p = h->p2p;
     if (hp) {
         // ---- chunks of tiles: upload | projection parameters, run kernel, association of the tiles it hands over, solve of the
         //      poses whose moments are complete | read-back, on three streams ---------------------------------------------------
@@ -968,6 +978,11 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
             CK(cudaMemcpy2DAsync(h->d2h_x, (size_t)h->d2h_ld * 8, kout, (size_t)kld * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToHost, ss));
             h->d2h_done = true;
         }
+        if (h->p2p.on) {     // the segment's boundary poses to its neighbours, theirs into the halo columns: behind the solve
+            k_p2p_halo<<<1, 32, 0, ss>>>(h->p2p, &h->d_ts->halo_seq, kout, kld, T, h->seg_lo, h->seg_hi, pp_out, st);
+            CK(cudaGetLastError());
+            h->n_launch += 1;
+        }
         if (fork) {
             CK(cudaEventRecord(h->ev_join, ss));
             h->join_pending = true;
@@ -985,9 +1000,18 @@ static int fused_part_b(icmslam_handle* h, cudaStream_t s)
     const int L = h->Lcap;
     const int t_start = h->seg_lo - (h->seg_first ? 0 : 1);
     k_tail_labels<<<148, 256, 0, s>>>(h->d_ts, h->d_far_list, h->d_blk_prefix, h->d_farbits, RT_TILE, t_start, h->d_off, h->d_st, L, h->d_c,
-                                              h->d_newraw, h->d_newraw + L, h->d_cnt);
+                                              h->d_newraw, h->d_newraw + L, h->d_cnt, h->p2p);
     CK(cudaGetLastError());
     h->n_launch += 1;
+    if (h->p2p.on) {      // this rank's slice of every rank's statistics (a reduce-scatter by remote loads, p2p.cuh)
+        const long long mine = h->p2p.per;
+        int nb = (int)((mine + 255) / 256);
+        if (nb > 148 * 4) nb = 148 * 4;
+        if (nb < 1) nb = 1;
+        k_p2p_reduce<<<nb, 256, 0, s>>>(h->p2p, &h->d_ts->p2p_seq, &h->d_ts->reduce_ticket, h->d_st);
+        CK(cudaGetLastError());
+        h->n_launch += 1;
+    }
     return ICMSLAM_OK;
 }
 
@@ -1002,7 +1026,8 @@ static int fused_part_c(icmslam_handle* h, double* dmap_out, int out_cap, int64_
     double* raw_x = h->d_raw;
     double* raw_y = h->d_raw + L;
     k_fused_means<<<nblk(L, 256), 256, 0, s>>>(st, h->d_fsum_x, h->d_fsum_y, h->d_cnt, min_x, min_y, 1.0 / h->fix_scale, h->dcfg.cota,
-                                               h->d_newraw, raw_x, raw_y, h->d_kflag, L, h->d_blk_kept, h->d_farbits, h->n_tiles * 4);
+                                               h->d_newraw, raw_x, raw_y, h->d_kflag, L, h->d_blk_kept, h->d_farbits, h->n_tiles * 4, h->p2p, ts,
+                                               h->d_cnt, st);
     CK(cudaGetLastError());
     k_tail_compact<<<nblk(L, 256), 256, 0, s>>>(st, h->d_kflag, h->d_blk_kept, h->d_kpos, raw_x, raw_y, h->d_cnt, h->d_kx, h->d_ky, h->d_kc,
                                                 h->d_parent, h->d_bb, L, h->d_klab, h->d_rawcnt);
@@ -1371,8 +1396,11 @@ extern "C" int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const
     const int T = h->T, L = h->Lcap;
     cudaStream_t s = h->stream;
     h->last_map_L = -1;
-    if (h->first_empty) return ICMSLAM_EMPTY_FIRST_SCAN;
-    if (h->last_empty && T > 1) return ICMSLAM_ERR_EMPTY_LAST;
+    if (h->seg_first && h->first_empty) return ICMSLAM_EMPTY_FIRST_SCAN;
+    if (h->seg_last && h->last_empty && T > 1) return ICMSLAM_ERR_EMPTY_LAST;
+    if (h->p2p.on && !(h->fused_ok && o.fused && o.schedule == ICMSLAM_SCHED_REDBLACK && o.solver == ICMSLAM_SOLVER_NEWTON &&
+                       o.map_view == ICMSLAM_VIEW_PREV))
+        return ICMSLAM_ERR_UNSUPPORTED;      // only the restated parallel sweep partitions in time
     if (x) {
         CK(cudaMemcpy2DAsync(h->d_x, (size_t)T * 8, x, (size_t)ld_x * 8, (size_t)T * 8, 3, cudaMemcpyDefault, s));
         h->x_cur = 0;
@@ -1516,6 +1544,63 @@ extern "C" int icmslam_device_ptr(icmslam_handle* h, int32_t which, void** ptr, 
     return ICMSLAM_OK;
 }
 
+// ---- peer-memory exchange (p2p.cuh): the ranks of a node open each other's exchange block, window and result buffer ---------
+// icmslam_p2p_export: 3 CUDA IPC handles (64 bytes each: exchange block, window, result buffer) of this rank.
+extern "C" int icmslam_p2p_export(icmslam_handle* h, void* handles, int64_t cap_bytes)
+{
+    if (!h || !handles || cap_bytes < (int64_t)(3 * sizeof(cudaIpcMemHandle_t)) || !h->d_exch) return ICMSLAM_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->d_win) {
+        CK(cudaMalloc((void**)&h->d_win, sizeof(P2PWin)));
+        CK(cudaMemset(h->d_win, 0, sizeof(P2PWin)));
+        CK(cudaMalloc((void**)&h->d_res, (size_t)h->exch_words * 8));
+        CK(cudaMemset(h->d_res, 0, (size_t)h->exch_words * 8));
+    }
+    cudaIpcMemHandle_t* out = (cudaIpcMemHandle_t*)handles;
+    CK(cudaIpcGetMemHandle(&out[0], h->d_exch));
+    CK(cudaIpcGetMemHandle(&out[1], h->d_win));
+    CK(cudaIpcGetMemHandle(&out[2], h->d_res));
+    return ICMSLAM_OK;
+}
+
+// icmslam_p2p_import: `all` = world x 3 handles in rank order (every rank's icmslam_p2p_export, gathered by the caller).  From then
+// on icmslam_iterate on a segment handle (icmslam_set_segment) exchanges with the other ranks by itself: every rank must call it
+// with the same number of sweeps, and no NCCL collective is needed inside a sweep.  Same node only (NVLink / PCIe peer access).
+extern "C" int icmslam_p2p_import(icmslam_handle* h, int32_t rank, int32_t world, const void* all, int64_t bytes)
+{
+    if (!h || !all || world < 1 || world > P2P_MAX_WORLD || rank < 0 || rank >= world || !h->d_win ||
+        bytes < (int64_t)world * 3 * (int64_t)sizeof(cudaIpcMemHandle_t))
+        return ICMSLAM_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    const cudaIpcMemHandle_t* hs = (const cudaIpcMemHandle_t*)all;
+    void* tab[3 * P2P_MAX_WORLD] = {};
+    for (int r = 0; r < world; ++r) {
+        for (int k = 0; k < 3; ++k) {
+            void* ptr = nullptr;
+            if (r == rank) ptr = k == 0 ? (void*)h->d_exch : (k == 1 ? (void*)h->d_win : (void*)h->d_res);
+            else {
+                if (h->p2p_opened[3 * r + k]) { cudaIpcCloseMemHandle(h->p2p_opened[3 * r + k]); h->p2p_opened[3 * r + k] = nullptr; }
+                CK(cudaIpcOpenMemHandle(&ptr, hs[3 * r + k], cudaIpcMemLazyEnablePeerAccess));
+                h->p2p_opened[3 * r + k] = ptr;
+            }
+            tab[k * P2P_MAX_WORLD + r] = ptr;      // three tables of P2P_MAX_WORLD pointers: exchange blocks, windows, result buffers
+        }
+    }
+    if (!h->d_p2p_ptrs) CK(cudaMalloc((void**)&h->d_p2p_ptrs, sizeof tab));
+    CK(cudaMemcpy(h->d_p2p_ptrs, tab, sizeof tab, cudaMemcpyHostToDevice));
+    P2PDev& p = h->p2p;
+    p.on = world > 1 ? 1 : 0; p.rank = rank; p.world = world;
+    p.exch = (const long long* const*)(h->d_p2p_ptrs);
+    p.win = (P2PWin* const*)(h->d_p2p_ptrs + P2P_MAX_WORLD);
+    p.res = (const long long* const*)(h->d_p2p_ptrs + 2 * P2P_MAX_WORLD);
+    p.my_res = h->d_res;
+    p.words = h->exch_words;
+    p.per = (h->exch_words + world - 1) / world;
+    drop_graphs(h);
+    return ICMSLAM_OK;
+}
+
 // Sweep of one segment, part 1: the fused kernel on the resident poses; leaves this segment's record
 // (boundary poses, far-scan count) in the ICMSLAM_PTR_SEG_REC buffer for the all-gather.
 extern "C" int icmslam_seg_begin(icmslam_handle* h, const double* x0, const icmslam_sweep_opts* opts)
@@ -1525,6 +1610,7 @@ extern "C" int icmslam_seg_begin(icmslam_handle* h, const double* x0, const icms
     default_opts(o, opts);
     if (!(o.fused && o.schedule == ICMSLAM_SCHED_REDBLACK && o.solver == ICMSLAM_SOLVER_NEWTON && o.map_view == ICMSLAM_VIEW_PREV))
         return ICMSLAM_ERR_UNSUPPORTED;     // only the restated parallel sweep partitions in time
+    if (h->p2p.on) return ICMSLAM_ERR_UNSUPPORTED;      // (peer-memory exchange: the sweeps go through icmslam_iterate)
     h->last_map_L = -1;
     CK(cudaSetDevice(h->cfg.device));
     const int T = h->T, L = h->Lcap;

@@ -24,6 +24,7 @@
 #include "assoc.cuh"
 #include "fastgrid.cuh"
 #include "mapfilter.cuh"
+#include "p2p.cuh"
 
 struct __align__(16) FarRec {
     int t, rank, n, pad;
@@ -47,6 +48,10 @@ struct TailState {
     int nn_ticket;      // blocks of k_tail_nn that have finished (the last one closes the sweep)
     int scan_ticket;    // blocks of k_cell_scan that have finished
     unsigned scan_seq;  // launch number of k_cell_scan: tags the block totals published through global memory (starts at 1)
+    unsigned p2p_seq;   // number of the sweep in flight (starts at 1): tags the peer-memory flags of p2p.cuh
+    unsigned halo_seq;  // ... of the halo exchange on the side stream (advanced by k_p2p_halo itself)
+    int labels_ticket;  // blocks of k_tail_labels that have finished (p2p: the last one flags the statistics as final)
+    int reduce_ticket;  // blocks of k_p2p_reduce that have finished
 };
 
 // A landmark as the fused kernel reads it by label: position and the squared radius inside which an
@@ -189,13 +194,33 @@ __device__ __forceinline__ void far_label_write(const FarRec& r, int label, int 
 }
 
 __global__ void __launch_bounds__(256)
-k_tail_labels(const TailState* ts, const FarRec* __restrict__ far, const int* __restrict__ blk_prefix, const unsigned* __restrict__ farbits, int tile,
-              int t_start, const int* __restrict__ off, const DevState* st, int Lcap, int* __restrict__ c, double* __restrict__ raw_x,
-              double* __restrict__ raw_y, int* __restrict__ cnt)
+k_tail_labels(TailState* ts, const FarRec* __restrict__ far, const int* __restrict__ blk_prefix, const unsigned* __restrict__ farbits, int tile,
+              int t_start, const int* __restrict__ off, DevState* st, int Lcap, int* __restrict__ c, double* __restrict__ raw_x,
+              double* __restrict__ raw_y, int* __restrict__ cnt, const P2PDev p2p)
 {
     __shared__ int wsum[8];
+    __shared__ int s_base;
     const int nrec = ts->far_count;
-    const int lact0 = st->lact0 + ts->label_base;
+    int label_base = ts->label_base;
+    if (p2p.on) {
+        // the global numbering of the sweep's new labels: every segment's count of label-creating scans, straight from the
+        // windows (what k_seg_unpack derives from the all-gathered records on the NCCL path)
+        if (threadIdx.x == 0) {
+            int base = 0, total = 0;
+            const bool ok = p2p_wait_far(p2p, *(volatile unsigned*)&ts->p2p_seq, base, total);
+            s_base = base;
+            if (blockIdx.x == 0) {
+                ts->label_base = base;
+                st->n_far_scans = total;
+                st->raw_l = st->lact0 + total;
+                if (st->lact0 + total > Lcap) st->status = ST_LABEL_CAP;
+                if (!ok) st->status |= ST_P2P_TIMEOUT;
+            }
+        }
+        __syncthreads();
+        label_base = s_base;
+    }
+    const int lact0 = st->lact0 + label_base;
     // the scan's far observations: -1 from the association kernel, or the label an earlier sweep gave them when the scan
     // was certified on its run records (labels >= lsearch are exactly the labels created inside a sweep)
     const int ls = st->lsearch;
@@ -220,8 +245,7 @@ k_tail_labels(const TailState* ts, const FarRec* __restrict__ far, const int* __
             for (int i = off[r.t] + threadIdx.x; i < off[r.t + 1]; i += blockDim.x)
                 if (c[i] < 0 || c[i] >= ls) c[i] = label;
         }
-        return;
-    }
+    } else
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nrec; k += gridDim.x * blockDim.x) {
         const FarRec r = far[k];
         // rank in time order: label-creating scans of the tiles before this one + those of this tile before the scan
@@ -234,31 +258,60 @@ k_tail_labels(const TailState* ts, const FarRec* __restrict__ far, const int* __
         for (int i = off[r.t]; i < off[r.t + 1]; ++i)
             if (c[i] < 0 || c[i] >= ls) c[i] = label;
     }
+    if (p2p.on) {      // the last block to finish: this segment's exchange block (statistics + new labels) is final
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_base = atomicAdd(&ts->labels_ticket, 1) == (int)gridDim.x - 1;
+            if (s_base) { ts->labels_ticket = 0; __threadfence_system(); }
+        }
+        __syncthreads();
+        if (s_base) p2p_post_ready(p2p, *(volatile unsigned*)&ts->p2p_seq);
+    }
 }
 
 // raw map of the previous-map landmarks from the fixed-point statistics + keep flags for all labels;
 // clears the statistics for the next sweep.
 __global__ void __launch_bounds__(256)
-k_fused_means(const DevState* st, long long* fsum_x, long long* fsum_y, const int* __restrict__ cnt,
+k_fused_means(const DevState* st, long long* fsum_x, long long* fsum_y, const int* cnt,
               const double* __restrict__ map_x, const double* __restrict__ map_y, double inv_scale, double cota,
               double* newraw /* 2 x Lcap: means of this sweep's new labels, zero elsewhere; cleared here.  ALIASES fsum_x / fsum_y
                                 (old labels use a word as int64 sum, new labels as double mean: disjoint index ranges) */,
               double* __restrict__ raw_x, double* __restrict__ raw_y, int* __restrict__ flag, int Lcap, int* __restrict__ blk_kept,
-              unsigned* __restrict__ farbits, int n_far_words)
+              unsigned* __restrict__ farbits, int n_far_words, const P2PDev p2p, const TailState* ts, int* cnt_w, DevState* st_w)
 {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p2p.on) {      // every segment's slice of the reduced statistics is in place (and nobody reads this segment's block any more)
+        __shared__ int s_ok;
+        if (threadIdx.x == 0) {
+            s_ok = p2p_wait_all32(p2p.win[p2p.rank]->rs_done, p2p.world, *(const volatile unsigned*)&ts->p2p_seq) ? 1 : 0;
+            if (!s_ok && blockIdx.x == 0) st_w->status |= ST_P2P_TIMEOUT;
+        }
+        __syncthreads();
+        __threadfence_system();
+    }
     for (int wd = l; wd < n_far_words; wd += gridDim.x * blockDim.x) farbits[wd] = 0u;      // (k_tail_labels was their last reader)
     int keep = 0;
     if (l < Lcap) {
     const int raw_l = st->raw_l, ls = st->lsearch;
-    const int k = l < raw_l ? cnt[l] : 0;
+    long long wx, wy;      // the landmark's two statistics words: int64 sums (l < ls) or the fp64 mean of a new label
+    int kg;
+    if (p2p.on) {          // ... from the segment that reduced them (the layout of the exchange block: x | y | counts)
+        wx = p2p_word(p2p, l); wy = p2p_word(p2p, (long long)Lcap + l);
+        const long long cw = p2p_word(p2p, 2ll * Lcap + (l >> 1));
+        kg = (int)((l & 1) ? (cw >> 32) : (cw & 0xffffffffll));
+        cnt_w[l] = kg;     // (k_tail_compact reads the global count)
+    } else {
+        wx = fsum_x[l]; wy = fsum_y[l]; kg = cnt[l];
+    }
+    const int k = l < raw_l ? kg : 0;
     if (l < ls) {
-        raw_x[l] = k > 0 ? map_x[l] + ((double)fsum_x[l] * inv_scale) / (double)k : 0.0;
-        raw_y[l] = k > 0 ? map_y[l] + ((double)fsum_y[l] * inv_scale) / (double)k : 0.0;
+        raw_x[l] = k > 0 ? map_x[l] + ((double)wx * inv_scale) / (double)k : 0.0;
+        raw_y[l] = k > 0 ? map_y[l] + ((double)wy * inv_scale) / (double)k : 0.0;
     } else {
         const bool have = l < raw_l && k > 0;
-        raw_x[l] = have ? newraw[l] : 0.0;
-        raw_y[l] = have ? newraw[Lcap + l] : 0.0;
+        raw_x[l] = have ? __longlong_as_double(wx) : 0.0;
+        raw_y[l] = have ? __longlong_as_double(wy) : 0.0;
     }
     newraw[l] = 0.0; newraw[Lcap + l] = 0.0;
     fsum_x[l] = 0; fsum_y[l] = 0;
@@ -529,6 +582,7 @@ k_tail_nn(DevState* st, TailState* ts, double* __restrict__ kx, double* __restri
             __threadfence();
             ts->nn_ticket = 0;
             ts->far_count = 0; ts->n_dirty = 0;      // (consumed by k_tail_labels / the association kernel: ready for the next sweep)
+            ts->p2p_seq += 1u;
             const int n_ind = atomicAdd(&ts->n_ind, 0);
             slow = (n_ind != 0 || ts->degenerate) ? 1 : 0;
             // every old label survived in place (its position among the kept landmarks is its index) and nothing was added

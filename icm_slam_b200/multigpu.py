@@ -16,8 +16,18 @@ the restated (red-black, exact inner solve, previous-map view) sweep does (DESIG
   stream and a second communicator: the pose solve of the segment, then an all-gather of its boundary
   poses (another 16-double record) that gives every rank its halo poses for the next sweep.
 
-Collectives go through torch.distributed (NCCL on GPUs; the host logic is exercised with gloo in
-tests/test_multigpu_cpu.py).  All device work happens in libicmslam.so; this module only moves pointers.
+Two implementations of the exchange (SegmentedSolver(exchange=...), default from ICMSLAM_EXCHANGE, else "p2p"):
+
+* "p2p"  -- the library's own kernels over peer memory (csrc/p2p.cuh): the ranks open each other's buffers once with CUDA IPC
+  (the handles travel through one torch.distributed all-gather at set-up); after that a sweep is ONE call into the library per
+  rank (icmslam_iterate: a CUDA graph with the solve and the halo exchange on a low-priority branch) and no collective: far
+  counts, statistics (reduce-scatter by remote loads, the gather folded into the landmark update) and halo poses are NVLink
+  loads / stores flagged with the sweep number.  GPUs of one node.
+* "nccl" -- torch.distributed collectives between the library's seg_begin / seg_halo / seg_exchange / seg_finish calls, as
+  described above (NCCL on GPUs; the host logic is exercised with gloo in tests/test_multigpu_cpu.py).
+
+Both give bit-identical results (integer statistics), identical to one GPU.  All device work happens in libicmslam.so; this
+module only moves pointers.
 """
 from __future__ import annotations
 
@@ -114,7 +124,7 @@ class _DevBuf:
 class SegmentedSolver:
     """One instance per rank.  `group` is a torch.distributed process group (default: the world)."""
 
-    def __init__(self, config, rank: int, world: int, device: int = 0, group=None, halo_group=None, split_exchange=True):
+    def __init__(self, config, rank: int, world: int, device: int = 0, group=None, halo_group=None, split_exchange=True, exchange=None):
         """halo_group: a second process group over the same ranks for the boundary-pose exchange that runs beside the label /
         statistics exchange (created with dist.new_group when None and world > 1: a collective call, like the constructor itself
         must then be).  split_exchange=False keeps everything on one stream and one communicator."""
@@ -122,6 +132,13 @@ class SegmentedSolver:
         self.config, self.rank, self.world, self.device, self.group = config, int(rank), int(world), int(device), group
         self.halo_group = halo_group
         self.split_exchange = bool(split_exchange)
+        import os
+        self.exchange = (exchange or os.environ.get("ICMSLAM_EXCHANGE") or "p2p").lower()
+        if self.exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        if self.world == 1:
+            self.exchange = "nccl"        # (nothing to exchange: the segment calls run back to back)
+        self._p2p_on = False
         self.engine = Engine(config, device=device)
         self._views = None
         self._graphs = {}
@@ -219,10 +236,27 @@ class SegmentedSolver:
         check(e.lib.icmslam_seg_finish(e._h), e._h)
         stamp()
 
+    def timed_sweep(self):
+        """One eager sweep with the library's kernel timers on (collective); returns engine.kernel_ms()."""
+        from . import _lib
+        import torch
+        self._prepare()
+        if self._p2p_on:
+            self.engine.iterate(None, self.x0, 1, timing=True)
+        else:
+            with torch.cuda.stream(self._stream):
+                self._sweep_once(_lib.SweepOpts(_lib.SCHED["redblack"], _lib.SOLVER["newton"], _lib.VIEW["prev"], 0, 0.0, 1, 2))
+            self._steady += 1
+            self._parity ^= 1
+            self._graphs = {}
+        return self.engine.kernel_ms()
+
     def stage_times(self, n=5):
         """Mean milliseconds per stage over n eager sweeps (CUDA events on the solver's stream): what a step is made of."""
         import torch
         self._prepare()
+        if self._p2p_on:
+            return None        # (no host-visible stages: the exchange happens inside the library's kernels)
         names = ["begin: k_runs + k_assoc_tiles + k_solve_tile + far scan", "all-gather (128 B per rank)", "exchange: halo unpack + new labels",
                  "all-reduce (statistics block)", "finish: landmark update + Mapa.filtrar + grid"] if self.world > 1 else \
                 ["begin: k_runs + k_assoc_tiles + k_solve_tile + far scan", "exchange + finish"]
@@ -261,6 +295,27 @@ class SegmentedSolver:
         if getattr(self, "_stream", None) is None:
             self._stream = torch.cuda.Stream(device=self.device, priority=-1)   # (above the handle's low-priority solve stream)
             self.engine.set_stream(self._stream.cuda_stream)
+        if self.exchange == "p2p" and not self._p2p_on:
+            self._enable_p2p()
+
+    def _enable_p2p(self):
+        """Collective: every rank exports its three IPC handles, all ranks gather them and open each other's buffers."""
+        import torch
+        import torch.distributed as dist
+        from ._lib import check
+        e = self.engine
+        nbytes = 192
+        buf = C.create_string_buffer(nbytes)
+        check(e.lib.icmslam_p2p_export(e._h, buf, nbytes), e._h)
+        dev = "cuda:%d" % self.device
+        mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(dev)
+        allh = torch.empty(self.world * nbytes, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine, group=self.group)
+        raw = allh.cpu().numpy().tobytes()
+        check(e.lib.icmslam_p2p_import(e._h, self.rank, self.world, raw, len(raw)), e._h)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)         # every window is mapped everywhere before the first flag is written
+        self._p2p_on = True
 
     def sweep(self, n_sweeps: int = 1, use_graph: bool = True):
         """n_sweeps sweeps of the whole trajectory (collective: every rank calls it).  In steady state two consecutive
@@ -270,6 +325,14 @@ class SegmentedSolver:
         self._prepare()
         caller = torch.cuda.current_stream(self.device)
         self._stream.wait_stream(caller)
+        if self._p2p_on:      # the library exchanges by itself: one call, its own CUDA graph per sweep
+            n0 = self.engine.launch_count()
+            self.engine.iterate(None, self.x0, int(n_sweeps))
+            self._launches += self.engine.launch_count() - n0
+            self._launches_per_sweep = (self.engine.launch_count() - n0) // max(int(n_sweeps), 1)
+            self._steady += int(n_sweeps)
+            caller.wait_stream(self._stream)
+            return
         with torch.cuda.stream(self._stream):
             done = 0
             while done < n_sweeps:
@@ -421,15 +484,37 @@ def bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, p
     offs = sol.engine.get_extraction()["off"]
     c_own = np.ascontiguousarray(sol.engine.associations()[offs[sol.t_lo]:offs[sol.t_hi]])
     c_all = sol.gather_ragged_int32(c_own)
-    sha = result_hash(x_all, sol.get_map(), c_all)
+    m_all = sol.get_map()
+    sha = result_hash(x_all, m_all, c_all)
     # run kernel time on this rank (separate short loop: reading the events synchronises)
     kt = []
-    from . import _lib
     for _ in range(5):
-        with torch.cuda.stream(sol._stream):
-            sol._sweep_once(_lib.SweepOpts(_lib.SCHED["redblack"], _lib.SOLVER["newton"], _lib.VIEW["prev"], 0, 0.0, 1, 2))
-        kt.append(sol.engine.kernel_ms()[0])
+        kt.append(sol.timed_sweep()[0])
     stages = sol.stage_times(6)
+    # the same job with the exchange through NCCL collectives (a second solver): what the peer-memory kernels replace
+    nccl_arm = None
+    if sol.exchange == "p2p" and not os.environ.get("ICMSLAM_BENCH_SKIP_NCCL_ARM"):
+        sol2 = SegmentedSolver(cfg, rank, world, device=local_rank, exchange="nccl")
+        sol2.load(d["observations"], d["odometry"], d["velocities"], precondition=True)
+        sol2.set_map(d["map_init"])
+        sol2.set_poses(d["x_init"])
+        for _ in range(max(args.warmup, 3)):
+            sol2.sweep()
+        sol2.sweep(2)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        sol2.sweep(args.steps)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms2 = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        st2 = sol2.stage_times(6)
+        x2 = sol2.gather_poses()
+        nccl_arm = {"ms_per_step": float(ms2.item()), "stages_ms_rank0_eager": st2,
+                    "same_result": bool(np.array_equal(x2, x_all) and np.array_equal(sol2.get_map(), m_all))}
+        sol2.close()
     k_ms = torch.tensor([float(np.mean(kt))], dtype=torch.float64, device=dev)
     dist.all_reduce(k_ms, op=dist.ReduceOp.MAX)
     # end to end: host buffers in, host buffers out, every step
@@ -469,8 +554,9 @@ def bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, p
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "T": T, "L_true": L_true, "n_obs": n_tot, "landmarks_after": int(L_now), "beams": 181,
                        "seed": SEED, "mode": "redblack/newton/prev",
-                       "partition": "%d contiguous time segments (2+1 halo poses each), per sweep: 1 all-gather of 128 B/rank + "
-                                    "sum-reduction of one block of 2.5 words per landmark slot (%d slots: int64 sums / fp64 new-label means sharing words, int32 counts)" % (world, L_true * 2),
+                       "partition": "%d contiguous time segments (2+1 halo poses each), per sweep: far counts and halo poses between the ranks + "
+                                    "sum-reduction of one block of 2.5 words per landmark slot (%d slots: int64 sums / fp64 new-label means sharing words, int32 counts); "
+                                    "exchange by %s" % (world, L_true * 2, "the library's kernels over peer memory (NVLink loads/stores, csrc/p2p.cuh)" if sol.exchange == "p2p" else "NCCL collectives"),
                        "segments": [list(s) for s in sol.segments], "untimed_graph_capture_sweeps": 2,
                        "l2": "inputs larger than L2 (observations %.0f MB per rank vs 126 MB L2)" % (16 * n_tot / world / 1e6)},
             "clocks": clocks,
@@ -478,7 +564,7 @@ def bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, p
                     "d2h_bytes_per_step": int(bytes_t[1].item()), "steps": e2e_steps,
                     "call": "SegmentedSolver.set_map/set_poses/sweep/owned_poses/get_map with host numpy buffers on every rank"},
             "gpu_launches": int(launches) * args.steps * world, "gpu_launches_per_step": int(launches),
-            "result_sha256": sha, "stages_ms_rank0_eager": stages,
+            "result_sha256": sha, "stages_ms_rank0_eager": stages, "exchange": sol.exchange, "nccl_exchange_arm": nccl_arm,
             "roofline": {"bound": "hbm", "kernel": "k_runs + k_assoc_tiles (rank 0's segment)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": float(k_ms.item()),
                          "algorithmic_bytes": int(seg_bytes),

@@ -187,6 +187,14 @@ int icmslam_seg_begin(icmslam_handle* h, const double* x0, const icmslam_sweep_o
 int icmslam_seg_halo(icmslam_handle* h, const double* gathered, int32_t rank, int32_t world);
 int icmslam_seg_exchange(icmslam_handle* h, const double* gathered, int32_t rank, int32_t world);
 int icmslam_seg_finish(icmslam_handle* h);
+/* The same exchange by the library's own kernels over peer memory (csrc/p2p.cuh; the ranks of ONE node): every rank exports three
+ * CUDA IPC handles (3 x 64 bytes), the caller gathers them in rank order and hands the table to every rank.  From then on
+ * icmslam_iterate(h, NULL, 0, x0, n, ...) on the segment handles -- called by every rank with the same n -- runs whole sweeps with
+ * no collective from outside: far counts, statistics (reduce-scatter by remote loads, the gather folded into the landmark
+ * update) and halo poses travel through NVLink stores / loads, flagged with the sweep number.  Results are bit-identical to the
+ * collective path and to one GPU. */
+int icmslam_p2p_export(icmslam_handle* h, void* handles, int64_t cap_bytes);
+int icmslam_p2p_import(icmslam_handle* h, int32_t rank, int32_t world, const void* all_handles, int64_t bytes);
 
 /* -- pass 0 (causal initialisation, sensors.py:51-123).  icmslam_fcluster is the one scipy call of its first
  * step: c = fcluster(linkage(pdist(obs)), dist_thr) - 1 (ICM_SLAM.py:161; single linkage, inconsistency

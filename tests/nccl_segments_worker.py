@@ -42,15 +42,21 @@ def main():
     # two landmarks missing from the initial map: their observations are far, scans create labels on both segments
     map0 = np.delete(d["map_init"], [17, 640], axis=1)
     cfg = ConfigICM.from_values(**dict(CONFIG_ROS, L=2 * L_true + 64, cota=20.0))
-    sol = SegmentedSolver(cfg, rank, world, device=local)
-    sol.load(d["observations"], d["odometry"], d["velocities"], precondition=True)
-    sol.set_map(map0)
-    sol.set_poses(d["x_init"])
-    sol.sweep(nsweeps)                       # eager sweeps, then the captured two-sweep graph
-    torch.cuda.synchronize()
-    x_seg = sol.gather_poses()
-    m_seg = sol.get_map()
-    res = {"segmented": digest(x_seg, m_seg)}
+    res = {}
+    sols = []
+    for exchange in ("p2p", "nccl"):         # the library's peer-memory kernels / NCCL collectives between the segment calls
+        sol = SegmentedSolver(cfg, rank, world, device=local, exchange=exchange)
+        sol.load(d["observations"], d["odometry"], d["velocities"], precondition=True)
+        sol.set_map(map0)
+        sol.set_poses(d["x_init"])
+        sol.sweep(3)                         # eager sweeps, then the captured graphs
+        sol.sweep(nsweeps - 3)
+        torch.cuda.synchronize()
+        x_seg = sol.gather_poses()
+        m_seg = sol.get_map()
+        res["segmented_" + exchange] = digest(x_seg, m_seg)
+        sols.append(sol)
+    res["segmented"] = res["segmented_p2p"]
     if rank == 0:
         e = Engine(cfg, device=local)
         e.load(d["observations"], d["odometry"], d["velocities"], precondition=True)
@@ -64,7 +70,8 @@ def main():
             json.dump(res, f)
         e.close()
     dist.barrier()
-    sol.close()                      # (drops the captured graphs and the solver's own halo group before the default group goes)
+    for sol in sols:
+        sol.close()                  # (drops the captured graphs and the solver's own halo group before the default group goes)
     dist.destroy_process_group()
 
 
