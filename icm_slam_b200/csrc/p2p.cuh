@@ -91,10 +91,12 @@ k_p2p_reduce(const P2PDev p, const unsigned* seq_ptr, int* ticket, DevState* st)
 {
     __shared__ int s_ok;
     const unsigned seq = *(const volatile unsigned*)seq_ptr;
-    if (threadIdx.x == 0) s_ok = p2p_wait_all32(p.win[p.rank]->ready, p.world, seq) ? 1 : 0;
+    if (threadIdx.x == 0) {
+        s_ok = p2p_wait_all32(p.win[p.rank]->ready, p.world, seq) ? 1 : 0;
+        __threadfence_system();      // (acquire: the polling thread fences, the barrier carries it to the block)
+    }
     __syncthreads();
     if (!s_ok) { if (threadIdx.x == 0 && blockIdx.x == 0) st->status |= ST_P2P_TIMEOUT; }
-    __threadfence_system();
     const long long lo = p.per * p.rank, hi = min(lo + p.per, p.words);
     for (long long w = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; w < hi; w += (long long)gridDim.x * blockDim.x) {
         long long s = 0;

@@ -286,9 +286,9 @@ k_fused_means(const DevState* st, long long* fsum_x, long long* fsum_y, const in
         if (threadIdx.x == 0) {
             s_ok = p2p_wait_all32(p2p.win[p2p.rank]->rs_done, p2p.world, *(const volatile unsigned*)&ts->p2p_seq) ? 1 : 0;
             if (!s_ok && blockIdx.x == 0) st_w->status |= ST_P2P_TIMEOUT;
+            __threadfence_system();
         }
         __syncthreads();
-        __threadfence_system();
     }
     for (int wd = l; wd < n_far_words; wd += gridDim.x * blockDim.x) farbits[wd] = 0u;      // (k_tail_labels was their last reader)
     int keep = 0;

@@ -510,10 +510,10 @@ def bench(args, rank, world, local_rank, WORKLOADS, SEED, METRIC, sweep_bytes, p
         torch.cuda.synchronize()
         ms2 = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-        st2 = sol2.stage_times(6)
         x2 = sol2.gather_poses()
-        nccl_arm = {"ms_per_step": float(ms2.item()), "stages_ms_rank0_eager": st2,
-                    "same_result": bool(np.array_equal(x2, x_all) and np.array_equal(sol2.get_map(), m_all))}
+        same = bool(np.array_equal(x2, x_all) and np.array_equal(sol2.get_map(), m_all))
+        st2 = sol2.stage_times(6)
+        nccl_arm = {"ms_per_step": float(ms2.item()), "stages_ms_rank0_eager": st2, "same_result": same}
         sol2.close()
     k_ms = torch.tensor([float(np.mean(kt))], dtype=torch.float64, device=dev)
     dist.all_reduce(k_ms, op=dist.ReduceOp.MAX)
