@@ -310,8 +310,8 @@ def run_gpu(args, rank, world, local_rank):
     eng.set_poses(x_init)                 # ICM.positions resident on the device
     eng.set_map(map_init)
     x_dev = None
-    for _ in range(args.warmup):
-        eng.iterate(x_dev, x0, 1, **mode)
+    for _ in range(args.warmup + 2):      # (+2: the N > 1 arm runs two more untimed sweeps; result_sha256 is taken after the
+        eng.iterate(x_dev, x0, 1, **mode)  #  same number of sweeps for every N, so the lines of a scaling run carry one hash)
     torch.cuda.synchronize()
     lc0 = eng.launch_count()
     sampler = ClockSampler(local_rank)

@@ -66,10 +66,14 @@ k_fgrid_bbox(const double* __restrict__ px, const double* __restrict__ py, const
     }
 }
 
-// cell edge h = 2*thr1*(1+2^-20) grown by 25 % steps until the grid fits the cell budget
+// A landmark is registered with the radius thr1 + FG_MARGIN * dist_thr: the cell lists then stay valid (supersets of what a query
+// needs) while every landmark is within the margin of where it was when the grid was built, which lets a sweep that neither
+// adds, drops nor merges a landmark keep the grid and only refresh the stored coordinates (tail.cuh k_tail_steady).
+#define FG_MARGIN 0.05
+// cell edge h = 2*(thr1 + margin)*(1+2^-20) grown by 25 % steps until the grid fits the cell budget
 __device__ __forceinline__ FGeom fgrid_make_geom(double mnx, double mny, double mxx, double mxy, double dist_thr, int max_cells)
 {
-    const double thr1 = dist_thr * (1.0 + 9.5367431640625e-07);   // 1 + 2^-20
+    const double thr1 = dist_thr * (1.0 + 9.5367431640625e-07) + FG_MARGIN * dist_thr;   // 1 + 2^-20, plus the margin
     double h = 2.0 * thr1 * (1.0 + 9.5367431640625e-07);
     if (!(h > 0.0)) h = 1.0;
     const double ex = mxx - mnx, ey = mxy - mny;
@@ -127,21 +131,28 @@ k_fgrid_count(const double* __restrict__ px, const double* __restrict__ py, cons
 
 __global__ void __launch_bounds__(256)
 k_fgrid_fill(const double* __restrict__ px, const double* __restrict__ py, const int* __restrict__ n_ptr, const FGeom* __restrict__ geom,
-             const int* __restrict__ cell_start, int* __restrict__ cell_fill, double2* __restrict__ pts, int* __restrict__ idx)
+             const int* __restrict__ cell_start, int* __restrict__ cell_fill, double2* __restrict__ pts, int* __restrict__ idx,
+             int4* __restrict__ slots = nullptr /* where each landmark's (at most 4) entries went */, const int* skip = nullptr)
 {
+    if (skip && *skip) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *n_ptr) return;
     const FGeom g = *geom;
     const double x = px[i], y = py[i];
     int cx0, cx1, cy0, cy1;
     fgrid_cell_range(g, x, y, cx0, cx1, cy0, cy1);
+    int sl[4] = {-1, -1, -1, -1};
+    int r = 0;
     for (int cy = cy0; cy <= cy1; ++cy)
         for (int cx = cx0; cx <= cx1; ++cx) {
             const int c = cy * g.nx + cx;
             const int p = cell_start[c] + atomicSub(cell_fill + c, 1) - 1;   // counts the cell back down to zero
             pts[p] = make_double2(x, y);
             idx[p] = i;
+            if (r < 4) sl[r] = p;
+            ++r;
         }
+    if (slots) slots[i] = make_int4(sl[0], sl[1], sl[2], sl[3]);
 }
 
 // Nearest landmark of (wx, wy) among the cell's entries [s, e).  Returns the winner's position in the

@@ -94,6 +94,9 @@ struct icmslam_handle {
     const double* hint_map = nullptr;   // the map buffer for which c[] (through d_remap) holds last sweep's labels
     LmRec* d_lmrec2[2] = {nullptr, nullptr};   // landmarks of a map by label (position + hint radius): the current map's in
     int lm_cur = 0;                            // d_lmrec2[lm_cur], the tail writes the new map's into the other one
+    // the steady tail (tail.cuh k_tail_steady): where every landmark was when the grid was built, a lower bound of its distance to
+    // any other landmark then, the positions of its grid entries, per-block calc_cambio partials
+    double2* d_gbuild = nullptr; double* d_nnd0 = nullptr; int4* d_gslots = nullptr; double* d_cpart = nullptr; int steady_enable = 1;
     int* d_blk_kept = nullptr;                 // kept landmarks per block of k_fused_means
     int* d_rawcnt = nullptr;                   // observation counts of the last fused sweep's raw map (the tail clears d_cnt)
     bool rawcnt_valid = false;
@@ -229,7 +232,7 @@ extern "C" int icmslam_destroy(icmslam_handle* h)
     DFREE(h->d_st); DFREE(h->d_cub); DFREE(h->d_sort_ws);
     DFREE(h->d_exch); DFREE(h->d_fg_cnt); DFREE(h->d_fg_start); DFREE(h->d_fg_idx);
     DFREE(h->d_fg_pts); DFREE(h->d_fg_geom); DFREE(h->d_bb); DFREE(h->d_ts); DFREE(h->d_seg_rec); DFREE(h->d_seg_rec_pose);
-    DFREE(h->d_lmrec2[0]); DFREE(h->d_lmrec2[1]); DFREE(h->d_blk_kept); DFREE(h->d_rawcnt); DFREE(h->d_scan_state); DFREE(h->d_remap); DFREE(h->d_nnd2); DFREE(h->d_klab); DFREE(h->d_aobs); DFREE(h->d_ac);
+    DFREE(h->d_lmrec2[0]); DFREE(h->d_lmrec2[1]); DFREE(h->d_blk_kept); DFREE(h->d_rawcnt); DFREE(h->d_gbuild); DFREE(h->d_nnd0); DFREE(h->d_gslots); DFREE(h->d_cpart); DFREE(h->d_scan_state); DFREE(h->d_remap); DFREE(h->d_nnd2); DFREE(h->d_klab); DFREE(h->d_aobs); DFREE(h->d_ac);
     if (h->h_st) cudaFreeHost(h->h_st);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -347,6 +350,11 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     if (e == cudaSuccess) e = dalloc(&h->d_lmrec2[1], L);
     if (e == cudaSuccess) e = dalloc(&h->d_blk_kept, (size_t)nblk((int)L, 256) + 1);
     if (e == cudaSuccess) e = dalloc(&h->d_rawcnt, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_gbuild, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_nnd0, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_gslots, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_cpart, (size_t)4 * (nblk((int)L, 256) + 1));
+    { const char* es = getenv("ICMSLAM_STEADY"); if (es) h->steady_enable = atoi(es) != 0; }
     if (e == cudaSuccess) e = dalloc(&h->d_scan_state, (size_t)nblk(h->fg_cells + 1, CS_THREADS * CS_ITEMS) + 1);
     if (e == cudaSuccess) e = dalloc(&h->d_remap, L);
     if (e == cudaSuccess) e = dalloc(&h->d_klab, L);
@@ -1025,25 +1033,39 @@ static int fused_part_c(icmslam_handle* h, double* dmap_out, int out_cap, int64_
     const double* min_y = h->d_map_in + L;
     double* raw_x = h->d_raw;
     double* raw_y = h->d_raw + L;
+    {
+        SteadyArgs a;
+        a.fsum_x = h->d_fsum_x; a.fsum_y = h->d_fsum_y; a.cnt = h->d_cnt; a.map_x = min_x; a.map_y = min_y;
+        a.inv_scale = 1.0 / h->fix_scale; a.cota = h->dcfg.cota; a.dist_thr = h->dcfg.dist_thr; a.thr1sq = h->thr1sq; a.thr2_hi = h->thr2_hi;
+        a.lmrec_old = h->d_lmrec2[h->lm_cur]; a.lmrec_new = h->d_lmrec2[h->lm_cur ^ 1];
+        a.gbuild = h->d_gbuild; a.nnd0 = h->d_nnd0; a.gslots = h->d_gslots; a.gpts = h->d_fg_pts;
+        a.raw_x = raw_x; a.raw_y = raw_y; a.rawcnt = h->d_rawcnt;
+        a.map_out = dmap_out; a.cap_out = out_cap; a.ld_out = out_ld; a.counts_state = h->d_counts; a.remap = h->d_remap; a.Lcap = L;
+        a.cpart = h->d_cpart;
+        k_tail_steady<<<nblk(L, 256), 256, 0, s>>>(st, ts, a, h->p2p);
+        CK(cudaGetLastError());
+        h->n_launch += 1;
+    }
     k_fused_means<<<nblk(L, 256), 256, 0, s>>>(st, h->d_fsum_x, h->d_fsum_y, h->d_cnt, min_x, min_y, 1.0 / h->fix_scale, h->dcfg.cota,
                                                h->d_newraw, raw_x, raw_y, h->d_kflag, L, h->d_blk_kept, h->d_farbits, h->n_tiles * 4, h->p2p, ts,
                                                h->d_cnt, st);
     CK(cudaGetLastError());
     k_tail_compact<<<nblk(L, 256), 256, 0, s>>>(st, h->d_kflag, h->d_blk_kept, h->d_kpos, raw_x, raw_y, h->d_cnt, h->d_kx, h->d_ky, h->d_kc,
-                                                h->d_parent, h->d_bb, L, h->d_klab, h->d_rawcnt);
+                                                h->d_parent, h->d_bb, L, h->d_klab, h->d_rawcnt, ts);
     CK(cudaGetLastError());
     k_tail_count<<<nblk(L, 256), 256, 0, s>>>(h->d_kx, h->d_ky, st, ts, h->d_bb, h->dcfg.dist_thr, h->fg_cells, h->d_fg_geom, h->d_fg_cnt);
     CK(cudaGetLastError());
     k_cell_scan<<<nblk(h->fg_cells + 1, CS_THREADS * CS_ITEMS), CS_THREADS, 0, s>>>(h->d_fg_cnt, h->d_fg_start, h->fg_cells + 1, h->d_scan_state, ts);
     CK(cudaGetLastError());
     k_fgrid_fill<<<nblk(L, 256), 256, 0, s>>>(h->d_kx, h->d_ky, &st->kept, h->d_fg_geom, h->d_fg_start, h->d_fg_cnt, h->d_fg_pts,
-                                              h->d_fg_idx);
+                                              h->d_fg_idx, h->d_gslots, &ts->steady_ok);
     CK(cudaGetLastError());
     {
         SlowArgs sa;
         sa.dist_thr = h->dcfg.dist_thr; sa.parent = h->d_parent; sa.ind_pos = h->d_indpos; sa.ind = h->d_ind; sa.lab = h->d_lab; sa.used = h->d_used;
         sa.rank = h->d_rank; sa.ox = h->d_ox; sa.oy = h->d_oy; sa.oc = h->d_oc; sa.max_cells = h->fg_cells; sa.geom = h->d_fg_geom;
         sa.cell_cnt = h->d_fg_cnt; sa.cell_start = h->d_fg_start; sa.pts = h->d_fg_pts; sa.gidx = h->d_fg_idx;
+        sa.gbuild = h->d_gbuild; sa.nnd0 = h->d_nnd0; sa.steady_enable = h->steady_enable;
         k_tail_nn<<<nblk(L, 256), 256, 0, s>>>(st, ts, h->d_kx, h->d_ky, h->d_kc, h->d_fg_geom, h->d_fg_start, h->d_fg_pts, h->d_fg_idx, h->thr2_lt,
                                                h->d_nn, h->d_indflag, L, h->d_klab, h->d_kflag, h->d_kpos, h->d_lmrec2[h->lm_cur],
                                                h->d_lmrec2[h->lm_cur ^ 1], dmap_out, out_cap, out_ld, h->d_counts, h->thr1sq, h->thr2_hi, h->d_remap, sa);
@@ -1780,7 +1802,7 @@ extern "C" int icmslam_get_sweep_stats(icmslam_handle* h, int64_t* stats, int32_
     TailState hts;
     CK(cudaMemcpy(&hts, h->d_ts, sizeof(TailState), cudaMemcpyDeviceToHost));
     int64_t v[16] = {(int64_t)s->newton_iters, s->n_far_scans, s->raw_l, s->kept, s->new_l, s->n_ind, s->lsearch, s->status, s->dirty_tiles,
-                     hts.epoch, (int64_t)h->n_tiles, hts.remap_identity, (int64_t)(h->last_runs_ms * 1e6), hts.n_dirty, hts.far_count, 0};
+                     hts.epoch, (int64_t)h->n_tiles, hts.remap_identity, (int64_t)(h->last_runs_ms * 1e6), hts.n_dirty, hts.far_count, hts.steady_sweeps};
     for (int i = 0; i < n && i < 16; ++i) stats[i] = v[i];
     return ICMSLAM_OK;
 }

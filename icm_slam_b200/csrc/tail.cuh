@@ -52,6 +52,10 @@ struct TailState {
     unsigned halo_seq;  // ... of the halo exchange on the side stream (advanced by k_p2p_halo itself)
     int labels_ticket;  // blocks of k_tail_labels that have finished (p2p: the last one flags the statistics as final)
     int reduce_ticket;  // blocks of k_p2p_reduce that have finished
+    // the steady tail (k_tail_steady): armed by a full chain that ended without a merge, for the K landmarks it left
+    int steady_armed, steady_K, steady_fail, steady_ticket;
+    int steady_ok;      // verdict of this sweep's k_tail_steady: 1 = the full chain has nothing to do
+    int steady_sweeps;  // sweeps closed by the steady tail since the handle was created (instrumentation)
 };
 
 // A landmark as the fused kernel reads it by label: position and the squared radius inside which an
@@ -281,6 +285,11 @@ k_fused_means(const DevState* st, long long* fsum_x, long long* fsum_y, const in
               unsigned* __restrict__ farbits, int n_far_words, const P2PDev p2p, const TailState* ts, int* cnt_w, DevState* st_w)
 {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ts->steady_ok) {      // the steady tail closed the sweep: only the statistics remain to be cleared for the next one
+        for (int wd = l; wd < n_far_words; wd += gridDim.x * blockDim.x) farbits[wd] = 0u;
+        if (l < Lcap) { newraw[l] = 0.0; newraw[Lcap + l] = 0.0; fsum_x[l] = 0; fsum_y[l] = 0; cnt_w[l] = 0; if (l == Lcap - 1) cnt_w[Lcap] = 0; }
+        return;
+    }
     if (p2p.on) {      // every segment's slice of the reduced statistics is in place (and nobody reads this segment's block any more)
         __shared__ int s_ok;
         if (threadIdx.x == 0) {
@@ -329,8 +338,9 @@ __global__ void __launch_bounds__(256)
 k_tail_compact(DevState* st, const int* __restrict__ flag, const int* __restrict__ blk_kept, int* __restrict__ pos,
                const double* __restrict__ raw_x, const double* __restrict__ raw_y, int* __restrict__ cnt, double* __restrict__ kx,
                double* __restrict__ ky, double* __restrict__ kc, int* __restrict__ parent, unsigned long long* bb, int Lcap,
-               int* __restrict__ klab, int* __restrict__ rawcnt)
+               int* __restrict__ klab, int* __restrict__ rawcnt, const TailState* ts)
 {
+    if (ts->steady_ok) return;
     __shared__ int wpart[8], wcnt[8];
     __shared__ double red[4][8];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -384,6 +394,7 @@ __global__ void __launch_bounds__(256)
 k_tail_count(const double* __restrict__ kx, const double* __restrict__ ky, const DevState* st, TailState* ts, const unsigned long long* bb,
              double dist_thr, int max_cells, FGeom* out, int* __restrict__ cell_cnt)
 {
+    if (ts->steady_ok) return;
     __shared__ FGeom sg;
     const int n = st->kept;
     if (threadIdx.x == 0) {
@@ -410,6 +421,7 @@ k_tail_count(const double* __restrict__ kx, const double* __restrict__ ky, const
 __global__ void __launch_bounds__(CS_THREADS)
 k_cell_scan(const int* __restrict__ in, int* __restrict__ out, int n, unsigned long long* state, TailState* ts)
 {
+    if (ts->steady_ok) return;
     __shared__ int wsum[32];
     __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
@@ -473,6 +485,7 @@ struct SlowArgs {
     int* parent; int* ind_pos; int* ind; int* lab; int* used; int* rank;
     double* ox; double* oy; double* oc;
     int max_cells; FGeom* geom; int* cell_cnt; int* cell_start; double2* pts; int* gidx;
+    double2* gbuild; double* nnd0; int steady_enable;      // for the steady tail of the next sweeps
 };
 
 __device__ void tail_slow_body(DevState* st, TailState* ts, double dist_thr, double* kx, double* ky, double* kc, int* parent, int* nn, int* ind_flag,
@@ -496,6 +509,7 @@ k_tail_nn(DevState* st, TailState* ts, double* __restrict__ kx, double* __restri
           LmRec* lmrec_new, double* map_out, int cap_out, int64_t ld_out, double* counts_state, double thr1sq, double thr2_hi,
           int* remap, const SlowArgs sa)
 {
+    if (ts->steady_ok) return;
     __shared__ double red[3][8];
     __shared__ int redn[2][8];
     __shared__ int s_last, s_slow;
@@ -561,6 +575,10 @@ k_tail_nn(DevState* st, TailState* ts, double* __restrict__ kx, double* __restri
         rec.x = mx; rec.y = my; rec.r2 = act ? hint_radius2(wide, 4.0 * thr1sq, thr2_hi) : 0.0; rec.r = __dsqrt_rd(rec.r2);
         lmrec_new[j] = rec;
         remap[j] = (j < st->raw_l && kflag[j]) ? kpos[j] : -1;      // label of this sweep -> index in the new map
+        if (act) {      // what the steady tail of the next sweeps starts from (k_tail_steady)
+            sa.gbuild[j] = make_double2(mx, my);
+            sa.nnd0[j] = __dsqrt_rd(fmin(wide, 4.0 * thr1sq));
+        }
     }
     // block totals -> one set of atomics per block
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -591,6 +609,8 @@ k_tail_nn(DevState* st, TailState* ts, double* __restrict__ kx, double* __restri
             // run records (runs.cuh) name landmarks by index: void every one of them when landmark indices changed
             if (!identity) ts->epoch += 1;
             if (!slow) { st->new_l = K; st->lact = K; st->n_ind = 0; ts->remap_identity = identity; }
+            ts->steady_armed = (!slow && sa.steady_enable) ? 1 : 0;      // (a merged map is rebuilt by one block without the steady tail's inputs)
+            ts->steady_K = K;
         }
         s_last = last; s_slow = slow;
     }
@@ -599,6 +619,154 @@ k_tail_nn(DevState* st, TailState* ts, double* __restrict__ kx, double* __restri
     tail_slow_body(st, ts, sa.dist_thr, kx, ky, kc, sa.parent, nn, ind_flag, sa.ind_pos, sa.ind, sa.lab, sa.used, sa.rank, sa.ox, sa.oy, sa.oc,
                    map_out, cap_out, ld_out, counts_state, Lcap, sa.max_cells, sa.geom, sa.cell_cnt, sa.cell_start, sa.pts, sa.gidx, kflag, kpos,
                    thr1sq, thr2_hi, lmrec_new, remap);
+}
+
+
+// ---- the steady tail ------------------------------------------------------------------------------------------------------
+// A sweep that neither adds, drops nor merges a landmark -- every sweep of a converging run after the first few -- needs none
+// of the filter's machinery: the new map is the means, in place; the landmark grid stays valid while every landmark is within
+// FG_MARGIN * dist_thr of where it was when the grid was built (fastgrid.cuh) and only its stored coordinates are refreshed; and
+// the proven radius follows from a bound instead of a neighbour search: with nnd0 a lower bound of the distance from landmark i
+// to any other landmark at build time and D the displacement since then (<= margin for all of them),
+// |p_i' - p_j'| >= nnd0_i - D_i - D_j >= nnd0_i - D_i - margin, which is also what rules out a merge (> dist_thr).
+// Every thread checks its landmark and writes its results on the assumption that all checks pass (nothing it writes is an input of
+// the full chain, which overwrites all of it); the last block to finish publishes the verdict in ts->steady_ok: 1 = done, the
+// kernels of the full chain return at once (k_fused_means only clears the statistics); 0 = the full chain runs as if this
+// kernel had not.  What is computed is bit-identical either way (same expressions for the map; the radius differs, and a radius
+// only decides which exact path labels an observation).
+struct SteadyArgs {
+    const long long* fsum_x; const long long* fsum_y; const int* cnt;
+    const double* map_x; const double* map_y;
+    double inv_scale, cota, dist_thr, thr1sq, thr2_hi;
+    const LmRec* lmrec_old; LmRec* lmrec_new;
+    const double2* gbuild; const double* nnd0; const int4* gslots; double2* gpts;
+    double* raw_x; double* raw_y; int* rawcnt;
+    double* map_out; int cap_out; int64_t ld_out; double* counts_state; int* remap; int Lcap;
+    double* cpart;      // 5 doubles per block: calc_cambio partials (min, max, sum, resolved?, unresolved)
+};
+
+__global__ void __launch_bounds__(256)
+k_tail_steady(DevState* st, TailState* ts, const SteadyArgs a, const P2PDev p2p)
+{
+    __shared__ double red[3][8];
+    __shared__ int redn[2][8];
+    __shared__ int s_flag;
+    const int K = ts->steady_K, ls = st->lsearch;
+    if (!(ts->steady_armed && ls == K && st->lact0 == K && K > 0)) {      // (the same for every block)
+        if (blockIdx.x == 0 && threadIdx.x == 0) ts->steady_ok = 0;
+        return;
+    }
+    if (p2p.on) {      // every segment's slice of the reduced statistics is in place
+        if (threadIdx.x == 0) {
+            s_flag = p2p_wait_all32(p2p.win[p2p.rank]->rs_done, p2p.world, *(const volatile unsigned*)&ts->p2p_seq) ? 1 : 0;
+            if (!s_flag && blockIdx.x == 0) st->status |= ST_P2P_TIMEOUT;
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    const int raw_l = st->raw_l;
+    const double margin = FG_MARGIN * a.dist_thr;
+    int fail = 0, cres = 0, cun = 0;
+    double cd = 0.0;
+    if (l < a.Lcap) {
+        long long wx, wy;
+        int kg;
+        if (p2p.on) {
+            wx = p2p_word(p2p, l); wy = p2p_word(p2p, (long long)a.Lcap + l);
+            const long long cw = p2p_word(p2p, 2ll * a.Lcap + (l >> 1));
+            kg = (int)((l & 1) ? (cw >> 32) : (cw & 0xffffffffll));
+        } else {
+            wx = a.fsum_x[l]; wy = a.fsum_y[l]; kg = a.cnt[l];
+        }
+        const int k = l < raw_l ? kg : 0;
+        LmRec rec;
+        rec.x = 0.0; rec.y = 0.0; rec.r2 = 0.0; rec.r = 0.0;
+        double mx = 0.0, my = 0.0, c = 0.0, rx = 0.0, ry = 0.0;
+        if (l < ls) {
+            if ((double)k < a.cota) fail = 1;                      // the landmark would be dropped (ICM_SLAM.py:232-236)
+            else {
+                c = (double)k;
+                rx = a.map_x[l] + ((double)wx * a.inv_scale) / c;      // k_fused_means
+                ry = a.map_y[l] + ((double)wy * a.inv_scale) / c;
+                mx = mul_rn(rx, c) / c; my = mul_rn(ry, c) / c;      // k_tail_nn (count-weighted mean of one member, :258-260)
+                const LmRec o = a.lmrec_old[l];
+                const double d = dist_rn(mx - o.x, my - o.y);
+                if (d < o.r * (1.0 - 1e-9)) { cres = 1; cd = d; }
+                cun = 1 - cres;
+                const double2 gb = a.gbuild[l];
+                const double D = dist_rn(mx - gb.x, my - gb.y) * (1.0 + 1e-12);
+                const double nb = a.nnd0[l] - D - margin;             // lower bound of the distance to any other landmark now
+                if (!(D <= margin) || !(nb > a.dist_thr * (1.0 + 1e-9))) fail = 1;
+                rec.x = mx; rec.y = my;
+                rec.r2 = nb > 0.0 ? hint_radius2(nb * nb, 4.0 * a.thr1sq, a.thr2_hi) : 0.0;
+                rec.r = __dsqrt_rd(rec.r2);
+                const int4 s4 = a.gslots[l];
+                const double2 np_ = make_double2(mx, my);
+                if (s4.x >= 0) a.gpts[s4.x] = np_;
+                if (s4.y >= 0) a.gpts[s4.y] = np_;
+                if (s4.z >= 0) a.gpts[s4.z] = np_;
+                if (s4.w >= 0) a.gpts[s4.w] = np_;
+            }
+            a.remap[l] = l;
+        } else {
+            const bool have = l < raw_l && k > 0;
+            if (l < raw_l && !((double)k < a.cota)) fail = 1;        // a label created in this sweep would be kept
+            rx = have ? __longlong_as_double(wx) : 0.0;
+            ry = have ? __longlong_as_double(wy) : 0.0;
+            a.remap[l] = -1;
+        }
+        a.raw_x[l] = rx; a.raw_y[l] = ry; a.rawcnt[l] = kg;
+        if (l < a.cap_out) { a.map_out[l] = mx; a.map_out[a.ld_out + l] = my; }
+        a.counts_state[l] = c;
+        a.lmrec_new[l] = rec;
+    }
+    // block partials of calc_cambio and of the verdict
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const double mn = warp_min(cres ? cd : INFINITY), mxv = warp_max(cres ? cd : 0.0), sm = warp_sum(cd);
+    const int un = warp_sum_i(cun), fl = warp_sum_i(fail);
+    if (lane == 0) { red[0][w] = mn; red[1][w] = mxv; red[2][w] = sm; redn[0][w] = un; redn[1][w] = fl; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double p0 = red[0][0], p1 = red[1][0], p2 = red[2][0];
+        int u = redn[0][0], f = redn[1][0];
+        for (int q = 1; q < (int)(blockDim.x >> 5); ++q) { p0 = fmin(p0, red[0][q]); p1 = fmax(p1, red[1][q]); p2 += red[2][q]; u += redn[0][q]; f += redn[1][q]; }
+        double* cp = a.cpart + (size_t)blockIdx.x * 4;
+        cp[0] = p0; cp[1] = p1; cp[2] = p2; cp[3] = (double)u;
+        if (f) atomicOr(&ts->steady_fail, 1);
+        __threadfence();
+        s_flag = atomicAdd(&ts->steady_ticket, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_flag) return;
+    // ---- last block: the verdict, and when it is "done" what the end of the full chain would have left ---------------------------
+    __threadfence();
+    const int ok = atomicOr(&ts->steady_fail, 0) == 0;
+    double p0 = INFINITY, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+    if (ok)
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+            const double* cp = a.cpart + (size_t)b * 4;
+            p0 = fmin(p0, __ldcg(cp)); p1 = fmax(p1, __ldcg(cp + 1)); p2 += __ldcg(cp + 2); p3 += __ldcg(cp + 3);
+        }
+    p0 = warp_min(p0); p1 = warp_max(p1); p2 = warp_sum(p2); p3 = warp_sum(p3);
+    __syncthreads();
+    if (lane == 0) { red[0][w] = p0; red[1][w] = p1; red[2][w] = p2; redn[0][w] = (int)p3; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ts->steady_ticket = 0;
+        ts->steady_fail = 0;
+        ts->steady_ok = ok;
+        if (ok) {
+            for (int q = 1; q < (int)(blockDim.x >> 5); ++q) { red[0][0] = fmin(red[0][0], red[0][q]); red[1][0] = fmax(red[1][0], red[1][q]); red[2][0] += red[2][q]; redn[0][0] += redn[0][q]; }
+            if (red[0][0] < INFINITY) { st->cambio[0] = red[0][0]; st->cambio[1] = red[1][0]; st->cambio[2] = red[2][0]; }
+            st->cambio_unres = redn[0][0];
+            st->kept = K; st->new_l = K; st->lact = K; st->n_ind = 0;
+            ts->n_ind = 0; ts->remap_identity = 1;
+            ts->far_count = 0; ts->n_dirty = 0;
+            ts->p2p_seq += 1u;
+            ts->steady_sweeps += 1;
+        }
+    }
 }
 
 // landmark records of a map whose grid has just been built (first sweep on a caller-supplied map)

@@ -297,7 +297,7 @@ class Engine:
         v = (C.c_int64 * 16)()
         check(self.lib.icmslam_get_sweep_stats(self._h, v, 16), self._h)
         keys = ["newton_iters", "n_far_scans", "raw_L", "kept", "new_L", "n_ind", "lsearch", "status", "dirty_tiles", "epoch",
-                "n_tiles", "stable_ids", "k_runs_ns", "n_dirty_now", "far_count", "_"]
+                "n_tiles", "stable_ids", "k_runs_ns", "n_dirty_now", "far_count", "steady_sweeps"]
         return dict(zip(keys, [int(t) for t in v]))
 
     # -- map utilities --------------------------------------------------------------------------

@@ -688,12 +688,12 @@ def test_run_offline_one_call_matches_stepwise(tmp_path):
 # ---- the sweep's variants: scheduling and staging switches change nothing (bit for bit) ---------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("env", [{"ICMSLAM_OVERLAP": "0"}, {"ICMSLAM_GRAPH": "0"}, {"ICMSLAM_RUNS": "0"}, {"ICMSLAM_OBS_CAP": "96"},
-                                 {"ICMSLAM_BLOCKS_PER_SM": "1"}])
+                                 {"ICMSLAM_BLOCKS_PER_SM": "1"}, {"ICMSLAM_STEADY": "0"}])
 def test_sweep_variants_agree(env):
     g = golden("synth_b.npz")
     z, odo, u = g["observations"].astype(np.float64), g["odometry"], g["velocities"]
     cfgd = dict(L=int(g["cfg_L"]), cota=float(g["cfg_cota"]))
-    base = {"ICMSLAM_OVERLAP": "1", "ICMSLAM_GRAPH": "1", "ICMSLAM_RUNS": "1"}
+    base = {"ICMSLAM_OVERLAP": "1", "ICMSLAM_GRAPH": "1", "ICMSLAM_RUNS": "1", "ICMSLAM_STEADY": "1"}
     a = _chain(z, odo, u, cfgd, g["map_init"], g["x_init"], 5, dict(base))
     b = _chain(z, odo, u, cfgd, g["map_init"], g["x_init"], 5, dict(base, **env))
     for k, (ra, rb) in enumerate(zip(a, b)):
