@@ -107,16 +107,38 @@ def result_hash(x, mapa, c):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / power / throttle reasons sampled through NVML in a thread (every 5 ms) from start() to stop(): no child
+    process -- forking a process that holds gigabytes of arrays next to the timed region stalls its CUDA launches for
+    milliseconds, longer than a whole timed region at 8 GPUs.  start() is called BEFORE the warm-up sweeps and stop() after a short
+    stretch of untimed sweeps that follows the timed region, so the samples cover the same load; `samples_timed` counts those
+    that fell inside the timed region itself (mark_timed()).  Falls back to `nvidia-smi -lms` when NVML is not importable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []          # (time, sm_mhz, max_mhz, watts, reasons bitmask)
         self.p = None
+        self.h = None
+        self.stop_flag = False
+        self.t_timed = [None, None]
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.h = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                        "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -125,34 +147,69 @@ class ClockSampler:
         except Exception:
             self.p = None
 
-    def _read(self):
-        for line in self.p.stdout:
-            self.rows.append(line.strip())
+    def mark_timed(self, which):
+        self.t_timed[which] = time.perf_counter()
 
-    def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.p.terminate()
+    def _poll(self):
+        nv, h = self.nv, self.h
         try:
-            self.p.wait(timeout=2)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
         except Exception:
-            self.p.kill()
-        sm, mx, reasons, pw = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [v.strip() for v in r.split(",")]
+            mx = None
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((time.perf_counter(), float(sm), float(mx) if mx else None, pw, int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def _read(self):
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        for line in self.p.stdout:
+            f = [v.strip() for v in line.strip().split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+                rs = 0
+                for n, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                    if v.lower().startswith("active"):
+                        rs |= bits[n]
+                self.rows.append((time.perf_counter(), float(f[0]), float(f[1]), float(f[2]), rs))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
+
+    def stop(self):
+        if self.h is None and self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML and nvidia-smi unavailable"]}
+        if self.p is not None:
+            time.sleep(0.12)
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=2)
+            except Exception:
+                self.p.kill()
+        else:
+            self.stop_flag = True
+            self.th.join(timeout=1)
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        sm = [r[1] for r in self.rows]
+        mx = [r[2] for r in self.rows if r[2]]
+        pw = [r[3] for r in self.rows]
+        reasons = set()
+        for r in self.rows:
+            for bit, n in names.items():
+                if r[4] & bit:
                     reasons.add(n)
+        t0, t1 = self.t_timed
+        inside = [r for r in self.rows if t0 is not None and t1 is not None and t0 <= r[0] <= t1]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "samples_timed": len(inside),
+                "sampled_over": "warm-up + timed region + >= 0.15 s of untimed sweeps after it (NVML, 5 ms period)" if self.h is not None
+                                else "nvidia-smi -lms 20 from before the warm-up",
+                "reasons": sorted(reasons)}
 
 
 def sweep_bytes(T, n, L):
@@ -310,24 +367,30 @@ def run_gpu(args, rank, world, local_rank):
     eng.set_poses(x_init)                 # ICM.positions resident on the device
     eng.set_map(map_init)
     x_dev = None
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup + 2):      # (+2: the N > 1 arm runs two more untimed sweeps; result_sha256 is taken after the
         eng.iterate(x_dev, x0, 1, **mode)  #  same number of sweeps for every N, so the lines of a scaling run carry one hash)
     torch.cuda.synchronize()
     lc0 = eng.launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    sampler.mark_timed(0)
     ev0.record(stream)
     for _ in range(args.steps):
         eng.iterate(x_dev, x0, 1, **mode)        # steady state: one CUDA-graph replay per sweep
     ev1.record(stream)
     torch.cuda.synchronize()
+    sampler.mark_timed(1)
     ms = ev0.elapsed_time(ev1) / args.steps
-    clocks = sampler.stop()
     launches = (eng.launch_count() - lc0) // max(args.steps, 1)
     L_now = eng.landmarks_actuales
     sha = result_hash(eng.get_poses(), eng.get_map(), eng.associations())
+    t_load = time.perf_counter()          # the same load, untimed, for the clock sampler
+    while time.perf_counter() - t_load < 0.15:
+        eng.iterate(x_dev, x0, 20, **mode)
+        torch.cuda.synchronize()
+    clocks = sampler.stop()
     # kernel time of the dominant kernels, measured live with CUDA events on the handle's stream in a
     # separate short loop (reading the events synchronises, so it stays out of the timed region)
     kt, dirty = [], []
