@@ -97,6 +97,9 @@ struct icmslam_handle {
     // the steady tail (tail.cuh k_tail_steady): where every landmark was when the grid was built, a lower bound of its distance to
     // any other landmark then, the positions of its grid entries, per-block calc_cambio partials
     double2* d_gbuild = nullptr; double* d_nnd0 = nullptr; int4* d_gslots = nullptr; double* d_cpart = nullptr; int steady_enable = 1;
+    long long *d_sh_x = nullptr, *d_sh_y = nullptr; int* d_sh_k = nullptr;      // shadow of the statistics (k_tail_steady clears the live ones)
+    // inside the library's own CUDA graph the full chain is the body of an IF node (cudaGraphSetConditional in k_tail_steady)
+    bool in_own_capture = false; int use_cond = 1; cudaStream_t cap_stream = nullptr;
     int* d_blk_kept = nullptr;                 // kept landmarks per block of k_fused_means
     int* d_rawcnt = nullptr;                   // observation counts of the last fused sweep's raw map (the tail clears d_cnt)
     bool rawcnt_valid = false;
@@ -130,6 +133,8 @@ struct icmslam_handle {
     // a host-memory sweep of a map chain goes through in chunks of tiles: upload, run kernel, solve and read-back of successive
     // chunks overlap (fused_part_a, HostPipe)
     cudaStream_t h2d_stream = nullptr; cudaEvent_t ev_in[16] = {}, ev_out[16] = {}; int pipe_chunks = 8; bool pipe_events = false;
+    bool tail_wait_fork = false;
+    int pipe_tiles_min = 64;
     double* d2h_x = nullptr; int64_t d2h_ld = 0; bool d2h_done = false;   // host destination of the sweep in flight's poses (fused path)
     // time-segment partition (icmslam_set_segment): this handle owns columns [seg_lo, seg_hi) of its T columns
     int seg_lo = 0, seg_hi = 0, seg_first = 1, seg_last = 1;
@@ -232,7 +237,9 @@ extern "C" int icmslam_destroy(icmslam_handle* h)
     DFREE(h->d_st); DFREE(h->d_cub); DFREE(h->d_sort_ws);
     DFREE(h->d_exch); DFREE(h->d_fg_cnt); DFREE(h->d_fg_start); DFREE(h->d_fg_idx);
     DFREE(h->d_fg_pts); DFREE(h->d_fg_geom); DFREE(h->d_bb); DFREE(h->d_ts); DFREE(h->d_seg_rec); DFREE(h->d_seg_rec_pose);
-    DFREE(h->d_lmrec2[0]); DFREE(h->d_lmrec2[1]); DFREE(h->d_blk_kept); DFREE(h->d_rawcnt); DFREE(h->d_gbuild); DFREE(h->d_nnd0); DFREE(h->d_gslots); DFREE(h->d_cpart); DFREE(h->d_scan_state); DFREE(h->d_remap); DFREE(h->d_nnd2); DFREE(h->d_klab); DFREE(h->d_aobs); DFREE(h->d_ac);
+    DFREE(h->d_lmrec2[0]); DFREE(h->d_lmrec2[1]); DFREE(h->d_blk_kept); DFREE(h->d_rawcnt); DFREE(h->d_gbuild); DFREE(h->d_nnd0); DFREE(h->d_gslots); DFREE(h->d_cpart);
+    DFREE(h->d_sh_x); DFREE(h->d_sh_y); DFREE(h->d_sh_k);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream); DFREE(h->d_scan_state); DFREE(h->d_remap); DFREE(h->d_nnd2); DFREE(h->d_klab); DFREE(h->d_aobs); DFREE(h->d_ac);
     if (h->h_st) cudaFreeHost(h->h_st);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -354,7 +361,11 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     if (e == cudaSuccess) e = dalloc(&h->d_nnd0, L);
     if (e == cudaSuccess) e = dalloc(&h->d_gslots, L);
     if (e == cudaSuccess) e = dalloc(&h->d_cpart, (size_t)4 * (nblk((int)L, 256) + 1));
+    if (e == cudaSuccess) e = dalloc(&h->d_sh_x, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_sh_y, L);
+    if (e == cudaSuccess) e = dalloc(&h->d_sh_k, L);
     { const char* es = getenv("ICMSLAM_STEADY"); if (es) h->steady_enable = atoi(es) != 0; }
+    { const char* es = getenv("ICMSLAM_COND"); if (es) h->use_cond = atoi(es) != 0; }
     if (e == cudaSuccess) e = dalloc(&h->d_scan_state, (size_t)nblk(h->fg_cells + 1, CS_THREADS * CS_ITEMS) + 1);
     if (e == cudaSuccess) e = dalloc(&h->d_remap, L);
     if (e == cudaSuccess) e = dalloc(&h->d_klab, L);
@@ -401,7 +412,11 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
         e = cudaStreamCreateWithPriority(&h->own_stream, cudaStreamNonBlocking, hi);
         if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, lo);
     }
+    { const char* ec = getenv("ICMSLAM_PIPE_CHUNKS"); if (ec) { int c = atoi(ec); h->pipe_chunks = c < 1 ? 1 : (c > 16 ? 16 : c); } }
+    { const char* ec = getenv("ICMSLAM_PIPE_TILES"); if (ec && atoi(ec) > 0) h->pipe_tiles_min = atoi(ec); }
+
     if (e == cudaSuccess) h->stream = h->own_stream;
+    if (e == cudaSuccess) { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); e = cudaStreamCreateWithPriority(&h->cap_stream, cudaStreamNonBlocking, hi); }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_tail, cudaEventDisableTiming);
@@ -844,9 +859,12 @@ static int ensure_stats_clean(icmslam_handle* h)
 // kernel could not certify + the pose solve (forked beside the tail when `overlap`) + the scan of far-scan counts
 struct HostPipe { double* x; int64_t ld; int chunks; };      // the caller's host poses (in and out) of a chunk-pipelined sweep
 
+static bool pipe_ready(icmslam_handle* h);
+
 static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, double* kout, int64_t kld, const double* x0,
                         const icmslam_sweep_opts& o, int n_search_cap, bool overlap = false, const HostPipe* hp = nullptr)
 {
+    h->tail_wait_fork = false;
     const int T = h->T, L = h->Lcap;
     cudaStream_t s = h->stream;
     DevState* st = h->d_st;
@@ -1024,6 +1042,8 @@ static int fused_part_b(icmslam_handle* h, cudaStream_t s)
 }
 
 // part C: landmark update, Mapa.filtrar and the grid of the new map (needs the statistics of ALL segments)
+static int full_chain(icmslam_handle* h, double* dmap_out, int out_cap, int64_t out_ld, cudaStream_t s);
+
 static int fused_part_c(icmslam_handle* h, double* dmap_out, int out_cap, int64_t out_ld, cudaStream_t s)
 {
     const int L = h->Lcap;
@@ -1042,13 +1062,72 @@ static int fused_part_c(icmslam_handle* h, double* dmap_out, int out_cap, int64_
         a.raw_x = raw_x; a.raw_y = raw_y; a.rawcnt = h->d_rawcnt;
         a.map_out = dmap_out; a.cap_out = out_cap; a.ld_out = out_ld; a.counts_state = h->d_counts; a.remap = h->d_remap; a.Lcap = L;
         a.cpart = h->d_cpart;
+        a.sh_x = h->d_sh_x; a.sh_y = h->d_sh_y; a.sh_k = h->d_sh_k; a.farbits = h->d_farbits; a.n_far_words = h->n_tiles * 4;
+        a.use_cond = 0;
+        memset(&a.cond, 0, sizeof a.cond);
+        // Inside the library's own graph capture the rest of the chain becomes the body of an IF node whose condition the steady
+        // kernel sets (1 = it could not close the sweep): a steady sweep then launches nothing after it.
+        cudaGraph_t cgraph = nullptr;
+        const cudaGraphNode_t* deps = nullptr;
+        size_t ndeps = 0;
+        if (h->in_own_capture && h->use_cond && h->steady_enable && h->cap_stream) {
+            cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
+            unsigned long long cid = 0;
+            if (cudaStreamGetCaptureInfo_v2(s, &cst, &cid, &cgraph, &deps, &ndeps) == cudaSuccess && cst == cudaStreamCaptureStatusActive && cgraph &&
+                cudaGraphConditionalHandleCreate(&a.cond, cgraph, 1, cudaGraphCondAssignDefault) == cudaSuccess)
+                a.use_cond = 1;
+            else { cudaGetLastError(); cgraph = nullptr; }
+        }
         k_tail_steady<<<nblk(L, 256), 256, 0, s>>>(st, ts, a, h->p2p);
         CK(cudaGetLastError());
         h->n_launch += 1;
+        if (a.use_cond) {
+            cudaStreamCaptureStatus cst2 = cudaStreamCaptureStatusNone;
+            unsigned long long cid2 = 0;
+            CK(cudaStreamGetCaptureInfo_v2(s, &cst2, &cid2, &cgraph, &deps, &ndeps));      // (now: the steady kernel's node)
+            cudaGraphNodeParams np = {};
+            np.type = cudaGraphNodeTypeConditional;
+            np.conditional.handle = a.cond; np.conditional.type = cudaGraphCondTypeIf; np.conditional.size = 1;
+            cudaGraphNode_t cnode = nullptr;
+            CK(cudaGraphAddNode(&cnode, cgraph, deps, ndeps, &np));
+            CK(cudaStreamBeginCaptureToGraph(h->cap_stream, np.conditional.phGraph_out[0], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+            int rc = full_chain(h, dmap_out, out_cap, out_ld, h->cap_stream);
+            cudaError_t ce = cudaStreamEndCapture(h->cap_stream, nullptr);
+            if (rc) return rc;
+            CK(ce);
+            CK(cudaStreamUpdateCaptureDependencies(s, &cnode, 1, cudaStreamSetCaptureDependencies));
+            // (the body's six kernels are not counted: they launch only in a sweep the steady kernel could not close)
+        } else {
+            int rc = full_chain(h, dmap_out, out_cap, out_ld, s);
+            if (rc) return rc;
+            h->n_launch += 6;
+        }
     }
+    h->lm_cur ^= 1;
+    h->stats_clean = true;
+    h->rawcnt_valid = true;
+    h->grid_map = (out_ld == L && out_cap == L) ? dmap_out : nullptr;   // the grid now indexes the new map
+    h->hint_map = h->grid_map;                                          // ... and c[] / d_remap carry this sweep's labels into it
+    h->timed_fused = true;
+    h->lact_dirty = true;
+    if (h->join_pending) { CK(cudaStreamWaitEvent(s, h->ev_join, 0)); h->join_pending = false; }
+    return ICMSLAM_OK;
+}
+
+// the filter's full chain (tail.cuh): everything after k_tail_steady
+static int full_chain(icmslam_handle* h, double* dmap_out, int out_cap, int64_t out_ld, cudaStream_t s)
+{
+    const int L = h->Lcap;
+    DevState* st = h->d_st;
+    TailState* ts = h->d_ts;
+    const double* min_x = h->d_map_in;
+    const double* min_y = h->d_map_in + L;
+    double* raw_x = h->d_raw;
+    double* raw_y = h->d_raw + L;
+    {
     k_fused_means<<<nblk(L, 256), 256, 0, s>>>(st, h->d_fsum_x, h->d_fsum_y, h->d_cnt, min_x, min_y, 1.0 / h->fix_scale, h->dcfg.cota,
                                                h->d_newraw, raw_x, raw_y, h->d_kflag, L, h->d_blk_kept, h->d_farbits, h->n_tiles * 4, h->p2p, ts,
-                                               h->d_cnt, st);
+                                               h->d_cnt, st, h->d_sh_x, h->d_sh_y, h->d_sh_k);
     CK(cudaGetLastError());
     k_tail_compact<<<nblk(L, 256), 256, 0, s>>>(st, h->d_kflag, h->d_blk_kept, h->d_kpos, raw_x, raw_y, h->d_cnt, h->d_kx, h->d_ky, h->d_kc,
                                                 h->d_parent, h->d_bb, L, h->d_klab, h->d_rawcnt, ts);
@@ -1071,15 +1150,7 @@ static int fused_part_c(icmslam_handle* h, double* dmap_out, int out_cap, int64_
                                                h->d_lmrec2[h->lm_cur ^ 1], dmap_out, out_cap, out_ld, h->d_counts, h->thr1sq, h->thr2_hi, h->d_remap, sa);
         CK(cudaGetLastError());
     }
-    h->lm_cur ^= 1;
-    h->stats_clean = true;
-    h->rawcnt_valid = true;
-    h->n_launch += 6;
-    h->grid_map = (out_ld == L && out_cap == L) ? dmap_out : nullptr;   // the grid now indexes the new map
-    h->hint_map = h->grid_map;                                          // ... and c[] / d_remap carry this sweep's labels into it
-    h->timed_fused = true;
-    h->lact_dirty = true;
-    if (h->join_pending) { CK(cudaStreamWaitEvent(s, h->ev_join, 0)); h->join_pending = false; }
+    }
     return ICMSLAM_OK;
 }
 
@@ -1087,9 +1158,6 @@ static int fused_part_c(icmslam_handle* h, double* dmap_out, int out_cap, int64_
 static bool pipe_ready(icmslam_handle* h)
 {
     if (h->pipe_events) return true;
-    const char* ec = getenv("ICMSLAM_PIPE_CHUNKS");
-    if (ec) { int c = atoi(ec); h->pipe_chunks = c < 1 ? 1 : (c > 16 ? 16 : c); }
-    if (h->pipe_chunks <= 1) return false;
     if (cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking) != cudaSuccess) { h->pipe_chunks = 1; return false; }
     for (int i = 0; i < 16; ++i)
         if (cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming) != cudaSuccess ||
@@ -1143,6 +1211,8 @@ static int sweep_core(icmslam_handle* h, const double* xin, int64_t ldin, double
         if (h->join_pending && h->own_stream && s != h->own_stream) {
             ts_ = h->own_stream;
             CK(cudaStreamWaitEvent(ts_, h->ev_fork, 0));
+        } else if (h->tail_wait_fork) {
+            CK(cudaStreamWaitEvent(ts_, h->ev_fork, 0));      // (chunked: the last association launch is on another stream)
         }
         rc = fused_part_b(h, ts_);
         if (rc) return rc;
@@ -1286,7 +1356,7 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
     HostPipe pipe;
     const bool piped = continued && h->fused_ok && o.fused && o.schedule == ICMSLAM_SCHED_REDBLACK && o.solver == ICMSLAM_SOLVER_NEWTON &&
                        o.map_view == ICMSLAM_VIEW_PREV && o.reserved == 0 && h->use_runs && h->side_stream && h->seg_first && h->seg_last &&
-                       h->seg_lo == 0 && h->pipe_chunks > 1 && h->n_tiles >= 64 * h->pipe_chunks && pipe_ready(h);
+                       h->seg_lo == 0 && h->pipe_chunks > 1 && h->n_tiles >= h->pipe_tiles_min * h->pipe_chunks && pipe_ready(h);
     if (memspace == ICMSLAM_HOST) {
         if (!piped) CK(cudaMemcpy2DAsync(h->d_x, (size_t)T * 8, x, (size_t)ld_x * 8, (size_t)T * 8, 3, cudaMemcpyHostToDevice, s));
         h->bytes_h2d += (int64_t)3 * T * 8;
@@ -1456,8 +1526,10 @@ extern "C" int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const
                 const double* hm = h->hint_map;
                 const int lm = h->lm_cur;
                 CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+                h->in_own_capture = true;
                 int rc = sweep_core(h, src, T, dst, T, x0, o, -1, h->d_map_out, L, L);
                 cudaError_t ce = cudaStreamEndCapture(s, &graph);
+                h->in_own_capture = false;
                 h->graph_launches = (int)(h->n_launch - nl0);
                 h->n_launch = nl0;
                 h->ppar_of = pof;
@@ -1467,7 +1539,7 @@ extern "C" int icmslam_iterate(icmslam_handle* h, double* x, int64_t ld_x, const
                 if (rc || ce != cudaSuccess || !graph) {
                     if (graph) cudaGraphDestroy(graph);
                     cudaGetLastError();
-                    snprintf(h->err, sizeof h->err, "graph capture of the sweep failed (%s)", cudaGetErrorString(ce));
+                    if (!rc) snprintf(h->err, sizeof h->err, "graph capture of the sweep failed (%s)", cudaGetErrorString(ce));
                     return rc ? rc : ICMSLAM_ERR_CUDA;
                 }
                 ce = cudaGraphInstantiate(&slot->exec, graph, cudaGraphInstantiateFlagUseNodePriority);   // (nodes keep the priority of the stream they were captured on)

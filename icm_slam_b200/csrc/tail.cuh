@@ -55,6 +55,7 @@ struct TailState {
     // the steady tail (k_tail_steady): armed by a full chain that ended without a merge, for the K landmarks it left
     int steady_armed, steady_K, steady_fail, steady_ticket;
     int steady_ok;      // verdict of this sweep's k_tail_steady: 1 = the full chain has nothing to do
+    int steady_cleared; // k_tail_steady moved this sweep's statistics to their shadow (the full chain reads them there)
     int steady_sweeps;  // sweeps closed by the steady tail since the handle was created (instrumentation)
 };
 
@@ -282,15 +283,13 @@ k_fused_means(const DevState* st, long long* fsum_x, long long* fsum_y, const in
               double* newraw /* 2 x Lcap: means of this sweep's new labels, zero elsewhere; cleared here.  ALIASES fsum_x / fsum_y
                                 (old labels use a word as int64 sum, new labels as double mean: disjoint index ranges) */,
               double* __restrict__ raw_x, double* __restrict__ raw_y, int* __restrict__ flag, int Lcap, int* __restrict__ blk_kept,
-              unsigned* __restrict__ farbits, int n_far_words, const P2PDev p2p, const TailState* ts, int* cnt_w, DevState* st_w)
+              unsigned* __restrict__ farbits, int n_far_words, const P2PDev p2p, const TailState* ts, int* cnt_w, DevState* st_w,
+              const long long* __restrict__ sh_x, const long long* __restrict__ sh_y, const int* __restrict__ sh_k)
 {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ts->steady_ok) {      // the steady tail closed the sweep: only the statistics remain to be cleared for the next one
-        for (int wd = l; wd < n_far_words; wd += gridDim.x * blockDim.x) farbits[wd] = 0u;
-        if (l < Lcap) { newraw[l] = 0.0; newraw[Lcap + l] = 0.0; fsum_x[l] = 0; fsum_y[l] = 0; cnt_w[l] = 0; if (l == Lcap - 1) cnt_w[Lcap] = 0; }
-        return;
-    }
-    if (p2p.on) {      // every segment's slice of the reduced statistics is in place (and nobody reads this segment's block any more)
+    if (ts->steady_ok) return;      // the steady tail closed the sweep (and cleared the statistics for the next one)
+    const bool shadow = ts->steady_cleared != 0;      // k_tail_steady ran and said no: the (reduced) statistics are in its shadow arrays
+    if (p2p.on && !shadow) {      // every segment's slice of the reduced statistics is in place (and nobody reads this segment's block any more)
         __shared__ int s_ok;
         if (threadIdx.x == 0) {
             s_ok = p2p_wait_all32(p2p.win[p2p.rank]->rs_done, p2p.world, *(const volatile unsigned*)&ts->p2p_seq) ? 1 : 0;
@@ -305,7 +304,10 @@ k_fused_means(const DevState* st, long long* fsum_x, long long* fsum_y, const in
     const int raw_l = st->raw_l, ls = st->lsearch;
     long long wx, wy;      // the landmark's two statistics words: int64 sums (l < ls) or the fp64 mean of a new label
     int kg;
-    if (p2p.on) {          // ... from the segment that reduced them (the layout of the exchange block: x | y | counts)
+    if (shadow) {
+        wx = sh_x[l]; wy = sh_y[l]; kg = sh_k[l];
+        cnt_w[l] = kg;
+    } else if (p2p.on) {   // ... from the segment that reduced them (the layout of the exchange block: x | y | counts)
         wx = p2p_word(p2p, l); wy = p2p_word(p2p, (long long)Lcap + l);
         const long long cw = p2p_word(p2p, 2ll * Lcap + (l >> 1));
         kg = (int)((l & 1) ? (cw >> 32) : (cw & 0xffffffffll));
@@ -635,7 +637,10 @@ k_tail_nn(DevState* st, TailState* ts, double* __restrict__ kx, double* __restri
 // kernel had not.  What is computed is bit-identical either way (same expressions for the map; the radius differs, and a radius
 // only decides which exact path labels an observation).
 struct SteadyArgs {
-    const long long* fsum_x; const long long* fsum_y; const int* cnt;
+    long long* fsum_x; long long* fsum_y; int* cnt;
+    long long* sh_x; long long* sh_y; int* sh_k;      // the statistics as this kernel found them (it clears them): what the full chain reads if it must run
+    unsigned* farbits; int n_far_words;
+    cudaGraphConditionalHandle cond; int use_cond;    // inside a CUDA graph the full chain is the body of an IF node: 1 = run it
     const double* map_x; const double* map_y;
     double inv_scale, cota, dist_thr, thr1sq, thr2_hi;
     const LmRec* lmrec_old; LmRec* lmrec_new;
@@ -653,7 +658,10 @@ k_tail_steady(DevState* st, TailState* ts, const SteadyArgs a, const P2PDev p2p)
     __shared__ int s_flag;
     const int K = ts->steady_K, ls = st->lsearch;
     if (!(ts->steady_armed && ls == K && st->lact0 == K && K > 0)) {      // (the same for every block)
-        if (blockIdx.x == 0 && threadIdx.x == 0) ts->steady_ok = 0;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            ts->steady_ok = 0; ts->steady_cleared = 0;
+            if (a.use_cond) cudaGraphSetConditional(a.cond, 1u);
+        }
         return;
     }
     if (p2p.on) {      // every segment's slice of the reduced statistics is in place
@@ -669,6 +677,7 @@ k_tail_steady(DevState* st, TailState* ts, const SteadyArgs a, const P2PDev p2p)
     const double margin = FG_MARGIN * a.dist_thr;
     int fail = 0, cres = 0, cun = 0;
     double cd = 0.0;
+    for (int wd = l; wd < a.n_far_words; wd += gridDim.x * blockDim.x) a.farbits[wd] = 0u;      // (k_tail_labels was their last reader)
     if (l < a.Lcap) {
         long long wx, wy;
         int kg;
@@ -679,6 +688,11 @@ k_tail_steady(DevState* st, TailState* ts, const SteadyArgs a, const P2PDev p2p)
         } else {
             wx = a.fsum_x[l]; wy = a.fsum_y[l]; kg = a.cnt[l];
         }
+        // the statistics move to their shadow and are cleared for the next sweep here: when the verdict is "done" nothing else
+        // of the tail has to run
+        a.sh_x[l] = wx; a.sh_y[l] = wy; a.sh_k[l] = kg;
+        a.fsum_x[l] = 0; a.fsum_y[l] = 0; a.cnt[l] = 0;
+        if (l == a.Lcap - 1) a.cnt[a.Lcap] = 0;
         const int k = l < raw_l ? kg : 0;
         LmRec rec;
         rec.x = 0.0; rec.y = 0.0; rec.r2 = 0.0; rec.r = 0.0;
@@ -756,6 +770,8 @@ k_tail_steady(DevState* st, TailState* ts, const SteadyArgs a, const P2PDev p2p)
         ts->steady_ticket = 0;
         ts->steady_fail = 0;
         ts->steady_ok = ok;
+        ts->steady_cleared = 1;
+        if (a.use_cond) cudaGraphSetConditional(a.cond, ok ? 0u : 1u);
         if (ok) {
             for (int q = 1; q < (int)(blockDim.x >> 5); ++q) { red[0][0] = fmin(red[0][0], red[0][q]); red[1][0] = fmax(red[1][0], red[1][q]); red[2][0] += red[2][q]; redn[0][0] += redn[0][q]; }
             if (red[0][0] < INFINITY) { st->cambio[0] = red[0][0]; st->cambio[1] = red[1][0]; st->cambio[2] = red[2][0]; }

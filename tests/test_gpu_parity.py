@@ -802,3 +802,60 @@ def test_concatenated_batch_equals_individual_runs():
         assert dx[:2].max() <= 1e-9 and dx[2].max() <= 1e-11, (i, dx.max(axis=1))
         assert got[i][1].shape == m1.shape, (i, got[i][1].shape, m1.shape)
         assert np.abs(got[i][1] - m1).max() <= 1e-9, i
+
+
+# ---- host-memory sweeps of a map chain: the chunk-pipelined path equals the one-piece path (bit for bit) ---------------------------
+def _host_chain(z, odo, u, cfgd, map0, x_init, nsweeps, env):
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        e = _engine(_cfg(**cfgd), z, odo, u)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    x = np.ascontiguousarray(x_init.copy())
+    mapa = np.ascontiguousarray(map0.copy())
+    e.landmarks_actuales = mapa.shape[1]
+    out = []
+    for k in range(nsweeps):
+        st, Lout, mapa = e.sweep(mapa, x, odo[:, 0])
+        assert st == 0
+        out.append((x.copy(), np.array(mapa, copy=True), e.associations().copy()))
+    e.close()
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunks", ["2", "4"])
+def test_host_sweeps_in_chunks_equal_one_piece(chunks):
+    g = golden("synth_b.npz")
+    z, odo, u = g["observations"].astype(np.float64), g["odometry"], g["velocities"]
+    cfgd = dict(L=int(g["cfg_L"]), cota=float(g["cfg_cota"]))
+    a = _host_chain(z, odo, u, cfgd, g["map_init"], g["x_init"], 6, {"ICMSLAM_PIPE_CHUNKS": "1"})
+    b = _host_chain(z, odo, u, cfgd, g["map_init"], g["x_init"], 6, {"ICMSLAM_PIPE_CHUNKS": chunks, "ICMSLAM_PIPE_TILES": "1"})
+    for k, (ra, rb) in enumerate(zip(a, b)):
+        assert np.array_equal(ra[2], rb[2]), k
+        assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1]), k
+
+
+@pytest.mark.gpu
+def test_chunked_sweeps_on_a_longer_trajectory():
+    """71 tiles, two landmarks missing from the initial map (labels are created in several chunks): host sweeps in 5 chunks equal
+    the one-piece host sweeps and the device-resident sweeps bit for bit."""
+    from icm_slam_b200.synthetic import make_synthetic
+    d = make_synthetic(900, T=9000, seed=20181 + 21)
+    z, odo, u = d["observations"], d["odometry"], d["velocities"]
+    map0 = np.delete(d["map_init"], [17, 640], axis=1)
+    cfgd = dict(CONFIG_ROS, L=2 * 900 + 64, cota=20.0)
+    a = _chain(z, odo, u, cfgd, map0, d["x_init"], 6, {})
+    ha = _host_chain(z, odo, u, cfgd, map0, d["x_init"], 5, {"ICMSLAM_PIPE_CHUNKS": "1"})
+    hb = _host_chain(z, odo, u, cfgd, map0, d["x_init"], 5, {"ICMSLAM_PIPE_CHUNKS": "5", "ICMSLAM_PIPE_TILES": "8"})
+    for k, (ra, rb) in enumerate(zip(ha, hb)):
+        assert np.array_equal(ra[2], rb[2]), k
+        assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1]), k
+    for k in range(5):      # and the host path equals the device-resident one
+        assert np.array_equal(ha[k][0], a[k][0]) and np.array_equal(ha[k][1], a[k][1]), k
