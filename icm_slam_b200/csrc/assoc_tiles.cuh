@@ -144,6 +144,7 @@ k_assoc_tiles(const AssocParams p)
     const int epoch = R.ts->epoch;
     const int n_dirty = R.ts->n_dirty;
     const int d_first = R.ts->dirty_done;
+    if (blockIdx.x == 0 && tid == 0) trace_mark(R.ts, 1);
     const int q = tid >> 1, sub = tid & 1;          // scan of the tile worked by this thread pair, and the thread's half of it
 
     for (int di = d_first + blockIdx.x; di < n_dirty; di += gridDim.x) {

@@ -78,6 +78,7 @@ struct icmslam_handle {
     FarRec* d_far_list = nullptr;
     int* d_blk_prefix = nullptr;
     unsigned* d_farbits = nullptr;             // 4 words per record tile: scans that created a label this sweep
+    int trace_on = 0;                          // ICMSLAM_TRACE=1: %globaltimer marks of the sweep's kernels (icmslam_get_trace)
     int begin_L = 0;                           // landmarks_actuales bound of the sweep being issued (k_sweep_begin / sweep_begin_state)
     int n_tiles_alloc = 0;                     // tiles the per-tile arrays were allocated for
     int n_tiles = 0, n_solve_tiles = 0;        // record tiles (RT_TILE scans) / solve tiles (ST_OWN poses)
@@ -115,6 +116,8 @@ struct icmslam_handle {
     GraphSlot graphs[4];
     int use_graph = 1, graph_launches = 0;
     int runs_occ = 24;           // resident one-warp blocks per SM k_runs is compiled for (24: 80 registers; ICMSLAM_RUNS_OCC=32: 64)
+    size_t solve_pad = 0;        // unused dynamic shared memory of k_solve_tile: caps its resident blocks per SM so that the tail's kernels,
+                                 // which run beside it, find free registers at once (ICMSLAM_SOLVE_PAD, bytes)
     int solve_occ = 5;           // resident 128-thread blocks per SM k_solve_tile is compiled for (ICMSLAM_SOLVE_OCC=4|5|6)
     int use_runs = 1;            // ICMSLAM_RUNS=0: every tile goes through the association kernel every sweep (no steady-state shortcut)
     int assoc_blocks = 0;        // grid of the (persistent) association kernel
@@ -365,6 +368,7 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     if (e == cudaSuccess) e = dalloc(&h->d_sh_y, L);
     if (e == cudaSuccess) e = dalloc(&h->d_sh_k, L);
     { const char* es = getenv("ICMSLAM_STEADY"); if (es) h->steady_enable = atoi(es) != 0; }
+    { const char* es = getenv("ICMSLAM_TRACE"); if (es && atoi(es)) h->trace_on = 1; }
     { const char* es = getenv("ICMSLAM_COND"); if (es) h->use_cond = atoi(es) != 0; }
     if (e == cudaSuccess) e = dalloc(&h->d_scan_state, (size_t)nblk(h->fg_cells + 1, CS_THREADS * CS_ITEMS) + 1);
     if (e == cudaSuccess) e = dalloc(&h->d_remap, L);
@@ -380,10 +384,21 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     if (e == cudaSuccess) { const unsigned one = 1u; e = cudaMemcpy(&h->d_ts->scan_seq, &one, sizeof one, cudaMemcpyHostToDevice); }
     if (e == cudaSuccess) { const unsigned one = 1u; e = cudaMemcpy(&h->d_ts->p2p_seq, &one, sizeof one, cudaMemcpyHostToDevice); }
     if (e == cudaSuccess) { const unsigned one = 1u; e = cudaMemcpy(&h->d_ts->halo_seq, &one, sizeof one, cudaMemcpyHostToDevice); }
+    if (e == cudaSuccess && h->trace_on) { const int one = 1; e = cudaMemcpy(&h->d_ts->trace_on, &one, sizeof one, cudaMemcpyHostToDevice); }
     { const char* eg = getenv("ICMSLAM_GRAPH"); if (eg) h->use_graph = atoi(eg); }
     { const char* er = getenv("ICMSLAM_RUNS"); if (er) h->use_runs = atoi(er) != 0; }
     { const char* er = getenv("ICMSLAM_SOLVE_OCC"); if (er && (atoi(er) == 4 || atoi(er) == 6)) h->solve_occ = atoi(er); }
     { const char* er = getenv("ICMSLAM_RUNS_OCC"); if (er && atoi(er) == 32) h->runs_occ = 32; }
+    {
+        const char* ep = getenv("ICMSLAM_SOLVE_PAD");
+        if (ep && atoi(ep) > 0) h->solve_pad = (size_t)atoi(ep);
+        if (h->solve_pad > 0) {
+            cudaFuncSetAttribute(k_solve_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->solve_pad);
+            cudaFuncSetAttribute(k_solve_tile<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->solve_pad);
+            cudaFuncSetAttribute(k_solve_tile<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->solve_pad);
+            cudaGetLastError();
+        }
+    }
     if (e == cudaSuccess) {
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
@@ -913,6 +928,7 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
         P.xin = xin; P.ldin = ldin; P.xout = kout; P.ldout = kld;
         P.inc = h->d_inc; P.ldinc = T; P.u = h->d_u; P.ldu = T; P.bm = h->d_bm; P.ldbm = T; P.dyn = h->d_dyn;
         P.ppin = pp_in; P.ppout = pp_out; P.cfg = h->dcfg; P.tol = o.newton_tol; P.maxit = o.newton_maxit; P.iters = nullptr; P.tile0 = 0;
+        P.trace_row = nullptr; P.trace_seq = nullptr;
         const int C = hp->chunks, per = (h->n_tiles + C - 1) / C;
         cudaStream_t sin = h->h2d_stream, sout = h->side_stream;
         CK(cudaEventRecord(h->ev_fork, s));
@@ -946,9 +962,9 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
             if (ready > h->n_solve_tiles) ready = h->n_solve_tiles;
             if (ready > solved) {
                 P.tile0 = solved;
-                if (h->solve_occ == 4) k_solve_tile<4><<<ready - solved, ST_THREADS, 0, s>>>(P);
-                else if (h->solve_occ == 6) k_solve_tile<6><<<ready - solved, ST_THREADS, 0, s>>>(P);
-                else k_solve_tile<5><<<ready - solved, ST_THREADS, 0, s>>>(P);
+                if (h->solve_occ == 4) k_solve_tile<4><<<ready - solved, ST_THREADS, h->solve_pad, s>>>(P);
+                else if (h->solve_occ == 6) k_solve_tile<6><<<ready - solved, ST_THREADS, h->solve_pad, s>>>(P);
+                else k_solve_tile<5><<<ready - solved, ST_THREADS, h->solve_pad, s>>>(P);
                 CK(cudaGetLastError());
                 h->n_launch += 1;
                 CK(cudaEventRecord(h->ev_out[c], s));
@@ -989,6 +1005,7 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
         P.inc = h->d_inc; P.ldinc = T; P.u = h->d_u; P.ldu = T; P.bm = h->d_bm; P.ldbm = T; P.dyn = h->d_dyn;
         P.ppin = pp_in; P.ppout = pp_out; P.cfg = h->dcfg; P.tol = o.newton_tol; P.maxit = o.newton_maxit;
         P.iters = (o.reserved & 1) ? &st->newton_iters : nullptr; P.tile0 = 0;
+        P.trace_row = h->trace_on ? &h->d_ts->trace[0][0] : nullptr; P.trace_seq = h->p2p.on ? &h->d_ts->halo_seq : &h->d_ts->sweep_no;
         cudaStream_t ss = s;
         const bool fork = overlap && h->overlap_solve && !timing && h->side_stream;
         if (fork) {      // the tail does not depend on the new poses: solve beside it
@@ -996,16 +1013,17 @@ static int fused_part_a(icmslam_handle* h, const double* xin, int64_t ldin, doub
             CK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
             ss = h->side_stream;
         }
-        if (h->solve_occ == 4) k_solve_tile<4><<<h->n_solve_tiles, ST_THREADS, 0, ss>>>(P);
-        else if (h->solve_occ == 6) k_solve_tile<6><<<h->n_solve_tiles, ST_THREADS, 0, ss>>>(P);
-        else k_solve_tile<5><<<h->n_solve_tiles, ST_THREADS, 0, ss>>>(P);
+        if (h->solve_occ == 4) k_solve_tile<4><<<h->n_solve_tiles, ST_THREADS, h->solve_pad, ss>>>(P);
+        else if (h->solve_occ == 6) k_solve_tile<6><<<h->n_solve_tiles, ST_THREADS, h->solve_pad, ss>>>(P);
+        else k_solve_tile<5><<<h->n_solve_tiles, ST_THREADS, h->solve_pad, ss>>>(P);
         CK(cudaGetLastError());
         if (h->d2h_x) {      // a host-memory caller: its poses start their way back as soon as they are solved, beside the tail
             CK(cudaMemcpy2DAsync(h->d2h_x, (size_t)h->d2h_ld * 8, kout, (size_t)kld * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToHost, ss));
             h->d2h_done = true;
         }
         if (h->p2p.on) {     // the segment's boundary poses to its neighbours, theirs into the halo columns: behind the solve
-            k_p2p_halo<<<1, 32, 0, ss>>>(h->p2p, &h->d_ts->halo_seq, kout, kld, T, h->seg_lo, h->seg_hi, pp_out, st);
+            k_p2p_halo<<<1, 32, 0, ss>>>(h->p2p, &h->d_ts->halo_seq, kout, kld, T, h->seg_lo, h->seg_hi, pp_out, st,
+                                         h->trace_on ? &h->d_ts->trace[0][0] : nullptr);
             CK(cudaGetLastError());
             h->n_launch += 1;
         }
@@ -1034,7 +1052,7 @@ static int fused_part_b(icmslam_handle* h, cudaStream_t s)
         int nb = (int)((mine + 255) / 256);
         if (nb > 148 * 4) nb = 148 * 4;
         if (nb < 1) nb = 1;
-        k_p2p_reduce<<<nb, 256, 0, s>>>(h->p2p, &h->d_ts->p2p_seq, &h->d_ts->reduce_ticket, h->d_st);
+        k_p2p_reduce<<<nb, 256, 0, s>>>(h->p2p, &h->d_ts->p2p_seq, &h->d_ts->reduce_ticket, h->d_st, h->trace_on ? &h->d_ts->trace[0][0] : nullptr);
         CK(cudaGetLastError());
         h->n_launch += 1;
     }
@@ -1861,6 +1879,19 @@ extern "C" int icmslam_get_raw_map(icmslam_handle* h, double* raw_map, int32_t c
         CK(cudaMemcpyAsync(raw_counts, h->d_tmp_a, (size_t)w * 8, cudaMemcpyDefault, h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
+    return ICMSLAM_OK;
+}
+
+// instrumentation: the ring of %globaltimer marks (32 sweeps x 8 marks, nanoseconds; TailState::trace) and the sweep counters
+extern "C" int icmslam_get_trace(icmslam_handle* h, uint64_t* out256, uint32_t* counters3)
+{
+    if (!h || !out256) return ICMSLAM_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    TailState hts;
+    CK(cudaMemcpy(&hts, h->d_ts, sizeof(TailState), cudaMemcpyDeviceToHost));
+    memcpy(out256, hts.trace, sizeof hts.trace);
+    if (counters3) { counters3[0] = hts.sweep_no; counters3[1] = hts.p2p_seq; counters3[2] = hts.halo_seq; }
     return ICMSLAM_OK;
 }
 

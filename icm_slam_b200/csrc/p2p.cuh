@@ -87,9 +87,10 @@ __device__ __forceinline__ void p2p_post_ready(const P2PDev& p, unsigned seq)
 // sums add exactly; a new label's fp64 mean is non-zero on one rank only, so adding bit patterns reproduces it; two int32
 // counts per word never carry).  Then the slice is flagged on every rank.
 __global__ void __launch_bounds__(256)
-k_p2p_reduce(const P2PDev p, const unsigned* seq_ptr, int* ticket, DevState* st)
+k_p2p_reduce(const P2PDev p, const unsigned* seq_ptr, int* ticket, DevState* st, unsigned long long* trace_row /* or null */)
 {
     __shared__ int s_ok;
+    if (trace_row && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace_row[((*seq_ptr) & 31) * 8 + 3] = t; }
     const unsigned seq = *(const volatile unsigned*)seq_ptr;
     if (threadIdx.x == 0) {
         s_ok = p2p_wait_all32(p.win[p.rank]->ready, p.world, seq) ? 1 : 0;
@@ -124,8 +125,9 @@ __device__ __forceinline__ long long p2p_word(const P2PDev& p, long long w)
 
 // Halo poses of the next sweep (side stream, behind the solve; one block of 32 threads).  x = the segment's NEW poses (3 x T, ld).
 __global__ void k_p2p_halo(const P2PDev p, unsigned* hseq_ptr, double* __restrict__ x, int64_t ld, int T, int t_lo, int t_hi,
-                           double4* __restrict__ ppar, DevState* st)
+                           double4* __restrict__ ppar, DevState* st, unsigned long long* trace_row /* or null */)
 {
+    if (trace_row && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace_row[((*hseq_ptr) & 31) * 8 + 6] = t; }
     const unsigned hseq = *(volatile unsigned*)hseq_ptr;
     const int par = hseq & 1, i = threadIdx.x;
     const bool has_l = p.rank > 0, has_r = p.rank + 1 < p.world;

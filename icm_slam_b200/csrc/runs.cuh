@@ -320,7 +320,7 @@ k_runs(const RunParams p)
     __shared__ TileSmem S;
     __shared__ SliceRing ring;
     const int slice = p.slice0 + blockIdx.x, tile = slice / RT_SLICES;
-    if (slice == 0 && threadIdx.x == 0) sweep_begin_state(p.st, p.L_in);      // (nothing in this launch reads it)
+    if (slice == 0 && threadIdx.x == 0) { sweep_begin_state(p.st, p.L_in); trace_mark(p.ts, 0); }      // (nothing in this launch reads it)
     const int nslots = p.tile_nslots[tile];
     if (p.tile_epoch[tile] != p.ts->epoch) {      // no records for this label numbering: the whole tile goes to the association kernel
         if (threadIdx.x == 0 && slice == tile * RT_SLICES) { p.tile_flag[tile] = 2; p.dirty_list[atomicAdd(&p.ts->n_dirty, 1)] = tile; }

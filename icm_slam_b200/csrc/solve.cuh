@@ -203,6 +203,8 @@ struct SolveParams {
     double tol; int maxit;
     unsigned long long* iters;
     int tile0;                            // first tile of this launch
+    unsigned long long* trace_row;        // instrumentation: ring of %globaltimer marks (or null), indexed by *trace_seq
+    const unsigned* trace_seq;
 };
 
 struct __align__(16) SolveSmem {
@@ -249,6 +251,7 @@ k_solve_tile(const SolveParams p)
 {
     __shared__ SolveSmem S;
     const int tid = threadIdx.x;
+    if (p.trace_row && blockIdx.x == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.trace_row[((*p.trace_seq) & 31) * 8 + 5] = t; }
     const int tb = p.t_lo + (p.tile0 + blockIdx.x) * ST_OWN;      // t_lo is even: colours stay aligned with the global time index
     const int T = p.T;
     const int q = tid >> 1, half = tid & 1;

@@ -57,7 +57,22 @@ struct TailState {
     int steady_ok;      // verdict of this sweep's k_tail_steady: 1 = the full chain has nothing to do
     int steady_cleared; // k_tail_steady moved this sweep's statistics to their shadow (the full chain reads them there)
     int steady_sweeps;  // sweeps closed by the steady tail since the handle was created (instrumentation)
+    // instrumentation (ICMSLAM_TRACE=1): %globaltimer at the entry of the sweep's kernels, a ring over the last 32 sweeps
+    // [0] k_runs [1] k_assoc_tiles [2] k_tail_labels [3] k_p2p_reduce [4] k_tail_steady [5] k_solve_tile [6] k_p2p_halo [7] end of k_tail_steady
+    int trace_on; unsigned sweep_no;
+    unsigned long long trace[32][8];
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace_mark(TailState* ts, int slot)
+{
+    if (ts->trace_on) ts->trace[ts->sweep_no & 31][slot] = globaltimer_ns();
+}
 
 // A landmark as the fused kernel reads it by label: position and the squared radius inside which an
 // observation is PROVABLY nearest to it and inside the gate (see hint_radius2).
@@ -205,6 +220,7 @@ k_tail_labels(TailState* ts, const FarRec* __restrict__ far, const int* __restri
 {
     __shared__ int wsum[8];
     __shared__ int s_base;
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace_mark(ts, 2);
     const int nrec = ts->far_count;
     int label_base = ts->label_base;
     if (p2p.on) {
@@ -603,6 +619,7 @@ k_tail_nn(DevState* st, TailState* ts, double* __restrict__ kx, double* __restri
             ts->nn_ticket = 0;
             ts->far_count = 0; ts->n_dirty = 0;      // (consumed by k_tail_labels / the association kernel: ready for the next sweep)
             ts->p2p_seq += 1u;
+            ts->sweep_no += 1u;
             const int n_ind = atomicAdd(&ts->n_ind, 0);
             slow = (n_ind != 0 || ts->degenerate) ? 1 : 0;
             // every old label survived in place (its position among the kept landmarks is its index) and nothing was added
@@ -657,6 +674,7 @@ k_tail_steady(DevState* st, TailState* ts, const SteadyArgs a, const P2PDev p2p)
     __shared__ int redn[2][8];
     __shared__ int s_flag;
     const int K = ts->steady_K, ls = st->lsearch;
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace_mark(ts, 4);
     if (!(ts->steady_armed && ls == K && st->lact0 == K && K > 0)) {      // (the same for every block)
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             ts->steady_ok = 0; ts->steady_cleared = 0;
@@ -771,6 +789,8 @@ k_tail_steady(DevState* st, TailState* ts, const SteadyArgs a, const P2PDev p2p)
         ts->steady_fail = 0;
         ts->steady_ok = ok;
         ts->steady_cleared = 1;
+        trace_mark(ts, 7);
+        if (ok) ts->sweep_no += 1u;
         if (a.use_cond) cudaGraphSetConditional(a.cond, ok ? 0u : 1u);
         if (ok) {
             for (int q = 1; q < (int)(blockDim.x >> 5); ++q) { red[0][0] = fmin(red[0][0], red[0][q]); red[1][0] = fmax(red[1][0], red[1][q]); red[2][0] += red[2][q]; redn[0][0] += redn[0][q]; }

@@ -212,6 +212,10 @@ int icmslam_pass0(icmslam_handle* h, const double* x0, double* x, int64_t ld_x, 
  * sweep kernel), out2[1] = pose kernels (0 when fused), milliseconds.  Launch count = kernels of
  * this library enqueued since icmslam_create. */
 int icmslam_get_kernel_ms(icmslam_handle* h, double* out2);
+/* With ICMSLAM_TRACE=1 in the environment when the handle is created, the sweep's kernels leave %globaltimer marks (ns) in a ring
+ * of the last 32 sweeps x 8 marks: entry of k_runs, k_assoc_tiles, k_tail_labels, k_p2p_reduce, k_tail_steady, k_solve_tile,
+ * k_p2p_halo, and the end of k_tail_steady.  counters3 = (sweeps closed, p2p sweep number, halo sweep number). */
+int icmslam_get_trace(icmslam_handle* h, uint64_t* out256, uint32_t* counters3);
 int icmslam_get_launch_count(icmslam_handle* h, int64_t* n);
 /* bytes icmslam_sweep has copied host->device / device->host so far for HOST-memspace callers (poses, maps, status words);
  * a map the caller feeds back unchanged is not re-uploaded (sensors.py:315, `mapa_viejo = mapa_refinado`). */
