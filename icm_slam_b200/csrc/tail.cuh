@@ -252,7 +252,13 @@ k_tail_labels(TailState* ts, const FarRec* __restrict__ far, const int* __restri
             const FarRec r = far[k];
             const int ti = (r.t - t_start) / tile, lt = (r.t - t_start) % tile;
             int part = 0;
-            for (int i = threadIdx.x; i < ti; i += blockDim.x) part += tile_far_count(farbits, i);
+            for (int i0 = threadIdx.x; i0 < ti; i0 += 8 * blockDim.x) {      // (eight independent loads in flight per thread)
+                int c8[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { const int i = i0 + q * blockDim.x; c8[q] = i < ti ? tile_far_count(farbits, i) : 0; }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) part += c8[q];
+            }
             part = warp_sum_i(part);
             __syncthreads();
             if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = part;
