@@ -31,3 +31,17 @@ for _ in range(4):
 print("n %d  cold %.3f ms  steady %.4f ms/sweep (%.0f sweeps/s)  runs+assoc %.4f  solve %.4f  k_runs %.4f  dirty %d/%d  env %s" % (
     n, cold, ms, 1000 / ms, np.mean([k[0] for k in kt]), np.mean([k[1] for k in kt]), s["k_runs_ns"] * 1e-6, s["dirty_tiles"], s["n_tiles"],
     {k: v for k, v in os.environ.items() if k.startswith("ICMSLAM")}))
+if os.environ.get("ICMSLAM_TRACE"):
+    import ctypes as C
+    e.iterate(None, x0, 12)
+    torch.cuda.synchronize()
+    buf = (C.c_uint64 * 256)(); cn = (C.c_uint32 * 3)()
+    e.lib.icmslam_get_trace(e._h, buf, cn)
+    tr = np.array(buf[:], dtype=np.uint64).reshape(32, 8).astype(np.int64)
+    k_last = int(cn[0]) - 1
+    names = ["runs", "assoc", "labels", "reduce", "steady", "solve", "halo", "steady_end"]
+    for k in range(k_last - 5, k_last + 1):
+        r = tr[k & 31]
+        t0 = r[0]
+        nxt = tr[(k + 1) & 31][0] if k < k_last else 0
+        print("sweep %d: " % k + "  ".join("%s %+.1f" % (n, (v - t0) / 1e3) for n, v in zip(names, r) if n not in ("reduce", "halo")) + ("  next_runs %+.1f" % ((nxt - t0) / 1e3) if nxt else ""))

@@ -100,6 +100,8 @@ def lib():
     L.icmslam_seg_exchange.argtypes = [vp, vp, i32, i32]
     L.icmslam_seg_halo.argtypes = [vp, vp, i32, i32]
     L.icmslam_get_trace.argtypes = [vp, vp, vp]
+    L.icmslam_pose_eval.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, C.POINTER(dbl), C.POINTER(i32),
+                                    C.POINTER(SweepOpts)]
     L.icmslam_p2p_export.argtypes = [vp, vp, i64]
     L.icmslam_p2p_import.argtypes = [vp, i32, i32, vp, i64]
     L.icmslam_seg_finish.argtypes = [vp]
@@ -131,7 +133,7 @@ EXPORTS = [
     "icmslam_sweep", "icmslam_get_associations", "icmslam_get_raw_map", "icmslam_get_sweep_stats", "icmslam_filter_map",
     "icmslam_calc_cambio", "icmslam_filtrar_obs", "icmslam_set_map", "icmslam_get_map", "icmslam_iterate",
     "icmslam_get_kernel_ms", "icmslam_get_launch_count", "icmslam_get_transfer_bytes", "icmslam_set_poses", "icmslam_get_poses", "icmslam_set_segment", "icmslam_device_ptr", "icmslam_seg_begin",
-    "icmslam_seg_exchange", "icmslam_seg_halo", "icmslam_p2p_export", "icmslam_p2p_import", "icmslam_get_trace", "icmslam_seg_finish", "icmslam_fcluster", "icmslam_pass0", "icmslam_associate", "icmslam_iterate_until", "icmslam_set_counts", "icmslam_set_batch",
+    "icmslam_seg_exchange", "icmslam_seg_halo", "icmslam_p2p_export", "icmslam_p2p_import", "icmslam_get_trace", "icmslam_pose_eval", "icmslam_seg_finish", "icmslam_fcluster", "icmslam_pass0", "icmslam_associate", "icmslam_iterate_until", "icmslam_set_counts", "icmslam_set_batch",
 ]
 
 

@@ -1882,6 +1882,122 @@ extern "C" int icmslam_get_raw_map(icmslam_handle* h, double* raw_map, int32_t c
     return ICMSLAM_OK;
 }
 
+// ---- the user-configurable model functions of the reference (sensors.py:170-282: h, g, fun_xn, fun_x, minimizar_xn, minimizar_x)
+// for ONE pose, on the device, with every input given explicitly (the reference reads them from attributes of the object)
+struct PoseEvalArgs {
+    int op, n, has_next, maxit;
+    double tol;
+    const double* zd; const double* zang; const double* sx; const double* sy;   // n each (device)
+    int* iota; double* bx; double* by;                                           // n each (device scratch)
+    double xa[3], xb[3], ua[2], uc[2], o0[3], o1[3], o2[3], x[3];
+    double* out;       // [0..2] pose, [3] energy, [4] evaluations / iterations
+};
+
+__global__ void k_pose_eval(const DevCfg cfg, const PoseEvalArgs a)
+{
+    for (int i = 0; i < a.n; ++i) {      // (one thread: the reference evaluates these one pose at a time)
+        a.iota[i] = i;
+        double s, c;
+        sincos(a.zang[i], &s, &c);
+        a.bx[i] = mul_rn(a.zd[i], c); a.by[i] = mul_rn(a.zd[i], s);      // ICM_SLAM.py:52-53
+    }
+    PoseProblem P;
+    ObsArrays O;
+    SeenSrc S;
+    for (int j = 0; j < 3; ++j) { P.a[j] = a.xa[j]; P.b[j] = a.xb[j]; P.o0[j] = a.o0[j]; P.o1[j] = a.o1[j]; P.o2[j] = a.o2[j]; }
+    P.ua[0] = a.ua[0]; P.ua[1] = a.ua[1]; P.uc[0] = a.uc[0]; P.uc[1] = a.uc[1];
+    P.has_next = a.has_next; P.o = 0; P.n = a.n;
+    O.bx = a.bx; O.by = a.by; O.d = a.zd; O.beam = a.iota; O.ang = a.zang;
+    S.view = ICMSLAM_VIEW_RUNNING; S.c = nullptr; S.seen_x = a.sx; S.seen_y = a.sy; S.raw_x = S.raw_y = S.min_x = S.min_y = nullptr; S.lsearch_ptr = nullptr;
+    double x[3] = {a.x[0], a.x[1], a.x[2]};
+    double f = 0.0, cnt = 0.0;
+    if (a.op == ICMSLAM_POSE_G) {                                   // g(xt, ut), sensors.py:206-211
+        g_step(P.a, P.ua[0], P.ua[1], cfg.dt, x);
+    } else if (a.op == ICMSLAM_POSE_H) {                            // h(xt, zt) with mapa_visto, sensors.py:175-204
+        for (int i = 0; i < a.n; ++i) {
+            double s, c;
+            sincos(a.zang[i] + x[2] - ICM_HALFPI, &s, &c);
+            const double dx = (x[0] + a.zd[i] * c) - a.sx[i], dy = (x[1] + a.zd[i] * s) - a.sy[i];
+            f += dx * cfg.q1 * dx;
+            f += dy * cfg.q2 * dy;
+        }
+    } else if (a.op == ICMSLAM_POSE_ENERGY) {                       // fun_xn / fun_x at x, sensors.py:224-282
+        f = pose_energy(cfg, P, O, S, x);
+    } else {
+        double start[3];
+        if (P.has_next) { for (int j = 0; j < 3; ++j) start[j] = (P.a[j] + P.b[j]) / 2.0; }      // sensors.py:221
+        else g_step(P.a, P.ua[0], P.ua[1], cfg.dt, start);                                       // sensors.py:262
+        if (a.op == ICMSLAM_POSE_MIN_NM) {
+            cnt = (double)nelder_mead(cfg, P, O, S, start, x);
+        } else {
+            Moments M;
+            moments_zero(M);
+            for (int i = 0; i < a.n; ++i) moments_add(M, a.bx[i], a.by[i], a.sx[i] - start[0], a.sy[i] - start[1]);
+            cnt = (double)newton_moments(cfg, P, M, start[0], start[1], start[2], a.tol, a.maxit, x);
+        }
+        f = pose_energy(cfg, P, O, S, x);
+    }
+    a.out[0] = x[0]; a.out[1] = x[1]; a.out[2] = x[2]; a.out[3] = f; a.out[4] = cnt;
+}
+
+extern "C" int icmslam_pose_eval(icmslam_handle* h, int32_t model, int32_t op, int32_t n, const double* z_d, const double* z_ang,
+                                 const double* seen_x, const double* seen_y, const double* x_ant, const double* x_pos, const double* u_ant,
+                                 const double* u_act, const double* odo, int64_t ld_odo, double* x, double* f, int32_t* n_eval,
+                                 const icmslam_sweep_opts* opts)
+{
+    if (!h || n < 0 || !x || op < ICMSLAM_POSE_ENERGY || op > ICMSLAM_POSE_H) return ICMSLAM_ERR_INVALID;
+    if (model != ICMSLAM_MODEL_UNICYCLE_LASER2D) return ICMSLAM_ERR_UNSUPPORTED;      // the one model the reference ships (and the sweep kernels implement)
+    if (n > 0 && (!z_d || !z_ang || !seen_x || !seen_y)) return ICMSLAM_ERR_INVALID;
+    const bool needs_prev = op != ICMSLAM_POSE_H;
+    if (needs_prev && (!x_ant || !u_ant)) return ICMSLAM_ERR_INVALID;
+    const bool full = op == ICMSLAM_POSE_ENERGY || op == ICMSLAM_POSE_MIN_NM || op == ICMSLAM_POSE_MIN_NEWTON;
+    if (full && (!odo || ld_odo < (x_pos ? 3 : 2) || (x_pos && !u_act))) return ICMSLAM_ERR_INVALID;
+    icmslam_sweep_opts o;
+    default_opts(o, opts);
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = h->stream;
+    const size_t nn = (size_t)(n > 0 ? n : 1);
+    double* dbuf = nullptr;
+    int* ibuf = nullptr;
+    CK(cudaMalloc((void**)&dbuf, (6 * nn + 8) * sizeof(double)));
+    if (cudaMalloc((void**)&ibuf, nn * sizeof(int)) != cudaSuccess) { cudaFree(dbuf); return ICMSLAM_ERR_ALLOC; }
+    PoseEvalArgs a;
+    memset(&a, 0, sizeof a);
+    a.op = op; a.n = n; a.has_next = x_pos ? 1 : 0; a.maxit = o.newton_maxit; a.tol = o.newton_tol;
+    double* dz = dbuf; double* dang = dbuf + nn; double* dsx = dbuf + 2 * nn; double* dsy = dbuf + 3 * nn;
+    a.zd = dz; a.zang = dang; a.sx = dsx; a.sy = dsy; a.bx = dbuf + 4 * nn; a.by = dbuf + 5 * nn; a.out = dbuf + 6 * nn; a.iota = ibuf;
+    int rc = ICMSLAM_OK;
+    cudaError_t ce = cudaSuccess;
+    if (n > 0) {
+        ce = cudaMemcpyAsync(dz, z_d, (size_t)n * 8, cudaMemcpyHostToDevice, s);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(dang, z_ang, (size_t)n * 8, cudaMemcpyHostToDevice, s);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(dsx, seen_x, (size_t)n * 8, cudaMemcpyHostToDevice, s);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(dsy, seen_y, (size_t)n * 8, cudaMemcpyHostToDevice, s);
+    }
+    for (int j = 0; j < 3; ++j) {
+        a.x[j] = x[j];
+        if (x_ant) a.xa[j] = x_ant[j];
+        if (x_pos) a.xb[j] = x_pos[j];
+        if (odo) { a.o0[j] = odo[j * ld_odo + 0]; a.o1[j] = odo[j * ld_odo + 1]; if (x_pos) a.o2[j] = odo[j * ld_odo + 2]; }
+    }
+    if (u_ant) { a.ua[0] = u_ant[0]; a.ua[1] = u_ant[1]; }
+    if (u_act) { a.uc[0] = u_act[0]; a.uc[1] = u_act[1]; }
+    double out[5] = {0, 0, 0, 0, 0};
+    if (ce == cudaSuccess) {
+        k_pose_eval<<<1, 1, 0, s>>>(h->dcfg, a);
+        ce = cudaGetLastError();
+        h->n_launch += 1;
+    }
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(out, a.out, sizeof out, cudaMemcpyDeviceToHost, s);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    cudaFree(dbuf); cudaFree(ibuf);
+    if (ce != cudaSuccess) { snprintf(h->err, sizeof h->err, "icmslam_pose_eval: %s", cudaGetErrorString(ce)); return ICMSLAM_ERR_CUDA; }
+    if (op != ICMSLAM_POSE_ENERGY && op != ICMSLAM_POSE_H) { x[0] = out[0]; x[1] = out[1]; x[2] = out[2]; }
+    if (f) *f = out[3];
+    if (n_eval) *n_eval = (int32_t)out[4];
+    return rc;
+}
+
 // instrumentation: the ring of %globaltimer marks (32 sweeps x 8 marks, nanoseconds; TailState::trace) and the sweep counters
 extern "C" int icmslam_get_trace(icmslam_handle* h, uint64_t* out256, uint32_t* counters3)
 {

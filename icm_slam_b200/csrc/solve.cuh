@@ -246,7 +246,7 @@ __device__ __forceinline__ SlotMom solve_slot_load(const SolveParams& p, int tb,
 }
 
 template <int MINB>      // resident blocks per SM the kernel is compiled for (4: 117 registers, 5: 96, 6: 80)
-__global__ void __launch_bounds__(ST_THREADS, MINB)
+__global__ void __launch_bounds__(ST_THREADS, MINB * 128 / ST_THREADS)
 k_solve_tile(const SolveParams p)
 {
     __shared__ SolveSmem S;

@@ -240,6 +240,33 @@ class Engine:
                                          _ptr(mapa)[0], min(int(mapa.shape[1]), self.L), _rows(mapa, 2), _ptr(c)[0], HOST), self._h)
         return c.astype(np.int64)
 
+    POSE_OPS = {"energy": 0, "min_nm": 1, "min_newton": 2, "g": 3, "h": 4}
+
+    def pose_eval(self, op, z=None, seen=None, x=None, x_ant=None, x_pos=None, u_ant=None, u_act=None, odo=None, newton_tol=0.0,
+                  newton_maxit=0, model=0):
+        """The reference's user-configurable model functions for one pose on the device (sensors.py:170-282; icmslam_pose_eval):
+        op 'g' -> g(x_ant, u_ant); 'h' -> h(x, z) against `seen`; 'energy' -> fun_xn(x) (fun_x(x) when x_pos is None);
+        'min_nm' / 'min_newton' -> the minimiser from the reference's start point.  z: (n, 2) [range, beam angle]; seen: (n, 2) matched
+        landmark of each observation; odo: 3 x 3 (columns t-1, t, t+1) or 3 x 2.  Returns (pose (3,), energy, evaluations)."""
+        f64 = lambda a, shape=None: None if a is None else np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(shape) if shape else np.asarray(a, dtype=np.float64))
+        z = np.zeros((0, 2)) if z is None else np.asarray(z, dtype=np.float64).reshape(-1, 2)
+        seen = np.zeros((0, 2)) if seen is None else np.asarray(seen, dtype=np.float64).reshape(-1, 2)
+        n = int(z.shape[0])
+        if seen.shape[0] != n:
+            raise ValueError("one matched landmark per observation")
+        zd, za = np.ascontiguousarray(z[:, 0]), np.ascontiguousarray(z[:, 1])
+        sx, sy = np.ascontiguousarray(seen[:, 0]), np.ascontiguousarray(seen[:, 1])
+        xx = np.zeros(3) if x is None else np.array(np.asarray(x, dtype=np.float64).reshape(3), copy=True)
+        xa, xb, ua, uc = f64(x_ant, 3), f64(x_pos, 3), f64(u_ant, 2), f64(u_act, 2)
+        od = None if odo is None else np.ascontiguousarray(np.asarray(odo, dtype=np.float64))
+        p = lambda a: None if a is None or a.size == 0 else C.c_void_p(a.ctypes.data)
+        opts = SweepOpts(_lib.SCHED["redblack"], _lib.SOLVER["newton"], _lib.VIEW["prev"], int(newton_maxit), float(newton_tol), 1, 0)
+        f, nev = C.c_double(0.0), C.c_int32(0)
+        check(self.lib.icmslam_pose_eval(self._h, int(model), self.POSE_OPS[op], n, p(zd), p(za), p(sx), p(sy), p(xa), p(xb), p(ua), p(uc), p(od),
+                                         int(od.shape[1]) if od is not None else 0, C.c_void_p(xx.ctypes.data), C.byref(f), C.byref(nev),
+                                         C.byref(opts)), self._h)
+        return xx, float(f.value), int(nev.value)
+
     def set_poses(self, x):
         """ICM.positions (3 x T) -> device; iterate(None, ...) then sweeps them in place on the device."""
         if not _is_torch(x) and not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.ndim == 2 and x.strides[1] == 8):

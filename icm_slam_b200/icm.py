@@ -280,6 +280,60 @@ class ICM_SLAM:
             self.mapa_obj._attach(self._engine)
             self._attached = self.mapa_obj
 
+    # ---- the model functions the reference leaves to the user (sensors.py:170-282) ----------------------------------------
+    # Same names, same attribute protocol (self.t, self.xt, self.x_ant, self.x_pos, self.medicion_actual, self.mapa_visto, self.u,
+    # self.odometria), evaluated on the device through icmslam_pose_eval.  The sweep kernels implement exactly this model
+    # (unicycle + 2-D laser, ICMSLAM_MODEL_UNICYCLE_LASER2D); overriding these methods in a subclass does NOT change the sweep.
+    def g(self, xt, ut):
+        """sensors.py:206-211."""
+        x, _, _ = self._engine.pose_eval("g", x_ant=np.asarray(xt, dtype=np.float64).reshape(3), u_ant=np.asarray(ut, dtype=np.float64).reshape(2))
+        return x.reshape((3, 1))
+
+    def h(self, xt, zt):
+        """sensors.py:175-204: observation potential of pose xt for zt = [range, beam angle] rows against self.mapa_visto."""
+        zt = np.asarray(zt, dtype=np.float64)
+        _, f, _ = self._engine.pose_eval("h", z=zt[:, 0:2], seen=self.mapa_visto, x=np.asarray(xt, dtype=np.float64).reshape(3))
+        return f
+
+    def _pose_args(self, with_next):
+        t = int(self.t)
+        z = np.asarray(self.medicion_actual, dtype=np.float64)
+        kw = dict(z=z[:, 0:2], seen=self.mapa_visto, x_ant=np.asarray(self.xt, dtype=np.float64).reshape(3),
+                  u_ant=np.asarray(self.u)[:, t - 1])
+        if with_next:
+            kw.update(x_pos=np.asarray(self.x_pos, dtype=np.float64).reshape(3), u_act=np.asarray(self.u)[:, t],
+                      odo=np.asarray(self.odometria)[:, t - 1:t + 2])
+        else:
+            kw.update(odo=np.asarray(self.odometria)[:, t - 1:t + 1])
+        return kw
+
+    def fun_xn(self, x):
+        """sensors.py:224-255."""
+        return self._engine.pose_eval("energy", x=x, **self._pose_args(True))[1]
+
+    def fun_x(self, x):
+        """sensors.py:266-282."""
+        return self._engine.pose_eval("energy", x=x, **self._pose_args(False))[1]
+
+    def minimizar_xn(self, medicion_actual, mapa_visto, x, t):
+        """sensors.py:213-222: Nelder-Mead on fun_xn from (x_ant + x_pos) / 2."""
+        x = np.asarray(x, dtype=np.float64)
+        self.x_ant = x[:, t - 1].reshape((3, 1))
+        self.x_pos = x[:, t + 1].reshape((3, 1))
+        self.xt = x[:, t - 1].reshape((3, 1))
+        self.t = t
+        self.medicion_actual = medicion_actual
+        self.mapa_visto = mapa_visto
+        solver = "min_nm" if getattr(self.config, "solver", "newton") == "nm" else "min_newton"
+        return self._engine.pose_eval(solver, **self._pose_args(True))[0]
+
+    def minimizar_x(self, medicion_actual, mapa_visto):
+        """sensors.py:257-264: Nelder-Mead on fun_x from g(xt, u[t-1]) (self.xt and self.t as the caller left them)."""
+        self.medicion_actual = medicion_actual
+        self.mapa_visto = mapa_visto
+        solver = "min_nm" if getattr(self.config, "solver", "newton") == "nm" else "min_newton"
+        return self._engine.pose_eval(solver, **self._pose_args(False))[0]
+
     # ---- the sweep ------------------------------------------------------------------------------
     def iterations_process_offline(self, mapa_viejo, x):
         """sensors.py:125-168: one ICM sweep.  `x` (3 x T) is updated IN PLACE and returned;

@@ -207,6 +207,20 @@ int icmslam_fcluster(const double* px, const double* py, int32_t n, double t, in
 int icmslam_pass0(icmslam_handle* h, const double* x0, double* x, int64_t ld_x, double* map_out, int32_t cap_out,
                   int64_t ld_map_out, int32_t* L_out, int32_t memspace);
 
+/* -- the model functions the reference leaves to the user (sensors.py:170-282) for ONE pose, on the device: `op` selects
+ * g(x_ant, u_ant) (:206-211), h(x, z) against the matched landmarks `seen` (:175-204), the energy fun_xn / fun_x at x (:224-282;
+ * fun_x when x_pos is NULL), or its minimiser as minimizar_xn / minimizar_x find it (Nelder-Mead from the reference's start
+ * point, :213-222 / :257-264) or exactly (Newton).  z = (range, beam angle) pairs, odo = 3 x 3 (columns t-1, t, t+1; 3 x 2 without
+ * x_pos), all HOST pointers.  x: evaluation point in (ENERGY, H), result out (G, MIN_*); *f the energy there; *n_eval the
+ * evaluations (NM) or iterations (Newton).  `model` names the motion / measurement model: ICMSLAM_MODEL_UNICYCLE_LASER2D is the
+ * reference's (and the only one the sweep kernels implement); anything else returns ICMSLAM_ERR_UNSUPPORTED. */
+enum { ICMSLAM_MODEL_UNICYCLE_LASER2D = 0 };
+enum { ICMSLAM_POSE_ENERGY = 0, ICMSLAM_POSE_MIN_NM = 1, ICMSLAM_POSE_MIN_NEWTON = 2, ICMSLAM_POSE_G = 3, ICMSLAM_POSE_H = 4 };
+int icmslam_pose_eval(icmslam_handle* h, int32_t model, int32_t op, int32_t n, const double* z_d, const double* z_ang,
+                      const double* seen_x, const double* seen_y, const double* x_ant, const double* x_pos, const double* u_ant,
+                      const double* u_act, const double* odo, int64_t ld_odo, double* x, double* f, int32_t* n_eval,
+                      const icmslam_sweep_opts* opts);
+
 /* -- instrumentation (no reference counterpart).  Kernel time of the last sweep run with
  * opts.reserved & 2, from CUDA events on the handle's stream: out2[0] = association (or the fused
  * sweep kernel), out2[1] = pose kernels (0 when fused), milliseconds.  Launch count = kernels of

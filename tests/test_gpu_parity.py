@@ -859,3 +859,61 @@ def test_chunked_sweeps_on_a_longer_trajectory():
         assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1]), k
     for k in range(5):      # and the host path equals the device-resident one
         assert np.array_equal(ha[k][0], a[k][0]) and np.array_equal(ha[k][1], a[k][1]), k
+
+
+# ---- the reference's user-configurable model functions, one pose at a time --------------------------------------
+@pytest.mark.gpu
+def test_model_hooks_match_the_oracle():
+    from oracle import oracle as orc
+    from icm_slam_b200.icm import ICM_SLAM
+    g = golden("c1_ref.npz")
+    z, odo, u = c1_inputs()
+    cfg = _cfg(**CONFIG_ROS)
+    _, ocfg, ext = _oracle(CONFIG_ROS, z, odo, u)
+    icm = ICM_SLAM(cfg, x0=odo[:, 0])
+    icm.mediciones, icm.odometria, icm.u = z, odo, u
+    x = np.ascontiguousarray(g["p0_x"].copy())
+    mapa = g["p0_map"]
+    rng = np.random.default_rng(5)
+    e = icm.engine
+    T = z.shape[1]
+    checked = 0
+    for t in list(rng.integers(1, T - 1, 12)) + [T - 1]:
+        o0, o1 = int(ext["off"][t]), int(ext["off"][t + 1])
+        if o1 == o0:
+            continue
+        d, ang = ext["d"][o0:o1], ext["beam"][o0:o1] * np.pi / 180.0
+        zt = np.stack([d, ang], axis=1)
+        seen = mapa[:, rng.integers(0, mapa.shape[1], o1 - o0)].T.copy()       # any matched landmark per observation
+        xq = x[:, t] + rng.normal(0.0, 0.01, 3)
+        icm.t, icm.xt, icm.medicion_actual, icm.mapa_visto = int(t), x[:, t - 1], zt, seen
+        # g and h
+        assert np.allclose(icm.g(x[:, t - 1], u[:, t - 1]).reshape(3),
+                           x[:, t - 1] + cfg.deltat * np.array([np.cos(x[2, t - 1]) * u[0, t - 1], np.sin(x[2, t - 1]) * u[0, t - 1], u[1, t - 1]]), rtol=0, atol=1e-15)
+        alfa = ang + xq[2] - np.pi / 2.0
+        dist = np.stack([xq[0] + d * np.cos(alfa), xq[1] + d * np.sin(alfa)], axis=1) - seen
+        h_np = float(np.sum(np.matmul(dist, cfg.Q) * dist))
+        assert abs(icm.h(xq, zt) - h_np) <= 1e-12 * max(1.0, abs(h_np))
+        if t + 1 < T:
+            icm.x_pos = x[:, t + 1]
+            f_o = orc.fun_xn(ocfg, xq, x[:, t - 1], x[:, t + 1], u[:, t - 1], u[:, t], odo[:, t - 1:t + 2], d, ang, seen[:, 0], seen[:, 1])
+            assert abs(icm.fun_xn(xq) - f_o) <= 1e-12 * max(1.0, abs(f_o)), t
+            for solver, op in (("nm", "min_nm"), ("newton", "min_newton")):
+                xo, nev = orc.solve_pose(ocfg, solver, x[:, t - 1], x[:, t + 1], u[:, t - 1], u[:, t], odo[:, t - 1:t + 2], d, ang, seen[:, 0], seen[:, 1])
+                xg, fg, ng = e.pose_eval(op, z=zt, seen=seen, x_ant=x[:, t - 1], x_pos=x[:, t + 1], u_ant=u[:, t - 1], u_act=u[:, t],
+                                         odo=odo[:, t - 1:t + 2], newton_tol=1e-14, newton_maxit=50)
+                dd = np.abs(xg - xo)
+                assert dd[:2].max() <= 1e-6 and dd[2] <= 1e-8, (t, solver, dd)
+                if solver == "nm":
+                    assert ng == nev, (t, ng, nev)
+        else:
+            f_o = orc.fun_x(ocfg, xq, x[:, t - 1], u[:, t - 1], odo[:, t - 1:t + 1], d, ang, seen[:, 0], seen[:, 1])
+            assert abs(icm.fun_x(xq) - f_o) <= 1e-12 * max(1.0, abs(f_o))
+            xo, nev = orc.solve_pose(ocfg, "nm", x[:, t - 1], None, u[:, t - 1], None, odo[:, t - 1:t + 1], d, ang, seen[:, 0], seen[:, 1])
+            xg, fg, ng = e.pose_eval("min_nm", z=zt, seen=seen, x_ant=x[:, t - 1], u_ant=u[:, t - 1], odo=odo[:, t - 1:t + 1])
+            dd = np.abs(xg - xo)
+            assert dd[:2].max() <= 1e-6 and dd[2] <= 1e-8 and ng == nev, (t, dd, ng, nev)
+        checked += 1
+    assert checked >= 8
+    with pytest.raises(Exception):
+        e.pose_eval("g", x_ant=np.zeros(3), u_ant=np.zeros(2), model=1)       # only the reference's model exists
