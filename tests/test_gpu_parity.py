@@ -917,3 +917,36 @@ def test_model_hooks_match_the_oracle():
     assert checked >= 8
     with pytest.raises(Exception):
         e.pose_eval("g", x_ant=np.zeros(3), u_ant=np.zeros(2), model=1)       # only the reference's model exists
+
+
+# ---- ROS ingestion end to end: a log replayed through the in-process publisher gives what the offline path gives
+@pytest.mark.gpu
+def test_online_ingestion_equals_offline_run():
+    from icm_slam_b200 import ros_ingest as ri
+    from icm_slam_b200.icm import ICM_SLAM, Mapa
+    z, odo, u = c1_inputs()
+    T = 400
+    z, odo, u = z[:, :T], odo[:, :T], u[:, :T]
+    cfgd = dict(CONFIG_ROS, N=3, topic_laser="/scan", topic_laser_msg="sensor_msgs/LaserScan", topic_odometry="/odom",
+                topic_odometry_msg="nav_msgs/Odometry")
+    cfg = _cfg(**cfgd)
+    raw = np.where(z >= cfg.rango_laser_max, np.nan, z - cfg.radio)          # ranges as a lidar reports them (no return: NaN)
+    online = ri.OnlineICM(cfg)
+    client = ri.FakeRos()
+
+    def pump(node):
+        ri.publish_log(client, cfg, raw, odo, u)
+        client.service("/icm_slam/iterative_flag").call({"data": True})       # "start iterating"
+        return False
+
+    mapa0, x0s = online.inicializar_online(client, pump)
+    assert online.iterations_flag and online.mediciones.shape == (180, T)
+    m_on, x_on = online.iterar(x0s.copy())
+    # the same arrays through the offline surface
+    off = ICM_SLAM(cfg, x0=np.array([online.odometria[:, 0]]).T)
+    off.load_data(Mapa(cfg), online.mediciones.copy(), online.u.copy(), online.odometria.copy())
+    mapa1, x1 = off.inicializar()
+    assert np.array_equal(mapa0, mapa1) and np.array_equal(x0s, x1)
+    m_off, x_off = off.iterar(x1.copy())
+    assert np.array_equal(m_on, m_off) and np.array_equal(x_on, x_off)
+    assert m_on.shape[1] >= 3
