@@ -283,7 +283,7 @@ class SegmentedSolver:
             self._allrec = torch.empty((self.world, SEG_REC), dtype=torch.float64, device="cuda:%d" % self.device)
             self._allpose = torch.empty((self.world, SEG_REC), dtype=torch.float64, device="cuda:%d" % self.device)
             self._side = torch.cuda.ExternalStream(self._ptr(PTR_SIDE_STREAM)[0], device=self.device)
-            if self.split_exchange and self.world > 1 and self.halo_group is None:
+            if self.exchange == "nccl" and self.split_exchange and self.world > 1 and self.halo_group is None:
                 import torch.distributed as dist
                 self.halo_group = dist.new_group(ranks=list(range(self.world))) if self.group is None else None
                 self._own_halo_group = self.halo_group is not None
@@ -297,23 +297,55 @@ class SegmentedSolver:
             self.engine.set_stream(self._stream.cuda_stream)
         if self.exchange == "p2p" and not self._p2p_on:
             self._enable_p2p()
+            if self.exchange == "nccl" and self.split_exchange and self.halo_group is None and self.world > 1:
+                import torch.distributed as dist      # (the fall-back needs its second communicator after all)
+                self.halo_group = dist.new_group(ranks=list(range(self.world))) if self.group is None else None
+                self._own_halo_group = self.halo_group is not None
+                if self.halo_group is None:
+                    self.split_exchange = False
 
     def _enable_p2p(self):
-        """Collective: every rank exports its three IPC handles, all ranks gather them and open each other's buffers."""
+        """Collective: every rank exports its three IPC handles, all ranks gather them and open each other's buffers.  If any
+        rank cannot (no peer access, IPC not permitted in this container, ...) ALL ranks fall back to the NCCL exchange."""
         import torch
         import torch.distributed as dist
         from ._lib import check
         e = self.engine
         nbytes = 192
-        buf = C.create_string_buffer(nbytes)
-        check(e.lib.icmslam_p2p_export(e._h, buf, nbytes), e._h)
         dev = "cuda:%d" % self.device
+        buf = C.create_string_buffer(nbytes)
+        ok, why = 1, ""
+        try:
+            check(e.lib.icmslam_p2p_export(e._h, buf, nbytes), e._h)
+            import os
+            if os.environ.get("ICMSLAM_P2P_FAIL") == str(self.rank):      # (test hook: this rank pretends it cannot export)
+                raise RuntimeError("peer memory switched off for this rank (ICMSLAM_P2P_FAIL)")
+        except Exception as ex:      # noqa: BLE001
+            ok, why = 0, str(ex)
         mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(dev)
         allh = torch.empty(self.world * nbytes, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(allh, mine, group=self.group)
         raw = allh.cpu().numpy().tobytes()
-        check(e.lib.icmslam_p2p_import(e._h, self.rank, self.world, raw, len(raw)), e._h)
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 1:
+            try:
+                check(e.lib.icmslam_p2p_import(e._h, self.rank, self.world, raw, len(raw)), e._h)
+            except Exception as ex:      # noqa: BLE001
+                ok, why = 0, str(ex)
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
         torch.cuda.synchronize(self.device)
+        if int(flag.item()) != 1:
+            # back to collectives on every rank (a rank that did import switches its peer tables off again)
+            own = raw[self.rank * nbytes:(self.rank + 1) * nbytes]
+            try:
+                e.lib.icmslam_p2p_import(e._h, 0, 1, own, len(own))
+            except Exception:            # noqa: BLE001
+                pass
+            self.exchange = "nccl"
+            self.p2p_fallback_reason = why or "another rank could not open the peer buffers"
+            return
         dist.barrier(group=self.group)         # every window is mapped everywhere before the first flag is written
         self._p2p_on = True
 

@@ -44,8 +44,10 @@ def main():
     cfg = ConfigICM.from_values(**dict(CONFIG_ROS, L=2 * L_true + 64, cota=20.0))
     res = {}
     sols = []
-    for exchange in ("p2p", "nccl"):         # the library's peer-memory kernels / NCCL collectives between the segment calls
-        sol = SegmentedSolver(cfg, rank, world, device=local, exchange=exchange)
+    for exchange in ("p2p", "nccl", "fallback"):   # the library's peer-memory kernels / NCCL collectives between the segment calls /
+        if exchange == "fallback":                 # ... and p2p requested but one rank cannot: every rank must end up on NCCL
+            os.environ["ICMSLAM_P2P_FAIL"] = "1"
+        sol = SegmentedSolver(cfg, rank, world, device=local, exchange="p2p" if exchange == "fallback" else exchange)
         sol.load(d["observations"], d["odometry"], d["velocities"], precondition=True)
         sol.set_map(map0)
         sol.set_poses(d["x_init"])
@@ -55,6 +57,9 @@ def main():
         x_seg = sol.gather_poses()
         m_seg = sol.get_map()
         res["segmented_" + exchange] = digest(x_seg, m_seg)
+        if exchange == "fallback":
+            os.environ.pop("ICMSLAM_P2P_FAIL", None)
+            res["fallback_exchange"] = sol.exchange
         sols.append(sol)
     res["segmented"] = res["segmented_p2p"]
     if rank == 0:

@@ -179,3 +179,4 @@ def test_two_nccl_ranks_equal_the_single_engine_bit_for_bit(tmp_path):
     res = json.loads(out.read_text())
     assert res["segmented_p2p"] == res["single"], res       # the library's exchange over peer memory (csrc/p2p.cuh)
     assert res["segmented_nccl"] == res["single"], res      # NCCL collectives between the segment calls
+    assert res["fallback_exchange"] == "nccl" and res["segmented_fallback"] == res["single"], res   # one rank without peer memory
