@@ -131,7 +131,8 @@ struct icmslam_handle {
     int obs_cap = 0, max_tile_obs = 0;
     // host-memspace sweeps: copy of the map returned by the last one (a caller that feeds it back continues the device-side
     // map chain: grid, hints and labels stay valid, sensors.py:315 `mapa_viejo = mapa_refinado`)
-    std::vector<double> last_map_host; int last_map_L = -1;
+    double* h_map_pin = nullptr;      // pinned 2 x Lcap: the map the last host-memory sweep returned (read back in one async copy; what
+    int last_map_L = -1;              // the next call's mapa_viejo is compared with to continue the device-side map chain)
     int64_t bytes_h2d = 0, bytes_d2h = 0;      // copied by host-memspace sweeps (icmslam_get_transfer_bytes)
     // a host-memory sweep of a map chain goes through in chunks of tiles: upload, run kernel, solve and read-back of successive
     // chunks overlap (fused_part_a, HostPipe)
@@ -250,6 +251,7 @@ extern "C" int icmslam_destroy(icmslam_handle* h)
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_tail) cudaEventDestroy(h->ev_tail);
+    if (h->h_map_pin) cudaFreeHost(h->h_map_pin);
     for (void*& q : h->p2p_opened) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
     DFREE(h->d_win); DFREE(h->d_res); DFREE(h->d_p2p_ptrs);
     if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
@@ -1363,8 +1365,8 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
     int64_t ldin = ld_x, ldout = ld_x;
     bool continued = false;
     if (memspace == ICMSLAM_HOST && L_in > 0 && L_in == h->last_map_L && h->grid_map != nullptr && h->grid_map == h->d_map_in &&
-        memcmp(map_in, h->last_map_host.data(), (size_t)L_in * 8) == 0 &&
-        memcmp(map_in + ld_map_in, h->last_map_host.data() + L_in, (size_t)L_in * 8) == 0) {
+        h->h_map_pin && memcmp(map_in, h->h_map_pin, (size_t)L_in * 8) == 0 &&
+        memcmp(map_in + ld_map_in, h->h_map_pin + L, (size_t)L_in * 8) == 0) {
         // the caller hands back the map the previous sweep returned: it is already on the device (the current map buffer),
         // with its grid, hints and run records
         continued = true;
@@ -1404,6 +1406,13 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
     if (memspace == ICMSLAM_HOST) {
         if (!h->d2h_done) CK(cudaMemcpy2DAsync(x, (size_t)ld_x * 8, xout, (size_t)T * 8, (size_t)T * 8, 3, cudaMemcpyDeviceToHost, s));
         h->bytes_d2h += (int64_t)3 * T * 8 + (int64_t)sizeof(DevState);
+        // the whole map buffer comes back with the state in ONE asynchronous copy into pinned memory (its width is only known on
+        // the device until then); the caller's array -- usually pageable -- is then filled by a host copy
+        if (map_out && !h->h_map_pin) CK(cudaMallocHost((void**)&h->h_map_pin, (size_t)2 * L * sizeof(double)));
+        if (map_out) {
+            CK(cudaMemcpyAsync(h->h_map_pin, h->d_map_in, (size_t)2 * L * sizeof(double), cudaMemcpyDeviceToHost, s));
+            h->bytes_d2h += (int64_t)2 * L * 8;       // (what actually crosses the bus: the whole buffer, not only the live columns)
+        }
         rc = sync_state(h);
         if (rc) return rc;
         int status = status_from_state(h->h_st);
@@ -1412,15 +1421,9 @@ extern "C" int icmslam_sweep(icmslam_handle* h, const double* map_in, int32_t L_
         if (map_out) {
             int w = newL < cap_out ? newL : cap_out;
             if (w > 0) {
-                CK(cudaMemcpy2DAsync(map_out, (size_t)ld_map_out * 8, h->d_map_in, (size_t)L * 8, (size_t)w * 8, 2, cudaMemcpyDeviceToHost, s));
-                CK(cudaStreamSynchronize(s));
-                h->bytes_d2h += (int64_t)2 * w * 8;
-                if (w == newL) {       // remember what the caller received (see `continued` above)
-                    h->last_map_host.resize((size_t)2 * newL);
-                    memcpy(h->last_map_host.data(), map_out, (size_t)newL * 8);
-                    memcpy(h->last_map_host.data() + newL, map_out + ld_map_out, (size_t)newL * 8);
-                    h->last_map_L = newL;
-                }
+                memcpy(map_out, h->h_map_pin, (size_t)w * 8);
+                memcpy(map_out + ld_map_out, h->h_map_pin + L, (size_t)w * 8);
+                if (w == newL) h->last_map_L = newL;       // the caller received all of it (see `continued` above)
             }
         }
         if (L_out) *L_out = newL;
