@@ -110,7 +110,6 @@ struct icmslam_handle {
     int* d_klab = nullptr;              // raw label of each kept landmark (fast tail)
     int traj_T = 0, traj_K = 0; double* d_x0s = nullptr;   // batch of independent trajectories laid end to end (icmslam_set_batch)
     double* d_aobs = nullptr; int* d_ac = nullptr;   // icmslam_associate: one scan's observations (2 x ASSOC_MAX_OBS) and labels
-    double* d_nnd2 = nullptr;
     double thr1sq = 0.0;
     struct GraphSlot { cudaGraphExec_t exec = nullptr; const double* src = nullptr; const double* map_in = nullptr; double x0[3] = {0, 0, 0}; double tol = 0; int maxit = 0; int lm = 0; };
     GraphSlot graphs[4];
@@ -243,7 +242,8 @@ extern "C" int icmslam_destroy(icmslam_handle* h)
     DFREE(h->d_fg_pts); DFREE(h->d_fg_geom); DFREE(h->d_bb); DFREE(h->d_ts); DFREE(h->d_seg_rec); DFREE(h->d_seg_rec_pose);
     DFREE(h->d_lmrec2[0]); DFREE(h->d_lmrec2[1]); DFREE(h->d_blk_kept); DFREE(h->d_rawcnt); DFREE(h->d_gbuild); DFREE(h->d_nnd0); DFREE(h->d_gslots); DFREE(h->d_cpart);
     DFREE(h->d_sh_x); DFREE(h->d_sh_y); DFREE(h->d_sh_k);
-    if (h->cap_stream) cudaStreamDestroy(h->cap_stream); DFREE(h->d_scan_state); DFREE(h->d_remap); DFREE(h->d_nnd2); DFREE(h->d_klab); DFREE(h->d_aobs); DFREE(h->d_ac);
+    DFREE(h->d_scan_state); DFREE(h->d_remap); DFREE(h->d_klab); DFREE(h->d_aobs); DFREE(h->d_ac);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     if (h->h_st) cudaFreeHost(h->h_st);
     for (int i = 0; i < 4; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -377,7 +377,6 @@ extern "C" int icmslam_create(const icmslam_config* cfg, icmslam_handle** out)
     if (e == cudaSuccess) e = dalloc(&h->d_klab, L);
     if (e == cudaSuccess) e = dalloc(&h->d_aobs, (size_t)2 * ASSOC_MAX_OBS);
     if (e == cudaSuccess) e = dalloc(&h->d_ac, (size_t)ASSOC_MAX_OBS);
-    if (e == cudaSuccess) e = dalloc(&h->d_nnd2, L);
     if (e == cudaSuccess) e = cudaMemset(h->d_lmrec2[0], 0, L * sizeof(LmRec));
     if (e == cudaSuccess) e = cudaMemset(h->d_lmrec2[1], 0, L * sizeof(LmRec));
     if (e == cudaSuccess) e = cudaMemset(h->d_scan_state, 0, ((size_t)nblk(h->fg_cells + 1, CS_THREADS * CS_ITEMS) + 1) * sizeof(unsigned long long));
