@@ -31,7 +31,7 @@ struct icmslam_handle {
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;   // created with the handle; replaced by icmslam_set_stream
     // the pose solve does not feed the tail (labels, landmark update, Mapa.filtrar): on one GPU the two run concurrently,
-    // the solve forked onto a side stream after k_sweep_fused and joined at the end of the sweep (also inside the CUDA graph)
+    // the solve forked onto a side stream after the association kernel and joined at the end of the sweep (also inside the CUDA graph)
     cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_tail = nullptr; bool join_pending = false; int overlap_solve = 1;
     char err[512];
     // dataset

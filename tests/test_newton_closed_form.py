@@ -1,4 +1,4 @@
-"""CPU pin of the math of `newton_trig` / `k_solve_colour` (icm_slam_b200/csrc/fused.cuh): the reduced 1-D problem in theta as a
+"""CPU pin of the math of `newton_trig` / `k_solve_tile` (icm_slam_b200/csrc/solve.cuh): the reduced 1-D problem in theta as a
 trigonometric polynomial whose four coefficients are formed once from the moment sums.
 
 `_coefficients` below is a line-by-line numpy mirror of the device code (role 0 = x rows, role 1 = y rows).  It is held to the
