@@ -834,7 +834,8 @@ static int build_fgrid(icmslam_handle* h, const double* px, const double* py, co
     return ICMSLAM_OK;
 }
 
-__global__ void k_epoch_bump(TailState* ts) { ts->epoch += 1; }
+// (a map from outside: run records are void, and so is what the steady tail remembers of the grid the previous chain built)
+__global__ void k_epoch_bump(TailState* ts) { ts->epoch += 1; ts->steady_armed = 0; }
 __global__ void k_note_dirty(DevState* st, const TailState* ts) { st->dirty_tiles = ts->n_dirty; }
 
 static TrajLayout traj_layout(const icmslam_handle* h, const double* x0)

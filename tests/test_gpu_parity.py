@@ -950,3 +950,32 @@ def test_online_ingestion_equals_offline_run():
     m_off, x_off = off.iterar(x1.copy())
     assert np.array_equal(m_on, m_off) and np.array_equal(x_on, x_off)
     assert m_on.shape[1] >= 3
+
+
+@pytest.mark.gpu
+def test_a_map_set_again_starts_a_clean_chain():
+    """A handle that has run a chain (steady tail armed, grid bookkeeping of ITS last build) and is then given a map with the same
+    number of landmarks must behave like a fresh handle given that map."""
+    g = golden("synth_b.npz")
+    z, odo, u = g["observations"].astype(np.float64), g["odometry"], g["velocities"]
+    cfgd = dict(L=int(g["cfg_L"]), cota=float(g["cfg_cota"]))
+    e1 = _engine(_cfg(**cfgd), z, odo, u)
+    e1.set_map(g["map_init"])
+    e1.set_poses(np.ascontiguousarray(g["x_init"].copy()))
+    e1.iterate(None, odo[:, 0], 8)
+    m8, x8 = e1.get_map().copy(), e1.get_poses().copy()
+    assert e1.sweep_stats()["steady_sweeps"] > 0          # the chain did reach the steady tail
+    shift = np.zeros_like(m8)
+    shift[0] += 0.01                                      # the same landmarks, moved within the grid's margin
+    for mapa in (m8, m8 + shift):
+        e1.set_map(mapa)
+        e1.set_poses(x8.copy())
+        e1.iterate(None, odo[:, 0], 4)
+        e2 = _engine(_cfg(**cfgd), z, odo, u)
+        e2.set_map(mapa)
+        e2.set_poses(x8.copy())
+        e2.iterate(None, odo[:, 0], 4)
+        assert np.array_equal(e1.associations(), e2.associations())
+        assert np.array_equal(e1.get_poses(), e2.get_poses()) and np.array_equal(e1.get_map(), e2.get_map())
+        e2.close()
+    e1.close()
